@@ -1,0 +1,221 @@
+"""Reductions, tempering search and resampling -- NumPy restatement.  TEST INFRASTRUCTURE.
+
+Follows (all under /root/reference/mocat/src/):
+  metrics.py:69-78          log_ess_log_weight / ess_log_weight
+  utils.py:205-237          bisect  (regula falsi)
+  transport/smc.py:303-326  MetropolisedSMCSampler.log_ess / next_temperature_adaptive
+  transport/smc.py:61-71    SMCSampler.resample          (random.categorical + gather)
+  ssm/filtering.py:196-199  _resample
+  abc/smc.py:163-166        next_threshold_adaptive      (jnp.quantile, linear interpolation)
+  abc/smc.py:94-98          adapt_stepsize_scaled_diag_cov (vmap(jnp.cov))
+and jax.scipy.special.logsumexp (third party, unpinned; semantics restated from its
+published source: m = max; m = 0 if not finite; log(sum(b*exp(a-m))) + m).
+"""
+import numpy as np
+
+Q_BITS = 52                      # weights are quantised to multiples of 2^-52 before the fp64 cumsum
+Q_SCALE = float(2 ** Q_BITS)
+Q_INV = float(2.0 ** -Q_BITS)
+
+
+# ----------------------------------------------------------------------------- LSE / ESS
+def logsumexp(a, b=None):
+    """jax.scipy.special.logsumexp semantics (call sites smc.py:160,214-215,288; metrics.py:74)."""
+    a = np.asarray(a, dtype=np.float64)
+    if a.size == 0:
+        return -np.inf
+    m = np.max(a)
+    if not np.isfinite(m):
+        m = 0.0
+    with np.errstate(divide='ignore', invalid='ignore'):
+        e = np.exp(a - m)
+        s = np.sum(e if b is None else b * e)
+        return float(np.log(s) + m)
+
+
+def log_ess_log_weight(lw):
+    """metrics.py:69-74: 2*LSE(w) - LSE(2w).  All -inf -> NaN (as in the reference)."""
+    lw = np.asarray(lw, dtype=np.float64)
+    with np.errstate(invalid='ignore'):
+        return 2.0 * logsumexp(lw) - logsumexp(2.0 * lw)
+
+
+def ess_log_weight(lw):
+    """metrics.py:77-78."""
+    return float(np.exp(log_ess_log_weight(lw)))
+
+
+def lse_ess(lw):
+    """(lse, lse2, log_ess) -- what mb_lse_ess returns."""
+    lw = np.asarray(lw, dtype=np.float64)
+    l1 = logsumexp(lw)
+    l2 = logsumexp(2.0 * lw)
+    with np.errstate(invalid='ignore'):
+        return l1, l2, 2.0 * l1 - l2
+
+
+def lse_ess_tempered(lw, lik, dbeta):
+    """log-ESS of  lw - dbeta*lik   (smc.py:303-309)."""
+    return lse_ess(np.asarray(lw, np.float64) - float(dbeta) * np.asarray(lik, np.float64))
+
+
+# ----------------------------------------------------------------------------- regula falsi
+def bisect(fun, bounds, max_iter=1000, tol=1e-5):
+    """utils.py:205-237 verbatim logic (the function is a secant/regula-falsi search).
+
+    returns (bounds[2], evals[2], iters)."""
+    b = [float(bounds[0]), float(bounds[1])]
+    e = [float(fun(b[0])), float(fun(b[1]))]
+    increasing = e[1] > e[0]                                   # :212
+    it = 0
+    while not (min(abs(e[0]), abs(e[1])) < tol or it >= max_iter
+               or (e[0] < 0 and e[1] < 0) or (e[0] > 0 and e[1] > 0)):   # :214-218
+        new_pos = b[0] - e[0] * (b[1] - b[0]) / (e[1] - e[0])  # :223
+        new_eval = float(fun(new_pos))
+        replace_upper = (new_eval > 0) if increasing else (new_eval < 0)   # :226
+        if replace_upper:
+            b, e = [b[0], new_pos], [e[0], new_eval]
+        else:
+            b, e = [new_pos, b[1]], [new_eval, e[1]]
+        it += 1
+    return b, e, it
+
+
+def next_temperature_adaptive(lw, lik, beta, beta_max, ess0, retain=0.9, tol=1e-5, max_iter=1000):
+    """transport/smc.py:311-326.  f(b') = log_ess(lw - (b'-beta)*lik) - log(ess0*retain);
+    returns (beta_next, iters) with beta_next = bracket end with the smaller |f|."""
+    lw = np.asarray(lw, np.float64)
+    lik = np.asarray(lik, np.float64)
+    log_target = np.log(ess0 * retain)
+    f = lambda x: log_ess_log_weight(lw - (x - beta) * lik) - log_target
+    b, e, it = bisect(f, [beta, beta_max], max_iter=max_iter, tol=tol)
+    # jnp.argmin(jnp.abs(evals)): first index on ties, NaN counts as the minimum
+    ae = np.abs(np.array(e))
+    return b[int(np.argmin(ae))], it
+
+
+# ----------------------------------------------------------------------------- resampling
+def quantise_weights(w, scale=None):
+    """Exact-fp64 convention (DESIGN.md "Resampling"): q_i = rint(w_i*scale) * 2^-52 with
+    scale = 2^52 / sum (or 2^52 when the weights are already normalised: scale=None).
+
+    All q_i are multiples of 2^-52 and sum to < 2, so EVERY fp64 partial sum is exact: the
+    cumsum is associative, monotone and identical for any scan order or GPU sharding.  For
+    fp32 weights >= 2^-28 the quantisation is the identity."""
+    w = np.asarray(w).astype(np.float64)
+    s = Q_SCALE if scale is None else float(scale)
+    return np.rint(w * s) * Q_INV
+
+
+def cdf_from_weights(w, normalised=True):
+    """Inclusive fp64 cumsum of the quantised weights; clamped to 1 and last forced to 1.0.
+
+    normalised=False: w are un-normalised (e.g. exp(lw - max)); scale = 2^52 / sum_fp64(w),
+    where the sum is the exact fp64 sequential sum mirrored by the device reduction to
+    within its stated tolerance -- tests feed the device's own `sum` back in via
+    cdf_from_weights_scaled for bit-exactness."""
+    w = np.asarray(w)
+    if normalised:
+        q = quantise_weights(w)
+    else:
+        q = quantise_weights(w, Q_SCALE / float(np.sum(w.astype(np.float64))))
+    return finish_cdf(np.cumsum(q))
+
+
+def cdf_from_weights_scaled(w, scale):
+    return finish_cdf(np.cumsum(quantise_weights(w, scale)))
+
+
+def finish_cdf(c):
+    c = np.minimum(c, 1.0)
+    if c.size:
+        c[-1] = 1.0
+    return c
+
+
+def cdf_from_log_weights(lw):
+    """cdf of softmax(lw): e = exp(lw - max) evaluated in fp32 (as the device does), then
+    cdf_from_weights(e, normalised=False).  Matches in law `random.categorical(key, lw)`
+    (smc.py:65-67, filtering.py:199)."""
+    lw = np.asarray(lw, dtype=np.float32)
+    m = np.max(lw)
+    if not np.isfinite(m):
+        m = np.float32(0.0)
+    with np.errstate(invalid='ignore'):
+        e = np.exp((lw - m).astype(np.float32)).astype(np.float32)
+    e = np.where(np.isnan(e), np.float32(0), e)
+    return cdf_from_weights(e, normalised=False)
+
+
+def systematic_uniforms(n_out, u0):
+    """u_i = (i + u0) / n_out in fp64 (one add, one divide), i = 0..n_out-1."""
+    return (np.arange(n_out, dtype=np.float64) + float(u0)) / float(n_out)
+
+
+def ancestors_from_uniforms(cdf, u):
+    """a_i = min{ j : cdf[j] > u_i } = searchsorted(cdf, u, side='right'), clipped to n-1."""
+    cdf = np.asarray(cdf, dtype=np.float64)
+    a = np.searchsorted(cdf, np.asarray(u, dtype=np.float64), side='right')
+    return np.minimum(a, cdf.shape[0] - 1).astype(np.int64)
+
+
+def ancestors_systematic(cdf, u0, n_out=None):
+    n_out = len(cdf) if n_out is None else n_out
+    return ancestors_from_uniforms(cdf, systematic_uniforms(n_out, u0))
+
+
+def ancestors_multinomial(cdf, u):
+    return ancestors_from_uniforms(cdf, u)
+
+
+def categorical_gumbel(rng, lw, n_out):
+    """Faithful restatement of jax.random.categorical(key, lw, shape=(n_out,)):
+    argmax(Gumbel(n_out, n) + lw) -- O(n_out * n) draws (smc.py:65, filtering.py:199).
+    Only feasible for n <= ~2e4; used as the 'faithful' CPU baseline."""
+    lw = np.asarray(lw, dtype=np.float32)
+    n = lw.shape[0]
+    out = np.empty(n_out, dtype=np.int64)
+    chunk = max(1, int(2 ** 24 // max(n, 1)))
+    for s in range(0, n_out, chunk):
+        e = min(n_out, s + chunk)
+        g = rng.gumbel(size=(e - s, n)).astype(np.float32)
+        out[s:e] = np.argmax(g + lw[None, :], axis=1)
+    return out
+
+
+def gather_state(cols, anc):
+    """cdict.__getitem__ (core.py:46-56): every array field indexed along axis 0."""
+    return [np.asarray(c)[anc] for c in cols]
+
+
+# ----------------------------------------------------------------------------- ABC helpers
+def quantile_linear(v, q):
+    """jnp.quantile default (linear interpolation), as used at abc/smc.py:166."""
+    v = np.sort(np.asarray(v, dtype=np.float64))
+    n = v.shape[0]
+    pos = float(q) * (n - 1)
+    lo = int(np.floor(pos))
+    hi = int(np.ceil(pos))
+    lo = min(max(lo, 0), n - 1)
+    hi = min(max(hi, 0), n - 1)
+    frac = pos - np.floor(pos)
+    return float(v[lo] * (1.0 - frac) + v[hi] * frac)
+
+
+def colstats(x):
+    """per-dimension mean and ddof=1 variance over ALL particles (abc/smc.py:97 vmap(jnp.cov))."""
+    x = np.asarray(x, dtype=np.float64)
+    return x.mean(axis=0), x.var(axis=0, ddof=1)
+
+
+# ----------------------------------------------------------------------------- driver
+def while_loop_stacked(cond_fun, body_fun, init_carry, max_iter=1000):
+    """utils.py:159-202: run body while cond, stacking the state part of the carry."""
+    carry = init_carry
+    stack = []
+    it = 0
+    while it < max_iter and cond_fun(*carry):
+        carry = body_fun(*carry)
+        stack.append(carry[0])
+        it += 1
+    return stack, carry

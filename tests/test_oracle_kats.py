@@ -1,0 +1,125 @@
+"""Pin the oracle on the reference's own known-answer tests.
+
+Each test names the reference test it restates (paths under /root/reference/mocat/src/tests/)."""
+import numpy as np
+import numpy.testing as npt
+from scipy.stats import multivariate_normal
+
+from oracle import core, models, mcmc, svgd, philox
+
+
+def test_philox_random123_kat():
+    # Random123 kat_vectors for philox4x32-10
+    h = lambda t: [int(x) for x in t]
+    assert h(philox.philox4x32_10(0, 0, 0, 0, 0, 0)) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    f = 0xffffffff
+    assert h(philox.philox4x32_10(f, f, f, f, f, f)) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert h(philox.philox4x32_10(0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344, 0xa4093822, 0x299f31d0)) \
+        == [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_leapfrog_kat():
+    # test_utils.py:120-147: 3 steps, eps=0.1, x0=0, p0=1, grad U_lik = x (prior 0); fp32, assert_array_equal
+    pg = lambda x: (np.float32(0.0), x)
+    x, p, _, g = mcmc.leapfrog(pg, np.zeros(2, np.float32), np.ones(2, np.float32),
+                               np.array([1., 2.], np.float32), 0.1, 3, dtype=np.float32)
+    npt.assert_array_equal(x, np.array([0.28120947, 0.266409], np.float32))
+    npt.assert_array_equal(g, np.array([0.28120947, 0.266409], np.float32))
+    npt.assert_array_equal(p, np.array([0.9075344, 0.8597696], np.float32))
+
+
+def test_gaussian_potential_vs_scipy():
+    # test_utils.py:37-118: potential == -logpdf for scalar / diag / full precision
+    rng = np.random.default_rng(0)
+    d = 3
+    x = rng.standard_normal(d)
+    mean = rng.standard_normal(d)
+    npt.assert_allclose(models.gaussian_potential(x), -multivariate_normal.logpdf(x, np.zeros(d), np.eye(d)))
+    npt.assert_allclose(models.gaussian_potential(x, mean, prec=2.0),
+                        -multivariate_normal.logpdf(x, mean, np.eye(d) / 2.0))
+    pd = np.array([0.5, 2.0, 3.0])
+    npt.assert_allclose(models.gaussian_potential(x, mean, prec=pd),
+                        -multivariate_normal.logpdf(x, mean, np.diag(1 / pd)))
+    A = rng.standard_normal((d, d))
+    cov = A @ A.T + np.eye(d)
+    prec = np.linalg.inv(cov)
+    npt.assert_allclose(models.gaussian_potential(x, mean, prec=prec, det_prec=np.linalg.det(prec)),
+                        -multivariate_normal.logpdf(x, mean, cov))
+    sp = np.linalg.cholesky(prec)                       # prec = sp sp^T  (utils.py:54 comment)
+    xs = rng.standard_normal((7, d))
+    npt.assert_allclose(models.gaussian_potential(xs, mean, sqrt_prec=sp, det_prec=np.linalg.det(prec)),
+                        -multivariate_normal.logpdf(xs, mean, cov))
+
+
+def test_gaussian_kernel_kat():
+    # test_kernels.py:16-29
+    z, o = np.zeros(5), np.ones(5)
+    npt.assert_array_almost_equal(svgd.gaussian_kernel(z, z), 1.0)
+    npt.assert_array_almost_equal(svgd.gaussian_kernel(z, o), 0.082085006)
+    npt.assert_array_almost_equal(svgd.gaussian_kernel_grad_x(z, z), np.zeros(5))
+    npt.assert_array_almost_equal(svgd.gaussian_kernel_grad_x(z, o), np.ones(5) * 0.082085006)
+
+
+def test_bisect_kat():
+    # test_utils.py:178-194
+    f = lambda x: x ** 2 - 10
+    b, e, it = core.bisect(f, [0.0, 1e2])
+    assert min(abs(e[0]), abs(e[1])) < 1e-3
+    npt.assert_allclose(b[int(np.argmin(np.abs(e)))], np.sqrt(10.0), rtol=1e-5)
+    b, e, it = core.bisect(f, [-1e1, 0.0])
+    assert min(abs(e[0]), abs(e[1])) < 1e-3
+    npt.assert_allclose(b[int(np.argmin(np.abs(e)))], -np.sqrt(10.0), rtol=1e-5)
+
+
+def test_while_loop_stacked_kat():
+    # test_utils.py:166-175
+    stack, _ = core.while_loop_stacked(lambda x, _: x < 10, lambda x, _: (x + 1, None), (0, None), 100)
+    npt.assert_array_equal(stack, np.arange(1, 11))
+
+
+def test_svgd_gemm_identity():
+    # double-vmap formula (svgd.py:25-31) == GEMM form
+    rng = np.random.default_rng(1)
+    X, G = rng.standard_normal((9, 3)), rng.standard_normal((9, 3))
+    npt.assert_allclose(svgd.phi(X, G, 0.7), svgd.phi_double_loop(X, G, 0.7), atol=1e-14)
+
+
+def test_lse_ess_semantics():
+    # Appendix A.1: w in {0,-inf} -> ess = #alive; all -inf -> LSE=-inf, log_ess NaN
+    lw = np.array([0.0, -np.inf, 0.0, 0.0, -np.inf])
+    assert abs(core.ess_log_weight(lw) - 3.0) < 1e-12
+    assert core.logsumexp(np.full(4, -np.inf)) == -np.inf
+    assert np.isnan(core.log_ess_log_weight(np.full(4, -np.inf)))
+    npt.assert_allclose(core.logsumexp(np.zeros(8), b=1 / 8), 0.0, atol=1e-15)
+
+
+def test_exact_cumsum_is_order_independent():
+    # the quantised weights make every fp64 partial sum exact: any association gives the same bits
+    rng = np.random.default_rng(3)
+    w = rng.random(100000).astype(np.float32)
+    w /= w.sum()
+    q = core.quantise_weights(w)
+    c = np.cumsum(q)
+    # pairwise / blocked association
+    blocks = q.reshape(100, 1000)
+    c2 = (np.cumsum(blocks, axis=1) + np.concatenate([[0.0], np.cumsum(blocks.sum(axis=1))[:-1]])[:, None]).ravel()
+    npt.assert_array_equal(c, c2)
+    # for fp32 weights >= 2^-28 quantisation is the identity, so this IS the plain fp64 cumsum
+    big = w >= 2.0 ** -28
+    npt.assert_array_equal(q[big], w[big].astype(np.float64))
+
+
+def test_ancestors_convention():
+    cdf = core.cdf_from_weights(np.array([0.1, 0.2, 0.3, 0.4], np.float32))
+    assert cdf[-1] == 1.0
+    npt.assert_array_equal(core.ancestors_from_uniforms(cdf, [0.0, 0.0999, 0.1000001, 0.31, 0.99999]),
+                           [0, 0, 1, 2, 3])
+    a = core.ancestors_systematic(cdf, 0.5)
+    npt.assert_array_equal(a, [1, 2, 3, 3])
+
+
+def test_quantile_linear_matches_numpy():
+    rng = np.random.default_rng(4)
+    v = rng.random(1001)
+    for q in (0.0, 0.1234, 0.5, 0.9, 1.0):
+        npt.assert_allclose(core.quantile_linear(v, q), np.quantile(v, q), rtol=1e-14)
