@@ -1,0 +1,226 @@
+/* mocat_b200.h -- C-ABI of libmocat_b200.so: the B200 (sm_100a) particle-population hot path
+ * behind mocat's Python API.
+ *
+ * The reference (SamDuffield/mocat v0.2.6) is pure Python on JAX and has NO FFI boundary; its seam
+ * is the Python method protocol (Sampler.startup/update, run_particle_filter_for_marginals ...).
+ * Each entry point below names the reference code (path:line under /root/reference/mocat/src/) whose
+ * device work it replaces; INTEGRATION.md shows the ctypes binding a mocat maintainer would add.
+ *
+ * Conventions
+ *  - every pointer is a CUDA DEVICE pointer owned by the caller unless the name ends in _host;
+ *  - particle state is SoA: column k of a (d x n) block lives at base + k*ld  (ld >= n, elements);
+ *  - every call is asynchronous on `stream` (a cudaStream_t passed as void*) and returns
+ *    MB_OK or an error code; mb_last_error() gives the message of the last failure in this thread;
+ *  - a context is bound to one device and one host thread; calls on one context are not thread safe;
+ *  - random numbers: Philox4x32-10, counter (gid_lo, gid_hi, step, (purpose<<20)|index), key = seed;
+ *    gid is the GLOBAL particle index = gid0 + local index, so results do not depend on sharding.
+ */
+#ifndef MOCAT_B200_H
+#define MOCAT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MB_ABI_VERSION 1
+
+#define MB_OK              0
+#define MB_ERR_CUDA        1
+#define MB_ERR_ARG         2
+#define MB_ERR_UNSUPPORTED 3
+
+#define MB_MAX_SMALL_DIM   8    /* dense d x d models (Gaussian target, linear-Gaussian SSM) */
+#define MB_HIST_MAX        16384
+
+typedef struct mb_ctx mb_ctx;
+typedef void* mb_stream_t;
+
+/* ---- device-resident control block: every per-iteration scalar the reference keeps replicated per
+ *      particle (temperature, ess, log_norm_constant: transport/smc.py:157-162,177-184; threshold:
+ *      abc/smc.py:86-91) lives here once, is updated by the kernels, and is read back by the host
+ *      only when it wants to look.  All kernels that take a control block early-exit when done != 0. */
+typedef struct {
+    double wmax, s1, s2;        /* max(lw), sum exp(lw-wmax), sum exp(2(lw-wmax)) of the CURRENT weights   */
+    double lse, lse2, log_ess;  /* logsumexp(lw), logsumexp(2lw), 2*lse-lse2   (metrics.py:69-74)          */
+    double ess;                 /* exp(log_ess)                                                            */
+    double log_z;               /* running log normalising constant (transport/smc.py:160,212-215)         */
+    double beta;                /* temperature (transport/smc.py:157) or ABC threshold (abc/smc.py:67)     */
+    double alpha_mean;          /* mean acceptance prob. of the last move (abc/smc.py:240-241)             */
+    double aux0, aux1;          /* kernel specific (alive count, sum alpha ...)                            */
+    int64_t nan_count;          /* NaN entries in the value block after the last move (smc.py:174-175)     */
+    int64_t alpha_fx;           /* sum of per-particle acceptance probabilities, fixed point 2^-32          */
+    int32_t iter;               /* extra.iter (sample.py:64-65)                                            */
+    int32_t resample;           /* resample_criterion evaluated for the NEXT update (smc.py:298-301)       */
+    int32_t done;               /* termination_criterion (smc.py:171-175, abc/smc.py:157-161)              */
+    int32_t search_iters;       /* regula-falsi iterations of the last temperature search                  */
+    int32_t resampled;          /* whether the last update resampled                                       */
+    int32_t pad0;
+} mb_control;
+
+/* per-iteration record appended by the adapt kernels (what clean_chain keeps: smc.py:177-184) */
+typedef struct {
+    double beta, ess, log_z, alpha_mean, lse;
+    int32_t resampled, search_iters;
+} mb_hist;
+
+/* ---- scenario descriptions (POD; replaces the per-particle Python callables of core.py:146-261) ---- */
+enum { MB_LIK_RASTRIGIN = 0,   /* scenarios/toy_examples.py:135-149 */
+       MB_LIK_GAUSSIAN  = 1,   /* scenarios/toy_examples.py:17-51   */
+       MB_LIK_NONE      = 2 };
+enum { MB_MOVE_MALA = 0,       /* mcmc/standard_mcmc.py:72-153 Underdamped(friction=inf), utils.py:108-146 */
+       MB_MOVE_RW   = 1 };     /* mcmc/standard_mcmc.py:21-65  RandomWalk                                   */
+enum { MB_RESAMPLE_SYSTEMATIC = 0, MB_RESAMPLE_MULTINOMIAL = 1 };
+
+typedef struct {
+    int32_t kind, dim;
+    float prior_mean, prior_std, prior_pscale; /* prior_sample = mean + std z; U_prior = .5 sum(((x-mean) pscale)^2) */
+    float a;                                   /* Rastrigin a                                                        */
+    float mean[MB_MAX_SMALL_DIM];              /* Gaussian target mean                                               */
+    float prec_sqrt[MB_MAX_SMALL_DIM * MB_MAX_SMALL_DIM]; /* row-major S: y = (x-mean) S^T, U = .5|y|^2              */
+} mb_target;
+
+typedef struct {
+    int32_t kind;            /* MB_MOVE_*                                  */
+    int32_t mcmc_steps;      /* transport/smc.py:255                       */
+    int32_t leapfrog_steps;  /* mcmc/standard_mcmc.py:78                   */
+    float   stepsize;
+} mb_move;
+
+typedef struct {             /* adaptive likelihood tempering, transport/smc.py:231-259,311-326 */
+    double  max_temperature, ess_retain, ess_resample, tol;
+    int32_t max_search_iter, max_iter;
+    const double* schedule;  /* device, or NULL for adaptive (transport/smc.py:115-126) */
+    int32_t schedule_len, pad;
+} mb_temper;
+
+enum { MB_SSM_LINEAR_GAUSSIAN = 0,  /* ssm/linear_gaussian/linear_gaussian.py:142-261 */
+       MB_SSM_LORENZ96 = 1 };       /* ssm/scenarios/lorenz96.py:14-44 on ssm/nonlinear_gaussian.py:19-131 */
+
+typedef struct {
+    int32_t kind, dim, dim_obs, substeps;
+    /* linear Gaussian (dim, dim_obs <= MB_MAX_SMALL_DIM), all row-major */
+    float m0[MB_MAX_SMALL_DIM];
+    float L0[MB_MAX_SMALL_DIM * MB_MAX_SMALL_DIM];      /* chol(P0)               */
+    float F[MB_MAX_SMALL_DIM * MB_MAX_SMALL_DIM];
+    float LQ[MB_MAX_SMALL_DIM * MB_MAX_SMALL_DIM];      /* chol(Q)                */
+    float H[MB_MAX_SMALL_DIM * MB_MAX_SMALL_DIM];
+    float Rps[MB_MAX_SMALL_DIM * MB_MAX_SMALL_DIM];     /* inv(chol(R)) used as in utils.py:26-30: .5|(y-Hx) Rps|^2 */
+    float lik_const;                                    /* .5 (d_y log 2pi - log det R^-1) */
+    /* Lorenz-96 with diagonal noise */
+    float forcing, dt, q_std, r_std, init_mean, init_std;
+} mb_ssm;
+
+typedef struct {              /* g-and-k, abc/scenarios/gk.py:68-96 */
+    int32_t m;                /* simulated draws per particle, sorted = summary (<= 16) */
+    float c, prior_min, prior_max, buffer;
+    float data[16];
+} mb_gk;
+
+/* ---- context ---------------------------------------------------------------------------------- */
+const char* mb_last_error(void);
+int         mb_abi_version(void);
+mb_ctx*     mb_create(int device);
+void        mb_destroy(mb_ctx* ctx);
+int         mb_sm_count(mb_ctx* ctx);
+
+/* ---- K2: log-sum-exp / ESS reduction.  Replaces metrics.py:69-78 (log_ess_log_weight), the logsumexp
+ *      calls at transport/smc.py:160,214-215,288 and MetropolisedSMCSampler.log_ess (smc.py:303-309).
+ *      out6 (device) = {wmax, s1, s2, lse, lse2, log_ess}. lik==NULL: plain; else weights lw - dbeta*lik. */
+int mb_lse_ess(mb_ctx* ctx, const float* lw, const float* lik, double dbeta, int64_t n,
+               double* out6, mb_stream_t stream);
+
+/* ---- K3: adaptive-temperature search + weight update, entirely on device.  Replaces utils.py:205-237
+ *      (bisect), transport/smc.py:311-326 (next_temperature_adaptive), :193-217 (adapt), :171-175
+ *      (termination), :298-301 (resample criterion for the next update).  Reads/writes ctl; lw updated
+ *      in place: lw += -(beta' - beta) * lik.  Appends one mb_hist record at hist[ctl->iter] if hist. */
+int mb_temper_adapt(mb_ctx* ctx, float* lw, const float* lik, int64_t n, const mb_temper* prm,
+                    int advance_iter, int64_t nan_denominator, int64_t n_total, mb_control* ctl,
+                    mb_hist* hist, mb_stream_t stream);
+
+/* ---- K4: inclusive fp64 CDF of the normalised weights (implicit in random.categorical at
+ *      transport/smc.py:65, ssm/filtering.py:199).  Exact-fp64 convention: q_i = rint(w_i*scale)*2^-52,
+ *      cdf = min(cumsum(q), 1), cdf[n-1] = 1.   _lw: w_i = exp(lw_i - ctl->wmax), scale from ctl->s1
+ *      (predicated on ctl->resample unless force).   _f32: caller supplies linear weights and scale. */
+int mb_cumsum_lw(mb_ctx* ctx, const float* lw, int64_t n, const mb_control* ctl, int force,
+                 double* cdf, mb_stream_t stream);
+int mb_cumsum_f32(mb_ctx* ctx, const float* w, int64_t n, double scale, double* cdf, mb_stream_t stream);
+
+/* ---- K5: ancestors a_i = min{ j : cdf[j] > u_i }.  mode systematic: u_i = (i + u0)/n_out;
+ *      multinomial: n_out iid u_i.  u (device, fp64) may be NULL => Philox(seed, step, P_RESAMPLE).
+ *      ctl may be NULL (always run) else predicated on ctl->resample. */
+int mb_ancestors(mb_ctx* ctx, const double* cdf, int64_t n, int mode, const double* u,
+                 uint64_t seed, uint32_t step, int64_t gid0, int32_t* anc, int64_t n_out,
+                 const mb_control* ctl, mb_stream_t stream);
+
+/* ---- K6: gather of SoA state columns by ancestor.  Replaces cdict.__getitem__ (core.py:46-56) as
+ *      used at transport/smc.py:68 and ssm/filtering.py:199. */
+int mb_gather_state(mb_ctx* ctx, const int32_t* anc, int64_t n_out, int ncols,
+                    const float* src, int64_t ld_src, float* dst, int64_t ld_dst, mb_stream_t stream);
+
+/* ---- K1a: tempered-SMC population move.  Replaces vmap(forward_proposal) (transport/smc.py:91-95,
+ *      337-365): MCMC startup (potentials re-evaluated at ctl->beta), mcmc_steps Metropolised moves
+ *      (mcmc/sampler.py:92-111, mcmc/metropolis.py:48-70), prior/likelihood potentials of the new state.
+ *      If ctl->resample: particle i starts from x_in[:, anc[i]] and lw[i] is reset to 0 (smc.py:61-71).
+ *      Outputs x_out (d x ld), up_out, lik_out, alpha_out (any of up/alpha may be NULL). */
+int mb_smc_init(mb_ctx* ctx, const mb_target* tgt, float* x, int64_t ld, int64_t n, int64_t n_total,
+                int sample_prior, float* up, float* lik, float* lw, uint64_t seed, int64_t gid0,
+                mb_control* ctl, mb_stream_t stream);
+int mb_smc_move(mb_ctx* ctx, const mb_target* tgt, const mb_move* mv, const float* x_in, float* x_out,
+                int64_t ld, int64_t n, const int32_t* anc, float* lw, float* up_out, float* lik_out,
+                float* alpha_out, uint64_t seed, int64_t gid0, mb_control* ctl, mb_stream_t stream);
+
+/* ---- K1b: bootstrap particle filter.  Replaces initiate_particles (ssm/filtering.py:173-193) and one
+ *      body of the scan in run_particle_filter_for_marginals (:280-311): optional ancestor gather,
+ *      transition_sample, log-weight increment -likelihood_potential, ESS, log-evidence, and the
+ *      resample decision for the next step (ess < ess_threshold*n, strict).  t is the time index. */
+int mb_pf_init(mb_ctx* ctx, const mb_ssm* ssm, float* x, int64_t ld, int64_t n, int64_t n_total,
+               const float* y0, float* lw, uint64_t seed, int64_t gid0, double ess_threshold,
+               mb_control* ctl, mb_hist* hist, mb_stream_t stream);
+int mb_pf_step(mb_ctx* ctx, const mb_ssm* ssm, const float* x_in, float* x_out, int64_t ld, int64_t n,
+               int64_t n_total, const int32_t* anc, const float* y, float* lw, uint64_t seed, uint32_t t,
+               int64_t gid0, double ess_threshold, mb_control* ctl, mb_hist* hist, mb_stream_t stream);
+
+/* weighted mean / variance of every column under weights exp(lw - ctl->wmax)/s1  (diagnostics) */
+int mb_weighted_moments(mb_ctx* ctx, const float* x, int64_t ld, int64_t n, int d, const float* lw,
+                        const mb_control* ctl, double* mean, double* var, mb_stream_t stream);
+
+/* ---- K7 / K1c: SMC-ABC.  mb_quantile: linear-interpolated quantile (jnp.quantile, abc/smc.py:166);
+ *      mb_colstats: per-dimension mean and ddof=1 variance (vmap(jnp.cov), abc/smc.py:97);
+ *      mb_abc_init / mb_abc_move: abc/smc.py:44-79,210-219 + abc/mcmc.py:56-76 for the g-and-k model;
+ *      mb_abc_adapt: abc/smc.py:228-245 (threshold, 0/-inf weights, ess, alpha_mean, RW scale). */
+int mb_quantile(mb_ctx* ctx, const float* v, int64_t n, double q, double* out3 /*value, v[lo], v[hi]*/,
+                mb_stream_t stream);
+int mb_colstats(mb_ctx* ctx, const float* x, int64_t ld, int64_t n, int d, double* mean, double* var,
+                mb_stream_t stream);
+int mb_abc_init(mb_ctx* ctx, const mb_gk* gk, float* x, int64_t ld, int64_t n, int64_t n_total, int sample_prior,
+                float* up, float* dist, float* lw, float* alpha, uint64_t seed, int64_t gid0, mb_control* ctl,
+                mb_stream_t stream);
+int mb_abc_move(mb_ctx* ctx, const mb_gk* gk, int mcmc_steps, const float* x_in, float* x_out, int64_t ld,
+                int64_t n, const int32_t* anc, const float* up_in, float* up_out, const float* dist_in,
+                float* dist_out, float* lw, const float* alpha_in, float* alpha_out,
+                const float* stepsize /*device [4]*/, uint64_t seed, int64_t gid0, mb_control* ctl,
+                mb_stream_t stream);
+int mb_abc_adapt(mb_ctx* ctx, const float* x, int64_t ld, int64_t n, int64_t n_total, int d, const float* dist,
+                 float* lw, const float* alpha, float* stepsize /*device [d]*/, double ess_retain, double ess_resample,
+                 double termination_alpha, int max_iter, const double* schedule, int advance_iter,
+                 mb_control* ctl, mb_hist* hist, mb_stream_t stream);
+
+/* ---- K8-K10: SVGD.  mb_svgd_phi replaces kernelised_grad_matrix (transport/svgd.py:18-32) with the
+ *      Gaussian kernel (kernels.py:90-102); X, G, phi are row-major (n x d).  mb_pairdist_bandwidth
+ *      replaces median/mean_bandwidth_update (kernels.py:220-229, utils.py:437-439); h on device.
+ *      mb_adagrad replaces jax.example_libraries.optimizers.adagrad (svgd.py:104-106,138-139). */
+int mb_svgd_phi(mb_ctx* ctx, const float* X, const float* G, int n, int d, const float* bandwidth,
+                float* phi, int variant, mb_stream_t stream);
+int mb_pairdist_bandwidth(mb_ctx* ctx, const float* X, int n, int d, int mode /*0 median, 1 mean*/,
+                          float* h, mb_stream_t stream);
+int mb_adagrad(mb_ctx* ctx, float* X, float* gsq, float* mom, const float* phi, int64_t len, float step,
+               float momentum, mb_stream_t stream);
+int mb_target_potential_grad(mb_ctx* ctx, const mb_target* tgt, double beta, const float* X /*n x d row-major*/,
+                             int n, float* U, float* G, mb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOCAT_B200_H */

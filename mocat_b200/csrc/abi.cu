@@ -1,0 +1,92 @@
+// abi.cu -- context management and error reporting of the C-ABI (include/mocat_b200.h).
+#include <stdarg.h>
+#include <string.h>
+#include "common.cuh"
+
+static thread_local char g_err[1024] = "";
+
+void mb_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char* mb_last_error(void) { return g_err; }
+extern "C" int mb_abi_version(void) { return MB_ABI_VERSION; }
+
+extern "C" mb_ctx* mb_create(int device) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || device < 0 || device >= count) {
+        mb_set_error("mb_create: no usable CUDA device %d (%s); this library has no CPU fallback", device,
+                     e == cudaSuccess ? "index out of range" : cudaGetErrorString(e));
+        return nullptr;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) { mb_set_error("mb_create: cudaSetDevice failed"); return nullptr; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { mb_set_error("mb_create: no device properties"); return nullptr; }
+    if (prop.major != 10) {
+        mb_set_error("mb_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major,
+                     prop.minor);
+        return nullptr;
+    }
+    mb_ctx* ctx = new mb_ctx();
+    memset(ctx, 0, sizeof(*ctx));
+    ctx->device = device;
+    ctx->sms = prop.multiProcessorCount;
+    ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    bool ok = true;
+    ok = ok && cudaMalloc(&ctx->partials, sizeof(double) * 3 * MB_MAX_PARTIAL_BLOCKS * 2) == cudaSuccess;
+    ok = ok && cudaMalloc(&ctx->counters, sizeof(uint32_t) * MB_NUM_COUNTERS) == cudaSuccess;
+    ok = ok && cudaMemset(ctx->counters, 0, sizeof(uint32_t) * MB_NUM_COUNTERS) == cudaSuccess;
+    ctx->scratch_bytes = 8u << 20;
+    ok = ok && cudaMalloc(&ctx->scratch, ctx->scratch_bytes) == cudaSuccess;
+    if (!ok) {
+        mb_set_error("mb_create: workspace allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        mb_destroy(ctx);
+        return nullptr;
+    }
+    return ctx;
+}
+
+extern "C" void mb_destroy(mb_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaFree(ctx->partials);
+    cudaFree(ctx->counters);
+    cudaFree(ctx->scan_flag);
+    cudaFree(ctx->scan_agg);
+    cudaFree(ctx->scan_incl);
+    cudaFree(ctx->scratch);
+    delete ctx;
+}
+
+extern "C" int mb_sm_count(mb_ctx* ctx) { return ctx ? ctx->sms : 0; }
+
+int mb_ensure_scratch(mb_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->scratch_bytes) return MB_OK;
+    MB_CUDA(cudaDeviceSynchronize());
+    cudaFree(ctx->scratch);
+    ctx->scratch = nullptr;
+    ctx->scratch_bytes = 0;
+    size_t nb = bytes + (bytes >> 1);
+    MB_CUDA(cudaMalloc(&ctx->scratch, nb));
+    ctx->scratch_bytes = nb;
+    return MB_OK;
+}
+
+int mb_ensure_scan(mb_ctx* ctx, int64_t tiles) {
+    if (tiles <= ctx->scan_tiles_cap) return MB_OK;
+    MB_CUDA(cudaDeviceSynchronize());
+    cudaFree(ctx->scan_flag); cudaFree(ctx->scan_agg); cudaFree(ctx->scan_incl);
+    ctx->scan_flag = nullptr; ctx->scan_agg = nullptr; ctx->scan_incl = nullptr; ctx->scan_tiles_cap = 0;
+    int64_t cap = tiles + (tiles >> 1) + 64;
+    MB_CUDA(cudaMalloc(&ctx->scan_flag, sizeof(int32_t) * cap));
+    MB_CUDA(cudaMalloc(&ctx->scan_agg, sizeof(double) * cap));
+    MB_CUDA(cudaMalloc(&ctx->scan_incl, sizeof(double) * cap));
+    MB_CUDA(cudaMemset(ctx->scan_flag, 0, sizeof(int32_t) * cap));
+    ctx->scan_tiles_cap = cap;
+    ctx->scan_epoch = 0;
+    return MB_OK;
+}

@@ -1,0 +1,512 @@
+// propagate.cu -- K1: per-particle move + potential/gradient evaluation + log-weight increment.
+//
+//   smc_move   : vmap(forward_proposal) of MetropolisedSMCSampler (transport/smc.py:91-95,337-365) with
+//                MALA/HMC (mcmc/standard_mcmc.py:72-153, utils.py:108-146) or random walk (:21-65) and the
+//                Metropolis correction (mcmc/metropolis.py:48-70), fused with the ancestor gather.
+//   pf_step    : bootstrap filter body (ssm/filtering.py:280-311, 154-170) for the linear-Gaussian model
+//                (ssm/linear_gaussian/linear_gaussian.py:86-94,118-128) and Lorenz-96 with a fixed-step
+//                RK4 flow (ssm/scenarios/lorenz96.py:14-26, ssm/nonlinear_gaussian.py:107-121), fused with
+//                the ancestor gather, the LSE/ESS reduction and the log-evidence / resample bookkeeping.
+//
+// Layout: SoA, one thread per particle, every column access is a fully coalesced 128 B/warp request;
+// the state of a particle lives in registers (D is a template parameter).
+#include "common.cuh"
+#include "rng.cuh"
+
+#define MV_THREADS 256
+#define TWO_PI_F 6.283185307179586f
+
+// =================================================================================================
+// potentials of the static targets (core.py:190-194: U = U_prior + beta * U_lik)
+template <int D>
+__device__ __forceinline__ void prior_eval(const mb_target& t, const float (&x)[D], float& up, float (&gp)[D]) {
+    up = 0.f;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        const float r = (x[k] - t.prior_mean) * t.prior_pscale;
+        up = fmaf(0.5f * r, r, up);
+        gp[k] = r * t.prior_pscale;
+    }
+}
+
+template <int LIK, int D>
+__device__ __forceinline__ void lik_eval(const mb_target& t, const float (&x)[D], float& ul, float (&gl)[D]) {
+    if (LIK == MB_LIK_RASTRIGIN) {            // toy_examples.py:146-149
+        float acc = t.a * (float)D;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            const float f = x[k] - rintf(x[k]);            // cos(2 pi x) = cos(2 pi frac), |2 pi frac| <= pi
+            float s, c;
+            __sincosf(TWO_PI_F * f, &s, &c);
+            acc += fmaf(x[k], x[k], -t.a * c);
+            gl[k] = fmaf(TWO_PI_F * t.a, s, 2.f * x[k]);
+        }
+        ul = acc;
+    } else if (LIK == MB_LIK_GAUSSIAN) {      // toy_examples.py:40-44: y = (x - mean) S^T
+        float y[D];
+#pragma unroll
+        for (int r = 0; r < D; ++r) {
+            float acc = 0.f;
+#pragma unroll
+            for (int c = 0; c < D; ++c) acc = fmaf(t.prec_sqrt[r * MB_MAX_SMALL_DIM + c], x[c] - t.mean[c], acc);
+            y[r] = acc;
+        }
+        ul = 0.f;
+#pragma unroll
+        for (int r = 0; r < D; ++r) ul = fmaf(0.5f * y[r], y[r], ul);
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+            float acc = 0.f;
+#pragma unroll
+            for (int r = 0; r < D; ++r) acc = fmaf(y[r], t.prec_sqrt[r * MB_MAX_SMALL_DIM + c], acc);
+            gl[c] = acc;
+        }
+    } else {
+        ul = 0.f;
+#pragma unroll
+        for (int k = 0; k < D; ++k) gl[k] = 0.f;
+    }
+}
+
+template <int LIK, int D>
+__device__ __forceinline__ void target_eval(const mb_target& t, float beta, const float (&x)[D], float& up, float& ul,
+                                            float (&g)[D]) {
+    float gp[D], gl[D];
+    prior_eval<D>(t, x, up, gp);
+    lik_eval<LIK, D>(t, x, ul, gl);
+#pragma unroll
+    for (int k = 0; k < D; ++k) g[k] = fmaf(beta, gl[k], gp[k]);
+}
+
+// =================================================================================================
+struct SmcArgs {
+    mb_target tgt;
+    mb_move mv;
+    const float* x_in; float* x_out; int64_t ld; int64_t n;
+    const int32_t* anc;
+    float* lw; float* up_out; float* lik_out; float* alpha_out;
+    uint64_t seed; int64_t gid0;
+    mb_control* ctl;
+    int sample_prior;
+};
+
+// initial population: x ~ prior (transport/sampler.py:24-30), potentials, lw = 0, control block reset
+// (transport/smc.py:128-164: temperature 0, log_weight 0, ess n, log_norm_constant LSE(0, b=1/n) = 0).
+template <int LIK, int D>
+__global__ void __launch_bounds__(MV_THREADS) smc_init_kernel(SmcArgs a, int64_t n_total) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
+        float x[D];
+        if (a.sample_prior) {
+            float z[D];
+            philox_normals<D>(z, a.seed, (uint64_t)(a.gid0 + i), 0u, MB_P_INIT, 0u);
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                x[k] = fmaf(a.tgt.prior_std, z[k], a.tgt.prior_mean);
+                a.x_out[(int64_t)k * a.ld + i] = x[k];
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < D; ++k) x[k] = a.x_out[(int64_t)k * a.ld + i];
+        }
+        float up, ul, g[D];
+        target_eval<LIK, D>(a.tgt, 0.f, x, up, ul, g);
+        if (a.up_out) a.up_out[i] = up;
+        a.lik_out[i] = ul;
+        a.lw[i] = 0.f;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        mb_control c;
+        memset(&c, 0, sizeof(c));
+        const double nd = (double)n_total;
+        c.wmax = 0.0; c.s1 = nd; c.s2 = nd;
+        c.lse = log(nd); c.lse2 = log(nd); c.log_ess = log(nd); c.ess = nd;
+        c.alpha_mean = 1.0;
+        *a.ctl = c;
+    }
+}
+
+template <int LIK, int D, int MOVE>
+__global__ void __launch_bounds__(MV_THREADS) smc_move_kernel(SmcArgs a) {
+    const mb_control* ctl = a.ctl;
+    if (ctl->done) return;
+    const bool resample = ctl->resample != 0;
+    const float beta = (float)ctl->beta;
+    const uint32_t step = (uint32_t)(ctl->iter + 1);
+    const float eps = a.mv.stepsize;
+    constexpr uint32_t NZ = (D + 3) / 4, S = NZ + 1;
+    __shared__ double red[MV_THREADS / 32];
+    long long nan_local = 0;
+    double alpha_local = 0.0;
+
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t src = resample ? (int64_t)a.anc[i] : i;          // fused ancestor gather (core.py:46-56)
+        float x[D];
+#pragma unroll
+        for (int k = 0; k < D; ++k) x[k] = __ldg(a.x_in + (int64_t)k * a.ld + src);
+        float up, ul, g[D];
+        target_eval<LIK, D>(a.tgt, beta, x, up, ul, g);                // MCMC startup, standard_mcmc.py:94-102
+        float U = fmaf(beta, ul, up);
+        float alpha_sum = 0.f;
+        const uint64_t gid = (uint64_t)(a.gid0 + i);
+        for (int s = 0; s < a.mv.mcmc_steps; ++s) {
+            float z[D];
+            philox_normals<D>(z, a.seed, gid, step, MB_P_MOVE, (uint32_t)s * S);
+            const float uacc = u24(philox_raw(a.seed, gid, step, MB_P_MOVE, (uint32_t)s * S + NZ).x);
+            float xp[D], gpn[D], upn, uln, Un, alpha;
+            if (MOVE == MB_MOVE_MALA) {
+                // always(): p = z (friction = inf, :116-122); leapfrog (utils.py:117-134); p' = -p' (:141)
+                float p[D], kin0 = 0.f;
+#pragma unroll
+                for (int k = 0; k < D; ++k) { p[k] = z[k]; kin0 = fmaf(0.5f * z[k], z[k], kin0); xp[k] = x[k]; gpn[k] = g[k]; }
+                for (int l = 0; l < a.mv.leapfrog_steps; ++l) {
+#pragma unroll
+                    for (int k = 0; k < D; ++k) {
+                        p[k] = fmaf(-0.5f * eps, gpn[k], p[k]);        // p_half
+                        xp[k] = fmaf(eps, p[k], xp[k]);
+                    }
+                    target_eval<LIK, D>(a.tgt, beta, xp, upn, uln, gpn);
+#pragma unroll
+                    for (int k = 0; k < D; ++k) p[k] = fmaf(-0.5f * eps, gpn[k], p[k]);
+                }
+                Un = fmaf(beta, uln, upn);
+                float kin1 = 0.f;
+#pragma unroll
+                for (int k = 0; k < D; ++k) kin1 = fmaf(0.5f * p[k], p[k], kin1);
+                alpha = fminf(1.f, __expf(-Un + U - kin1 + kin0));     // standard_mcmc.py:145-153
+            } else {
+                const float sq = sqrtf(eps);                           // standard_mcmc.py:57
+#pragma unroll
+                for (int k = 0; k < D; ++k) xp[k] = fmaf(sq, z[k], x[k]);
+                target_eval<LIK, D>(a.tgt, beta, xp, upn, uln, gpn);
+                Un = fmaf(beta, uln, upn);
+                alpha = fminf(1.f, __expf(-Un + U));                   // :61-65
+            }
+            if (alpha != alpha) alpha = 0.f;                           // metropolis.py:58
+            if (uacc < alpha) {                                        // :61-66
+#pragma unroll
+                for (int k = 0; k < D; ++k) { x[k] = xp[k]; g[k] = gpn[k]; }
+                up = upn; ul = uln; U = Un;
+            }
+            alpha_sum += alpha;
+        }
+        const float alpha_mean = alpha_sum / (float)a.mv.mcmc_steps;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            a.x_out[(int64_t)k * a.ld + i] = x[k];
+            nan_local += (x[k] != x[k]);
+        }
+        if (a.up_out) a.up_out[i] = up;
+        a.lik_out[i] = ul;
+        if (a.alpha_out) a.alpha_out[i] = alpha_mean;
+        if (resample) a.lw[i] = 0.f;                                   // smc.py:69
+        alpha_local += (double)alpha_mean;
+    }
+    // deterministic (integer) accumulation of NaN count and mean acceptance
+    const double asum = block_sum_d(alpha_local, red);
+    const double nsum = block_sum_d((double)nan_local, red);
+    if (threadIdx.x == 0) {
+        atomicAdd((unsigned long long*)&a.ctl->alpha_fx, (unsigned long long)llrint(asum * 4294967296.0));
+        if (nsum > 0) atomicAdd((unsigned long long*)&a.ctl->nan_count, (unsigned long long)nsum);
+        if (blockIdx.x == 0) a.ctl->resampled = resample ? 1 : 0;
+    }
+}
+
+// dispatch over (likelihood kind, dimension, move)
+#define SMC_DIMS(X) X(1) X(2) X(3) X(4) X(5) X(6) X(8) X(10) X(16)
+
+template <int LIK, int D>
+static int smc_launch(const SmcArgs& a, int init, int64_t n_total, int grid, cudaStream_t st) {
+    if (init) { smc_init_kernel<LIK, D><<<grid, MV_THREADS, 0, st>>>(a, n_total); }
+    else if (a.mv.kind == MB_MOVE_MALA) { smc_move_kernel<LIK, D, MB_MOVE_MALA><<<grid, MV_THREADS, 0, st>>>(a); }
+    else if (a.mv.kind == MB_MOVE_RW) { smc_move_kernel<LIK, D, MB_MOVE_RW><<<grid, MV_THREADS, 0, st>>>(a); }
+    else { mb_set_error("smc: unknown move kind %d", a.mv.kind); return MB_ERR_ARG; }
+    MB_CHECK_LAUNCH();
+    return MB_OK;
+}
+
+static int smc_dispatch(mb_ctx* ctx, const SmcArgs& a, int init, int64_t n_total, cudaStream_t st) {
+    int64_t grid = (a.n + MV_THREADS - 1) / MV_THREADS;
+    if (grid > (int64_t)ctx->sms * 16) grid = (int64_t)ctx->sms * 16;
+    const int d = a.tgt.dim;
+#define CASE_R(DD) if (d == DD) return smc_launch<MB_LIK_RASTRIGIN, DD>(a, init, n_total, (int)grid, st);
+#define CASE_G(DD) if (d == DD && DD <= MB_MAX_SMALL_DIM) return smc_launch<MB_LIK_GAUSSIAN, (DD <= MB_MAX_SMALL_DIM ? DD : 1)>(a, init, n_total, (int)grid, st);
+#define CASE_N(DD) if (d == DD) return smc_launch<MB_LIK_NONE, DD>(a, init, n_total, (int)grid, st);
+    if (a.tgt.kind == MB_LIK_RASTRIGIN) { SMC_DIMS(CASE_R) }
+    else if (a.tgt.kind == MB_LIK_GAUSSIAN) { SMC_DIMS(CASE_G) }
+    else if (a.tgt.kind == MB_LIK_NONE) { SMC_DIMS(CASE_N) }
+    mb_set_error("smc: unsupported target kind %d / dim %d (built-in device scenarios only; no CPU fallback)",
+                 a.tgt.kind, d);
+    return MB_ERR_UNSUPPORTED;
+}
+
+extern "C" int mb_smc_init(mb_ctx* ctx, const mb_target* tgt, float* x, int64_t ld, int64_t n, int64_t n_total,
+                           int sample_prior, float* up, float* lik, float* lw, uint64_t seed, int64_t gid0,
+                           mb_control* ctl, mb_stream_t stream) {
+    MB_REQUIRE(ctx && tgt && x && lik && lw && ctl && n > 0 && ld >= n, "mb_smc_init: bad arguments");
+    SmcArgs a{};
+    a.tgt = *tgt; a.x_in = x; a.x_out = x; a.ld = ld; a.n = n; a.lw = lw; a.up_out = up; a.lik_out = lik;
+    a.seed = seed; a.gid0 = gid0; a.ctl = ctl; a.sample_prior = sample_prior;
+    return smc_dispatch(ctx, a, 1, n_total, mb_s(stream));
+}
+
+extern "C" int mb_smc_move(mb_ctx* ctx, const mb_target* tgt, const mb_move* mv, const float* x_in, float* x_out,
+                           int64_t ld, int64_t n, const int32_t* anc, float* lw, float* up_out, float* lik_out,
+                           float* alpha_out, uint64_t seed, int64_t gid0, mb_control* ctl, mb_stream_t stream) {
+    MB_REQUIRE(ctx && tgt && mv && x_in && x_out && anc && lw && lik_out && ctl && n > 0 && ld >= n && x_in != x_out,
+               "mb_smc_move: bad arguments");
+    MB_REQUIRE(mv->mcmc_steps >= 1 && mv->leapfrog_steps >= 1, "mb_smc_move: mcmc_steps/leapfrog_steps must be >= 1");
+    SmcArgs a{};
+    a.tgt = *tgt; a.mv = *mv; a.x_in = x_in; a.x_out = x_out; a.ld = ld; a.n = n; a.anc = anc; a.lw = lw;
+    a.up_out = up_out; a.lik_out = lik_out; a.alpha_out = alpha_out; a.seed = seed; a.gid0 = gid0; a.ctl = ctl;
+    return smc_dispatch(ctx, a, 0, 0, mb_s(stream));
+}
+
+// potential and gradient of a static target at row-major points (SVGD: vmap(potential_and_grad),
+// transport/svgd.py:99,141-142).  One thread per particle.
+template <int LIK, int D>
+__global__ void __launch_bounds__(MV_THREADS)
+target_pg_kernel(mb_target tgt, float beta, const float* __restrict__ X, int n, float* U, float* G) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float x[D], g[D], up, ul;
+#pragma unroll
+    for (int k = 0; k < D; ++k) x[k] = X[(int64_t)i * D + k];
+    target_eval<LIK, D>(tgt, beta, x, up, ul, g);
+    if (U) U[i] = fmaf(beta, ul, up);
+#pragma unroll
+    for (int k = 0; k < D; ++k) G[(int64_t)i * D + k] = g[k];
+}
+
+extern "C" int mb_target_potential_grad(mb_ctx* ctx, const mb_target* tgt, double beta, const float* X, int n,
+                                        float* U, float* G, mb_stream_t stream) {
+    MB_REQUIRE(ctx && tgt && X && G && n > 0, "mb_target_potential_grad: bad arguments");
+    const int grid = (n + MV_THREADS - 1) / MV_THREADS;
+    const int d = tgt->dim;
+    cudaStream_t st = mb_s(stream);
+#define PG_R(DD) if (tgt->kind == MB_LIK_RASTRIGIN && d == DD) { target_pg_kernel<MB_LIK_RASTRIGIN, DD><<<grid, MV_THREADS, 0, st>>>(*tgt, (float)beta, X, n, U, G); MB_CHECK_LAUNCH(); return MB_OK; }
+#define PG_G(DD) if (tgt->kind == MB_LIK_GAUSSIAN && d == DD && DD <= MB_MAX_SMALL_DIM) { target_pg_kernel<MB_LIK_GAUSSIAN, (DD <= MB_MAX_SMALL_DIM ? DD : 1)><<<grid, MV_THREADS, 0, st>>>(*tgt, (float)beta, X, n, U, G); MB_CHECK_LAUNCH(); return MB_OK; }
+    SMC_DIMS(PG_R)
+    SMC_DIMS(PG_G)
+    mb_set_error("mb_target_potential_grad: unsupported target kind %d / dim %d", tgt->kind, d);
+    return MB_ERR_UNSUPPORTED;
+}
+
+// =================================================================================================
+// bootstrap particle filter
+struct PfArgs {
+    mb_ssm ssm;
+    const float* x_in; float* x_out; int64_t ld; int64_t n; int64_t n_total;
+    const int32_t* anc;
+    const float* y;            // device, dim_obs floats for this time step
+    float* lw;
+    uint64_t seed; uint32_t t; int64_t gid0;
+    double ess_threshold;
+    mb_control* ctl; mb_hist* hist;
+    double* partials; uint32_t* counter;
+    int init;
+};
+
+template <int D>
+__device__ __forceinline__ void lorenz_rhs(const float (&x)[D], float forcing, float (&k)[D]) {
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+        const float xp1 = x[(j + 1) % D], xm1 = x[(j + D - 1) % D], xm2 = x[(j + D - 2) % D];
+        k[j] = fmaf(xp1 - xm2, xm1, forcing - x[j]);                  // lorenz96.py:18-19
+    }
+}
+
+// one classical RK4 step of size h (device definition of the L96 flow)
+template <int D>
+__device__ __forceinline__ void lorenz_rk4(float (&x)[D], float h, float forcing) {
+    float k[D], xt[D], acc[D];
+    lorenz_rhs<D>(x, forcing, k);
+#pragma unroll
+    for (int j = 0; j < D; ++j) { acc[j] = k[j]; xt[j] = fmaf(0.5f * h, k[j], x[j]); }
+    lorenz_rhs<D>(xt, forcing, k);
+#pragma unroll
+    for (int j = 0; j < D; ++j) { acc[j] = fmaf(2.f, k[j], acc[j]); xt[j] = fmaf(0.5f * h, k[j], x[j]); }
+    lorenz_rhs<D>(xt, forcing, k);
+#pragma unroll
+    for (int j = 0; j < D; ++j) { acc[j] = fmaf(2.f, k[j], acc[j]); xt[j] = fmaf(h, k[j], x[j]); }
+    lorenz_rhs<D>(xt, forcing, k);
+#pragma unroll
+    for (int j = 0; j < D; ++j) x[j] = fmaf(h * (1.f / 6.f), acc[j] + k[j], x[j]);
+}
+
+template <int KIND, int D>
+__device__ __forceinline__ float pf_particle(const mb_ssm& m, float (&x)[D], const float (&z)[D], const float* ys,
+                                             bool init) {
+    // returns the log-weight increment -likelihood_potential(x', y)
+    if (KIND == MB_SSM_LINEAR_GAUSSIAN) {
+        float xn[D];
+        if (init) {                                     // linear_gaussian.py:45-50: L0 z + m0
+#pragma unroll
+            for (int r = 0; r < D; ++r) {
+                float acc = m.m0[r];
+#pragma unroll
+                for (int c = 0; c < D; ++c) acc = fmaf(m.L0[r * MB_MAX_SMALL_DIM + c], z[c], acc);
+                xn[r] = acc;
+            }
+        } else {                                        // :86-94: F x + LQ z
+#pragma unroll
+            for (int r = 0; r < D; ++r) {
+                float acc = 0.f;
+#pragma unroll
+                for (int c = 0; c < D; ++c) acc = fmaf(m.F[r * MB_MAX_SMALL_DIM + c], x[c], acc);
+#pragma unroll
+                for (int c = 0; c < D; ++c) acc = fmaf(m.LQ[r * MB_MAX_SMALL_DIM + c], z[c], acc);
+                xn[r] = acc;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < D; ++r) x[r] = xn[r];
+        float diff[D];                                  // :118-128 with utils.py:26-30 (diff @ sqrt_prec)
+#pragma unroll
+        for (int r = 0; r < D; ++r) {
+            float acc = ys[r];
+#pragma unroll
+            for (int c = 0; c < D; ++c) acc = fmaf(-m.H[r * MB_MAX_SMALL_DIM + c], x[c], acc);
+            diff[r] = acc;
+        }
+        float quad = 0.f;
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+            float acc = 0.f;
+#pragma unroll
+            for (int r = 0; r < D; ++r) acc = fmaf(diff[r], m.Rps[r * MB_MAX_SMALL_DIM + c], acc);
+            quad = fmaf(0.5f * acc, acc, quad);
+        }
+        return -(quad + m.lik_const);
+    } else {                                            // Lorenz-96, diagonal noise, H = I
+        if (init) {
+#pragma unroll
+            for (int j = 0; j < D; ++j) x[j] = fmaf(m.init_std, z[j], m.init_mean);
+        } else {
+            const float h = m.dt / (float)m.substeps;
+            for (int s = 0; s < m.substeps; ++s) lorenz_rk4<D>(x, h, m.forcing);
+#pragma unroll
+            for (int j = 0; j < D; ++j) x[j] = fmaf(m.q_std, z[j], x[j]);      // nonlinear_gaussian.py:112-113
+        }
+        const float ir = 1.f / m.r_std;
+        float quad = 0.f;
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+            const float r = (ys[j] - x[j]) * ir;
+            quad = fmaf(0.5f * r, r, quad);
+        }
+        return -(quad + m.lik_const);
+    }
+}
+
+template <int KIND, int D>
+__global__ void __launch_bounds__(MV_THREADS) pf_step_kernel(PfArgs a) {
+    mb_control* ctl = a.ctl;
+    const bool init = a.init != 0;
+    if (!init && ctl->done) return;
+    const bool resample = !init && ctl->resample != 0;
+    __shared__ Lse3 smem[MV_THREADS / 32];
+    __shared__ float ys[D];
+    __shared__ bool is_last;
+    if (threadIdx.x < D) ys[threadIdx.x] = (threadIdx.x < a.ssm.dim_obs) ? a.y[threadIdx.x] : 0.f;
+    __syncthreads();
+
+    // per-thread online LSE accumulator (same association rules as reduce.cu)
+    float am = -INFINITY;
+    double as1 = 0.0, as2 = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t src = resample ? (int64_t)a.anc[i] : i;
+        float x[D], z[D];
+        if (!init) {
+#pragma unroll
+            for (int k = 0; k < D; ++k) x[k] = __ldg(a.x_in + (int64_t)k * a.ld + src);
+        }
+        philox_normals<D>(z, a.seed, (uint64_t)(a.gid0 + i), a.t, init ? MB_P_INIT : MB_P_MOVE, 0u);
+        const float incr = pf_particle<KIND, D>(a.ssm, x, z, ys, init);
+#pragma unroll
+        for (int k = 0; k < D; ++k) a.x_out[(int64_t)k * a.ld + i] = x[k];
+        const float w = ((init || resample) ? 0.f : a.lw[i]) + incr;           // filtering.py:292,303
+        a.lw[i] = w;
+        // online (max, sum, sumsq)
+        if (w > am) {
+            if (am != -INFINITY) { const double f = exp((double)am - (double)w); as1 *= f; as2 *= f * f; }
+            am = w;
+        }
+        if (am != -INFINITY || w != w) {
+            const float e = __expf(w - ((am == -INFINITY) ? 0.f : am));
+            as1 += (double)e; as2 += (double)e * (double)e;
+        }
+    }
+    const Lse3 b = lse3_block_reduce(Lse3{(double)am, as1, as2}, smem);
+    if (threadIdx.x == 0) {
+        a.partials[3 * blockIdx.x] = b.m; a.partials[3 * blockIdx.x + 1] = b.s1; a.partials[3 * blockIdx.x + 2] = b.s2;
+        __threadfence();
+        is_last = (atomicAdd(a.counter, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    Lse3 v = lse3_empty();
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x)
+        v = lse3_merge(v, Lse3{a.partials[3 * i], a.partials[3 * i + 1], a.partials[3 * i + 2]});
+    v = lse3_block_reduce(v, smem);
+    if (threadIdx.x == 0) {
+        *a.counter = 0;
+        mb_control c;
+        if (init) memset(&c, 0, sizeof(c)); else c = *ctl;
+        const double nd = (double)a.n_total;
+        const double lse_prev = (init || resample) ? log(nd) : c.lse;          // log Z convention, SURVEY 8c
+        ctl_set_weights(&c, v);
+        c.log_z = (init ? 0.0 : c.log_z) + (c.lse - lse_prev);
+        c.iter = (int32_t)a.t;
+        c.resampled = resample ? 1 : 0;
+        c.resample = (c.ess < a.ess_threshold * nd) ? 1 : 0;                   // filtering.py:287 (strict <)
+        c.done = 0;
+        *ctl = c;
+        if (a.hist && a.t < MB_HIST_MAX) {
+            mb_hist h;
+            h.beta = 0.0; h.ess = c.ess; h.log_z = c.log_z; h.alpha_mean = 0.0; h.lse = c.lse;
+            h.resampled = c.resampled; h.search_iters = 0;
+            a.hist[a.t] = h;
+        }
+    }
+}
+
+static int pf_dispatch(mb_ctx* ctx, PfArgs& a, cudaStream_t st) {
+    int64_t grid = (a.n + MV_THREADS - 1) / MV_THREADS;
+    int64_t cap = (int64_t)ctx->sms * 8;
+    if (cap > MB_MAX_PARTIAL_BLOCKS) cap = MB_MAX_PARTIAL_BLOCKS;
+    if (grid > cap) grid = cap;
+    a.partials = ctx->partials;
+    a.counter = ctx->counters + MB_CNT_MOVE;
+    const int d = a.ssm.dim;
+#define PF_LG(DD) if (a.ssm.kind == MB_SSM_LINEAR_GAUSSIAN && d == DD) { pf_step_kernel<MB_SSM_LINEAR_GAUSSIAN, DD><<<(unsigned)grid, MV_THREADS, 0, st>>>(a); MB_CHECK_LAUNCH(); return MB_OK; }
+#define PF_L96(DD) if (a.ssm.kind == MB_SSM_LORENZ96 && d == DD) { pf_step_kernel<MB_SSM_LORENZ96, DD><<<(unsigned)grid, MV_THREADS, 0, st>>>(a); MB_CHECK_LAUNCH(); return MB_OK; }
+    PF_LG(1) PF_LG(2) PF_LG(3) PF_LG(4) PF_LG(5) PF_LG(6) PF_LG(8)
+    PF_L96(8) PF_L96(40)
+    mb_set_error("pf: unsupported ssm kind %d / dim %d (built-in device models only; no CPU fallback)", a.ssm.kind, d);
+    return MB_ERR_UNSUPPORTED;
+}
+
+extern "C" int mb_pf_init(mb_ctx* ctx, const mb_ssm* ssm, float* x, int64_t ld, int64_t n, int64_t n_total,
+                          const float* y0, float* lw, uint64_t seed, int64_t gid0, double ess_threshold,
+                          mb_control* ctl, mb_hist* hist, mb_stream_t stream) {
+    MB_REQUIRE(ctx && ssm && x && y0 && lw && ctl && n > 0 && ld >= n, "mb_pf_init: bad arguments");
+    MB_REQUIRE(ssm->dim_obs <= ssm->dim, "mb_pf_init: dim_obs must be <= dim");
+    PfArgs a{};
+    a.ssm = *ssm; a.x_in = x; a.x_out = x; a.ld = ld; a.n = n; a.n_total = n_total; a.y = y0; a.lw = lw;
+    a.seed = seed; a.t = 0; a.gid0 = gid0; a.ess_threshold = ess_threshold; a.ctl = ctl; a.hist = hist; a.init = 1;
+    return pf_dispatch(ctx, a, mb_s(stream));
+}
+
+extern "C" int mb_pf_step(mb_ctx* ctx, const mb_ssm* ssm, const float* x_in, float* x_out, int64_t ld, int64_t n,
+                          int64_t n_total, const int32_t* anc, const float* y, float* lw, uint64_t seed, uint32_t t,
+                          int64_t gid0, double ess_threshold, mb_control* ctl, mb_hist* hist, mb_stream_t stream) {
+    MB_REQUIRE(ctx && ssm && x_in && x_out && anc && y && lw && ctl && n > 0 && ld >= n && x_in != x_out,
+               "mb_pf_step: bad arguments");
+    MB_REQUIRE(ssm->dim_obs <= ssm->dim && ssm->substeps >= 1, "mb_pf_step: bad model");
+    PfArgs a{};
+    a.ssm = *ssm; a.x_in = x_in; a.x_out = x_out; a.ld = ld; a.n = n; a.n_total = n_total; a.anc = anc; a.y = y;
+    a.lw = lw; a.seed = seed; a.t = t; a.gid0 = gid0; a.ess_threshold = ess_threshold; a.ctl = ctl; a.hist = hist;
+    a.init = 0;
+    return pf_dispatch(ctx, a, mb_s(stream));
+}

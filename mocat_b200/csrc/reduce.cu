@@ -1,0 +1,396 @@
+// reduce.cu -- K2 (log-sum-exp / ESS), K3 (on-device adaptive tempering), column statistics,
+// weighted moments and the radix-select quantile (K7).
+//
+// All kernels are HBM-bound streaming reductions: 128-bit loads, fp32 exponentials, fp64 accumulation,
+// deterministic two-level reduction (per-block partials merged in fixed order by the last block / by
+// every block after a grid sync) -- no floating-point atomics anywhere.
+#include <cooperative_groups.h>
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+#define RED_THREADS 256
+
+// ------------------------------------------------------------------------------------------------
+// per-thread online accumulator of (max, sum e^{w-max}, sum e^{2(w-max)})
+struct LseAcc {
+    float m;
+    double s1, s2;
+};
+
+__device__ __forceinline__ void acc_rescale(LseAcc& a, float cm) {
+    if (cm > a.m) {
+        if (a.m != -INFINITY) {
+            const double f = exp((double)a.m - (double)cm);
+            a.s1 *= f;
+            a.s2 *= f * f;
+        }
+        a.m = cm;
+    }
+}
+
+__device__ __forceinline__ void acc_add4(LseAcc& a, float w0, float w1, float w2, float w3) {
+    acc_rescale(a, fmaxf(fmaxf(w0, w1), fmaxf(w2, w3)));
+    const bool any_nan = (w0 != w0) | (w1 != w1) | (w2 != w2) | (w3 != w3);
+    if (a.m == -INFINITY && !any_nan) return;
+    const float mm = (a.m == -INFINITY) ? 0.f : a.m;
+    const float e0 = __expf(w0 - mm), e1 = __expf(w1 - mm), e2 = __expf(w2 - mm), e3 = __expf(w3 - mm);
+    a.s1 += (double)((e0 + e1) + (e2 + e3));
+    a.s2 += (double)((e0 * e0 + e1 * e1) + (e2 * e2 + e3 * e3));
+}
+
+__device__ __forceinline__ void acc_add1(LseAcc& a, float w) {
+    acc_rescale(a, w);
+    if (a.m == -INFINITY && w == w) return;
+    const float mm = (a.m == -INFINITY) ? 0.f : a.m;
+    const float e = __expf(w - mm);
+    a.s1 += (double)e;
+    a.s2 += (double)(e * e);
+}
+
+// One streaming pass over this block's share of the weights lw - dbeta*lik (lik may be NULL).
+// Returns the block-level triple in thread 0.
+__device__ __forceinline__ Lse3 lse_block_pass(const float* __restrict__ lw, const float* __restrict__ lik,
+                                               float dbeta, int64_t n, Lse3* smem) {
+    LseAcc a{-INFINITY, 0.0, 0.0};
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    const bool aligned = (((uintptr_t)lw & 15) == 0) && (lik == nullptr || ((uintptr_t)lik & 15) == 0);
+    int64_t done = 0;
+    if (aligned) {
+        const int64_t n4 = n >> 2;
+        const float4* lw4 = reinterpret_cast<const float4*>(lw);
+        const float4* lk4 = reinterpret_cast<const float4*>(lik);
+        for (int64_t i = tid; i < n4; i += nthreads) {
+            float4 w = __ldg(lw4 + i);
+            if (lik) {
+                const float4 l = __ldg(lk4 + i);
+                w.x = fmaf(-dbeta, l.x, w.x); w.y = fmaf(-dbeta, l.y, w.y);
+                w.z = fmaf(-dbeta, l.z, w.z); w.w = fmaf(-dbeta, l.w, w.w);
+            }
+            acc_add4(a, w.x, w.y, w.z, w.w);
+        }
+        done = n4 << 2;
+    }
+    for (int64_t i = done + tid; i < n; i += nthreads) {
+        float w = lw[i];
+        if (lik) w = fmaf(-dbeta, lik[i], w);
+        acc_add1(a, w);
+    }
+    return lse3_block_reduce(Lse3{(double)a.m, a.s1, a.s2}, smem);
+}
+
+// merge `count` partial triples in a fixed order; result broadcast to all threads of the block
+__device__ __forceinline__ Lse3 lse_merge_partials(const double* __restrict__ partials, int count, Lse3* smem) {
+    Lse3 v = lse3_empty();
+    for (int i = threadIdx.x; i < count; i += blockDim.x) {
+        const Lse3 p{partials[3 * i], partials[3 * i + 1], partials[3 * i + 2]};
+        v = lse3_merge(v, p);
+    }
+    v = lse3_block_reduce(v, smem);
+    __shared__ Lse3 bc;
+    if (threadIdx.x == 0) bc = v;
+    __syncthreads();
+    v = bc;
+    __syncthreads();
+    return v;
+}
+
+__device__ __forceinline__ void write_out6(double* out6, const Lse3& r) {
+    mb_control tmp;
+    ctl_set_weights(&tmp, r);
+    out6[0] = tmp.wmax; out6[1] = tmp.s1; out6[2] = tmp.s2;
+    out6[3] = tmp.lse;  out6[4] = tmp.lse2; out6[5] = tmp.log_ess;
+}
+
+// ------------------------------------------------------------------------------------------------ K2
+__global__ void __launch_bounds__(RED_THREADS)
+lse_ess_kernel(const float* __restrict__ lw, const float* __restrict__ lik, float dbeta, int64_t n,
+               double* partials, uint32_t* counter, double* out6) {
+    __shared__ Lse3 smem[RED_THREADS / 32];
+    __shared__ bool is_last;
+    const Lse3 b = lse_block_pass(lw, lik, dbeta, n, smem);
+    if (threadIdx.x == 0) {
+        partials[3 * blockIdx.x] = b.m; partials[3 * blockIdx.x + 1] = b.s1; partials[3 * blockIdx.x + 2] = b.s2;
+        __threadfence();
+        const uint32_t t = atomicAdd(counter, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    const Lse3 r = lse_merge_partials(partials, gridDim.x, smem);
+    if (threadIdx.x == 0) {
+        write_out6(out6, r);
+        *counter = 0;                                    // self-reset for the next launch
+    }
+}
+
+static int reduce_grid(const mb_ctx* ctx, int64_t n) {
+    int64_t blocks = (n + (int64_t)RED_THREADS * 16 - 1) / ((int64_t)RED_THREADS * 16);
+    int64_t cap = (int64_t)ctx->sms * 8;
+    if (cap > MB_MAX_PARTIAL_BLOCKS) cap = MB_MAX_PARTIAL_BLOCKS;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+extern "C" int mb_lse_ess(mb_ctx* ctx, const float* lw, const float* lik, double dbeta, int64_t n,
+                          double* out6, mb_stream_t stream) {
+    MB_REQUIRE(ctx && lw && out6 && n >= 0, "mb_lse_ess: bad arguments");
+    const int grid = reduce_grid(ctx, n);
+    lse_ess_kernel<<<grid, RED_THREADS, 0, mb_s(stream)>>>(lw, lik, (float)dbeta, n, ctx->partials,
+                                                          ctx->counters + MB_CNT_REDUCE, out6);
+    MB_CHECK_LAUNCH();
+    return MB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ K3
+// Persistent cooperative kernel: the whole regula-falsi search of utils.py:205-237 runs on the device,
+// one streaming pass + one grid sync per evaluation; every block merges the same partials in the same
+// order, so all blocks take identical decisions without a second sync.
+struct TemperArgs {
+    float* lw;
+    const float* lik;
+    int64_t n;
+    mb_temper prm;
+    int advance_iter;
+    int64_t nan_denominator;
+    int64_t n_total;
+    mb_control* ctl;
+    mb_hist* hist;
+    double* partials;      // [2][MB_MAX_PARTIAL_BLOCKS][3]
+};
+
+__device__ __forceinline__ double lse3_log_ess(const Lse3& r) {
+    const double mm = (r.m == -INFINITY || r.m == INFINITY) ? 0.0 : r.m;
+    return 2.0 * (log(r.s1) + mm) - (log(r.s2) + 2.0 * mm);
+}
+
+__global__ void __launch_bounds__(RED_THREADS)
+temper_adapt_kernel(TemperArgs a) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ Lse3 smem[RED_THREADS / 32];
+    mb_control c0 = *a.ctl;                             // read before the first grid sync (see below)
+    if (c0.done) return;                                // uniform over the grid: done only changes at the end
+    if (a.advance_iter && c0.resampled) {               // the move kernel resampled: weights were reset to 0,
+        const double nd = (double)a.n_total;            // ess to n (transport/smc.py:69-70)
+        c0.wmax = 0.0; c0.s1 = nd; c0.s2 = nd;
+        c0.lse = log(nd); c0.lse2 = log(nd); c0.log_ess = log(nd); c0.ess = nd;
+    }
+    const mb_temper& P = a.prm;
+    const double beta = c0.beta;
+    const int iter_new = c0.iter + (a.advance_iter ? 1 : 0);
+    int parity = 0;
+
+    auto evaluate = [&](double b) -> Lse3 {
+        const float dbeta = (float)(b - beta);
+        const Lse3 blk = lse_block_pass(a.lw, a.lik, dbeta, a.n, smem);
+        double* part = a.partials + (size_t)parity * 3 * MB_MAX_PARTIAL_BLOCKS;
+        if (threadIdx.x == 0) {
+            part[3 * blockIdx.x] = blk.m; part[3 * blockIdx.x + 1] = blk.s1; part[3 * blockIdx.x + 2] = blk.s2;
+        }
+        grid.sync();
+        const Lse3 r = lse_merge_partials(part, gridDim.x, smem);
+        parity ^= 1;
+        return r;
+    };
+
+    double b_new;
+    Lse3 t_new;
+    int it = 0;
+    if (P.schedule != nullptr) {                         // transport/smc.py:123
+        int idx = iter_new < P.schedule_len ? iter_new : P.schedule_len - 1;
+        b_new = P.schedule[idx];
+        t_new = evaluate(b_new);
+    } else {                                             // transport/smc.py:311-326 + utils.py:205-237
+        const double log_target = log(c0.ess * P.ess_retain);
+        double b0 = beta, b1 = P.max_temperature;
+        Lse3 t0{c0.wmax, c0.s1, c0.s2};
+        double e0 = c0.log_ess - log_target;
+        Lse3 t1 = evaluate(b1);
+        double e1 = lse3_log_ess(t1) - log_target;
+        const bool increasing = e1 > e0;
+        while (!(fmin(fabs(e0), fabs(e1)) < P.tol || it >= P.max_search_iter || (e0 < 0 && e1 < 0) ||
+                 (e0 > 0 && e1 > 0) || e0 != e0 || e1 != e1)) {
+            const double x = b0 - e0 * (b1 - b0) / (e1 - e0);
+            const Lse3 tx = evaluate(x);
+            const double ex = lse3_log_ess(tx) - log_target;
+            const bool upper = increasing ? (ex > 0) : (ex < 0);
+            if (upper) { b1 = x; e1 = ex; t1 = tx; } else { b0 = x; e0 = ex; t0 = tx; }
+            ++it;
+        }
+        // jnp.argmin(jnp.abs(evals)): first index on ties, NaN wins
+        const bool pick0 = (e0 != e0) || (!(e1 != e1) && fabs(e0) <= fabs(e1));
+        b_new = pick0 ? b0 : b1;
+        t_new = pick0 ? t0 : t1;
+    }
+
+    // weight update  lw += -(beta' - beta) * lik   (transport/smc.py:201-203, 367-373)
+    {
+        const float dbeta = (float)(b_new - beta);
+        const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+        if (dbeta != 0.f) {
+            const bool aligned = (((uintptr_t)a.lw & 15) == 0) && (((uintptr_t)a.lik & 15) == 0);
+            int64_t done = 0;
+            if (aligned) {
+                const int64_t n4 = a.n >> 2;
+                float4* lw4 = reinterpret_cast<float4*>(a.lw);
+                const float4* lk4 = reinterpret_cast<const float4*>(a.lik);
+                for (int64_t i = tid; i < n4; i += nthreads) {
+                    float4 w = lw4[i];
+                    const float4 l = __ldg(lk4 + i);
+                    w.x = fmaf(-dbeta, l.x, w.x); w.y = fmaf(-dbeta, l.y, w.y);
+                    w.z = fmaf(-dbeta, l.z, w.z); w.w = fmaf(-dbeta, l.w, w.w);
+                    lw4[i] = w;
+                }
+                done = n4 << 2;
+            }
+            for (int64_t i = done + tid; i < a.n; i += nthreads) a.lw[i] = fmaf(-dbeta, a.lik[i], a.lw[i]);
+        }
+    }
+
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        mb_control c = c0;
+        const double lse_prev = c0.lse;
+        ctl_set_weights(&c, t_new);
+        c.log_z = c0.log_z + (c.lse - lse_prev);         // transport/smc.py:212-215
+        c.beta = b_new;
+        c.iter = iter_new;
+        c.search_iters = it;
+        c.resample = (c.ess <= P.ess_resample * (double)a.n_total) ? 1 : 0;          // smc.py:298-301
+        const double nan_frac = a.nan_denominator > 0 ? (double)c0.nan_count / (double)a.nan_denominator : 0.0;
+        c.done = (b_new >= P.max_temperature || iter_new >= P.max_iter || nan_frac > 0.1) ? 1 : 0;  // :171-175
+        c.nan_count = 0;
+        if (a.advance_iter) c.alpha_mean = (double)c0.alpha_fx / 4294967296.0 / (double)a.n_total;
+        c.alpha_fx = 0;
+        *a.ctl = c;
+        if (a.hist && iter_new < MB_HIST_MAX) {
+            mb_hist h;
+            h.beta = c.beta; h.ess = c.ess; h.log_z = c.log_z; h.alpha_mean = c.alpha_mean; h.lse = c.lse;
+            h.resampled = c0.resampled; h.search_iters = it;
+            a.hist[iter_new] = h;
+        }
+    }
+}
+
+extern "C" int mb_temper_adapt(mb_ctx* ctx, float* lw, const float* lik, int64_t n, const mb_temper* prm,
+                               int advance_iter, int64_t nan_denominator, int64_t n_total, mb_control* ctl,
+                               mb_hist* hist, mb_stream_t stream) {
+    MB_REQUIRE(ctx && lw && lik && prm && ctl && n > 0, "mb_temper_adapt: bad arguments");
+    static int blocks_per_sm = 0;
+    if (blocks_per_sm == 0) {
+        MB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, temper_adapt_kernel, RED_THREADS, 0));
+        if (blocks_per_sm < 1) { mb_set_error("temper kernel cannot be resident"); return MB_ERR_CUDA; }
+    }
+    int64_t grid = (int64_t)blocks_per_sm * ctx->sms;
+    const int64_t need = (n + (int64_t)RED_THREADS * 8 - 1) / ((int64_t)RED_THREADS * 8);
+    if (grid > need) grid = need;
+    if (grid > MB_MAX_PARTIAL_BLOCKS) grid = MB_MAX_PARTIAL_BLOCKS;
+    if (grid < 1) grid = 1;
+    TemperArgs args{lw, lik, n, *prm, advance_iter, nan_denominator, n_total > 0 ? n_total : n, ctl, hist, ctx->partials};
+    void* kargs[] = {&args};
+    MB_CUDA(cudaLaunchCooperativeKernel((void*)temper_adapt_kernel, dim3((unsigned)grid), dim3(RED_THREADS), kargs, 0,
+                                        mb_s(stream)));
+    return MB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// column statistics: per-dimension mean and ddof=1 variance over all n particles (abc/smc.py:97),
+// or weighted by exp(lw - wmax) when lw != NULL.  One block column-slab per blockIdx.y = column.
+__global__ void __launch_bounds__(RED_THREADS)
+colstats_kernel(const float* __restrict__ x, int64_t ld, int64_t n, const float* __restrict__ lw,
+                const mb_control* ctl, double* partials /*[d][gridDim.x][3]*/) {
+    __shared__ double smem[RED_THREADS / 32];
+    const int col = blockIdx.y;
+    const float* xc = x + (int64_t)col * ld;
+    const float shift = xc[0];
+    const float wmax = lw ? (float)ctl->wmax : 0.f;
+    double s0 = 0, s1 = 0, s2 = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float v = xc[i] - shift;
+        const float w = lw ? __expf(lw[i] - wmax) : 1.f;
+        if (w > 0.f) { s0 += w; s1 += (double)w * v; s2 += (double)w * v * v; }
+    }
+    s0 = block_sum_d(s0, smem); s1 = block_sum_d(s1, smem); s2 = block_sum_d(s2, smem);
+    if (threadIdx.x == 0) {
+        double* p = partials + ((size_t)col * gridDim.x + blockIdx.x) * 3;
+        p[0] = s0; p[1] = s1; p[2] = s2;
+    }
+}
+
+__global__ void colstats_finish_kernel(const float* __restrict__ x, int64_t ld, const double* partials, int nblocks,
+                                       int weighted, double* mean, double* var) {
+    const int col = blockIdx.x;
+    if (threadIdx.x != 0) return;
+    double s0 = 0, s1 = 0, s2 = 0;
+    for (int b = 0; b < nblocks; ++b) {
+        const double* p = partials + ((size_t)col * nblocks + b) * 3;
+        s0 += p[0]; s1 += p[1]; s2 += p[2];
+    }
+    const double shift = (double)x[(int64_t)col * ld];
+    const double m = s1 / s0;
+    mean[col] = m + shift;
+    if (var) var[col] = weighted ? (s2 / s0 - m * m) : (s2 - s0 * m * m) / (s0 - 1.0);
+}
+
+static int colstats_impl(mb_ctx* ctx, const float* x, int64_t ld, int64_t n, int d, const float* lw,
+                         const mb_control* ctl, double* mean, double* var, cudaStream_t st) {
+    int gx = reduce_grid(ctx, n);
+    if (gx > 256) gx = 256;
+    const size_t bytes = (size_t)d * gx * 3 * sizeof(double);
+    if (mb_ensure_scratch(ctx, bytes) != MB_OK) return MB_ERR_CUDA;
+    colstats_kernel<<<dim3(gx, d), RED_THREADS, 0, st>>>(x, ld, n, lw, ctl, (double*)ctx->scratch);
+    MB_CHECK_LAUNCH();
+    colstats_finish_kernel<<<d, 32, 0, st>>>(x, ld, (const double*)ctx->scratch, gx, lw != nullptr, mean, var);
+    MB_CHECK_LAUNCH();
+    return MB_OK;
+}
+
+extern "C" int mb_colstats(mb_ctx* ctx, const float* x, int64_t ld, int64_t n, int d, double* mean, double* var,
+                           mb_stream_t stream) {
+    MB_REQUIRE(ctx && x && mean && n > 1 && d > 0, "mb_colstats: bad arguments");
+    return colstats_impl(ctx, x, ld, n, d, nullptr, nullptr, mean, var, mb_s(stream));
+}
+
+extern "C" int mb_weighted_moments(mb_ctx* ctx, const float* x, int64_t ld, int64_t n, int d, const float* lw,
+                                   const mb_control* ctl, double* mean, double* var, mb_stream_t stream) {
+    MB_REQUIRE(ctx && x && lw && ctl && mean && n > 0 && d > 0, "mb_weighted_moments: bad arguments");
+    return colstats_impl(ctx, x, ld, n, d, lw, ctl, mean, var, mb_s(stream));
+}
+
+// ------------------------------------------------------------------------------------------------ K7
+// Exact order statistics by 3-pass radix select on the order-preserving integer image of fp32
+// (11 + 11 + 10 bits), then one pass for the next-larger value: linear-interpolated quantile exactly
+// as jnp.quantile (abc/smc.py:166) without sorting.  Integer histograms -> deterministic.
+#include "select.cuh"
+
+int mb_quantile_impl(mb_ctx* ctx, const float* v, int64_t n, const double* q_dev, double q_host, double* out3,
+                     cudaStream_t st) {
+    // scratch: SelectState | frac[2] | hist[2048]
+    const size_t bytes = 256 + 2048 * sizeof(uint32_t);
+    if (mb_ensure_scratch(ctx, (1u << 20) + bytes) != MB_OK) return MB_ERR_CUDA;
+    char* base = (char*)ctx->scratch + (1u << 20);       // [0, 1 MiB) is the colstats partial area
+    SelectState* state = (SelectState*)base;
+    double* frac = (double*)(base + 64);
+    uint32_t* hist = (uint32_t*)(base + 256);
+    MB_CUDA(cudaMemsetAsync(hist, 0, 2048 * sizeof(uint32_t), st));
+    const int grid = reduce_grid(ctx, n);
+    select_rank_kernel<<<1, 1, 0, st>>>(state, q_dev, q_host, n, frac);
+    select_hist_kernel<21, 11, 0><<<grid, RED_THREADS, 0, st>>>(v, n, state, hist);
+    select_pick_kernel<21, 11><<<1, 256, 0, st>>>(state, hist);
+    select_hist_kernel<10, 11, 11><<<grid, RED_THREADS, 0, st>>>(v, n, state, hist);
+    select_pick_kernel<10, 11><<<1, 256, 0, st>>>(state, hist);
+    select_hist_kernel<0, 10, 22><<<grid, RED_THREADS, 0, st>>>(v, n, state, hist);
+    select_pick_kernel<0, 10><<<1, 256, 0, st>>>(state, hist);
+    select_next_kernel<<<grid, RED_THREADS, 0, st>>>(v, n, state);
+    select_finish_dev_kernel<<<1, 1, 0, st>>>(state, frac, out3);
+    MB_CHECK_LAUNCH();
+    return MB_OK;
+}
+
+extern "C" int mb_quantile(mb_ctx* ctx, const float* v, int64_t n, double q, double* out, mb_stream_t stream) {
+    MB_REQUIRE(ctx && v && out && n > 0, "mb_quantile: bad arguments");
+    return mb_quantile_impl(ctx, v, n, nullptr, q, out, mb_s(stream));
+}

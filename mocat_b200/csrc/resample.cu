@@ -1,0 +1,348 @@
+// resample.cu -- K4 (exact-fp64 CDF by single-pass decoupled look-back scan), K5 (ancestor search),
+// K6 (SoA gather).  Replaces the O(n^2) Gumbel-max `random.categorical` + `cdict.__getitem__` of the
+// reference (transport/smc.py:61-71, ssm/filtering.py:196-199, core.py:46-56).
+//
+// Exact-fp64 convention: weights are quantised to multiples of 2^-52,
+//     q_i = rint(w_i * scale) * 2^-52,   scale = 2^52 (1 + 2^-24) / sum(w)   (or caller supplied),
+// so every fp64 partial sum (< 2) is exactly representable: fp64 addition is associative on these
+// values, the scan result is independent of tile order / look-back timing / GPU sharding and equals
+// the sequential numpy cumsum bit for bit.  cdf = min(cumsum, 1), cdf[n-1] = 1.
+#include "common.cuh"
+#include "rng.cuh"
+
+#define SCAN_THREADS 256
+#define SCAN_ITEMS 16
+#define SCAN_TILE (SCAN_THREADS * SCAN_ITEMS)
+
+#define ST_INVALID 0
+#define ST_AGG 1
+#define ST_INCL 2
+
+__device__ __forceinline__ int ld_acquire(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ double ld_relaxed_d(const double* p) {
+    double v;
+    asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+
+struct ScanArgs {
+    const float* in;          // lw (log mode) or w (linear mode)
+    int64_t n;
+    int log_mode;             // 1: w = exp(lw - ctl->wmax), scale from ctl->s1
+    double scale;             // linear mode
+    const mb_control* ctl;    // may be NULL in linear mode
+    int predicated;           // 1: run only if ctl->resample && !ctl->done
+    double* cdf;
+    int32_t* flag; double* agg; double* incl;
+    uint32_t epoch;
+    uint32_t* tile_counter; uint32_t* done_counter;
+    int64_t num_tiles;
+};
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_cdf_kernel(ScanArgs a) {
+    if (a.predicated && (a.ctl->done || !a.ctl->resample)) return;
+    __shared__ double warp_tot[SCAN_THREADS / 32];
+    __shared__ double tile_prefix_s;
+    __shared__ unsigned tile_s;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    double scale;
+    float wmax = 0.f;
+    if (a.log_mode) {
+        wmax = (float)a.ctl->wmax;
+        if (!(wmax > -INFINITY) || wmax == INFINITY) wmax = 0.f;
+        scale = 4503599627370496.0 * (1.0 + 5.9604644775390625e-8) / a.ctl->s1;
+    } else {
+        scale = a.scale;
+    }
+    const int st_base = (int)(a.epoch << 2);
+
+    while (true) {
+        if (threadIdx.x == 0) tile_s = atomicAdd(a.tile_counter, 1u);
+        __syncthreads();
+        const int64_t tile = tile_s;
+        if (tile >= a.num_tiles) break;
+        const int64_t base = tile * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+
+        // ---- load 16 consecutive items per thread (4 x 128-bit), quantise
+        double q[SCAN_ITEMS];
+        const bool full = (base + SCAN_ITEMS <= a.n) && (((uintptr_t)a.in & 15) == 0);
+        if (full) {
+            const float4* p = reinterpret_cast<const float4*>(a.in + base);
+#pragma unroll
+            for (int k = 0; k < SCAN_ITEMS / 4; ++k) {
+                const float4 v = __ldcs(p + k);
+                q[4 * k + 0] = v.x; q[4 * k + 1] = v.y; q[4 * k + 2] = v.z; q[4 * k + 3] = v.w;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < SCAN_ITEMS; ++k)
+                q[k] = (base + k < a.n) ? (double)a.in[base + k] : (a.log_mode ? -INFINITY : 0.0);
+        }
+        double run = 0.0;
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k) {
+            float w = (float)q[k];
+            if (a.log_mode) {
+                w = __expf(w - wmax);
+                if (w != w) w = 0.f;
+            }
+            const double qq = rint((double)w * scale) * 2.220446049250313e-16;
+            run += qq;
+            q[k] = run;                                   // thread-local inclusive
+        }
+        // ---- warp + block exclusive offsets (exact arithmetic: any association is the same)
+        double incl_w = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double t = __shfl_up_sync(MB_FULL, incl_w, o);
+            if (lane >= o) incl_w += t;
+        }
+        if (lane == 31) warp_tot[warp] = incl_w;
+        __syncthreads();
+        double warp_off = 0.0, tile_total = 0.0;
+#pragma unroll
+        for (int w = 0; w < SCAN_THREADS / 32; ++w) {
+            const double t = warp_tot[w];
+            if (w < warp) warp_off += t;
+            tile_total += t;
+        }
+        const double thread_off = warp_off + (incl_w - run);
+
+        // ---- decoupled look-back (warp 0)
+        if (warp == 0) {
+            double prefix = 0.0;
+            if (tile == 0) {
+                if (lane == 0) {
+                    a.incl[0] = tile_total;
+                    __threadfence();
+                    st_release(a.flag + 0, st_base | ST_INCL);
+                }
+            } else {
+                if (lane == 0) {
+                    a.agg[tile] = tile_total;
+                    __threadfence();
+                    st_release(a.flag + tile, st_base | ST_AGG);
+                }
+                int64_t look = tile - 1;
+                while (true) {
+                    const int64_t idx = look - lane;
+                    int f = st_base | ST_INCL;               // lanes before tile 0 behave as "inclusive 0"
+                    double val = 0.0;
+                    if (idx >= 0) {
+                        do { f = ld_acquire(a.flag + idx); } while ((f >> 2) != (int)a.epoch || (f & 3) == ST_INVALID);
+                        val = ((f & 3) == ST_INCL) ? ld_relaxed_d(a.incl + idx) : ld_relaxed_d(a.agg + idx);
+                    }
+                    const unsigned incl_mask = __ballot_sync(MB_FULL, (f & 3) == ST_INCL);
+                    const int first = incl_mask ? (__ffs(incl_mask) - 1) : 32;
+                    double contrib = (lane <= first) ? val : 0.0;
+                    contrib = warp_sum_d(contrib);
+                    contrib = __shfl_sync(MB_FULL, contrib, 0);
+                    prefix += contrib;
+                    if (incl_mask) break;
+                    look -= 32;
+                }
+                if (lane == 0) {
+                    a.incl[tile] = prefix + tile_total;
+                    __threadfence();
+                    st_release(a.flag + tile, st_base | ST_INCL);
+                }
+            }
+            if (lane == 0) tile_prefix_s = prefix;
+        }
+        __syncthreads();
+        const double off = tile_prefix_s + thread_off;
+
+        // ---- write cdf = min(off + local, 1); last element forced to 1
+        if (base + SCAN_ITEMS <= a.n && (((uintptr_t)a.cdf & 15) == 0)) {
+            double2* o2 = reinterpret_cast<double2*>(a.cdf + base);
+#pragma unroll
+            for (int k = 0; k < SCAN_ITEMS / 2; ++k) {
+                double c0 = fmin(off + q[2 * k], 1.0), c1 = fmin(off + q[2 * k + 1], 1.0);
+                if (base + 2 * k + 1 == a.n - 1) c1 = 1.0;
+                __stcs(o2 + k, make_double2(c0, c1));
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < SCAN_ITEMS; ++k)
+                if (base + k < a.n) a.cdf[base + k] = (base + k == a.n - 1) ? 1.0 : fmin(off + q[k], 1.0);
+        }
+        __syncthreads();
+    }
+    // every block fetches exactly one terminating tile id; the last block to exit resets the counters
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(a.done_counter, 1u);
+        if (t == gridDim.x - 1) {
+            *a.done_counter = 0;
+            *a.tile_counter = 0;
+        }
+    }
+}
+
+static int scan_launch(mb_ctx* ctx, ScanArgs& a, cudaStream_t st) {
+    a.num_tiles = (a.n + SCAN_TILE - 1) / SCAN_TILE;
+    MB_REQUIRE(a.num_tiles < 0xffff0000ll, "scan: too many tiles");
+    if (mb_ensure_scan(ctx, a.num_tiles) != MB_OK) return MB_ERR_CUDA;
+    a.flag = ctx->scan_flag; a.agg = ctx->scan_agg; a.incl = ctx->scan_incl;
+    ctx->scan_epoch = (ctx->scan_epoch + 1) & 0x1fffffffu;
+    if (ctx->scan_epoch == 0) ctx->scan_epoch = 1;
+    a.epoch = ctx->scan_epoch;
+    a.tile_counter = ctx->counters + MB_CNT_SCAN_TILE;
+    a.done_counter = ctx->counters + MB_CNT_SCAN_DONE;
+    int64_t grid = (int64_t)ctx->sms * 6;                 // resident-sized grid, tiles fetched dynamically
+    if (grid > a.num_tiles) grid = a.num_tiles;
+    if (grid > 0xffff) grid = 0xffff;
+    if (grid < 1) grid = 1;
+    scan_cdf_kernel<<<(unsigned)grid, SCAN_THREADS, 0, st>>>(a);
+    MB_CHECK_LAUNCH();
+    return MB_OK;
+}
+
+extern "C" int mb_cumsum_lw(mb_ctx* ctx, const float* lw, int64_t n, const mb_control* ctl, int force,
+                            double* cdf, mb_stream_t stream) {
+    MB_REQUIRE(ctx && lw && ctl && cdf && n > 0, "mb_cumsum_lw: bad arguments");
+    ScanArgs a{};
+    a.in = lw; a.n = n; a.log_mode = 1; a.scale = 0; a.ctl = ctl; a.predicated = force ? 0 : 1; a.cdf = cdf;
+    return scan_launch(ctx, a, mb_s(stream));
+}
+
+extern "C" int mb_cumsum_f32(mb_ctx* ctx, const float* w, int64_t n, double scale, double* cdf, mb_stream_t stream) {
+    MB_REQUIRE(ctx && w && cdf && n > 0 && scale > 0, "mb_cumsum_f32: bad arguments");
+    ScanArgs a{};
+    a.in = w; a.n = n; a.log_mode = 0; a.scale = scale; a.ctl = nullptr; a.predicated = 0; a.cdf = cdf;
+    return scan_launch(ctx, a, mb_s(stream));
+}
+
+// ------------------------------------------------------------------------------------------------ K5
+// upper_bound: smallest j in [lo, hi) with cdf[j] > u (hi if none)
+__device__ __forceinline__ int64_t upper_bound_g(const double* __restrict__ cdf, int64_t lo, int64_t hi, double u) {
+    while (lo < hi) {
+        const int64_t mid = lo + ((hi - lo) >> 1);
+        if (__ldg(cdf + mid) > u) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+__device__ __forceinline__ int upper_bound_s(const double* s, int lo, int hi, double u) {
+    while (lo < hi) {
+        const int mid = lo + ((hi - lo) >> 1);
+        if (s[mid] > u) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+
+#define ANC_THREADS 256
+#define ANC_ITEMS 8
+#define ANC_BLOCK_OUT (ANC_THREADS * ANC_ITEMS)
+#define ANC_SMEM_CAP 5120        // doubles (40 KiB)
+
+struct AncArgs {
+    const double* cdf; int64_t n;
+    const double* u;            // NULL => Philox
+    uint64_t seed; uint32_t step; int64_t gid0;
+    int32_t* anc; int64_t n_out;
+    const mb_control* ctl;
+};
+
+// Systematic: u_i = (i + u0)/n_out is monotone in i, so a block of outputs maps to one contiguous
+// window of the CDF: two full binary searches per block find the window, it is staged in shared
+// memory (coalesced), and the per-output searches run there.
+__global__ void __launch_bounds__(ANC_THREADS)
+ancestors_systematic_kernel(AncArgs a) {
+    if (a.ctl && (a.ctl->done || !a.ctl->resample)) return;
+    __shared__ double win[ANC_SMEM_CAP];
+    __shared__ int64_t w_lo, w_hi;
+    double u0;
+    if (a.u) u0 = a.u[0];
+    else { const Philox4 r = philox_raw(a.seed, 0ull, a.step, MB_P_RESAMPLE, 0u); u0 = u53(r.x, r.y); }
+    const double nd = (double)a.n_out;
+    for (int64_t b0 = (int64_t)blockIdx.x * ANC_BLOCK_OUT; b0 < a.n_out; b0 += (int64_t)gridDim.x * ANC_BLOCK_OUT) {
+        const int64_t b1 = min(b0 + (int64_t)ANC_BLOCK_OUT, a.n_out);
+        if (threadIdx.x == 0) w_lo = upper_bound_g(a.cdf, 0, a.n, ((double)b0 + u0) / nd);
+        if (threadIdx.x == 32) w_hi = upper_bound_g(a.cdf, 0, a.n, ((double)(b1 - 1) + u0) / nd);
+        __syncthreads();
+        const int64_t lo = w_lo;
+        const int64_t hi = min(w_hi, a.n - 1);            // inclusive upper end of the window
+        const int64_t len = hi - lo + 1;
+        const bool staged = len <= ANC_SMEM_CAP;
+        if (staged) {
+            for (int64_t k = threadIdx.x; k < len; k += ANC_THREADS) win[k] = __ldg(a.cdf + lo + k);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < ANC_ITEMS; ++k) {
+            const int64_t i = b0 + (int64_t)k * ANC_THREADS + threadIdx.x;
+            if (i < b1) {
+                const double u = ((double)i + u0) / nd;
+                int64_t j;
+                if (staged) j = lo + upper_bound_s(win, 0, (int)len, u);
+                else j = upper_bound_g(a.cdf, lo, hi + 1, u);
+                if (j > a.n - 1) j = a.n - 1;
+                a.anc[i] = (int32_t)j;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// Multinomial: n_out iid uniforms (unsorted) -> independent binary searches over the whole CDF.
+__global__ void __launch_bounds__(ANC_THREADS)
+ancestors_multinomial_kernel(AncArgs a) {
+    if (a.ctl && (a.ctl->done || !a.ctl->resample)) return;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n_out; i += (int64_t)gridDim.x * blockDim.x) {
+        double u;
+        if (a.u) u = a.u[i];
+        else { const Philox4 r = philox_raw(a.seed, (uint64_t)(a.gid0 + i), a.step, MB_P_RESAMPLE, 0u); u = u53(r.x, r.y); }
+        int64_t j = upper_bound_g(a.cdf, 0, a.n, u);
+        if (j > a.n - 1) j = a.n - 1;
+        a.anc[i] = (int32_t)j;
+    }
+}
+
+extern "C" int mb_ancestors(mb_ctx* ctx, const double* cdf, int64_t n, int mode, const double* u, uint64_t seed,
+                            uint32_t step, int64_t gid0, int32_t* anc, int64_t n_out, const mb_control* ctl,
+                            mb_stream_t stream) {
+    MB_REQUIRE(ctx && cdf && anc && n > 0 && n_out > 0 && n <= 0x7fffffffll, "mb_ancestors: bad arguments");
+    AncArgs a{cdf, n, u, seed, step, gid0, anc, n_out, ctl};
+    if (mode == MB_RESAMPLE_SYSTEMATIC) {
+        int64_t grid = (n_out + ANC_BLOCK_OUT - 1) / ANC_BLOCK_OUT;
+        if (grid > (int64_t)ctx->sms * 16) grid = (int64_t)ctx->sms * 16;
+        ancestors_systematic_kernel<<<(unsigned)grid, ANC_THREADS, 0, mb_s(stream)>>>(a);
+    } else if (mode == MB_RESAMPLE_MULTINOMIAL) {
+        int64_t grid = (n_out + ANC_THREADS - 1) / ANC_THREADS;
+        if (grid > (int64_t)ctx->sms * 32) grid = (int64_t)ctx->sms * 32;
+        ancestors_multinomial_kernel<<<(unsigned)grid, ANC_THREADS, 0, mb_s(stream)>>>(a);
+    } else {
+        mb_set_error("mb_ancestors: unknown mode %d", mode);
+        return MB_ERR_ARG;
+    }
+    MB_CHECK_LAUNCH();
+    return MB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ K6
+__global__ void __launch_bounds__(256)
+gather_state_kernel(const int32_t* __restrict__ anc, int64_t n_out, int ncols, const float* __restrict__ src,
+                    int64_t ld_src, float* __restrict__ dst, int64_t ld_dst) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_out; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t a = anc[i];
+        for (int c = 0; c < ncols; ++c) dst[(int64_t)c * ld_dst + i] = __ldg(src + (int64_t)c * ld_src + a);
+    }
+}
+
+extern "C" int mb_gather_state(mb_ctx* ctx, const int32_t* anc, int64_t n_out, int ncols, const float* src,
+                               int64_t ld_src, float* dst, int64_t ld_dst, mb_stream_t stream) {
+    MB_REQUIRE(ctx && anc && src && dst && n_out > 0 && ncols > 0, "mb_gather_state: bad arguments");
+    int64_t grid = (n_out + 255) / 256;
+    if (grid > (int64_t)ctx->sms * 32) grid = (int64_t)ctx->sms * 32;
+    gather_state_kernel<<<(unsigned)grid, 256, 0, mb_s(stream)>>>(anc, n_out, ncols, src, ld_src, dst, ld_dst);
+    MB_CHECK_LAUNCH();
+    return MB_OK;
+}

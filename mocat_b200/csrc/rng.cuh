@@ -1,0 +1,75 @@
+// rng.cuh -- Philox4x32-10 counter RNG and uniform/normal conversions (mirrored bit-for-bit on the
+// integer/uniform level by oracle/philox.py).  Replaces the jax.random (threefry) draws of the
+// reference, e.g. transport/smc.py:82, ssm/filtering.py:294, mcmc/standard_mcmc.py:54-56,120-122.
+#pragma once
+#include <stdint.h>
+
+#define MB_P_INIT     0u
+#define MB_P_MOVE     1u
+#define MB_P_RESAMPLE 2u
+#define MB_P_SIM      3u
+
+struct Philox4 { uint32_t x, y, z, w; };
+
+__device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                 uint32_t k0, uint32_t k1) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        if (r > 0) { k0 += W0; k1 += W1; }
+        const uint64_t p0 = (uint64_t)M0 * c0;
+        const uint64_t p1 = (uint64_t)M1 * c2;
+        const uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
+        const uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+        c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+    }
+    return Philox4{c0, c1, c2, c3};
+}
+
+__device__ __forceinline__ Philox4 philox_raw(uint64_t seed, uint64_t gid, uint32_t step, uint32_t purpose,
+                                              uint32_t index) {
+    return philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), step, (purpose << 20) | index,
+                         (uint32_t)seed, (uint32_t)(seed >> 32));
+}
+
+// [0,1) with 24 bits, exact in fp32
+__device__ __forceinline__ float u24(uint32_t x) { return (float)(x >> 8) * 5.9604644775390625e-8f; }
+// (0,1]: (float(x) + 0.5f) * 2^-32, round-to-nearest at each step
+__device__ __forceinline__ float u_open(uint32_t x) {
+    return __fmul_rn(__fadd_rn(__uint2float_rn(x), 0.5f), 2.3283064365386963e-10f);
+}
+// [0,1) fp64 with 53 bits from two words
+__device__ __forceinline__ double u53(uint32_t a, uint32_t b) {
+    return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) * 1.1102230246251565e-16;
+}
+
+// Box-Muller: z0 = r cos(2 pi u2), z1 = r sin(2 pi u2), r = sqrt(-2 ln u1).
+// cos/sin evaluated on phi = 2 pi u2 - pi in [-pi, pi) where the MUFU approximations are accurate:
+// cos(2 pi u2) = -cos(phi), sin(2 pi u2) = -sin(phi).
+__device__ __forceinline__ void box_muller(uint32_t xa, uint32_t xb, float& z0, float& z1) {
+    const float u1 = u_open(xa);
+    const float u2 = u24(xb);
+    const float r = sqrtf(-2.0f * __logf(u1));
+    const float phi = fmaf(u2, 6.283185307179586f, -3.141592653589793f);
+    float s, c;
+    __sincosf(phi, &s, &c);
+    z0 = -r * c;
+    z1 = -r * s;
+}
+
+// D standard normals for particle gid: normal j <- slot index0 + j/4, words (0,1) / (2,3).
+template <int D>
+__device__ __forceinline__ void philox_normals(float (&z)[D], uint64_t seed, uint64_t gid, uint32_t step,
+                                               uint32_t purpose, uint32_t index0) {
+#pragma unroll
+    for (int s = 0; s < (D + 3) / 4; ++s) {
+        const Philox4 r = philox_raw(seed, gid, step, purpose, index0 + s);
+        float a, b, c, d;
+        box_muller(r.x, r.y, a, b);
+        box_muller(r.z, r.w, c, d);
+        if (4 * s + 0 < D) z[4 * s + 0] = a;
+        if (4 * s + 1 < D) z[4 * s + 1] = b;
+        if (4 * s + 2 < D) z[4 * s + 2] = c;
+        if (4 * s + 3 < D) z[4 * s + 3] = d;
+    }
+}

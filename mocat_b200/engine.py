@@ -1,0 +1,337 @@
+"""Device engines: torch tensors own the HBM, the C-ABI kernels do the work.
+
+Layout in HBM: particle values are SoA `x[d][ld]` (a torch (d, ld) float32 tensor, ld = n
+rounded up to 32 elements so every column starts 128 B aligned), double buffered for the fused
+ancestor-gather; per-particle scalars (`lw`, `lik`, `up`, `alpha`, `dist`) are (n,) float32; the fp64 CDF
+(n,) and int32 ancestors (n,) are allocated on first resample; all per-iteration scalars live in one
+136-byte control block on the device plus a history ring of 48-byte records.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import ptr, stream
+
+
+def _pad(n):
+    return (int(n) + 31) // 32 * 32
+
+
+def _dev():
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+class ControlBlock:
+    """Device mb_control + history ring."""
+
+    def __init__(self, hist_len=_lib.MB_HIST_MAX):
+        self.t = torch.zeros(_lib.CONTROL_DTYPE.itemsize, dtype=torch.uint8, device=_dev())
+        self.hist = torch.zeros(hist_len * _lib.HIST_DTYPE.itemsize, dtype=torch.uint8, device=_dev())
+        self._pin = torch.empty(_lib.CONTROL_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+
+    def read(self):
+        """synchronising read of the control block -> numpy record"""
+        self._pin.copy_(self.t, non_blocking=False)
+        return self._pin.numpy().view(_lib.CONTROL_DTYPE)[0].copy()
+
+    def write(self, rec):
+        buf = np.zeros(1, dtype=_lib.CONTROL_DTYPE)
+        buf[0] = rec
+        self.t.copy_(torch.from_numpy(buf.view(np.uint8)))
+
+    def read_hist(self, count):
+        nbytes = count * _lib.HIST_DTYPE.itemsize
+        return self.hist[:nbytes].cpu().numpy().view(_lib.HIST_DTYPE).copy()
+
+
+# ------------------------------------------------------------------------------------------- primitives
+def lse_ess(lw, lik=None, dbeta=0.0):
+    """(wmax, s1, s2, lse, lse2, log_ess) of lw - dbeta*lik as a (6,) float64 device tensor."""
+    L = _lib.get()
+    out = torch.empty(6, dtype=torch.float64, device=lw.device)
+    L.call("mb_lse_ess", L.ctx(), ptr(lw), ptr(lik), float(dbeta), lw.numel(), ptr(out), stream())
+    return out
+
+
+def cumsum_f32(w, scale):
+    L = _lib.get()
+    cdf = torch.empty(w.numel(), dtype=torch.float64, device=w.device)
+    L.call("mb_cumsum_f32", L.ctx(), ptr(w), w.numel(), float(scale), ptr(cdf), stream())
+    return cdf
+
+
+def cumsum_lw(lw, ctl, force=True, out=None):
+    L = _lib.get()
+    cdf = out if out is not None else torch.empty(lw.numel(), dtype=torch.float64, device=lw.device)
+    L.call("mb_cumsum_lw", L.ctx(), ptr(lw), lw.numel(), ptr(ctl.t), 1 if force else 0, ptr(cdf), stream())
+    return cdf
+
+
+def ancestors(cdf, mode, n_out=None, u=None, seed=0, step=0, gid0=0, ctl=None, out=None):
+    L = _lib.get()
+    n_out = cdf.numel() if n_out is None else int(n_out)
+    anc = out if out is not None else torch.empty(n_out, dtype=torch.int32, device=cdf.device)
+    L.call("mb_ancestors", L.ctx(), ptr(cdf), cdf.numel(), int(mode), ptr(u), int(seed), int(step), int(gid0),
+           ptr(anc), n_out, ptr(ctl.t) if ctl is not None else None, stream())
+    return anc
+
+
+def gather_state(anc, src, n_out=None):
+    """src: (ncols, ld) float32 SoA block -> (ncols, pad(n_out))"""
+    L = _lib.get()
+    n_out = anc.numel() if n_out is None else n_out
+    dst = torch.empty((src.shape[0], _pad(n_out)), dtype=torch.float32, device=src.device)
+    L.call("mb_gather_state", L.ctx(), ptr(anc), n_out, src.shape[0], ptr(src), src.stride(0), ptr(dst), dst.stride(0),
+           stream())
+    return dst
+
+
+def quantile(v, q):
+    L = _lib.get()
+    out = torch.empty(3, dtype=torch.float64, device=v.device)
+    L.call("mb_quantile", L.ctx(), ptr(v), v.numel(), float(q), ptr(out), stream())
+    return out
+
+
+def colstats(x, n):
+    """x: (d, ld) SoA -> (mean (d,), var ddof=1 (d,)) float64 device tensors"""
+    L = _lib.get()
+    d = x.shape[0]
+    mean = torch.empty(d, dtype=torch.float64, device=x.device)
+    var = torch.empty(d, dtype=torch.float64, device=x.device)
+    L.call("mb_colstats", L.ctx(), ptr(x), x.stride(0), int(n), d, ptr(mean), ptr(var), stream())
+    return mean, var
+
+
+def weighted_moments(x, n, lw, ctl):
+    L = _lib.get()
+    d = x.shape[0]
+    mean = torch.empty(d, dtype=torch.float64, device=x.device)
+    var = torch.empty(d, dtype=torch.float64, device=x.device)
+    L.call("mb_weighted_moments", L.ctx(), ptr(x), x.stride(0), int(n), d, ptr(lw), ptr(ctl.t), ptr(mean), ptr(var),
+           stream())
+    return mean, var
+
+
+def target_potential_grad(target, beta, X):
+    """X: (n, d) row-major float32 -> (U (n,), G (n, d))"""
+    L = _lib.get()
+    n, d = X.shape
+    U = torch.empty(n, dtype=torch.float32, device=X.device)
+    G = torch.empty((n, d), dtype=torch.float32, device=X.device)
+    L.call("mb_target_potential_grad", L.ctx(), C.byref(target), float(beta), ptr(X), n, ptr(U), ptr(G), stream())
+    return U, G
+
+
+# ------------------------------------------------------------------------------------------- tempered SMC
+class SMCEngine:
+    """Device state + kernel sequence of one tempered-SMC population (transport/smc.py)."""
+
+    def __init__(self, target, move, temper, n, seed, resampling=_lib.RESAMPLE_MULTINOMIAL, gid0=0, n_total=None,
+                 keep_alpha=True, keep_prior_potential=True, schedule=None):
+        self.L = _lib.get()
+        self.ctx = self.L.ctx()
+        self.target, self.move, self.temper = target, move, temper
+        self.n, self.d, self.ld = int(n), int(target.dim), _pad(n)
+        self.n_total = self.n if n_total is None else int(n_total)
+        self.seed, self.gid0, self.resampling = int(seed), int(gid0), int(resampling)
+        dev = _dev()
+        self.xbuf = [torch.zeros((self.d, self.ld), dtype=torch.float32, device=dev) for _ in range(2)]
+        self.cur = 0
+        f = lambda: torch.zeros(self.n, dtype=torch.float32, device=dev)
+        self.lw, self.lik = f(), f()
+        self.up = f() if keep_prior_potential else None
+        self.alpha = f() if keep_alpha else None
+        self.cdf = torch.empty(self.n, dtype=torch.float64, device=dev)
+        self.anc = torch.zeros(self.n, dtype=torch.int32, device=dev)
+        self.ctl = ControlBlock()
+        self._schedule = None
+        if schedule is not None:
+            self._schedule = torch.as_tensor(np.asarray(schedule, np.float64), device=dev)
+            self.temper.schedule = self._schedule.data_ptr()
+            self.temper.schedule_len = self._schedule.numel()
+        self.enqueued = 0
+
+    @property
+    def x(self):
+        return self.xbuf[self.cur]
+
+    def _temper(self, advance):
+        self.L.call("mb_temper_adapt", self.ctx, ptr(self.lw), ptr(self.lik), self.n, C.byref(self.temper),
+                    1 if advance else 0, self.n_total * self.d, self.n_total, ptr(self.ctl.t), ptr(self.ctl.hist), stream())
+
+    def startup(self, x0=None):
+        """transport/smc.py:128-164 + 267-296.  x0: optional (n, d) host/device array of initial values."""
+        if x0 is not None:
+            x0 = torch.as_tensor(x0, dtype=torch.float32, device=self.x.device)
+            self.x[:, :self.n].copy_(x0.t())
+        self.L.call("mb_smc_init", self.ctx, C.byref(self.target), ptr(self.x), self.ld, self.n, self.n_total,
+                    0 if x0 is not None else 1, ptr(self.up), ptr(self.lik), ptr(self.lw), self.seed, self.gid0,
+                    ptr(self.ctl.t), stream())
+        self._temper(advance=False)
+        self.enqueued = 0
+
+    def update(self):
+        """enqueue one SMCSampler.update (transport/smc.py:73-99); fully asynchronous, predicated on device"""
+        st = stream()
+        self.L.call("mb_cumsum_lw", self.ctx, ptr(self.lw), self.n, ptr(self.ctl.t), 0, ptr(self.cdf), st)
+        self.L.call("mb_ancestors", self.ctx, ptr(self.cdf), self.n, self.resampling, None, self.seed,
+                    self.enqueued + 1, self.gid0, ptr(self.anc), self.n, ptr(self.ctl.t), st)
+        src, dst = self.xbuf[self.cur], self.xbuf[self.cur ^ 1]
+        self.L.call("mb_smc_move", self.ctx, C.byref(self.target), C.byref(self.move), ptr(src), ptr(dst), self.ld,
+                    self.n, ptr(self.anc), ptr(self.lw), ptr(self.up), ptr(self.lik), ptr(self.alpha), self.seed,
+                    self.gid0, ptr(self.ctl.t), st)
+        self.cur ^= 1
+        self._temper(advance=True)
+        self.enqueued += 1
+
+    def values(self):
+        """(n, d) float32 device tensor view of the current particle values"""
+        return self.x[:, :self.n].t()
+
+
+# ------------------------------------------------------------------------------------------- bootstrap PF
+class PFEngine:
+    """Device state + kernel sequence of a bootstrap particle filter (ssm/filtering.py)."""
+
+    def __init__(self, ssm, n, seed, ess_threshold=0.5, resampling=_lib.RESAMPLE_MULTINOMIAL, gid0=0, n_total=None):
+        self.L = _lib.get()
+        self.ctx = self.L.ctx()
+        self.ssm = ssm
+        self.n, self.d, self.ld = int(n), int(ssm.dim), _pad(n)
+        self.n_total = self.n if n_total is None else int(n_total)
+        self.seed, self.gid0, self.resampling = int(seed), int(gid0), int(resampling)
+        self.ess_threshold = float(ess_threshold)
+        dev = _dev()
+        self.xbuf = [torch.zeros((self.d, self.ld), dtype=torch.float32, device=dev) for _ in range(2)]
+        self.cur = 0
+        self.lw = torch.zeros(self.n, dtype=torch.float32, device=dev)
+        self.cdf = torch.empty(self.n, dtype=torch.float64, device=dev)
+        self.anc = torch.zeros(self.n, dtype=torch.int32, device=dev)
+        self.ctl = ControlBlock()
+        self.t = 0
+
+    @property
+    def x(self):
+        return self.xbuf[self.cur]
+
+    def init(self, y0):
+        """initiate_particles (ssm/filtering.py:173-193).  y0: device float32 (dim_obs,)"""
+        self.L.call("mb_pf_init", self.ctx, C.byref(self.ssm), ptr(self.x), self.ld, self.n, self.n_total, ptr(y0),
+                    ptr(self.lw), self.seed, self.gid0, self.ess_threshold, ptr(self.ctl.t), ptr(self.ctl.hist),
+                    stream())
+        self.t = 0
+
+    def step(self, y):
+        """one body of the scan in run_particle_filter_for_marginals (ssm/filtering.py:280-311)"""
+        st = stream()
+        self.t += 1
+        self.L.call("mb_cumsum_lw", self.ctx, ptr(self.lw), self.n, ptr(self.ctl.t), 0, ptr(self.cdf), st)
+        self.L.call("mb_ancestors", self.ctx, ptr(self.cdf), self.n, self.resampling, None, self.seed, self.t,
+                    self.gid0, ptr(self.anc), self.n, ptr(self.ctl.t), st)
+        src, dst = self.xbuf[self.cur], self.xbuf[self.cur ^ 1]
+        self.L.call("mb_pf_step", self.ctx, C.byref(self.ssm), ptr(src), ptr(dst), self.ld, self.n, self.n_total,
+                    ptr(self.anc), ptr(y), ptr(self.lw), self.seed, self.t, self.gid0, self.ess_threshold,
+                    ptr(self.ctl.t), ptr(self.ctl.hist), st)
+        self.cur ^= 1
+
+    def values(self):
+        return self.x[:, :self.n].t()
+
+
+# ------------------------------------------------------------------------------------------- SMC-ABC
+class ABCEngine:
+    """Device state + kernel sequence of SMC-ABC on the g-and-k model (abc/smc.py, abc/mcmc.py)."""
+
+    def __init__(self, gk, n, seed, mcmc_steps=1, max_iter=10000, ess_retain=0.9, ess_resample=0.5,
+                 termination_alpha=0.01, threshold_schedule=None, resampling=_lib.RESAMPLE_MULTINOMIAL, gid0=0,
+                 n_total=None):
+        self.L = _lib.get()
+        self.ctx = self.L.ctx()
+        self.gk = gk
+        self.n, self.d, self.ld = int(n), 4, _pad(n)
+        self.n_total = self.n if n_total is None else int(n_total)
+        self.seed, self.gid0, self.resampling = int(seed), int(gid0), int(resampling)
+        self.mcmc_steps, self.max_iter = int(mcmc_steps), int(max_iter)
+        self.ess_retain, self.ess_resample, self.termination_alpha = float(ess_retain), float(ess_resample), \
+            float(termination_alpha)
+        dev = _dev()
+        f = lambda: torch.zeros(self.n, dtype=torch.float32, device=dev)
+        self.xbuf = [torch.zeros((self.d, self.ld), dtype=torch.float32, device=dev) for _ in range(2)]
+        self.upbuf, self.distbuf, self.alphabuf = [f(), f()], [f(), f()], [f(), f()]
+        self.cur = 0
+        self.lw = f()
+        self.stepsize = torch.ones(self.d, dtype=torch.float32, device=dev)
+        self.cdf = torch.empty(self.n, dtype=torch.float64, device=dev)
+        self.anc = torch.zeros(self.n, dtype=torch.int32, device=dev)
+        self.ctl = ControlBlock()
+        self._schedule = None
+        if threshold_schedule is not None:
+            self._schedule = torch.as_tensor(np.asarray(threshold_schedule, np.float64), device=dev)
+            self.max_iter = self._schedule.numel()
+        self.enqueued = 0
+
+    x = property(lambda self: self.xbuf[self.cur])
+    up = property(lambda self: self.upbuf[self.cur])
+    dist = property(lambda self: self.distbuf[self.cur])
+    alpha = property(lambda self: self.alphabuf[self.cur])
+
+    def _adapt(self, advance):
+        self.L.call("mb_abc_adapt", self.ctx, ptr(self.x), self.ld, self.n, self.n_total, self.d, ptr(self.dist),
+                    ptr(self.lw), ptr(self.alpha), ptr(self.stepsize), self.ess_retain, self.ess_resample,
+                    self.termination_alpha, self.max_iter, ptr(self._schedule), 1 if advance else 0, ptr(self.ctl.t),
+                    ptr(self.ctl.hist), stream())
+
+    def startup(self, x0=None):
+        if x0 is not None:
+            x0 = torch.as_tensor(x0, dtype=torch.float32, device=self.x.device)
+            self.x[:, :self.n].copy_(x0.t())
+        self.L.call("mb_abc_init", self.ctx, C.byref(self.gk), ptr(self.x), self.ld, self.n, self.n_total,
+                    0 if x0 is not None else 1, ptr(self.up), ptr(self.dist), ptr(self.lw), ptr(self.alpha), self.seed,
+                    self.gid0, ptr(self.ctl.t), stream())
+        self._adapt(advance=False)
+        self.enqueued = 0
+
+    def update(self):
+        st = stream()
+        self.L.call("mb_cumsum_lw", self.ctx, ptr(self.lw), self.n, ptr(self.ctl.t), 0, ptr(self.cdf), st)
+        self.L.call("mb_ancestors", self.ctx, ptr(self.cdf), self.n, self.resampling, None, self.seed,
+                    self.enqueued + 1, self.gid0, ptr(self.anc), self.n, ptr(self.ctl.t), st)
+        c, o = self.cur, self.cur ^ 1
+        self.L.call("mb_abc_move", self.ctx, C.byref(self.gk), self.mcmc_steps, ptr(self.xbuf[c]), ptr(self.xbuf[o]),
+                    self.ld, self.n, ptr(self.anc), ptr(self.upbuf[c]), ptr(self.upbuf[o]), ptr(self.distbuf[c]),
+                    ptr(self.distbuf[o]), ptr(self.lw), ptr(self.alphabuf[c]), ptr(self.alphabuf[o]),
+                    ptr(self.stepsize), self.seed, self.gid0, ptr(self.ctl.t), st)
+        self.cur = o
+        self._adapt(advance=True)
+        self.enqueued += 1
+
+    def values(self):
+        return self.x[:, :self.n].t()
+
+
+# ------------------------------------------------------------------------------------------- SVGD
+def svgd_phi(X, G, bandwidth, variant=0):
+    """X, G: (n, d) row-major float32; bandwidth: device float32 scalar tensor -> phi (n, d)"""
+    L = _lib.get()
+    n, d = X.shape
+    phi = torch.empty_like(X)
+    L.call("mb_svgd_phi", L.ctx(), ptr(X), ptr(G), n, d, ptr(bandwidth), ptr(phi), int(variant), stream())
+    return phi
+
+
+def pairdist_bandwidth(X, mode):
+    """mode 'median' | 'mean' -> device float32 (1,) tensor h = stat(D)/sqrt(2 log n)  (kernels.py:220-229)"""
+    L = _lib.get()
+    n, d = X.shape
+    h = torch.empty(1, dtype=torch.float32, device=X.device)
+    L.call("mb_pairdist_bandwidth", L.ctx(), ptr(X), n, d, 0 if mode == "median" else 1, ptr(h), stream())
+    return h
+
+
+def adagrad_step(X, gsq, mom, phi, step, momentum=0.9):
+    L = _lib.get()
+    L.call("mb_adagrad", L.ctx(), ptr(X), ptr(gsq), ptr(mom), ptr(phi), X.numel(), float(step), float(momentum),
+           stream())

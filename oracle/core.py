@@ -16,6 +16,8 @@ import numpy as np
 Q_BITS = 52                      # weights are quantised to multiples of 2^-52 before the fp64 cumsum
 Q_SCALE = float(2 ** Q_BITS)
 Q_INV = float(2.0 ** -Q_BITS)
+Q_MARGIN = 1.0 + 2.0 ** -24      # un-normalised weights are scaled to sum to 1 + 6e-8 so the clamp at 1
+                                 # (not the forced last element) closes the CDF; see DESIGN.md
 
 
 # ----------------------------------------------------------------------------- LSE / ESS
@@ -118,7 +120,7 @@ def cdf_from_weights(w, normalised=True):
     if normalised:
         q = quantise_weights(w)
     else:
-        q = quantise_weights(w, Q_SCALE / float(np.sum(w.astype(np.float64))))
+        q = quantise_weights(w, Q_SCALE * Q_MARGIN / float(np.sum(w.astype(np.float64))))
     return finish_cdf(np.cumsum(q))
 
 

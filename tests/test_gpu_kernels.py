@@ -1,0 +1,154 @@
+"""GPU parity tests of the individual kernels (through the C-ABI) against the NumPy oracle."""
+import ctypes as C
+
+import numpy as np
+import numpy.testing as npt
+import pytest
+
+from oracle import core, philox
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng(lib):
+    import mocat_b200.engine as e
+    return e
+
+
+def _t(a, dtype=None):
+    import torch
+    return torch.as_tensor(np.ascontiguousarray(a), device="cuda") if dtype is None else \
+        torch.as_tensor(np.ascontiguousarray(a), dtype=dtype, device="cuda")
+
+
+# ------------------------------------------------------------------------------------------------ K2
+@pytest.mark.parametrize("n", [1, 31, 1000, 10_000, 1_000_003])
+def test_lse_ess_parity(eng, n):
+    rng = np.random.default_rng(n)
+    lw = (rng.standard_normal(n) * 3.0).astype(np.float32)
+    out = eng.lse_ess(_t(lw)).cpu().numpy()
+    ref = core.lse_ess(lw)
+    # fp32 exp on the device (2 ulp) + fp64 accumulation: tolerance 2e-6 absolute on the logs
+    npt.assert_allclose(out[3:], ref, atol=2e-6, rtol=0)
+    assert out[0] == np.float64(lw.max())
+
+
+def test_lse_ess_inf_and_tempered(eng):
+    rng = np.random.default_rng(0)
+    n = 50_000
+    lw = rng.standard_normal(n).astype(np.float32)
+    lw[rng.random(n) < 0.3] = -np.inf                       # ABC-style dead particles
+    out = eng.lse_ess(_t(lw)).cpu().numpy()
+    npt.assert_allclose(out[3:], core.lse_ess(lw), atol=2e-6)
+    w01 = np.where(rng.random(n) < 0.4, 0.0, -np.inf).astype(np.float32)
+    out = eng.lse_ess(_t(w01)).cpu().numpy()
+    npt.assert_allclose(np.exp(out[5]), np.sum(w01 == 0), rtol=1e-9)      # ess = #alive (Appendix A.1)
+    dead = np.full(1000, -np.inf, np.float32)
+    out = eng.lse_ess(_t(dead)).cpu().numpy()
+    assert out[3] == -np.inf and np.isnan(out[5])                          # all -inf: LSE -inf, log-ESS NaN
+    lik = (rng.random(n) * 20).astype(np.float32)
+    out = eng.lse_ess(_t(lw), _t(lik), 0.37).cpu().numpy()
+    npt.assert_allclose(out[3:], core.lse_ess_tempered(lw, lik, np.float32(0.37)), atol=5e-6)
+
+
+# ------------------------------------------------------------------------------------------------ K4
+@pytest.mark.parametrize("n", [1, 5, 4095, 4096, 4097, 100_000, 3_000_017])
+def test_cumsum_bit_exact(eng, n):
+    rng = np.random.default_rng(n)
+    w = rng.random(n).astype(np.float32) ** 4
+    w[rng.random(n) < 0.1] = 0.0
+    w = (w / w.astype(np.float64).sum()).astype(np.float32)
+    cdf = eng.cumsum_f32(_t(w), 2.0 ** 52).cpu().numpy()
+    ref = core.cdf_from_weights(w, normalised=True)
+    npt.assert_array_equal(cdf, ref)                       # bit-exact, any n / tile order
+    assert cdf[-1] == 1.0 and np.all(np.diff(cdf) >= 0)
+    # run-to-run determinism of the decoupled look-back
+    npt.assert_array_equal(eng.cumsum_f32(_t(w), 2.0 ** 52).cpu().numpy(), cdf)
+
+
+def test_cumsum_from_log_weights(eng):
+    import torch
+    rng = np.random.default_rng(1)
+    n = 200_000
+    lw = (rng.standard_normal(n) * 2).astype(np.float32)
+    lw[::7] = -np.inf
+    ctl = eng.ControlBlock()
+    rec = np.zeros(1, dtype=eng._lib.CONTROL_DTYPE)[0]
+    o = eng.lse_ess(_t(lw)).cpu().numpy()
+    rec["wmax"], rec["s1"], rec["s2"], rec["resample"] = o[0], o[1], o[2], 1
+    ctl.write(rec)
+    cdf = eng.cumsum_lw(_t(lw), ctl).cpu().numpy()
+    ref = core.cdf_from_log_weights(lw)
+    npt.assert_allclose(cdf, ref, atol=5e-7)               # device __expf vs numpy exp: tolerance, not bits
+    assert cdf[-1] == 1.0 and np.all(np.diff(cdf) >= 0)
+    dead = np.where(np.isinf(lw))[0]
+    dead = dead[dead > 0]
+    npt.assert_array_equal(cdf[dead], cdf[dead - 1])       # dead particles own no mass -> never selected
+
+
+# ------------------------------------------------------------------------------------------------ K5
+@pytest.mark.parametrize("n,n_out", [(1, 1), (7, 7), (5000, 5000), (100_003, 100_003), (10_000, 3_000), (3_000, 50_000)])
+def test_ancestors_bit_exact(eng, n, n_out):
+    rng = np.random.default_rng(n + n_out)
+    w = rng.random(n).astype(np.float32) ** 8              # skewed: long runs and long gaps
+    w[rng.random(n) < 0.3] = 0.0
+    w[0] = max(w[0], 1e-3)
+    w = (w / w.astype(np.float64).sum()).astype(np.float32)
+    cdf = core.cdf_from_weights(w)
+    cdf_d = _t(cdf)
+    u0 = 0.37123456789
+    a = eng.ancestors(cdf_d, 0, n_out, u=_t(np.array([u0]))).cpu().numpy()
+    npt.assert_array_equal(a, core.ancestors_systematic(cdf, u0, n_out))
+    u = rng.random(n_out)
+    a = eng.ancestors(cdf_d, 1, n_out, u=_t(u)).cpu().numpy()
+    npt.assert_array_equal(a, core.ancestors_multinomial(cdf, u))
+
+
+def test_ancestors_philox_and_degenerate(eng):
+    n = 20_000
+    cdf = core.cdf_from_weights(np.full(n, 1.0 / n, np.float32))
+    a = eng.ancestors(_t(cdf), 0, n, seed=5, step=3).cpu().numpy()
+    u0 = philox.uniform53(5, np.zeros(1, np.uint64), 3, philox.P_RESAMPLE)[0]
+    npt.assert_array_equal(a, core.ancestors_systematic(cdf, u0))
+    a = eng.ancestors(_t(cdf), 1, n, seed=5, step=3, gid0=100).cpu().numpy()
+    u = philox.uniform53(5, np.arange(100, 100 + n, dtype=np.uint64), 3, philox.P_RESAMPLE)
+    npt.assert_array_equal(a, core.ancestors_multinomial(cdf, u))
+    # all mass on one particle
+    w = np.zeros(n, np.float32); w[1234] = 1.0
+    cdf = core.cdf_from_weights(w)
+    a = eng.ancestors(_t(cdf), 0, n, u=_t(np.array([0.5]))).cpu().numpy()
+    assert np.all(a == 1234)
+
+
+# ------------------------------------------------------------------------------------------------ K6
+def test_gather_state(eng):
+    rng = np.random.default_rng(2)
+    n, d = 10_001, 7
+    ld = (n + 31) // 32 * 32
+    src = np.zeros((d, ld), np.float32)
+    src[:, :n] = rng.standard_normal((d, n))
+    anc = np.sort(rng.integers(0, n, n)).astype(np.int32)
+    dst = eng.gather_state(_t(anc), _t(src)).cpu().numpy()
+    npt.assert_array_equal(dst[:, :n], src[:, anc])
+
+
+# ------------------------------------------------------------------------------------------------ K7
+def test_quantile_and_colstats(eng):
+    rng = np.random.default_rng(3)
+    n = 100_001
+    v = np.abs(rng.standard_normal(n)).astype(np.float32) * 10
+    v[::11] = v[5]                                          # duplicates
+    for q in (0.0, 0.1234, 0.45, 0.9, 1.0):
+        out = eng.quantile(_t(v), q).cpu().numpy()
+        npt.assert_allclose(out[0], core.quantile_linear(v, q), rtol=1e-12)
+    v2 = rng.standard_normal(1000).astype(np.float32)       # negatives
+    npt.assert_allclose(eng.quantile(_t(v2), 0.3).cpu().numpy()[0], core.quantile_linear(v2, 0.3), rtol=1e-12)
+    d = 4
+    ld = (n + 31) // 32 * 32
+    x = np.zeros((d, ld), np.float32)
+    x[:, :n] = rng.standard_normal((d, n)) * np.array([[1.], [2.], [0.1], [5.]]) + 100.0
+    mean, var = eng.colstats(_t(x), n)
+    rm, rv = core.colstats(x[:, :n].T)
+    npt.assert_allclose(mean.cpu().numpy(), rm, rtol=1e-9)
+    npt.assert_allclose(var.cpu().numpy(), rv, rtol=1e-6)
