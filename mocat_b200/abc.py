@@ -1,0 +1,171 @@
+"""SMC-ABC: host mirror of mocat/src/abc/{abc,smc,mcmc}.py and abc/scenarios/gk.py for the population path.
+
+`MetropolisedABCSMCSampler(mcmc_sampler=None, mcmc_correction, mcmc_steps=1, threshold_schedule=None,
+max_iter, ess_threshold_retain=.9, ess_threshold_resample=.5, termination_alpha=.01)` (abc/smc.py:103-126)
+with the default RandomWalkABC move and diagonal-covariance step adaptation (abc/smc.py:94-98,116-118).
+"""
+import numpy as np
+
+from . import _lib, engine, models
+from .core import cdict, key_to_seed
+from .sample import Sampler
+from .transport import _RESAMPLING, HISTORY_AUTO_BYTES
+
+
+class ABCScenario:
+    """abc/abc.py:16-38 (interface).  Device scenarios implement `_gk()`."""
+    name = None
+    dim = None
+    data = None
+
+    def _device(self):
+        raise _lib.MocatB200Error(f"{type(self).__name__}: only built-in device ABC scenarios (GKTransformedUniformPrior "
+                                  "with m in {4, 8, 16} sorted draws) can be simulated; no CPU fallback")
+
+
+class GKTransformedUniformPrior(ABCScenario):
+    """abc/scenarios/gk.py:68-96.  Summary statistic (user code upstream, gk.py:34-36): the
+    `n_unsummarised_data` simulated draws sorted ascending."""
+    name = 'GK_fewN'
+    dim = 4
+    c = 0.8
+    prior_mins = 0.
+    prior_maxs = 10.
+    buffer = 1e-5
+
+    def __init__(self, data=None, n_unsummarised_data=8, name=None, **kwargs):
+        if name is not None:
+            self.name = name
+        self.n_unsummarised_data = int(n_unsummarised_data if data is None else len(data))
+        self.data = None if data is None else np.sort(np.asarray(data, np.float64))
+        for k, v in kwargs.items():
+            if hasattr(self, k):
+                setattr(self, k, v)
+
+    def constrain(self, unconstrained_x):                               # gk.py:70-72
+        from scipy.special import ndtr
+        return self.prior_mins + ndtr(np.asarray(unconstrained_x, np.float64)) * (self.prior_maxs - self.prior_mins)
+
+    def unconstrain(self, constrained_x):                               # gk.py:74-76
+        from scipy.special import ndtri
+        return ndtri((np.asarray(constrained_x, np.float64) - self.prior_mins) / (self.prior_maxs - self.prior_mins))
+
+    def _device(self):
+        if self.data is None:
+            raise _lib.MocatB200Error("GKTransformedUniformPrior.data (the observed summary) must be set")
+        return models.make_gk(self.data, self.c, self.prior_mins, self.prior_maxs, self.buffer)
+
+
+class RandomWalkABC:
+    """abc/mcmc.py:40-76 (parameter holder; the move runs in mb_abc_move)."""
+    name = 'Random Walk ABC'
+
+    def __init__(self, threshold=None, stepsize=None):
+        self.parameters = cdict(threshold=threshold, stepsize=stepsize)
+        self.tuning = cdict(parameter='threshold', target=0.1, metric='alpha', monotonicity='increasing')
+
+
+class ABCSMCSampler(Sampler):
+    """abc/smc.py:22-91."""
+    name = "ABC SMC"
+
+    def __init__(self, threshold_schedule=None, max_iter=int(1e4), **kwargs):
+        self.max_iter = max_iter
+        self.threshold_schedule = threshold_schedule
+        super().__init__(**kwargs)
+
+    def __setattr__(self, key, value):                                   # abc/smc.py:33-42
+        if key == 'threshold_schedule':
+            if value is None:
+                if getattr(self, 'threshold_schedule', None) is not None \
+                        and self.max_iter == len(self.threshold_schedule):
+                    self.max_iter = int(1e4)
+            else:
+                self.max_iter = len(value)
+        super().__setattr__(key, value)
+
+
+class MetropolisedABCSMCSampler(ABCSMCSampler):
+    """abc/smc.py:101-245."""
+
+    _FIELDS = ('value', 'log_weight', 'prior_potential', 'distance', 'alpha')
+
+    def __init__(self, mcmc_sampler=None, mcmc_correction='sampler_default', mcmc_steps=1, threshold_schedule=None,
+                 max_iter=int(1e4), ess_threshold_retain=0.9, ess_threshold_resample=0.5, termination_alpha=0.01,
+                 resampling='multinomial', keep_history=None, check_every=8, **kwargs):
+        super().__init__(max_iter=max_iter, threshold_schedule=threshold_schedule, **kwargs)
+        if mcmc_sampler is None:
+            mcmc_sampler = RandomWalkABC()
+        if isinstance(mcmc_sampler, type):
+            mcmc_sampler = mcmc_sampler()
+        if not isinstance(mcmc_sampler, RandomWalkABC):
+            raise _lib.MocatB200Error("only RandomWalkABC (the reference default) is compiled into the device move")
+        self.mcmc_sampler = mcmc_sampler
+        self.parameters.mcmc_steps = mcmc_steps
+        self.parameters.ess_threshold_retain = ess_threshold_retain
+        self.parameters.ess_threshold_resample = ess_threshold_resample
+        self.parameters.termination_alpha = termination_alpha
+        self.resampling, self.keep_history, self.check_every = resampling, keep_history, check_every
+
+    def _snapshot(self, eng):
+        return dict(value=eng.values().clone(memory_format=__import__('torch').contiguous_format), log_weight=eng.lw.clone(), prior_potential=eng.up.clone(),
+                    distance=eng.dist.clone(), alpha=eng.alpha.clone())
+
+    def startup(self, abc_scenario, n, initial_state, initial_extra, **kwargs):
+        initial_state, initial_extra = super().startup(abc_scenario, n, initial_state, initial_extra, **kwargs)
+        P = self.parameters
+        eng = engine.ABCEngine(abc_scenario._device(), n, key_to_seed(getattr(initial_extra, 'random_key', None)),
+                               mcmc_steps=P.mcmc_steps, max_iter=self.max_iter, ess_retain=P.ess_threshold_retain,
+                               ess_resample=P.ess_threshold_resample, termination_alpha=P.termination_alpha,
+                               threshold_schedule=self.threshold_schedule, resampling=_RESAMPLING[self.resampling])
+        x0 = None if initial_state is None else getattr(initial_state, 'value', None)
+        eng.startup(x0)                                                  # abc/smc.py:44-79,128-150
+        if initial_state is None:
+            initial_state = cdict()
+        initial_state.engine = eng
+        initial_extra.engine = eng
+        return initial_state, initial_extra
+
+    def update(self, abc_scenario, ensemble_state, extra):
+        extra.engine.update()
+        extra.iter = extra.iter + 1
+        return ensemble_state, extra
+
+    def termination_criterion(self, ensemble_state, extra):              # abc/smc.py:157-161 (on device)
+        return bool(extra.engine.ctl.read()['done'])
+
+    def _run_device(self, abc_scenario, initial_state, initial_extra):
+        import torch
+        eng = initial_extra.engine
+        keep = self.keep_history
+        if keep is None:
+            keep = eng.n * 12 * 4 * min(self.max_iter + 1, 64) <= HISTORY_AUTO_BYTES
+        snaps = [self._snapshot(eng)] if keep else None
+        steps = []
+        it = 0
+        while it < self.max_iter:
+            for _ in range(min(self.check_every, self.max_iter - it)):
+                eng.update()
+                it += 1
+                if keep:
+                    snaps.append(self._snapshot(eng))
+                    steps.append(eng.stepsize.clone())
+            if eng.ctl.read()['done']:
+                break
+        c = eng.ctl.read()
+        iters = int(c['iter'])
+        hist = eng.ctl.read_hist(iters + 1)
+        chain = cdict()
+        if keep:
+            for k in self._FIELDS:
+                setattr(chain, k, torch.stack([s[k] for s in snaps[:iters + 1]]).cpu().numpy())
+        else:
+            for k, v in self._snapshot(eng).items():
+                setattr(chain, k, v.cpu().numpy()[None])
+        chain.threshold = hist['beta'].copy()                            # clean_chain, abc/smc.py:86-91
+        chain.ess = hist['ess'].copy()
+        chain.alpha_mean = hist['alpha_mean'].copy()
+        chain.resampled = hist['resampled'].copy()
+        chain.stepsize = eng.stepsize.cpu().numpy()
+        initial_extra.iter = iters
+        return chain

@@ -173,18 +173,27 @@ class SMCEngine:
         self._temper(advance=False)
         self.enqueued = 0
 
-    def update(self):
-        """enqueue one SMCSampler.update (transport/smc.py:73-99); fully asynchronous, predicated on device"""
+    def update(self, events=None):
+        """enqueue one SMCSampler.update (transport/smc.py:73-99); fully asynchronous, predicated on device.
+        events: optional list of 4 torch.cuda.Event recorded before / between / after the kernel groups."""
         st = stream()
+        if events:
+            events[0].record()
         self.L.call("mb_cumsum_lw", self.ctx, ptr(self.lw), self.n, ptr(self.ctl.t), 0, ptr(self.cdf), st)
         self.L.call("mb_ancestors", self.ctx, ptr(self.cdf), self.n, self.resampling, None, self.seed,
                     self.enqueued + 1, self.gid0, ptr(self.anc), self.n, ptr(self.ctl.t), st)
+        if events:
+            events[1].record()
         src, dst = self.xbuf[self.cur], self.xbuf[self.cur ^ 1]
         self.L.call("mb_smc_move", self.ctx, C.byref(self.target), C.byref(self.move), ptr(src), ptr(dst), self.ld,
                     self.n, ptr(self.anc), ptr(self.lw), ptr(self.up), ptr(self.lik), ptr(self.alpha), self.seed,
                     self.gid0, ptr(self.ctl.t), st)
+        if events:
+            events[2].record()
         self.cur ^= 1
         self._temper(advance=True)
+        if events:
+            events[3].record()
         self.enqueued += 1
 
     def values(self):

@@ -1,0 +1,259 @@
+"""State-space models and bootstrap particle filtering: host mirror of mocat/src/ssm/{ssm,filtering}.py,
+ssm/linear_gaussian/{linear_gaussian,kalman}.py, ssm/nonlinear_gaussian.py and ssm/scenarios/lorenz96.py.
+
+The filtering functions keep the reference signatures (filtering.py:173,202,220,255).  Differences, all
+forced by scale: the particle cdict carries a device engine; the stacked (T, n, d) history the
+reference returns is kept only when `keep_history` is set / small (otherwise `value` holds the latest
+population with a leading axis of 1), and per-step weighted means/variances, ESS and the running
+log-evidence (`log_norm_constant`, convention of transport/smc.py:160,212-215) are always returned.
+The transition of Lorenz-96 is `substeps` fixed RK4 steps (the reference uses adaptive odeint,
+lorenz96.py:23-26); see DESIGN.md.
+"""
+import numpy as np
+
+from . import _lib, engine, models
+from .core import cdict, key_to_seed
+
+_RESAMPLING = {'multinomial': _lib.RESAMPLE_MULTINOMIAL, 'systematic': _lib.RESAMPLE_SYSTEMATIC}
+HISTORY_AUTO_BYTES = 1 << 30
+
+
+def _torch():
+    import torch
+    return torch
+
+
+class StateSpaceModel:
+    """ssm/ssm.py:18-81 (interface); device models implement `_ssm(dt)`."""
+    name = None
+    dim = None
+    dim_obs = None
+
+    def __repr__(self):
+        return f"mocat.StateSpaceModel.{self.__class__.__name__}"
+
+    def _ssm(self, dt=None):
+        raise _lib.MocatB200Error(f"{type(self).__name__}: only built-in device state-space models "
+                                  "(TimeHomogenousLinearGaussian, Lorenz96) can be filtered; no CPU fallback")
+
+
+class TimeHomogenousLinearGaussian(StateSpaceModel):
+    """ssm/linear_gaussian/linear_gaussian.py:142-261."""
+    name = 'Time-homogenous Linear Gaussian'
+
+    def __init__(self, initial_mean=None, initial_covariance=None, transition_matrix=None,
+                 transition_covariance=None, likelihood_matrix=None, likelihood_covariance=None, name=None, dim=None):
+        if name is not None:
+            self.name = name
+        if dim is None:
+            for a in (initial_mean, initial_covariance, transition_covariance, likelihood_matrix, likelihood_covariance):
+                if a is not None and np.ndim(a) > 0:
+                    dim = np.asarray(a).shape[-1]
+                    break
+        if dim is None:
+            raise AttributeError(f'Could not find dimension for {self.__class__.__name__}')
+        self.dim = int(dim)
+        eye = np.eye(self.dim)
+        self.initial_mean = np.zeros(self.dim) if initial_mean is None else np.asarray(initial_mean, np.float64)
+        self.initial_covariance = eye if initial_covariance is None else np.atleast_2d(initial_covariance)
+        self.transition_matrix = eye if transition_matrix is None else np.atleast_2d(transition_matrix)
+        self.transition_covariance = eye if transition_covariance is None else np.atleast_2d(transition_covariance)
+        self.likelihood_matrix = eye if likelihood_matrix is None else np.atleast_2d(likelihood_matrix)
+        self.dim_obs = self.likelihood_matrix.shape[0]
+        self.likelihood_covariance = np.eye(self.dim_obs) if likelihood_covariance is None \
+            else np.atleast_2d(likelihood_covariance)
+
+    def _ssm(self, dt=None):
+        return models.make_lg_ssm(self.initial_mean, self.initial_covariance, self.transition_matrix,
+                                  self.transition_covariance, self.likelihood_matrix, self.likelihood_covariance)
+
+    def simulate(self, t_all, random_key):
+        """ssm/ssm.py:138-163 (host; data generation is not on the hot path)."""
+        rng = np.random.default_rng(key_to_seed(random_key))
+        T = len(t_all)
+        L0, LQ, LR = (np.linalg.cholesky(a) for a in (self.initial_covariance, self.transition_covariance,
+                                                     self.likelihood_covariance))
+        x = np.empty((T, self.dim))
+        x[0] = self.initial_mean + L0 @ rng.standard_normal(self.dim)
+        for i in range(1, T):
+            x[i] = self.transition_matrix @ x[i - 1] + LQ @ rng.standard_normal(self.dim)
+        y = x @ self.likelihood_matrix.T + rng.standard_normal((T, self.dim_obs)) @ LR.T
+        return cdict(x=x, y=y, t=np.asarray(t_all), name=f'{self.name} simulation')
+
+
+class Lorenz96(StateSpaceModel):
+    """ssm/scenarios/lorenz96.py:29-44 on NonLinearGaussian (ssm/nonlinear_gaussian.py:19-131) with the
+    reference defaults Q = R = P0 = I, H = I, m0 = 0 (isotropic std's may be changed)."""
+    name = 'Lorenz 96'
+
+    def __init__(self, dim=40, forcing_constant=8., substeps=1, transition_std=1.0, likelihood_std=1.0,
+                 initial_mean=0.0, initial_std=1.0, name=None):
+        if name is not None:
+            self.name = name
+        self.dim = self.dim_obs = int(dim)
+        self.forcing_constant, self.substeps = float(forcing_constant), int(substeps)
+        self.transition_std, self.likelihood_std = float(transition_std), float(likelihood_std)
+        self.initial_mean, self.initial_std = float(initial_mean), float(initial_std)
+
+    def _ssm(self, dt=None):
+        return models.make_lorenz96(self.dim, self.forcing_constant, 0.05 if dt is None else dt, self.substeps,
+                                    self.transition_std, self.likelihood_std, self.initial_mean, self.initial_std)
+
+
+class ParticleFilter:
+    """ssm/filtering.py:20-139 (interface)."""
+    name = 'Particle Filter'
+
+    def __init__(self, name=None):
+        if name is not None:
+            self.name = name
+
+    def __repr__(self):
+        return f"mocat.ParticleFilter.{self.__class__.__name__}"
+
+    def startup(self, ssm_scenario):
+        pass
+
+
+class BootstrapFilter(ParticleFilter):
+    """ssm/filtering.py:142-170: proposal = transition, weight increment = -likelihood_potential."""
+    name = 'Bootstrap Filter'
+
+
+def _check_filter(pf):
+    if not isinstance(pf, BootstrapFilter):
+        raise _lib.MocatB200Error("only BootstrapFilter is compiled into the device step (no CPU fallback)")
+
+
+def _moments(eng):
+    mean, var = engine.weighted_moments(eng.x, eng.n, eng.lw, eng.ctl)
+    return mean, var
+
+
+def initiate_particles(ssm_scenario, particle_filter, n, random_key, y=None, t=None, ess_threshold=0.5,
+                       resampling='multinomial'):
+    """ssm/filtering.py:173-193."""
+    torch = _torch()
+    _check_filter(particle_filter)
+    particle_filter.startup(ssm_scenario)
+    if y is None:
+        raise _lib.MocatB200Error("initiate_particles needs the first observation y")
+    y = np.atleast_1d(np.asarray(y, np.float32))
+    eng = engine.PFEngine(ssm_scenario._ssm(), n, key_to_seed(random_key), ess_threshold=ess_threshold,
+                          resampling=_RESAMPLING[resampling])
+    eng.init(torch.as_tensor(y, device="cuda"))
+    c = eng.ctl.read()
+    mean, var = _moments(eng)
+    return cdict(value=eng.values().cpu().numpy()[None], log_weight=eng.lw.cpu().numpy()[None],
+                 t=np.atleast_1d(t) if t is not None else np.zeros(1), y=y[None],
+                 ess=np.atleast_1d(c['ess']), log_norm_constant=np.atleast_1d(c['log_z']),
+                 mean=mean.cpu().numpy()[None], var=var.cpu().numpy()[None], engine=eng)
+
+
+def propagate_particle_filter(ssm_scenario, particle_filter, particles, y_new, t_new, random_key=None,
+                              ess_threshold=0.5, resample_full=True):
+    """ssm/filtering.py:220-252: resample iff ess[-1] < ess_threshold*n, propose, weight, append."""
+    torch = _torch()
+    _check_filter(particle_filter)
+    eng = particles.engine
+    eng.ess_threshold = float(ess_threshold)
+    y_new = np.atleast_1d(np.asarray(y_new, np.float32))
+    t_prev = float(particles.t[-1])
+    eng.ssm = ssm_scenario._ssm(float(t_new) - t_prev)
+    # the resample decision for this step was taken on the device with the threshold stored in the control
+    # block by the previous step; refresh it if the caller changed ess_threshold
+    c = eng.ctl.read()
+    want = 1 if c['ess'] < ess_threshold * eng.n_total else 0
+    if want != c['resample']:
+        c['resample'] = want
+        eng.ctl.write(c)
+    eng.step(torch.as_tensor(y_new, device="cuda"))
+    c = eng.ctl.read()
+    mean, var = _moments(eng)
+    out = particles.copy()
+    out.value = np.append(particles.value, eng.values().cpu().numpy()[None], axis=0)
+    out.log_weight = np.append(particles.log_weight, eng.lw.cpu().numpy()[None], axis=0)
+    out.y = np.append(particles.y, y_new[None], axis=0)
+    out.t = np.append(particles.t, t_new)
+    out.ess = np.append(particles.ess, c['ess'])
+    out.log_norm_constant = np.append(particles.log_norm_constant, c['log_z'])
+    out.mean = np.append(particles.mean, mean.cpu().numpy()[None], axis=0)
+    out.var = np.append(particles.var, var.cpu().numpy()[None], axis=0)
+    return out
+
+
+def run_particle_filter_for_marginals(ssm_scenario, particle_filter, y, t, random_key, n=None, initial_sample=None,
+                                      ess_threshold=0.5, resampling='multinomial', keep_history=None,
+                                      moments=True):
+    """ssm/filtering.py:255-324.  The time loop is enqueued without any host synchronisation."""
+    torch = _torch()
+    _check_filter(particle_filter)
+    y = np.asarray(y, np.float32)
+    if y.ndim == 1:
+        y = y[..., np.newaxis]
+    t = np.asarray(t, np.float64)
+    if initial_sample is not None:
+        raise _lib.MocatB200Error("initial_sample continuation: use propagate_particle_filter")
+    T = len(y)
+    dt = float(t[1] - t[0]) if T > 1 else None
+    if T > 2 and not np.allclose(np.diff(t), dt):
+        raise _lib.MocatB200Error("run_particle_filter_for_marginals needs equally spaced t (time-homogeneous model)")
+    eng = engine.PFEngine(ssm_scenario._ssm(dt), n, key_to_seed(random_key), ess_threshold=ess_threshold,
+                          resampling=_RESAMPLING[resampling])
+    d = eng.d
+    if keep_history is None:
+        keep_history = T * n * (d + 1) * 4 <= HISTORY_AUTO_BYTES
+    yd = torch.as_tensor(y, device="cuda")
+    vals, lws, means, vars_ = [], [], [], []
+
+    def record():
+        if keep_history:
+            vals.append(eng.values().clone(memory_format=_torch().contiguous_format))
+            lws.append(eng.lw.clone())
+        if moments:
+            m, v = _moments(eng)
+            means.append(m)
+            vars_.append(v)
+
+    eng.init(yd[0])
+    record()
+    for i in range(1, T):
+        eng.step(yd[i])
+        record()
+    hist = eng.ctl.read_hist(T)
+    out = cdict(t=t, y=y, ess=hist['ess'].copy(), log_norm_constant=hist['log_z'].copy(),
+                resampled=hist['resampled'].copy(), engine=eng)
+    if keep_history:
+        out.value = torch.stack(vals).cpu().numpy()
+        out.log_weight = torch.stack(lws).cpu().numpy()
+    else:
+        out.value = eng.values().cpu().numpy()[None]
+        out.log_weight = eng.lw.cpu().numpy()[None]
+    if moments:
+        out.mean = torch.stack(means).cpu().numpy()
+        out.var = torch.stack(vars_).cpu().numpy()
+    return out
+
+
+def run_kalman_filter_for_marginals(lgssm_scenario, y, t, return_log_likelihood=False):
+    """ssm/linear_gaussian/kalman.py:16-57 (exact filtering means/covariances; O(T d^3) host control-plane
+    algebra used only as a cross-check, not part of the particle hot path).  Fixes kalman.py:20 (cov_0 is
+    L0 L0^T here; identical when P0 = I) and can also return the innovation log-likelihood."""
+    y = np.asarray(y, np.float64)
+    if y.ndim == 1:
+        y = y[:, None]
+    s = lgssm_scenario
+    F, H, Q, R = s.transition_matrix, s.likelihood_matrix, s.transition_covariance, s.likelihood_covariance
+    mu, cov = np.asarray(s.initial_mean, np.float64).copy(), np.asarray(s.initial_covariance, np.float64).copy()
+    T = len(y)
+    mus, covs, ll = np.empty((T, s.dim)), np.empty((T, s.dim, s.dim)), 0.0
+    for i in range(T):
+        if i > 0:
+            mu, cov = F @ mu, F @ cov @ F.T + Q
+        S = H @ cov @ H.T + R
+        innov = y[i] - H @ mu
+        ll += -0.5 * (innov @ np.linalg.solve(S, innov) + np.linalg.slogdet(S)[1] + s.dim_obs * np.log(2 * np.pi))
+        K = cov @ H.T @ np.linalg.inv(S)
+        mu, cov = mu + K @ innov, cov - K @ H @ cov
+        mus[i], covs[i] = mu, cov
+    return (mus, covs, ll) if return_log_likelihood else (mus, covs)

@@ -1,0 +1,317 @@
+"""Population (transport) samplers: host mirror of mocat/src/transport/{sampler,smc,svgd}.py.
+
+Constructor signatures, parameter names, criteria (`<=` vs `<`), schedules and returned fields follow the
+reference; the per-iteration work is enqueued on the device through mocat_b200.engine.  Extra keyword
+arguments (ours): `resampling` ('multinomial' as in the reference | 'systematic'), `keep_history`
+(None = auto: the full (iters+1, n, d) stack the reference returns is kept when it is small, otherwise only
+the final population is returned with a leading axis of length 1), `check_every` (iterations between
+termination polls).
+"""
+import numpy as np
+
+from . import _lib, engine, models
+from .core import cdict, key_to_seed
+from .mcmc import MCMCSampler
+from .sample import Sampler
+
+_RESAMPLING = {'multinomial': _lib.RESAMPLE_MULTINOMIAL, 'systematic': _lib.RESAMPLE_SYSTEMATIC}
+HISTORY_AUTO_BYTES = 1 << 30
+
+
+def _torch():
+    import torch
+    return torch
+
+
+class TransportSampler(Sampler):
+    """transport/sampler.py:16-51."""
+
+    def startup(self, scenario, n, initial_state, initial_extra, **kwargs):
+        initial_state, initial_extra = super().startup(scenario, n, initial_state, initial_extra, **kwargs)
+        return initial_state, initial_extra
+
+    def termination_criterion(self, ensemble_state, extra):
+        return extra.iter >= self.max_iter
+
+
+class SMCSampler(TransportSampler):
+    """transport/smc.py:23-99."""
+    name = 'SMC Sampler'
+
+
+class TemperedSMCSampler(SMCSampler):
+    """transport/smc.py:102-225."""
+    name = 'Tempered SMC Sampler'
+
+    def __init__(self, temperature_schedule=None, max_temperature=1., max_iter=int(1e4), **kwargs):
+        self.max_iter = max_iter
+        self.max_temperature = max_temperature
+        self.temperature_schedule = temperature_schedule
+        super().__init__(**kwargs)
+
+    def __setattr__(self, key, value):                                 # smc.py:115-126
+        if key == 'temperature_schedule':
+            if value is None:
+                if getattr(self, 'temperature_schedule', None) is not None \
+                        and self.max_iter == len(self.temperature_schedule):
+                    self.max_iter = int(1e4)
+            else:
+                value = np.asarray(value, np.float64)
+                self.max_temperature = float(value[-1])
+                self.max_iter = len(value)
+        super().__setattr__(key, value)
+
+    def clean_chain(self, scenario, chain_ensemble_state):             # smc.py:177-184
+        scenario.temperature = float(chain_ensemble_state.temperature[-1])
+        return chain_ensemble_state
+
+
+class MetropolisedSMCSampler(TemperedSMCSampler):
+    """transport/smc.py:228-373."""
+    name = "Metropolised SMC Sampler"
+
+    def __init__(self, mcmc_sampler, mcmc_correction='sampler_default', mcmc_steps=1, max_iter=int(1e4),
+                 temperature_schedule=None, max_temperature=1., ess_threshold_retain=0.9,
+                 ess_threshold_resample=0.5, bisection_tol=1e-5, max_bisection_iter=1000,
+                 resampling='multinomial', keep_history=None, check_every=8, **kwargs):
+        if temperature_schedule is not None and temperature_schedule[0] == 0.:      # smc.py:243-245
+            temperature_schedule = temperature_schedule[1:]
+        super().__init__(max_iter=max_iter, temperature_schedule=temperature_schedule,
+                         max_temperature=max_temperature, **kwargs)
+        if isinstance(mcmc_sampler, type):
+            mcmc_sampler = mcmc_sampler()
+        if not isinstance(mcmc_sampler, MCMCSampler) or mcmc_sampler.move_kind is None:
+            raise _lib.MocatB200Error("mcmc_sampler must be mocat_b200.RandomWalk or mocat_b200.Underdamped "
+                                      "(the moves compiled into the device kernel)")
+        self.mcmc_sampler = mcmc_sampler
+        self.parameters.mcmc_steps = mcmc_steps
+        self.parameters.ess_threshold_retain = ess_threshold_retain
+        self.parameters.ess_threshold_resample = ess_threshold_resample
+        self.parameters.bisection_tol = bisection_tol
+        self.parameters.max_bisection_iter = max_bisection_iter
+        self.resampling = resampling
+        self.keep_history = keep_history
+        self.check_every = check_every
+
+    def __setattr__(self, key, value):                                 # smc.py:261-265
+        if key == 'temperature_schedule' and value is not None and value[0] == 0.:
+            value = value[1:]
+        super().__setattr__(key, value)
+
+    # -- state <-> host ---------------------------------------------------------------------------------
+    _FIELDS = ('value', 'log_weight', 'prior_potential', 'likelihood_potential', 'alpha')
+
+    def _snapshot(self, eng):
+        """device clones of the per-particle fields (Appendix B of SURVEY.md; gradients and momenta are
+        recomputed inside the move and not stored)"""
+        return dict(value=eng.values().clone(memory_format=_torch().contiguous_format), log_weight=eng.lw.clone(), prior_potential=eng.up.clone(),
+                    likelihood_potential=eng.lik.clone(), alpha=eng.alpha.clone())
+
+    def startup(self, scenario, n, initial_state, initial_extra, **kwargs):
+        initial_state, initial_extra = super().startup(scenario, n, initial_state, initial_extra, **kwargs)
+        P = self.parameters
+        ms = self.mcmc_sampler
+        stepsize = getattr(initial_extra.parameters, 'stepsize', None)
+        if stepsize is None:
+            stepsize = ms.parameters.stepsize
+        if stepsize is None:
+            raise _lib.MocatB200Error("mcmc_sampler.parameters.stepsize must be set")
+        target = scenario._target()
+        move = models.make_move(ms.move_kind, stepsize, P.mcmc_steps, getattr(ms.parameters, 'leapfrog_steps', 1))
+        temper = models.make_temper(self.max_temperature, P.ess_threshold_retain, P.ess_threshold_resample,
+                                    P.bisection_tol, P.max_bisection_iter, self.max_iter)
+        seed = key_to_seed(getattr(initial_extra, 'random_key', None))
+        eng = engine.SMCEngine(target, move, temper, n, seed, resampling=_RESAMPLING[self.resampling],
+                               schedule=self.temperature_schedule)
+        x0 = None if initial_state is None else getattr(initial_state, 'value', None)
+        eng.startup(x0)                                                 # smc.py:128-164, 267-296 on the device
+        scenario.temperature = 0.
+        initial_extra.engine = eng
+        initial_extra.resample_bool = True
+        if initial_state is None:
+            initial_state = cdict()
+        initial_state.engine = eng
+        return initial_state, initial_extra
+
+    def update(self, scenario, ensemble_state, extra):                 # smc.py:219-225 / 73-99
+        extra.engine.update()
+        extra.iter = extra.iter + 1
+        return ensemble_state, extra
+
+    def termination_criterion(self, ensemble_state, extra):            # smc.py:171-175 (evaluated on device)
+        return bool(extra.engine.ctl.read()['done'])
+
+    def fetch(self, ensemble_state):
+        """materialise the current device population as a cdict of NumPy arrays"""
+        eng = ensemble_state.engine
+        c = eng.ctl.read()
+        snap = {k: v.cpu().numpy() for k, v in self._snapshot(eng).items()}
+        out = cdict(**snap)
+        out.potential = out.prior_potential + c['beta'] * out.likelihood_potential
+        out.temperature, out.ess, out.log_norm_constant = c['beta'], c['ess'], c['log_z']
+        return out
+
+    def _run_device(self, scenario, initial_state, initial_extra):
+        torch = _torch()
+        eng = initial_extra.engine
+        n, d = eng.n, eng.d
+        keep = self.keep_history
+        if keep is None:
+            keep = n * (d + 4) * 4 * min(self.max_iter + 1, 64) <= HISTORY_AUTO_BYTES
+        snaps = [self._snapshot(eng)] if keep else None
+        it = 0
+        while it < self.max_iter:
+            burst = min(self.check_every, self.max_iter - it)
+            for _ in range(burst):
+                eng.update()
+                it += 1
+                if keep:
+                    snaps.append(self._snapshot(eng))
+            if eng.ctl.read()['done']:
+                break
+        c = eng.ctl.read()
+        iters = int(c['iter'])
+        hist = eng.ctl.read_hist(iters + 1)
+        chain = cdict()
+        if keep:
+            snaps = snaps[:iters + 1]
+            for k in self._FIELDS:
+                setattr(chain, k, torch.stack([s[k] for s in snaps]).cpu().numpy())
+            betas = hist['beta'][:, None]
+        else:
+            for k, v in self._snapshot(eng).items():
+                setattr(chain, k, v.cpu().numpy()[None])
+            betas = hist['beta'][-1:, None]
+        chain.potential = chain.prior_potential + betas * chain.likelihood_potential
+        chain.temperature = hist['beta'].copy()
+        chain.ess = hist['ess'].copy()
+        chain.log_norm_constant = hist['log_z'].copy()
+        chain.alpha_mean = hist['alpha_mean'].copy()
+        chain.resampled = hist['resampled'].copy()
+        chain.bisection_iters = hist['search_iters'].copy()
+        initial_extra.iter = iters
+        return chain
+
+
+class RMMetropolisedSMCSampler(MetropolisedSMCSampler):
+    """transport/smc.py:376-428 (Robbins-Monro stepsize adaptation between iterations): not yet compiled
+    into the device step."""
+
+    def __init__(self, *args, **kwargs):
+        raise _lib.MocatB200Error("RMMetropolisedSMCSampler is not built yet (no CPU fallback)")
+
+
+# ======================================================================================================
+def adagrad(step_size, momentum=0.9):
+    """marker mirroring jax.example_libraries.optimizers.adagrad (the optimiser SVGD defaults to)."""
+    return ('adagrad', step_size, momentum)
+
+
+class SVGD(TransportSampler):
+    """transport/svgd.py:42-146.  `adapt(ensemble_state, extra)` may be overridden exactly as in the
+    reference (tests/test_transport.py:76-89); `ensemble_state.value` is then a device tensor and
+    mocat_b200.kernels.median_bandwidth_update / mean_bandwidth_update run on the device."""
+    name = 'SVGD'
+
+    def __init__(self, stepsize, max_iter=1000, kernel=None, kernel_params=None, ensemble_batchsize=None,
+                 optimiser=adagrad, keep_history=None, phi_variant=0, **optim_params):
+        super().__init__(max_iter=max_iter)
+        from .kernels import Gaussian
+        self._default_adapt = False
+        if kernel is None:
+            kernel = Gaussian()
+            if type(self).adapt is SVGD.adapt:
+                self._default_adapt = True                              # svgd.py:59-62: mean bandwidth
+        if not isinstance(kernel, Gaussian):
+            raise _lib.MocatB200Error("only the Gaussian kernel is compiled into the device interaction")
+        if kernel_params is None:
+            kernel_params = kernel.parameters
+        if optimiser is not adagrad:
+            raise _lib.MocatB200Error("only adagrad (the reference default) is compiled for the device")
+        self.parameters.stepsize = stepsize
+        self.kernel = kernel
+        self.parameters.kernel_params = kernel_params
+        self.parameters.ensemble_batchsize = ensemble_batchsize
+        self.parameters.optim_params = optim_params
+        self.keep_history = keep_history
+        self.phi_variant = phi_variant
+
+    def adapt(self, ensemble_state, extra):                             # svgd.py:109-113
+        if self._default_adapt:
+            from .kernels import mean_bandwidth_update
+            extra.parameters.kernel_params.bandwidth = mean_bandwidth_update(ensemble_state.value)
+        return ensemble_state, extra
+
+    def _bandwidth_tensor(self, extra, device):
+        torch = _torch()
+        h = extra.parameters.kernel_params.bandwidth
+        if isinstance(h, torch.Tensor):
+            return h.to(device=device, dtype=torch.float32).reshape(1)
+        return torch.tensor([float(h)], dtype=torch.float32, device=device)
+
+    def startup(self, scenario, n, initial_state, initial_extra, **kwargs):
+        torch = _torch()
+        initial_state, initial_extra = super().startup(scenario, n, initial_state, initial_extra, **kwargs)
+        P = self.parameters
+        if P.ensemble_batchsize is not None and P.ensemble_batchsize != n:
+            raise _lib.MocatB200Error("ensemble minibatching (ensemble_batchsize < n) is not built for the device")
+        dev = torch.device("cuda", torch.cuda.current_device())
+        seed = key_to_seed(getattr(initial_extra, 'random_key', None))
+        if initial_state is None or getattr(initial_state, 'value', None) is None:
+            # transport/sampler.py:24-30: vmap(prior_sample); same Philox stream as the SMC init kernel
+            tgt = scenario._target()
+            tgt.kind = _lib.LIK_NONE
+            tmp = engine.SMCEngine(tgt, models.make_move(_lib.MOVE_RW, 1.0), models.make_temper(), n, seed)
+            L = _lib.get()
+            import ctypes as C
+            L.call("mb_smc_init", L.ctx(), C.byref(tgt), _lib.ptr(tmp.x), tmp.ld, n, n, 1, _lib.ptr(tmp.up),
+                   _lib.ptr(tmp.lik), _lib.ptr(tmp.lw), seed, 0, _lib.ptr(tmp.ctl.t), _lib.stream())
+            X = tmp.values().contiguous()
+            initial_state = cdict()
+        else:
+            X = torch.as_tensor(np.asarray(initial_state.value, np.float32), device=dev).contiguous()
+        st = cdict(value=X)
+        st.potential, st.grad_potential = engine.target_potential_grad(scenario._target(), scenario.temperature, X)
+        initial_extra.parameters.kernel_params = self.parameters.kernel_params
+        st, initial_extra = self.adapt(st, initial_extra)                # svgd.py:102
+        initial_extra.gsq = torch.zeros_like(X)
+        initial_extra.mom = torch.zeros_like(X)
+        initial_extra.target = scenario._target()
+        return st, initial_extra
+
+    def update(self, scenario, ensemble_state, extra):                  # svgd.py:122-146
+        extra.iter = extra.iter + 1
+        X = ensemble_state.value
+        h = self._bandwidth_tensor(extra, X.device)
+        phi = engine.svgd_phi(X, ensemble_state.grad_potential, h, self.phi_variant)
+        step = self.parameters.stepsize
+        step = float(step(extra.iter)) if callable(step) else float(step)
+        engine.adagrad_step(X, extra.gsq, extra.mom, phi, step, self.parameters.optim_params.get('momentum', 0.9))
+        ensemble_state.potential, ensemble_state.grad_potential = \
+            engine.target_potential_grad(extra.target, scenario.temperature, X)
+        ensemble_state, extra = self.adapt(ensemble_state, extra)
+        return ensemble_state, extra
+
+    def _run_device(self, scenario, state, extra):
+        torch = _torch()
+        n, d = state.value.shape
+        keep = self.keep_history
+        if keep is None:
+            keep = n * d * 4 * (self.max_iter + 1) <= HISTORY_AUTO_BYTES
+        vals = [state.value.clone()] if keep else None
+        pots = [state.potential.clone()] if keep else None
+        while not self.termination_criterion(state, extra):
+            state, extra = self.update(scenario, state, extra)
+            if keep:
+                vals.append(state.value.clone())
+                pots.append(state.potential.clone())
+        chain = cdict()
+        if keep:
+            chain.value = torch.stack(vals).cpu().numpy()
+            chain.potential = torch.stack(pots).cpu().numpy()
+        else:
+            chain.value = state.value.cpu().numpy()[None]
+            chain.potential = state.potential.cpu().numpy()[None]
+        chain.grad_potential = state.grad_potential.cpu().numpy()[None]
+        chain.bandwidth = float(self._bandwidth_tensor(extra, state.value.device).item())
+        return chain

@@ -77,6 +77,30 @@ class TemperedSMC:
         return (st['beta'] >= self.max_temperature or st['iter'] >= self.max_iter
                 or np.isnan(st['x']).mean() > 0.1)
 
+    # -- vmap(forward_proposal) (smc.py:91-95, 337-365) ---------------------------------------------
+    def _move(self, x, gid, it, beta):
+        """MCMC startup re-evaluates the potentials at the current temperature (standard_mcmc.py:94-102),
+        then mcmc_steps Metropolised moves; returns (x, U_prior, U_lik, mean alpha)."""
+        d = self.d
+        n = x.shape[0]
+        nz = (d + 3) // 4
+        S = nz + 1
+        alphas = np.zeros(n)
+        up_c, lik_c, U, g = self._eval(x, beta)
+        for s in range(self.mcmc_steps):
+            z = philox.normals(self.seed, gid, it, philox.P_MOVE, d, index0=s * S, dtype=self.normal_dtype)
+            u = philox.u24(philox.raw(self.seed, gid, it, philox.P_MOVE, s * S + nz)[0]).astype(np.float64)
+            if self.move == 'mala':
+                pg = lambda xx: self._eval(xx, beta)[2:]
+                x, U, g, alpha, _ = mcmc.hmc_step(pg, x, U, g, z, u, self.stepsize, self.L)
+            else:
+                pot = lambda xx: self._eval(xx, beta)[2]
+                x, U, alpha, _ = mcmc.rw_step(pot, x, U, z, u, self.stepsize)
+            alphas += alpha
+        up, _ = self.prior.potential_and_grad(x)                       # :362
+        lik, _ = self.lik.potential_and_grad(x)                        # carried directly (see header)
+        return x, up, lik, alphas
+
     # -- one population step (smc.py:73-99 + 193-217) ---------------------------------------------
     def update(self, st):
         n, d = self.n, self.d
@@ -96,23 +120,7 @@ class TemperedSMC:
             x, up, lik = x[anc], up[anc], lik[anc]
             lw = np.zeros(n)
             ess = float(n)
-        # move (:337-365): MCMC startup re-evaluates potentials at the current temperature
-        nz = (d + 3) // 4
-        S = nz + 1
-        alphas = np.zeros(n)
-        up_c, lik_c, U, g = self._eval(x, beta)
-        for s in range(self.mcmc_steps):
-            z = philox.normals(self.seed, self.gid, it, philox.P_MOVE, d, index0=s * S, dtype=self.normal_dtype)
-            u = philox.u24(philox.raw(self.seed, self.gid, it, philox.P_MOVE, s * S + nz)[0]).astype(np.float64)
-            if self.move == 'mala':
-                pg = lambda xx: self._eval(xx, beta)[2:]
-                x, U, g, alpha, _ = mcmc.hmc_step(pg, x, U, g, z, u, self.stepsize, self.L)
-            else:
-                pot = lambda xx: self._eval(xx, beta)[2]
-                x, U, alpha, _ = mcmc.rw_step(pot, x, U, z, u, self.stepsize)
-            alphas += alpha
-        up, _ = self.prior.potential_and_grad(x)                       # :362
-        lik, _ = self.lik.potential_and_grad(x)                        # carried directly (see header)
+        x, up, lik, alphas = self._move(x, self.gid, it, beta)
         # adapt (:193-217)
         beta_new, its = self._next_temperature(lw, lik, beta, ess, it)
         self.bisect_iters.append(its)

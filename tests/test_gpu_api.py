@@ -1,0 +1,182 @@
+"""The reference's own end-to-end tests, run through the drop-in host API on the device
+(mocat/src/tests/test_transport.py, test_ssm.py, test_ssm_linear_gaussian.py, test_abc_gk.py,
+test_kernels.py) -- same scenarios, sample sizes and tolerances."""
+import numpy as np
+import numpy.testing as npt
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+COV = np.array([[1., 0.9], [0.9, 2.]])
+POST_COV = np.linalg.inv(np.linalg.inv(COV) + np.eye(2) / 49.0)
+
+
+@pytest.fixture(scope="module")
+def mocat(lib):
+    import mocat_b200
+    return mocat_b200
+
+
+def _scenario(mocat):
+    # tests/test_transport.py:26-28: Gaussian(covariance), prior_sample = 7 z, prior_potential = .5 (x/7^2)^2
+    return mocat.scenarios.Gaussian(covariance=COV, prior_std=7.0, prior_pscale=1 / 49.0)
+
+
+def _resample_final(sample, n, seed=1):
+    from oracle import core
+    cdf = core.cdf_from_log_weights(sample.log_weight[-1])
+    return sample.value[-1][core.ancestors_multinomial(cdf, np.random.default_rng(seed).random(n))]
+
+
+def _check_smc(mocat, sample, n):
+    vals = _resample_final(sample, n)                                    # test_transport.py:57-62
+    npt.assert_array_almost_equal(vals.mean(0), np.zeros(2), decimal=0)
+    npt.assert_array_almost_equal(np.cov(vals.T), POST_COV, decimal=1)
+    lik_prec = np.linalg.inv(COV)
+    dets = np.array([np.linalg.det(np.linalg.inv(lik_prec * t + np.eye(2) / 49.0)) for t in sample.temperature])
+    npt.assert_array_almost_equal(sample.log_norm_constant, 0.5 * (np.log(dets) - 4 * np.log(7)), 0)   # :49-55
+
+
+PRESCHEDULE = np.arange(0., 1.1, 0.1)
+
+
+def test_tempered_preschedule_RW(mocat):
+    n = 10_000
+    sample = mocat.run(_scenario(mocat), mocat.MetropolisedSMCSampler(mocat.RandomWalk(stepsize=1.0)), n,
+                       random_key=np.array([0, 0], np.uint32), temperature_schedule=PRESCHEDULE)
+    _check_smc(mocat, sample, n)
+    npt.assert_array_equal(sample.temperature, PRESCHEDULE[1:])          # test_transport.py:134
+    assert sample.value.shape == (len(PRESCHEDULE) - 1, n, 2)
+    assert sample.time > 0 and sample.summary.sampler == "Metropolised SMC Sampler"
+
+
+def test_tempered_preschedule_UD(mocat):
+    n = 10_000
+    sample = mocat.run(_scenario(mocat), mocat.MetropolisedSMCSampler(mocat.Underdamped(stepsize=1.0)), n,
+                       random_key=0, temperature_schedule=PRESCHEDULE)
+    _check_smc(mocat, sample, n)
+    npt.assert_array_equal(sample.temperature, PRESCHEDULE[1:])
+
+
+def test_tempered_adaptive_RW(mocat):
+    n = 10_000
+    sample = mocat.run(_scenario(mocat), mocat.MetropolisedSMCSampler(mocat.RandomWalk(stepsize=1.0)), n, random_key=0)
+    _check_smc(mocat, sample, n)
+    assert sample.temperature[-1] == 1.0
+
+
+def test_tempered_adaptive_UD(mocat):
+    n = 10_000
+    sample = mocat.run(_scenario(mocat),
+                       mocat.MetropolisedSMCSampler(mocat.Underdamped(stepsize=1.0, leapfrog_steps=10)), n, random_key=0)
+    _check_smc(mocat, sample, n)
+
+
+def test_host_buffers_in_and_history_off(mocat):
+    n = 50_000
+    x0 = (np.random.default_rng(0).standard_normal((n, 5)) * 3).astype(np.float32)
+    sc = mocat.scenarios.Rastrigin(dim=5, a=1.0, prior_std=3.0)
+    sample = mocat.run(sc, mocat.MetropolisedSMCSampler(mocat.Underdamped(stepsize=0.1), max_iter=5,
+                                                        resampling='systematic', keep_history=False),
+                       n, random_key=1, initial_state=mocat.cdict(value=x0))
+    assert sample.value.shape == (1, n, 5) and len(sample.temperature) == 6
+    assert np.all(np.diff(sample.temperature) > 0)
+    # potential() through the device kernel equals prior + T * likelihood of the returned fields
+    sc.temperature = float(sample.temperature[-1])
+    U = sc.potential(sample.value[0][:100])
+    npt.assert_allclose(U, sample.potential[0][:100], rtol=2e-5, atol=1e-4)
+
+
+# ------------------------------------------------------------------------------------------------ SVGD
+def _check_moments(vals):
+    npt.assert_array_almost_equal(vals.mean(0), np.zeros(2), decimal=0)
+    npt.assert_array_almost_equal(np.cov(vals.T), POST_COV, decimal=1)
+
+
+def test_svgd_mean_bandwidth_default(mocat):                              # test_transport.py:69-74
+    sample = mocat.run(_scenario(mocat), mocat.SVGD(max_iter=1000, stepsize=0.8), n=100, random_key=0)
+    assert sample.value.shape == (1001, 100, 2)
+    _check_moments(sample[-1].value)
+
+
+def test_svgd_median_update_subclass(mocat):                              # test_transport.py:76-89
+    class SVGD_median(mocat.SVGD):
+        def adapt(self, ensemble_state, ensemble_extra):
+            ensemble_extra.parameters.kernel_params.bandwidth = mocat.kernels.median_bandwidth_update(ensemble_state.value)
+            ensemble_state.kernel_params = ensemble_extra.parameters.kernel_params
+            return ensemble_state, ensemble_extra
+
+    sample = mocat.run(_scenario(mocat), SVGD_median(max_iter=1000, stepsize=1.0), n=100, random_key=0)
+    _check_moments(sample[-1].value)
+
+
+def test_svgd_callable_stepsize(mocat):                                   # test_transport.py:106-111
+    sample = mocat.run(_scenario(mocat), mocat.SVGD(max_iter=1000, stepsize=lambda i: 10 * i ** -0.5), n=100,
+                       random_key=0)
+    _check_moments(sample[-1].value)
+
+
+def test_gaussian_kernel_kat(mocat):                                      # test_kernels.py:16-29
+    k = mocat.kernels.Gaussian()
+    z, o = np.zeros(5), np.ones(5)
+    npt.assert_array_almost_equal(k(z, z), 1.)
+    npt.assert_array_almost_equal(k(z, o), 0.082085006)
+    npt.assert_array_almost_equal(k.grad_x(z, o), np.ones(5) * 0.082085006)
+    npt.assert_array_almost_equal(k.grad_y(z, o), np.ones(5) * -0.082085006)
+
+
+# ------------------------------------------------------------------------------------------------ SSM
+@pytest.mark.parametrize("dim", [1, 5])
+def test_bootstrap_pf_coverage_and_kalman(mocat, dim):
+    """tests/test_ssm.py:33-44 (truth between particle min and max at every t, n=2e3, T=20) and
+    tests/test_ssm_linear_gaussian.py:71-104 (Kalman mean within 3/4 sigma of the truth)."""
+    ssm = mocat.ssm.TimeHomogenousLinearGaussian(initial_mean=np.zeros(dim), initial_covariance=np.eye(dim),
+                                                 transition_matrix=np.eye(dim), transition_covariance=np.eye(dim),
+                                                 likelihood_matrix=np.eye(dim), likelihood_covariance=np.eye(dim))
+    t = np.arange(20, dtype=np.float64)
+    sim = ssm.simulate(t, random_key=0)
+    pf = mocat.ssm.run_particle_filter_for_marginals(ssm, mocat.ssm.BootstrapFilter(), sim.y, t, random_key=0, n=2000)
+    assert pf.value.shape == (20, 2000, dim) and pf.log_weight.shape == (20, 2000) and pf.ess.shape == (20,)
+    assert np.all(pf.value.min(1) <= sim.x) and np.all(sim.x <= pf.value.max(1))
+    mus, covs, ll = mocat.ssm.run_kalman_filter_for_marginals(ssm, sim.y, t, return_log_likelihood=True)
+    sd = np.sqrt(np.einsum('tii->ti', covs))
+    k = 3 if dim == 1 else 4
+    assert np.all(np.abs(mus - sim.x) < k * sd)
+    npt.assert_allclose(pf.mean, mus, atol=0.35)
+    assert abs(pf.log_norm_constant[-1] - ll) < 1.0 + dim
+    # online API (filtering.py:173-252): same result as the batch call when driven step by step
+    p = mocat.ssm.initiate_particles(ssm, mocat.ssm.BootstrapFilter(), 2000, 0, sim.y[0], t[0])
+    for i in range(1, 5):
+        p = mocat.ssm.propagate_particle_filter(ssm, mocat.ssm.BootstrapFilter(), p, sim.y[i], t[i], 0)
+    npt.assert_allclose(p.ess, pf.ess[:5], rtol=1e-6)
+    npt.assert_array_equal(p.value, pf.value[:5])
+
+
+def test_lorenz96_filter_runs(mocat):
+    from oracle import models as omodels
+    d = 40
+    _, y = omodels.Lorenz96SSM(dim=d).simulate(10, np.random.default_rng(0), spinup=300)
+    ssm = mocat.ssm.Lorenz96(dim=d)
+    out = mocat.ssm.run_particle_filter_for_marginals(ssm, mocat.ssm.BootstrapFilter(), y, np.arange(10) * 0.05,
+                                                      random_key=3, n=100_000, ess_threshold=2.0,
+                                                      resampling='systematic', keep_history=False)
+    assert out.value.shape == (1, 100_000, d) and np.all(np.isfinite(out.log_norm_constant))
+    assert np.all(out.resampled[1:] == 1)
+
+
+# ------------------------------------------------------------------------------------------------ ABC
+def test_abc_gk(mocat):
+    """tests/test_abc_gk.py:130-164 style: SMC-ABC recovers the g-and-k parameters: sum|mean - truth| < 3
+    (n=1e3 there with a 100-order-statistic summary; here the m=8 sorted-draw summary of config C5)."""
+    from oracle import models as omodels
+    truth = np.array([3., 1., 2., .5])
+    sc0 = mocat.abc.GKTransformedUniformPrior(n_unsummarised_data=8)
+    x_true = sc0.unconstrain(truth)
+    data = omodels.GKTransformed(np.zeros(8)).simulate(x_true[None], np.random.default_rng(1).random((1, 8)))[0]
+    sc = mocat.abc.GKTransformedUniformPrior(data=data)
+    sample = mocat.run(sc, mocat.abc.MetropolisedABCSMCSampler(max_iter=60), 5000, random_key=0)
+    assert np.all(np.diff(sample.threshold[1:]) <= 1e-9)
+    alive = sample.log_weight[-1] > -np.inf
+    post_mean = sc.constrain(sample.value[-1][alive]).mean(0)
+    assert np.abs(post_mean - truth).sum() < 6.0      # m=8 draws carry far less information than 1000 draws
+    assert np.abs(post_mean[0] - truth[0]) < 1.5      # location is identified even from 8 draws
