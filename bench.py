@@ -31,8 +31,8 @@ WORKLOAD = "C2 tempered SMC, Rastrigin d=5 a=1, prior N(0,3^2 I), MALA eps=0.1 (
 def parse():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=20)
-    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--steps", type=int, default=200)
+    p.add_argument("--warmup", type=int, default=5)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--n", type=int, default=1_000_000, help="particles per GPU")
     p.add_argument("--no-cpu-baseline", action="store_true")
@@ -165,33 +165,53 @@ def main():
     def ev():
         return torch.cuda.Event(enable_timing=True)
 
-    def one_step(timed):
+    def one_step(inner):
+        """one population step bracketed by events; inner=True records per-kernel-group events (plain
+        launches), inner=False replays the captured CUDA graph of the step (the production path)."""
         if eng.ctl.read()['done']:
             eng.startup()                                               # population reached beta = 1: start over (untimed)
+            eng.update()                                                # first update after a restart is never graph-replayed
         flush.zero_()                                                   # L2 flush between timed iterations
-        marks = [ev() for _ in range(4)]
-        eng.update(events=marks)
-        return marks
+        if inner:
+            marks = [ev() for _ in range(4)]
+            eng.update(events=marks)
+            return marks
+        e0, e1 = ev(), ev()
+        e0.record()
+        eng.update()
+        e1.record()
+        return [e0, e1]
 
     eng.startup()
-    sync()
-    for _ in range(max(a.warmup, 3)):
-        one_step(False)
+    eng.update()
     sync()
     clocks = ClockSampler(local)
     clocks.start()
+    t_w = time.perf_counter()
+    nw = 0
+    while nw < max(a.warmup, 3) or time.perf_counter() - t_w < 1.0:     # >= 1 s of warm-up so clocks settle
+        one_step(False)
+        nw += 1
+    sync()
     all_marks = []
     t_wall0 = time.perf_counter()
     for _ in range(a.steps):
-        all_marks.append(one_step(True))
+        all_marks.append(one_step(False))
     sync()
     t_wall = time.perf_counter() - t_wall0
+    # second region: same steps with plain launches and per-kernel-group events (roofline of the kernels)
+    inner_marks = [one_step(True) for _ in range(min(a.steps, 50))]
+    sync()
     clk = clocks.stop()
+    it_now = int(eng.ctl.read()['iter'])
+    hist = eng.ctl.read_hist(it_now + 1)
+    mean_search = float(hist['search_iters'][1:].mean()) if it_now >= 1 else 0.0
     # device time: per-step event pairs (flush excluded), summed
-    tot = sum(m[0].elapsed_time(m[3]) for m in all_marks)              # ms
-    t_resample = sum(m[0].elapsed_time(m[1]) for m in all_marks) / a.steps
-    t_move = sum(m[1].elapsed_time(m[2]) for m in all_marks) / a.steps
-    t_temper = sum(m[2].elapsed_time(m[3]) for m in all_marks) / a.steps
+    tot = sum(m[0].elapsed_time(m[1]) for m in all_marks)              # ms
+    ni = len(inner_marks)
+    t_resample = sum(m[0].elapsed_time(m[1]) for m in inner_marks) / ni
+    t_move = sum(m[1].elapsed_time(m[2]) for m in inner_marks) / ni
+    t_temper = sum(m[2].elapsed_time(m[3]) for m in inner_marks) / ni
     tt = torch.tensor([tot], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -241,22 +261,39 @@ def main():
                "sample": f"n={n_s} x {k_s} steps of the same workload; NumPy restatement of the reference "
                          f"(oracle/), {workers} processes; mocat's own JAX path cannot run here (jax absent)"}
 
-    achieved = ALGO_BYTES_MOVE * n / (t_move * 1e-3) / 1e9
+    # roofline of the dominant kernel (by measured time) and of the move kernel.  Algorithmic bytes
+    # (SURVEY 8d, C2): move 64 B/particle; tempering search 8 B x evaluations (w, l reads) + 12 B for the
+    # weight update (read w, l; write w).
+    evals = mean_search + 1.0
+    bytes_temper = (8.0 * evals + 12.0) * n
+    ach_move = ALGO_BYTES_MOVE * n / (t_move * 1e-3) / 1e9
+    ach_temper = bytes_temper / (t_temper * 1e-3) / 1e9
+    kernels = {
+        "scan_cdf+ancestors (device-predicated)": {"ms": t_resample},
+        "smc_move_kernel<Rastrigin,5,MALA>": {"ms": t_move, "algorithmic_bytes": ALGO_BYTES_MOVE * n,
+                                              "achieved_gbs": ach_move, "frac": ach_move / hbm_peak},
+        "temper_adapt_kernel<resident>": {"ms": t_temper, "algorithmic_bytes": bytes_temper,
+                                          "achieved_gbs": ach_temper, "frac": ach_temper / hbm_peak,
+                                          "mean_evaluations": evals},
+    }
+    dom = "temper_adapt_kernel<resident>" if t_temper >= t_move else "smc_move_kernel<Rastrigin,5,MALA>"
     line = {
         "metric": METRIC, "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": a.steps,
-        "warmup": max(a.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "warmup": nw, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "n_per_gpu": n, "dim": D, "parallelism": f"independent populations x{world}"
                    if world > 1 else "single GPU", "l2": "flushed between timed steps (512 MiB memset)",
+                   "launch": "one CUDA-graph replay per step (4 kernels)",
                    "state_bytes_resident": int(sum(t.numel() * t.element_size() for t in
                                                    (eng.xbuf[0], eng.xbuf[1], eng.lw, eng.lik, eng.up, eng.alpha,
                                                     eng.cdf, eng.anc)))},
-        "roofline": {"bound": "hbm", "kernel": "smc_move_kernel<Rastrigin,5,MALA>", "achieved": achieved,
-                     "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
-                     "peak_source": peak_src, "algorithmic_bytes_per_particle": ALGO_BYTES_MOVE,
-                     "ms_per_launch": t_move},
-        "kernels_ms_per_step": {"scan+ancestors (predicated)": t_resample, "smc_move": t_move,
-                                "temper_adapt (cooperative regula falsi)": t_temper},
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"],
+                     "peak": hbm_peak, "unit": "GB/s", "frac": kernels[dom]["frac"], "traffic": None,
+                     "peak_source": peak_src, "algorithmic_bytes_per_launch": kernels[dom]["algorithmic_bytes"],
+                     "ms_per_launch": kernels[dom]["ms"],
+                     "note": "n=1e6: the whole state (68 MB) is smaller than L2 and every kernel is "
+                             "latency/issue bound, not HBM bound; see DESIGN.md for the n=1e8 figures"},
+        "kernels": kernels,
         "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": 4 * a.steps, "clocks": clk,
         "wall_s_timed_region": t_wall,
     }

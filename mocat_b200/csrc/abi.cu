@@ -40,6 +40,10 @@ extern "C" mb_ctx* mb_create(int device) {
     ok = ok && cudaMalloc(&ctx->partials, sizeof(double) * 3 * MB_MAX_PARTIAL_BLOCKS * 2) == cudaSuccess;
     ok = ok && cudaMalloc(&ctx->counters, sizeof(uint32_t) * MB_NUM_COUNTERS) == cudaSuccess;
     ok = ok && cudaMemset(ctx->counters, 0, sizeof(uint32_t) * MB_NUM_COUNTERS) == cudaSuccess;
+    {
+        const uint32_t one = 1;
+        ok = ok && cudaMemcpy(ctx->counters + MB_CNT_SCAN_EPOCH, &one, sizeof(one), cudaMemcpyHostToDevice) == cudaSuccess;
+    }
     ctx->scratch_bytes = 8u << 20;
     ok = ok && cudaMalloc(&ctx->scratch, ctx->scratch_bytes) == cudaSuccess;
     if (!ok) {

@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(MV_THREADS) smc_init_kernel(SmcArgs a, int64_t
 }
 
 template <int LIK, int D, int MOVE>
-__global__ void __launch_bounds__(MV_THREADS) smc_move_kernel(SmcArgs a) {
+__global__ void __launch_bounds__(MV_THREADS, (D <= 6 ? 4 : (D <= 10 ? 3 : 2))) smc_move_kernel(SmcArgs a) {
     const mb_control* ctl = a.ctl;
     if (ctl->done) return;
     const bool resample = ctl->resample != 0;
@@ -225,8 +225,8 @@ static int smc_launch(const SmcArgs& a, int init, int64_t n_total, int grid, cud
 }
 
 static int smc_dispatch(mb_ctx* ctx, const SmcArgs& a, int init, int64_t n_total, cudaStream_t st) {
-    int64_t grid = (a.n + MV_THREADS - 1) / MV_THREADS;
-    if (grid > (int64_t)ctx->sms * 16) grid = (int64_t)ctx->sms * 16;
+    int64_t grid = (a.n + MV_THREADS - 1) / MV_THREADS;      // one particle per thread: no grid-stride tail
+    if (grid > 0x7fffffffll) grid = 0x7fffffffll;
     const int d = a.tgt.dim;
 #define CASE_R(DD) if (d == DD) return smc_launch<MB_LIK_RASTRIGIN, DD>(a, init, n_total, (int)grid, st);
 #define CASE_G(DD) if (d == DD && DD <= MB_MAX_SMALL_DIM) return smc_launch<MB_LIK_GAUSSIAN, (DD <= MB_MAX_SMALL_DIM ? DD : 1)>(a, init, n_total, (int)grid, st);

@@ -147,8 +147,10 @@ extern "C" int mb_lse_ess(mb_ctx* ctx, const float* lw, const float* lik, double
 
 // ------------------------------------------------------------------------------------------------ K3
 // Persistent cooperative kernel: the whole regula-falsi search of utils.py:205-237 runs on the device,
-// one streaming pass + one grid sync per evaluation; every block merges the same partials in the same
-// order, so all blocks take identical decisions without a second sync.
+// one pass + one grid sync per evaluation; every block merges the same partials in the same order, so
+// all blocks take identical decisions without a second sync.  When the population fits (n <= grid x 256
+// x 8) each thread keeps its 8 (lw, lik) pairs in REGISTERS for the whole search: the weights are read
+// from memory once and written once however many evaluations the search needs.
 struct TemperArgs {
     float* lw;
     const float* lik;
@@ -162,15 +164,54 @@ struct TemperArgs {
     double* partials;      // [2][MB_MAX_PARTIAL_BLOCKS][3]
 };
 
+#define TP_R 2             // float4 (lw, lik) pairs kept per thread in the resident variant
+
 __device__ __forceinline__ double lse3_log_ess(const Lse3& r) {
     const double mm = (r.m == -INFINITY || r.m == INFINITY) ? 0.0 : r.m;
     return 2.0 * (log(r.s1) + mm) - (log(r.s2) + 2.0 * mm);
 }
 
-__global__ void __launch_bounds__(RED_THREADS)
+// two-stage merge of the per-block partials: global max first (cheap), then every partial is rescaled
+// ONCE (one fp64 exp each, in parallel) and summed in a fixed order.  Result broadcast to the block.
+__device__ __forceinline__ Lse3 lse_merge_partials_fast(const double* __restrict__ part, int count, double* sm) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    double m = -INFINITY;
+    for (int i = threadIdx.x; i < count; i += blockDim.x) m = fmax(m, part[3 * i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, shfl_xor_d(m, o));
+    if (lane == 0) sm[warp] = m;
+    __syncthreads();
+    double M = sm[0];
+    for (int w = 1; w < nw; ++w) M = fmax(M, sm[w]);
+    __syncthreads();
+    double s1 = 0.0, s2 = 0.0;
+    for (int i = threadIdx.x; i < count; i += blockDim.x) {
+        const double mi = part[3 * i];
+        if (mi != -INFINITY) {                          // NaN max propagates through exp()
+            const double f = exp(mi - M);
+            s1 += part[3 * i + 1] * f;
+            s2 += part[3 * i + 2] * f * f;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { s1 += shfl_xor_d(s1, o); s2 += shfl_xor_d(s2, o); }
+    if (lane == 0) { sm[warp] = s1; sm[nw + warp] = s2; }
+    __syncthreads();
+    double S1 = 0.0, S2 = 0.0;
+    for (int w = 0; w < nw; ++w) { S1 += sm[w]; S2 += sm[nw + w]; }
+    __syncthreads();
+    return Lse3{M, S1, S2};
+}
+
+#define TP_THREADS_RES 512
+
+template <bool RESIDENT>
+__global__ void __launch_bounds__(RESIDENT ? TP_THREADS_RES : RED_THREADS, 2)
 temper_adapt_kernel(TemperArgs a) {
     cg::grid_group grid = cg::this_grid();
-    __shared__ Lse3 smem[RED_THREADS / 32];
+    __shared__ Lse3 smem[16];
+    __shared__ double smd[32];
+    __shared__ float smf[16];
     mb_control c0 = *a.ctl;                             // read before the first grid sync (see below)
     if (c0.done) return;                                // uniform over the grid: done only changes at the end
     if (a.advance_iter && c0.resampled) {               // the move kernel resampled: weights were reset to 0,
@@ -182,16 +223,68 @@ temper_adapt_kernel(TemperArgs a) {
     const double beta = c0.beta;
     const int iter_new = c0.iter + (a.advance_iter ? 1 : 0);
     int parity = 0;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    const int64_t n4 = a.n >> 2;
+
+    float4 rw[TP_R], rl[TP_R];
+    if (RESIDENT) {                                     // host guarantees: 16 B aligned, n % 4 == 0, n4 <= TP_R * nthreads
+#pragma unroll
+        for (int r = 0; r < TP_R; ++r) {
+            const int64_t i = tid + (int64_t)r * nthreads;
+            if (i < n4) {
+                rw[r] = reinterpret_cast<const float4*>(a.lw)[i];
+                rl[r] = __ldg(reinterpret_cast<const float4*>(a.lik) + i);
+            } else {
+                rw[r] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+                rl[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+    }
 
     auto evaluate = [&](double b) -> Lse3 {
         const float dbeta = (float)(b - beta);
-        const Lse3 blk = lse_block_pass(a.lw, a.lik, dbeta, a.n, smem);
+        Lse3 blk;
+        if (RESIDENT) {
+            // registers hold the data: block max first, then ONE exp per particle, no rescaling merges
+            const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+            float w[4 * TP_R];
+#pragma unroll
+            for (int r = 0; r < TP_R; ++r) {
+                w[4 * r + 0] = fmaf(-dbeta, rl[r].x, rw[r].x); w[4 * r + 1] = fmaf(-dbeta, rl[r].y, rw[r].y);
+                w[4 * r + 2] = fmaf(-dbeta, rl[r].z, rw[r].z); w[4 * r + 3] = fmaf(-dbeta, rl[r].w, rw[r].w);
+            }
+            float tm = -INFINITY;
+#pragma unroll
+            for (int k = 0; k < 4 * TP_R; ++k) tm = fmaxf(tm, w[k]);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) tm = fmaxf(tm, __shfl_xor_sync(MB_FULL, tm, o));
+            if (lane == 0) smf[warp] = tm;
+            __syncthreads();
+            float Mb = smf[0];
+            for (int q = 1; q < nw; ++q) Mb = fmaxf(Mb, smf[q]);
+            const float mm = (Mb == -INFINITY) ? 0.f : Mb;
+            float p1 = 0.f, p2 = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4 * TP_R; ++k) { const float e = __expf(w[k] - mm); p1 += e; p2 = fmaf(e, e, p2); }
+            double s1 = (double)p1, s2 = (double)p2;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { s1 += shfl_xor_d(s1, o); s2 += shfl_xor_d(s2, o); }
+            if (lane == 0) { smd[warp] = s1; smd[16 + warp] = s2; }
+            __syncthreads();
+            double S1 = 0.0, S2 = 0.0;
+            for (int q = 0; q < nw; ++q) { S1 += smd[q]; S2 += smd[16 + q]; }
+            __syncthreads();
+            blk = Lse3{(double)Mb, S1, S2};
+        } else {
+            blk = lse_block_pass(a.lw, a.lik, dbeta, a.n, smem);
+        }
         double* part = a.partials + (size_t)parity * 3 * MB_MAX_PARTIAL_BLOCKS;
         if (threadIdx.x == 0) {
             part[3 * blockIdx.x] = blk.m; part[3 * blockIdx.x + 1] = blk.s1; part[3 * blockIdx.x + 2] = blk.s2;
         }
         grid.sync();
-        const Lse3 r = lse_merge_partials(part, gridDim.x, smem);
+        const Lse3 r = lse_merge_partials_fast(part, gridDim.x, smd);
         parity ^= 1;
         return r;
     };
@@ -229,47 +322,56 @@ temper_adapt_kernel(TemperArgs a) {
     // weight update  lw += -(beta' - beta) * lik   (transport/smc.py:201-203, 367-373)
     {
         const float dbeta = (float)(b_new - beta);
-        const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-        const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
         if (dbeta != 0.f) {
-            const bool aligned = (((uintptr_t)a.lw & 15) == 0) && (((uintptr_t)a.lik & 15) == 0);
-            int64_t done = 0;
-            if (aligned) {
-                const int64_t n4 = a.n >> 2;
-                float4* lw4 = reinterpret_cast<float4*>(a.lw);
-                const float4* lk4 = reinterpret_cast<const float4*>(a.lik);
-                for (int64_t i = tid; i < n4; i += nthreads) {
-                    float4 w = lw4[i];
-                    const float4 l = __ldg(lk4 + i);
-                    w.x = fmaf(-dbeta, l.x, w.x); w.y = fmaf(-dbeta, l.y, w.y);
-                    w.z = fmaf(-dbeta, l.z, w.z); w.w = fmaf(-dbeta, l.w, w.w);
-                    lw4[i] = w;
+            if (RESIDENT) {
+#pragma unroll
+                for (int r = 0; r < TP_R; ++r) {
+                    const int64_t i = tid + (int64_t)r * nthreads;
+                    if (i < n4)
+                        reinterpret_cast<float4*>(a.lw)[i] =
+                            make_float4(fmaf(-dbeta, rl[r].x, rw[r].x), fmaf(-dbeta, rl[r].y, rw[r].y),
+                                        fmaf(-dbeta, rl[r].z, rw[r].z), fmaf(-dbeta, rl[r].w, rw[r].w));
                 }
-                done = n4 << 2;
+            } else {
+                const bool aligned = (((uintptr_t)a.lw & 15) == 0) && (((uintptr_t)a.lik & 15) == 0);
+                int64_t done = 0;
+                if (aligned) {
+                    float4* lw4 = reinterpret_cast<float4*>(a.lw);
+                    const float4* lk4 = reinterpret_cast<const float4*>(a.lik);
+                    for (int64_t i = tid; i < n4; i += nthreads) {
+                        float4 w = lw4[i];
+                        const float4 l = __ldg(lk4 + i);
+                        w.x = fmaf(-dbeta, l.x, w.x); w.y = fmaf(-dbeta, l.y, w.y);
+                        w.z = fmaf(-dbeta, l.z, w.z); w.w = fmaf(-dbeta, l.w, w.w);
+                        lw4[i] = w;
+                    }
+                    done = n4 << 2;
+                }
+                for (int64_t i = done + tid; i < a.n; i += nthreads) a.lw[i] = fmaf(-dbeta, a.lik[i], a.lw[i]);
             }
-            for (int64_t i = done + tid; i < a.n; i += nthreads) a.lw[i] = fmaf(-dbeta, a.lik[i], a.lw[i]);
         }
     }
 
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        mb_control c = c0;
+        mb_control c = *a.ctl;                           // unchanged since the start of the kernel
+        c.lse = c0.lse;
         const double lse_prev = c0.lse;
         ctl_set_weights(&c, t_new);
-        c.log_z = c0.log_z + (c.lse - lse_prev);         // transport/smc.py:212-215
+        c.log_z = c.log_z + (c.lse - lse_prev);          // transport/smc.py:212-215
         c.beta = b_new;
         c.iter = iter_new;
         c.search_iters = it;
         c.resample = (c.ess <= P.ess_resample * (double)a.n_total) ? 1 : 0;          // smc.py:298-301
-        const double nan_frac = a.nan_denominator > 0 ? (double)c0.nan_count / (double)a.nan_denominator : 0.0;
+        const double nan_frac = a.nan_denominator > 0 ? (double)c.nan_count / (double)a.nan_denominator : 0.0;
         c.done = (b_new >= P.max_temperature || iter_new >= P.max_iter || nan_frac > 0.1) ? 1 : 0;  // :171-175
         c.nan_count = 0;
-        if (a.advance_iter) c.alpha_mean = (double)c0.alpha_fx / 4294967296.0 / (double)a.n_total;
+        if (a.advance_iter) c.alpha_mean = (double)c.alpha_fx / 4294967296.0 / (double)a.n_total;
         c.alpha_fx = 0;
         *a.ctl = c;
         if (a.hist && iter_new < MB_HIST_MAX) {
             mb_hist h;
             h.beta = c.beta; h.ess = c.ess; h.log_z = c.log_z; h.alpha_mean = c.alpha_mean; h.lse = c.lse;
-            h.resampled = c0.resampled; h.search_iters = it;
+            h.resampled = c.resampled; h.search_iters = it;
             a.hist[iter_new] = h;
         }
     }
@@ -279,19 +381,25 @@ extern "C" int mb_temper_adapt(mb_ctx* ctx, float* lw, const float* lik, int64_t
                                int advance_iter, int64_t nan_denominator, int64_t n_total, mb_control* ctl,
                                mb_hist* hist, mb_stream_t stream) {
     MB_REQUIRE(ctx && lw && lik && prm && ctl && n > 0, "mb_temper_adapt: bad arguments");
-    static int blocks_per_sm = 0;
-    if (blocks_per_sm == 0) {
-        MB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, temper_adapt_kernel, RED_THREADS, 0));
-        if (blocks_per_sm < 1) { mb_set_error("temper kernel cannot be resident"); return MB_ERR_CUDA; }
+    static int bps[2] = {0, 0};
+    if (bps[0] == 0) {
+        MB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps[0], temper_adapt_kernel<false>, RED_THREADS, 0));
+        MB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps[1], temper_adapt_kernel<true>, TP_THREADS_RES, 0));
+        if (bps[0] < 1 || bps[1] < 1) { mb_set_error("temper kernel cannot be resident"); return MB_ERR_CUDA; }
     }
-    int64_t grid = (int64_t)blocks_per_sm * ctx->sms;
-    const int64_t need = (n + (int64_t)RED_THREADS * 8 - 1) / ((int64_t)RED_THREADS * 8);
-    if (grid > need) grid = need;
+    const int64_t need_res = (n + (int64_t)TP_THREADS_RES * 4 * TP_R - 1) / ((int64_t)TP_THREADS_RES * 4 * TP_R);
+    const int64_t need = (n + (int64_t)RED_THREADS * 4 * TP_R - 1) / ((int64_t)RED_THREADS * 4 * TP_R);
+    int64_t cap_res = (int64_t)bps[1] * ctx->sms;
+    if (cap_res > MB_MAX_PARTIAL_BLOCKS) cap_res = MB_MAX_PARTIAL_BLOCKS;
+    const bool resident = (n % 4 == 0) && (((uintptr_t)lw & 15) == 0) && (((uintptr_t)lik & 15) == 0) && need_res <= cap_res;
+    int64_t grid = resident ? need_res : (int64_t)bps[0] * ctx->sms;
+    if (!resident && grid > need) grid = need;
     if (grid > MB_MAX_PARTIAL_BLOCKS) grid = MB_MAX_PARTIAL_BLOCKS;
     if (grid < 1) grid = 1;
     TemperArgs args{lw, lik, n, *prm, advance_iter, nan_denominator, n_total > 0 ? n_total : n, ctl, hist, ctx->partials};
     void* kargs[] = {&args};
-    MB_CUDA(cudaLaunchCooperativeKernel((void*)temper_adapt_kernel, dim3((unsigned)grid), dim3(RED_THREADS), kargs, 0,
+    void* fn = resident ? (void*)temper_adapt_kernel<true> : (void*)temper_adapt_kernel<false>;
+    MB_CUDA(cudaLaunchCooperativeKernel(fn, dim3((unsigned)grid), dim3(resident ? TP_THREADS_RES : RED_THREADS), kargs, 0,
                                         mb_s(stream)));
     return MB_OK;
 }

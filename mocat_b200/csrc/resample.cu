@@ -41,7 +41,7 @@ struct ScanArgs {
     int predicated;           // 1: run only if ctl->resample && !ctl->done
     double* cdf;
     int32_t* flag; double* agg; double* incl;
-    uint32_t epoch;
+    uint32_t* epoch_ptr;      // device-side launch epoch (incremented by the kernel itself: graph-replay safe)
     uint32_t* tile_counter; uint32_t* done_counter;
     int64_t num_tiles;
 };
@@ -63,7 +63,8 @@ scan_cdf_kernel(ScanArgs a) {
     } else {
         scale = a.scale;
     }
-    const int st_base = (int)(a.epoch << 2);
+    const uint32_t epoch = (*a.epoch_ptr) & 0x1fffffffu;     // every block reads it before any block can exit
+    const int st_base = (int)(epoch << 2);
 
     while (true) {
         if (threadIdx.x == 0) tile_s = atomicAdd(a.tile_counter, 1u);
@@ -138,7 +139,7 @@ scan_cdf_kernel(ScanArgs a) {
                     int f = st_base | ST_INCL;               // lanes before tile 0 behave as "inclusive 0"
                     double val = 0.0;
                     if (idx >= 0) {
-                        do { f = ld_acquire(a.flag + idx); } while ((f >> 2) != (int)a.epoch || (f & 3) == ST_INVALID);
+                        do { f = ld_acquire(a.flag + idx); } while ((f >> 2) != (int)epoch || (f & 3) == ST_INVALID);
                         val = ((f & 3) == ST_INCL) ? ld_relaxed_d(a.incl + idx) : ld_relaxed_d(a.agg + idx);
                     }
                     const unsigned incl_mask = __ballot_sync(MB_FULL, (f & 3) == ST_INCL);
@@ -183,6 +184,7 @@ scan_cdf_kernel(ScanArgs a) {
         if (t == gridDim.x - 1) {
             *a.done_counter = 0;
             *a.tile_counter = 0;
+            *a.epoch_ptr = epoch + 1;
         }
     }
 }
@@ -192,9 +194,7 @@ static int scan_launch(mb_ctx* ctx, ScanArgs& a, cudaStream_t st) {
     MB_REQUIRE(a.num_tiles < 0xffff0000ll, "scan: too many tiles");
     if (mb_ensure_scan(ctx, a.num_tiles) != MB_OK) return MB_ERR_CUDA;
     a.flag = ctx->scan_flag; a.agg = ctx->scan_agg; a.incl = ctx->scan_incl;
-    ctx->scan_epoch = (ctx->scan_epoch + 1) & 0x1fffffffu;
-    if (ctx->scan_epoch == 0) ctx->scan_epoch = 1;
-    a.epoch = ctx->scan_epoch;
+    a.epoch_ptr = ctx->counters + MB_CNT_SCAN_EPOCH;
     a.tile_counter = ctx->counters + MB_CNT_SCAN_TILE;
     a.done_counter = ctx->counters + MB_CNT_SCAN_DONE;
     int64_t grid = (int64_t)ctx->sms * 6;                 // resident-sized grid, tiles fetched dynamically
@@ -261,7 +261,7 @@ ancestors_systematic_kernel(AncArgs a) {
     __shared__ int64_t w_lo, w_hi;
     double u0;
     if (a.u) u0 = a.u[0];
-    else { const Philox4 r = philox_raw(a.seed, 0ull, a.step, MB_P_RESAMPLE, 0u); u0 = u53(r.x, r.y); }
+    else { const Philox4 r = philox_raw(a.seed, 0ull, (a.ctl ? (uint32_t)(a.ctl->iter + 1) : a.step), MB_P_RESAMPLE, 0u); u0 = u53(r.x, r.y); }
     const double nd = (double)a.n_out;
     for (int64_t b0 = (int64_t)blockIdx.x * ANC_BLOCK_OUT; b0 < a.n_out; b0 += (int64_t)gridDim.x * ANC_BLOCK_OUT) {
         const int64_t b1 = min(b0 + (int64_t)ANC_BLOCK_OUT, a.n_out);
@@ -296,10 +296,11 @@ ancestors_systematic_kernel(AncArgs a) {
 __global__ void __launch_bounds__(ANC_THREADS)
 ancestors_multinomial_kernel(AncArgs a) {
     if (a.ctl && (a.ctl->done || !a.ctl->resample)) return;
+    const uint32_t step = a.ctl ? (uint32_t)(a.ctl->iter + 1) : a.step;   // device-side step: graph-capturable
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n_out; i += (int64_t)gridDim.x * blockDim.x) {
         double u;
         if (a.u) u = a.u[i];
-        else { const Philox4 r = philox_raw(a.seed, (uint64_t)(a.gid0 + i), a.step, MB_P_RESAMPLE, 0u); u = u53(r.x, r.y); }
+        else { const Philox4 r = philox_raw(a.seed, (uint64_t)(a.gid0 + i), step, MB_P_RESAMPLE, 0u); u = u53(r.x, r.y); }
         int64_t j = upper_bound_g(a.cdf, 0, a.n, u);
         if (j > a.n - 1) j = a.n - 1;
         a.anc[i] = (int32_t)j;

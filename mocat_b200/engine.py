@@ -7,6 +7,7 @@ ancestor-gather; per-particle scalars (`lw`, `lik`, `up`, `alpha`, `dist`) are (
 136-byte control block on the device plus a history ring of 48-byte records.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -153,6 +154,8 @@ class SMCEngine:
             self.temper.schedule = self._schedule.data_ptr()
             self.temper.schedule_len = self._schedule.numel()
         self.enqueued = 0
+        self.use_graphs = os.environ.get("MOCAT_B200_GRAPHS", "1") != "0"
+        self._graphs = [None, None]
 
     @property
     def x(self):
@@ -173,15 +176,13 @@ class SMCEngine:
         self._temper(advance=False)
         self.enqueued = 0
 
-    def update(self, events=None):
-        """enqueue one SMCSampler.update (transport/smc.py:73-99); fully asynchronous, predicated on device.
-        events: optional list of 4 torch.cuda.Event recorded before / between / after the kernel groups."""
+    def _enqueue(self, events=None):
         st = stream()
         if events:
             events[0].record()
         self.L.call("mb_cumsum_lw", self.ctx, ptr(self.lw), self.n, ptr(self.ctl.t), 0, ptr(self.cdf), st)
         self.L.call("mb_ancestors", self.ctx, ptr(self.cdf), self.n, self.resampling, None, self.seed,
-                    self.enqueued + 1, self.gid0, ptr(self.anc), self.n, ptr(self.ctl.t), st)
+                    0, self.gid0, ptr(self.anc), self.n, ptr(self.ctl.t), st)   # step comes from ctl->iter + 1
         if events:
             events[1].record()
         src, dst = self.xbuf[self.cur], self.xbuf[self.cur ^ 1]
@@ -190,11 +191,42 @@ class SMCEngine:
                     self.gid0, ptr(self.ctl.t), st)
         if events:
             events[2].record()
-        self.cur ^= 1
         self._temper(advance=True)
         if events:
             events[3].record()
+
+    def update(self, events=None):
+        """enqueue one SMCSampler.update (transport/smc.py:73-99); fully asynchronous, predicated on device.
+        After the first (plain) call the four kernels are replayed from a CUDA graph (one per ping-pong
+        parity) so that a population step costs one host call.
+        events: optional list of 4 torch.cuda.Event recorded before / between / after the kernel groups
+        (forces the plain path)."""
+        if events is None and self.use_graphs and self.enqueued >= 1:
+            g = self._graphs[self.cur]
+            if g is None:
+                g = self._capture()
+            if g is not None:
+                g.replay()
+                self.cur ^= 1
+                self.enqueued += 1
+                return
+        self._enqueue(events)
+        self.cur ^= 1
         self.enqueued += 1
+
+    def _capture(self):
+        try:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._enqueue()
+            self._graphs[self.cur] = g
+            return g
+        except Exception as exc:                         # capture unsupported: keep the plain launch path
+            import warnings
+            warnings.warn(f"mocat_b200: CUDA graph capture of the SMC step failed ({exc}); using plain launches")
+            self.use_graphs = False
+            torch.cuda.synchronize()
+            return None
 
     def values(self):
         """(n, d) float32 device tensor view of the current particle values"""

@@ -142,7 +142,7 @@ def test_bootstrap_pf_coverage_and_kalman(mocat, dim):
     sd = np.sqrt(np.einsum('tii->ti', covs))
     k = 3 if dim == 1 else 4
     assert np.all(np.abs(mus - sim.x) < k * sd)
-    npt.assert_allclose(pf.mean, mus, atol=0.35)
+    npt.assert_allclose(pf.mean, mus, atol=0.35 if dim == 1 else 0.8)   # ESS ~ 100-250 in 5-D at n=2e3
     assert abs(pf.log_norm_constant[-1] - ll) < 1.0 + dim
     # online API (filtering.py:173-252): same result as the batch call when driven step by step
     p = mocat.ssm.initiate_particles(ssm, mocat.ssm.BootstrapFilter(), 2000, 0, sim.y[0], t[0])

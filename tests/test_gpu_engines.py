@@ -154,14 +154,15 @@ def test_pf_c1_vs_kalman_and_oracle(E):
     out = opf.BootstrapPF(lg, n, seed, ess_threshold=0.5).run(y)
     oess = np.array([o['ess'] for o in out])
     ores = np.array([o['resampled'] for o in out], dtype=np.int32)
-    # the two runs share every random number; they stay together until a resample decision is taken
-    # within 0.2% of the threshold (where the fp32-vs-fp64 difference in ESS may flip it)
-    amb = np.where(np.abs(oess - 0.5 * n) < 0.002 * n)[0]
-    k = int(amb[0]) if len(amb) else len(oess)
-    assert k >= 5
-    npt.assert_allclose(hist['ess'][:k], oess[:k], rtol=5e-3)
-    npt.assert_array_equal(hist['resampled'][1:k], ores[1:k])
-    npt.assert_allclose(hist['log_z'][k - 1], out[k - 1]['log_z'], atol=0.01)
+    # the two runs share every random number: identical up to the first resampling, within a few flipped
+    # ancestors (fp32 exp on the device) right after it; later they decorrelate like any two particle systems
+    first = int(np.argmax(ores[1:] == 1)) + 1
+    assert first >= 2
+    npt.assert_allclose(hist['ess'][:first], oess[:first], rtol=1e-5)
+    npt.assert_array_equal(hist['resampled'][1:first + 1], ores[1:first + 1])
+    npt.assert_allclose(hist['ess'][first], oess[first], rtol=2e-3)
+    npt.assert_allclose(hist['log_z'][first], out[first]['log_z'], atol=2e-3)
+    assert abs(out[-1]['log_z'] - ll) < 0.5
 
 
 def test_pf_lg5_coverage(E):
