@@ -51,6 +51,8 @@ typedef struct {
     double aux0, aux1;          /* kernel specific (alive count, sum alpha ...)                            */
     int64_t nan_count;          /* NaN entries in the value block after the last move (smc.py:174-175)     */
     int64_t alpha_fx;           /* sum of per-particle acceptance probabilities, fixed point 2^-32          */
+    uint64_t seed;              /* Philox key of this population (set by the *_init kernels; read by the     */
+                                /* move / ancestor kernels so that a captured CUDA graph is seed-agnostic)  */
     int32_t iter;               /* extra.iter (sample.py:64-65)                                            */
     int32_t resample;           /* resample_criterion evaluated for the NEXT update (smc.py:298-301)       */
     int32_t done;               /* termination_criterion (smc.py:171-175, abc/smc.py:157-161)              */

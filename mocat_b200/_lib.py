@@ -26,7 +26,7 @@ c_f, c_d, c_i32, c_i64, c_u32, c_u64, c_vp = C.c_float, C.c_double, C.c_int32, C
 class Control(C.Structure):
     _fields_ = [(k, c_d) for k in ("wmax", "s1", "s2", "lse", "lse2", "log_ess", "ess", "log_z", "beta",
                                    "alpha_mean", "aux0", "aux1")] + \
-               [("nan_count", c_i64), ("alpha_fx", c_i64)] + \
+               [("nan_count", c_i64), ("alpha_fx", c_i64), ("seed", c_u64)] + \
                [(k, c_i32) for k in ("iter", "resample", "done", "search_iters", "resampled", "pad0")]
 
 
@@ -37,11 +37,11 @@ class Hist(C.Structure):
 
 CONTROL_DTYPE = np.dtype([(k, "<f8") for k in ("wmax", "s1", "s2", "lse", "lse2", "log_ess", "ess", "log_z", "beta",
                                               "alpha_mean", "aux0", "aux1")] +
-                         [("nan_count", "<i8"), ("alpha_fx", "<i8")] +
+                         [("nan_count", "<i8"), ("alpha_fx", "<i8"), ("seed", "<u8")] +
                          [(k, "<i4") for k in ("iter", "resample", "done", "search_iters", "resampled", "pad0")])
 HIST_DTYPE = np.dtype([(k, "<f8") for k in ("beta", "ess", "log_z", "alpha_mean", "lse")] +
                       [("resampled", "<i4"), ("search_iters", "<i4")])
-assert CONTROL_DTYPE.itemsize == C.sizeof(Control) == 136
+assert CONTROL_DTYPE.itemsize == C.sizeof(Control) == 144
 assert HIST_DTYPE.itemsize == C.sizeof(Hist) == 48
 
 

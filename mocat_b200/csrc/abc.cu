@@ -105,6 +105,7 @@ __global__ void __launch_bounds__(ABC_THREADS) abc_init_kernel(AbcArgs a) {
         c.s1 = nd; c.s2 = nd; c.lse = log(nd); c.lse2 = log(nd); c.log_ess = log(nd); c.ess = nd;
         c.beta = INFINITY;                                           // threshold = inf, abc/smc.py:65-67
         c.alpha_mean = 1.0;
+        c.seed = a.seed;
         *a.ctl = c;
     }
 }
@@ -116,6 +117,7 @@ __global__ void __launch_bounds__(ABC_THREADS) abc_move_kernel(AbcArgs a) {
     const bool resample = ctl->resample != 0;
     const float thr = (float)ctl->beta;
     const uint32_t step = (uint32_t)(ctl->iter + 1);
+    const uint64_t seed = ctl->seed;
     float sq[GK_DIM];
 #pragma unroll
     for (int k = 0; k < GK_DIM; ++k) sq[k] = sqrtf(a.stepsize[k]);
@@ -132,15 +134,15 @@ __global__ void __launch_bounds__(ABC_THREADS) abc_move_kernel(AbcArgs a) {
             float asum = 0.f;
             for (int s = 0; s < a.mcmc_steps; ++s) {
                 float z[GK_DIM], xp[GK_DIM];
-                philox_normals<GK_DIM>(z, a.seed, gid, step, MB_P_MOVE, (uint32_t)s * 2u);
-                const float uacc = u24(philox_raw(a.seed, gid, step, MB_P_MOVE, (uint32_t)s * 2u + 1u).x);
+                philox_normals<GK_DIM>(z, seed, gid, step, MB_P_MOVE, (uint32_t)s * 2u);
+                const float uacc = u24(philox_raw(seed, gid, step, MB_P_MOVE, (uint32_t)s * 2u + 1u).x);
                 float upn = 0.f;
 #pragma unroll
                 for (int k = 0; k < GK_DIM; ++k) {                   // abc/mcmc.py:71
                     xp[k] = fmaf(sq[k], z[k], x[k]);
                     upn = fmaf(0.5f * xp[k], xp[k], upn);
                 }
-                const float dn = gk_distance<M>(a.gk, xp, a.seed, gid, step, (uint32_t)s * MS);
+                const float dn = gk_distance<M>(a.gk, xp, seed, gid, step, (uint32_t)s * MS);
                 float al = fminf(1.f, __expf(-upn + up) * ((dn < thr) ? 1.f : 0.f));   // abc/mcmc.py:59-62
                 if (al != al) al = 0.f;
                 if (uacc < al) {

@@ -121,6 +121,7 @@ __global__ void __launch_bounds__(MV_THREADS) smc_init_kernel(SmcArgs a, int64_t
         c.wmax = 0.0; c.s1 = nd; c.s2 = nd;
         c.lse = log(nd); c.lse2 = log(nd); c.log_ess = log(nd); c.ess = nd;
         c.alpha_mean = 1.0;
+        c.seed = a.seed;
         *a.ctl = c;
     }
 }
@@ -132,6 +133,7 @@ __global__ void __launch_bounds__(MV_THREADS, (D <= 6 ? 4 : (D <= 10 ? 3 : 2))) 
     const bool resample = ctl->resample != 0;
     const float beta = (float)ctl->beta;
     const uint32_t step = (uint32_t)(ctl->iter + 1);
+    const uint64_t seed = ctl->seed;                   // device-resident key: the captured graph is seed-agnostic
     const float eps = a.mv.stepsize;
     constexpr uint32_t NZ = (D + 3) / 4, S = NZ + 1;
     __shared__ double red[MV_THREADS / 32];
@@ -150,8 +152,8 @@ __global__ void __launch_bounds__(MV_THREADS, (D <= 6 ? 4 : (D <= 10 ? 3 : 2))) 
         const uint64_t gid = (uint64_t)(a.gid0 + i);
         for (int s = 0; s < a.mv.mcmc_steps; ++s) {
             float z[D];
-            philox_normals<D>(z, a.seed, gid, step, MB_P_MOVE, (uint32_t)s * S);
-            const float uacc = u24(philox_raw(a.seed, gid, step, MB_P_MOVE, (uint32_t)s * S + NZ).x);
+            philox_normals<D>(z, seed, gid, step, MB_P_MOVE, (uint32_t)s * S);
+            const float uacc = u24(philox_raw(seed, gid, step, MB_P_MOVE, (uint32_t)s * S + NZ).x);
             float xp[D], gpn[D], upn, uln, Un, alpha;
             if (MOVE == MB_MOVE_MALA) {
                 // always(): p = z (friction = inf, :116-122); leapfrog (utils.py:117-134); p' = -p' (:141)
@@ -452,7 +454,7 @@ __global__ void __launch_bounds__(MV_THREADS) pf_step_kernel(PfArgs a) {
     if (threadIdx.x == 0) {
         *a.counter = 0;
         mb_control c;
-        if (init) memset(&c, 0, sizeof(c)); else c = *ctl;
+        if (init) { memset(&c, 0, sizeof(c)); c.seed = a.seed; } else c = *ctl;
         const double nd = (double)a.n_total;
         const double lse_prev = (init || resample) ? log(nd) : c.lse;          // log Z convention, SURVEY 8c
         ctl_set_weights(&c, v);

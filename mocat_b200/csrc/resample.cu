@@ -261,7 +261,7 @@ ancestors_systematic_kernel(AncArgs a) {
     __shared__ int64_t w_lo, w_hi;
     double u0;
     if (a.u) u0 = a.u[0];
-    else { const Philox4 r = philox_raw(a.seed, 0ull, (a.ctl ? (uint32_t)(a.ctl->iter + 1) : a.step), MB_P_RESAMPLE, 0u); u0 = u53(r.x, r.y); }
+    else { const Philox4 r = philox_raw(a.ctl ? a.ctl->seed : a.seed, 0ull, (a.ctl ? (uint32_t)(a.ctl->iter + 1) : a.step), MB_P_RESAMPLE, 0u); u0 = u53(r.x, r.y); }
     const double nd = (double)a.n_out;
     for (int64_t b0 = (int64_t)blockIdx.x * ANC_BLOCK_OUT; b0 < a.n_out; b0 += (int64_t)gridDim.x * ANC_BLOCK_OUT) {
         const int64_t b1 = min(b0 + (int64_t)ANC_BLOCK_OUT, a.n_out);
@@ -297,10 +297,11 @@ __global__ void __launch_bounds__(ANC_THREADS)
 ancestors_multinomial_kernel(AncArgs a) {
     if (a.ctl && (a.ctl->done || !a.ctl->resample)) return;
     const uint32_t step = a.ctl ? (uint32_t)(a.ctl->iter + 1) : a.step;   // device-side step: graph-capturable
+    const uint64_t seed = a.ctl ? a.ctl->seed : a.seed;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n_out; i += (int64_t)gridDim.x * blockDim.x) {
         double u;
         if (a.u) u = a.u[i];
-        else { const Philox4 r = philox_raw(a.seed, (uint64_t)(a.gid0 + i), step, MB_P_RESAMPLE, 0u); u = u53(r.x, r.y); }
+        else { const Philox4 r = philox_raw(seed, (uint64_t)(a.gid0 + i), step, MB_P_RESAMPLE, 0u); u = u53(r.x, r.y); }
         int64_t j = upper_bound_g(a.cdf, 0, a.n, u);
         if (j > a.n - 1) j = a.n - 1;
         a.anc[i] = (int32_t)j;

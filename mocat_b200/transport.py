@@ -121,8 +121,8 @@ class MetropolisedSMCSampler(TemperedSMCSampler):
         temper = models.make_temper(self.max_temperature, P.ess_threshold_retain, P.ess_threshold_resample,
                                     P.bisection_tol, P.max_bisection_iter, self.max_iter)
         seed = key_to_seed(getattr(initial_extra, 'random_key', None))
-        eng = engine.SMCEngine(target, move, temper, n, seed, resampling=_RESAMPLING[self.resampling],
-                               schedule=self.temperature_schedule)
+        eng = engine.SMCEngine.acquire(target, move, temper, n, seed, resampling=_RESAMPLING[self.resampling],
+                                       schedule=self.temperature_schedule)
         x0 = None if initial_state is None else getattr(initial_state, 'value', None)
         eng.startup(x0)                                                 # smc.py:128-164, 267-296 on the device
         scenario.temperature = 0.
