@@ -33,8 +33,10 @@ extern "C" {
 
 #define MB_MAX_SMALL_DIM   8    /* dense d x d models (Gaussian target, linear-Gaussian SSM) */
 #define MB_HIST_MAX        16384
+#define MB_MAX_WORLD       8    /* GPUs of one NVSwitch domain sharing a population */
 
 typedef struct mb_ctx mb_ctx;
+typedef struct mb_comm mb_comm;
 typedef void* mb_stream_t;
 
 /* ---- device-resident control block: every per-iteration scalar the reference keeps replicated per
@@ -120,6 +122,18 @@ typedef struct {              /* g-and-k, abc/scenarios/gk.py:68-96 */
     float data[16];
 } mb_gk;
 
+/* ---- sharded population: rank r owns the contiguous global index range [r*n_local, (r+1)*n_local).  The
+ *      peer tables hold CUDA-IPC mapped pointers into every rank's HBM so that a kernel can read an
+ *      ancestor's state (or CDF) directly over NVLink: the redistribution after resampling is fused into
+ *      the move kernel's gather instead of being a separate all-to-all. */
+typedef struct {
+    int32_t rank, world;
+    int64_t n_local, n_total;
+    const float*  x_peers[MB_MAX_WORLD];     /* input value block (d x ld) of every rank for this step   */
+    const double* cdf_peers[MB_MAX_WORLD];   /* rank-relative exact fp64 CDF of every rank               */
+    const double* totals;                    /* device [world]: quantised weight total of every rank     */
+} mb_shard;
+
 /* ---- context ---------------------------------------------------------------------------------- */
 const char* mb_last_error(void);
 int         mb_abi_version(void);
@@ -139,13 +153,13 @@ int mb_lse_ess(mb_ctx* ctx, const float* lw, const float* lik, double dbeta, int
  *      in place: lw += -(beta' - beta) * lik.  Appends one mb_hist record at hist[ctl->iter] if hist. */
 int mb_temper_adapt(mb_ctx* ctx, float* lw, const float* lik, int64_t n, const mb_temper* prm,
                     int advance_iter, int64_t nan_denominator, int64_t n_total, mb_control* ctl,
-                    mb_hist* hist, mb_stream_t stream);
+                    mb_hist* hist, mb_comm* comm /*NULL: single GPU*/, mb_stream_t stream);
 
 /* ---- K4: inclusive fp64 CDF of the normalised weights (implicit in random.categorical at
  *      transport/smc.py:65, ssm/filtering.py:199).  Exact-fp64 convention: q_i = rint(w_i*scale)*2^-52,
  *      cdf = min(cumsum(q), 1), cdf[n-1] = 1.   _lw: w_i = exp(lw_i - ctl->wmax), scale from ctl->s1
  *      (predicated on ctl->resample unless force).   _f32: caller supplies linear weights and scale. */
-int mb_cumsum_lw(mb_ctx* ctx, const float* lw, int64_t n, const mb_control* ctl, int force,
+int mb_cumsum_lw(mb_ctx* ctx, const float* lw, int64_t n, const mb_control* ctl, int flags /*1 force, 2 raw*/,
                  double* cdf, mb_stream_t stream);
 int mb_cumsum_f32(mb_ctx* ctx, const float* w, int64_t n, double scale, double* cdf, mb_stream_t stream);
 
@@ -155,6 +169,29 @@ int mb_cumsum_f32(mb_ctx* ctx, const float* w, int64_t n, double scale, double* 
 int mb_ancestors(mb_ctx* ctx, const double* cdf, int64_t n, int mode, const double* u,
                  uint64_t seed, uint32_t step, int64_t gid0, int32_t* anc, int64_t n_out,
                  const mb_control* ctl, mb_stream_t stream);
+
+/* sharded variant: this rank's n_out output slots are the global slots sh->rank*n_local + [0, n_out); the
+ * ancestors are GLOBAL particle indices found in the concatenation of the ranks' relative CDFs
+ * (offset_r + cdf_r[j], exact in fp64), i.e. bit-identical to the single-GPU result. */
+int mb_ancestors_sharded(mb_ctx* ctx, const mb_shard* sh, int mode, uint64_t seed, uint32_t step, int32_t* anc,
+                         int64_t n_out, const mb_control* ctl, mb_stream_t stream);
+
+/* ---- sorted-uniform resampling (production path of the engines).  Systematic, or STRATIFIED-EXACT multinomial:
+ *      the n iid uniforms of multinomial resampling are generated as (counts of first-stage uniforms in B equal
+ *      strata) + (fresh second-stage uniforms inside each stratum) -- identical in law to Cat(softmax(w))^n
+ *      (transport/smc.py:65-67) but sorted by stratum, so ancestors are nearly sorted, the CDF window of a block
+ *      of outputs is staged in shared memory and the fused gather stays coalesced.  B = mb_strata_count(n).
+ *      mb_strata_hist: first stage (integer histogram, deterministic); mb_strata_reduce: sum over the ranks of
+ *      a sharded population (peer reads after a mailbox barrier); mb_ancestors_sorted: scan of the counts +
+ *      ancestor search (sh == NULL: cdf is the materialised CDF of n particles; else the sharded global CDF). */
+int mb_strata_count(int64_t n_total_out);
+int mb_strata_hist(mb_ctx* ctx, int64_t n_out, int64_t gid0, int B, uint64_t seed, uint32_t step,
+                   const mb_control* ctl, uint32_t* hist, mb_stream_t stream);
+int mb_strata_reduce(mb_ctx* ctx, mb_comm* comm, const void* const* hist_peers, int world, int B,
+                     uint32_t* hist_out, const mb_control* ctl, mb_stream_t stream);
+int mb_ancestors_sorted(mb_ctx* ctx, const double* cdf, int64_t n, const mb_shard* sh, int mode,
+                        const uint32_t* hist, uint32_t* offsets, int B, uint64_t seed, uint32_t step, int64_t gid0,
+                        int64_t n_total_out, int32_t* anc, int64_t n_out, const mb_control* ctl, mb_stream_t stream);
 
 /* ---- K6: gather of SoA state columns by ancestor.  Replaces cdict.__getitem__ (core.py:46-56) as
  *      used at transport/smc.py:68 and ssm/filtering.py:199. */
@@ -171,7 +208,8 @@ int mb_smc_init(mb_ctx* ctx, const mb_target* tgt, float* x, int64_t ld, int64_t
                 mb_control* ctl, mb_stream_t stream);
 int mb_smc_move(mb_ctx* ctx, const mb_target* tgt, const mb_move* mv, const float* x_in, float* x_out,
                 int64_t ld, int64_t n, const int32_t* anc, float* lw, float* up_out, float* lik_out,
-                float* alpha_out, uint64_t seed, int64_t gid0, mb_control* ctl, mb_stream_t stream);
+                float* alpha_out, uint64_t seed, int64_t gid0, mb_control* ctl, const mb_shard* sh /*or NULL*/,
+                mb_stream_t stream);
 
 /* ---- K1b: bootstrap particle filter.  Replaces initiate_particles (ssm/filtering.py:173-193) and one
  *      body of the scan in run_particle_filter_for_marginals (:280-311): optional ancestor gather,
@@ -179,10 +217,11 @@ int mb_smc_move(mb_ctx* ctx, const mb_target* tgt, const mb_move* mv, const floa
  *      resample decision for the next step (ess < ess_threshold*n, strict).  t is the time index. */
 int mb_pf_init(mb_ctx* ctx, const mb_ssm* ssm, float* x, int64_t ld, int64_t n, int64_t n_total,
                const float* y0, float* lw, uint64_t seed, int64_t gid0, double ess_threshold,
-               mb_control* ctl, mb_hist* hist, mb_stream_t stream);
+               mb_control* ctl, mb_hist* hist, mb_comm* comm /*or NULL*/, mb_stream_t stream);
 int mb_pf_step(mb_ctx* ctx, const mb_ssm* ssm, const float* x_in, float* x_out, int64_t ld, int64_t n,
                int64_t n_total, const int32_t* anc, const float* y, float* lw, uint64_t seed, uint32_t t,
-               int64_t gid0, double ess_threshold, mb_control* ctl, mb_hist* hist, mb_stream_t stream);
+               int64_t gid0, double ess_threshold, mb_control* ctl, mb_hist* hist, const mb_shard* sh /*or NULL*/,
+               mb_comm* comm /*or NULL*/, mb_stream_t stream);
 
 /* weighted mean / variance of every column under weights exp(lw - ctl->wmax)/s1  (diagnostics) */
 int mb_weighted_moments(mb_ctx* ctx, const float* x, int64_t ld, int64_t n, int d, const float* lw,
@@ -221,6 +260,20 @@ int mb_adagrad(mb_ctx* ctx, float* X, float* gsq, float* mom, const float* phi, 
                float momentum, mb_stream_t stream);
 int mb_target_potential_grad(mb_ctx* ctx, const mb_target* tgt, double beta, const float* X /*n x d row-major*/,
                              int n, float* U, float* G, mb_stream_t stream);
+
+/* ---- multi-GPU plumbing (one process per GPU; handles are exchanged by the host) ------------------------
+ *      mb_alloc/mb_free: cudaMalloc'd (IPC-shareable) buffers; mb_ipc_*: 64-byte CUDA IPC handles;
+ *      mb_comm_*: peer-mapped mailbox communicator used INSIDE kernels for the LSE/ESS allreduce and the
+ *      allgather of the ranks' weight totals (the only collectives the path needs). */
+int  mb_alloc(mb_ctx* ctx, size_t bytes, void** out);
+int  mb_free(mb_ctx* ctx, void* p);
+int  mb_ipc_get_handle(mb_ctx* ctx, void* dev_ptr, void* handle64_host);
+int  mb_ipc_open(mb_ctx* ctx, const void* handle64_host, void** out);
+int  mb_ipc_close(mb_ctx* ctx, void* p);
+int  mb_comm_create(mb_ctx* ctx, int rank, int world, mb_comm** out, void* handle64_host);
+int  mb_comm_connect(mb_comm* comm, const void* handles_host /*world x 64 bytes*/);
+void mb_comm_destroy(mb_comm* comm);
+int  mb_comm_allgather(mb_comm* comm, const double* in, int nd, double* out, mb_stream_t stream);
 
 #ifdef __cplusplus
 }

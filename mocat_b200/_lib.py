@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libmocat_b200.so")
 
 MB_MAX_SMALL_DIM = 8
 MB_HIST_MAX = 16384
+MB_MAX_WORLD = 8
 
 LIK_RASTRIGIN, LIK_GAUSSIAN, LIK_NONE = 0, 1, 2
 MOVE_MALA, MOVE_RW = 0, 1
@@ -70,6 +71,11 @@ class SSM(C.Structure):
                 ("init_mean", c_f), ("init_std", c_f)]
 
 
+class Shard(C.Structure):
+    _fields_ = [("rank", c_i32), ("world", c_i32), ("n_local", c_i64), ("n_total", c_i64),
+                ("x_peers", c_vp * MB_MAX_WORLD), ("cdf_peers", c_vp * MB_MAX_WORLD), ("totals", c_vp)]
+
+
 class GK(C.Structure):
     _fields_ = [("m", c_i32), ("c", c_f), ("prior_min", c_f), ("prior_max", c_f), ("buffer", c_f), ("data", c_f * 16)]
 
@@ -91,7 +97,7 @@ SIGNATURES = {
     "mb_destroy": (None, [c_vp]),
     "mb_sm_count": (C.c_int, [c_vp]),
     "mb_lse_ess": (C.c_int, [c_vp, c_vp, c_vp, c_d, c_i64, c_vp, c_vp]),
-    "mb_temper_adapt": (C.c_int, [c_vp, c_vp, c_vp, c_i64, C.POINTER(Temper), C.c_int, c_i64, c_i64, c_vp, c_vp, c_vp]),
+    "mb_temper_adapt": (C.c_int, [c_vp, c_vp, c_vp, c_i64, C.POINTER(Temper), C.c_int, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "mb_cumsum_lw": (C.c_int, [c_vp, c_vp, c_i64, c_vp, C.c_int, c_vp, c_vp]),
     "mb_cumsum_f32": (C.c_int, [c_vp, c_vp, c_i64, c_d, c_vp, c_vp]),
     "mb_ancestors": (C.c_int, [c_vp, c_vp, c_i64, C.c_int, c_vp, c_u64, c_u32, c_i64, c_vp, c_i64, c_vp, c_vp]),
@@ -99,11 +105,26 @@ SIGNATURES = {
     "mb_smc_init": (C.c_int, [c_vp, C.POINTER(Target), c_vp, c_i64, c_i64, c_i64, C.c_int, c_vp, c_vp, c_vp, c_u64,
                               c_i64, c_vp, c_vp]),
     "mb_smc_move": (C.c_int, [c_vp, C.POINTER(Target), C.POINTER(Move), c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp,
-                              c_vp, c_vp, c_u64, c_i64, c_vp, c_vp]),
+                              c_vp, c_vp, c_u64, c_i64, c_vp, c_vp, c_vp]),
     "mb_pf_init": (C.c_int, [c_vp, C.POINTER(SSM), c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_u64, c_i64, c_d, c_vp,
-                             c_vp, c_vp]),
+                             c_vp, c_vp, c_vp]),
     "mb_pf_step": (C.c_int, [c_vp, C.POINTER(SSM), c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_u64, c_u32,
-                             c_i64, c_d, c_vp, c_vp, c_vp]),
+                             c_i64, c_d, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "mb_ancestors_sharded": (C.c_int, [c_vp, c_vp, C.c_int, c_u64, c_u32, c_vp, c_i64, c_vp, c_vp]),
+    "mb_strata_count": (C.c_int, [c_i64]),
+    "mb_strata_hist": (C.c_int, [c_vp, c_i64, c_i64, C.c_int, c_u64, c_u32, c_vp, c_vp, c_vp]),
+    "mb_strata_reduce": (C.c_int, [c_vp, c_vp, c_vp, C.c_int, C.c_int, c_vp, c_vp, c_vp]),
+    "mb_ancestors_sorted": (C.c_int, [c_vp, c_vp, c_i64, c_vp, C.c_int, c_vp, c_vp, C.c_int, c_u64, c_u32, c_i64, c_i64,
+                                      c_vp, c_i64, c_vp, c_vp]),
+    "mb_alloc": (C.c_int, [c_vp, C.c_size_t, C.POINTER(c_vp)]),
+    "mb_free": (C.c_int, [c_vp, c_vp]),
+    "mb_ipc_get_handle": (C.c_int, [c_vp, c_vp, c_vp]),
+    "mb_ipc_open": (C.c_int, [c_vp, c_vp, C.POINTER(c_vp)]),
+    "mb_ipc_close": (C.c_int, [c_vp, c_vp]),
+    "mb_comm_create": (C.c_int, [c_vp, C.c_int, C.c_int, C.POINTER(c_vp), c_vp]),
+    "mb_comm_connect": (C.c_int, [c_vp, c_vp]),
+    "mb_comm_destroy": (None, [c_vp]),
+    "mb_comm_allgather": (C.c_int, [c_vp, c_vp, C.c_int, c_vp, c_vp]),
     "mb_weighted_moments": (C.c_int, [c_vp, c_vp, c_i64, c_i64, C.c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "mb_quantile": (C.c_int, [c_vp, c_vp, c_i64, c_d, c_vp, c_vp]),
     "mb_colstats": (C.c_int, [c_vp, c_vp, c_i64, c_i64, C.c_int, c_vp, c_vp, c_vp]),

@@ -37,7 +37,7 @@ extern "C" mb_ctx* mb_create(int device) {
     ctx->sms = prop.multiProcessorCount;
     ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
     bool ok = true;
-    ok = ok && cudaMalloc(&ctx->partials, sizeof(double) * 3 * MB_MAX_PARTIAL_BLOCKS * 2) == cudaSuccess;
+    ok = ok && cudaMalloc(&ctx->partials, sizeof(double) * (3 * MB_MAX_PARTIAL_BLOCKS * 2 + 64)) == cudaSuccess;
     ok = ok && cudaMalloc(&ctx->counters, sizeof(uint32_t) * MB_NUM_COUNTERS) == cudaSuccess;
     ok = ok && cudaMemset(ctx->counters, 0, sizeof(uint32_t) * MB_NUM_COUNTERS) == cudaSuccess;
     {

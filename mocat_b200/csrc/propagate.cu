@@ -12,6 +12,9 @@
 // the state of a particle lives in registers (D is a template parameter).
 #include "common.cuh"
 #include "rng.cuh"
+#include "comm.cuh"
+
+const MbCommDev* mb_comm_dev(const mb_comm* c);
 
 #define MV_THREADS 256
 #define TWO_PI_F 6.283185307179586f
@@ -88,6 +91,7 @@ struct SmcArgs {
     uint64_t seed; int64_t gid0;
     mb_control* ctl;
     int sample_prior;
+    mb_shard sh; int sharded;
 };
 
 // initial population: x ~ prior (transport/sampler.py:24-30), potentials, lw = 0, control block reset
@@ -141,10 +145,16 @@ __global__ void __launch_bounds__(MV_THREADS, (D <= 6 ? 4 : (D <= 10 ? 3 : 2))) 
     double alpha_local = 0.0;
 
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t src = resample ? (int64_t)a.anc[i] : i;          // fused ancestor gather (core.py:46-56)
+        int64_t src = resample ? (int64_t)a.anc[i] : i;                // fused ancestor gather (core.py:46-56)
+        const float* xb = a.x_in;
+        if (a.sharded && resample) {                                   // ancestor lives on rank `owner`: read it over NVLink
+            const int owner = (int)(src / a.sh.n_local);
+            src -= (int64_t)owner * a.sh.n_local;
+            xb = a.sh.x_peers[owner];
+        }
         float x[D];
 #pragma unroll
-        for (int k = 0; k < D; ++k) x[k] = __ldg(a.x_in + (int64_t)k * a.ld + src);
+        for (int k = 0; k < D; ++k) x[k] = __ldg(xb + (int64_t)k * a.ld + src);
         float up, ul, g[D];
         target_eval<LIK, D>(a.tgt, beta, x, up, ul, g);                // MCMC startup, standard_mcmc.py:94-102
         float U = fmaf(beta, ul, up);
@@ -253,13 +263,15 @@ extern "C" int mb_smc_init(mb_ctx* ctx, const mb_target* tgt, float* x, int64_t 
 
 extern "C" int mb_smc_move(mb_ctx* ctx, const mb_target* tgt, const mb_move* mv, const float* x_in, float* x_out,
                            int64_t ld, int64_t n, const int32_t* anc, float* lw, float* up_out, float* lik_out,
-                           float* alpha_out, uint64_t seed, int64_t gid0, mb_control* ctl, mb_stream_t stream) {
+                           float* alpha_out, uint64_t seed, int64_t gid0, mb_control* ctl, const mb_shard* sh,
+                           mb_stream_t stream) {
     MB_REQUIRE(ctx && tgt && mv && x_in && x_out && anc && lw && lik_out && ctl && n > 0 && ld >= n && x_in != x_out,
                "mb_smc_move: bad arguments");
     MB_REQUIRE(mv->mcmc_steps >= 1 && mv->leapfrog_steps >= 1, "mb_smc_move: mcmc_steps/leapfrog_steps must be >= 1");
     SmcArgs a{};
     a.tgt = *tgt; a.mv = *mv; a.x_in = x_in; a.x_out = x_out; a.ld = ld; a.n = n; a.anc = anc; a.lw = lw;
     a.up_out = up_out; a.lik_out = lik_out; a.alpha_out = alpha_out; a.seed = seed; a.gid0 = gid0; a.ctl = ctl;
+    if (sh) { a.sh = *sh; a.sharded = sh->world > 1; }
     return smc_dispatch(ctx, a, 0, 0, mb_s(stream));
 }
 
@@ -306,6 +318,8 @@ struct PfArgs {
     mb_control* ctl; mb_hist* hist;
     double* partials; uint32_t* counter;
     int init;
+    mb_shard sh; int sharded;
+    MbCommDev comm; int has_comm;
 };
 
 template <int D>
@@ -416,11 +430,17 @@ __global__ void __launch_bounds__(MV_THREADS) pf_step_kernel(PfArgs a) {
     float am = -INFINITY;
     double as1 = 0.0, as2 = 0.0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t src = resample ? (int64_t)a.anc[i] : i;
+        int64_t src = resample ? (int64_t)a.anc[i] : i;
+        const float* xb = a.x_in;
+        if (a.sharded && resample) {                                   // ancestor on another rank: NVLink peer read
+            const int owner = (int)(src / a.sh.n_local);
+            src -= (int64_t)owner * a.sh.n_local;
+            xb = a.sh.x_peers[owner];
+        }
         float x[D], z[D];
         if (!init) {
 #pragma unroll
-            for (int k = 0; k < D; ++k) x[k] = __ldg(a.x_in + (int64_t)k * a.ld + src);
+            for (int k = 0; k < D; ++k) x[k] = __ldg(xb + (int64_t)k * a.ld + src);
         }
         philox_normals<D>(z, a.seed, (uint64_t)(a.gid0 + i), a.t, init ? MB_P_INIT : MB_P_MOVE, 0u);
         const float incr = pf_particle<KIND, D>(a.ssm, x, z, ys, init);
@@ -453,6 +473,12 @@ __global__ void __launch_bounds__(MV_THREADS) pf_step_kernel(PfArgs a) {
     v = lse3_block_reduce(v, smem);
     if (threadIdx.x == 0) {
         *a.counter = 0;
+        if (a.has_comm) {                                              // global LSE/ESS: exchange the rank triples
+            double in[3] = {v.m, v.s1, v.s2}, out[3 * MB_MAX_WORLD];
+            comm_allgather(a.comm, in, 3, out);
+            v = lse3_empty();
+            for (int r = 0; r < a.comm.world; ++r) v = lse3_merge(v, Lse3{out[3 * r], out[3 * r + 1], out[3 * r + 2]});
+        }
         mb_control c;
         if (init) { memset(&c, 0, sizeof(c)); c.seed = a.seed; } else c = *ctl;
         const double nd = (double)a.n_total;
@@ -491,18 +517,20 @@ static int pf_dispatch(mb_ctx* ctx, PfArgs& a, cudaStream_t st) {
 
 extern "C" int mb_pf_init(mb_ctx* ctx, const mb_ssm* ssm, float* x, int64_t ld, int64_t n, int64_t n_total,
                           const float* y0, float* lw, uint64_t seed, int64_t gid0, double ess_threshold,
-                          mb_control* ctl, mb_hist* hist, mb_stream_t stream) {
+                          mb_control* ctl, mb_hist* hist, mb_comm* comm, mb_stream_t stream) {
     MB_REQUIRE(ctx && ssm && x && y0 && lw && ctl && n > 0 && ld >= n, "mb_pf_init: bad arguments");
     MB_REQUIRE(ssm->dim_obs <= ssm->dim, "mb_pf_init: dim_obs must be <= dim");
     PfArgs a{};
     a.ssm = *ssm; a.x_in = x; a.x_out = x; a.ld = ld; a.n = n; a.n_total = n_total; a.y = y0; a.lw = lw;
     a.seed = seed; a.t = 0; a.gid0 = gid0; a.ess_threshold = ess_threshold; a.ctl = ctl; a.hist = hist; a.init = 1;
+    if (comm) { a.comm = *mb_comm_dev(comm); a.has_comm = a.comm.world > 1; }
     return pf_dispatch(ctx, a, mb_s(stream));
 }
 
 extern "C" int mb_pf_step(mb_ctx* ctx, const mb_ssm* ssm, const float* x_in, float* x_out, int64_t ld, int64_t n,
                           int64_t n_total, const int32_t* anc, const float* y, float* lw, uint64_t seed, uint32_t t,
-                          int64_t gid0, double ess_threshold, mb_control* ctl, mb_hist* hist, mb_stream_t stream) {
+                          int64_t gid0, double ess_threshold, mb_control* ctl, mb_hist* hist, const mb_shard* sh,
+                          mb_comm* comm, mb_stream_t stream) {
     MB_REQUIRE(ctx && ssm && x_in && x_out && anc && y && lw && ctl && n > 0 && ld >= n && x_in != x_out,
                "mb_pf_step: bad arguments");
     MB_REQUIRE(ssm->dim_obs <= ssm->dim && ssm->substeps >= 1, "mb_pf_step: bad model");
@@ -510,5 +538,7 @@ extern "C" int mb_pf_step(mb_ctx* ctx, const mb_ssm* ssm, const float* x_in, flo
     a.ssm = *ssm; a.x_in = x_in; a.x_out = x_out; a.ld = ld; a.n = n; a.n_total = n_total; a.anc = anc; a.y = y;
     a.lw = lw; a.seed = seed; a.t = t; a.gid0 = gid0; a.ess_threshold = ess_threshold; a.ctl = ctl; a.hist = hist;
     a.init = 0;
+    if (sh) { a.sh = *sh; a.sharded = sh->world > 1; }
+    if (comm) { a.comm = *mb_comm_dev(comm); a.has_comm = a.comm.world > 1; }
     return pf_dispatch(ctx, a, mb_s(stream));
 }

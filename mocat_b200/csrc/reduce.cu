@@ -6,6 +6,9 @@
 // every block after a grid sync) -- no floating-point atomics anywhere.
 #include <cooperative_groups.h>
 #include "common.cuh"
+#include "comm.cuh"
+
+const MbCommDev* mb_comm_dev(const mb_comm* c);
 
 namespace cg = cooperative_groups;
 
@@ -162,6 +165,8 @@ struct TemperArgs {
     mb_control* ctl;
     mb_hist* hist;
     double* partials;      // [2][MB_MAX_PARTIAL_BLOCKS][3]
+    MbCommDev comm; int has_comm;
+    double* gbuf;          // [2][8] global triple broadcast (sharded)
 };
 
 #define TP_R 2             // float4 (lw, lik) pairs kept per thread in the resident variant
@@ -223,6 +228,7 @@ temper_adapt_kernel(TemperArgs a) {
     const double beta = c0.beta;
     const int iter_new = c0.iter + (a.advance_iter ? 1 : 0);
     int parity = 0;
+    double g_alpha_fx = (double)c0.alpha_fx, g_nan = (double)c0.nan_count;   // global sums when sharded
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
     const int64_t n4 = a.n >> 2;
@@ -284,7 +290,25 @@ temper_adapt_kernel(TemperArgs a) {
             part[3 * blockIdx.x] = blk.m; part[3 * blockIdx.x + 1] = blk.s1; part[3 * blockIdx.x + 2] = blk.s2;
         }
         grid.sync();
-        const Lse3 r = lse_merge_partials_fast(part, gridDim.x, smd);
+        Lse3 r = lse_merge_partials_fast(part, gridDim.x, smd);
+        if (a.has_comm) {                                // sharded population: exchange the rank triples over NVLink
+            double* gb = a.gbuf + parity * 8;
+            if (blockIdx.x == 0 && threadIdx.x == 0) {
+                double in[6] = {r.m, r.s1, r.s2, (double)c0.alpha_fx, (double)c0.nan_count, 0.0}, out[6 * MB_MAX_WORLD];
+                comm_allgather(a.comm, in, 6, out);
+                Lse3 g = lse3_empty();
+                double afx = 0.0, nanc = 0.0;
+                for (int q = 0; q < a.comm.world; ++q) {
+                    g = lse3_merge(g, Lse3{out[6 * q], out[6 * q + 1], out[6 * q + 2]});
+                    afx += out[6 * q + 3]; nanc += out[6 * q + 4];
+                }
+                gb[0] = g.m; gb[1] = g.s1; gb[2] = g.s2; gb[3] = afx; gb[4] = nanc;
+                __threadfence();
+            }
+            grid.sync();
+            r = Lse3{gb[0], gb[1], gb[2]};
+            g_alpha_fx = gb[3]; g_nan = gb[4];
+        }
         parity ^= 1;
         return r;
     };
@@ -362,10 +386,10 @@ temper_adapt_kernel(TemperArgs a) {
         c.iter = iter_new;
         c.search_iters = it;
         c.resample = (c.ess <= P.ess_resample * (double)a.n_total) ? 1 : 0;          // smc.py:298-301
-        const double nan_frac = a.nan_denominator > 0 ? (double)c.nan_count / (double)a.nan_denominator : 0.0;
+        const double nan_frac = a.nan_denominator > 0 ? g_nan / (double)a.nan_denominator : 0.0;
         c.done = (b_new >= P.max_temperature || iter_new >= P.max_iter || nan_frac > 0.1) ? 1 : 0;  // :171-175
         c.nan_count = 0;
-        if (a.advance_iter) c.alpha_mean = (double)c.alpha_fx / 4294967296.0 / (double)a.n_total;
+        if (a.advance_iter) c.alpha_mean = g_alpha_fx / 4294967296.0 / (double)a.n_total;
         c.alpha_fx = 0;
         *a.ctl = c;
         if (a.hist && iter_new < MB_HIST_MAX) {
@@ -379,7 +403,7 @@ temper_adapt_kernel(TemperArgs a) {
 
 extern "C" int mb_temper_adapt(mb_ctx* ctx, float* lw, const float* lik, int64_t n, const mb_temper* prm,
                                int advance_iter, int64_t nan_denominator, int64_t n_total, mb_control* ctl,
-                               mb_hist* hist, mb_stream_t stream) {
+                               mb_hist* hist, mb_comm* comm, mb_stream_t stream) {
     MB_REQUIRE(ctx && lw && lik && prm && ctl && n > 0, "mb_temper_adapt: bad arguments");
     static int bps[2] = {0, 0};
     if (bps[0] == 0) {
@@ -397,6 +421,9 @@ extern "C" int mb_temper_adapt(mb_ctx* ctx, float* lw, const float* lik, int64_t
     if (grid > MB_MAX_PARTIAL_BLOCKS) grid = MB_MAX_PARTIAL_BLOCKS;
     if (grid < 1) grid = 1;
     TemperArgs args{lw, lik, n, *prm, advance_iter, nan_denominator, n_total > 0 ? n_total : n, ctl, hist, ctx->partials};
+    args.has_comm = 0;
+    args.gbuf = ctx->partials + 2 * 3 * MB_MAX_PARTIAL_BLOCKS;          // 64 spare doubles after the partials
+    if (comm) { args.comm = *mb_comm_dev(comm); args.has_comm = args.comm.world > 1; }
     void* kargs[] = {&args};
     void* fn = resident ? (void*)temper_adapt_kernel<true> : (void*)temper_adapt_kernel<false>;
     MB_CUDA(cudaLaunchCooperativeKernel(fn, dim3((unsigned)grid), dim3(resident ? TP_THREADS_RES : RED_THREADS), kargs, 0,

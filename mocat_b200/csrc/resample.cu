@@ -9,6 +9,9 @@
 // the sequential numpy cumsum bit for bit.  cdf = min(cumsum, 1), cdf[n-1] = 1.
 #include "common.cuh"
 #include "rng.cuh"
+#include "comm.cuh"
+
+const MbCommDev* mb_comm_dev(const mb_comm* c);
 
 #define SCAN_THREADS 256
 #define SCAN_ITEMS 16
@@ -39,6 +42,7 @@ struct ScanArgs {
     double scale;             // linear mode
     const mb_control* ctl;    // may be NULL in linear mode
     int predicated;           // 1: run only if ctl->resample && !ctl->done
+    int raw;                  // 1: rank-relative CDF for the sharded path: no clamp at 1, last element not forced
     double* cdf;
     int32_t* flag; double* agg; double* incl;
     uint32_t* epoch_ptr;      // device-side launch epoch (incremented by the kernel itself: graph-replay safe)
@@ -167,14 +171,18 @@ scan_cdf_kernel(ScanArgs a) {
             double2* o2 = reinterpret_cast<double2*>(a.cdf + base);
 #pragma unroll
             for (int k = 0; k < SCAN_ITEMS / 2; ++k) {
-                double c0 = fmin(off + q[2 * k], 1.0), c1 = fmin(off + q[2 * k + 1], 1.0);
-                if (base + 2 * k + 1 == a.n - 1) c1 = 1.0;
+                double c0 = off + q[2 * k], c1 = off + q[2 * k + 1];
+                if (!a.raw) {
+                    c0 = fmin(c0, 1.0); c1 = fmin(c1, 1.0);
+                    if (base + 2 * k + 1 == a.n - 1) c1 = 1.0;
+                }
                 __stcs(o2 + k, make_double2(c0, c1));
             }
         } else {
 #pragma unroll
             for (int k = 0; k < SCAN_ITEMS; ++k)
-                if (base + k < a.n) a.cdf[base + k] = (base + k == a.n - 1) ? 1.0 : fmin(off + q[k], 1.0);
+                if (base + k < a.n)
+                    a.cdf[base + k] = a.raw ? (off + q[k]) : ((base + k == a.n - 1) ? 1.0 : fmin(off + q[k], 1.0));
         }
         __syncthreads();
     }
@@ -206,11 +214,13 @@ static int scan_launch(mb_ctx* ctx, ScanArgs& a, cudaStream_t st) {
     return MB_OK;
 }
 
-extern "C" int mb_cumsum_lw(mb_ctx* ctx, const float* lw, int64_t n, const mb_control* ctl, int force,
+extern "C" int mb_cumsum_lw(mb_ctx* ctx, const float* lw, int64_t n, const mb_control* ctl, int flags,
                             double* cdf, mb_stream_t stream) {
+    const int force = flags & 1;
     MB_REQUIRE(ctx && lw && ctl && cdf && n > 0, "mb_cumsum_lw: bad arguments");
     ScanArgs a{};
     a.in = lw; a.n = n; a.log_mode = 1; a.scale = 0; a.ctl = ctl; a.predicated = force ? 0 : 1; a.cdf = cdf;
+    a.raw = (flags & 2) ? 1 : 0;
     return scan_launch(ctx, a, mb_s(stream));
 }
 
@@ -325,6 +335,321 @@ extern "C" int mb_ancestors(mb_ctx* ctx, const double* cdf, int64_t n, int mode,
         mb_set_error("mb_ancestors: unknown mode %d", mode);
         return MB_ERR_ARG;
     }
+    MB_CHECK_LAUNCH();
+    return MB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stratified-exact multinomial resampling: n iid uniforms are equivalent in law to
+//   (1) the counts N_b of uniforms falling into B equal strata of [0,1)  -- obtained as an integer histogram
+//       of first-stage Philox uniforms (deterministic), and
+//   (2) N_b fresh iid uniforms inside stratum b                          -- second-stage Philox uniforms.
+// Output slot g (global) takes stratum s(g) = upper_bound(offsets, g) - 1 and u_g = (s + v_g)/B.  The u's come
+// out sorted by stratum, so (like systematic resampling) a block of outputs maps to one contiguous CDF window
+// that is staged in shared memory, ancestors are nearly sorted and the fused gather stays coalesced.  The law
+// is exactly Cat(softmax(w))^n as in the reference (transport/smc.py:65-67).
+struct StrataArgs {
+    uint32_t* hist; uint32_t* offsets; int B;
+    int64_t n_out; int64_t gid0;
+    uint64_t seed; uint32_t step;
+    const mb_control* ctl;
+};
+
+__global__ void __launch_bounds__(256) strata_hist_kernel(StrataArgs a) {
+    if (a.ctl && (a.ctl->done || !a.ctl->resample)) return;
+    const uint32_t step = a.ctl ? (uint32_t)(a.ctl->iter + 1) : a.step;
+    const uint64_t seed = a.ctl ? a.ctl->seed : a.seed;
+    const double Bd = (double)a.B;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n_out; i += (int64_t)gridDim.x * blockDim.x) {
+        const Philox4 r = philox_raw(seed, (uint64_t)(a.gid0 + i), step, MB_P_RESAMPLE, 0u);
+        const int b = (int)(u53(r.x, r.y) * Bd);                      // exact: B is a power of two
+        atomicAdd(a.hist + b, 1u);
+    }
+}
+
+// single-block exclusive scan of the B strata counts -> offsets[B+1]
+__global__ void __launch_bounds__(1024) strata_scan_kernel(StrataArgs a) {
+    if (a.ctl && (a.ctl->done || !a.ctl->resample)) return;
+    __shared__ uint32_t wsum[32];
+    __shared__ uint32_t carry_s;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int base = 0; base < a.B; base += 1024) {
+        const int i = base + threadIdx.x;
+        const uint32_t v = (i < a.B) ? a.hist[i] : 0u;
+        uint32_t x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(MB_FULL, x, o); if (lane >= o) x += t; }
+        if (lane == 31) wsum[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = wsum[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(MB_FULL, w, o); if (lane >= o) w += t; }
+            wsum[lane] = w;
+        }
+        __syncthreads();
+        const uint32_t carry = carry_s;
+        const uint32_t incl = x + (warp ? wsum[warp - 1] : 0u) + carry;
+        if (i < a.B) a.offsets[i] = incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) a.offsets[a.B] = carry_s;
+}
+
+struct SortedAncArgs {
+    int stratified;                      // 0: systematic, 1: stratified-exact multinomial
+    const double* cdf; int64_t n;        // single-GPU: materialised clamped CDF
+    mb_shard sh; int sharded;            // sharded: rank-relative CDFs of all ranks + totals
+    const uint32_t* offsets; int B;      // strata offsets (stratified)
+    uint64_t seed; uint32_t step; int64_t gid0; int64_t n_out; int64_t n_total_out;
+    int32_t* anc;
+    const mb_control* ctl;
+};
+
+struct GlobalCdf {                       // unified view of the (possibly sharded) global CDF
+    const double* cdf; int64_t n;
+    bool sharded; int W; int64_t nl;
+    const double* peers[MB_MAX_WORLD];
+    double off[MB_MAX_WORLD + 1];
+
+    __device__ __forceinline__ double at(int64_t j) const {           // min(C_j, 1), cdf[n-1] = 1
+        if (!sharded) return __ldg(cdf + j);
+        if (j >= n - 1) return 1.0;
+        const int r = (int)(j / nl);
+        return fmin(off[r] + __ldg(peers[r] + (j - (int64_t)r * nl)), 1.0);
+    }
+    __device__ __forceinline__ int64_t upper_bound(int64_t lo, int64_t hi, double u) const {
+        if (sharded) {                                                // narrow to one rank first (<= 8 compares)
+            for (int r = 0; r < W; ++r) {
+                const int64_t r0 = (int64_t)r * nl, r1 = r0 + nl;
+                if (r1 <= lo) continue;
+                if (r0 >= hi) break;
+                if (fmin(off[r + 1], 1.0) > u || r == W - 1) { lo = max(lo, r0); hi = min(hi, r1); break; }
+                lo = r1;
+            }
+        }
+        while (lo < hi) {
+            const int64_t mid = lo + ((hi - lo) >> 1);
+            if (at(mid) > u) hi = mid; else lo = mid + 1;
+        }
+        return lo;
+    }
+};
+
+__global__ void __launch_bounds__(ANC_THREADS)
+ancestors_sorted_kernel(SortedAncArgs a) {
+    if (a.ctl && (a.ctl->done || !a.ctl->resample)) return;
+    __shared__ double win[ANC_SMEM_CAP];
+    __shared__ uint32_t soff[1024];
+    __shared__ int64_t w_lo, w_hi;
+    __shared__ int s_lo_s, s_hi_s;
+    const uint32_t step = a.ctl ? (uint32_t)(a.ctl->iter + 1) : a.step;
+    const uint64_t seed = a.ctl ? a.ctl->seed : a.seed;
+    GlobalCdf G;
+    G.cdf = a.cdf; G.n = a.sharded ? a.sh.n_total : a.n; G.sharded = a.sharded != 0; G.W = a.sh.world; G.nl = a.sh.n_local;
+    if (G.sharded) {
+        G.off[0] = 0.0;
+        for (int r = 0; r < G.W; ++r) { G.peers[r] = a.sh.cdf_peers[r]; G.off[r + 1] = G.off[r] + a.sh.totals[r]; }
+    }
+    double u0 = 0.0;
+    if (!a.stratified) { const Philox4 r = philox_raw(seed, 0ull, step, MB_P_RESAMPLE, 0u); u0 = u53(r.x, r.y); }
+    const double nd = (double)a.n_total_out, Bd = (double)a.B;
+
+    for (int64_t b0 = (int64_t)blockIdx.x * ANC_BLOCK_OUT; b0 < a.n_out; b0 += (int64_t)gridDim.x * ANC_BLOCK_OUT) {
+        const int64_t b1 = min(b0 + (int64_t)ANC_BLOCK_OUT, a.n_out);
+        const int64_t g_first = a.gid0 + b0, g_last = a.gid0 + b1 - 1;
+        // ---- u-range of the block -> CDF window
+        if (threadIdx.x == 0) {
+            double ulo;
+            if (a.stratified) {
+                int lo = 0, hi = a.B;                                  // stratum(g) = upper_bound(offsets, g) - 1
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if ((int64_t)a.offsets[mid + 1] > g_first) hi = mid; else lo = mid + 1; }
+                s_lo_s = lo;
+                ulo = (double)lo / Bd;
+            } else ulo = ((double)g_first + u0) / nd;
+            w_lo = G.upper_bound(0, G.n, ulo);
+        }
+        if (threadIdx.x == 32) {
+            double uhi;
+            if (a.stratified) {
+                int lo = 0, hi = a.B;
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if ((int64_t)a.offsets[mid + 1] > g_last) hi = mid; else lo = mid + 1; }
+                s_hi_s = lo;
+                uhi = (double)(lo + 1) / Bd;                           // every u of the block is < uhi
+            } else uhi = ((double)g_last + u0) / nd;
+            w_hi = G.upper_bound(0, G.n, uhi);
+        }
+        __syncthreads();
+        const int64_t lo = w_lo, hi = min(w_hi, G.n - 1);
+        const int64_t len = hi - lo + 1;
+        const bool staged = len <= ANC_SMEM_CAP;
+        const int s_lo = s_lo_s, s_hi = s_hi_s;
+        const bool soff_staged = a.stratified && (s_hi - s_lo + 2) <= 1024;
+        if (staged) for (int64_t k = threadIdx.x; k < len; k += ANC_THREADS) win[k] = G.at(lo + k);
+        if (soff_staged) for (int k = threadIdx.x; k < s_hi - s_lo + 2; k += ANC_THREADS) soff[k] = a.offsets[s_lo + k];
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < ANC_ITEMS; ++k) {
+            const int64_t i = b0 + (int64_t)k * ANC_THREADS + threadIdx.x;
+            if (i < b1) {
+                const int64_t g = a.gid0 + i;
+                double u;
+                if (a.stratified) {
+                    int l = s_lo, h = s_hi;                           // stratum of g inside [s_lo, s_hi]
+                    if (soff_staged) { while (l < h) { const int mid = (l + h) >> 1; if ((int64_t)soff[mid + 1 - s_lo] > g) h = mid; else l = mid + 1; } }
+                    else { while (l < h) { const int mid = (l + h) >> 1; if ((int64_t)a.offsets[mid + 1] > g) h = mid; else l = mid + 1; } }
+                    const Philox4 r = philox_raw(seed, (uint64_t)g, step, MB_P_RESAMPLE, 1u);
+                    u = ((double)l + u53(r.x, r.y)) / Bd;
+                } else u = ((double)g + u0) / nd;
+                int64_t j;
+                if (staged) j = lo + upper_bound_s(win, 0, (int)len, u);
+                else j = G.upper_bound(lo, hi + 1, u);
+                if (j > G.n - 1) j = G.n - 1;
+                a.anc[i] = (int32_t)j;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+static int strata_B(int64_t n_total_out) {
+    int B = 1;
+    while ((int64_t)B * 32 <= n_total_out && B < (1 << 24)) B <<= 1;   // largest power of two <= n/16
+    return B;
+}
+
+extern "C" int mb_strata_count(int64_t n_total_out) { return strata_B(n_total_out); }
+
+// first stage: histogram of this rank's outputs over the B strata (hist must hold B uint32; it is zeroed here)
+extern "C" int mb_strata_hist(mb_ctx* ctx, int64_t n_out, int64_t gid0, int B, uint64_t seed, uint32_t step,
+                              const mb_control* ctl, uint32_t* hist, mb_stream_t stream) {
+    MB_REQUIRE(ctx && hist && n_out > 0 && B >= 1 && (B & (B - 1)) == 0, "mb_strata_hist: bad arguments");
+    MB_CUDA(cudaMemsetAsync(hist, 0, sizeof(uint32_t) * B, mb_s(stream)));
+    StrataArgs a{hist, nullptr, B, n_out, gid0, seed, step, ctl};
+    int64_t grid = (n_out + 255) / 256;
+    if (grid > (int64_t)ctx->sms * 16) grid = (int64_t)ctx->sms * 16;
+    strata_hist_kernel<<<(unsigned)grid, 256, 0, mb_s(stream)>>>(a);
+    MB_CHECK_LAUNCH();
+    return MB_OK;
+}
+
+// second stage: exclusive scan -> offsets[B+1]; then ancestors for this rank's outputs.
+// sh == NULL: single GPU (cdf = materialised clamped CDF of n particles); else the sharded global CDF.
+extern "C" int mb_ancestors_sorted(mb_ctx* ctx, const double* cdf, int64_t n, const mb_shard* sh, int mode,
+                                   const uint32_t* hist, uint32_t* offsets, int B, uint64_t seed, uint32_t step,
+                                   int64_t gid0, int64_t n_total_out, int32_t* anc, int64_t n_out,
+                                   const mb_control* ctl, mb_stream_t stream) {
+    MB_REQUIRE(ctx && anc && n_out > 0 && n_total_out >= n_out && (cdf || sh), "mb_ancestors_sorted: bad arguments");
+    MB_REQUIRE(mode == MB_RESAMPLE_SYSTEMATIC || (hist && offsets && B >= 1), "mb_ancestors_sorted: strata buffers missing");
+    SortedAncArgs a{};
+    a.stratified = (mode == MB_RESAMPLE_MULTINOMIAL) ? 1 : 0;
+    a.cdf = cdf; a.n = n;
+    if (sh) { a.sh = *sh; a.sharded = 1; }
+    a.offsets = offsets; a.B = B; a.seed = seed; a.step = step; a.gid0 = gid0; a.n_out = n_out;
+    a.n_total_out = n_total_out; a.anc = anc; a.ctl = ctl;
+    if (a.stratified) {
+        StrataArgs sa{const_cast<uint32_t*>(hist), offsets, B, n_out, gid0, seed, step, ctl};
+        strata_scan_kernel<<<1, 1024, 0, mb_s(stream)>>>(sa);
+        MB_CHECK_LAUNCH();
+    }
+    int64_t grid = (n_out + ANC_BLOCK_OUT - 1) / ANC_BLOCK_OUT;
+    if (grid > (int64_t)ctx->sms * 16) grid = (int64_t)ctx->sms * 16;
+    ancestors_sorted_kernel<<<(unsigned)grid, ANC_THREADS, 0, mb_s(stream)>>>(a);
+    MB_CHECK_LAUNCH();
+    return MB_OK;
+}
+
+// sharded: global strata counts = sum of the ranks' local histograms, read over NVLink after a mailbox barrier
+struct StrataSumArgs {
+    const uint32_t* peers[MB_MAX_WORLD]; int world; int B; uint32_t* out; const mb_control* ctl;
+};
+__global__ void __launch_bounds__(256) strata_sum_kernel(StrataSumArgs a) {
+    if (a.ctl && (a.ctl->done || !a.ctl->resample)) return;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.B; i += gridDim.x * blockDim.x) {
+        uint32_t s = 0;
+        for (int r = 0; r < a.world; ++r) s += a.peers[r][i];
+        a.out[i] = s;
+    }
+}
+__global__ void strata_barrier_kernel(MbCommDev c, const mb_control* ctl) {
+    if (ctl && (ctl->done || !ctl->resample)) return;               // identical decision on every rank
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double in[1] = {0.0}, out[MB_MAX_WORLD];
+        comm_allgather(c, in, 1, out);
+    }
+}
+
+extern "C" int mb_strata_reduce(mb_ctx* ctx, mb_comm* comm, const void* const* hist_peers, int world, int B,
+                                uint32_t* hist_out, const mb_control* ctl, mb_stream_t stream) {
+    MB_REQUIRE(ctx && comm && hist_peers && hist_out && world >= 1 && world <= MB_MAX_WORLD && B >= 1,
+               "mb_strata_reduce: bad arguments");
+    strata_barrier_kernel<<<1, 32, 0, mb_s(stream)>>>(*mb_comm_dev(comm), ctl);
+    MB_CHECK_LAUNCH();
+    StrataSumArgs a{};
+    for (int r = 0; r < world; ++r) a.peers[r] = (const uint32_t*)hist_peers[r];
+    a.world = world; a.B = B; a.out = hist_out; a.ctl = ctl;
+    int grid = (B + 255) / 256;
+    if (grid > ctx->sms * 8) grid = ctx->sms * 8;
+    strata_sum_kernel<<<grid, 256, 0, mb_s(stream)>>>(a);
+    MB_CHECK_LAUNCH();
+    return MB_OK;
+}
+
+// ---- sharded ancestors: global search over the ranks' relative CDFs (peer-mapped)
+struct ShardAncArgs {
+    mb_shard sh;
+    int mode;
+    uint64_t seed; uint32_t step;
+    int32_t* anc; int64_t n_out;
+    const mb_control* ctl;
+};
+
+__global__ void __launch_bounds__(ANC_THREADS)
+ancestors_sharded_kernel(ShardAncArgs a) {
+    if (a.ctl && (a.ctl->done || !a.ctl->resample)) return;
+    const uint32_t step = a.ctl ? (uint32_t)(a.ctl->iter + 1) : a.step;
+    const uint64_t seed = a.ctl ? a.ctl->seed : a.seed;
+    const int W = a.sh.world;
+    double off[MB_MAX_WORLD + 1];                       // exclusive prefix of the (exact) rank totals
+    off[0] = 0.0;
+    for (int r = 0; r < W; ++r) off[r + 1] = off[r] + a.sh.totals[r];
+    double u0 = 0.0;
+    if (a.mode == MB_RESAMPLE_SYSTEMATIC) { const Philox4 r = philox_raw(seed, 0ull, step, MB_P_RESAMPLE, 0u); u0 = u53(r.x, r.y); }
+    const int64_t g0 = (int64_t)a.sh.rank * a.sh.n_local;
+    const int64_t nl = a.sh.n_local, nt = a.sh.n_total;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n_out; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t g = g0 + i;
+        double u;
+        if (a.mode == MB_RESAMPLE_SYSTEMATIC) u = ((double)g + u0) / (double)nt;
+        else { const Philox4 r = philox_raw(seed, (uint64_t)g, step, MB_P_RESAMPLE, 0u); u = u53(r.x, r.y); }
+        // owner: first rank whose last global CDF value min(off_r + T_r, 1) exceeds u
+        int r = 0;
+        while (r < W - 1 && !(fmin(off[r + 1], 1.0) > u)) ++r;
+        const double* c = a.sh.cdf_peers[r];
+        const double o = off[r];
+        int64_t lo = 0, hi = nl;
+        while (lo < hi) {                               // smallest j with min(o + c[j], 1) > u (exact fp64 add)
+            const int64_t mid = lo + ((hi - lo) >> 1);
+            if (fmin(o + __ldg(c + mid), 1.0) > u) hi = mid; else lo = mid + 1;
+        }
+        int64_t j = (int64_t)r * nl + lo;
+        if (j > nt - 1) j = nt - 1;                     // cdf[n-1] = 1 convention
+        a.anc[i] = (int32_t)j;
+    }
+}
+
+extern "C" int mb_ancestors_sharded(mb_ctx* ctx, const mb_shard* sh, int mode, uint64_t seed, uint32_t step,
+                                    int32_t* anc, int64_t n_out, const mb_control* ctl, mb_stream_t stream) {
+    MB_REQUIRE(ctx && sh && anc && n_out > 0 && sh->world >= 1 && sh->world <= MB_MAX_WORLD && sh->totals &&
+                   sh->n_total <= 0x7fffffffll, "mb_ancestors_sharded: bad arguments");
+    ShardAncArgs a{*sh, mode, seed, step, anc, n_out, ctl};
+    int64_t grid = (n_out + ANC_THREADS - 1) / ANC_THREADS;
+    if (grid > (int64_t)ctx->sms * 32) grid = (int64_t)ctx->sms * 32;
+    ancestors_sharded_kernel<<<(unsigned)grid, ANC_THREADS, 0, mb_s(stream)>>>(a);
     MB_CHECK_LAUNCH();
     return MB_OK;
 }

@@ -126,8 +126,29 @@ def target_potential_grad(target, beta, X):
     return U, G
 
 
+class _Resampler:
+    """scan -> (strata histogram) -> sorted-uniform ancestor search; every kernel is predicated on the device-side
+    resample flag of the control block, so the host enqueues them unconditionally."""
+
+    def _alloc_resampler(self):
+        dev = _dev()
+        self.cdf = torch.empty(self.n, dtype=torch.float64, device=dev)
+        self.anc = torch.zeros(self.n, dtype=torch.int32, device=dev)
+        self.B = int(self.L.dll.mb_strata_count(self.n_total))
+        self.hist = torch.zeros(self.B, dtype=torch.int32, device=dev)
+        self.offsets = torch.zeros(self.B + 1, dtype=torch.int32, device=dev)
+
+    def _resample_kernels(self, st):
+        L = self.L
+        L.call("mb_cumsum_lw", self.ctx, ptr(self.lw), self.n, ptr(self.ctl.t), 0, ptr(self.cdf), st)
+        if self.resampling == _lib.RESAMPLE_MULTINOMIAL:
+            L.call("mb_strata_hist", self.ctx, self.n, self.gid0, self.B, self.seed, 0, ptr(self.ctl.t), ptr(self.hist), st)
+        L.call("mb_ancestors_sorted", self.ctx, ptr(self.cdf), self.n, None, self.resampling, ptr(self.hist),
+               ptr(self.offsets), self.B, self.seed, 0, self.gid0, self.n_total, ptr(self.anc), self.n, ptr(self.ctl.t), st)
+
+
 # ------------------------------------------------------------------------------------------- tempered SMC
-class SMCEngine:
+class SMCEngine(_Resampler):
     """Device state + kernel sequence of one tempered-SMC population (transport/smc.py)."""
 
     def __init__(self, target, move, temper, n, seed, resampling=_lib.RESAMPLE_MULTINOMIAL, gid0=0, n_total=None,
@@ -145,8 +166,7 @@ class SMCEngine:
         self.lw, self.lik = f(), f()
         self.up = f() if keep_prior_potential else None
         self.alpha = f() if keep_alpha else None
-        self.cdf = torch.empty(self.n, dtype=torch.float64, device=dev)
-        self.anc = torch.zeros(self.n, dtype=torch.int32, device=dev)
+        self._alloc_resampler()
         self.ctl = ControlBlock()
         self._schedule = None
         if schedule is not None:
@@ -156,6 +176,10 @@ class SMCEngine:
         self.enqueued = 0
         self.use_graphs = os.environ.get("MOCAT_B200_GRAPHS", "1") != "0"
         self._graphs = [None, None]
+        self.comm = None          # mb_comm* when the population is sharded over several GPUs (parallel.py)
+
+    def _shard_ref(self):
+        return None
 
     @property
     def x(self):
@@ -163,7 +187,8 @@ class SMCEngine:
 
     def _temper(self, advance):
         self.L.call("mb_temper_adapt", self.ctx, ptr(self.lw), ptr(self.lik), self.n, C.byref(self.temper),
-                    1 if advance else 0, self.n_total * self.d, self.n_total, ptr(self.ctl.t), ptr(self.ctl.hist), stream())
+                    1 if advance else 0, self.n_total * self.d, self.n_total, ptr(self.ctl.t), ptr(self.ctl.hist), self.comm,
+                    stream())
 
     def startup(self, x0=None):
         """transport/smc.py:128-164 + 267-296.  x0: optional (n, d) host/device array of initial values."""
@@ -180,15 +205,13 @@ class SMCEngine:
         st = stream()
         if events:
             events[0].record()
-        self.L.call("mb_cumsum_lw", self.ctx, ptr(self.lw), self.n, ptr(self.ctl.t), 0, ptr(self.cdf), st)
-        self.L.call("mb_ancestors", self.ctx, ptr(self.cdf), self.n, self.resampling, None, self.seed,
-                    0, self.gid0, ptr(self.anc), self.n, ptr(self.ctl.t), st)   # step comes from ctl->iter + 1
+        self._resample_kernels(st)                                  # RNG step comes from ctl->iter + 1 on the device
         if events:
             events[1].record()
         src, dst = self.xbuf[self.cur], self.xbuf[self.cur ^ 1]
         self.L.call("mb_smc_move", self.ctx, C.byref(self.target), C.byref(self.move), ptr(src), ptr(dst), self.ld,
                     self.n, ptr(self.anc), ptr(self.lw), ptr(self.up), ptr(self.lik), ptr(self.alpha), self.seed,
-                    self.gid0, ptr(self.ctl.t), st)
+                    self.gid0, ptr(self.ctl.t), self._shard_ref(), st)
         if events:
             events[2].record()
         self._temper(advance=True)
@@ -270,7 +293,7 @@ class SMCEngine:
 
 
 # ------------------------------------------------------------------------------------------- bootstrap PF
-class PFEngine:
+class PFEngine(_Resampler):
     """Device state + kernel sequence of a bootstrap particle filter (ssm/filtering.py)."""
 
     def __init__(self, ssm, n, seed, ess_threshold=0.5, resampling=_lib.RESAMPLE_MULTINOMIAL, gid0=0, n_total=None):
@@ -285,8 +308,7 @@ class PFEngine:
         self.xbuf = [torch.zeros((self.d, self.ld), dtype=torch.float32, device=dev) for _ in range(2)]
         self.cur = 0
         self.lw = torch.zeros(self.n, dtype=torch.float32, device=dev)
-        self.cdf = torch.empty(self.n, dtype=torch.float64, device=dev)
-        self.anc = torch.zeros(self.n, dtype=torch.int32, device=dev)
+        self._alloc_resampler()
         self.ctl = ControlBlock()
         self.t = 0
 
@@ -298,20 +320,18 @@ class PFEngine:
         """initiate_particles (ssm/filtering.py:173-193).  y0: device float32 (dim_obs,)"""
         self.L.call("mb_pf_init", self.ctx, C.byref(self.ssm), ptr(self.x), self.ld, self.n, self.n_total, ptr(y0),
                     ptr(self.lw), self.seed, self.gid0, self.ess_threshold, ptr(self.ctl.t), ptr(self.ctl.hist),
-                    stream())
+                    None, stream())
         self.t = 0
 
     def step(self, y):
         """one body of the scan in run_particle_filter_for_marginals (ssm/filtering.py:280-311)"""
         st = stream()
         self.t += 1
-        self.L.call("mb_cumsum_lw", self.ctx, ptr(self.lw), self.n, ptr(self.ctl.t), 0, ptr(self.cdf), st)
-        self.L.call("mb_ancestors", self.ctx, ptr(self.cdf), self.n, self.resampling, None, self.seed, self.t,
-                    self.gid0, ptr(self.anc), self.n, ptr(self.ctl.t), st)
+        self._resample_kernels(st)
         src, dst = self.xbuf[self.cur], self.xbuf[self.cur ^ 1]
         self.L.call("mb_pf_step", self.ctx, C.byref(self.ssm), ptr(src), ptr(dst), self.ld, self.n, self.n_total,
                     ptr(self.anc), ptr(y), ptr(self.lw), self.seed, self.t, self.gid0, self.ess_threshold,
-                    ptr(self.ctl.t), ptr(self.ctl.hist), st)
+                    ptr(self.ctl.t), ptr(self.ctl.hist), None, None, st)
         self.cur ^= 1
 
     def values(self):
@@ -319,7 +339,7 @@ class PFEngine:
 
 
 # ------------------------------------------------------------------------------------------- SMC-ABC
-class ABCEngine:
+class ABCEngine(_Resampler):
     """Device state + kernel sequence of SMC-ABC on the g-and-k model (abc/smc.py, abc/mcmc.py)."""
 
     def __init__(self, gk, n, seed, mcmc_steps=1, max_iter=10000, ess_retain=0.9, ess_resample=0.5,
@@ -341,8 +361,7 @@ class ABCEngine:
         self.cur = 0
         self.lw = f()
         self.stepsize = torch.ones(self.d, dtype=torch.float32, device=dev)
-        self.cdf = torch.empty(self.n, dtype=torch.float64, device=dev)
-        self.anc = torch.zeros(self.n, dtype=torch.int32, device=dev)
+        self._alloc_resampler()
         self.ctl = ControlBlock()
         self._schedule = None
         if threshold_schedule is not None:
@@ -373,9 +392,7 @@ class ABCEngine:
 
     def update(self):
         st = stream()
-        self.L.call("mb_cumsum_lw", self.ctx, ptr(self.lw), self.n, ptr(self.ctl.t), 0, ptr(self.cdf), st)
-        self.L.call("mb_ancestors", self.ctx, ptr(self.cdf), self.n, self.resampling, None, self.seed,
-                    self.enqueued + 1, self.gid0, ptr(self.anc), self.n, ptr(self.ctl.t), st)
+        self._resample_kernels(st)
         c, o = self.cur, self.cur ^ 1
         self.L.call("mb_abc_move", self.ctx, C.byref(self.gk), self.mcmc_steps, ptr(self.xbuf[c]), ptr(self.xbuf[o]),
                     self.ld, self.n, ptr(self.anc), ptr(self.upbuf[c]), ptr(self.upbuf[o]), ptr(self.distbuf[c]),

@@ -1,0 +1,241 @@
+"""Sharded populations over the GPUs of one NVSwitch domain.
+
+One process per GPU (torchrun).  Rank r owns the contiguous global particle range [r*n_local, (r+1)*n_local);
+Philox is keyed on the global particle id, the fp64 CDF arithmetic is exact, so a population sharded over P GPUs
+produces the same ancestors and the same particles as on one GPU.  The only communication of a population step:
+
+  * the (max, sum, sumsq) LSE/ESS triple of every rank        -> exchanged INSIDE the kernels (tempering search:
+    once per regula-falsi evaluation; particle filter: once per step) through peer-mapped mailboxes (csrc/comm.cuh);
+  * the ranks' quantised weight totals (one fp64 each)          -> `mb_comm_allgather`, gives every rank's CDF offset;
+  * the ancestors' state                                        -> read directly from the owning rank's HBM over
+    NVLink by the move kernel's fused gather (peer pointers), i.e. the redistribution all-to-all is not a
+    separate pass.
+
+`torch.distributed` (NCCL on GPUs, gloo in the CPU tests) is used only as plumbing: exchanging the 64-byte CUDA
+IPC handles at start-up and the timing barriers of bench.py.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+def shard_range(n_total, rank, world):
+    """contiguous equal shards; n_total must be divisible by world (the engines require equal shards)"""
+    if n_total % world:
+        raise _lib.MocatB200Error(f"n_total={n_total} must be divisible by the number of ranks {world}")
+    n_local = n_total // world
+    return rank * n_local, n_local
+
+
+def owner_of(global_index, n_local):
+    """(owner rank, local index) of a global particle index (host mirror of the kernels' arithmetic)"""
+    g = np.asarray(global_index, dtype=np.int64)
+    return g // n_local, g % n_local
+
+
+def global_cdf_offsets(totals):
+    """exclusive prefix of the ranks' exact weight totals = CDF offset of every rank (fp64, exact)"""
+    t = np.asarray(totals, dtype=np.float64)
+    return np.concatenate([[0.0], np.cumsum(t)])
+
+
+def all_gather_bytes(payload: bytes, group=None):
+    """gather one bytes object from every rank (works on nccl and gloo process groups)"""
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return [payload]
+    out = [None] * dist.get_world_size(group)
+    dist.all_gather_object(out, payload, group=group)
+    return out
+
+
+class _RawCuda:
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2}
+
+
+class ShardContext:
+    """rank / world + the peer-mapped mailbox communicator + IPC-shared allocations"""
+
+    def __init__(self, group=None):
+        import torch
+        import torch.distributed as dist
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if self.world > _lib.MB_MAX_WORLD:
+            raise _lib.MocatB200Error(f"at most {_lib.MB_MAX_WORLD} GPUs share one population")
+        self.L = _lib.get()
+        self.ctx = self.L.ctx()
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        handle = (C.c_char * 64)()
+        comm = C.c_void_p()
+        self.L.call("mb_comm_create", self.ctx, self.rank, self.world, C.byref(comm), handle)
+        handles = all_gather_bytes(bytes(handle), group)
+        self.L.call("mb_comm_connect", comm, b"".join(handles))
+        self.comm = comm
+        self._allocs = []
+
+    def alloc_shared(self, shape, dtype):
+        """cudaMalloc'd tensor on this rank + the device pointers of the same tensor on every rank"""
+        import torch
+        typestr = {torch.float32: "<f4", torch.float64: "<f8", torch.int32: "<i4"}[dtype]
+        nbytes = int(np.prod(shape)) * {"<f4": 4, "<f8": 8, "<i4": 4}[typestr]
+        p = C.c_void_p()
+        self.L.call("mb_alloc", self.ctx, nbytes, C.byref(p))
+        handle = (C.c_char * 64)()
+        self.L.call("mb_ipc_get_handle", self.ctx, p, handle)
+        handles = all_gather_bytes(bytes(handle), self.group)
+        peers = []
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                peers.append(p.value)
+            else:
+                q = C.c_void_p()
+                self.L.call("mb_ipc_open", self.ctx, h, C.byref(q))
+                peers.append(q.value)
+        t = torch.as_tensor(_RawCuda(p.value, shape, typestr), device=self.device)
+        self._allocs.append((p, peers))
+        return t, peers
+
+    def allgather(self, src, nd, dst):
+        self.L.call("mb_comm_allgather", self.comm, _lib.ptr(src), int(nd), _lib.ptr(dst), _lib.stream())
+
+
+def _make_shard(sc, n_local, x_peers, cdf_peers, totals):
+    sh = _lib.Shard()
+    sh.rank, sh.world, sh.n_local, sh.n_total = sc.rank, sc.world, int(n_local), int(n_local) * sc.world
+    for r in range(sc.world):
+        sh.x_peers[r] = x_peers[r]
+        sh.cdf_peers[r] = cdf_peers[r]
+    sh.totals = totals.data_ptr()
+    return sh
+
+
+def _sharded_alloc(eng, sc):
+    import torch
+    xs = [sc.alloc_shared((eng.d, eng.ld), torch.float32) for _ in range(2)]
+    eng.xbuf = [xs[0][0], xs[1][0]]
+    eng.cdf, cdf_peers = sc.alloc_shared((eng.n,), torch.float64)
+    eng.hist_local, hist_peers = sc.alloc_shared((eng.B,), torch.int32)
+    eng.hist_peers = (C.c_void_p * sc.world)(*hist_peers)
+    eng.totals = torch.zeros(sc.world, dtype=torch.float64, device=sc.device)
+    eng.shards = [_make_shard(sc, eng.n, xs[k][1], cdf_peers, eng.totals) for k in range(2)]
+
+
+def _sharded_resample_kernels(eng, sc, st):
+    """scan (rank-relative, exact) -> weight totals exchange -> [strata histogram + reduction over ranks] ->
+    global sorted-uniform ancestor search over the peer-mapped CDFs"""
+    L, ptr = eng.L, _lib.ptr
+    ctl = ptr(eng.ctl.t)
+    L.call("mb_cumsum_lw", eng.ctx, ptr(eng.lw), eng.n, ctl, 2, ptr(eng.cdf), st)
+    sc.allgather(eng.cdf[eng.n - 1:], 1, eng.totals)
+    if eng.resampling == _lib.RESAMPLE_MULTINOMIAL:
+        L.call("mb_strata_hist", eng.ctx, eng.n, eng.gid0, eng.B, eng.seed, 0, ctl, ptr(eng.hist_local), st)
+        L.call("mb_strata_reduce", eng.ctx, sc.comm, eng.hist_peers, sc.world, eng.B, ptr(eng.hist), ctl, st)
+    L.call("mb_ancestors_sorted", eng.ctx, None, eng.n_total, C.byref(eng.shards[eng.cur]), eng.resampling,
+           ptr(eng.hist), ptr(eng.offsets), eng.B, eng.seed, 0, eng.gid0, eng.n_total, ptr(eng.anc), eng.n, ctl, st)
+
+
+def ShardedSMCEngine(sc, target, move, temper, n_local, seed, resampling=_lib.RESAMPLE_MULTINOMIAL, schedule=None):
+    """engine.SMCEngine whose population is sharded over sc.world GPUs (n_total = world * n_local)"""
+    import torch
+    from . import engine
+
+    class _Eng(engine.SMCEngine):
+        def __init__(self):
+            super().__init__(target, move, temper, n_local, seed, resampling=resampling, gid0=sc.rank * n_local,
+                             n_total=sc.world * n_local, schedule=schedule)
+            self.sc = sc
+            self.comm = sc.comm
+            self.use_graphs = False
+            _sharded_alloc(self, sc)
+
+        def _shard_ref(self):
+            return C.byref(self.shards[self.cur])
+
+        def _enqueue(self, events=None):
+            st = _lib.stream()
+            if events:
+                events[0].record()
+            L, ptr = self.L, _lib.ptr
+            _sharded_resample_kernels(self, sc, st)
+            if events:
+                events[1].record()
+            src, dst = self.xbuf[self.cur], self.xbuf[self.cur ^ 1]
+            L.call("mb_smc_move", self.ctx, C.byref(self.target), C.byref(self.move), ptr(src), ptr(dst), self.ld, self.n,
+                   ptr(self.anc), ptr(self.lw), ptr(self.up), ptr(self.lik), ptr(self.alpha), self.seed, self.gid0,
+                   ptr(self.ctl.t), self._shard_ref(), st)
+            if events:
+                events[2].record()
+            self._temper(advance=True)
+            if events:
+                events[3].record()
+
+    return _Eng()
+
+
+_SC = None
+_SMC_POOL = {}
+
+
+def shard_context():
+    """process-wide ShardContext (created on first use; collective: every rank must call it)"""
+    global _SC
+    if _SC is None:
+        _SC = ShardContext()
+    return _SC
+
+
+def acquire_sharded_smc(target, move, temper, n_local, seed, resampling, schedule=None):
+    """pooled ShardedSMCEngine (IPC allocations and handle exchange are collective and cost milliseconds:
+    repeated runs of one configuration reuse them).  Every rank takes the same decisions."""
+    sc = shard_context()
+    sched = None if schedule is None else np.asarray(schedule, np.float64)
+    key = (bytes(target), bytes(move), temper.max_temperature, temper.ess_retain, temper.ess_resample, temper.tol,
+           temper.max_search_iter, temper.max_iter, int(n_local), int(resampling),
+           None if sched is None else sched.tobytes())
+    eng = _SMC_POOL.get(key)
+    if eng is None:
+        if len(_SMC_POOL) >= 2:
+            _SMC_POOL.pop(next(iter(_SMC_POOL)))
+        eng = ShardedSMCEngine(sc, target, move, temper, n_local, seed, resampling=resampling, schedule=schedule)
+        _SMC_POOL[key] = eng
+    eng.seed = int(seed)
+    return eng
+
+
+def ShardedPFEngine(sc, ssm, n_local, seed, ess_threshold=0.5, resampling=_lib.RESAMPLE_MULTINOMIAL):
+    """engine.PFEngine whose population is sharded over sc.world GPUs"""
+    import torch
+    from . import engine
+
+    class _Eng(engine.PFEngine):
+        def __init__(self):
+            super().__init__(ssm, n_local, seed, ess_threshold=ess_threshold, resampling=resampling,
+                             gid0=sc.rank * n_local, n_total=sc.world * n_local)
+            self.sc = sc
+            _sharded_alloc(self, sc)
+
+        def init(self, y0):
+            self.L.call("mb_pf_init", self.ctx, C.byref(self.ssm), _lib.ptr(self.x), self.ld, self.n, self.n_total,
+                        _lib.ptr(y0), _lib.ptr(self.lw), self.seed, self.gid0, self.ess_threshold, _lib.ptr(self.ctl.t),
+                        _lib.ptr(self.ctl.hist), sc.comm, _lib.stream())
+            self.t = 0
+
+        def step(self, y):
+            st = _lib.stream()
+            L, ptr = self.L, _lib.ptr
+            self.t += 1
+            _sharded_resample_kernels(self, sc, st)
+            sh = self.shards[self.cur]
+            src, dst = self.xbuf[self.cur], self.xbuf[self.cur ^ 1]
+            L.call("mb_pf_step", self.ctx, C.byref(self.ssm), ptr(src), ptr(dst), self.ld, self.n, self.n_total,
+                   ptr(self.anc), ptr(y), ptr(self.lw), self.seed, self.t, self.gid0, self.ess_threshold,
+                   ptr(self.ctl.t), ptr(self.ctl.hist), C.byref(sh), sc.comm, st)
+            self.cur ^= 1
+
+    return _Eng()

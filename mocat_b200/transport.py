@@ -121,8 +121,23 @@ class MetropolisedSMCSampler(TemperedSMCSampler):
         temper = models.make_temper(self.max_temperature, P.ess_threshold_retain, P.ess_threshold_resample,
                                     P.bisection_tol, P.max_bisection_iter, self.max_iter)
         seed = key_to_seed(getattr(initial_extra, 'random_key', None))
-        eng = engine.SMCEngine.acquire(target, move, temper, n, seed, resampling=_RESAMPLING[self.resampling],
-                                       schedule=self.temperature_schedule)
+        world = 1
+        try:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                world = dist.get_world_size()
+        except Exception:
+            world = 1
+        if world > 1 and getattr(self, 'sharded', True):
+            # under torchrun `n` is the GLOBAL population size; every rank holds n/world particles, passes its
+            # own shard of initial_state.value and gets its own shard back (mocat_b200/parallel.py)
+            from . import parallel
+            _, n_local = parallel.shard_range(n, dist.get_rank(), world)
+            eng = parallel.acquire_sharded_smc(target, move, temper, n_local, seed, _RESAMPLING[self.resampling],
+                                               schedule=self.temperature_schedule)
+        else:
+            eng = engine.SMCEngine.acquire(target, move, temper, n, seed, resampling=_RESAMPLING[self.resampling],
+                                           schedule=self.temperature_schedule)
         x0 = None if initial_state is None else getattr(initial_state, 'value', None)
         eng.startup(x0)                                                 # smc.py:128-164, 267-296 on the device
         scenario.temperature = 0.

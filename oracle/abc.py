@@ -77,7 +77,7 @@ class SMCABC:
                 u0 = philox.uniform53(self.seed, np.zeros(1, np.uint64), it, philox.P_RESAMPLE)[0]
                 anc = core.ancestors_systematic(cdf, u0)
             else:
-                anc = core.ancestors_multinomial(cdf, philox.uniform53(self.seed, self.gid, it, philox.P_RESAMPLE))
+                anc = core.ancestors_multinomial_stratified(cdf, self.seed, it)[0]
             x, up, dist = x[anc], up[anc], dist[anc]
             lw, ess = np.zeros(n), float(n)
         alive = lw > -np.inf                                           # :210-219

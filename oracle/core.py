@@ -170,6 +170,31 @@ def ancestors_multinomial(cdf, u):
     return ancestors_from_uniforms(cdf, u)
 
 
+def strata_count(n_total_out):
+    """B = largest power of two <= n/16 (at least 1, at most 2^24): ~16-32 outputs per stratum"""
+    B = 1
+    while B * 32 <= n_total_out and B < (1 << 24):
+        B <<= 1
+    return B
+
+
+def ancestors_multinomial_stratified(cdf, seed, step, n_out=None):
+    """Stratified-exact multinomial (mirrors csrc/resample.cu strata_hist/ancestors_sorted): the law of n iid
+    uniforms = (histogram of first-stage uniforms over B equal strata) + (fresh second-stage uniforms inside each
+    stratum); output g takes stratum s(g) = upper_bound(offsets, g) - 1 and u_g = (s + v_g)/B."""
+    from . import philox
+    n_out = len(cdf) if n_out is None else int(n_out)
+    B = strata_count(n_out)
+    g = np.arange(n_out, dtype=np.uint64)
+    u1 = philox.uniform53(seed, g, step, philox.P_RESAMPLE, 0)
+    hist = np.bincount((u1 * B).astype(np.int64), minlength=B)
+    offsets = np.concatenate([[0], np.cumsum(hist)])
+    s = np.searchsorted(offsets, np.arange(n_out), side='right') - 1
+    v = philox.uniform53(seed, g, step, philox.P_RESAMPLE, 1)
+    u = (s.astype(np.float64) + v) / float(B)
+    return ancestors_from_uniforms(cdf, u), u
+
+
 def categorical_gumbel(rng, lw, n_out):
     """Faithful restatement of jax.random.categorical(key, lw, shape=(n_out,)):
     argmax(Gumbel(n_out, n) + lw) -- O(n_out * n) draws (smc.py:65, filtering.py:199).

@@ -42,7 +42,7 @@ class BootstrapPF:
                 u0 = philox.uniform53(self.seed, np.zeros(1, np.uint64), t, philox.P_RESAMPLE)[0]
                 anc = core.ancestors_systematic(cdf, u0)
             else:
-                anc = core.ancestors_multinomial(cdf, philox.uniform53(self.seed, self.gid, t, philox.P_RESAMPLE))
+                anc = core.ancestors_multinomial_stratified(cdf, self.seed, t)[0]
             x = x[anc]
             lw = np.zeros(n)                                           # :292
         z = philox.normals(self.seed, self.gid, t, philox.P_MOVE, self.ssm.dim, dtype=self.normal_dtype)

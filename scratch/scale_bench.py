@@ -50,7 +50,7 @@ eng.use_graphs = False
 eng.startup()
 def step_move():
     src_, dst_ = eng.xbuf[eng.cur], eng.xbuf[eng.cur ^ 1]
-    L.call("mb_smc_move", ctx, C.byref(eng.target), C.byref(eng.move), ptr(src_), ptr(dst_), eng.ld, n, ptr(eng.anc), ptr(eng.lw), ptr(eng.up), ptr(eng.lik), ptr(eng.alpha), 1, 0, ptr(eng.ctl.t), stream())
+    L.call("mb_smc_move", ctx, C.byref(eng.target), C.byref(eng.move), ptr(src_), ptr(dst_), eng.ld, n, ptr(eng.anc), ptr(eng.lw), ptr(eng.up), ptr(eng.lik), ptr(eng.alpha), 1, 0, ptr(eng.ctl.t), None, stream())
 report("smc_move Rastrigin d=5 MALA", timeit(step_move), 64, "contract 64 B (actual 4d r + 4d+12 w = 52)")
 report("temper_adapt (search+update)", timeit(lambda: eng._temper(True)), 8 * 6 + 12, "8 B x ~6 evals + 12")
 c = eng.ctl.read(); print("   search iters", c['search_iters'], "beta", c['beta'])
@@ -69,7 +69,7 @@ y = torch.randn(d, device=dev) + 2
 pf.init(y)
 def pf_only():
     src_, dst_ = pf.xbuf[pf.cur], pf.xbuf[pf.cur ^ 1]
-    L.call("mb_pf_step", ctx, C.byref(pf.ssm), ptr(src_), ptr(dst_), pf.ld, n, n, ptr(pf.anc), ptr(y), ptr(pf.lw), 3, 1, 0, 2.0, ptr(pf.ctl.t), ptr(pf.ctl.hist), stream())
+    L.call("mb_pf_step", ctx, C.byref(pf.ssm), ptr(src_), ptr(dst_), pf.ld, n, n, ptr(pf.anc), ptr(y), ptr(pf.lw), 3, 1, 0, 2.0, ptr(pf.ctl.t), ptr(pf.ctl.hist), None, None, stream())
 rec = pf.ctl.read(); rec['resample'] = 0; pf.ctl.write(rec)
 report("pf_step L96 d=40 (no resample)", timeit(pf_only, reps=3, warm=1), 8 * d + 8, "x r/w + lw r/w")
 ms_steps = []

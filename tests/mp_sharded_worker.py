@@ -1,0 +1,114 @@
+"""torchrun worker: sharded SMC / PF over WORLD_SIZE GPUs must reproduce the single-GPU population.
+Launched by tests/test_gpu_multi.py:  torchrun --nproc-per-node N tests/mp_sharded_worker.py"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from mocat_b200 import _lib, engine, models, parallel  # noqa: E402
+
+
+def main():
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    sc = parallel.ShardContext()
+    ok = True
+
+    # ---- mailbox allgather
+    src = torch.tensor([rank + 0.5, 10.0 * rank, -1.0], dtype=torch.float64, device="cuda")
+    dst = torch.zeros(3 * world, dtype=torch.float64, device="cuda")
+    for rep in range(5):
+        sc.allgather(src + rep, 3, dst)
+        exp = np.concatenate([[r + 0.5 + rep, 10.0 * r + rep, -1.0 + rep] for r in range(world)])
+        ok &= bool(np.array_equal(dst.cpu().numpy(), exp))
+    print(f"[rank {rank}] allgather ok={ok}", flush=True)
+
+    # ---- tempered SMC, systematic + multinomial: step-by-step against the single-GPU engine.
+    # Reductions are partitioned differently (fp32 partial sums per block), so temperatures agree to ~1e-8
+    # relative, not bitwise; particles are bit-identical until the first resampling, where >= 99 % of the
+    # ancestors must coincide (exact CDF; the scale differs by ~1e-9), afterwards the runs are compared
+    # statistically.
+    n_local, d, seed = 40_000, 5, 9
+
+    def gather(t):
+        t = t.contiguous()
+        g = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(g, t)
+        return torch.cat(g).cpu().numpy()
+
+    for resampling in (_lib.RESAMPLE_SYSTEMATIC, _lib.RESAMPLE_MULTINOMIAL):
+        tgt = models.make_target(_lib.LIK_RASTRIGIN, d, prior_std=3.0, a=1.0)
+        mk = lambda: (models.make_move(_lib.MOVE_MALA, 0.1), models.make_temper(max_iter=25))
+        eng = parallel.ShardedSMCEngine(sc, tgt, *mk(), n_local, seed, resampling=resampling)
+        ref = None
+        if rank == 0:
+            ref = engine.SMCEngine(tgt, *mk(), n_local * world, seed, resampling=resampling)
+            ref.use_graphs = False
+            ref.startup()
+        eng.startup()
+        seen_resample = False
+        for it in range(25):
+            eng.update()
+            xg, ag = gather(eng.values()), gather(eng.anc)
+            c = eng.ctl.read()
+            if rank == 0:
+                ref.update()
+                cr = ref.ctl.read()
+                ok &= c['iter'] == cr['iter'] and c['resampled'] == cr['resampled']
+                if not seen_resample and not c['resampled']:
+                    ok &= abs(c['beta'] - cr['beta']) < 1e-6 * cr['beta'] and abs(c['ess'] - cr['ess']) < 1e-6 * cr['ess']
+                    ok &= bool(np.array_equal(xg, ref.values().cpu().numpy()))
+                elif not seen_resample:
+                    same_anc = float(np.mean(ag == ref.anc.cpu().numpy()))
+                    print(f"[smc mode {resampling}] first resampling at iter {it + 1}: ancestors identical {same_anc:.5f}",
+                          flush=True)
+                    ok &= same_anc > 0.99
+                    seen_resample = True
+        c = eng.ctl.read()
+        if rank == 0:
+            cr = ref.ctl.read()
+            print(f"[smc mode {resampling}] final beta {c['beta']:.6f} vs {cr['beta']:.6f}  log_z {c['log_z']:.4f} vs "
+                  f"{cr['log_z']:.4f} ok={ok}", flush=True)
+            ok &= seen_resample and abs(c['beta'] - cr['beta']) < 2e-2 * cr['beta'] and abs(c['log_z'] - cr['log_z']) < 0.05
+        dist.barrier()
+
+    # ---- bootstrap PF on Lorenz-96 d=8, resampling every step
+    from oracle import models as omodels
+    d = 8
+    _, y = omodels.Lorenz96SSM(dim=d).simulate(8, np.random.default_rng(0), spinup=200)
+    yd = torch.as_tensor(y.astype(np.float32), device="cuda")
+    s = models.make_lorenz96(dim=d)
+    pf = parallel.ShardedPFEngine(sc, s, 30_000, 5, ess_threshold=2.0, resampling=_lib.RESAMPLE_SYSTEMATIC)
+    pf.init(yd[0])
+    for t in range(1, len(y)):
+        pf.step(yd[t])
+    c = pf.ctl.read()
+    xs = pf.values().contiguous()
+    gathered = [torch.empty_like(xs) for _ in range(world)]
+    dist.all_gather(gathered, xs)
+    if rank == 0:
+        ref = engine.PFEngine(s, 30_000 * world, 5, ess_threshold=2.0, resampling=_lib.RESAMPLE_SYSTEMATIC)
+        ref.init(yd[0])
+        for t in range(1, len(y)):
+            ref.step(yd[t])
+        cr = ref.ctl.read()
+        same = float(np.mean(np.all(torch.cat(gathered).cpu().numpy() == ref.values().cpu().numpy(), axis=1)))
+        print(f"[pf] log_z {c['log_z']:.6f} vs {cr['log_z']:.6f}; ess {c['ess']:.3f} vs {cr['ess']:.3f}; "
+              f"identical particles {same:.5f}", flush=True)
+        ok &= abs(c['log_z'] - cr['log_z']) < 1e-6 * abs(cr['log_z']) + 1e-6 and same > 0.995
+    dist.barrier()
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("SHARDED_OK" if flag.item() == 1 else "SHARDED_FAIL", flush=True)
+    dist.destroy_process_group()
+    sys.exit(0 if flag.item() == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()

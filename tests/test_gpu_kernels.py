@@ -152,3 +152,61 @@ def test_quantile_and_colstats(eng):
     rm, rv = core.colstats(x[:, :n].T)
     npt.assert_allclose(mean.cpu().numpy(), rm, rtol=1e-9)
     npt.assert_allclose(var.cpu().numpy(), rv, rtol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------ sorted-uniform path
+def _sorted_ancestors(eng, cdf_d, n, n_out, mode, seed, step):
+    import torch
+    from mocat_b200 import _lib
+    L = _lib.get()
+    B = int(L.dll.mb_strata_count(n_out))
+    hist = torch.zeros(B, dtype=torch.int32, device="cuda")
+    offs = torch.zeros(B + 1, dtype=torch.int32, device="cuda")
+    anc = torch.empty(n_out, dtype=torch.int32, device="cuda")
+    if mode == 1:
+        L.call("mb_strata_hist", L.ctx(), n_out, 0, B, seed, step, None, _lib.ptr(hist), _lib.stream())
+    L.call("mb_ancestors_sorted", L.ctx(), _lib.ptr(cdf_d), n, None, mode, _lib.ptr(hist), _lib.ptr(offs), B, seed, step,
+           0, n_out, _lib.ptr(anc), n_out, None, _lib.stream())
+    return anc.cpu().numpy(), hist.cpu().numpy(), offs.cpu().numpy(), B
+
+
+@pytest.mark.parametrize("n", [1, 17, 5000, 100_003, 1_000_000])
+def test_sorted_ancestors_bit_exact(eng, n):
+    """production resampling path (systematic and stratified-exact multinomial) == oracle, bit for bit"""
+    rng = np.random.default_rng(n)
+    w = rng.random(n).astype(np.float32) ** 6
+    w[rng.random(n) < 0.3] = 0.0
+    w[0] = max(w[0], 1e-3)
+    w = (w / w.astype(np.float64).sum()).astype(np.float32)
+    cdf = core.cdf_from_weights(w)
+    cdf_d = _t(cdf)
+    seed, step = 77, 5
+    a_sys, _, _, _ = _sorted_ancestors(eng, cdf_d, n, n, 0, seed, step)
+    u0 = philox.uniform53(seed, np.zeros(1, np.uint64), step, philox.P_RESAMPLE)[0]
+    npt.assert_array_equal(a_sys, core.ancestors_systematic(cdf, u0))
+    a_mul, hist, offs, B = _sorted_ancestors(eng, cdf_d, n, n, 1, seed, step)
+    ref, u = core.ancestors_multinomial_stratified(cdf, seed, step)
+    assert B == core.strata_count(n) and hist.sum() == n and offs[-1] == n
+    npt.assert_array_equal(a_mul, ref)
+    assert np.all(w[a_mul] > 0)                             # zero-weight particles are never selected
+
+
+def test_stratified_multinomial_is_multinomial(eng):
+    """offspring counts of the stratified-exact scheme follow Multinomial(n, w): chi-square on 50 weight bins and
+    the variance of the counts (systematic resampling would have ~zero variance here)"""
+    n = 200_000
+    rng = np.random.default_rng(0)
+    w = rng.random(n).astype(np.float32)
+    w = (w / w.astype(np.float64).sum()).astype(np.float32)
+    cdf = core.cdf_from_weights(w)
+    a, _, _, _ = _sorted_ancestors(eng, _t(cdf), n, n, 1, 3, 1)
+    counts = np.bincount(a, minlength=n)
+    bins = np.array_split(np.arange(n), 50)
+    obs = np.array([counts[b].sum() for b in bins], dtype=np.float64)
+    exp = np.array([w[b].astype(np.float64).sum() for b in bins]) * n
+    chi2 = np.sum((obs - exp) ** 2 / exp)
+    assert chi2 < 100.0                                     # 49 dof: mean 49, sd 9.9
+    # per-particle counts ~ Poisson-like: Var ~ E for multinomial (for systematic Var << E)
+    big = w > np.median(w)
+    ratio = counts[big].var() / counts[big].mean()
+    assert 0.8 < ratio < 1.4
