@@ -367,20 +367,52 @@ __global__ void __launch_bounds__(256) strata_hist_kernel(StrataArgs a) {
     }
 }
 
-// single-block exclusive scan of the B strata counts -> offsets[B+1]
-__global__ void __launch_bounds__(1024) strata_scan_kernel(StrataArgs a) {
+// exclusive scan of the B strata counts -> offsets[B+1]: chunk totals, single-block scan of the totals,
+// per-chunk rescan (B <= 2^24 -> <= 4096 chunks of 4096 counts)
+#define SS_CHUNK 4096
+__global__ void __launch_bounds__(1024) strata_chunk_sum_kernel(StrataArgs a, uint32_t* chunk_tot) {
     if (a.ctl && (a.ctl->done || !a.ctl->resample)) return;
     __shared__ uint32_t wsum[32];
-    __shared__ uint32_t carry_s;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) carry_s = 0;
+    const int base = blockIdx.x * SS_CHUNK;
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const int i = base + k * 1024 + threadIdx.x; if (i < a.B) s += a.hist[i]; }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(MB_FULL, s, o);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = s;
     __syncthreads();
-    for (int base = 0; base < a.B; base += 1024) {
-        const int i = base + threadIdx.x;
+    if (threadIdx.x < 32) {
+        uint32_t w = wsum[threadIdx.x];
+        for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(MB_FULL, w, o);
+        if (threadIdx.x == 0) chunk_tot[blockIdx.x] = w;
+    }
+}
+
+__global__ void __launch_bounds__(1024) strata_chunk_scan_kernel(StrataArgs a, uint32_t* chunk_tot, int nchunks) {
+    if (a.ctl && (a.ctl->done || !a.ctl->resample)) return;
+    // every block scans the (<= 4096) chunk totals up to its own chunk in shared memory, then its chunk
+    __shared__ uint32_t wsum[32];
+    __shared__ uint32_t base_s;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t pre = 0;
+    for (int i = threadIdx.x; i < (int)blockIdx.x; i += 1024) pre += chunk_tot[i];
+    for (int o = 16; o > 0; o >>= 1) pre += __shfl_xor_sync(MB_FULL, pre, o);
+    if (lane == 0) wsum[warp] = pre;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        uint32_t w = wsum[threadIdx.x];
+        for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(MB_FULL, w, o);
+        if (threadIdx.x == 0) base_s = w;
+    }
+    __syncthreads();
+    uint32_t carry = base_s;
+    const int base = blockIdx.x * SS_CHUNK;
+    for (int k = 0; k < 4; ++k) {
+        const int i = base + k * 1024 + threadIdx.x;
         const uint32_t v = (i < a.B) ? a.hist[i] : 0u;
         uint32_t x = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(MB_FULL, x, o); if (lane >= o) x += t; }
+        __syncthreads();
         if (lane == 31) wsum[warp] = x;
         __syncthreads();
         if (warp == 0) {
@@ -390,14 +422,11 @@ __global__ void __launch_bounds__(1024) strata_scan_kernel(StrataArgs a) {
             wsum[lane] = w;
         }
         __syncthreads();
-        const uint32_t carry = carry_s;
         const uint32_t incl = x + (warp ? wsum[warp - 1] : 0u) + carry;
         if (i < a.B) a.offsets[i] = incl - v;
-        __syncthreads();
-        if (threadIdx.x == 1023) carry_s = incl;
-        __syncthreads();
+        carry += wsum[31];
+        if (i == a.B - 1) a.offsets[a.B] = incl;
     }
-    if (threadIdx.x == 0) a.offsets[a.B] = carry_s;
 }
 
 struct SortedAncArgs {
@@ -553,7 +582,10 @@ extern "C" int mb_ancestors_sorted(mb_ctx* ctx, const double* cdf, int64_t n, co
     a.n_total_out = n_total_out; a.anc = anc; a.ctl = ctl;
     if (a.stratified) {
         StrataArgs sa{const_cast<uint32_t*>(hist), offsets, B, n_out, gid0, seed, step, ctl};
-        strata_scan_kernel<<<1, 1024, 0, mb_s(stream)>>>(sa);
+        const int nchunks = (B + SS_CHUNK - 1) / SS_CHUNK;
+        uint32_t* chunk_tot = reinterpret_cast<uint32_t*>((char*)ctx->scratch + (3u << 20));    // <= 16 KiB of the scratch
+        strata_chunk_sum_kernel<<<nchunks, 1024, 0, mb_s(stream)>>>(sa, chunk_tot);
+        strata_chunk_scan_kernel<<<nchunks, 1024, 0, mb_s(stream)>>>(sa, chunk_tot, nchunks);
         MB_CHECK_LAUNCH();
     }
     int64_t grid = (n_out + ANC_BLOCK_OUT - 1) / ANC_BLOCK_OUT;

@@ -315,6 +315,7 @@ extern "C" int mb_svgd_phi(mb_ctx* ctx, const float* X, const float* G, int n, i
                            float* phi, int variant, mb_stream_t stream) {
     MB_REQUIRE(ctx && X && G && bandwidth && phi && n > 0 && d > 0, "mb_svgd_phi: bad arguments");
     if (variant == 0) return svgd_dispatch(ctx, 0, X, G, n, d, bandwidth, phi, mb_s(stream));
+    if (variant == 1) return mb_svgd_phi_tc(ctx, X, G, n, d, bandwidth, phi, mb_s(stream));
     mb_set_error("mb_svgd_phi: variant %d not built", variant);
     return MB_ERR_UNSUPPORTED;
 }

@@ -1,0 +1,371 @@
+// svgd_tc.cu -- K8 on the 5th-generation tensor cores: the SVGD interaction
+//     phi = [ -K G + (X o rowsum(K) - K X)/h^2 ] / n,   K_ij = exp(-|x_i - x_j|^2 / (2 h^2))      (transport/svgd.py:18-32)
+// as a FlashAttention-shaped tcgen05 pipeline (Q = K = X, V = [G, X, 1], un-normalised exp):
+//
+//   MMA1 (tcgen05.mma kind::f16, bf16 x bf16 -> fp32 in TMEM):  S = A_i B_j^T = -1/2 |x_i - x_j|^2
+//        with the squared norms folded into the K dimension:  A_i = [x_i, 1, 1, s_i^hi, s_i^lo],
+//        B_j = [x_j, s_j^hi, s_j^lo, 1, 1],  s = -1/2 |x|^2 split in two bf16 terms (16-bit mantissa);
+//   softmax warps (tcgen05.ld):  P = exp2(S * log2(e)/h^2)  -> bf16 -> shared memory (128B-swizzled, K-major);
+//   MMA2:  O += P V_j   (O stays in TMEM for the whole j loop; V^T tiles K-major);
+//   epilogue (tcgen05.ld):  phi_i = ( -O_G + (x_i O_1 - O_X)/h^2 ) / n.
+//
+// Operands are prepared once per iteration by svgd_tc_prep_kernel as per-tile blobs already in the
+// UMMA canonical SWIZZLE_128B K-major layout, so the producer warp moves them with plain 1-D TMA bulk
+// copies (cp.async.bulk + mbarrier complete_tx), 3 stages deep.  X is centred (distances are translation
+// invariant) before rounding to bf16 ("SVGD numerics").  The n x n matrix never exists.
+//
+// Warp roles (192 threads, 1 CTA/SM, one CTA per 128-row i-tile): warp 0 = TMA producer, warp 1 = MMA issuer
+// (one elected lane) + TMEM allocator, warps 2-5 = softmax / epilogue (one TMEM lane = one row each).
+#include <cuda_bf16.h>
+#include "common.cuh"
+
+#define TC_BM 128
+#define TC_BN 128
+#define TC_K 64
+#define TC_STAGES 3
+#define TC_THREADS 192
+#define TC_TILE_X_BYTES (TC_BM * TC_K * 2)          // 16384
+#define TC_P_BYTES (TC_BM * TC_BN * 2)              // 32768
+
+// ---- PTX helpers --------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T, bf16 inputs, fp32 accumulate
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc),
+        "r"(acc) : "memory");
+}
+// shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart (sm_100 descriptor version 1)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+    const uint32_t lo = ((saddr & 0x3FFFFu) >> 4) | (1u << 16);               // start address, LBO = 16 B (unused)
+    const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);               // SBO = 1024 B, version 1, SWIZZLE_128B
+    return (uint64_t)lo | ((uint64_t)hi << 32);
+}
+__device__ __forceinline__ uint32_t umma_idesc_bf16(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+#define TMEM_LD16(taddr, v)                                                                                        \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];" \
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),     \
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]) \
+                 : "r"(taddr))
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float ex2f(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// byte offset of element (row r, k) inside a K-major SWIZZLE_128B panel of 64 bf16 per row
+__host__ __device__ __forceinline__ uint32_t sw128_off(int r, int k) {
+    return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((((k >> 3) ^ (r & 7)) & 7) << 4) + (k & 7) * 2);
+}
+
+// ---- operand preparation ------------------------------------------------------------------------
+__global__ void svgd_tc_colmean_kernel(const float* __restrict__ X, int n, int d, float* mean) {
+    __shared__ double red[8];
+    const int c = blockIdx.x;
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s += (double)X[(int64_t)i * d + c];
+    s = block_sum_d(s, red);
+    if (threadIdx.x == 0) mean[c] = (float)(s / (double)n);
+}
+
+struct TcPrepArgs {
+    const float* X; const float* G; const float* mean; int n, d, n_pad, NV;
+    uint8_t* XA; uint8_t* XB; uint8_t* VT; float* xc;       // xc: centred bf16-rounded x as fp32 (n_pad x d) for the epilogue
+};
+
+// one thread per (row, 16-byte chunk of 8 k's) of the A/B tiles; the same grid then fills the V^T tiles
+__global__ void __launch_bounds__(256) svgd_tc_prep_kernel(TcPrepArgs a) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t n_ab = (int64_t)a.n_pad * 8;
+    if (tid < n_ab) {
+        const int row = (int)(tid >> 3), ch = (int)(tid & 7);
+        const int tile = row / TC_BM, r = row % TC_BM;
+        const bool valid = row < a.n;
+        // -1/2 |x|^2 from the bf16-rounded centred coordinates (so that D_ii = 0 up to the hi/lo split)
+        float sq = 0.f;
+        if (valid)
+            for (int k = 0; k < a.d; ++k) {
+                const float v = __bfloat162float(__float2bfloat16_rn(a.X[(int64_t)row * a.d + k] - a.mean[k]));
+                sq = fmaf(v, v, sq);
+            }
+        const float s = valid ? -0.5f * sq : -1.0e30f;                 // padded rows: exp2(-huge) = 0
+        const __nv_bfloat16 shi = __float2bfloat16_rn(s);
+        const __nv_bfloat16 slo = __float2bfloat16_rn(s - __bfloat162float(shi));
+        __nv_bfloat16 va[8], vb[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int k = ch * 8 + e;
+            __nv_bfloat16 x = __float2bfloat16_rn(0.f), xa = x, xb = x;
+            if (k < a.d) {
+                if (valid) x = __float2bfloat16_rn(a.X[(int64_t)row * a.d + k] - a.mean[k]);
+                xa = x; xb = x;
+                if (ch * 8 + e < a.d) a.xc[(int64_t)row * a.d + k] = __bfloat162float(x);
+            } else if (k == a.d)     { xa = __float2bfloat16_rn(1.f); xb = shi; }
+            else if (k == a.d + 1)   { xa = __float2bfloat16_rn(1.f); xb = slo; }
+            else if (k == a.d + 2)   { xa = valid ? shi : __float2bfloat16_rn(0.f); xb = __float2bfloat16_rn(1.f); }
+            else if (k == a.d + 3)   { xa = valid ? slo : __float2bfloat16_rn(0.f); xb = __float2bfloat16_rn(1.f); }
+            va[e] = xa; vb[e] = xb;
+        }
+        const uint32_t off = sw128_off(r, ch * 8);
+        *reinterpret_cast<uint4*>(a.XA + (int64_t)tile * TC_TILE_X_BYTES + off) = *reinterpret_cast<uint4*>(va);
+        *reinterpret_cast<uint4*>(a.XB + (int64_t)tile * TC_TILE_X_BYTES + off) = *reinterpret_cast<uint4*>(vb);
+    }
+    // V^T tiles: rows c in [0, NV), K = j within the tile (2 panels of 64)
+    const int64_t n_vt = (int64_t)(a.n_pad / TC_BN) * a.NV * 16;
+    if (tid < n_vt) {
+        const int q = (int)(tid & 15);                               // 16-byte chunk along j
+        const int c = (int)((tid >> 4) % a.NV);
+        const int tile = (int)((tid >> 4) / a.NV);
+        __nv_bfloat16 v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int j = tile * TC_BN + q * 8 + e;
+            float f = 0.f;
+            if (j < a.n) {
+                if (c < a.d) f = a.G[(int64_t)j * a.d + c];
+                else if (c < 2 * a.d) f = a.X[(int64_t)j * a.d + (c - a.d)] - a.mean[c - a.d];
+                else if (c == 2 * a.d) f = 1.f;
+            }
+            v[e] = __float2bfloat16_rn(f);
+        }
+        const int panel = q >> 3;
+        const uint32_t off = (uint32_t)panel * (uint32_t)(a.NV * 128) + sw128_off(c, (q & 7) * 8);
+        *reinterpret_cast<uint4*>(a.VT + (int64_t)tile * (a.NV * 256) + off) = *reinterpret_cast<uint4*>(v);
+    }
+}
+
+// ---- main kernel --------------------------------------------------------------------------------
+struct TcArgs {
+    const uint8_t* XA; const uint8_t* XB; const uint8_t* VT; const float* xc;
+    const float* bandwidth; float* phi;
+    int n, d, n_pad, NV;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1) svgd_phi_tc_kernel(TcArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t vt_bytes = (uint32_t)a.NV * 256u;
+    const uint32_t stage_bytes = TC_TILE_X_BYTES + vt_bytes;
+    uint8_t* sXA = smem;
+    uint8_t* sStage = sXA + TC_TILE_X_BYTES;
+    uint8_t* sP = sStage + TC_STAGES * stage_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + TC_P_BYTES);
+    uint64_t* full = bars;                    // [TC_STAGES]
+    uint64_t* empty = bars + TC_STAGES;       // [TC_STAGES]
+    uint64_t* s_full = bars + 2 * TC_STAGES;  // [2]
+    uint64_t* s_empty = s_full + 2;           // [2]
+    uint64_t* p_full = s_empty + 2;
+    uint64_t* p_empty = p_full + 1;
+    uint64_t* o_full = p_empty + 1;
+    uint64_t* xa_full = o_full + 1;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(xa_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int T = a.n_pad / TC_BN;
+    const int itile = blockIdx.x;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(s_full + b, 1); mbar_init(s_empty + b, 128); }
+        mbar_init(p_full, 128); mbar_init(p_empty, 1); mbar_init(o_full, 1); mbar_init(xa_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {                                                   // TMEM: 512 columns (S x2, O)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(512u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_ptr;
+    const uint32_t tmem_S = tmem, tmem_O = tmem + 256u;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            mbar_expect_tx(xa_full, TC_TILE_X_BYTES);
+            bulk_g2s(sXA, a.XA + (int64_t)itile * TC_TILE_X_BYTES, TC_TILE_X_BYTES, xa_full);
+            for (int t = 0; t < T; ++t) {
+                const int st = t % TC_STAGES, k = t / TC_STAGES;
+                mbar_wait(empty + st, (uint32_t)((k & 1) ^ 1));
+                mbar_expect_tx(full + st, stage_bytes);
+                uint8_t* dst = sStage + (size_t)st * stage_bytes;
+                bulk_g2s(dst, a.XB + (int64_t)t * TC_TILE_X_BYTES, TC_TILE_X_BYTES, full + st);
+                bulk_g2s(dst + TC_TILE_X_BYTES, a.VT + (int64_t)t * vt_bytes, vt_bytes, full + st);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc1 = umma_idesc_bf16(TC_BM, TC_BN), idesc2 = umma_idesc_bf16(TC_BM, a.NV);
+            const uint32_t aXA = smem_u32(sXA), aP = smem_u32(sP);
+            auto mma1 = [&](int t) {
+                const int st = t % TC_STAGES;
+                const uint32_t bXB = smem_u32(sStage + (size_t)st * stage_bytes);
+                const uint32_t dS = tmem_S + (uint32_t)(t & 1) * TC_BN;
+#pragma unroll
+                for (int ks = 0; ks < TC_K / 16; ++ks)
+                    tc_mma_bf16(dS, umma_desc(aXA + ks * 32), umma_desc(bXB + ks * 32), idesc1, ks > 0 ? 1u : 0u);
+                tc_commit(s_full + (t & 1));
+            };
+            mbar_wait(xa_full, 0);
+            mbar_wait(full + 0, 0);
+            tc_fence_after();
+            mma1(0);
+            for (int t = 0; t < T; ++t) {
+                if (t + 1 < T) {
+                    const int t1 = t + 1, st1 = t1 % TC_STAGES;
+                    mbar_wait(full + st1, (uint32_t)((t1 / TC_STAGES) & 1));
+                    if (t1 >= 2) mbar_wait(s_empty + (t1 & 1), (uint32_t)(((t1 >> 1) - 1) & 1));
+                    tc_fence_after();
+                    mma1(t1);
+                }
+                mbar_wait(p_full, (uint32_t)(t & 1));
+                tc_fence_after();
+                const int st = t % TC_STAGES;
+                const uint32_t bVT = smem_u32(sStage + (size_t)st * stage_bytes + TC_TILE_X_BYTES);
+#pragma unroll
+                for (int ks = 0; ks < TC_BN / 16; ++ks) {
+                    const uint32_t pa = aP + (uint32_t)(ks >> 2) * (TC_BM * 128) + (uint32_t)(ks & 3) * 32;
+                    const uint32_t pb = bVT + (uint32_t)(ks >> 2) * (uint32_t)(a.NV * 128) + (uint32_t)(ks & 3) * 32;
+                    tc_mma_bf16(tmem_O, umma_desc(pa), umma_desc(pb), idesc2, (t > 0 || ks > 0) ? 1u : 0u);
+                }
+                tc_commit(empty + st);                                 // stage smem free once MMA2(t) has read it
+                tc_commit(p_empty);                                    // P tile free
+            }
+            tc_commit(o_full);
+        }
+    } else {
+        // ===================== softmax + epilogue (warps 2..5) =====================
+        const int wq = warp & 3;                                       // TMEM lane quarter this warp may access
+        const int row = wq * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
+        const float h = a.bandwidth[0];
+        const float cprime = 1.4426950408889634f / (h * h);            // exp(-D^2/(2h^2)) = exp2(S * log2e/h^2), S = -D^2/2
+        for (int t = 0; t < T; ++t) {
+            const int b = t & 1;
+            mbar_wait(s_full + b, (uint32_t)((t >> 1) & 1));
+            tc_fence_after();
+            uint32_t packed[TC_BN / 2];
+#pragma unroll
+            for (int c = 0; c < TC_BN / 16; ++c) {
+                uint32_t v[16];
+                TMEM_LD16(tmem_S + lane_addr + (uint32_t)(b * TC_BN + c * 16), v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int e = 0; e < 16; e += 2) {
+                    const float p0 = ex2f(__uint_as_float(v[e]) * cprime);
+                    const float p1 = ex2f(__uint_as_float(v[e + 1]) * cprime);
+                    const __nv_bfloat162 pk = __floats2bfloat162_rn(p0, p1);
+                    packed[c * 8 + (e >> 1)] = *reinterpret_cast<const uint32_t*>(&pk);
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(s_empty + b);                                  // S[b] may be overwritten by MMA1(t+2)
+            if (t >= 1) mbar_wait(p_empty, (uint32_t)((t - 1) & 1));   // MMA2(t-1) has consumed the P tile
+#pragma unroll
+            for (int cc = 0; cc < TC_BN / 8; ++cc) {                   // 16 chunks of 8 bf16 (16 B)
+                const uint32_t off = (uint32_t)(cc >> 3) * (TC_BM * 128) + sw128_off(row, (cc & 7) * 8);
+                *reinterpret_cast<uint4*>(sP + off) =
+                    make_uint4(packed[cc * 4], packed[cc * 4 + 1], packed[cc * 4 + 2], packed[cc * 4 + 3]);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to UMMA
+            mbar_arrive(p_full);
+        }
+        // ---- epilogue: phi_i = ( -O_G + (x_i O_1 - O_X)/h^2 ) / n
+        mbar_wait(o_full, 0);
+        tc_fence_after();
+        float o[128];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            if (c * 16 < a.NV) {
+                uint32_t v[16];
+                TMEM_LD16(tmem_O + lane_addr + (uint32_t)(c * 16), v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int e = 0; e < 16; ++e) o[c * 16 + e] = __uint_as_float(v[e]);
+            }
+        }
+        const int gi = itile * TC_BM + row;
+        if (gi < a.n) {
+            const float invh2 = 1.f / (h * h), invn = 1.f / (float)a.n;
+            const float o1 = o[2 * a.d];
+            for (int k = 0; k < a.d; ++k) {
+                const float xik = a.xc[(int64_t)gi * a.d + k];
+                a.phi[(int64_t)gi * a.d + k] = (-o[k] + (xik * o1 - o[a.d + k]) * invh2) * invn;
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u));
+    }
+}
+
+// ---- host ---------------------------------------------------------------------------------------
+int mb_svgd_phi_tc(mb_ctx* ctx, const float* X, const float* G, int n, int d, const float* bandwidth, float* phi,
+                   cudaStream_t st) {
+    MB_REQUIRE(d >= 1 && d + 4 <= TC_K, "svgd tcgen05 variant needs d <= 60");
+    const int NV = ((2 * d + 1 + 15) / 16) * 16;
+    MB_REQUIRE(NV <= 128, "svgd tcgen05 variant: 2d+1 must be <= 128");
+    const int n_pad = ((n + TC_BM - 1) / TC_BM) * TC_BM;
+    const int tiles = n_pad / TC_BM;
+    const size_t bx = (size_t)tiles * TC_TILE_X_BYTES, bv = (size_t)tiles * NV * 256;
+    const size_t need = 256 + 2 * bx + bv + (size_t)n_pad * d * 4 + 4096;
+    if (mb_ensure_scratch(ctx, (4u << 20) + need) != MB_OK) return MB_ERR_CUDA;
+    uint8_t* base = (uint8_t*)ctx->scratch + (4u << 20);              // [0, 4 MiB) is used by the other kernels
+    base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(base) + 255) & ~(uintptr_t)255);
+    float* mean = reinterpret_cast<float*>(base);
+    uint8_t* XA = base + 256;
+    uint8_t* XB = XA + bx;
+    uint8_t* VT = XB + bx;
+    float* xc = reinterpret_cast<float*>(VT + bv);
+    svgd_tc_colmean_kernel<<<d, 256, 0, st>>>(X, n, d, mean);
+    TcPrepArgs p{X, G, mean, n, d, n_pad, NV, XA, XB, VT, xc};
+    const int64_t work = max((int64_t)n_pad * 8, (int64_t)tiles * NV * 16);
+    svgd_tc_prep_kernel<<<(unsigned)((work + 255) / 256), 256, 0, st>>>(p);
+    MB_CHECK_LAUNCH();
+    const size_t smem = 1024 + TC_TILE_X_BYTES + (size_t)TC_STAGES * (TC_TILE_X_BYTES + NV * 256) + TC_P_BYTES + 256;
+    MB_CUDA(cudaFuncSetAttribute(svgd_phi_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TcArgs a{XA, XB, VT, xc, bandwidth, phi, n, d, n_pad, NV};
+    svgd_phi_tc_kernel<<<tiles, TC_THREADS, smem, st>>>(a);
+    MB_CHECK_LAUNCH();
+    return MB_OK;
+}
