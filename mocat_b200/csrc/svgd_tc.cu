@@ -5,8 +5,8 @@
 //   MMA1 (tcgen05.mma kind::f16, bf16 x bf16 -> fp32 in TMEM):  S = A_i B_j^T = -1/2 |x_i - x_j|^2
 //        with the squared norms folded into the K dimension:  A_i = [x_i, 1, 1, s_i^hi, s_i^lo],
 //        B_j = [x_j, s_j^hi, s_j^lo, 1, 1],  s = -1/2 |x|^2 split in two bf16 terms (16-bit mantissa);
-//   softmax warps (tcgen05.ld):  P = exp2(S * log2(e)/h^2)  -> bf16 -> shared memory (128B-swizzled, K-major);
-//   MMA2:  O += P V_j   (O stays in TMEM for the whole j loop; V^T tiles K-major);
+//   softmax warps (tcgen05.ld):  P = exp2(S * log2(e)/h^2)  -> bf16 -> back into TMEM (tcgen05.st), never shared memory;
+//   MMA2:  O += P V_j   (A operand = P from TMEM, B = V^T tile K-major from smem; O stays in TMEM for the j loop);
 //   epilogue (tcgen05.ld):  phi_i = ( -O_G + (x_i O_1 - O_X)/h^2 ) / n.
 //
 // Operands are prepared once per iteration by svgd_tc_prep_kernel as per-tile blobs already in the
@@ -15,15 +15,19 @@
 // invariant) before rounding to bf16 ("SVGD numerics").  The n x n matrix never exists.
 //
 // Warp roles (192 threads, 1 CTA/SM, one CTA per 128-row i-tile): warp 0 = TMA producer, warp 1 = MMA issuer
-// (one elected lane) + TMEM allocator, warps 2-5 = softmax / epilogue (one TMEM lane = one row each).
+// (one elected lane) + TMEM allocator, warps 2-9 = softmax / epilogue: two warpgroups, each thread owns one row
+// (TMEM lane) and one 64-column half of every S tile, so every SM sub-partition has two warps to overlap the
+// MUFU.EX2 issue interval of one with the FMUL / pack / store instructions of the other.
 #include <cuda_bf16.h>
 #include "common.cuh"
 
 #define TC_BM 128
 #define TC_BN 128
 #define TC_K 64
-#define TC_STAGES 3
-#define TC_THREADS 192
+#define TC_STAGES 4
+#define TC_THREADS 576                               // 2 control warps + 16 softmax warps (4 per SM sub-partition)
+#define TC_SM_THREADS 512
+#define TC_SPLIT 4                                   // j range split: tiles*4 CTAs on 148 SMs -> < 2 % wave tail
 #define TC_TILE_X_BYTES (TC_BM * TC_K * 2)          // 16384
 #define TC_P_BYTES (TC_BM * TC_BN * 2)              // 32768
 
@@ -81,12 +85,53 @@ __device__ __forceinline__ uint32_t umma_idesc_bf16(int M, int N) {
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),     \
                    "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]) \
                  : "r"(taddr))
+#define TMEM_LD32(taddr, v)                                                                                        \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"    \
+                 "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"                            \
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),     \
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), \
+                   "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), \
+                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]) \
+                 : "r"(taddr))
+#define TMEM_ST32(taddr, v)                                                                                        \
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16," \
+                 "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"                                   \
+                 :: "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), \
+                   "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),       \
+                   "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),     \
+                   "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31]) : "memory")
+#define TMEM_ST16(taddr, v)                                                                                        \
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" \
+                 :: "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), \
+                   "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory")
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] * B[smem desc]^T : the P operand never touches shared memory
+__device__ __forceinline__ void tc_mma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc),
+        "r"(acc) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float ex2f(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+
+// exp2 on the FMA/ALU pipes (Cody-Waite split + degree-3 minimax on [-0.5, 0.5], max rel. error 7.5e-5, far below
+// the bf16 rounding of P): a fraction of the exponentials is taken off the MUFU pipe, which otherwise paces the
+// whole pipeline (n^2 = 1.07e9 exps per iteration at 16 lanes/clk/SM).
+__device__ __forceinline__ float ex2_poly(float x) {
+    x = fmaxf(x, -125.f);
+    const float xi = x + 12582912.f;                   // 1.5 * 2^23: integer part lands in the low mantissa bits
+    const float f = x - (xi - 12582912.f);
+    const float p = fmaf(fmaf(fmaf(0.05517167f, f, 0.24261113f), f, 0.69326097f), f, 0.99992806f);
+    return __int_as_float(__float_as_int(p) + (__float_as_int(xi) << 23));
+}
+#define TC_POLY_MASK 0x7fffffff                        // measured: offloading exps to the FMA pipe is SLOWER here (issue-bound,
+                                                       // not MUFU-bound: 0.559 vs 0.514 ms at 25 %), so it is disabled
 
 // byte offset of element (row r, k) inside a K-major SWIZZLE_128B panel of 64 bf16 per row
 __host__ __device__ __forceinline__ uint32_t sw128_off(int r, int k) {
@@ -104,7 +149,7 @@ __global__ void svgd_tc_colmean_kernel(const float* __restrict__ X, int n, int d
 }
 
 struct TcPrepArgs {
-    const float* X; const float* G; const float* mean; int n, d, n_pad, NV;
+    const float* X; const float* G; const float* mean; const float* bandwidth; int n, d, n_pad, NV;
     uint8_t* XA; uint8_t* XB; uint8_t* VT; float* xc;       // xc: centred bf16-rounded x as fp32 (n_pad x d) for the epilogue
 };
 
@@ -116,11 +161,14 @@ __global__ void __launch_bounds__(256) svgd_tc_prep_kernel(TcPrepArgs a) {
         const int row = (int)(tid >> 3), ch = (int)(tid & 7);
         const int tile = row / TC_BM, r = row % TC_BM;
         const bool valid = row < a.n;
-        // -1/2 |x|^2 from the bf16-rounded centred coordinates (so that D_ii = 0 up to the hi/lo split)
+        // MMA1 operands are the centred coordinates scaled by sc = sqrt(log2 e)/h, so that S = A.B^T is directly the
+        // exp2 argument  -|x_i - x_j|^2 log2(e) / (2 h^2)  and the softmax warps need no multiply.
+        const float sc = sqrtf(1.4426950408889634f) / a.bandwidth[0];
+        // -1/2 |x|^2 from the bf16-rounded scaled coordinates (so that D_ii = 0 up to the hi/lo split)
         float sq = 0.f;
         if (valid)
             for (int k = 0; k < a.d; ++k) {
-                const float v = __bfloat162float(__float2bfloat16_rn(a.X[(int64_t)row * a.d + k] - a.mean[k]));
+                const float v = __bfloat162float(__float2bfloat16_rn((a.X[(int64_t)row * a.d + k] - a.mean[k]) * sc));
                 sq = fmaf(v, v, sq);
             }
         const float s = valid ? -0.5f * sq : -1.0e30f;                 // padded rows: exp2(-huge) = 0
@@ -132,9 +180,10 @@ __global__ void __launch_bounds__(256) svgd_tc_prep_kernel(TcPrepArgs a) {
             const int k = ch * 8 + e;
             __nv_bfloat16 x = __float2bfloat16_rn(0.f), xa = x, xb = x;
             if (k < a.d) {
-                if (valid) x = __float2bfloat16_rn(a.X[(int64_t)row * a.d + k] - a.mean[k]);
+                const float xc = valid ? a.X[(int64_t)row * a.d + k] - a.mean[k] : 0.f;
+                x = __float2bfloat16_rn(xc * sc);
                 xa = x; xb = x;
-                if (ch * 8 + e < a.d) a.xc[(int64_t)row * a.d + k] = __bfloat162float(x);
+                a.xc[(int64_t)row * a.d + k] = __bfloat162float(__float2bfloat16_rn(xc));   // as rounded in the V tiles
             } else if (k == a.d)     { xa = __float2bfloat16_rn(1.f); xb = shi; }
             else if (k == a.d + 1)   { xa = __float2bfloat16_rn(1.f); xb = slo; }
             else if (k == a.d + 2)   { xa = valid ? shi : __float2bfloat16_rn(0.f); xb = __float2bfloat16_rn(1.f); }
@@ -174,6 +223,7 @@ struct TcArgs {
     const uint8_t* XA; const uint8_t* XB; const uint8_t* VT; const float* xc;
     const float* bandwidth; float* phi;
     int n, d, n_pad, NV;
+    float* opart;            // [TC_SPLIT][n_pad][NV] partial O
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1) svgd_phi_tc_kernel(TcArgs a) {
@@ -183,8 +233,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) svgd_phi_tc_kernel(TcArgs a) {
     const uint32_t stage_bytes = TC_TILE_X_BYTES + vt_bytes;
     uint8_t* sXA = smem;
     uint8_t* sStage = sXA + TC_TILE_X_BYTES;
-    uint8_t* sP = sStage + TC_STAGES * stage_bytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + TC_P_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + TC_STAGES * stage_bytes);
     uint64_t* full = bars;                    // [TC_STAGES]
     uint64_t* empty = bars + TC_STAGES;       // [TC_STAGES]
     uint64_t* s_full = bars + 2 * TC_STAGES;  // [2]
@@ -196,13 +245,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) svgd_phi_tc_kernel(TcArgs a) {
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(xa_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int T = a.n_pad / TC_BN;
-    const int itile = blockIdx.x;
+    const int T_all = a.n_pad / TC_BN;
+    const int itile = blockIdx.x / TC_SPLIT, part = blockIdx.x % TC_SPLIT;
+    const int t_begin = (int)(((int64_t)T_all * part) / TC_SPLIT), t_end = (int)(((int64_t)T_all * (part + 1)) / TC_SPLIT);
+    const int T = t_end - t_begin;                                     // this CTA's j tiles: [t_begin, t_end)
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(s_full + b, 1); mbar_init(s_empty + b, 128); }
-        mbar_init(p_full, 128); mbar_init(p_empty, 1); mbar_init(o_full, 1); mbar_init(xa_full, 1);
+        for (int b = 0; b < 2; ++b) { mbar_init(s_full + b, 1); mbar_init(s_empty + b, TC_SM_THREADS); }
+        mbar_init(p_full, TC_SM_THREADS); mbar_init(p_empty, 1); mbar_init(o_full, 1); mbar_init(xa_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {                                                   // TMEM: 512 columns (S x2, O)
@@ -213,7 +264,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) svgd_phi_tc_kernel(TcArgs a) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_ptr;
-    const uint32_t tmem_S = tmem, tmem_O = tmem + 256u;
+    const uint32_t tmem_S = tmem, tmem_O = tmem + 256u, tmem_P = tmem + 384u;   // P: 128 x 128 bf16 = 64 columns
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -225,15 +276,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) svgd_phi_tc_kernel(TcArgs a) {
                 mbar_wait(empty + st, (uint32_t)((k & 1) ^ 1));
                 mbar_expect_tx(full + st, stage_bytes);
                 uint8_t* dst = sStage + (size_t)st * stage_bytes;
-                bulk_g2s(dst, a.XB + (int64_t)t * TC_TILE_X_BYTES, TC_TILE_X_BYTES, full + st);
-                bulk_g2s(dst + TC_TILE_X_BYTES, a.VT + (int64_t)t * vt_bytes, vt_bytes, full + st);
+                bulk_g2s(dst, a.XB + (int64_t)(t_begin + t) * TC_TILE_X_BYTES, TC_TILE_X_BYTES, full + st);
+                bulk_g2s(dst + TC_TILE_X_BYTES, a.VT + (int64_t)(t_begin + t) * vt_bytes, vt_bytes, full + st);
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
             const uint32_t idesc1 = umma_idesc_bf16(TC_BM, TC_BN), idesc2 = umma_idesc_bf16(TC_BM, a.NV);
-            const uint32_t aXA = smem_u32(sXA), aP = smem_u32(sP);
+            const uint32_t aXA = smem_u32(sXA);
             auto mma1 = [&](int t) {
                 const int st = t % TC_STAGES;
                 const uint32_t bXB = smem_u32(sStage + (size_t)st * stage_bytes);
@@ -244,9 +295,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) svgd_phi_tc_kernel(TcArgs a) {
                 tc_commit(s_full + (t & 1));
             };
             mbar_wait(xa_full, 0);
-            mbar_wait(full + 0, 0);
-            tc_fence_after();
-            mma1(0);
+            if (T > 0) {
+                mbar_wait(full + 0, 0);
+                tc_fence_after();
+                mma1(0);
+            }
             for (int t = 0; t < T; ++t) {
                 if (t + 1 < T) {
                     const int t1 = t + 1, st1 = t1 % TC_STAGES;
@@ -260,74 +313,60 @@ __global__ void __launch_bounds__(TC_THREADS, 1) svgd_phi_tc_kernel(TcArgs a) {
                 const int st = t % TC_STAGES;
                 const uint32_t bVT = smem_u32(sStage + (size_t)st * stage_bytes + TC_TILE_X_BYTES);
 #pragma unroll
-                for (int ks = 0; ks < TC_BN / 16; ++ks) {
-                    const uint32_t pa = aP + (uint32_t)(ks >> 2) * (TC_BM * 128) + (uint32_t)(ks & 3) * 32;
+                for (int ks = 0; ks < TC_BN / 16; ++ks) {                // A = P from TMEM (8 columns per K=16 step)
                     const uint32_t pb = bVT + (uint32_t)(ks >> 2) * (uint32_t)(a.NV * 128) + (uint32_t)(ks & 3) * 32;
-                    tc_mma_bf16(tmem_O, umma_desc(pa), umma_desc(pb), idesc2, (t > 0 || ks > 0) ? 1u : 0u);
+                    tc_mma_bf16_ts(tmem_O, tmem_P + (uint32_t)ks * 8u, umma_desc(pb), idesc2, (t > 0 || ks > 0) ? 1u : 0u);
                 }
                 tc_commit(empty + st);                                 // stage smem free once MMA2(t) has read it
                 tc_commit(p_empty);                                    // P tile free
             }
-            tc_commit(o_full);
+            if (T > 0) tc_commit(o_full);
         }
     } else {
-        // ===================== softmax + epilogue (warps 2..5) =====================
+        // ===================== softmax + epilogue (warps 2..9) =====================
         const int wq = warp & 3;                                       // TMEM lane quarter this warp may access
+        const int cq = (warp - 2) >> 2;                                // which 32-column quarter of the S tile
         const int row = wq * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
-        const float h = a.bandwidth[0];
-        const float cprime = 1.4426950408889634f / (h * h);            // exp(-D^2/(2h^2)) = exp2(S * log2e/h^2), S = -D^2/2
         for (int t = 0; t < T; ++t) {
             const int b = t & 1;
             mbar_wait(s_full + b, (uint32_t)((t >> 1) & 1));
             tc_fence_after();
-            uint32_t packed[TC_BN / 2];
-#pragma unroll
-            for (int c = 0; c < TC_BN / 16; ++c) {
-                uint32_t v[16];
-                TMEM_LD16(tmem_S + lane_addr + (uint32_t)(b * TC_BN + c * 16), v);
-                tmem_ld_wait();
-#pragma unroll
-                for (int e = 0; e < 16; e += 2) {
-                    const float p0 = ex2f(__uint_as_float(v[e]) * cprime);
-                    const float p1 = ex2f(__uint_as_float(v[e + 1]) * cprime);
-                    const __nv_bfloat162 pk = __floats2bfloat162_rn(p0, p1);
-                    packed[c * 8 + (e >> 1)] = *reinterpret_cast<const uint32_t*>(&pk);
-                }
-            }
+            uint32_t packed[16], va[32];
+            TMEM_LD32(tmem_S + lane_addr + (uint32_t)(b * TC_BN + cq * 32), va);
+            tmem_ld_wait();
             tc_fence_before();
             mbar_arrive(s_empty + b);                                  // S[b] may be overwritten by MMA1(t+2)
-            if (t >= 1) mbar_wait(p_empty, (uint32_t)((t - 1) & 1));   // MMA2(t-1) has consumed the P tile
 #pragma unroll
-            for (int cc = 0; cc < TC_BN / 8; ++cc) {                   // 16 chunks of 8 bf16 (16 B)
-                const uint32_t off = (uint32_t)(cc >> 3) * (TC_BM * 128) + sw128_off(row, (cc & 7) * 8);
-                *reinterpret_cast<uint4*>(sP + off) =
-                    make_uint4(packed[cc * 4], packed[cc * 4 + 1], packed[cc * 4 + 2], packed[cc * 4 + 3]);
+            for (int e = 0; e < 32; e += 2) {
+                const __nv_bfloat162 pk = __floats2bfloat162_rn(ex2f(__uint_as_float(va[e])), ex2f(__uint_as_float(va[e + 1])));
+                packed[e >> 1] = *reinterpret_cast<const uint32_t*>(&pk);
             }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to UMMA
+            if (t >= 1) mbar_wait(p_empty, (uint32_t)((t - 1) & 1));   // MMA2(t-1) has consumed the P tile
+            tc_fence_after();
+            TMEM_ST16(tmem_P + lane_addr + (uint32_t)(cq * 16), packed);     // this row's 32 bf16 = 16 packed columns
+            tmem_st_wait();
+            tc_fence_before();
             mbar_arrive(p_full);
         }
-        // ---- epilogue: phi_i = ( -O_G + (x_i O_1 - O_X)/h^2 ) / n
-        mbar_wait(o_full, 0);
-        tc_fence_after();
-        float o[128];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            if (c * 16 < a.NV) {
-                uint32_t v[16];
-                TMEM_LD16(tmem_O + lane_addr + (uint32_t)(c * 16), v);
-                tmem_ld_wait();
-#pragma unroll
-                for (int e = 0; e < 16; ++e) o[c * 16 + e] = __uint_as_float(v[e]);
-            }
+        // ---- partial O of this j range -> workspace (summed in fixed order by svgd_tc_finish_kernel)
+        if (T > 0) {
+            mbar_wait(o_full, 0);
+            tc_fence_after();
         }
-        const int gi = itile * TC_BM + row;
-        if (gi < a.n) {
-            const float invh2 = 1.f / (h * h), invn = 1.f / (float)a.n;
-            const float o1 = o[2 * a.d];
-            for (int k = 0; k < a.d; ++k) {
-                const float xik = a.xc[(int64_t)gi * a.d + k];
-                a.phi[(int64_t)gi * a.d + k] = (-o[k] + (xik * o1 - o[a.d + k]) * invh2) * invn;
+        float* orow = a.opart + ((int64_t)part * a.n_pad + (int64_t)itile * TC_BM + row) * a.NV;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const int col = (cq * 2 + c) * 16;
+            if (col < a.NV) {
+                uint32_t v[16];
+                if (T > 0) { TMEM_LD16(tmem_O + lane_addr + (uint32_t)col, v); tmem_ld_wait(); }
+#pragma unroll
+                for (int e = 0; e < 16; e += 4)
+                    *reinterpret_cast<float4*>(orow + col + e) =
+                        T > 0 ? make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]), __uint_as_float(v[e + 2]),
+                                            __uint_as_float(v[e + 3]))
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
         tc_fence_before();
@@ -339,6 +378,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) svgd_phi_tc_kernel(TcArgs a) {
     }
 }
 
+// phi_i = ( -O_G + (x_i O_1 - O_X)/h^2 ) / n  with O = sum of the TC_SPLIT partials (fixed order: deterministic)
+__global__ void __launch_bounds__(256) svgd_tc_finish_kernel(TcArgs a) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)a.n * a.d) return;
+    const int i = (int)(idx / a.d), k = (int)(idx % a.d);
+    float og = 0.f, ox = 0.f, o1 = 0.f;
+#pragma unroll
+    for (int p = 0; p < TC_SPLIT; ++p) {
+        const float* o = a.opart + ((int64_t)p * a.n_pad + i) * a.NV;
+        og += o[k]; ox += o[a.d + k]; o1 += o[2 * a.d];
+    }
+    const float h = a.bandwidth[0];
+    const float invh2 = 1.f / (h * h), invn = 1.f / (float)a.n;
+    a.phi[idx] = (-og + (a.xc[idx] * o1 - ox) * invh2) * invn;
+}
+
 // ---- host ---------------------------------------------------------------------------------------
 int mb_svgd_phi_tc(mb_ctx* ctx, const float* X, const float* G, int n, int d, const float* bandwidth, float* phi,
                    cudaStream_t st) {
@@ -348,7 +403,8 @@ int mb_svgd_phi_tc(mb_ctx* ctx, const float* X, const float* G, int n, int d, co
     const int n_pad = ((n + TC_BM - 1) / TC_BM) * TC_BM;
     const int tiles = n_pad / TC_BM;
     const size_t bx = (size_t)tiles * TC_TILE_X_BYTES, bv = (size_t)tiles * NV * 256;
-    const size_t need = 256 + 2 * bx + bv + (size_t)n_pad * d * 4 + 4096;
+    const size_t bo = (size_t)TC_SPLIT * n_pad * NV * 4;
+    const size_t need = 256 + 2 * bx + bv + (size_t)n_pad * d * 4 + bo + 8192;
     if (mb_ensure_scratch(ctx, (4u << 20) + need) != MB_OK) return MB_ERR_CUDA;
     uint8_t* base = (uint8_t*)ctx->scratch + (4u << 20);              // [0, 4 MiB) is used by the other kernels
     base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(base) + 255) & ~(uintptr_t)255);
@@ -357,15 +413,18 @@ int mb_svgd_phi_tc(mb_ctx* ctx, const float* X, const float* G, int n, int d, co
     uint8_t* XB = XA + bx;
     uint8_t* VT = XB + bx;
     float* xc = reinterpret_cast<float*>(VT + bv);
+    float* opart = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(xc + (size_t)n_pad * d) + 255) & ~(uintptr_t)255);
     svgd_tc_colmean_kernel<<<d, 256, 0, st>>>(X, n, d, mean);
-    TcPrepArgs p{X, G, mean, n, d, n_pad, NV, XA, XB, VT, xc};
+    TcPrepArgs p{X, G, mean, bandwidth, n, d, n_pad, NV, XA, XB, VT, xc};
     const int64_t work = max((int64_t)n_pad * 8, (int64_t)tiles * NV * 16);
     svgd_tc_prep_kernel<<<(unsigned)((work + 255) / 256), 256, 0, st>>>(p);
     MB_CHECK_LAUNCH();
-    const size_t smem = 1024 + TC_TILE_X_BYTES + (size_t)TC_STAGES * (TC_TILE_X_BYTES + NV * 256) + TC_P_BYTES + 256;
+    const size_t smem = 1024 + TC_TILE_X_BYTES + (size_t)TC_STAGES * (TC_TILE_X_BYTES + NV * 256) + 256;
     MB_CUDA(cudaFuncSetAttribute(svgd_phi_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    TcArgs a{XA, XB, VT, xc, bandwidth, phi, n, d, n_pad, NV};
-    svgd_phi_tc_kernel<<<tiles, TC_THREADS, smem, st>>>(a);
+    TcArgs a{XA, XB, VT, xc, bandwidth, phi, n, d, n_pad, NV, opart};
+    svgd_phi_tc_kernel<<<tiles * TC_SPLIT, TC_THREADS, smem, st>>>(a);
+    MB_CHECK_LAUNCH();
+    svgd_tc_finish_kernel<<<(unsigned)(((int64_t)n * d + 255) / 256), 256, 0, st>>>(a);
     MB_CHECK_LAUNCH();
     return MB_OK;
 }
