@@ -2,20 +2,24 @@
 //     phi = [ -K G + (X o rowsum(K) - K X)/h^2 ] / n,   K_ij = exp(-|x_i - x_j|^2 / (2 h^2))      (transport/svgd.py:18-32)
 // as a FlashAttention-shaped tcgen05 pipeline (Q = K = X, V = [G, X, 1], un-normalised exp):
 //
-//   MMA1 (tcgen05.mma kind::f16, bf16 x bf16 -> fp32 in TMEM):  S = A_i B_j^T = -1/2 |x_i - x_j|^2
-//        with the squared norms folded into the K dimension:  A_i = [x_i, 1, 1, s_i^hi, s_i^lo],
-//        B_j = [x_j, s_j^hi, s_j^lo, 1, 1],  s = -1/2 |x|^2 split in two bf16 terms (16-bit mantissa);
-//   softmax warps (tcgen05.ld):  P = exp2(S * log2(e)/h^2)  -> bf16 -> back into TMEM (tcgen05.st), never shared memory;
-//   MMA2:  O += P V_j   (A operand = P from TMEM, B = V^T tile K-major from smem; O stays in TMEM for the j loop);
-//   epilogue (tcgen05.ld):  phi_i = ( -O_G + (x_i O_1 - O_X)/h^2 ) / n.
+//   MMA1 (tcgen05.mma kind::f16, bf16 x bf16 -> fp32 in TMEM):  S = A_i B_j^T = exp2 argument -|x_i-x_j|^2 log2e/(2h^2)
+//        coordinates centred and scaled by sc = sqrt(log2 e)/h; squared norms folded into the K dimension:
+//        A_i = [x_i, 1, 1, s_i^hi, s_i^lo, 0..],  B_j = [x_j, s_j^hi, s_j^lo, 1, 1, ..],  s = -1/2 |x|^2 split in two bf16;
+//   softmax warps (tcgen05.ld):  P = exp2(S) -> bf16 -> back into TMEM (tcgen05.st), never shared memory;
+//   MMA2:  O += P W_j  (A operand = P from TMEM, B = W^T tile from smem; O stays in TMEM for the whole j loop);
+//   finish kernel:  phi_i = ( -O_G + (x_i O_1 - O_X)/h^2 ) / n.
 //
-// Operands are prepared once per iteration by svgd_tc_prep_kernel as per-tile blobs already in the
-// UMMA canonical SWIZZLE_128B K-major layout, so the producer warp moves them with plain 1-D TMA bulk
-// copies (cp.async.bulk + mbarrier complete_tx), 3 stages deep.  X is centred (distances are translation
-// invariant) before rounding to bf16 ("SVGD numerics").  The n x n matrix never exists.
+// ONE operand tile per j-tile serves both GEMMs.  W^T[c][j] (rows c, 128 j's, SWIZZLE_128B, two 64-wide panels) holds
+//   rows 0..d-1: scaled x_j | d, d+1: s_j^hi, s_j^lo | d+2, d+3: 1 | d+4..2d+3: g_j | zero padding to NV rows.
+// MMA2 reads it as the K-major B operand (K = j).  MMA1 reads rows 0..63 of the SAME bytes as an MN-major B operand
+// (N = j contiguous, K = row): B_j above is exactly column j of those rows (the g rows meet zero columns of A).
+// This removed the separate X_j tile: the kernel is bound by L2->SM bandwidth (every CTA streams all of W^T), and
+// bytes per tile went 44 KiB -> 28 KiB.  Tiles are prepared once per iteration in the UMMA canonical layout, so the
+// producer warp moves them with plain 1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx), 4 stages deep.
+// X is centred (distances are translation invariant) before rounding to bf16 ("SVGD numerics").
 //
-// Warp roles (192 threads, 1 CTA/SM, one CTA per 128-row i-tile): warp 0 = TMA producer, warp 1 = MMA issuer
-// (one elected lane) + TMEM allocator, warps 2-9 = softmax / epilogue: two warpgroups, each thread owns one row
+// Warp roles (608 threads, 1 CTA/SM): warp 0 = TMA producer, warp 1 = MMA1 issuer + TMEM allocator, warp 2 = MMA2
+// issuer, warps 3-18 = softmax / epilogue in two ping-pong groups: each thread owns one row
 // (TMEM lane) and one 64-column half of every S tile, so every SM sub-partition has two warps to overlap the
 // MUFU.EX2 issue interval of one with the FMUL / pack / store instructions of the other.
 #include <cuda_bf16.h>
@@ -24,8 +28,8 @@
 #define TC_BM 128
 #define TC_BN 128
 #define TC_K 64
-#define TC_STAGES 4
-#define TC_THREADS 576                               // 2 control warps + 16 softmax warps (4 per SM sub-partition)
+#define TC_STAGES 6
+#define TC_THREADS 608                               // 3 control warps + 16 softmax warps (4 per SM sub-partition)
 #define TC_SM_THREADS 512
 #define TC_SPLIT 4                                   // j range split: tiles*4 CTAs on 148 SMs -> < 2 % wave tail
 #define TC_TILE_X_BYTES (TC_BM * TC_K * 2)          // 16384
@@ -77,8 +81,15 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
     const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);               // SBO = 1024 B, version 1, SWIZZLE_128B
     return (uint64_t)lo | ((uint64_t)hi << 32);
 }
-__device__ __forceinline__ uint32_t umma_idesc_bf16(int M, int N) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// same bytes viewed MN-major (N contiguous): 64-element rows repeat every `lbo` bytes along N, 8-row K groups 1024 B apart
+__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr, uint32_t lbo) {
+    const uint32_t lo = ((saddr & 0x3FFFFu) >> 4) | ((lbo >> 4) << 16);
+    const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    return (uint64_t)lo | ((uint64_t)hi << 32);
+}
+__device__ __forceinline__ uint32_t umma_idesc_bf16(int M, int N, int b_mn_major = 0) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) |
+           ((uint32_t)(M >> 4) << 24);
 }
 #define TMEM_LD16(taddr, v)                                                                                        \
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];" \
@@ -130,7 +141,10 @@ __device__ __forceinline__ float ex2_poly(float x) {
     const float p = fmaf(fmaf(fmaf(0.05517167f, f, 0.24261113f), f, 0.69326097f), f, 0.99992806f);
     return __int_as_float(__float_as_int(p) + (__float_as_int(xi) << 23));
 }
-#define TC_POLY_MASK 0x7fffffff                        // measured: offloading exps to the FMA pipe is SLOWER here (issue-bound,
+#ifndef TC_POLY_MASK
+#define TC_POLY_MASK 0x7fffffff
+#endif
+// (default: disabled)                        // measured: offloading exps to the FMA pipe is SLOWER here (issue-bound,
                                                        // not MUFU-bound: 0.559 vs 0.514 ms at 25 %), so it is disabled
 
 // byte offset of element (row r, k) inside a K-major SWIZZLE_128B panel of 64 bf16 per row
@@ -139,88 +153,91 @@ __host__ __device__ __forceinline__ uint32_t sw128_off(int r, int k) {
 }
 
 // ---- operand preparation ------------------------------------------------------------------------
-__global__ void svgd_tc_colmean_kernel(const float* __restrict__ X, int n, int d, float* mean) {
-    __shared__ double red[8];
-    const int c = blockIdx.x;
+// column means, coalesced: 64 column lanes x 4 row groups per block, fp64 partials, fixed-order final sum
+__global__ void __launch_bounds__(256) svgd_tc_colsum_kernel(const float* __restrict__ X, int n, int d, double* part) {
+    __shared__ double sm[4][64];
+    const int c = threadIdx.x & 63, rg = threadIdx.x >> 6;
     double s = 0.0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) s += (double)X[(int64_t)i * d + c];
-    s = block_sum_d(s, red);
-    if (threadIdx.x == 0) mean[c] = (float)(s / (double)n);
+    if (c < d)
+        for (int i = blockIdx.x * 4 + rg; i < n; i += gridDim.x * 4) s += (double)X[(int64_t)i * d + c];
+    sm[rg][c] = s;
+    __syncthreads();
+    if (rg == 0) part[blockIdx.x * 64 + c] = sm[0][c] + sm[1][c] + sm[2][c] + sm[3][c];
+}
+__global__ void svgd_tc_colmean_kernel(const double* part, int nblocks, int n, int d, float* mean) {
+    const int c = threadIdx.x;
+    if (c >= d) return;
+    double s = 0.0;
+    for (int b = 0; b < nblocks; ++b) s += part[b * 64 + c];
+    mean[c] = (float)(s / (double)n);
 }
 
 struct TcPrepArgs {
     const float* X; const float* G; const float* mean; const float* bandwidth; int n, d, n_pad, NV;
-    uint8_t* XA; uint8_t* XB; uint8_t* VT; float* xc;       // xc: centred bf16-rounded x as fp32 (n_pad x d) for the epilogue
+    uint8_t* XA; uint8_t* WT; float* xs; float* saux;   // xs: bf16-rounded scaled centred x as fp32 (n_pad x d); saux: (hi, lo)
 };
 
-// one thread per (row, 16-byte chunk of 8 k's) of the A/B tiles; the same grid then fills the V^T tiles
-__global__ void __launch_bounds__(256) svgd_tc_prep_kernel(TcPrepArgs a) {
+// pass 1, one thread per (row, 16-byte chunk of 8 k's): A tiles, rounded scaled coordinates, split -|x|^2/2
+__global__ void __launch_bounds__(256) svgd_tc_rows_kernel(TcPrepArgs a) {
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t n_ab = (int64_t)a.n_pad * 8;
-    if (tid < n_ab) {
-        const int row = (int)(tid >> 3), ch = (int)(tid & 7);
-        const int tile = row / TC_BM, r = row % TC_BM;
-        const bool valid = row < a.n;
-        // MMA1 operands are the centred coordinates scaled by sc = sqrt(log2 e)/h, so that S = A.B^T is directly the
-        // exp2 argument  -|x_i - x_j|^2 log2(e) / (2 h^2)  and the softmax warps need no multiply.
-        const float sc = sqrtf(1.4426950408889634f) / a.bandwidth[0];
-        // -1/2 |x|^2 from the bf16-rounded scaled coordinates (so that D_ii = 0 up to the hi/lo split)
-        float sq = 0.f;
-        if (valid)
-            for (int k = 0; k < a.d; ++k) {
-                const float v = __bfloat162float(__float2bfloat16_rn((a.X[(int64_t)row * a.d + k] - a.mean[k]) * sc));
-                sq = fmaf(v, v, sq);
-            }
-        const float s = valid ? -0.5f * sq : -1.0e30f;                 // padded rows: exp2(-huge) = 0
-        const __nv_bfloat16 shi = __float2bfloat16_rn(s);
-        const __nv_bfloat16 slo = __float2bfloat16_rn(s - __bfloat162float(shi));
-        __nv_bfloat16 va[8], vb[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const int k = ch * 8 + e;
-            __nv_bfloat16 x = __float2bfloat16_rn(0.f), xa = x, xb = x;
-            if (k < a.d) {
-                const float xc = valid ? a.X[(int64_t)row * a.d + k] - a.mean[k] : 0.f;
-                x = __float2bfloat16_rn(xc * sc);
-                xa = x; xb = x;
-                a.xc[(int64_t)row * a.d + k] = __bfloat162float(__float2bfloat16_rn(xc));   // as rounded in the V tiles
-            } else if (k == a.d)     { xa = __float2bfloat16_rn(1.f); xb = shi; }
-            else if (k == a.d + 1)   { xa = __float2bfloat16_rn(1.f); xb = slo; }
-            else if (k == a.d + 2)   { xa = valid ? shi : __float2bfloat16_rn(0.f); xb = __float2bfloat16_rn(1.f); }
-            else if (k == a.d + 3)   { xa = valid ? slo : __float2bfloat16_rn(0.f); xb = __float2bfloat16_rn(1.f); }
-            va[e] = xa; vb[e] = xb;
+    if (tid >= (int64_t)a.n_pad * 8) return;
+    const int row = (int)(tid >> 3), ch = (int)(tid & 7);
+    const int tile = row / TC_BM, r = row % TC_BM;
+    const bool valid = row < a.n;
+    const float sc = sqrtf(1.4426950408889634f) / a.bandwidth[0];
+    float sq = 0.f;                                    // from the ROUNDED coordinates, so that D_ii = 0 up to the hi/lo split
+    if (valid)
+        for (int k = 0; k < a.d; ++k) {
+            const float v = __bfloat162float(__float2bfloat16_rn((a.X[(int64_t)row * a.d + k] - a.mean[k]) * sc));
+            sq = fmaf(v, v, sq);
         }
-        const uint32_t off = sw128_off(r, ch * 8);
-        *reinterpret_cast<uint4*>(a.XA + (int64_t)tile * TC_TILE_X_BYTES + off) = *reinterpret_cast<uint4*>(va);
-        *reinterpret_cast<uint4*>(a.XB + (int64_t)tile * TC_TILE_X_BYTES + off) = *reinterpret_cast<uint4*>(vb);
-    }
-    // V^T tiles: rows c in [0, NV), K = j within the tile (2 panels of 64)
-    const int64_t n_vt = (int64_t)(a.n_pad / TC_BN) * a.NV * 16;
-    if (tid < n_vt) {
-        const int q = (int)(tid & 15);                               // 16-byte chunk along j
-        const int c = (int)((tid >> 4) % a.NV);
-        const int tile = (int)((tid >> 4) / a.NV);
-        __nv_bfloat16 v[8];
+    const float s = valid ? -0.5f * sq : -1.0e30f;     // padded rows: exp2(-huge) = 0
+    const __nv_bfloat16 shi = __float2bfloat16_rn(s);
+    const __nv_bfloat16 slo = __float2bfloat16_rn(s - __bfloat162float(shi));
+    if (ch == 0) { a.saux[2 * row] = __bfloat162float(shi); a.saux[2 * row + 1] = __bfloat162float(slo); }
+    __nv_bfloat16 va[8];
+    const __nv_bfloat16 zero = __float2bfloat16_rn(0.f), one = __float2bfloat16_rn(1.f);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const int j = tile * TC_BN + q * 8 + e;
-            float f = 0.f;
-            if (j < a.n) {
-                if (c < a.d) f = a.G[(int64_t)j * a.d + c];
-                else if (c < 2 * a.d) f = a.X[(int64_t)j * a.d + (c - a.d)] - a.mean[c - a.d];
-                else if (c == 2 * a.d) f = 1.f;
-            }
-            v[e] = __float2bfloat16_rn(f);
-        }
-        const int panel = q >> 3;
-        const uint32_t off = (uint32_t)panel * (uint32_t)(a.NV * 128) + sw128_off(c, (q & 7) * 8);
-        *reinterpret_cast<uint4*>(a.VT + (int64_t)tile * (a.NV * 256) + off) = *reinterpret_cast<uint4*>(v);
+    for (int e = 0; e < 8; ++e) {
+        const int k = ch * 8 + e;
+        __nv_bfloat16 xa = zero;
+        if (k < a.d) {
+            xa = __float2bfloat16_rn(valid ? (a.X[(int64_t)row * a.d + k] - a.mean[k]) * sc : 0.f);
+            a.xs[(int64_t)row * a.d + k] = __bfloat162float(xa);
+        } else if (k == a.d || k == a.d + 1) xa = one;
+        else if (k == a.d + 2) xa = valid ? shi : zero;
+        else if (k == a.d + 3) xa = valid ? slo : zero;
+        va[e] = xa;
     }
+    *reinterpret_cast<uint4*>(a.XA + (int64_t)tile * TC_TILE_X_BYTES + sw128_off(r, ch * 8)) = *reinterpret_cast<uint4*>(va);
+}
+
+// pass 2, one thread per (tile, row c, 16-byte chunk of 8 j's): the W^T tiles
+__global__ void __launch_bounds__(256) svgd_tc_wt_kernel(TcPrepArgs a) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (int64_t)(a.n_pad / TC_BN) * a.NV * 16) return;
+    const int q = (int)(tid & 15);
+    const int c = (int)((tid >> 4) % a.NV);
+    const int tile = (int)((tid >> 4) / a.NV);
+    __nv_bfloat16 v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int j = tile * TC_BN + q * 8 + e;          // j < n_pad always
+        float f = 0.f;
+        if (c < a.d) f = a.xs[(int64_t)j * a.d + c];
+        else if (c == a.d) f = a.saux[2 * j];
+        else if (c == a.d + 1) f = a.saux[2 * j + 1];
+        else if (c == a.d + 2 || c == a.d + 3) f = 1.f;
+        else if (c < 2 * a.d + 4) f = (j < a.n) ? a.G[(int64_t)j * a.d + (c - a.d - 4)] : 0.f;
+        v[e] = __float2bfloat16_rn(f);
+    }
+    const uint32_t off = (uint32_t)(q >> 3) * (uint32_t)(a.NV * 128) + sw128_off(c, (q & 7) * 8);
+    *reinterpret_cast<uint4*>(a.WT + (int64_t)tile * (a.NV * 256) + off) = *reinterpret_cast<uint4*>(v);
 }
 
 // ---- main kernel --------------------------------------------------------------------------------
 struct TcArgs {
-    const uint8_t* XA; const uint8_t* XB; const uint8_t* VT; const float* xc;
+    const uint8_t* XA; const uint8_t* WT; const float* xs;
     const float* bandwidth; float* phi;
     int n, d, n_pad, NV;
     float* opart;            // [TC_SPLIT][n_pad][NV] partial O
@@ -229,8 +246,7 @@ struct TcArgs {
 __global__ void __launch_bounds__(TC_THREADS, 1) svgd_phi_tc_kernel(TcArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const uint32_t vt_bytes = (uint32_t)a.NV * 256u;
-    const uint32_t stage_bytes = TC_TILE_X_BYTES + vt_bytes;
+    const uint32_t stage_bytes = (uint32_t)a.NV * 256u;               // one W^T tile
     uint8_t* sXA = smem;
     uint8_t* sStage = sXA + TC_TILE_X_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + TC_STAGES * stage_bytes);
@@ -238,9 +254,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) svgd_phi_tc_kernel(TcArgs a) {
     uint64_t* empty = bars + TC_STAGES;       // [TC_STAGES]
     uint64_t* s_full = bars + 2 * TC_STAGES;  // [2]
     uint64_t* s_empty = s_full + 2;           // [2]
-    uint64_t* p_full = s_empty + 2;
-    uint64_t* p_empty = p_full + 1;
-    uint64_t* o_full = p_empty + 1;
+    uint64_t* p_full = s_empty + 2;           // [2]
+    uint64_t* p_empty = p_full + 2;           // [2]
+    uint64_t* o_full = p_empty + 2;
     uint64_t* xa_full = o_full + 1;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(xa_full + 1);
 
@@ -251,9 +267,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) svgd_phi_tc_kernel(TcArgs a) {
     const int T = t_end - t_begin;                                     // this CTA's j tiles: [t_begin, t_end)
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(s_full + b, 1); mbar_init(s_empty + b, TC_SM_THREADS); }
-        mbar_init(p_full, TC_SM_THREADS); mbar_init(p_empty, 1); mbar_init(o_full, 1); mbar_init(xa_full, 1);
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 2); }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(s_full + b, 1); mbar_init(s_empty + b, TC_SM_THREADS / 2);
+            mbar_init(p_full + b, TC_SM_THREADS / 2); mbar_init(p_empty + b, 1);
+        }
+        mbar_init(o_full, 1); mbar_init(xa_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {                                                   // TMEM: 512 columns (S x2, O)
@@ -264,7 +283,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) svgd_phi_tc_kernel(TcArgs a) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_ptr;
-    const uint32_t tmem_S = tmem, tmem_O = tmem + 256u, tmem_P = tmem + 384u;   // P: 128 x 128 bf16 = 64 columns
+    const uint32_t tmem_S = tmem, tmem_O = tmem + 256u, tmem_P = tmem + 384u;   // P[2]: 128 x 128 bf16 = 64 columns each
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -276,79 +295,90 @@ __global__ void __launch_bounds__(TC_THREADS, 1) svgd_phi_tc_kernel(TcArgs a) {
                 mbar_wait(empty + st, (uint32_t)((k & 1) ^ 1));
                 mbar_expect_tx(full + st, stage_bytes);
                 uint8_t* dst = sStage + (size_t)st * stage_bytes;
-                bulk_g2s(dst, a.XB + (int64_t)(t_begin + t) * TC_TILE_X_BYTES, TC_TILE_X_BYTES, full + st);
-                bulk_g2s(dst + TC_TILE_X_BYTES, a.VT + (int64_t)(t_begin + t) * vt_bytes, vt_bytes, full + st);
+                bulk_g2s(dst, a.WT + (int64_t)(t_begin + t) * stage_bytes, stage_bytes, full + st);
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
+        // ===================== MMA1 issuer: S(t) = A_i B_t^T, runs ahead of the softmax groups =====================
+        // (separate issuing threads for the two GEMMs: MMA1(t+2) must not wait behind the p_full(t) that gates MMA2(t),
+        //  otherwise both softmax groups idle for the MMA latency and then contend for the MUFU pipe in phase)
         if (lane == 0) {
-            const uint32_t idesc1 = umma_idesc_bf16(TC_BM, TC_BN), idesc2 = umma_idesc_bf16(TC_BM, a.NV);
+            const uint32_t idesc1 = umma_idesc_bf16(TC_BM, TC_BN, 1);
+            const uint32_t lbo = (uint32_t)a.NV * 128u;                // panel (64 j's) stride of the W^T tile
             const uint32_t aXA = smem_u32(sXA);
-            auto mma1 = [&](int t) {
+            mbar_wait(xa_full, 0);
+            for (int t = 0; t < T; ++t) {
                 const int st = t % TC_STAGES;
-                const uint32_t bXB = smem_u32(sStage + (size_t)st * stage_bytes);
+                mbar_wait(full + st, (uint32_t)((t / TC_STAGES) & 1));
+                if (t >= 2) mbar_wait(s_empty + (t & 1), (uint32_t)(((t >> 1) - 1) & 1));
+                tc_fence_after();
+                const uint32_t bW = smem_u32(sStage + (size_t)st * stage_bytes);
                 const uint32_t dS = tmem_S + (uint32_t)(t & 1) * TC_BN;
 #pragma unroll
-                for (int ks = 0; ks < TC_K / 16; ++ks)
-                    tc_mma_bf16(dS, umma_desc(aXA + ks * 32), umma_desc(bXB + ks * 32), idesc1, ks > 0 ? 1u : 0u);
+                for (int ks = 0; ks < TC_K / 16; ++ks)                 // B = rows 16ks..16ks+15 of W^T, MN-major
+                    tc_mma_bf16(dS, umma_desc(aXA + ks * 32), umma_desc_mn(bW + ks * 2048, lbo), idesc1, ks > 0 ? 1u : 0u);
                 tc_commit(s_full + (t & 1));
-            };
-            mbar_wait(xa_full, 0);
-            if (T > 0) {
-                mbar_wait(full + 0, 0);
-                tc_fence_after();
-                mma1(0);
+                tc_commit(empty + st);                                 // first of the two releases of the stage
             }
+        }
+    } else if (warp == 2) {
+        // ===================== MMA2 issuer: O += P(t) W_t =====================
+        if (lane == 0) {
+            const uint32_t idesc2 = umma_idesc_bf16(TC_BM, a.NV);
             for (int t = 0; t < T; ++t) {
-                if (t + 1 < T) {
-                    const int t1 = t + 1, st1 = t1 % TC_STAGES;
-                    mbar_wait(full + st1, (uint32_t)((t1 / TC_STAGES) & 1));
-                    if (t1 >= 2) mbar_wait(s_empty + (t1 & 1), (uint32_t)(((t1 >> 1) - 1) & 1));
-                    tc_fence_after();
-                    mma1(t1);
-                }
-                mbar_wait(p_full, (uint32_t)(t & 1));
-                tc_fence_after();
                 const int st = t % TC_STAGES;
-                const uint32_t bVT = smem_u32(sStage + (size_t)st * stage_bytes + TC_TILE_X_BYTES);
+                mbar_wait(full + st, (uint32_t)((t / TC_STAGES) & 1));
+                mbar_wait(p_full + (t & 1), (uint32_t)((t >> 1) & 1));
+                tc_fence_after();
+                const uint32_t bVT = smem_u32(sStage + (size_t)st * stage_bytes);
 #pragma unroll
                 for (int ks = 0; ks < TC_BN / 16; ++ks) {                // A = P from TMEM (8 columns per K=16 step)
                     const uint32_t pb = bVT + (uint32_t)(ks >> 2) * (uint32_t)(a.NV * 128) + (uint32_t)(ks & 3) * 32;
-                    tc_mma_bf16_ts(tmem_O, tmem_P + (uint32_t)ks * 8u, umma_desc(pb), idesc2, (t > 0 || ks > 0) ? 1u : 0u);
+                    tc_mma_bf16_ts(tmem_O, tmem_P + (uint32_t)(t & 1) * 64u + (uint32_t)ks * 8u, umma_desc(pb), idesc2,
+                                   (t > 0 || ks > 0) ? 1u : 0u);
                 }
-                tc_commit(empty + st);                                 // stage smem free once MMA2(t) has read it
-                tc_commit(p_empty);                                    // P tile free
+                tc_commit(empty + st);                                 // second release: stage smem free
+                tc_commit(p_empty + (t & 1));                          // P[t&1] free
             }
             if (T > 0) tc_commit(o_full);
         }
     } else {
         // ===================== softmax + epilogue (warps 2..9) =====================
         const int wq = warp & 3;                                       // TMEM lane quarter this warp may access
-        const int cq = (warp - 2) >> 2;                                // which 32-column quarter of the S tile
+        // two ping-pong groups of 8 warps: group g exponentiates the tiles of parity g (S[g] -> P[g]), so the MUFU phase
+        // of one group overlaps the barrier / TMEM load / TMEM store phases of the other and the XU pipe stays busy
+        const int idx = warp - 3;
+        const int grp = idx >> 3;                                      // tile parity handled by this warp
+        const int ch = (idx >> 2) & 1;                                 // 64-column half of the S tile
         const int row = wq * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
-        for (int t = 0; t < T; ++t) {
-            const int b = t & 1;
-            mbar_wait(s_full + b, (uint32_t)((t >> 1) & 1));
+        for (int t = grp; t < T; t += 2) {
+            const int u = t >> 1;                                      // use index of S[grp] / P[grp]
+            mbar_wait(s_full + grp, (uint32_t)(u & 1));
             tc_fence_after();
-            uint32_t packed[16], va[32];
-            TMEM_LD32(tmem_S + lane_addr + (uint32_t)(b * TC_BN + cq * 32), va);
+            uint32_t packed[32], va[64];
+            const uint32_t sbase = tmem_S + lane_addr + (uint32_t)(grp * TC_BN + ch * 64);
+            TMEM_LD32(sbase, va);
+            TMEM_LD32(sbase + 32u, (va + 32));
             tmem_ld_wait();
             tc_fence_before();
-            mbar_arrive(s_empty + b);                                  // S[b] may be overwritten by MMA1(t+2)
+            mbar_arrive(s_empty + grp);                                // S[grp] may be overwritten by MMA1(t+2)
 #pragma unroll
-            for (int e = 0; e < 32; e += 2) {
-                const __nv_bfloat162 pk = __floats2bfloat162_rn(ex2f(__uint_as_float(va[e])), ex2f(__uint_as_float(va[e + 1])));
+            for (int e = 0; e < 64; e += 2) {
+                const float p0 = ex2f(__uint_as_float(va[e]));
+                const float p1 = ((e + 1) & TC_POLY_MASK) == TC_POLY_MASK ? ex2_poly(__uint_as_float(va[e + 1]))
+                                                                          : ex2f(__uint_as_float(va[e + 1]));
+                const __nv_bfloat162 pk = __floats2bfloat162_rn(p0, p1);
                 packed[e >> 1] = *reinterpret_cast<const uint32_t*>(&pk);
             }
-            if (t >= 1) mbar_wait(p_empty, (uint32_t)((t - 1) & 1));   // MMA2(t-1) has consumed the P tile
+            if (u >= 1) mbar_wait(p_empty + grp, (uint32_t)((u - 1) & 1));   // MMA2(t-2) has consumed P[grp]
             tc_fence_after();
-            TMEM_ST16(tmem_P + lane_addr + (uint32_t)(cq * 16), packed);     // this row's 32 bf16 = 16 packed columns
+            TMEM_ST32(tmem_P + lane_addr + (uint32_t)(grp * 64 + ch * 32), packed);   // this row's 64 bf16 = 32 packed columns
             tmem_st_wait();
             tc_fence_before();
-            mbar_arrive(p_full);
+            mbar_arrive(p_full + grp);
         }
+        const int cq = idx >> 2;                                       // epilogue: 32-column quarter of O per warp
         // ---- partial O of this j range -> workspace (summed in fixed order by svgd_tc_finish_kernel)
         if (T > 0) {
             mbar_wait(o_full, 0);
@@ -378,7 +408,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) svgd_phi_tc_kernel(TcArgs a) {
     }
 }
 
-// phi_i = ( -O_G + (x_i O_1 - O_X)/h^2 ) / n  with O = sum of the TC_SPLIT partials (fixed order: deterministic)
+// phi_i = ( -O_G + (x_i O_1 - O_X)/h^2 ) / n  with O = sum of the TC_SPLIT partials (fixed order: deterministic).
+// O columns follow the W^T rows: [0,d) = sum_j P x_j (scaled by sc), d+2 = sum_j P, [d+4, 2d+4) = sum_j P g_j.
 __global__ void __launch_bounds__(256) svgd_tc_finish_kernel(TcArgs a) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (int64_t)a.n * a.d) return;
@@ -387,41 +418,44 @@ __global__ void __launch_bounds__(256) svgd_tc_finish_kernel(TcArgs a) {
 #pragma unroll
     for (int p = 0; p < TC_SPLIT; ++p) {
         const float* o = a.opart + ((int64_t)p * a.n_pad + i) * a.NV;
-        og += o[k]; ox += o[a.d + k]; o1 += o[2 * a.d];
+        ox += o[k]; o1 += o[a.d + 2]; og += o[a.d + 4 + k];
     }
     const float h = a.bandwidth[0];
-    const float invh2 = 1.f / (h * h), invn = 1.f / (float)a.n;
-    a.phi[idx] = (-og + (a.xc[idx] * o1 - ox) * invh2) * invn;
+    const float sc = sqrtf(1.4426950408889634f) / h;
+    const float invn = 1.f / (float)a.n;
+    a.phi[idx] = (-og + (a.xs[idx] * o1 - ox) / (sc * h * h)) * invn;
 }
 
 // ---- host ---------------------------------------------------------------------------------------
 int mb_svgd_phi_tc(mb_ctx* ctx, const float* X, const float* G, int n, int d, const float* bandwidth, float* phi,
                    cudaStream_t st) {
     MB_REQUIRE(d >= 1 && d + 4 <= TC_K, "svgd tcgen05 variant needs d <= 60");
-    const int NV = ((2 * d + 1 + 15) / 16) * 16;
-    MB_REQUIRE(NV <= 128, "svgd tcgen05 variant: 2d+1 must be <= 128");
+    int NV = ((2 * d + 4 + 15) / 16) * 16;
+    if (NV < TC_K) NV = TC_K;                          // MMA1 reads rows 0..63 of every W^T tile
     const int n_pad = ((n + TC_BM - 1) / TC_BM) * TC_BM;
     const int tiles = n_pad / TC_BM;
-    const size_t bx = (size_t)tiles * TC_TILE_X_BYTES, bv = (size_t)tiles * NV * 256;
-    const size_t bo = (size_t)TC_SPLIT * n_pad * NV * 4;
-    const size_t need = 256 + 2 * bx + bv + (size_t)n_pad * d * 4 + bo + 8192;
+    const size_t bx = (size_t)tiles * TC_TILE_X_BYTES, bw = (size_t)tiles * NV * 256;
+    const size_t bs = (size_t)n_pad * d * 4, ba = (size_t)n_pad * 2 * 4, bo = (size_t)TC_SPLIT * n_pad * NV * 4;
+    const size_t need = 1024 + bx + bw + bs + ba + bo + 8192;
     if (mb_ensure_scratch(ctx, (4u << 20) + need) != MB_OK) return MB_ERR_CUDA;
     uint8_t* base = (uint8_t*)ctx->scratch + (4u << 20);              // [0, 4 MiB) is used by the other kernels
-    base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(base) + 255) & ~(uintptr_t)255);
-    float* mean = reinterpret_cast<float*>(base);
-    uint8_t* XA = base + 256;
-    uint8_t* XB = XA + bx;
-    uint8_t* VT = XB + bx;
-    float* xc = reinterpret_cast<float*>(VT + bv);
-    float* opart = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(xc + (size_t)n_pad * d) + 255) & ~(uintptr_t)255);
-    svgd_tc_colmean_kernel<<<d, 256, 0, st>>>(X, n, d, mean);
-    TcPrepArgs p{X, G, mean, bandwidth, n, d, n_pad, NV, XA, XB, VT, xc};
-    const int64_t work = max((int64_t)n_pad * 8, (int64_t)tiles * NV * 16);
-    svgd_tc_prep_kernel<<<(unsigned)((work + 255) / 256), 256, 0, st>>>(p);
+    auto align = [](uint8_t* p) { return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~(uintptr_t)1023); };
+    float* mean = reinterpret_cast<float*>(align(base));
+    uint8_t* XA = align(reinterpret_cast<uint8_t*>(mean) + 256);
+    uint8_t* WT = align(XA + bx);
+    float* xs = reinterpret_cast<float*>(align(WT + bw));
+    float* saux = reinterpret_cast<float*>(align(reinterpret_cast<uint8_t*>(xs) + bs));
+    float* opart = reinterpret_cast<float*>(align(reinterpret_cast<uint8_t*>(saux) + ba));
+    double* cpart = reinterpret_cast<double*>((char*)ctx->scratch + (3u << 20) + (64u << 10));   // 148 x 64 doubles
+    svgd_tc_colsum_kernel<<<ctx->sms, 256, 0, st>>>(X, n, d, cpart);
+    svgd_tc_colmean_kernel<<<1, 64, 0, st>>>(cpart, ctx->sms, n, d, mean);
+    TcPrepArgs p{X, G, mean, bandwidth, n, d, n_pad, NV, XA, WT, xs, saux};
+    svgd_tc_rows_kernel<<<(unsigned)(((int64_t)n_pad * 8 + 255) / 256), 256, 0, st>>>(p);
+    svgd_tc_wt_kernel<<<(unsigned)(((int64_t)tiles * NV * 16 + 255) / 256), 256, 0, st>>>(p);
     MB_CHECK_LAUNCH();
-    const size_t smem = 1024 + TC_TILE_X_BYTES + (size_t)TC_STAGES * (TC_TILE_X_BYTES + NV * 256) + 256;
+    const size_t smem = 1024 + TC_TILE_X_BYTES + (size_t)TC_STAGES * NV * 256 + 256;
     MB_CUDA(cudaFuncSetAttribute(svgd_phi_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    TcArgs a{XA, XB, VT, xc, bandwidth, phi, n, d, n_pad, NV, opart};
+    TcArgs a{XA, WT, xs, bandwidth, phi, n, d, n_pad, NV, opart};
     svgd_phi_tc_kernel<<<tiles * TC_SPLIT, TC_THREADS, smem, st>>>(a);
     MB_CHECK_LAUNCH();
     svgd_tc_finish_kernel<<<(unsigned)(((int64_t)n * d + 255) / 256), 256, 0, st>>>(a);
