@@ -141,11 +141,10 @@ __device__ __forceinline__ float ex2_poly(float x) {
     const float p = fmaf(fmaf(fmaf(0.05517167f, f, 0.24261113f), f, 0.69326097f), f, 0.99992806f);
     return __int_as_float(__float_as_int(p) + (__float_as_int(xi) << 23));
 }
-#ifndef TC_POLY_MASK
-#define TC_POLY_MASK 0x7fffffff
+#ifndef TC_POLY_NUM
+#define TC_POLY_NUM 3                                  // of every 16 exponentials, this many use ex2_poly (measured: 0:0.417 2:.. 3:0.378 4:0.389 5:0.400 8:0.446 ms)
 #endif
-// (default: disabled)                        // measured: offloading exps to the FMA pipe is SLOWER here (issue-bound,
-                                                       // not MUFU-bound: 0.559 vs 0.514 ms at 25 %), so it is disabled
+__device__ __forceinline__ constexpr bool tc_use_poly(int e) { return ((e * TC_POLY_NUM) & 15) < TC_POLY_NUM && TC_POLY_NUM > 0; }
 
 // byte offset of element (row r, k) inside a K-major SWIZZLE_128B panel of 64 bf16 per row
 __host__ __device__ __forceinline__ uint32_t sw128_off(int r, int k) {
@@ -365,9 +364,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) svgd_phi_tc_kernel(TcArgs a) {
             mbar_arrive(s_empty + grp);                                // S[grp] may be overwritten by MMA1(t+2)
 #pragma unroll
             for (int e = 0; e < 64; e += 2) {
-                const float p0 = ex2f(__uint_as_float(va[e]));
-                const float p1 = ((e + 1) & TC_POLY_MASK) == TC_POLY_MASK ? ex2_poly(__uint_as_float(va[e + 1]))
-                                                                          : ex2f(__uint_as_float(va[e + 1]));
+                const float p0 = tc_use_poly(e) ? ex2_poly(__uint_as_float(va[e])) : ex2f(__uint_as_float(va[e]));
+                const float p1 = tc_use_poly(e + 1) ? ex2_poly(__uint_as_float(va[e + 1])) : ex2f(__uint_as_float(va[e + 1]));
                 const __nv_bfloat162 pk = __floats2bfloat162_rn(p0, p1);
                 packed[e >> 1] = *reinterpret_cast<const uint32_t*>(&pk);
             }
