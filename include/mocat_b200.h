@@ -255,9 +255,19 @@ int mb_abc_adapt(mb_ctx* ctx, const float* x, int64_t ld, int64_t n, int64_t n_t
 int mb_svgd_phi(mb_ctx* ctx, const float* X, const float* G, int n, int d, const float* bandwidth,
                 float* phi, int variant, mb_stream_t stream);
 int mb_pairdist_bandwidth(mb_ctx* ctx, const float* X, int n, int d, int mode /*0 median, 1 mean*/,
-                          float* h, mb_stream_t stream);
+                          float* h, int variant /*0 exact fp32 SIMT, 1 tcgen05 (bf16 coordinates)*/,
+                          mb_stream_t stream);
 int mb_adagrad(mb_ctx* ctx, float* X, float* gsq, float* mom, const float* phi, int64_t len, float step,
                float momentum, mb_stream_t stream);
+/* x ~ N(prior_mean, prior_std^2 I) at row-major X (n x d), any d: transport/sampler.py:24-30 (vmap(prior_sample));
+ * same Philox stream as mb_smc_init (purpose INIT, step 0). */
+int mb_prior_sample(mb_ctx* ctx, float prior_mean, float prior_std, int d, int64_t n, uint64_t seed, int64_t gid0,
+                    float* X, mb_stream_t stream);
+/* Bayesian logistic regression target of config C4 (the reference has no such Scenario): features
+ * (N x d), labels (N) on the device, isotropic Gaussian prior; W, G row-major (n x d). */
+int mb_logistic_potential_grad(mb_ctx* ctx, const float* features, const float* labels, int N, int d,
+                               float prior_mean, float prior_pscale, double beta, const float* W, int n, float* U,
+                               float* G, int variant, mb_stream_t stream);
 int mb_target_potential_grad(mb_ctx* ctx, const mb_target* tgt, double beta, const float* X /*n x d row-major*/,
                              int n, float* U, float* G, mb_stream_t stream);
 

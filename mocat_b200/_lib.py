@@ -129,6 +129,9 @@ SIGNATURES = {
     "mb_quantile": (C.c_int, [c_vp, c_vp, c_i64, c_d, c_vp, c_vp]),
     "mb_colstats": (C.c_int, [c_vp, c_vp, c_i64, c_i64, C.c_int, c_vp, c_vp, c_vp]),
     "mb_target_potential_grad": (C.c_int, [c_vp, C.POINTER(Target), c_d, c_vp, C.c_int, c_vp, c_vp, c_vp]),
+    "mb_prior_sample": (C.c_int, [c_vp, c_f, c_f, C.c_int, c_i64, c_u64, c_i64, c_vp, c_vp]),
+    "mb_logistic_potential_grad": (C.c_int, [c_vp, c_vp, c_vp, C.c_int, C.c_int, c_f, c_f, c_d, c_vp, C.c_int, c_vp, c_vp,
+                                             C.c_int, c_vp]),
     "mb_abc_init": (C.c_int, [c_vp, C.POINTER(GK), c_vp, c_i64, c_i64, c_i64, C.c_int, c_vp, c_vp, c_vp, c_vp, c_u64,
                               c_i64, c_vp, c_vp]),
     "mb_abc_move": (C.c_int, [c_vp, C.POINTER(GK), C.c_int, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp,
@@ -136,7 +139,7 @@ SIGNATURES = {
     "mb_abc_adapt": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, C.c_int, c_vp, c_vp, c_vp, c_vp, c_d, c_d, c_d,
                                C.c_int, c_vp, C.c_int, c_vp, c_vp, c_vp]),
     "mb_svgd_phi": (C.c_int, [c_vp, c_vp, c_vp, C.c_int, C.c_int, c_vp, c_vp, C.c_int, c_vp]),
-    "mb_pairdist_bandwidth": (C.c_int, [c_vp, c_vp, C.c_int, C.c_int, C.c_int, c_vp, c_vp]),
+    "mb_pairdist_bandwidth": (C.c_int, [c_vp, c_vp, C.c_int, C.c_int, C.c_int, c_vp, C.c_int, c_vp]),
     "mb_adagrad": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_f, c_f, c_vp]),
 }
 

@@ -134,13 +134,17 @@ class Scenario:
     def _target(self):
         raise NotImplementedError
 
+    def _potential_grad_device(self, X, temperature):
+        """(U (n,), G (n, d)) device tensors for X (n, d) row-major float32 on the device"""
+        from . import engine
+        return engine.target_potential_grad(self._target(), temperature, X)
+
     def _eval(self, x, temperature):
         import torch
-        from . import engine
         x = np.asarray(x, dtype=np.float32)
         single = x.ndim == 1
         X = torch.as_tensor(np.atleast_2d(x), device="cuda").contiguous()
-        U, G = engine.target_potential_grad(self._target(), temperature, X)
+        U, G = self._potential_grad_device(X, temperature)
         U, G = U.cpu().numpy(), G.cpu().numpy()
         return (U[0], G[0]) if single else (U, G)
 

@@ -58,6 +58,7 @@ struct mb_ctx {
 #define MB_CNT_MOVE     3
 #define MB_CNT_MISC     4
 #define MB_CNT_SCAN_EPOCH 5
+#define MB_CNT_BW_FALLBACK 8 // (64-bit, slots 8-9) median-bracket misses of the tcgen05 bandwidth kernel
 #define MB_NUM_COUNTERS 64
 
 int mb_ensure_scratch(mb_ctx* ctx, size_t bytes);

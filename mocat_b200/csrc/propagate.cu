@@ -542,3 +542,28 @@ extern "C" int mb_pf_step(mb_ctx* ctx, const mb_ssm* ssm, const float* x_in, flo
     if (comm) { a.comm = *mb_comm_dev(comm); a.has_comm = a.comm.world > 1; }
     return pf_dispatch(ctx, a, mb_s(stream));
 }
+
+// prior sample of any dimension at row-major points (transport/sampler.py:24-30 vmap(prior_sample)); the same
+// Philox stream as smc_init_kernel (purpose INIT, step 0): one thread per (particle, 4-normal slot).
+__global__ void prior_sample_kernel(float mean, float std, int d, int64_t n, uint64_t seed, int64_t gid0, float* X) {
+    const int nz = (d + 3) / 4;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * nz) return;
+    const int64_t i = t / nz;
+    const int s = (int)(t - i * nz);
+    const Philox4 r = philox_raw(seed, (uint64_t)(gid0 + i), 0u, MB_P_INIT, (uint32_t)s);
+    float z[4];
+    box_muller(r.x, r.y, z[0], z[1]);
+    box_muller(r.z, r.w, z[2], z[3]);
+    for (int c = 0; c < 4; ++c)
+        if (4 * s + c < d) X[i * d + 4 * s + c] = fmaf(std, z[c], mean);
+}
+
+extern "C" int mb_prior_sample(mb_ctx* ctx, float prior_mean, float prior_std, int d, int64_t n, uint64_t seed,
+                               int64_t gid0, float* X, mb_stream_t stream) {
+    MB_REQUIRE(ctx && X && d > 0 && n > 0, "mb_prior_sample: bad arguments");
+    const int64_t total = n * ((d + 3) / 4);
+    prior_sample_kernel<<<(unsigned)((total + 255) / 256), 256, 0, mb_s(stream)>>>(prior_mean, prior_std, d, n, seed, gid0, X);
+    MB_CHECK_LAUNCH();
+    return MB_OK;
+}

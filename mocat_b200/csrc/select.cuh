@@ -42,23 +42,41 @@ select_hist_kernel(const float* __restrict__ v, int64_t n, const SelectState* st
 }
 
 template <int SHIFT, int BITS>
-static __global__ void select_pick_kernel(SelectState* st, uint32_t* hist) {
-    // single thread: walk the histogram (<= 2048 bins) to the bucket holding the rank
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        int64_t r = st->rank;
-        uint32_t b = 0;
-        for (; b < (1u << BITS); ++b) {
-            const int64_t c = hist[b];
-            if (r < c) break;
-            r -= c;
-        }
-        if (b == (1u << BITS)) b = (1u << BITS) - 1;
-        st->rank = r;
-        st->prefix |= (b << SHIFT);
-        if (SHIFT == 0) { st->sel_key = st->prefix; st->count_le = 0; st->min_gt_key = 0xffffffffu; }
-    }
+static __global__ void __launch_bounds__(256) select_pick_kernel(SelectState* st, uint32_t* hist) {
+    // 256 threads x (bins/256) consecutive bins: block-wide exclusive scan, the thread whose range holds the rank
+    // publishes bucket and remaining rank; the histogram is cleared for the next pass
+    constexpr int NB = 1 << BITS, PER = NB / 256;
+    static_assert(NB % 256 == 0, "bins per thread");
+    __shared__ long long wsum[8];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    uint32_t c[PER];
+    long long loc = 0;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) { c[k] = hist[tid * PER + k]; loc += c[k]; }
+    long long inc = loc;
+    for (int o = 1; o < 32; o <<= 1) { const long long t = __shfl_up_sync(MB_FULL, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) wsum[w] = inc;
+    const long long r0 = st->rank;
+    const uint32_t prefix0 = st->prefix;
     __syncthreads();
-    for (int i = threadIdx.x; i < (1 << BITS); i += blockDim.x) hist[i] = 0;
+    long long cum = inc - loc, total = 0;
+    for (int k = 0; k < 8; ++k) { if (k < w) cum += wsum[k]; total += wsum[k]; }
+    uint32_t b = 0xffffffffu;
+    long long r = 0;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        if (b == 0xffffffffu && r0 >= cum && r0 < cum + (long long)c[k]) { b = (uint32_t)(tid * PER + k); r = r0 - cum; }
+        cum += c[k];
+    }
+    if (r0 >= total && tid == 255) { b = NB - 1; r = r0 - (total - (long long)c[PER - 1]); }   // rank beyond the data: last bucket
+    if (b != 0xffffffffu) {
+        st->rank = r;
+        const uint32_t pf = prefix0 | (b << SHIFT);
+        st->prefix = pf;
+        if (SHIFT == 0) { st->sel_key = pf; st->count_le = 0; st->min_gt_key = 0xffffffffu; }
+    }
+#pragma unroll
+    for (int k = 0; k < PER; ++k) hist[tid * PER + k] = 0;
 }
 
 static __global__ void __launch_bounds__(SEL_THREADS)

@@ -320,8 +320,13 @@ extern "C" int mb_svgd_phi(mb_ctx* ctx, const float* X, const float* G, int n, i
     return MB_ERR_UNSUPPORTED;
 }
 
-extern "C" int mb_pairdist_bandwidth(mb_ctx* ctx, const float* X, int n, int d, int mode, float* h, mb_stream_t stream) {
+int mb_pairdist_bandwidth_tc(mb_ctx* ctx, const float* X, int n, int d, int mode, float* h, cudaStream_t st);
+
+extern "C" int mb_pairdist_bandwidth(mb_ctx* ctx, const float* X, int n, int d, int mode, float* h, int variant,
+                                     mb_stream_t stream) {
     MB_REQUIRE(ctx && X && h && n > 1 && d > 0 && (mode == 0 || mode == 1), "mb_pairdist_bandwidth: bad arguments");
+    if (variant == 1) return mb_pairdist_bandwidth_tc(ctx, X, n, d, mode, h, mb_s(stream));
+    MB_REQUIRE(variant == 0, "mb_pairdist_bandwidth: variant not built");
     return svgd_dispatch(ctx, mode == 0 ? 1 : 2, X, nullptr, n, d, nullptr, h, mb_s(stream));
 }
 
@@ -346,6 +351,80 @@ extern "C" int mb_adagrad(mb_ctx* ctx, float* X, float* gsq, float* mom, const f
     int64_t grid = (len + 255) / 256;
     if (grid > (int64_t)ctx->sms * 16) grid = (int64_t)ctx->sms * 16;
     adagrad_kernel<<<(unsigned)grid, 256, 0, mb_s(stream)>>>(X, gsq, mom, phi, len, step, momentum);
+    MB_CHECK_LAUNCH();
+    return MB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Bayesian logistic regression (config C4; no such Scenario exists upstream): labels t in {0,1},
+// features A (N x d), prior N(mean, 1/pscale^2 I):
+//   U(w) = U_prior(w) + beta * sum_k [ softplus(a_k.w) - t_k a_k.w ],   grad = grad_prior + beta * A^T (sigma(A w) - t).
+// variant 0: exact fp32, one thread per particle, data rows broadcast from shared memory.
+#define LR_THREADS 128
+#define LR_TILE 64
+template <int DP>
+__global__ void __launch_bounds__(LR_THREADS)
+logistic_pg_simt_kernel(const float* __restrict__ A, const float* __restrict__ t, int N, int d, float prior_mean,
+                        float prior_pscale, float beta, const float* __restrict__ W, int n, float* U, float* G) {
+    __shared__ __align__(16) float sa[LR_TILE * DP];
+    __shared__ float st[LR_TILE];
+    const int i = blockIdx.x * LR_THREADS + threadIdx.x;
+    float w[DP], g[DP];
+#pragma unroll
+    for (int k = 0; k < DP; ++k) { w[k] = (i < n && k < d) ? W[(int64_t)i * d + k] : 0.f; g[k] = 0.f; }
+    float ul = 0.f;
+    for (int j0 = 0; j0 < N; j0 += LR_TILE) {
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < LR_TILE * DP; idx += LR_THREADS) {
+            const int j = idx / DP, k = idx - j * DP;
+            sa[idx] = (j0 + j < N && k < d) ? A[(int64_t)(j0 + j) * d + k] : 0.f;
+        }
+        if (threadIdx.x < LR_TILE) st[threadIdx.x] = (j0 + threadIdx.x < N) ? t[j0 + threadIdx.x] : 0.f;
+        __syncthreads();
+        const int jn = min(LR_TILE, N - j0);
+        for (int j = 0; j < jn; ++j) {
+            const float4* ar = reinterpret_cast<const float4*>(sa + j * DP);
+            float s = 0.f;
+#pragma unroll
+            for (int k4 = 0; k4 < DP / 4; ++k4) {
+                const float4 v = ar[k4];
+                s = fmaf(w[4 * k4], v.x, s); s = fmaf(w[4 * k4 + 1], v.y, s);
+                s = fmaf(w[4 * k4 + 2], v.z, s); s = fmaf(w[4 * k4 + 3], v.w, s);
+            }
+            const float e = __expf(-fabsf(s));                        // stable softplus / sigmoid
+            const float inv = 1.f / (1.f + e);
+            const float sig = s >= 0.f ? inv : e * inv;
+            ul += fmaxf(s, 0.f) + log1pf(e) - st[j] * s;
+            const float r = sig - st[j];
+#pragma unroll
+            for (int k4 = 0; k4 < DP / 4; ++k4) {
+                const float4 v = ar[k4];
+                g[4 * k4] = fmaf(r, v.x, g[4 * k4]); g[4 * k4 + 1] = fmaf(r, v.y, g[4 * k4 + 1]);
+                g[4 * k4 + 2] = fmaf(r, v.z, g[4 * k4 + 2]); g[4 * k4 + 3] = fmaf(r, v.w, g[4 * k4 + 3]);
+            }
+        }
+    }
+    if (i >= n) return;
+    float up = 0.f;
+    for (int k = 0; k < d; ++k) {
+        const float rr = (w[k] - prior_mean) * prior_pscale;
+        up = fmaf(0.5f * rr, rr, up);
+        G[(int64_t)i * d + k] = fmaf(beta, g[k], rr * prior_pscale);
+    }
+    if (U) U[i] = fmaf(beta, ul, up);
+}
+
+extern "C" int mb_logistic_potential_grad(mb_ctx* ctx, const float* features, const float* labels, int N, int d,
+                                          float prior_mean, float prior_pscale, double beta, const float* W, int n,
+                                          float* U, float* G, int variant, mb_stream_t stream) {
+    MB_REQUIRE(ctx && features && labels && W && G && N > 0 && d > 0 && n > 0, "mb_logistic_potential_grad: bad arguments");
+    MB_REQUIRE(variant == 0, "mb_logistic_potential_grad: only variant 0 (fp32) is built");
+    const int grid = (n + LR_THREADS - 1) / LR_THREADS;
+    cudaStream_t st = mb_s(stream);
+#define LR_CASE(DPV) logistic_pg_simt_kernel<DPV><<<grid, LR_THREADS, 0, st>>>(features, labels, N, d, prior_mean, prior_pscale, (float)beta, W, n, U, G)
+    if (d <= 4) LR_CASE(4); else if (d <= 8) LR_CASE(8); else if (d <= 16) LR_CASE(16); else if (d <= 32) LR_CASE(32);
+    else if (d <= 52) LR_CASE(52); else if (d <= 64) LR_CASE(64);
+    else { mb_set_error("logistic regression: dim %d > 64 not built", d); return MB_ERR_UNSUPPORTED; }
     MB_CHECK_LAUNCH();
     return MB_OK;
 }

@@ -163,12 +163,18 @@ __global__ void __launch_bounds__(256) svgd_tc_colsum_kernel(const float* __rest
     __syncthreads();
     if (rg == 0) part[blockIdx.x * 64 + c] = sm[0][c] + sm[1][c] + sm[2][c] + sm[3][c];
 }
-__global__ void svgd_tc_colmean_kernel(const double* part, int nblocks, int n, int d, float* mean) {
-    const int c = threadIdx.x;
-    if (c >= d) return;
+__global__ void __launch_bounds__(1024) svgd_tc_colmean_kernel(const double* part, int nblocks, int n, int d, float* mean) {
+    __shared__ double sm[16][64];
+    const int c = threadIdx.x & 63, g = threadIdx.x >> 6;              // 16 block groups per column, fixed order
     double s = 0.0;
-    for (int b = 0; b < nblocks; ++b) s += part[b * 64 + c];
-    mean[c] = (float)(s / (double)n);
+    for (int b = g; b < nblocks; b += 16) s += part[b * 64 + c];
+    sm[g][c] = s;
+    __syncthreads();
+    if (g == 0 && c < d) {
+        double t = 0.0;
+        for (int k = 0; k < 16; ++k) t += sm[k][c];
+        mean[c] = (float)(t / (double)n);
+    }
 }
 
 struct TcPrepArgs {
@@ -183,7 +189,7 @@ __global__ void __launch_bounds__(256) svgd_tc_rows_kernel(TcPrepArgs a) {
     const int row = (int)(tid >> 3), ch = (int)(tid & 7);
     const int tile = row / TC_BM, r = row % TC_BM;
     const bool valid = row < a.n;
-    const float sc = sqrtf(1.4426950408889634f) / a.bandwidth[0];
+    const float sc = a.bandwidth ? sqrtf(1.4426950408889634f) / a.bandwidth[0] : 1.f;   // NULL: plain centred coordinates
     float sq = 0.f;                                    // from the ROUNDED coordinates, so that D_ii = 0 up to the hi/lo split
     if (valid)
         for (int k = 0; k < a.d; ++k) {
@@ -227,7 +233,7 @@ __global__ void __launch_bounds__(256) svgd_tc_wt_kernel(TcPrepArgs a) {
         else if (c == a.d) f = a.saux[2 * j];
         else if (c == a.d + 1) f = a.saux[2 * j + 1];
         else if (c == a.d + 2 || c == a.d + 3) f = 1.f;
-        else if (c < 2 * a.d + 4) f = (j < a.n) ? a.G[(int64_t)j * a.d + (c - a.d - 4)] : 0.f;
+        else if (c < 2 * a.d + 4 && a.G) f = (j < a.n) ? a.G[(int64_t)j * a.d + (c - a.d - 4)] : 0.f;
         v[e] = __float2bfloat16_rn(f);
     }
     const uint32_t off = (uint32_t)(q >> 3) * (uint32_t)(a.NV * 128) + sw128_off(c, (q & 7) * 8);
@@ -446,7 +452,7 @@ int mb_svgd_phi_tc(mb_ctx* ctx, const float* X, const float* G, int n, int d, co
     float* opart = reinterpret_cast<float*>(align(reinterpret_cast<uint8_t*>(saux) + ba));
     double* cpart = reinterpret_cast<double*>((char*)ctx->scratch + (3u << 20) + (64u << 10));   // 148 x 64 doubles
     svgd_tc_colsum_kernel<<<ctx->sms, 256, 0, st>>>(X, n, d, cpart);
-    svgd_tc_colmean_kernel<<<1, 64, 0, st>>>(cpart, ctx->sms, n, d, mean);
+    svgd_tc_colmean_kernel<<<1, 1024, 0, st>>>(cpart, ctx->sms, n, d, mean);
     TcPrepArgs p{X, G, mean, bandwidth, n, d, n_pad, NV, XA, WT, xs, saux};
     svgd_tc_rows_kernel<<<(unsigned)(((int64_t)n_pad * 8 + 255) / 256), 256, 0, st>>>(p);
     svgd_tc_wt_kernel<<<(unsigned)(((int64_t)tiles * NV * 16 + 255) / 256), 256, 0, st>>>(p);
@@ -457,6 +463,322 @@ int mb_svgd_phi_tc(mb_ctx* ctx, const float* X, const float* G, int n, int d, co
     svgd_phi_tc_kernel<<<tiles * TC_SPLIT, TC_THREADS, smem, st>>>(a);
     MB_CHECK_LAUNCH();
     svgd_tc_finish_kernel<<<(unsigned)(((int64_t)n * d + 255) / 256), 256, 0, st>>>(a);
+    MB_CHECK_LAUNCH();
+    return MB_OK;
+}
+
+// =================================================================================================
+// K9 on the tensor cores: bandwidth heuristics over the full n x n distance matrix (kernels.py:220-229,
+// utils.py:437-439).  S = -|x_i - x_j|^2 / 2 comes from the same MMA1 as above (centred, unscaled bf16 coordinates,
+// fp32 accumulation); the 16 consumer warps reduce every S tile straight out of TMEM:
+//   mean   : sum of sqrt(-2 S)                            (fp64 per-thread accumulators, fixed-order reduction)
+//   median : a bracket [lo, hi] of the median of |x_i-x_j|^2 is taken from 2^18 hashed sample pairs (exact fp32,
+//            +-6 sigma of the sample quantile); ONE pass over the matrix counts the entries below the bracket and
+//            histograms the <~ 2 % inside it into 2048 bins; the finish kernel walks the histogram to the two middle
+//            ranks.  Resolution (hi-lo)/2048, far below the bf16 rounding of the coordinates (~1e-3 per entry, which
+//            moves the median only at second order).  If the bracket misses (probability ~1e-9) the sample median is
+//            used and MB_CNT_BW_FALLBACK is incremented.
+#define DT_THREADS 576                               // producer + MMA warps, 16 consumer warps
+#define DT_STAGES 8
+#define DT_BINS 2048
+#define DT_SAMPLES (1 << 18)
+
+struct DtBracket { float bin_off, inv_bw; double lo_w, bw_d2, fallback_d2; };
+struct DtArgs {
+    const uint8_t* XA; const uint8_t* WT; int n, n_pad;
+    const DtBracket* br; uint32_t* hist; unsigned long long* below; double* partials;
+};
+
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+template <int MODE>   // 0 median (count + bracket histogram), 1 mean
+__global__ void __launch_bounds__(DT_THREADS, 1) svgd_dist_tc_kernel(DtArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    constexpr uint32_t stage_bytes = TC_K * 256u;                      // W^T tile with NV = 64 rows
+    uint8_t* sXA = smem;
+    uint8_t* sStage = sXA + TC_TILE_X_BYTES;
+    uint32_t* shist = reinterpret_cast<uint32_t*>(sStage + DT_STAGES * stage_bytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(shist + DT_BINS);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + DT_STAGES;
+    uint64_t* s_full = bars + 2 * DT_STAGES;
+    uint64_t* s_empty = s_full + 2;
+    uint64_t* xa_full = s_empty + 2;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(xa_full + 1);
+    double* red = reinterpret_cast<double*>(tmem_ptr + 2);            // [16]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int T_all = a.n_pad / TC_BN;
+    const int itile = blockIdx.x / TC_SPLIT, part = blockIdx.x % TC_SPLIT;
+    const int t_begin = (int)(((int64_t)T_all * part) / TC_SPLIT), t_end = (int)(((int64_t)T_all * (part + 1)) / TC_SPLIT);
+    const int T = t_end - t_begin;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < DT_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(s_full + b, 1); mbar_init(s_empty + b, TC_SM_THREADS / 2); }
+        mbar_init(xa_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (MODE == 0)
+        for (int i = threadIdx.x; i < DT_BINS; i += DT_THREADS) shist[i] = 0;
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(256u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_S = *tmem_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(xa_full, TC_TILE_X_BYTES);
+            bulk_g2s(sXA, a.XA + (int64_t)itile * TC_TILE_X_BYTES, TC_TILE_X_BYTES, xa_full);
+            for (int t = 0; t < T; ++t) {
+                const int st = t % DT_STAGES, k = t / DT_STAGES;
+                mbar_wait(empty + st, (uint32_t)((k & 1) ^ 1));
+                mbar_expect_tx(full + st, stage_bytes);
+                bulk_g2s(sStage + (size_t)st * stage_bytes, a.WT + (int64_t)(t_begin + t) * stage_bytes, stage_bytes, full + st);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc1 = umma_idesc_bf16(TC_BM, TC_BN, 1);
+            const uint32_t aXA = smem_u32(sXA);
+            mbar_wait(xa_full, 0);
+            for (int t = 0; t < T; ++t) {
+                const int st = t % DT_STAGES;
+                mbar_wait(full + st, (uint32_t)((t / DT_STAGES) & 1));
+                if (t >= 2) mbar_wait(s_empty + (t & 1), (uint32_t)(((t >> 1) - 1) & 1));
+                tc_fence_after();
+                const uint32_t bW = smem_u32(sStage + (size_t)st * stage_bytes);
+                const uint32_t dS = tmem_S + (uint32_t)(t & 1) * TC_BN;
+#pragma unroll
+                for (int ks = 0; ks < TC_K / 16; ++ks)
+                    tc_mma_bf16(dS, umma_desc(aXA + ks * 32), umma_desc_mn(bW + ks * 2048, TC_K * 128u), idesc1, ks > 0 ? 1u : 0u);
+                tc_commit(s_full + (t & 1));
+                tc_commit(empty + st);
+            }
+        }
+    } else {
+        const int wq = warp & 3;
+        const int idx = warp - 2;
+        const int grp = idx >> 3, ch = (idx >> 2) & 1;
+        const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
+        const bool row_valid = itile * TC_BM + wq * 32 + lane < a.n;     // padded rows of the last i tile count nothing
+        float bin_scale = 0.f, bin_off = 0.f;
+        if (MODE == 0) { bin_scale = -a.br->inv_bw; bin_off = a.br->bin_off; }
+        uint32_t cnt = 0;
+        double dsum = 0.0;
+        for (int t = grp; t < T; t += 2) {
+            const int u = t >> 1;
+            mbar_wait(s_full + grp, (uint32_t)(u & 1));
+            tc_fence_after();
+            uint32_t va[64];
+            const uint32_t sbase = tmem_S + lane_addr + (uint32_t)(grp * TC_BN + ch * 64);
+            TMEM_LD32(sbase, va);
+            TMEM_LD32(sbase + 32u, (va + 32));
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(s_empty + grp);
+            if (!row_valid) continue;
+            if (MODE == 0) {
+                // bin = round(D^2/bw - k0) through the 1.5*2^23 trick (one FFMA, no F2I on the XU pipe):
+                // bin < 0: below the bracket (counted), 0 <= bin < DT_BINS: histogrammed, otherwise above (padding: +huge)
+#pragma unroll
+                for (int e = 0; e < 64; ++e) {
+                    const int b = __float_as_int(fmaf(__uint_as_float(va[e]), bin_scale, bin_off)) - 0x4B400000;
+                    cnt += (uint32_t)b >> 31;
+                    if ((uint32_t)b < (uint32_t)DT_BINS) atomicAdd(&shist[b], 1u);
+                }
+            } else {
+                float ts = 0.f;
+#pragma unroll
+                for (int e = 0; e < 64; ++e) {
+                    const float v = __uint_as_float(va[e]);
+                    const float dd = sqrt_approx(fmaxf(-2.f * v, 0.f));
+                    ts += (v > -1.0e29f) ? dd : 0.f;                   // padded columns carry -1e30
+                }
+                dsum += (double)ts;
+            }
+        }
+        if (MODE == 0) {
+            unsigned long long c = cnt;
+            for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(MB_FULL, c, o);
+            if (lane == 0) reinterpret_cast<unsigned long long*>(red)[idx] = c;
+        } else {
+            for (int o = 16; o > 0; o >>= 1) dsum += __shfl_down_sync(MB_FULL, dsum, o);
+            if (lane == 0) red[idx] = dsum;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (MODE == 0) {
+        for (int i = threadIdx.x; i < DT_BINS; i += DT_THREADS)
+            if (shist[i]) atomicAdd(a.hist + i, shist[i]);
+        if (threadIdx.x == 0) {
+            unsigned long long c = 0;
+            for (int w = 0; w < 16; ++w) c += reinterpret_cast<unsigned long long*>(red)[w];
+            atomicAdd(a.below, c);
+        }
+    } else if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < 16; ++w) s += red[w];
+        a.partials[blockIdx.x] = s;
+    }
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_S), "r"(256u));
+    }
+}
+
+__device__ __forceinline__ uint32_t dt_mix(uint32_t x) {              // murmur3 finaliser
+    x ^= x >> 16; x *= 0x85ebca6bu; x ^= x >> 13; x *= 0xc2b2ae35u; x ^= x >> 16;
+    return x;
+}
+// squared distances (exact fp32) of DT_SAMPLES hashed pairs
+__global__ void __launch_bounds__(256) svgd_dist_sample_kernel(const float* __restrict__ X, int n, int d, float* out) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= DT_SAMPLES) return;
+    const uint32_t i = dt_mix(2u * p + 1u) % (uint32_t)n, j = dt_mix((2u * p + 2u) ^ 0x9e3779b9u) % (uint32_t)n;
+    const float* xi = X + (int64_t)i * d;
+    const float* xj = X + (int64_t)j * d;
+    float s = 0.f;
+    for (int k = 0; k < d; ++k) { const float t = xi[k] - xj[k]; s = fmaf(t, t, s); }
+    out[p] = s;
+}
+__global__ void svgd_dist_bracket_kernel(const double* q /*[2][3]*/, DtBracket* br, uint32_t* hist, unsigned long long* below) {
+    const int i = threadIdx.x;
+    for (int b = i; b < DT_BINS; b += blockDim.x) hist[b] = 0;
+    if (i == 0) {
+        *below = 0ull;
+        const double lo = q[0], hi = q[3];
+        const double lo_w = lo * (1.0 - 2e-3), hi_w = hi * (1.0 + 2e-3) + 1e-30;
+        // centred bins of width bw: bin b = round(D^2/bw - k0) covers [(k0 + b - 1/2) bw, (k0 + b + 1/2) bw); k0 integer so
+        // that the kernel's offset -k0 + 1.5*2^23 is exact in fp32 (bw is widened if the bracket is too narrow for that)
+        double bw = (hi_w - lo_w) / (DT_BINS - 2);
+        if (lo_w / bw > 2097152.0) bw = lo_w / 2097152.0;
+        const double k0 = floor(lo_w / bw);
+        br->lo_w = (k0 - 0.5) * bw;
+        br->bw_d2 = bw;
+        br->fallback_d2 = 0.5 * (lo + hi);
+        br->inv_bw = (float)(2.0 / bw);                                // S = -D^2/2  ->  D^2/bw = -S * (2/bw)
+        br->bin_off = (float)(12582912.0 - k0);
+    }
+}
+// 256 threads x 8 bins: block-wide exclusive scan of the histogram, then the two middle ranks are located in parallel
+__global__ void __launch_bounds__(256) svgd_dist_median_finish(const DtBracket* br, const uint32_t* hist,
+                                                               const unsigned long long* below, int n, float* h,
+                                                               unsigned long long* fallback_counter) {
+    __shared__ long long wsum[8];
+    __shared__ double dist[2];
+    __shared__ int found[2];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    uint32_t c[8];
+    long long loc = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { c[k] = hist[tid * 8 + k]; loc += c[k]; }
+    long long inc = loc;
+    for (int o = 1; o < 32; o <<= 1) { const long long t = __shfl_up_sync(MB_FULL, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) wsum[w] = inc;
+    if (tid < 2) found[tid] = 0;
+    __syncthreads();
+    long long base = inc - loc;
+    for (int k = 0; k < w; ++k) base += wsum[k];
+    const long long N2 = (long long)n * n, c_lo = (long long)*below;
+    const long long ranks[2] = {(N2 - 1) / 2 - c_lo, N2 / 2 - c_lo};    // np.median: mean of the two middle entries
+    long long cum = base;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        for (int r = 0; r < 2; ++r)
+            if (ranks[r] >= cum && ranks[r] < cum + (long long)c[k]) {
+                const double frac = ((double)(ranks[r] - cum) + 0.5) / (double)c[k];
+                dist[r] = sqrt(fmax(br->lo_w + ((double)(tid * 8 + k) + frac) * br->bw_d2, 0.0));
+                found[r] = 1;
+            }
+        cum += c[k];
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double med;
+        if (found[0] && found[1]) med = 0.5 * (dist[0] + dist[1]);
+        else { med = sqrt(fmax(br->fallback_d2, 0.0)); atomicAdd(fallback_counter, 1ull); }
+        h[0] = (float)(med / sqrt(2.0 * log((double)n)));
+    }
+}
+__global__ void __launch_bounds__(256) svgd_dist_mean_finish(const double* partials, int nblocks, int n, float* h) {
+    __shared__ double sm[256];
+    double s = 0.0;
+    for (int b = threadIdx.x; b < nblocks; b += 256) s += partials[b];
+    sm[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) h[0] = (float)(sm[0] / ((double)n * (double)n) / sqrt(2.0 * log((double)n)));
+}
+
+int mb_quantile_impl(mb_ctx* ctx, const float* v, int64_t n, const double* q_dev, double q_host, double* out3, cudaStream_t st);
+
+int mb_pairdist_bandwidth_tc(mb_ctx* ctx, const float* X, int n, int d, int mode, float* h, cudaStream_t st) {
+    MB_REQUIRE(d >= 1 && d + 4 <= TC_K, "pairwise-distance tcgen05 variant needs d <= 60");
+    MB_REQUIRE((int64_t)n * n >= 4 * (int64_t)DT_SAMPLES, "pairwise-distance tcgen05 variant needs n >= 1024 (use variant 0)");
+    const int NV = TC_K;
+    const int n_pad = ((n + TC_BM - 1) / TC_BM) * TC_BM;
+    const int tiles = n_pad / TC_BM;
+    const int grid = tiles * TC_SPLIT;
+    const size_t bx = (size_t)tiles * TC_TILE_X_BYTES, bw = (size_t)tiles * NV * 256;
+    const size_t bs = (size_t)n_pad * d * 4, ba = (size_t)n_pad * 2 * 4, bsmp = (size_t)DT_SAMPLES * 4;
+    const size_t bmisc = 1024 + DT_BINS * 4 + (size_t)grid * 8;
+    const size_t need = 1024 + bx + bw + bs + ba + bsmp + bmisc + 8192;
+    if (mb_ensure_scratch(ctx, (4u << 20) + need) != MB_OK) return MB_ERR_CUDA;
+    uint8_t* base = (uint8_t*)ctx->scratch + (4u << 20);
+    auto align = [](uint8_t* p) { return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~(uintptr_t)1023); };
+    float* mean = reinterpret_cast<float*>(align(base));
+    uint8_t* XA = align(reinterpret_cast<uint8_t*>(mean) + 256);
+    uint8_t* WT = align(XA + bx);
+    float* xs = reinterpret_cast<float*>(align(WT + bw));
+    float* saux = reinterpret_cast<float*>(align(reinterpret_cast<uint8_t*>(xs) + bs));
+    float* smp = reinterpret_cast<float*>(align(reinterpret_cast<uint8_t*>(saux) + ba));
+    uint8_t* misc = align(reinterpret_cast<uint8_t*>(smp) + bsmp);
+    double* qout = reinterpret_cast<double*>(misc);                    // [2][3]
+    DtBracket* br = reinterpret_cast<DtBracket*>(misc + 64);
+    unsigned long long* below = reinterpret_cast<unsigned long long*>(misc + 192);
+    uint32_t* hist = reinterpret_cast<uint32_t*>(misc + 1024);
+    double* partials = reinterpret_cast<double*>(misc + 1024 + DT_BINS * 4);
+    double* cpart = reinterpret_cast<double*>((char*)ctx->scratch + (3u << 20) + (64u << 10));
+    svgd_tc_colsum_kernel<<<ctx->sms, 256, 0, st>>>(X, n, d, cpart);
+    svgd_tc_colmean_kernel<<<1, 1024, 0, st>>>(cpart, ctx->sms, n, d, mean);
+    TcPrepArgs p{X, nullptr, mean, nullptr, n, d, n_pad, NV, XA, WT, xs, saux};
+    svgd_tc_rows_kernel<<<(unsigned)(((int64_t)n_pad * 8 + 255) / 256), 256, 0, st>>>(p);
+    svgd_tc_wt_kernel<<<(unsigned)(((int64_t)tiles * NV * 16 + 255) / 256), 256, 0, st>>>(p);
+    MB_CHECK_LAUNCH();
+    DtArgs a{XA, WT, n, n_pad, br, hist, below, partials};
+    const size_t smem = 1024 + TC_TILE_X_BYTES + (size_t)DT_STAGES * NV * 256 + DT_BINS * 4 + 512;
+    if (mode == 0) {
+        svgd_dist_sample_kernel<<<DT_SAMPLES / 256, 256, 0, st>>>(X, n, d, smp);
+        const double delta = 3.0 / sqrt((double)DT_SAMPLES);           // 6 sigma of the sample median's quantile level
+        int rc = mb_quantile_impl(ctx, smp, DT_SAMPLES, nullptr, 0.5 - delta, qout, st);
+        if (rc != MB_OK) return rc;
+        rc = mb_quantile_impl(ctx, smp, DT_SAMPLES, nullptr, 0.5 + delta, qout + 3, st);
+        if (rc != MB_OK) return rc;
+        svgd_dist_bracket_kernel<<<1, 256, 0, st>>>(qout, br, hist, below);
+        MB_CUDA(cudaFuncSetAttribute(svgd_dist_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        svgd_dist_tc_kernel<0><<<grid, DT_THREADS, smem, st>>>(a);
+        MB_CHECK_LAUNCH();
+        svgd_dist_median_finish<<<1, 256, 0, st>>>(br, hist, below, n, h, (unsigned long long*)(ctx->counters + MB_CNT_BW_FALLBACK));
+    } else {
+        MB_CUDA(cudaFuncSetAttribute(svgd_dist_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        svgd_dist_tc_kernel<1><<<grid, DT_THREADS, smem, st>>>(a);
+        MB_CHECK_LAUNCH();
+        svgd_dist_mean_finish<<<1, 256, 0, st>>>(partials, grid, n, h);
+    }
     MB_CHECK_LAUNCH();
     return MB_OK;
 }

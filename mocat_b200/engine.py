@@ -126,6 +126,17 @@ def target_potential_grad(target, beta, X):
     return U, G
 
 
+def logistic_potential_grad(features, labels, prior_mean, prior_pscale, beta, X, variant=0):
+    """Bayesian logistic regression (config C4): features (N, d), labels (N,), X (n, d) -> (U (n,), G (n, d))"""
+    L = _lib.get()
+    n, d = X.shape
+    U = torch.empty(n, dtype=torch.float32, device=X.device)
+    G = torch.empty((n, d), dtype=torch.float32, device=X.device)
+    L.call("mb_logistic_potential_grad", L.ctx(), ptr(features), ptr(labels), features.shape[0], d, float(prior_mean),
+           float(prior_pscale), float(beta), ptr(X), n, ptr(U), ptr(G), int(variant), stream())
+    return U, G
+
+
 class _Resampler:
     """scan -> (strata histogram) -> sorted-uniform ancestor search; every kernel is predicated on the device-side
     resample flag of the control block, so the host enqueues them unconditionally."""
@@ -407,21 +418,34 @@ class ABCEngine(_Resampler):
 
 
 # ------------------------------------------------------------------------------------------- SVGD
-def svgd_phi(X, G, bandwidth, variant=0):
+TENSOR_CORE_MIN_N = 2048
+
+
+def interaction_variant(n, d, variant=None):
+    """0 = exact fp32 SIMT kernels, 1 = tcgen05 kernels (bf16 operands, fp32 accumulation; |err| ~ 3e-3 of max|phi|).
+    None picks the tensor cores for ensembles that are large enough to fill them (n >= 2048, d <= 60)."""
+    if variant is None:
+        return 1 if (n >= TENSOR_CORE_MIN_N and d <= 60) else 0
+    return int(variant)
+
+
+def svgd_phi(X, G, bandwidth, variant=None):
     """X, G: (n, d) row-major float32; bandwidth: device float32 scalar tensor -> phi (n, d)"""
     L = _lib.get()
     n, d = X.shape
+    variant = interaction_variant(n, d, variant)
     phi = torch.empty_like(X)
     L.call("mb_svgd_phi", L.ctx(), ptr(X), ptr(G), n, d, ptr(bandwidth), ptr(phi), int(variant), stream())
     return phi
 
 
-def pairdist_bandwidth(X, mode):
+def pairdist_bandwidth(X, mode, variant=None):
     """mode 'median' | 'mean' -> device float32 (1,) tensor h = stat(D)/sqrt(2 log n)  (kernels.py:220-229)"""
     L = _lib.get()
     n, d = X.shape
     h = torch.empty(1, dtype=torch.float32, device=X.device)
-    L.call("mb_pairdist_bandwidth", L.ctx(), ptr(X), n, d, 0 if mode == "median" else 1, ptr(h), stream())
+    L.call("mb_pairdist_bandwidth", L.ctx(), ptr(X), n, d, 0 if mode == "median" else 1, ptr(h),
+           interaction_variant(n, d, variant), stream())
     return h
 
 

@@ -45,19 +45,20 @@ class Gaussian(Kernel):
         return (np.asarray(x, np.float64) - np.asarray(y, np.float64)) * self._pair(x, y, b) / b ** 2
 
 
-def _bandwidth(vals, mode):
+def _bandwidth(vals, mode, variant=None):
     torch = _torch()
     if isinstance(vals, torch.Tensor):
-        return engine.pairdist_bandwidth(vals.contiguous(), mode)        # stays on the device
+        return engine.pairdist_bandwidth(vals.contiguous(), mode, variant)   # stays on the device
     X = torch.as_tensor(np.asarray(vals, np.float32), device="cuda").contiguous()
-    return float(engine.pairdist_bandwidth(X, mode).item())
+    return float(engine.pairdist_bandwidth(X, mode, variant).item())
 
 
-def median_bandwidth_update(vals):
-    """kernels.py:220-224: median of the full n x n distance matrix / sqrt(2 log n)."""
-    return _bandwidth(vals, "median")
+def median_bandwidth_update(vals, variant=None):
+    """kernels.py:220-224: median of the full n x n distance matrix / sqrt(2 log n).
+    variant: engine.interaction_variant (None = tensor cores for n >= 2048, exact fp32 below)."""
+    return _bandwidth(vals, "median", variant)
 
 
-def mean_bandwidth_update(vals):
+def mean_bandwidth_update(vals, variant=None):
     """kernels.py:227-229."""
-    return _bandwidth(vals, "mean")
+    return _bandwidth(vals, "mean", variant)

@@ -44,3 +44,31 @@ class Rastrigin(Scenario):
 
     def _target(self):
         return models.make_target(self.lik_kind, self.dim, self.prior_mean, self.prior_std, self.prior_pscale, a=self.a)
+
+
+class LogisticRegression(Scenario):
+    """Bayesian logistic regression of config C4 (BASELINE.json configs[3]; the reference ships no such Scenario,
+    SURVEY 8d): U_lik(w) = sum_k softplus(a_k.w) - t_k a_k.w for features a_k (N x d) and labels t_k in {0,1}.
+    Evaluated for whole ensembles by mb_logistic_potential_grad (SVGD's grad_potential); it is not one of the
+    targets compiled into the SMC move kernels."""
+    name = "LogisticRegression"
+    lik_kind = _lib.LIK_NONE
+
+    def __init__(self, features, labels, **kwargs):
+        import torch
+        f = np.ascontiguousarray(np.asarray(features, np.float32))
+        t = np.ascontiguousarray(np.asarray(labels, np.float32))
+        if f.ndim != 2 or t.shape != (f.shape[0],):
+            raise _lib.MocatB200Error("LogisticRegression: features (N, d) and labels (N,) expected")
+        self.dim = int(f.shape[1])
+        self.features = torch.as_tensor(f, device="cuda")
+        self.labels = torch.as_tensor(t, device="cuda")
+        super().__init__(**kwargs)
+
+    def _target(self):                                                 # prior only (prior sampling in SVGD.startup)
+        return models.make_target(_lib.LIK_NONE, self.dim, self.prior_mean, self.prior_std, self.prior_pscale)
+
+    def _potential_grad_device(self, X, temperature):
+        from . import engine
+        pscale = 1.0 / self.prior_std if self.prior_pscale is None else self.prior_pscale
+        return engine.logistic_potential_grad(self.features, self.labels, self.prior_mean, pscale, temperature, X)

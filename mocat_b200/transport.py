@@ -229,7 +229,7 @@ class SVGD(TransportSampler):
     name = 'SVGD'
 
     def __init__(self, stepsize, max_iter=1000, kernel=None, kernel_params=None, ensemble_batchsize=None,
-                 optimiser=adagrad, keep_history=None, phi_variant=0, **optim_params):
+                 optimiser=adagrad, keep_history=None, phi_variant=None, **optim_params):
         super().__init__(max_iter=max_iter)
         from .kernels import Gaussian
         self._default_adapt = False
@@ -254,7 +254,7 @@ class SVGD(TransportSampler):
     def adapt(self, ensemble_state, extra):                             # svgd.py:109-113
         if self._default_adapt:
             from .kernels import mean_bandwidth_update
-            extra.parameters.kernel_params.bandwidth = mean_bandwidth_update(ensemble_state.value)
+            extra.parameters.kernel_params.bandwidth = mean_bandwidth_update(ensemble_state.value, self.phi_variant)
         return ensemble_state, extra
 
     def _bandwidth_tensor(self, extra, device):
@@ -274,24 +274,19 @@ class SVGD(TransportSampler):
         seed = key_to_seed(getattr(initial_extra, 'random_key', None))
         if initial_state is None or getattr(initial_state, 'value', None) is None:
             # transport/sampler.py:24-30: vmap(prior_sample); same Philox stream as the SMC init kernel
-            tgt = scenario._target()
-            tgt.kind = _lib.LIK_NONE
-            tmp = engine.SMCEngine(tgt, models.make_move(_lib.MOVE_RW, 1.0), models.make_temper(), n, seed)
             L = _lib.get()
-            import ctypes as C
-            L.call("mb_smc_init", L.ctx(), C.byref(tgt), _lib.ptr(tmp.x), tmp.ld, n, n, 1, _lib.ptr(tmp.up),
-                   _lib.ptr(tmp.lik), _lib.ptr(tmp.lw), seed, 0, _lib.ptr(tmp.ctl.t), _lib.stream())
-            X = tmp.values().contiguous()
+            X = torch.empty((n, scenario.dim), dtype=torch.float32, device=dev)
+            L.call("mb_prior_sample", L.ctx(), scenario.prior_mean, scenario.prior_std, scenario.dim, n, seed, 0,
+                   _lib.ptr(X), _lib.stream())
             initial_state = cdict()
         else:
             X = torch.as_tensor(np.asarray(initial_state.value, np.float32), device=dev).contiguous()
         st = cdict(value=X)
-        st.potential, st.grad_potential = engine.target_potential_grad(scenario._target(), scenario.temperature, X)
+        st.potential, st.grad_potential = scenario._potential_grad_device(X, scenario.temperature)
         initial_extra.parameters.kernel_params = self.parameters.kernel_params
         st, initial_extra = self.adapt(st, initial_extra)                # svgd.py:102
         initial_extra.gsq = torch.zeros_like(X)
         initial_extra.mom = torch.zeros_like(X)
-        initial_extra.target = scenario._target()
         return st, initial_extra
 
     def update(self, scenario, ensemble_state, extra):                  # svgd.py:122-146
@@ -303,7 +298,7 @@ class SVGD(TransportSampler):
         step = float(step(extra.iter)) if callable(step) else float(step)
         engine.adagrad_step(X, extra.gsq, extra.mom, phi, step, self.parameters.optim_params.get('momentum', 0.9))
         ensemble_state.potential, ensemble_state.grad_potential = \
-            engine.target_potential_grad(extra.target, scenario.temperature, X)
+            scenario._potential_grad_device(X, scenario.temperature)
         ensemble_state, extra = self.adapt(ensemble_state, extra)
         return ensemble_state, extra
 

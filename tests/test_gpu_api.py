@@ -180,3 +180,50 @@ def test_abc_gk(mocat):
     post_mean = sc.constrain(sample.value[-1][alive]).mean(0)
     assert np.abs(post_mean - truth).sum() < 6.0      # m=8 draws carry far less information than 1000 draws
     assert np.abs(post_mean[0] - truth[0]) < 1.5      # location is identified even from 8 draws
+
+
+# ------------------------------------------------------------------------------------------------ config C4
+def _logistic_data(N=257, d=11, seed=3):
+    rng = np.random.default_rng(seed)
+    A = rng.normal(size=(N, d)).astype(np.float32)
+    w_true = rng.normal(size=d)
+    t = (rng.random(N) < 1 / (1 + np.exp(-A @ w_true))).astype(np.float32)
+    return A, t
+
+
+@pytest.mark.parametrize("d", [3, 11, 50])
+def test_logistic_regression_potential_grad(mocat, d):
+    from oracle import models
+    A, t = _logistic_data(N=257, d=d)
+    sc = mocat.scenarios.LogisticRegression(A, t, prior_std=2.0)
+    ref = models.LogisticRegression(A, t)
+    prior = models.IsoGaussianPrior(d, 0.0, 2.0)
+    X = np.random.default_rng(0).normal(size=(300, d)).astype(np.float32) * 0.7
+    X[0] *= 30.0                                                            # saturated logits: stable softplus
+    ul, gl = ref.potential_and_grad(X)
+    up, gp = prior.potential_and_grad(X)
+    for beta in (1.0, 0.3):
+        U, G = sc.tempered_potential_and_grad(X, beta)
+        npt.assert_allclose(U, up + beta * ul, rtol=2e-5, atol=1e-3)
+        npt.assert_allclose(G, gp + beta * gl, rtol=2e-4, atol=2e-3)
+
+
+def test_svgd_logistic_regression_matches_oracle(mocat):
+    """C4 at test size: 40 SVGD iterations (mean bandwidth, adagrad) against the NumPy restatement"""
+    from oracle import models, philox, svgd
+    d, n = 11, 128
+    A, t = _logistic_data(N=257, d=d)
+    sc = mocat.scenarios.LogisticRegression(A, t)
+    sample = mocat.run(sc, mocat.SVGD(max_iter=40, stepsize=0.05), n=n, random_key=5)
+    x0 = philox.normals(5, np.arange(n, dtype=np.uint64), 0, philox.P_INIT, d, dtype=np.float32)
+    npt.assert_allclose(sample.value[0], x0, atol=1e-5)
+    ref, prior = models.LogisticRegression(A, t), models.IsoGaussianPrior(d, 0.0, 1.0)
+
+    def pg(x):
+        ul, gl = ref.potential_and_grad(x)
+        up, gp = prior.potential_and_grad(x)
+        return up + ul, gp + gl
+    o = svgd.SVGD(pg, x0.astype(np.float64), 0.05, bandwidth='mean', max_iter=40)
+    o.run()
+    npt.assert_allclose(sample.value[-1], o.x, atol=5e-3)
+    npt.assert_allclose(sample.bandwidth, o.h, rtol=1e-3)

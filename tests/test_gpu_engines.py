@@ -314,3 +314,30 @@ def test_svgd_phi_tcgen05_parity(E, n, d):
     # run-to-run determinism (fixed-order split-j reduction, no atomics)
     phi2 = e.svgd_phi(Xd, Gd, hd, 1).cpu().numpy()
     npt.assert_array_equal(phi, phi2)
+
+
+@pytest.mark.parametrize("n,d,scale", [(2048, 50, 1.0), (2500, 7, 0.05), (4096, 50, 0.2)])
+def test_pairdist_bandwidth_tcgen05(E, n, d, scale):
+    """tensor-core bandwidth heuristics (bf16 coordinates, one pass over the n x n matrix) against the exact ones:
+    tolerance 1e-3 relative (the per-entry rounding is ~1e-3 but moves mean and median only at second order)"""
+    import torch
+    from oracle import svgd as osvgd
+    e, m, l = E
+    X = (np.random.default_rng(n).standard_normal((n, d)) * scale + 3.0).astype(np.float32)
+    Xd = torch.as_tensor(X, device="cuda")
+    med = e.pairdist_bandwidth(Xd, "median", 1).item()
+    mean = e.pairdist_bandwidth(Xd, "mean", 1).item()
+    npt.assert_allclose(med, osvgd.median_bandwidth(X), rtol=1e-3)
+    npt.assert_allclose(mean, osvgd.mean_bandwidth(X), rtol=1e-3)
+    npt.assert_allclose(med, e.pairdist_bandwidth(Xd, "median", 0).item(), rtol=1e-3)
+    assert e.pairdist_bandwidth(Xd, "median", 1).item() == med            # integer histograms: deterministic
+    assert e.pairdist_bandwidth(Xd, "mean", 1).item() == mean
+
+
+def test_pairdist_bandwidth_tcgen05_degenerate(E):
+    """all particles equal: every distance is 0, the bracket is empty and the sample median (0) is used"""
+    import torch
+    e, m, l = E
+    Xd = torch.ones((2048, 5), device="cuda")
+    assert abs(e.pairdist_bandwidth(Xd, "median", 1).item()) < 1e-12
+    assert abs(e.pairdist_bandwidth(Xd, "mean", 1).item()) < 1e-12
