@@ -188,7 +188,8 @@ int mb_strata_count(int64_t n_total_out);
 int mb_strata_hist(mb_ctx* ctx, int64_t n_out, int64_t gid0, int B, uint64_t seed, uint32_t step,
                    const mb_control* ctl, uint32_t* hist, mb_stream_t stream);
 int mb_strata_reduce(mb_ctx* ctx, mb_comm* comm, const void* const* hist_peers, int world, int B,
-                     uint32_t* hist_out, const mb_control* ctl, mb_stream_t stream);
+                     uint32_t* hist_out, int barrier /*0: caller exchanged after its histogram kernel*/,
+                     const mb_control* ctl, mb_stream_t stream);
 int mb_ancestors_sorted(mb_ctx* ctx, const double* cdf, int64_t n, const mb_shard* sh, int mode,
                         const uint32_t* hist, uint32_t* offsets, int B, uint64_t seed, uint32_t step, int64_t gid0,
                         int64_t n_total_out, int32_t* anc, int64_t n_out, const mb_control* ctl, mb_stream_t stream);
@@ -248,6 +249,14 @@ int mb_abc_adapt(mb_ctx* ctx, const float* x, int64_t ld, int64_t n, int64_t n_t
                  double termination_alpha, int max_iter, const double* schedule, int advance_iter,
                  mb_control* ctl, mb_hist* hist, mb_stream_t stream);
 
+/* ---- conditional section of a captured step.  Every resampling kernel is predicated on the control block, so
+ *      enqueueing them unconditionally is always correct (reference: `cond(resample_bool, ...)`,
+ *      transport/smc.py:76-78, ssm/filtering.py:287-293).  While `stream` is under CUDA-graph capture, launches made
+ *      between mb_cond_begin and mb_cond_end on *body_stream go into the body of a graph IF node whose condition
+ *      (ctl->resample && !ctl->done) is evaluated on the device; outside capture *body_stream = stream. */
+int mb_cond_begin(mb_ctx* ctx, const mb_control* ctl, mb_stream_t stream, mb_stream_t* body_stream);
+int mb_cond_end(mb_ctx* ctx, mb_stream_t stream);
+
 /* ---- K8-K10: SVGD.  mb_svgd_phi replaces kernelised_grad_matrix (transport/svgd.py:18-32) with the
  *      Gaussian kernel (kernels.py:90-102); X, G, phi are row-major (n x d).  mb_pairdist_bandwidth
  *      replaces median/mean_bandwidth_update (kernels.py:220-229, utils.py:437-439); h on device.
@@ -283,7 +292,10 @@ int  mb_ipc_close(mb_ctx* ctx, void* p);
 int  mb_comm_create(mb_ctx* ctx, int rank, int world, mb_comm** out, void* handle64_host);
 int  mb_comm_connect(mb_comm* comm, const void* handles_host /*world x 64 bytes*/);
 void mb_comm_destroy(mb_comm* comm);
-int  mb_comm_allgather(mb_comm* comm, const double* in, int nd, double* out, mb_stream_t stream);
+/* ctl != NULL: skipped unless the replicated control block asks for a resampling step.  Doubles as a barrier:
+ * every rank's kernels that precede the call in stream order are complete once it returns on any rank. */
+int  mb_comm_allgather(mb_comm* comm, const double* in, int nd, double* out, const mb_control* ctl,
+                       mb_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -113,7 +113,7 @@ SIGNATURES = {
     "mb_ancestors_sharded": (C.c_int, [c_vp, c_vp, C.c_int, c_u64, c_u32, c_vp, c_i64, c_vp, c_vp]),
     "mb_strata_count": (C.c_int, [c_i64]),
     "mb_strata_hist": (C.c_int, [c_vp, c_i64, c_i64, C.c_int, c_u64, c_u32, c_vp, c_vp, c_vp]),
-    "mb_strata_reduce": (C.c_int, [c_vp, c_vp, c_vp, C.c_int, C.c_int, c_vp, c_vp, c_vp]),
+    "mb_strata_reduce": (C.c_int, [c_vp, c_vp, c_vp, C.c_int, C.c_int, c_vp, C.c_int, c_vp, c_vp]),
     "mb_ancestors_sorted": (C.c_int, [c_vp, c_vp, c_i64, c_vp, C.c_int, c_vp, c_vp, C.c_int, c_u64, c_u32, c_i64, c_i64,
                                       c_vp, c_i64, c_vp, c_vp]),
     "mb_alloc": (C.c_int, [c_vp, C.c_size_t, C.POINTER(c_vp)]),
@@ -124,11 +124,13 @@ SIGNATURES = {
     "mb_comm_create": (C.c_int, [c_vp, C.c_int, C.c_int, C.POINTER(c_vp), c_vp]),
     "mb_comm_connect": (C.c_int, [c_vp, c_vp]),
     "mb_comm_destroy": (None, [c_vp]),
-    "mb_comm_allgather": (C.c_int, [c_vp, c_vp, C.c_int, c_vp, c_vp]),
+    "mb_comm_allgather": (C.c_int, [c_vp, c_vp, C.c_int, c_vp, c_vp, c_vp]),
     "mb_weighted_moments": (C.c_int, [c_vp, c_vp, c_i64, c_i64, C.c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "mb_quantile": (C.c_int, [c_vp, c_vp, c_i64, c_d, c_vp, c_vp]),
     "mb_colstats": (C.c_int, [c_vp, c_vp, c_i64, c_i64, C.c_int, c_vp, c_vp, c_vp]),
     "mb_target_potential_grad": (C.c_int, [c_vp, C.POINTER(Target), c_d, c_vp, C.c_int, c_vp, c_vp, c_vp]),
+    "mb_cond_begin": (C.c_int, [c_vp, c_vp, c_vp, c_vp]),
+    "mb_cond_end": (C.c_int, [c_vp, c_vp]),
     "mb_prior_sample": (C.c_int, [c_vp, c_f, c_f, C.c_int, c_i64, c_u64, c_i64, c_vp, c_vp]),
     "mb_logistic_potential_grad": (C.c_int, [c_vp, c_vp, c_vp, C.c_int, C.c_int, c_f, c_f, c_d, c_vp, C.c_int, c_vp, c_vp,
                                              C.c_int, c_vp]),

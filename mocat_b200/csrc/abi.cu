@@ -44,6 +44,7 @@ extern "C" mb_ctx* mb_create(int device) {
         const uint32_t one = 1;
         ok = ok && cudaMemcpy(ctx->counters + MB_CNT_SCAN_EPOCH, &one, sizeof(one), cudaMemcpyHostToDevice) == cudaSuccess;
     }
+    ok = ok && cudaStreamCreateWithFlags(&ctx->body_stream, cudaStreamNonBlocking) == cudaSuccess;
     ctx->scratch_bytes = 8u << 20;
     ok = ok && cudaMalloc(&ctx->scratch, ctx->scratch_bytes) == cudaSuccess;
     if (!ok) {
@@ -63,6 +64,7 @@ extern "C" void mb_destroy(mb_ctx* ctx) {
     cudaFree(ctx->scan_agg);
     cudaFree(ctx->scan_incl);
     cudaFree(ctx->scratch);
+    if (ctx->body_stream) cudaStreamDestroy(ctx->body_stream);
     delete ctx;
 }
 
@@ -92,5 +94,58 @@ int mb_ensure_scan(mb_ctx* ctx, int64_t tiles) {
     MB_CUDA(cudaMemset(ctx->scan_flag, 0, sizeof(int32_t) * cap));
     ctx->scan_tiles_cap = cap;
     ctx->scan_epoch = 0;
+    return MB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Conditional section of a captured population step.  All resampling kernels are predicated on the device-side
+// flags of the control block, so launching them unconditionally is always correct; but an early-exit kernel still
+// costs a graph node (~2-3 us each, 6-9 of them per step).  While `stream` is being captured, the launches issued
+// between mb_cond_begin and mb_cond_end (on the stream returned in *body_stream) are recorded into the body of a
+// CUDA-graph conditional IF node whose condition (ctl->resample && !ctl->done) is set on the device by a one-thread
+// kernel.  Outside capture the pair is a no-op and *body_stream = stream.
+__global__ void cond_set_kernel(cudaGraphConditionalHandle h, const mb_control* ctl) {
+    cudaGraphSetConditional(h, (ctl->resample != 0 && ctl->done == 0) ? 1u : 0u);
+}
+
+extern "C" int mb_cond_begin(mb_ctx* ctx, const mb_control* ctl, mb_stream_t stream, mb_stream_t* body_stream) {
+    MB_REQUIRE(ctx && ctl && body_stream, "mb_cond_begin: bad arguments");
+    MB_REQUIRE(!ctx->cond_active, "mb_cond_begin: conditional sections do not nest");
+    cudaStream_t st = mb_s(stream);
+    *body_stream = stream;
+    cudaStreamCaptureStatus status = cudaStreamCaptureStatusNone;
+    unsigned long long id = 0;
+    cudaGraph_t graph = nullptr;
+    const cudaGraphNode_t* deps = nullptr;
+    size_t ndeps = 0;
+    MB_CUDA(cudaStreamGetCaptureInfo_v2(st, &status, &id, &graph, &deps, &ndeps));
+    if (status != cudaStreamCaptureStatusActive) return MB_OK;
+    cudaGraphConditionalHandle handle;
+    MB_CUDA(cudaGraphConditionalHandleCreate(&handle, graph, 0, cudaGraphCondAssignDefault));
+    cond_set_kernel<<<1, 1, 0, st>>>(handle, ctl);
+    MB_CHECK_LAUNCH();
+    MB_CUDA(cudaStreamGetCaptureInfo_v2(st, &status, &id, &graph, &deps, &ndeps));
+    cudaGraphNodeParams p = {};
+    p.type = cudaGraphNodeTypeConditional;
+    p.conditional.handle = handle;
+    p.conditional.type = cudaGraphCondTypeIf;
+    p.conditional.size = 1;
+    cudaGraphNode_t node;
+    MB_CUDA(cudaGraphAddNode(&node, graph, deps, ndeps, &p));
+    cudaGraph_t body = p.conditional.phGraph_out[0];
+    MB_CUDA(cudaStreamUpdateCaptureDependencies(st, &node, 1, cudaStreamSetCaptureDependencies));
+    MB_CUDA(cudaStreamBeginCaptureToGraph(ctx->body_stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
+    ctx->cond_active = 1;
+    *body_stream = (mb_stream_t)ctx->body_stream;
+    return MB_OK;
+}
+
+extern "C" int mb_cond_end(mb_ctx* ctx, mb_stream_t stream) {
+    MB_REQUIRE(ctx, "mb_cond_end: bad arguments");
+    (void)stream;
+    if (!ctx->cond_active) return MB_OK;
+    ctx->cond_active = 0;
+    cudaGraph_t g = nullptr;
+    MB_CUDA(cudaStreamEndCapture(ctx->body_stream, &g));
     return MB_OK;
 }

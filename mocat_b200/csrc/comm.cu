@@ -94,15 +94,19 @@ extern "C" void mb_comm_destroy(mb_comm* c) {
 
 const MbCommDev* mb_comm_dev(const mb_comm* c) { return &c->dev; }
 
-__global__ void comm_allgather_kernel(MbCommDev c, const double* in, int nd, double* out) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) comm_allgather(c, in, nd, out);
+__global__ void comm_allgather_kernel(MbCommDev c, const double* in, int nd, double* out, const mb_control* ctl) {
+    if (ctl && (ctl->done || !ctl->resample)) return;               // identical decision on every rank
+    comm_allgather_warp(c, in, nd, out);
 }
 
 // out[world][nd] <- in[nd] of every rank (device pointers), nd <= 6.  Every rank must call it the same
-// number of times in the same order.
-extern "C" int mb_comm_allgather(mb_comm* c, const double* in, int nd, double* out, mb_stream_t stream) {
+// number of times in the same order.  ctl != NULL: skipped unless the (replicated) control block asks for a
+// resampling step.  Kernels of this rank that precede the call in stream order are complete on every rank's
+// side of the exchange, so it doubles as the barrier before peer reads of their output.
+extern "C" int mb_comm_allgather(mb_comm* c, const double* in, int nd, double* out, const mb_control* ctl,
+                                 mb_stream_t stream) {
     MB_REQUIRE(c && in && out && nd >= 1 && nd <= MB_MAIL_DOUBLES, "mb_comm_allgather: bad arguments");
-    comm_allgather_kernel<<<1, 32, 0, mb_s(stream)>>>(c->dev, in, nd, out);
+    comm_allgather_kernel<<<1, 32, 0, mb_s(stream)>>>(c->dev, in, nd, out, ctl);
     MB_CHECK_LAUNCH();
     return MB_OK;
 }

@@ -48,6 +48,9 @@ struct mb_ctx {
     // generic scratch
     void*     scratch;
     size_t    scratch_bytes;
+    // CUDA-graph conditional capture (mb_cond_begin / mb_cond_end)
+    cudaStream_t body_stream;
+    int          cond_active;
 };
 
 #define MB_MAX_PARTIAL_BLOCKS 4096

@@ -471,14 +471,19 @@ __global__ void __launch_bounds__(MV_THREADS) pf_step_kernel(PfArgs a) {
     for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x)
         v = lse3_merge(v, Lse3{a.partials[3 * i], a.partials[3 * i + 1], a.partials[3 * i + 2]});
     v = lse3_block_reduce(v, smem);
+    if (a.has_comm) {                                                  // global LSE/ESS: exchange the rank triples
+        __shared__ double xin[3], xout[3 * MB_MAX_WORLD];
+        if (threadIdx.x == 0) { xin[0] = v.m; xin[1] = v.s1; xin[2] = v.s2; }
+        __syncthreads();
+        if (threadIdx.x < 32) comm_allgather_warp(a.comm, xin, 3, xout);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            v = lse3_empty();
+            for (int r = 0; r < a.comm.world; ++r) v = lse3_merge(v, Lse3{xout[3 * r], xout[3 * r + 1], xout[3 * r + 2]});
+        }
+    }
     if (threadIdx.x == 0) {
         *a.counter = 0;
-        if (a.has_comm) {                                              // global LSE/ESS: exchange the rank triples
-            double in[3] = {v.m, v.s1, v.s2}, out[3 * MB_MAX_WORLD];
-            comm_allgather(a.comm, in, 3, out);
-            v = lse3_empty();
-            for (int r = 0; r < a.comm.world; ++r) v = lse3_merge(v, Lse3{out[3 * r], out[3 * r + 1], out[3 * r + 2]});
-        }
         mb_control c;
         if (init) { memset(&c, 0, sizeof(c)); c.seed = a.seed; } else c = *ctl;
         const double nd = (double)a.n_total;

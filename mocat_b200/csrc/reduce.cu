@@ -217,6 +217,8 @@ temper_adapt_kernel(TemperArgs a) {
     __shared__ Lse3 smem[16];
     __shared__ double smd[32];
     __shared__ float smf[16];
+    __shared__ double xin[8], xout[5 * MB_MAX_WORLD];
+    unsigned long long xseq = a.has_comm ? *a.comm.seq : 0ull;   // read before the first grid sync; block 0 writes it back at the end
     mb_control c0 = *a.ctl;                             // read before the first grid sync (see below)
     if (c0.done) return;                                // uniform over the grid: done only changes at the end
     if (a.advance_iter && c0.resampled) {               // the move kernel resampled: weights were reset to 0,
@@ -292,22 +294,28 @@ temper_adapt_kernel(TemperArgs a) {
         grid.sync();
         Lse3 r = lse_merge_partials_fast(part, gridDim.x, smd);
         if (a.has_comm) {                                // sharded population: exchange the rank triples over NVLink
-            double* gb = a.gbuf + parity * 8;
-            if (blockIdx.x == 0 && threadIdx.x == 0) {
-                double in[6] = {r.m, r.s1, r.s2, (double)c0.alpha_fx, (double)c0.nan_count, 0.0}, out[6 * MB_MAX_WORLD];
-                comm_allgather(a.comm, in, 6, out);
-                Lse3 g = lse3_empty();
-                double afx = 0.0, nanc = 0.0;
-                for (int q = 0; q < a.comm.world; ++q) {
-                    g = lse3_merge(g, Lse3{out[6 * q], out[6 * q + 1], out[6 * q + 2]});
-                    afx += out[6 * q + 3]; nanc += out[6 * q + 4];
-                }
-                gb[0] = g.m; gb[1] = g.s1; gb[2] = g.s2; gb[3] = afx; gb[4] = nanc;
-                __threadfence();
+            // block 0 publishes, EVERY block receives for itself from the local mailbox: no second grid barrier
+            ++xseq;
+            if (threadIdx.x == 0) {
+                xin[0] = r.m; xin[1] = r.s1; xin[2] = r.s2; xin[3] = (double)c0.alpha_fx; xin[4] = (double)c0.nan_count;
             }
-            grid.sync();
-            r = Lse3{gb[0], gb[1], gb[2]};
-            g_alpha_fx = gb[3]; g_nan = gb[4];
+            __syncthreads();
+            if (threadIdx.x < 32) {
+                comm_exchange_warp(a.comm, xseq, blockIdx.x == 0, xin, 5, xout);
+                if (threadIdx.x == 0) {
+                    Lse3 g = lse3_empty();
+                    double afx = 0.0, nanc = 0.0;
+                    for (int q = 0; q < a.comm.world; ++q) {
+                        g = lse3_merge(g, Lse3{xout[5 * q], xout[5 * q + 1], xout[5 * q + 2]});
+                        afx += xout[5 * q + 3]; nanc += xout[5 * q + 4];
+                    }
+                    xin[0] = g.m; xin[1] = g.s1; xin[2] = g.s2; xin[3] = afx; xin[4] = nanc;
+                }
+            }
+            __syncthreads();
+            r = Lse3{xin[0], xin[1], xin[2]};
+            g_alpha_fx = xin[3]; g_nan = xin[4];
+            __syncthreads();
         }
         parity ^= 1;
         return r;
@@ -392,6 +400,7 @@ temper_adapt_kernel(TemperArgs a) {
         if (a.advance_iter) c.alpha_mean = g_alpha_fx / 4294967296.0 / (double)a.n_total;
         c.alpha_fx = 0;
         *a.ctl = c;
+        if (a.has_comm) *a.comm.seq = xseq;             // every block read it before the first grid sync
         if (a.hist && iter_new < MB_HIST_MAX) {
             mb_hist h;
             h.beta = c.beta; h.ess = c.ess; h.log_z = c.log_z; h.alpha_mean = c.alpha_mean; h.lse = c.lse;

@@ -609,18 +609,20 @@ __global__ void __launch_bounds__(256) strata_sum_kernel(StrataSumArgs a) {
 }
 __global__ void strata_barrier_kernel(MbCommDev c, const mb_control* ctl) {
     if (ctl && (ctl->done || !ctl->resample)) return;               // identical decision on every rank
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        double in[1] = {0.0}, out[MB_MAX_WORLD];
-        comm_allgather(c, in, 1, out);
-    }
+    __shared__ double in[1], out[MB_MAX_WORLD];
+    if (threadIdx.x == 0) in[0] = 0.0;
+    __syncwarp();
+    comm_allgather_warp(c, in, 1, out);
 }
 
 extern "C" int mb_strata_reduce(mb_ctx* ctx, mb_comm* comm, const void* const* hist_peers, int world, int B,
-                                uint32_t* hist_out, const mb_control* ctl, mb_stream_t stream) {
+                                uint32_t* hist_out, int barrier, const mb_control* ctl, mb_stream_t stream) {
     MB_REQUIRE(ctx && comm && hist_peers && hist_out && world >= 1 && world <= MB_MAX_WORLD && B >= 1,
                "mb_strata_reduce: bad arguments");
-    strata_barrier_kernel<<<1, 32, 0, mb_s(stream)>>>(*mb_comm_dev(comm), ctl);
-    MB_CHECK_LAUNCH();
+    if (barrier) {                                   // 0: the caller exchanged (mb_comm_allgather) after its histogram kernel
+        strata_barrier_kernel<<<1, 32, 0, mb_s(stream)>>>(*mb_comm_dev(comm), ctl);
+        MB_CHECK_LAUNCH();
+    }
     StrataSumArgs a{};
     for (int r = 0; r < world; ++r) a.peers[r] = (const uint32_t*)hist_peers[r];
     a.world = world; a.B = B; a.out = hist_out; a.ctl = ctl;

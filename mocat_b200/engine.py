@@ -149,6 +149,17 @@ class _Resampler:
         self.hist = torch.zeros(self.B, dtype=torch.int32, device=dev)
         self.offsets = torch.zeros(self.B + 1, dtype=torch.int32, device=dev)
 
+    def _cond_begin(self, st):
+        """open the graph-conditional section (no-op outside capture); returns the stream to launch the body on"""
+        if os.environ.get("MOCAT_B200_COND", "0") != "1":      # measured: the IF node costs more than 6 early-exit kernels
+            return st
+        body = C.c_void_p()
+        self.L.call("mb_cond_begin", self.ctx, ptr(self.ctl.t), st, C.byref(body))
+        return body
+
+    def _cond_end(self, st):
+        self.L.call("mb_cond_end", self.ctx, st)
+
     def _resample_kernels(self, st):
         L = self.L
         L.call("mb_cumsum_lw", self.ctx, ptr(self.lw), self.n, ptr(self.ctl.t), 0, ptr(self.cdf), st)
@@ -216,7 +227,11 @@ class SMCEngine(_Resampler):
         st = stream()
         if events:
             events[0].record()
-        self._resample_kernels(st)                                  # RNG step comes from ctl->iter + 1 on the device
+        body = self._cond_begin(st)                                 # captured: body of a device-evaluated IF node
+        try:
+            self._resample_kernels(body)                            # RNG step comes from ctl->iter + 1 on the device
+        finally:
+            self._cond_end(st)
         if events:
             events[1].record()
         src, dst = self.xbuf[self.cur], self.xbuf[self.cur ^ 1]
@@ -257,7 +272,7 @@ class SMCEngine(_Resampler):
             side = self._side_stream()
             side.wait_stream(cur)
             with torch.cuda.stream(side):
-                g.capture_begin()
+                g.capture_begin(capture_error_mode="thread_local")
                 try:
                     self._enqueue()
                 finally:

@@ -102,7 +102,7 @@ class ShardContext:
         return t, peers
 
     def allgather(self, src, nd, dst):
-        self.L.call("mb_comm_allgather", self.comm, _lib.ptr(src), int(nd), _lib.ptr(dst), _lib.stream())
+        self.L.call("mb_comm_allgather", self.comm, _lib.ptr(src), int(nd), _lib.ptr(dst), None, _lib.stream())
 
 
 def _make_shard(sc, n_local, x_peers, cdf_peers, totals):
@@ -127,15 +127,18 @@ def _sharded_alloc(eng, sc):
 
 
 def _sharded_resample_kernels(eng, sc, st):
-    """scan (rank-relative, exact) -> weight totals exchange -> [strata histogram + reduction over ranks] ->
-    global sorted-uniform ancestor search over the peer-mapped CDFs"""
+    """scan (rank-relative, exact) + local strata histogram -> ONE exchange (weight totals; also the barrier before
+    the peers read each other's histograms) -> histogram sum over ranks -> global sorted-uniform ancestor search over
+    the peer-mapped CDFs.  Every launch is predicated on the replicated control block."""
     L, ptr = eng.L, _lib.ptr
     ctl = ptr(eng.ctl.t)
+    multinomial = eng.resampling == _lib.RESAMPLE_MULTINOMIAL
     L.call("mb_cumsum_lw", eng.ctx, ptr(eng.lw), eng.n, ctl, 2, ptr(eng.cdf), st)
-    sc.allgather(eng.cdf[eng.n - 1:], 1, eng.totals)
-    if eng.resampling == _lib.RESAMPLE_MULTINOMIAL:
+    if multinomial:
         L.call("mb_strata_hist", eng.ctx, eng.n, eng.gid0, eng.B, eng.seed, 0, ctl, ptr(eng.hist_local), st)
-        L.call("mb_strata_reduce", eng.ctx, sc.comm, eng.hist_peers, sc.world, eng.B, ptr(eng.hist), ctl, st)
+    L.call("mb_comm_allgather", sc.comm, ptr(eng.cdf[eng.n - 1:]), 1, ptr(eng.totals), ctl, st)
+    if multinomial:
+        L.call("mb_strata_reduce", eng.ctx, sc.comm, eng.hist_peers, sc.world, eng.B, ptr(eng.hist), 0, ctl, st)
     L.call("mb_ancestors_sorted", eng.ctx, None, eng.n_total, C.byref(eng.shards[eng.cur]), eng.resampling,
            ptr(eng.hist), ptr(eng.offsets), eng.B, eng.seed, 0, eng.gid0, eng.n_total, ptr(eng.anc), eng.n, ctl, st)
 
@@ -151,7 +154,6 @@ def ShardedSMCEngine(sc, target, move, temper, n_local, seed, resampling=_lib.RE
                              n_total=sc.world * n_local, schedule=schedule)
             self.sc = sc
             self.comm = sc.comm
-            self.use_graphs = False
             _sharded_alloc(self, sc)
 
         def _shard_ref(self):
@@ -162,7 +164,11 @@ def ShardedSMCEngine(sc, target, move, temper, n_local, seed, resampling=_lib.RE
             if events:
                 events[0].record()
             L, ptr = self.L, _lib.ptr
-            _sharded_resample_kernels(self, sc, st)
+            body = self._cond_begin(st)
+            try:
+                _sharded_resample_kernels(self, sc, body)
+            finally:
+                self._cond_end(st)
             if events:
                 events[1].record()
             src, dst = self.xbuf[self.cur], self.xbuf[self.cur ^ 1]
