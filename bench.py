@@ -198,9 +198,16 @@ def main():
     clocks.start()
     t_w = time.perf_counter()
     nw = 0
-    while nw < max(a.warmup, 3) or time.perf_counter() - t_w < 1.0:     # >= 1 s of warm-up so clocks settle
-        one_step(False)
-        nw += 1
+    while True:                                                         # >= 1 s of warm-up so clocks settle
+        for _ in range(max(a.warmup, 3) if nw == 0 else 100):
+            one_step(False)
+            nw += 1
+        # the step count must be IDENTICAL on every rank (each step is a cross-GPU exchange): decide collectively
+        el = torch.tensor([time.perf_counter() - t_w], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(el, op=dist.ReduceOp.MIN)
+        if float(el.item()) >= 1.0:
+            break
     sync()
     all_marks = []
     t_wall0 = time.perf_counter()
@@ -292,7 +299,7 @@ def main():
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "n_per_gpu": n, "dim": D, "parallelism": f"one population of {world * n} particles sharded over {world} GPUs "
                    "(peer-memory mailbox exchange + NVLink ancestor gather)" if world > 1 else "single GPU", "l2": "flushed between timed steps (512 MiB memset)",
-                   "launch": "one CUDA-graph replay per step (4 kernels)" if world == 1 else "plain launches (5 kernels)",
+                   "launch": "one CUDA-graph replay per step",
                    "state_bytes_resident": int(sum(t.numel() * t.element_size() for t in
                                                    (eng.xbuf[0], eng.xbuf[1], eng.lw, eng.lik, eng.up, eng.alpha,
                                                     eng.cdf, eng.anc)))},
@@ -303,7 +310,8 @@ def main():
                      "note": "n=1e6: the whole state (68 MB) is smaller than L2 and every kernel is "
                              "latency/issue bound, not HBM bound; see DESIGN.md for the n=1e8 figures"},
         "kernels": kernels,
-        "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": 4 * a.steps, "clocks": clk,
+        "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": (7 if world == 1 else 9) * a.steps,   # kernels per step: scan, strata hist, 2 x offsets scan, ancestors, move, temper (+ exchange, histogram sum when sharded)
+        "clocks": clk,
         "wall_s_timed_region": t_wall,
     }
     print(json.dumps(line), flush=True)
