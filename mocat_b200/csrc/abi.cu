@@ -45,6 +45,8 @@ extern "C" mb_ctx* mb_create(int device) {
         ok = ok && cudaMemcpy(ctx->counters + MB_CNT_SCAN_EPOCH, &one, sizeof(one), cudaMemcpyHostToDevice) == cudaSuccess;
     }
     ok = ok && cudaStreamCreateWithFlags(&ctx->body_stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaMalloc(&ctx->ll_slots, sizeof(unsigned long long) * (2 * MB_LL_BLOCKS * 8 + 8)) == cudaSuccess;
+    ok = ok && cudaMemset(ctx->ll_slots, 0, sizeof(unsigned long long) * (2 * MB_LL_BLOCKS * 8 + 8)) == cudaSuccess;
     ctx->scratch_bytes = 8u << 20;
     ok = ok && cudaMalloc(&ctx->scratch, ctx->scratch_bytes) == cudaSuccess;
     if (!ok) {
@@ -64,6 +66,7 @@ extern "C" void mb_destroy(mb_ctx* ctx) {
     cudaFree(ctx->scan_agg);
     cudaFree(ctx->scan_incl);
     cudaFree(ctx->scratch);
+    cudaFree(ctx->ll_slots);
     if (ctx->body_stream) cudaStreamDestroy(ctx->body_stream);
     delete ctx;
 }

@@ -48,12 +48,15 @@ struct mb_ctx {
     // generic scratch
     void*     scratch;
     size_t    scratch_bytes;
+    // intra-GPU flag-in-data exchange of the resident tempering kernel: [2][MB_LL_BLOCKS][8] words + sequence counter
+    unsigned long long* ll_slots;
     // CUDA-graph conditional capture (mb_cond_begin / mb_cond_end)
     cudaStream_t body_stream;
     int          cond_active;
 };
 
 #define MB_MAX_PARTIAL_BLOCKS 4096
+#define MB_LL_BLOCKS 320          // >= 2 resident blocks x 148 SMs
 // counters layout
 #define MB_CNT_REDUCE   0    // last-block-done counter of the reduction kernels
 #define MB_CNT_SCAN_TILE 1   // dynamic tile id of the scan

@@ -167,9 +167,10 @@ struct TemperArgs {
     double* partials;      // [2][MB_MAX_PARTIAL_BLOCKS][3]
     MbCommDev comm; int has_comm;
     double* gbuf;          // [2][8] global triple broadcast (sharded)
+    unsigned long long* ll;   // resident variant: [2][MB_LL_BLOCKS][8] flag-in-data slots, then the sequence counter
 };
 
-#define TP_R 2             // float4 (lw, lik) pairs kept per thread in the resident variant
+#define TP_R 4             // float4 (lw, lik) pairs kept per thread in the resident variant
 
 __device__ __forceinline__ double lse3_log_ess(const Lse3& r) {
     const double mm = (r.m == -INFINITY || r.m == INFINITY) ? 0.0 : r.m;
@@ -210,15 +211,78 @@ __device__ __forceinline__ Lse3 lse_merge_partials_fast(const double* __restrict
 
 #define TP_THREADS_RES 512
 
+__device__ __forceinline__ void st_gpu_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_gpu_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// merge of one triple per lane (empty lanes: lse3_empty()); the butterfly is symmetric, so every lane ends with the
+// same bits.  NaN maxima propagate through exp().
+__device__ __forceinline__ Lse3 lse3_warp_merge(Lse3 v) {
+    double M = v.m;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) M = fmax(M, shfl_xor_d(M, o));
+    double s1 = 0.0, s2 = 0.0;
+    if (v.m != -INFINITY) { const double f = exp(v.m - M); s1 = v.s1 * f; s2 = v.s2 * f * f; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { s1 += shfl_xor_d(s1, o); s2 += shfl_xor_d(s2, o); }
+    return Lse3{M, s1, s2};
+}
+
+// merge of <= MB_LL_BLOCKS triples held in shared memory with ONE block barrier: every warp finds the global max
+// redundantly (no barrier), thread t rescales triple t (one fp64 exp), warp butterflies, then every thread adds the
+// (<= 10) warp partials in a fixed order.  `sm` needs 2 * 16 doubles.
+__device__ __forceinline__ Lse3 lse_merge_smem_once(const double* sp, int count, double* sm) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double M = -INFINITY;
+    for (int i = lane; i < count; i += 32) M = fmax(M, sp[3 * i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) M = fmax(M, shfl_xor_d(M, o));
+    const int nwu = (count + 31) >> 5;                  // warps that own triples
+    if (warp < nwu) {
+        double s1 = 0.0, s2 = 0.0;
+        const int i = threadIdx.x;
+        if (i < count) {
+            const double mi = sp[3 * i];
+            if (mi != -INFINITY) { const double f = exp(mi - M); s1 = sp[3 * i + 1] * f; s2 = sp[3 * i + 2] * f * f; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { s1 += shfl_xor_d(s1, o); s2 += shfl_xor_d(s2, o); }
+        if (lane == 0) { sm[warp] = s1; sm[16 + warp] = s2; }
+    }
+    __syncthreads();
+    double S1 = 0.0, S2 = 0.0;
+    for (int w = 0; w < nwu; ++w) { S1 += sm[w]; S2 += sm[16 + w]; }
+    return Lse3{M, S1, S2};
+}
+
+// phase timing of the resident kernel (debug builds only: nvcc -DMB_TEMPER_TRACE): block 0 accumulates globaltimer
+// deltas per phase and reports them through the history record (lse <- phase ns; see scratch/temper_trace.py)
+#ifdef MB_TEMPER_TRACE
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define TP_TRACE(k) do { const unsigned long long _t = gtimer(); tr_acc[k] += (double)(_t - tr_last); tr_last = _t; } while (0)
+#else
+#define TP_TRACE(k) do { } while (0)
+#endif
+
 template <bool RESIDENT>
-__global__ void __launch_bounds__(RESIDENT ? TP_THREADS_RES : RED_THREADS, 2)
+__global__ void __launch_bounds__(RESIDENT ? TP_THREADS_RES : RED_THREADS, RESIDENT ? 1 : 2)
 temper_adapt_kernel(TemperArgs a) {
     cg::grid_group grid = cg::this_grid();
     __shared__ Lse3 smem[16];
     __shared__ double smd[32];
     __shared__ float smf[16];
     __shared__ double xin[8], xout[5 * MB_MAX_WORLD];
+    __shared__ double sparts[RESIDENT ? 3 * MB_LL_BLOCKS : 1];
+    unsigned long long lseq = RESIDENT ? a.ll[2 * MB_LL_BLOCKS * 8] : 0ull;   // block 0 writes it back at the end
     unsigned long long xseq = a.has_comm ? *a.comm.seq : 0ull;   // read before the first grid sync; block 0 writes it back at the end
+#ifdef MB_TEMPER_TRACE
+    double tr_acc[6] = {0, 0, 0, 0, 0, 0};
+    unsigned long long tr_last = gtimer();
+#endif
     mb_control c0 = *a.ctl;                             // read before the first grid sync (see below)
     if (c0.done) return;                                // uniform over the grid: done only changes at the end
     if (a.advance_iter && c0.resampled) {               // the move kernel resampled: weights were reset to 0,
@@ -251,11 +315,14 @@ temper_adapt_kernel(TemperArgs a) {
     }
 
     auto evaluate = [&](double b) -> Lse3 {
+        TP_TRACE(0);
         const float dbeta = (float)(b - beta);
         Lse3 blk;
         if (RESIDENT) {
-            // registers hold the data: block max first, then ONE exp per particle, no rescaling merges
-            const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+            // registers hold the data: ONE exp per particle relative to the WARP max; the 16 warp triples meet in
+            // shared memory (one block barrier) and warp 0 merges them with a butterfly -- only warp 0 needs the
+            // block triple, it is the one that publishes it
+            const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
             float w[4 * TP_R];
 #pragma unroll
             for (int r = 0; r < TP_R; ++r) {
@@ -267,32 +334,59 @@ temper_adapt_kernel(TemperArgs a) {
             for (int k = 0; k < 4 * TP_R; ++k) tm = fmaxf(tm, w[k]);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) tm = fmaxf(tm, __shfl_xor_sync(MB_FULL, tm, o));
-            if (lane == 0) smf[warp] = tm;
-            __syncthreads();
-            float Mb = smf[0];
-            for (int q = 1; q < nw; ++q) Mb = fmaxf(Mb, smf[q]);
-            const float mm = (Mb == -INFINITY) ? 0.f : Mb;
+            const float mm = (tm == -INFINITY) ? 0.f : tm;
             float p1 = 0.f, p2 = 0.f;
 #pragma unroll
             for (int k = 0; k < 4 * TP_R; ++k) { const float e = __expf(w[k] - mm); p1 += e; p2 = fmaf(e, e, p2); }
             double s1 = (double)p1, s2 = (double)p2;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) { s1 += shfl_xor_d(s1, o); s2 += shfl_xor_d(s2, o); }
-            if (lane == 0) { smd[warp] = s1; smd[16 + warp] = s2; }
+            if (lane == 0) { sparts[3 * warp] = (double)tm; sparts[3 * warp + 1] = s1; sparts[3 * warp + 2] = s2; }
             __syncthreads();
-            double S1 = 0.0, S2 = 0.0;
-            for (int q = 0; q < nw; ++q) { S1 += smd[q]; S2 += smd[16 + q]; }
-            __syncthreads();
-            blk = Lse3{(double)Mb, S1, S2};
+            blk = lse3_empty();
+            if (warp == 0) {
+                const int nw = blockDim.x >> 5;
+                blk = lse3_warp_merge(lane < nw ? Lse3{sparts[3 * lane], sparts[3 * lane + 1], sparts[3 * lane + 2]} : lse3_empty());
+            }
+            __syncthreads();                            // sparts is reused by the gather below
         } else {
             blk = lse_block_pass(a.lw, a.lik, dbeta, a.n, smem);
         }
-        double* part = a.partials + (size_t)parity * 3 * MB_MAX_PARTIAL_BLOCKS;
-        if (threadIdx.x == 0) {
-            part[3 * blockIdx.x] = blk.m; part[3 * blockIdx.x + 1] = blk.s1; part[3 * blockIdx.x + 2] = blk.s2;
+        Lse3 r;
+        if (RESIDENT) {
+            // no grid-wide barrier: every block publishes its triple as six self-validating words {32 data bits,
+            // 32-bit sequence flag} and every block gathers all of them (spinning on L2) -- barrier and data
+            // exchange are the same memory operation.  Two parities: a slot is rewritten two evaluations later, which
+            // its owner cannot reach before every block has gathered this one.  (A two-level gather through group
+            // leaders was measured slower: the extra hop costs more than the polling traffic it saves.)
+            TP_TRACE(1);
+            ++lseq;
+            const unsigned long long flag = (lseq & 0xffffffffull) << 32;
+            unsigned long long* base = a.ll + (size_t)(lseq & 1ull) * MB_LL_BLOCKS * 8;
+            if (threadIdx.x < 6) {
+                const double v = threadIdx.x < 2 ? blk.m : (threadIdx.x < 4 ? blk.s1 : blk.s2);
+                const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+                const unsigned long long half = (threadIdx.x & 1) ? (bits >> 32) : (bits & 0xffffffffull);
+                st_gpu_u64(base + (size_t)blockIdx.x * 8 + threadIdx.x, flag | half);
+            }
+            for (int idx = threadIdx.x; idx < (int)gridDim.x * 6; idx += blockDim.x) {
+                const int b = idx / 6, k = idx - b * 6;
+                unsigned long long v;
+                do { v = ld_gpu_u64(base + (size_t)b * 8 + k); } while ((v & 0xffffffff00000000ull) != flag);
+                reinterpret_cast<unsigned int*>(sparts)[idx] = (unsigned int)(v & 0xffffffffull);
+            }
+            __syncthreads();
+            TP_TRACE(2);
+            r = lse_merge_smem_once(sparts, gridDim.x, smd);
+            TP_TRACE(3);
+        } else {
+            double* part = a.partials + (size_t)parity * 3 * MB_MAX_PARTIAL_BLOCKS;
+            if (threadIdx.x == 0) {
+                part[3 * blockIdx.x] = blk.m; part[3 * blockIdx.x + 1] = blk.s1; part[3 * blockIdx.x + 2] = blk.s2;
+            }
+            grid.sync();
+            r = lse_merge_partials_fast(part, gridDim.x, smd);
         }
-        grid.sync();
-        Lse3 r = lse_merge_partials_fast(part, gridDim.x, smd);
         if (a.has_comm) {                                // sharded population: exchange the rank triples over NVLink
             // block 0 publishes, EVERY block receives for itself from the local mailbox: no second grid barrier
             ++xseq;
@@ -384,6 +478,7 @@ temper_adapt_kernel(TemperArgs a) {
         }
     }
 
+    TP_TRACE(4);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         mb_control c = *a.ctl;                           // unchanged since the start of the kernel
         c.lse = c0.lse;
@@ -400,11 +495,15 @@ temper_adapt_kernel(TemperArgs a) {
         if (a.advance_iter) c.alpha_mean = g_alpha_fx / 4294967296.0 / (double)a.n_total;
         c.alpha_fx = 0;
         *a.ctl = c;
-        if (a.has_comm) *a.comm.seq = xseq;             // every block read it before the first grid sync
+        if (a.has_comm) *a.comm.seq = xseq;             // every block read it before the first exchange
+        if (RESIDENT) a.ll[2 * MB_LL_BLOCKS * 8] = lseq;
         if (a.hist && iter_new < MB_HIST_MAX) {
             mb_hist h;
             h.beta = c.beta; h.ess = c.ess; h.log_z = c.log_z; h.alpha_mean = c.alpha_mean; h.lse = c.lse;
             h.resampled = c.resampled; h.search_iters = it;
+#ifdef MB_TEMPER_TRACE
+            h.beta = tr_acc[0]; h.ess = tr_acc[1]; h.log_z = tr_acc[2]; h.alpha_mean = tr_acc[3]; h.lse = tr_acc[4];
+#endif
             a.hist[iter_new] = h;
         }
     }
@@ -423,7 +522,7 @@ extern "C" int mb_temper_adapt(mb_ctx* ctx, float* lw, const float* lik, int64_t
     const int64_t need_res = (n + (int64_t)TP_THREADS_RES * 4 * TP_R - 1) / ((int64_t)TP_THREADS_RES * 4 * TP_R);
     const int64_t need = (n + (int64_t)RED_THREADS * 4 * TP_R - 1) / ((int64_t)RED_THREADS * 4 * TP_R);
     int64_t cap_res = (int64_t)bps[1] * ctx->sms;
-    if (cap_res > MB_MAX_PARTIAL_BLOCKS) cap_res = MB_MAX_PARTIAL_BLOCKS;
+    if (cap_res > MB_LL_BLOCKS) cap_res = MB_LL_BLOCKS;
     const bool resident = (n % 4 == 0) && (((uintptr_t)lw & 15) == 0) && (((uintptr_t)lik & 15) == 0) && need_res <= cap_res;
     int64_t grid = resident ? need_res : (int64_t)bps[0] * ctx->sms;
     if (!resident && grid > need) grid = need;
@@ -431,6 +530,7 @@ extern "C" int mb_temper_adapt(mb_ctx* ctx, float* lw, const float* lik, int64_t
     if (grid < 1) grid = 1;
     TemperArgs args{lw, lik, n, *prm, advance_iter, nan_denominator, n_total > 0 ? n_total : n, ctl, hist, ctx->partials};
     args.has_comm = 0;
+    args.ll = ctx->ll_slots;
     args.gbuf = ctx->partials + 2 * 3 * MB_MAX_PARTIAL_BLOCKS;          // 64 spare doubles after the partials
     if (comm) { args.comm = *mb_comm_dev(comm); args.has_comm = args.comm.world > 1; }
     void* kargs[] = {&args};
