@@ -331,29 +331,50 @@ __device__ __forceinline__ void lorenz_rhs(const float (&x)[D], float forcing, f
     }
 }
 
-// one classical RK4 step of size h (device definition of the L96 flow)
 template <int D>
-__device__ __forceinline__ void lorenz_rk4(float (&x)[D], float h, float forcing) {
-    float k[D], xt[D], acc[D];
-    lorenz_rhs<D>(x, forcing, k);
-#pragma unroll
-    for (int j = 0; j < D; ++j) { acc[j] = k[j]; xt[j] = fmaf(0.5f * h, k[j], x[j]); }
-    lorenz_rhs<D>(xt, forcing, k);
-#pragma unroll
-    for (int j = 0; j < D; ++j) { acc[j] = fmaf(2.f, k[j], acc[j]); xt[j] = fmaf(0.5f * h, k[j], x[j]); }
-    lorenz_rhs<D>(xt, forcing, k);
-#pragma unroll
-    for (int j = 0; j < D; ++j) { acc[j] = fmaf(2.f, k[j], acc[j]); xt[j] = fmaf(h, k[j], x[j]); }
-    lorenz_rhs<D>(xt, forcing, k);
-#pragma unroll
-    for (int j = 0; j < D; ++j) x[j] = fmaf(h * (1.f / 6.f), acc[j] + k[j], x[j]);
+__device__ __forceinline__ float lorenz_rhs1(const float (&x)[D], float forcing, int j) {
+    return fmaf(x[(j + 1) % D] - x[(j + D - 2) % D], x[(j + D - 1) % D], forcing - x[j]);   // lorenz96.py:18-19
 }
 
+// one classical RK4 step of size h (device definition of the L96 flow).  Written stage by stage with a
+// scalar slope so that only x, the slope accumulator and two stage states are live (register budget: 128/thread).
+template <int D>
+__device__ __forceinline__ void lorenz_rk4(float (&x)[D], float h, float forcing) {
+    float acc[D], xa[D], xb[D];
+#pragma unroll
+    for (int j = 0; j < D; ++j) { const float k = lorenz_rhs1<D>(x, forcing, j); acc[j] = k; xa[j] = fmaf(0.5f * h, k, x[j]); }
+#pragma unroll
+    for (int j = 0; j < D; ++j) { const float k = lorenz_rhs1<D>(xa, forcing, j); acc[j] = fmaf(2.f, k, acc[j]); xb[j] = fmaf(0.5f * h, k, x[j]); }
+#pragma unroll
+    for (int j = 0; j < D; ++j) { const float k = lorenz_rhs1<D>(xb, forcing, j); acc[j] = fmaf(2.f, k, acc[j]); xa[j] = fmaf(h, k, x[j]); }
+#pragma unroll
+    for (int j = 0; j < D; ++j) { const float k = lorenz_rhs1<D>(xa, forcing, j); x[j] = fmaf(h * (1.f / 6.f), acc[j] + k, x[j]); }
+}
+
+// normals of one particle, produced four at a time where they are consumed (keeps them out of the register budget
+// of the Lorenz-96 flow): slot s holds normals 4s..4s+3 (rng.cuh)
+struct PfNormals {
+    uint64_t seed, gid; uint32_t step, purpose;
+    __device__ __forceinline__ void slot(int s, float (&z4)[4]) const {
+        const Philox4 r = philox_raw(seed, gid, step, purpose, (uint32_t)s);
+        box_muller(r.x, r.y, z4[0], z4[1]);
+        box_muller(r.z, r.w, z4[2], z4[3]);
+    }
+};
+
 template <int KIND, int D>
-__device__ __forceinline__ float pf_particle(const mb_ssm& m, float (&x)[D], const float (&z)[D], const float* ys,
+__device__ __forceinline__ float pf_particle(const mb_ssm& m, float (&x)[D], const PfNormals& rng, const float* ys,
                                              bool init) {
     // returns the log-weight increment -likelihood_potential(x', y)
     if (KIND == MB_SSM_LINEAR_GAUSSIAN) {
+        float z[D];
+#pragma unroll
+        for (int s = 0; s < (D + 3) / 4; ++s) {
+            float z4[4];
+            rng.slot(s, z4);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) if (4 * s + c < D) z[4 * s + c] = z4[c];
+        }
         float xn[D];
         if (init) {                                     // linear_gaussian.py:45-50: L0 z + m0
 #pragma unroll
@@ -394,28 +415,34 @@ __device__ __forceinline__ float pf_particle(const mb_ssm& m, float (&x)[D], con
         }
         return -(quad + m.lik_const);
     } else {                                            // Lorenz-96, diagonal noise, H = I
-        if (init) {
-#pragma unroll
-            for (int j = 0; j < D; ++j) x[j] = fmaf(m.init_std, z[j], m.init_mean);
-        } else {
+        if (!init) {
             const float h = m.dt / (float)m.substeps;
             for (int s = 0; s < m.substeps; ++s) lorenz_rk4<D>(x, h, m.forcing);
-#pragma unroll
-            for (int j = 0; j < D; ++j) x[j] = fmaf(m.q_std, z[j], x[j]);      // nonlinear_gaussian.py:112-113
         }
         const float ir = 1.f / m.r_std;
         float quad = 0.f;
 #pragma unroll
-        for (int j = 0; j < D; ++j) {
-            const float r = (ys[j] - x[j]) * ir;
-            quad = fmaf(0.5f * r, r, quad);
+        for (int s = 0; s < (D + 3) / 4; ++s) {         // noise and likelihood, four coordinates per Philox call
+            float z4[4];
+            rng.slot(s, z4);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int j = 4 * s + c;
+                if (j < D) {
+                    x[j] = init ? fmaf(m.init_std, z4[c], m.init_mean)
+                                : fmaf(m.q_std, z4[c], x[j]);                  // nonlinear_gaussian.py:112-113
+                    const float r = (ys[j] - x[j]) * ir;
+                    quad = fmaf(0.5f * r, r, quad);
+                }
+            }
         }
         return -(quad + m.lik_const);
     }
 }
 
+#define PF_THREADS(D) ((D) >= 32 ? 128 : MV_THREADS)
 template <int KIND, int D>
-__global__ void __launch_bounds__(MV_THREADS) pf_step_kernel(PfArgs a) {
+__global__ void __launch_bounds__(PF_THREADS(D), (D) >= 32 ? 4 : 1) pf_step_kernel(PfArgs a) {
     mb_control* ctl = a.ctl;
     const bool init = a.init != 0;
     if (!init && ctl->done) return;
@@ -437,13 +464,13 @@ __global__ void __launch_bounds__(MV_THREADS) pf_step_kernel(PfArgs a) {
             src -= (int64_t)owner * a.sh.n_local;
             xb = a.sh.x_peers[owner];
         }
-        float x[D], z[D];
+        float x[D];
         if (!init) {
 #pragma unroll
             for (int k = 0; k < D; ++k) x[k] = __ldg(xb + (int64_t)k * a.ld + src);
         }
-        philox_normals<D>(z, a.seed, (uint64_t)(a.gid0 + i), a.t, init ? MB_P_INIT : MB_P_MOVE, 0u);
-        const float incr = pf_particle<KIND, D>(a.ssm, x, z, ys, init);
+        const PfNormals rng{a.seed, (uint64_t)(a.gid0 + i), a.t, init ? MB_P_INIT : MB_P_MOVE};
+        const float incr = pf_particle<KIND, D>(a.ssm, x, rng, ys, init);
 #pragma unroll
         for (int k = 0; k < D; ++k) a.x_out[(int64_t)k * a.ld + i] = x[k];
         const float w = ((init || resample) ? 0.f : a.lw[i]) + incr;           // filtering.py:292,303
@@ -504,16 +531,19 @@ __global__ void __launch_bounds__(MV_THREADS) pf_step_kernel(PfArgs a) {
     }
 }
 
-static int pf_dispatch(mb_ctx* ctx, PfArgs& a, cudaStream_t st) {
-    int64_t grid = (a.n + MV_THREADS - 1) / MV_THREADS;
-    int64_t cap = (int64_t)ctx->sms * 8;
+static int64_t pf_grid(mb_ctx* ctx, int64_t n, int threads) {
+    int64_t grid = (n + threads - 1) / threads;
+    int64_t cap = (int64_t)ctx->sms * (threads == 128 ? 16 : 8);
     if (cap > MB_MAX_PARTIAL_BLOCKS) cap = MB_MAX_PARTIAL_BLOCKS;
-    if (grid > cap) grid = cap;
+    return grid > cap ? cap : grid;
+}
+
+static int pf_dispatch(mb_ctx* ctx, PfArgs& a, cudaStream_t st) {
     a.partials = ctx->partials;
     a.counter = ctx->counters + MB_CNT_MOVE;
     const int d = a.ssm.dim;
-#define PF_LG(DD) if (a.ssm.kind == MB_SSM_LINEAR_GAUSSIAN && d == DD) { pf_step_kernel<MB_SSM_LINEAR_GAUSSIAN, DD><<<(unsigned)grid, MV_THREADS, 0, st>>>(a); MB_CHECK_LAUNCH(); return MB_OK; }
-#define PF_L96(DD) if (a.ssm.kind == MB_SSM_LORENZ96 && d == DD) { pf_step_kernel<MB_SSM_LORENZ96, DD><<<(unsigned)grid, MV_THREADS, 0, st>>>(a); MB_CHECK_LAUNCH(); return MB_OK; }
+#define PF_LG(DD) if (a.ssm.kind == MB_SSM_LINEAR_GAUSSIAN && d == DD) { pf_step_kernel<MB_SSM_LINEAR_GAUSSIAN, DD><<<(unsigned)pf_grid(ctx, a.n, PF_THREADS(DD)), PF_THREADS(DD), 0, st>>>(a); MB_CHECK_LAUNCH(); return MB_OK; }
+#define PF_L96(DD) if (a.ssm.kind == MB_SSM_LORENZ96 && d == DD) { pf_step_kernel<MB_SSM_LORENZ96, DD><<<(unsigned)pf_grid(ctx, a.n, PF_THREADS(DD)), PF_THREADS(DD), 0, st>>>(a); MB_CHECK_LAUNCH(); return MB_OK; }
     PF_LG(1) PF_LG(2) PF_LG(3) PF_LG(4) PF_LG(5) PF_LG(6) PF_LG(8)
     PF_L96(8) PF_L96(40)
     mb_set_error("pf: unsupported ssm kind %d / dim %d (built-in device models only; no CPU fallback)", a.ssm.kind, d);

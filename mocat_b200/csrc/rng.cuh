@@ -17,10 +17,9 @@ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint3
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
         if (r > 0) { k0 += W0; k1 += W1; }
-        const uint64_t p0 = (uint64_t)M0 * c0;
-        const uint64_t p1 = (uint64_t)M1 * c2;
-        const uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
-        const uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+        // __umulhi + 32-bit product fuse into ONE IMAD.WIDE each; the (uint64_t) form costs two stray adds per round
+        const uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+        const uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
         c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
     }
     return Philox4{c0, c1, c2, c3};
@@ -47,9 +46,11 @@ __device__ __forceinline__ double u53(uint32_t a, uint32_t b) {
 // cos/sin evaluated on phi = 2 pi u2 - pi in [-pi, pi) where the MUFU approximations are accurate:
 // cos(2 pi u2) = -cos(phi), sin(2 pi u2) = -sin(phi).
 __device__ __forceinline__ void box_muller(uint32_t xa, uint32_t xb, float& z0, float& z1) {
-    const float u1 = u_open(xa);
+    const float u1 = u_open(xa);                       // in [2^-33, 1]: never denormal, so the raw MUFU ops are safe
     const float u2 = u24(xb);
-    const float r = sqrtf(-2.0f * __logf(u1));
+    float l2, r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(u1));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(l2 * -1.3862943611198906f));   // sqrt(-2 ln u1), -2 ln 2 folded
     const float phi = fmaf(u2, 6.283185307179586f, -3.141592653589793f);
     float s, c;
     __sincosf(phi, &s, &c);
