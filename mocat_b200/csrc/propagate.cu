@@ -432,19 +432,19 @@ __device__ __forceinline__ float pf_particle(const mb_ssm& m, float (&x)[D], con
                     x[j] = init ? fmaf(m.init_std, z4[c], m.init_mean)
                                 : fmaf(m.q_std, z4[c], x[j]);                  // nonlinear_gaussian.py:112-113
                     const float r = (ys[j] - x[j]) * ir;
-                    quad = fmaf(0.5f * r, r, quad);
+                    quad = fmaf(r, r, quad);
                 }
             }
         }
-        return -(quad + m.lik_const);
+        return -(0.5f * quad + m.lik_const);
     }
 }
 
 #define PF_THREADS(D) ((D) >= 32 ? 128 : MV_THREADS)
-template <int KIND, int D>
+template <int KIND, int D, bool INIT>
 __global__ void __launch_bounds__(PF_THREADS(D), (D) >= 32 ? 4 : 1) pf_step_kernel(PfArgs a) {
     mb_control* ctl = a.ctl;
-    const bool init = a.init != 0;
+    constexpr bool init = INIT;                       // compile-time: the initial-sample variant is a separate (small) kernel
     if (!init && ctl->done) return;
     const bool resample = !init && ctl->resample != 0;
     __shared__ Lse3 smem[MV_THREADS / 32];
@@ -538,12 +538,13 @@ static int64_t pf_grid(mb_ctx* ctx, int64_t n, int threads) {
     return grid > cap ? cap : grid;
 }
 
+#define PF_LAUNCH(K, DD) (a.init ? pf_step_kernel<K, DD, true> : pf_step_kernel<K, DD, false>)
 static int pf_dispatch(mb_ctx* ctx, PfArgs& a, cudaStream_t st) {
     a.partials = ctx->partials;
     a.counter = ctx->counters + MB_CNT_MOVE;
     const int d = a.ssm.dim;
-#define PF_LG(DD) if (a.ssm.kind == MB_SSM_LINEAR_GAUSSIAN && d == DD) { pf_step_kernel<MB_SSM_LINEAR_GAUSSIAN, DD><<<(unsigned)pf_grid(ctx, a.n, PF_THREADS(DD)), PF_THREADS(DD), 0, st>>>(a); MB_CHECK_LAUNCH(); return MB_OK; }
-#define PF_L96(DD) if (a.ssm.kind == MB_SSM_LORENZ96 && d == DD) { pf_step_kernel<MB_SSM_LORENZ96, DD><<<(unsigned)pf_grid(ctx, a.n, PF_THREADS(DD)), PF_THREADS(DD), 0, st>>>(a); MB_CHECK_LAUNCH(); return MB_OK; }
+#define PF_LG(DD) if (a.ssm.kind == MB_SSM_LINEAR_GAUSSIAN && d == DD) { PF_LAUNCH(MB_SSM_LINEAR_GAUSSIAN, DD)<<<(unsigned)pf_grid(ctx, a.n, PF_THREADS(DD)), PF_THREADS(DD), 0, st>>>(a); MB_CHECK_LAUNCH(); return MB_OK; }
+#define PF_L96(DD) if (a.ssm.kind == MB_SSM_LORENZ96 && d == DD) { PF_LAUNCH(MB_SSM_LORENZ96, DD)<<<(unsigned)pf_grid(ctx, a.n, PF_THREADS(DD)), PF_THREADS(DD), 0, st>>>(a); MB_CHECK_LAUNCH(); return MB_OK; }
     PF_LG(1) PF_LG(2) PF_LG(3) PF_LG(4) PF_LG(5) PF_LG(6) PF_LG(8)
     PF_L96(8) PF_L96(40)
     mb_set_error("pf: unsupported ssm kind %d / dim %d (built-in device models only; no CPU fallback)", a.ssm.kind, d);
