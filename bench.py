@@ -24,6 +24,10 @@ if ROOT not in sys.path:
 METRIC = "particle-steps/sec"
 D = 5
 ALGO_BYTES_MOVE = 64.0          # x(5)+w+l+U_prior read + write
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the two step kernels at n = 1e6, one `ncu --set full`
+# capture of this command (profiles/ncu_step_r1d.md); scaled linearly for other n.  The state is L2 resident, the
+# writes of both kernels stay in L2, so the traffic is BELOW the algorithmic bytes (no wasted re-reads).
+NCU_DRAM_BYTES_PER_PARTICLE = {"temper_adapt_kernel<resident>": 8.10, "smc_move_kernel<Rastrigin,5,MALA>": 24.27}
 WORKLOAD = "C2 tempered SMC, Rastrigin d=5 a=1, prior N(0,3^2 I), MALA eps=0.1 (1 leapfrog), adaptive " \
            "tempering retain 0.9 / resample 0.5, multinomial resampling"
 
@@ -304,7 +308,8 @@ def main():
                                                    (eng.xbuf[0], eng.xbuf[1], eng.lw, eng.lik, eng.up, eng.alpha,
                                                     eng.cdf, eng.anc)))},
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"],
-                     "peak": hbm_peak, "unit": "GB/s", "frac": kernels[dom]["frac"], "traffic": None,
+                     "peak": hbm_peak, "unit": "GB/s", "frac": kernels[dom]["frac"],
+                     "traffic": NCU_DRAM_BYTES_PER_PARTICLE[dom] * n,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": kernels[dom]["algorithmic_bytes"],
                      "ms_per_launch": kernels[dom]["ms"],
                      "note": "n=1e6: the whole state (68 MB) is smaller than L2 and every kernel is "
