@@ -213,12 +213,26 @@ __global__ void __launch_bounds__(MV_THREADS, (D <= 6 ? 4 : (D <= 10 ? 3 : 2))) 
         if (resample) a.lw[i] = 0.f;                                   // smc.py:69
         alpha_local += (double)alpha_mean;
     }
-    // deterministic (integer) accumulation of NaN count and mean acceptance
-    const double asum = block_sum_d(alpha_local, red);
-    const double nsum = block_sum_d((double)nan_local, red);
+    // deterministic (integer) accumulation of NaN count and mean acceptance.  One particle per thread, so this tail runs
+    // once per particle: fixed point (24 fractional bits) + the hardware integer warp reduction (REDUX) instead of two
+    // fp64 shuffle trees (~200 -> ~15 instructions per particle).  A thread that looped over several particles
+    // (grids beyond 2^31 blocks) is still exact up to 255 particles per thread.
+    const unsigned long long afx = (unsigned long long)llrint(alpha_local * 16777216.0);
+    const unsigned wa_lo = __reduce_add_sync(MB_FULL, (unsigned)(afx & 0xffffffu));        // 32 x 2^24 < 2^32
+    const unsigned wa_hi = __reduce_add_sync(MB_FULL, (unsigned)(afx >> 24));
+    const unsigned wn = __reduce_add_sync(MB_FULL, (unsigned)nan_local);
+    unsigned long long* redu = reinterpret_cast<unsigned long long*>(red);
+    __shared__ unsigned redn[MV_THREADS / 32];
+    if ((threadIdx.x & 31) == 0) {
+        redu[threadIdx.x >> 5] = (unsigned long long)wa_lo + ((unsigned long long)wa_hi << 24);
+        redn[threadIdx.x >> 5] = wn;
+    }
+    __syncthreads();
     if (threadIdx.x == 0) {
-        atomicAdd((unsigned long long*)&a.ctl->alpha_fx, (unsigned long long)llrint(asum * 4294967296.0));
-        if (nsum > 0) atomicAdd((unsigned long long*)&a.ctl->nan_count, (unsigned long long)nsum);
+        unsigned long long asum = 0, nsum = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { asum += redu[w]; nsum += redn[w]; }
+        atomicAdd((unsigned long long*)&a.ctl->alpha_fx, asum << 8);                      // units of 2^-32
+        if (nsum > 0) atomicAdd((unsigned long long*)&a.ctl->nan_count, nsum);
         if (blockIdx.x == 0) a.ctl->resampled = resample ? 1 : 0;
     }
 }
