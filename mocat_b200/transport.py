@@ -190,12 +190,16 @@ class MetropolisedSMCSampler(TemperedSMCSampler):
         chain = cdict()
         if keep:
             snaps = snaps[:iters + 1]
+            host = _to_host({k: torch.stack([s[k] for s in snaps]) for k in self._FIELDS})
             for k in self._FIELDS:
-                setattr(chain, k, torch.stack([s[k] for s in snaps]).cpu().numpy())
+                setattr(chain, k, host[k])
             betas = hist['beta'][:, None]
         else:
-            for k, v in self._snapshot(eng).items():
-                setattr(chain, k, v.cpu().numpy()[None])
+            # no device clones: only `value` needs a kernel (SoA -> row-major), the rest is copied from the engine buffers
+            host = _to_host(dict(value=eng.values().contiguous(), log_weight=eng.lw, prior_potential=eng.up,
+                                 likelihood_potential=eng.lik, alpha=eng.alpha))
+            for k in self._FIELDS:
+                setattr(chain, k, host[k][None])
             betas = hist['beta'][-1:, None]
         chain.potential = chain.prior_potential + betas * chain.likelihood_potential
         chain.temperature = hist['beta'].copy()
@@ -206,6 +210,18 @@ class MetropolisedSMCSampler(TemperedSMCSampler):
         chain.bisection_iters = hist['search_iters'].copy()
         initial_extra.iter = iters
         return chain
+
+
+def _to_host(tensors):
+    """device tensors -> NumPy arrays through pinned host memory (torch's caching host allocator hands the blocks of
+    a dropped result back to the next run): all copies are enqueued, ONE synchronisation, PCIe at DMA speed instead
+    of the staged pageable path.  The arrays own their (pinned) memory."""
+    torch = _torch()
+    outs = {k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True) for k, v in tensors.items()}
+    for k, v in tensors.items():
+        outs[k].copy_(v, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return {k: o.numpy() for k, o in outs.items()}
 
 
 class RMMetropolisedSMCSampler(MetropolisedSMCSampler):
