@@ -123,3 +123,25 @@ def test_quantile_linear_matches_numpy():
     v = rng.random(1001)
     for q in (0.0, 0.1234, 0.5, 0.9, 1.0):
         npt.assert_allclose(core.quantile_linear(v, q), np.quantile(v, q), rtol=1e-14)
+
+
+def test_logistic_regression_oracle_gradient():
+    # config C4's target has no upstream test: pin the restatement on central finite differences and on
+    # the closed form at w = 0 (U = N log 2, grad = A^T (1/2 - t))
+    rng = np.random.default_rng(4)
+    A = rng.standard_normal((40, 6))
+    t = (rng.random(40) < 0.5).astype(np.float64)
+    lr = models.LogisticRegression(A, t)
+    u0, g0 = lr.potential_and_grad(np.zeros((1, 6)))
+    npt.assert_allclose(u0[0], 40 * np.log(2.0), rtol=1e-12)
+    npt.assert_allclose(g0[0], A.T @ (0.5 - t), rtol=1e-12)
+    w = rng.standard_normal((3, 6))
+    _, g = lr.potential_and_grad(w)
+    eps = 1e-6
+    for k in range(6):
+        e = np.zeros(6); e[k] = eps
+        fd = (lr.potential_and_grad(w + e)[0] - lr.potential_and_grad(w - e)[0]) / (2 * eps)
+        npt.assert_allclose(g[:, k], fd, rtol=1e-6, atol=1e-7)
+    # saturated logits stay finite
+    u, g = lr.potential_and_grad(np.full((1, 6), 200.0))
+    assert np.all(np.isfinite(u)) and np.all(np.isfinite(g))
