@@ -119,7 +119,7 @@ class LogisticRegression:
         x = np.asarray(x, np.float64)
         s = x @ self.A.T                                   # (n, N)
         u = np.sum(np.logaddexp(0.0, s) - self.t * s, axis=-1)
-        p = 1.0 / (1.0 + np.exp(-s))
+        p = 0.5 * (1.0 + np.tanh(0.5 * s))                     # sigmoid without overflow
         return u, (p - self.t) @ self.A
 
 
