@@ -315,7 +315,7 @@ def main():
                      "note": "n=1e6: the whole state (68 MB) is smaller than L2 and every kernel is "
                              "latency/issue bound, not HBM bound; see DESIGN.md for the n=1e8 figures"},
         "kernels": kernels,
-        "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": (7 if world == 1 else 9) * a.steps,   # kernels per step: scan, strata hist, 2 x offsets scan, ancestors, move, temper (+ exchange, histogram sum when sharded)
+        "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": (6 if world == 1 else 8) * a.steps,   # kernels per step: scan, strata hist, offsets scan, ancestors, move, temper (+ exchange, histogram sum when sharded)
         "clocks": clk,
         "wall_s_timed_region": t_wall,
     }

@@ -186,12 +186,13 @@ int mb_ancestors_sharded(mb_ctx* ctx, const mb_shard* sh, int mode, uint64_t see
  *      ancestor search (sh == NULL: cdf is the materialised CDF of n particles; else the sharded global CDF). */
 int mb_strata_count(int64_t n_total_out);
 int mb_strata_hist(mb_ctx* ctx, int64_t n_out, int64_t gid0, int B, uint64_t seed, uint32_t step,
-                   const mb_control* ctl, uint32_t* hist, mb_stream_t stream);
+                   const mb_control* ctl, uint32_t* hist, int clear /*1: zero hist first; 0: it is already zero --
+                   mb_ancestors_sorted leaves the counts it consumed zeroed*/, mb_stream_t stream);
 int mb_strata_reduce(mb_ctx* ctx, mb_comm* comm, const void* const* hist_peers, int world, int B,
                      uint32_t* hist_out, int barrier /*0: caller exchanged after its histogram kernel*/,
                      const mb_control* ctl, mb_stream_t stream);
 int mb_ancestors_sorted(mb_ctx* ctx, const double* cdf, int64_t n, const mb_shard* sh, int mode,
-                        const uint32_t* hist, uint32_t* offsets, int B, uint64_t seed, uint32_t step, int64_t gid0,
+                        uint32_t* hist /*consumed: zero on return*/, uint32_t* offsets, int B, uint64_t seed, uint32_t step, int64_t gid0,
                         int64_t n_total_out, int32_t* anc, int64_t n_out, const mb_control* ctl, mb_stream_t stream);
 
 /* ---- K6: gather of SoA state columns by ancestor.  Replaces cdict.__getitem__ (core.py:46-56) as

@@ -112,7 +112,7 @@ SIGNATURES = {
                              c_i64, c_d, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "mb_ancestors_sharded": (C.c_int, [c_vp, c_vp, C.c_int, c_u64, c_u32, c_vp, c_i64, c_vp, c_vp]),
     "mb_strata_count": (C.c_int, [c_i64]),
-    "mb_strata_hist": (C.c_int, [c_vp, c_i64, c_i64, C.c_int, c_u64, c_u32, c_vp, c_vp, c_vp]),
+    "mb_strata_hist": (C.c_int, [c_vp, c_i64, c_i64, C.c_int, c_u64, c_u32, c_vp, c_vp, C.c_int, c_vp]),
     "mb_strata_reduce": (C.c_int, [c_vp, c_vp, c_vp, C.c_int, C.c_int, c_vp, C.c_int, c_vp, c_vp]),
     "mb_ancestors_sorted": (C.c_int, [c_vp, c_vp, c_i64, c_vp, C.c_int, c_vp, c_vp, C.c_int, c_u64, c_u32, c_i64, c_i64,
                                       c_vp, c_i64, c_vp, c_vp]),

@@ -387,14 +387,25 @@ __global__ void __launch_bounds__(1024) strata_chunk_sum_kernel(StrataArgs a, ui
     }
 }
 
-__global__ void __launch_bounds__(1024) strata_chunk_scan_kernel(StrataArgs a, uint32_t* chunk_tot, int nchunks) {
+// DIRECT (few chunks, the n ~ 1e6 regime): every block sums the counts in front of its chunk itself, which saves the
+// chunk-total kernel (one graph node per step); otherwise the prefix comes from the chunk totals.
+template <bool DIRECT>
+__global__ void __launch_bounds__(1024) strata_chunk_scan_kernel(StrataArgs a, const uint32_t* chunk_tot, int nchunks) {
     if (a.ctl && (a.ctl->done || !a.ctl->resample)) return;
     // every block scans the (<= 4096) chunk totals up to its own chunk in shared memory, then its chunk
     __shared__ uint32_t wsum[32];
     __shared__ uint32_t base_s;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t pre = 0;
-    for (int i = threadIdx.x; i < (int)blockIdx.x; i += 1024) pre += chunk_tot[i];
+    if (DIRECT) {
+        const uint4* h4 = reinterpret_cast<const uint4*>(a.hist);      // chunk starts are multiples of 4096 counts
+        for (int i = threadIdx.x; i < (int)blockIdx.x * (SS_CHUNK / 4); i += 1024) {
+            const uint4 v = h4[i];
+            pre += v.x + v.y + v.z + v.w;
+        }
+    } else {
+        for (int i = threadIdx.x; i < (int)blockIdx.x; i += 1024) pre += chunk_tot[i];
+    }
     for (int o = 16; o > 0; o >>= 1) pre += __shfl_xor_sync(MB_FULL, pre, o);
     if (lane == 0) wsum[warp] = pre;
     __syncthreads();
@@ -434,6 +445,7 @@ struct SortedAncArgs {
     const double* cdf; int64_t n;        // single-GPU: materialised clamped CDF
     mb_shard sh; int sharded;            // sharded: rank-relative CDFs of all ranks + totals
     const uint32_t* offsets; int B;      // strata offsets (stratified)
+    uint32_t* hist_clear;                // stratified: the consumed counts are zeroed for the next resampling
     uint64_t seed; uint32_t step; int64_t gid0; int64_t n_out; int64_t n_total_out;
     int32_t* anc;
     const mb_control* ctl;
@@ -478,6 +490,9 @@ ancestors_sorted_kernel(SortedAncArgs a) {
     __shared__ int s_lo_s, s_hi_s;
     const uint32_t step = a.ctl ? (uint32_t)(a.ctl->iter + 1) : a.step;
     const uint64_t seed = a.ctl ? a.ctl->seed : a.seed;
+    if (a.hist_clear)
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.B; i += (int64_t)gridDim.x * blockDim.x)
+            a.hist_clear[i] = 0u;
     GlobalCdf G;
     G.cdf = a.cdf; G.n = a.sharded ? a.sh.n_total : a.n; G.sharded = a.sharded != 0; G.W = a.sh.world; G.nl = a.sh.n_local;
     if (G.sharded) {
@@ -555,9 +570,9 @@ extern "C" int mb_strata_count(int64_t n_total_out) { return strata_B(n_total_ou
 
 // first stage: histogram of this rank's outputs over the B strata (hist must hold B uint32; it is zeroed here)
 extern "C" int mb_strata_hist(mb_ctx* ctx, int64_t n_out, int64_t gid0, int B, uint64_t seed, uint32_t step,
-                              const mb_control* ctl, uint32_t* hist, mb_stream_t stream) {
+                              const mb_control* ctl, uint32_t* hist, int clear, mb_stream_t stream) {
     MB_REQUIRE(ctx && hist && n_out > 0 && B >= 1 && (B & (B - 1)) == 0, "mb_strata_hist: bad arguments");
-    MB_CUDA(cudaMemsetAsync(hist, 0, sizeof(uint32_t) * B, mb_s(stream)));
+    if (clear) MB_CUDA(cudaMemsetAsync(hist, 0, sizeof(uint32_t) * B, mb_s(stream)));
     StrataArgs a{hist, nullptr, B, n_out, gid0, seed, step, ctl};
     int64_t grid = (n_out + 255) / 256;
     if (grid > (int64_t)ctx->sms * 16) grid = (int64_t)ctx->sms * 16;
@@ -569,7 +584,7 @@ extern "C" int mb_strata_hist(mb_ctx* ctx, int64_t n_out, int64_t gid0, int B, u
 // second stage: exclusive scan -> offsets[B+1]; then ancestors for this rank's outputs.
 // sh == NULL: single GPU (cdf = materialised clamped CDF of n particles); else the sharded global CDF.
 extern "C" int mb_ancestors_sorted(mb_ctx* ctx, const double* cdf, int64_t n, const mb_shard* sh, int mode,
-                                   const uint32_t* hist, uint32_t* offsets, int B, uint64_t seed, uint32_t step,
+                                   uint32_t* hist, uint32_t* offsets, int B, uint64_t seed, uint32_t step,
                                    int64_t gid0, int64_t n_total_out, int32_t* anc, int64_t n_out,
                                    const mb_control* ctl, mb_stream_t stream) {
     MB_REQUIRE(ctx && anc && n_out > 0 && n_total_out >= n_out && (cdf || sh), "mb_ancestors_sorted: bad arguments");
@@ -581,11 +596,16 @@ extern "C" int mb_ancestors_sorted(mb_ctx* ctx, const double* cdf, int64_t n, co
     a.offsets = offsets; a.B = B; a.seed = seed; a.step = step; a.gid0 = gid0; a.n_out = n_out;
     a.n_total_out = n_total_out; a.anc = anc; a.ctl = ctl;
     if (a.stratified) {
-        StrataArgs sa{const_cast<uint32_t*>(hist), offsets, B, n_out, gid0, seed, step, ctl};
+        StrataArgs sa{hist, offsets, B, n_out, gid0, seed, step, ctl};
+        a.hist_clear = hist;
         const int nchunks = (B + SS_CHUNK - 1) / SS_CHUNK;
         uint32_t* chunk_tot = reinterpret_cast<uint32_t*>((char*)ctx->scratch + (3u << 20));    // <= 16 KiB of the scratch
-        strata_chunk_sum_kernel<<<nchunks, 1024, 0, mb_s(stream)>>>(sa, chunk_tot);
-        strata_chunk_scan_kernel<<<nchunks, 1024, 0, mb_s(stream)>>>(sa, chunk_tot, nchunks);
+        if (nchunks <= 32 && (((uintptr_t)hist & 15) == 0)) {
+            strata_chunk_scan_kernel<true><<<nchunks, 1024, 0, mb_s(stream)>>>(sa, chunk_tot, nchunks);
+        } else {
+            strata_chunk_sum_kernel<<<nchunks, 1024, 0, mb_s(stream)>>>(sa, chunk_tot);
+            strata_chunk_scan_kernel<false><<<nchunks, 1024, 0, mb_s(stream)>>>(sa, chunk_tot, nchunks);
+        }
         MB_CHECK_LAUNCH();
     }
     int64_t grid = (n_out + ANC_BLOCK_OUT - 1) / ANC_BLOCK_OUT;

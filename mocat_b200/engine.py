@@ -164,7 +164,8 @@ class _Resampler:
         L = self.L
         L.call("mb_cumsum_lw", self.ctx, ptr(self.lw), self.n, ptr(self.ctl.t), 0, ptr(self.cdf), st)
         if self.resampling == _lib.RESAMPLE_MULTINOMIAL:
-            L.call("mb_strata_hist", self.ctx, self.n, self.gid0, self.B, self.seed, 0, ptr(self.ctl.t), ptr(self.hist), st)
+            # clear = 0: allocated zeroed, and mb_ancestors_sorted zeroes the counts it consumed (no memset node per step)
+            L.call("mb_strata_hist", self.ctx, self.n, self.gid0, self.B, self.seed, 0, ptr(self.ctl.t), ptr(self.hist), 0, st)
         L.call("mb_ancestors_sorted", self.ctx, ptr(self.cdf), self.n, None, self.resampling, ptr(self.hist),
                ptr(self.offsets), self.B, self.seed, 0, self.gid0, self.n_total, ptr(self.anc), self.n, ptr(self.ctl.t), st)
 

@@ -135,7 +135,7 @@ def _sharded_resample_kernels(eng, sc, st):
     multinomial = eng.resampling == _lib.RESAMPLE_MULTINOMIAL
     L.call("mb_cumsum_lw", eng.ctx, ptr(eng.lw), eng.n, ctl, 2, ptr(eng.cdf), st)
     if multinomial:
-        L.call("mb_strata_hist", eng.ctx, eng.n, eng.gid0, eng.B, eng.seed, 0, ctl, ptr(eng.hist_local), st)
+        L.call("mb_strata_hist", eng.ctx, eng.n, eng.gid0, eng.B, eng.seed, 0, ctl, ptr(eng.hist_local), 1, st)
     L.call("mb_comm_allgather", sc.comm, ptr(eng.cdf[eng.n - 1:]), 1, ptr(eng.totals), ctl, st)
     if multinomial:
         L.call("mb_strata_reduce", eng.ctx, sc.comm, eng.hist_peers, sc.world, eng.B, ptr(eng.hist), 0, ctl, st)

@@ -38,7 +38,7 @@ report("ancestors systematic", timeit(lambda: L.call("mb_ancestors", ctx, ptr(cd
 report("ancestors multinomial iid-u", timeit(lambda: L.call("mb_ancestors", ctx, ptr(cdf), n, 1, None, 1, 1, 0, ptr(anc), n, None, stream()), reps=2, warm=1), 12, "legacy: unsorted u, random binary search")
 B = int(L.dll.mb_strata_count(n)); hist = torch.zeros(B, dtype=torch.int32, device=dev); offs = torch.zeros(B + 1, dtype=torch.int32, device=dev)
 def strat():
-    L.call("mb_strata_hist", ctx, n, 0, B, 1, 1, None, ptr(hist), stream())
+    L.call("mb_strata_hist", ctx, n, 0, B, 1, 1, None, ptr(hist), 1, stream())
     L.call("mb_ancestors_sorted", ctx, ptr(cdf), n, None, 1, ptr(hist), ptr(offs), B, 1, 1, 0, n, ptr(anc), n, None, stream())
 report("ancestors multinomial stratified", timeit(strat), 12, "hist + scan + sorted search (B=%d)" % B)
 report("ancestors systematic (sorted kernel)", timeit(lambda: L.call("mb_ancestors_sorted", ctx, ptr(cdf), n, None, 0, ptr(hist), ptr(offs), B, 1, 1, 0, n, ptr(anc), n, None, stream())), 12, "8 read + 4 write")

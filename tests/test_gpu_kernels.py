@@ -163,11 +163,14 @@ def _sorted_ancestors(eng, cdf_d, n, n_out, mode, seed, step):
     hist = torch.zeros(B, dtype=torch.int32, device="cuda")
     offs = torch.zeros(B + 1, dtype=torch.int32, device="cuda")
     anc = torch.empty(n_out, dtype=torch.int32, device="cuda")
+    counts = None
     if mode == 1:
-        L.call("mb_strata_hist", L.ctx(), n_out, 0, B, seed, step, None, _lib.ptr(hist), _lib.stream())
+        L.call("mb_strata_hist", L.ctx(), n_out, 0, B, seed, step, None, _lib.ptr(hist), 1, _lib.stream())
+        counts = hist.cpu().numpy().copy()
     L.call("mb_ancestors_sorted", L.ctx(), _lib.ptr(cdf_d), n, None, mode, _lib.ptr(hist), _lib.ptr(offs), B, seed, step,
            0, n_out, _lib.ptr(anc), n_out, None, _lib.stream())
-    return anc.cpu().numpy(), hist.cpu().numpy(), offs.cpu().numpy(), B
+    assert int(hist.sum().item()) == 0                      # the consumed counts are left zeroed for the next resampling
+    return anc.cpu().numpy(), counts, offs.cpu().numpy(), B
 
 
 @pytest.mark.parametrize("n", [1, 17, 5000, 100_003, 1_000_000])
