@@ -128,6 +128,8 @@ class MetropolisedSMCSampler(TemperedSMCSampler):
                 world = dist.get_world_size()
         except Exception:
             world = 1
+        if world > 1 and getattr(self, '_private_engine', False):
+            raise _lib.MocatB200Error("RMMetropolisedSMCSampler is single-GPU for now (stepsize is a host-side launch parameter)")
         if world > 1 and getattr(self, 'sharded', True):
             # under torchrun `n` is the GLOBAL population size; every rank holds n/world particles, passes its
             # own shard of initial_state.value and gets its own shard back (mocat_b200/parallel.py)
@@ -136,8 +138,13 @@ class MetropolisedSMCSampler(TemperedSMCSampler):
             eng = parallel.acquire_sharded_smc(target, move, temper, n_local, seed, _RESAMPLING[self.resampling],
                                                schedule=self.temperature_schedule)
         else:
-            eng = engine.SMCEngine.acquire(target, move, temper, n, seed, resampling=_RESAMPLING[self.resampling],
-                                           schedule=self.temperature_schedule)
+            if getattr(self, '_private_engine', False):                  # launch parameters change between iterations
+                eng = engine.SMCEngine(target, move, temper, n, seed, resampling=_RESAMPLING[self.resampling],
+                                       schedule=self.temperature_schedule)
+                eng.use_graphs = False
+            else:
+                eng = engine.SMCEngine.acquire(target, move, temper, n, seed, resampling=_RESAMPLING[self.resampling],
+                                               schedule=self.temperature_schedule)
         x0 = None if initial_state is None else getattr(initial_state, 'value', None)
         eng.startup(x0)                                                 # smc.py:128-164, 267-296 on the device
         scenario.temperature = 0.
@@ -166,6 +173,9 @@ class MetropolisedSMCSampler(TemperedSMCSampler):
         out.temperature, out.ess, out.log_norm_constant = c['beta'], c['ess'], c['log_z']
         return out
 
+    def _post_update(self, eng, extra):
+        """hook between population steps (the reference's `adapt` extensions); nothing for the plain sampler"""
+
     def _run_device(self, scenario, initial_state, initial_extra):
         torch = _torch()
         eng = initial_extra.engine
@@ -180,6 +190,7 @@ class MetropolisedSMCSampler(TemperedSMCSampler):
             for _ in range(burst):
                 eng.update()
                 it += 1
+                self._post_update(eng, initial_extra)
                 if keep:
                     snaps.append(self._snapshot(eng))
             if eng.ctl.read()['done']:
@@ -225,11 +236,33 @@ def _to_host(tensors):
 
 
 class RMMetropolisedSMCSampler(MetropolisedSMCSampler):
-    """transport/smc.py:376-428 (Robbins-Monro stepsize adaptation between iterations): not yet compiled
-    into the device step."""
+    """transport/smc.py:376-428: Robbins-Monro adaptation of the MCMC stepsize between iterations,
+    log eps += rm_stepsize * (alpha_mean - target), alpha_mean = average acceptance weighted by exp(w - max w).
+    The weighted mean is reduced on the device (mb_weighted_moments); the stepsize is a launch parameter of the move
+    kernel, so this sampler enqueues plain launches (no graph replay) and reads one double per iteration."""
+    _private_engine = True
 
-    def __init__(self, *args, **kwargs):
-        raise _lib.MocatB200Error("RMMetropolisedSMCSampler is not built yet (no CPU fallback)")
+    def __init__(self, *args, rm_stepsize=1., **kwargs):
+        super().__init__(*args, **kwargs)
+        self.parameters.rm_stepsize = rm_stepsize
+        self.check_every = 1
+
+    def startup(self, scenario, n, initial_state, initial_extra, **kwargs):
+        initial_state, initial_extra = super().startup(scenario, n, initial_state, initial_extra, **kwargs)
+        self._stepsizes = [float(initial_extra.engine.move.stepsize)]   # smc.py:403: state.stepsize at iteration 0
+        return initial_state, initial_extra
+
+    def _post_update(self, eng, extra):                                # smc.py:406-421
+        alpha_mean = float(engine.weighted_moments(eng.alpha.view(1, eng.n), eng.n, eng.lw, eng.ctl)[0].item())
+        log_eps = np.log(float(eng.move.stepsize)) + self.parameters.rm_stepsize * (alpha_mean - self.mcmc_sampler.tuning.target)
+        eng.move.stepsize = float(np.exp(log_eps))
+        extra.parameters.stepsize = eng.move.stepsize
+        self._stepsizes.append(eng.move.stepsize)
+
+    def _run_device(self, scenario, initial_state, initial_extra):
+        chain = super()._run_device(scenario, initial_state, initial_extra)
+        chain.stepsize = np.asarray(self._stepsizes[:len(chain.temperature)])      # clean_chain :423-428
+        return chain
 
 
 # ======================================================================================================

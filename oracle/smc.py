@@ -25,7 +25,8 @@ class TemperedSMC:
     def __init__(self, prior, likelihood, n, seed, move='mala', stepsize=0.1, leapfrog_steps=1,
                  mcmc_steps=1, temperature_schedule=None, max_temperature=1.0, max_iter=10000,
                  ess_threshold_retain=0.9, ess_threshold_resample=0.5, bisection_tol=1e-5,
-                 max_bisection_iter=1000, resampling='multinomial', normal_dtype=np.float64):
+                 max_bisection_iter=1000, resampling='multinomial', normal_dtype=np.float64,
+                 rm_stepsize=None, rm_target=0.651):
         self.prior, self.lik, self.n, self.seed = prior, likelihood, int(n), int(seed)
         self.d = prior.dim
         self.move, self.stepsize, self.L, self.mcmc_steps = move, float(stepsize), int(leapfrog_steps), int(mcmc_steps)
@@ -42,6 +43,7 @@ class TemperedSMC:
         self.normal_dtype = normal_dtype
         self.gid = np.arange(self.n, dtype=np.uint64)
         self.bisect_iters = []
+        self.rm_stepsize, self.rm_target = rm_stepsize, float(rm_target)   # smc.py:376-421 (RMMetropolisedSMCSampler)
 
     # -- potentials ---------------------------------------------------------------------------
     def _eval(self, x, beta):
@@ -129,6 +131,11 @@ class TemperedSMC:
                    alpha=alphas / self.mcmc_steps, ess=core.ess_log_weight(lw_new),
                    log_norm_constant=st['log_norm_constant'] + core.logsumexp(lw_new) - core.logsumexp(lw),
                    resampled=bool(resample), ancestors=anc)
+        if self.rm_stepsize is not None:                               # smc.py:406-421: Robbins-Monro on log stepsize
+            w = np.exp(lw_new - np.max(lw_new))
+            alpha_mean = float(np.sum(w * new['alpha']) / np.sum(w))
+            self.stepsize = float(np.exp(np.log(self.stepsize) + self.rm_stepsize * (alpha_mean - self.rm_target)))
+        new['stepsize'] = self.stepsize
         return new
 
     def run(self, x0=None):

@@ -227,3 +227,24 @@ def test_svgd_logistic_regression_matches_oracle(mocat):
     o.run()
     npt.assert_allclose(sample.value[-1], o.x, atol=5e-3)
     npt.assert_allclose(sample.bandwidth, o.h, rtol=1e-3)
+
+
+def test_rm_metropolised_smc_stepsize_adaptation(mocat):
+    """RMMetropolisedSMCSampler (transport/smc.py:376-428): the stepsize follows the oracle's Robbins-Monro recursion
+    (same Philox streams; the weighted mean acceptance differs by O(1/n) through rare accept/reject flips)"""
+    from oracle import models, smc as osmc
+    n, d, seed = 4000, 2, 3
+    sc = mocat.scenarios.Rastrigin(dim=d, a=1.0, prior_std=3.0)
+    smp = mocat.RMMetropolisedSMCSampler(mocat.Underdamped(stepsize=0.3), rm_stepsize=1.0, resampling='systematic',
+                                         keep_history=False)
+    out = mocat.run(sc, smp, n, random_key=seed)
+    orc = osmc.TemperedSMC(models.IsoGaussianPrior(d, 0.0, 3.0), models.Rastrigin(d, 1.0), n, seed, move='mala',
+                           stepsize=0.3, resampling='systematic', rm_stepsize=1.0, rm_target=0.651)
+    chain = orc.run()
+    ref = np.array([0.3] + [c['stepsize'] for c in chain[1:]])
+    assert out.stepsize.shape == out.temperature.shape
+    assert out.stepsize[0] == pytest.approx(0.3)
+    npt.assert_allclose(out.stepsize[1:4], ref[1:4], rtol=2e-2)        # before the particle systems decorrelate
+    assert abs(len(out.stepsize) - len(ref)) <= 3
+    assert np.all(np.diff(np.log(out.stepsize)) <= 1.0 * (1 - 0.651) + 1e-6)   # |log step| <= rm * (1 - target)
+    assert out.temperature[-1] == 1.0
