@@ -414,11 +414,17 @@ logistic_pg_simt_kernel(const float* __restrict__ A, const float* __restrict__ t
     if (U) U[i] = fmaf(beta, ul, up);
 }
 
+int mb_logistic_potential_grad_tc(mb_ctx* ctx, const float* features, const float* labels, int N, int d, float prior_mean,
+                                  float prior_pscale, float beta, const float* W, int n, float* U, float* G, cudaStream_t st);
+
 extern "C" int mb_logistic_potential_grad(mb_ctx* ctx, const float* features, const float* labels, int N, int d,
                                           float prior_mean, float prior_pscale, double beta, const float* W, int n,
                                           float* U, float* G, int variant, mb_stream_t stream) {
     MB_REQUIRE(ctx && features && labels && W && G && N > 0 && d > 0 && n > 0, "mb_logistic_potential_grad: bad arguments");
-    MB_REQUIRE(variant == 0, "mb_logistic_potential_grad: only variant 0 (fp32) is built");
+    if (variant == 1)
+        return mb_logistic_potential_grad_tc(ctx, features, labels, N, d, prior_mean, prior_pscale, (float)beta, W, n, U, G,
+                                             mb_s(stream));
+    MB_REQUIRE(variant == 0, "mb_logistic_potential_grad: variant not built");
     const int grid = (n + LR_THREADS - 1) / LR_THREADS;
     cudaStream_t st = mb_s(stream);
 #define LR_CASE(DPV) logistic_pg_simt_kernel<DPV><<<grid, LR_THREADS, 0, st>>>(features, labels, N, d, prior_mean, prior_pscale, (float)beta, W, n, U, G)

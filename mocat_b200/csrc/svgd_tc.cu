@@ -131,6 +131,17 @@ __device__ __forceinline__ float ex2f(float x) {
     return y;
 }
 
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 // exp2 on the FMA/ALU pipes (Cody-Waite split + degree-3 minimax on [-0.5, 0.5], max rel. error 7.5e-5, far below
 // the bf16 rounding of P): a fraction of the exponentials is taken off the MUFU pipe, which otherwise paces the
 // whole pipeline (n^2 = 1.07e9 exps per iteration at 16 lanes/clk/SM).
@@ -246,8 +257,13 @@ struct TcArgs {
     const float* bandwidth; float* phi;
     int n, d, n_pad, NV;
     float* opart;            // [TC_SPLIT][n_pad][NV] partial O
+    float* upart;            // logistic mode: [TC_SPLIT][n_pad][4] partial row sums of softplus
+    int ncols_pad;           // padded number of columns (j): = n_pad for the SVGD interaction, the data count for the logits
 };
 
+// MODE 0: P = exp2(S) (SVGD interaction).  MODE 1: S is the logit w_i . a_j of a logistic regression; P = sigmoid(S)
+// and the row sums of softplus(S) are accumulated on the side (the potential), O = P A is the data part of the gradient.
+template <int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1) svgd_phi_tc_kernel(TcArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -266,7 +282,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) svgd_phi_tc_kernel(TcArgs a) {
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(xa_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int T_all = a.n_pad / TC_BN;
+    const int T_all = a.ncols_pad / TC_BN;
     const int itile = blockIdx.x / TC_SPLIT, part = blockIdx.x % TC_SPLIT;
     const int t_begin = (int)(((int64_t)T_all * part) / TC_SPLIT), t_end = (int)(((int64_t)T_all * (part + 1)) / TC_SPLIT);
     const int T = t_end - t_begin;                                     // this CTA's j tiles: [t_begin, t_end)
@@ -357,6 +373,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) svgd_phi_tc_kernel(TcArgs a) {
         const int ch = (idx >> 2) & 1;                                 // 64-column half of the S tile
         const int row = wq * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
+        float usum = 0.f;
         for (int t = grp; t < T; t += 2) {
             const int u = t >> 1;                                      // use index of S[grp] / P[grp]
             mbar_wait(s_full + grp, (uint32_t)(u & 1));
@@ -368,12 +385,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) svgd_phi_tc_kernel(TcArgs a) {
             tmem_ld_wait();
             tc_fence_before();
             mbar_arrive(s_empty + grp);                                // S[grp] may be overwritten by MMA1(t+2)
+            if (MODE == 0) {
 #pragma unroll
-            for (int e = 0; e < 64; e += 2) {
-                const float p0 = tc_use_poly(e) ? ex2_poly(__uint_as_float(va[e])) : ex2f(__uint_as_float(va[e]));
-                const float p1 = tc_use_poly(e + 1) ? ex2_poly(__uint_as_float(va[e + 1])) : ex2f(__uint_as_float(va[e + 1]));
-                const __nv_bfloat162 pk = __floats2bfloat162_rn(p0, p1);
-                packed[e >> 1] = *reinterpret_cast<const uint32_t*>(&pk);
+                for (int e = 0; e < 64; e += 2) {
+                    const float p0 = tc_use_poly(e) ? ex2_poly(__uint_as_float(va[e])) : ex2f(__uint_as_float(va[e]));
+                    const float p1 = tc_use_poly(e + 1) ? ex2_poly(__uint_as_float(va[e + 1])) : ex2f(__uint_as_float(va[e + 1]));
+                    const __nv_bfloat162 pk = __floats2bfloat162_rn(p0, p1);
+                    packed[e >> 1] = *reinterpret_cast<const uint32_t*>(&pk);
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < 64; e += 2) {
+                    float p[2];
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {                      // stable sigmoid / softplus: t = e^{-|s|} in (0, 1]
+                        const float sv = __uint_as_float(va[e + q]);
+                        const float t = ex2f(-1.4426950408889634f * fabsf(sv));
+                        const float inv = rcp_approx(1.f + t);
+                        p[q] = sv >= 0.f ? inv : t * inv;
+                        usum += fmaxf(sv, 0.f) + 0.6931471805599453f * lg2_approx(1.f + t);
+                    }
+                    const __nv_bfloat162 pk = __floats2bfloat162_rn(p[0], p[1]);
+                    packed[e >> 1] = *reinterpret_cast<const uint32_t*>(&pk);
+                }
             }
             if (u >= 1) mbar_wait(p_empty + grp, (uint32_t)((u - 1) & 1));   // MMA2(t-2) has consumed P[grp]
             tc_fence_after();
@@ -382,6 +416,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) svgd_phi_tc_kernel(TcArgs a) {
             tc_fence_before();
             mbar_arrive(p_full + grp);
         }
+        if (MODE == 1) a.upart[(((int64_t)part * a.n_pad + (int64_t)itile * TC_BM + row) << 2) + grp * 2 + ch] = usum;
         const int cq = idx >> 2;                                       // epilogue: 32-column quarter of O per warp
         // ---- partial O of this j range -> workspace (summed in fixed order by svgd_tc_finish_kernel)
         if (T > 0) {
@@ -458,9 +493,9 @@ int mb_svgd_phi_tc(mb_ctx* ctx, const float* X, const float* G, int n, int d, co
     svgd_tc_wt_kernel<<<(unsigned)(((int64_t)tiles * NV * 16 + 255) / 256), 256, 0, st>>>(p);
     MB_CHECK_LAUNCH();
     const size_t smem = 1024 + TC_TILE_X_BYTES + (size_t)TC_STAGES * NV * 256 + 256;
-    MB_CUDA(cudaFuncSetAttribute(svgd_phi_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    TcArgs a{XA, WT, xs, bandwidth, phi, n, d, n_pad, NV, opart};
-    svgd_phi_tc_kernel<<<tiles * TC_SPLIT, TC_THREADS, smem, st>>>(a);
+    MB_CUDA(cudaFuncSetAttribute(svgd_phi_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TcArgs a{XA, WT, xs, bandwidth, phi, n, d, n_pad, NV, opart, nullptr, n_pad};
+    svgd_phi_tc_kernel<0><<<tiles * TC_SPLIT, TC_THREADS, smem, st>>>(a);
     MB_CHECK_LAUNCH();
     svgd_tc_finish_kernel<<<(unsigned)(((int64_t)n * d + 255) / 256), 256, 0, st>>>(a);
     MB_CHECK_LAUNCH();
@@ -779,6 +814,103 @@ int mb_pairdist_bandwidth_tc(mb_ctx* ctx, const float* X, int n, int d, int mode
         MB_CHECK_LAUNCH();
         svgd_dist_mean_finish<<<1, 256, 0, st>>>(partials, grid, n, h);
     }
+    MB_CHECK_LAUNCH();
+    return MB_OK;
+}
+
+// =================================================================================================
+// Config C4's target on the tensor cores (variant 1 of mb_logistic_potential_grad; bf16 operands, fp32 accumulation):
+// the same pipeline with MODE 1.  A tile rows = particles w_i (bf16), W^T tiles = features (rows c < d of the tile are
+// a_j[c]); S = W A^T are the logits, P = sigmoid(S), O = P A; the potential comes from the softplus row sums and
+// b = A^T t is exact fp32:   U_lik = sum_j softplus(s_ij) - w_i . b,   grad_lik = O_i - b.
+__global__ void __launch_bounds__(256) logit_rows_kernel(const float* __restrict__ W, int n, int d, int n_pad, uint8_t* XA) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (int64_t)n_pad * 8) return;
+    const int row = (int)(tid >> 3), ch = (int)(tid & 7);
+    __nv_bfloat16 va[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int k = ch * 8 + e;
+        va[e] = __float2bfloat16_rn((row < n && k < d) ? W[(int64_t)row * d + k] : 0.f);
+    }
+    *reinterpret_cast<uint4*>(XA + (int64_t)(row / TC_BM) * TC_TILE_X_BYTES + sw128_off(row % TC_BM, ch * 8)) =
+        *reinterpret_cast<uint4*>(va);
+}
+__global__ void __launch_bounds__(256) logit_wt_kernel(const float* __restrict__ A, int N, int d, int N_pad, uint8_t* WT) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (int64_t)(N_pad / TC_BN) * TC_K * 16) return;
+    const int q = (int)(tid & 15), c = (int)((tid >> 4) % TC_K), tile = (int)((tid >> 4) / TC_K);
+    __nv_bfloat16 v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int j = tile * TC_BN + q * 8 + e;
+        v[e] = __float2bfloat16_rn((c < d && j < N) ? A[(int64_t)j * d + c] : 0.f);
+    }
+    const uint32_t off = (uint32_t)(q >> 3) * (uint32_t)(TC_K * 128) + sw128_off(c, (q & 7) * 8);
+    *reinterpret_cast<uint4*>(WT + (int64_t)tile * (TC_K * 256) + off) = *reinterpret_cast<uint4*>(v);
+}
+__global__ void logit_b_kernel(const float* __restrict__ A, const float* __restrict__ t, int N, int d, float* b) {
+    const int k = threadIdx.x;
+    if (k >= d) return;
+    float s = 0.f;
+    for (int j = 0; j < N; ++j) s = fmaf(t[j], A[(int64_t)j * d + k], s);
+    b[k] = s;
+}
+struct LogitFinishArgs {
+    const float* W; const float* b; const float* opart; const float* upart; int n, d, n_pad, N, N_pad;
+    float prior_mean, prior_pscale, beta; float* U; float* G;
+};
+__global__ void __launch_bounds__(128) logit_finish_kernel(LogitFinishArgs a) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    float up = 0.f, wb = 0.f;
+    for (int k = 0; k < a.d; ++k) {
+        const float w = a.W[(int64_t)i * a.d + k];
+        float o = 0.f;
+#pragma unroll
+        for (int p = 0; p < TC_SPLIT; ++p) o += a.opart[((int64_t)p * a.n_pad + i) * TC_K + k];
+        const float r = (w - a.prior_mean) * a.prior_pscale;
+        up = fmaf(0.5f * r, r, up);
+        wb = fmaf(w, a.b[k], wb);
+        a.G[(int64_t)i * a.d + k] = fmaf(a.beta, o - a.b[k], r * a.prior_pscale);
+    }
+    if (a.U) {
+        float sp = 0.f;
+        for (int p = 0; p < TC_SPLIT; ++p)
+            for (int q = 0; q < 4; ++q) sp += a.upart[(((int64_t)p * a.n_pad + i) << 2) + q];
+        sp -= (float)(a.N_pad - a.N) * 0.6931471805599453f;           // padded data columns: softplus(0) = ln 2 each
+        a.U[i] = fmaf(a.beta, sp - wb, up);
+    }
+}
+
+int mb_logistic_potential_grad_tc(mb_ctx* ctx, const float* features, const float* labels, int N, int d, float prior_mean,
+                                  float prior_pscale, float beta, const float* W, int n, float* U, float* G, cudaStream_t st) {
+    MB_REQUIRE(d >= 1 && d <= TC_K, "logistic tcgen05 variant needs d <= 64");
+    const int NV = TC_K;
+    const int n_pad = ((n + TC_BM - 1) / TC_BM) * TC_BM, N_pad = ((N + TC_BN - 1) / TC_BN) * TC_BN;
+    const int tiles = n_pad / TC_BM, jtiles = N_pad / TC_BN;
+    const size_t bx = (size_t)tiles * TC_TILE_X_BYTES, bw = (size_t)jtiles * NV * 256;
+    const size_t bo = (size_t)TC_SPLIT * n_pad * NV * 4, bu = (size_t)TC_SPLIT * n_pad * 4 * 4;
+    const size_t need = 1024 + bx + bw + bo + bu + 8192;
+    if (mb_ensure_scratch(ctx, (4u << 20) + need) != MB_OK) return MB_ERR_CUDA;
+    uint8_t* base = (uint8_t*)ctx->scratch + (4u << 20);
+    auto align = [](uint8_t* p) { return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~(uintptr_t)1023); };
+    float* b = reinterpret_cast<float*>(align(base));
+    uint8_t* XA = align(reinterpret_cast<uint8_t*>(b) + 256);
+    uint8_t* WT = align(XA + bx);
+    float* opart = reinterpret_cast<float*>(align(WT + bw));
+    float* upart = reinterpret_cast<float*>(align(reinterpret_cast<uint8_t*>(opart) + bo));
+    logit_b_kernel<<<1, 64, 0, st>>>(features, labels, N, d, b);
+    logit_rows_kernel<<<(unsigned)(((int64_t)n_pad * 8 + 255) / 256), 256, 0, st>>>(W, n, d, n_pad, XA);
+    logit_wt_kernel<<<(unsigned)(((int64_t)jtiles * NV * 16 + 255) / 256), 256, 0, st>>>(features, N, d, N_pad, WT);
+    MB_CHECK_LAUNCH();
+    const size_t smem = 1024 + TC_TILE_X_BYTES + (size_t)TC_STAGES * NV * 256 + 256;
+    MB_CUDA(cudaFuncSetAttribute(svgd_phi_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TcArgs a{XA, WT, nullptr, nullptr, nullptr, n, d, n_pad, NV, opart, upart, N_pad};
+    svgd_phi_tc_kernel<1><<<tiles * TC_SPLIT, TC_THREADS, smem, st>>>(a);
+    MB_CHECK_LAUNCH();
+    LogitFinishArgs f{W, b, opart, upart, n, d, n_pad, N, N_pad, prior_mean, prior_pscale, beta, U, G};
+    logit_finish_kernel<<<(n + 127) / 128, 128, 0, st>>>(f);
     MB_CHECK_LAUNCH();
     return MB_OK;
 }

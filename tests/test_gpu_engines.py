@@ -341,3 +341,23 @@ def test_pairdist_bandwidth_tcgen05_degenerate(E):
     Xd = torch.ones((2048, 5), device="cuda")
     assert abs(e.pairdist_bandwidth(Xd, "median", 1).item()) < 1e-12
     assert abs(e.pairdist_bandwidth(Xd, "mean", 1).item()) < 1e-12
+
+
+@pytest.mark.parametrize("n,N,d", [(4096, 1024, 50), (2500, 1000, 11)])
+def test_logistic_potential_grad_tcgen05(E, n, N, d):
+    """variant 1 (tcgen05, bf16 operands) of the C4 target against the exact fp32 kernel: the logits carry the bf16
+    rounding of w and of the features (~0.3 % each), so the tolerance is 1.5e-2 of max|grad| / 3e-3 relative on U"""
+    import torch
+    e, m, l = E
+    rng = np.random.default_rng(n)
+    A = rng.standard_normal((N, d)).astype(np.float32)
+    t = (rng.random(N) < 0.5).astype(np.float32)
+    W = (rng.standard_normal((n, d)) * 0.3).astype(np.float32)
+    Ad, td, Wd = (torch.as_tensor(a, device="cuda") for a in (A, t, W))
+    U0, G0 = e.logistic_potential_grad(Ad, td, 0.0, 1.0, 0.8, Wd, variant=0)
+    U1, G1 = e.logistic_potential_grad(Ad, td, 0.0, 1.0, 0.8, Wd, variant=1)
+    g0, g1 = G0.cpu().numpy(), G1.cpu().numpy()
+    assert np.max(np.abs(g1 - g0)) < 1.5e-2 * np.max(np.abs(g0))
+    npt.assert_allclose(U1.cpu().numpy(), U0.cpu().numpy(), rtol=3e-3)
+    U2, G2 = e.logistic_potential_grad(Ad, td, 0.0, 1.0, 0.8, Wd, variant=1)
+    assert torch.equal(G1, G2) and torch.equal(U1, U2)                   # deterministic
