@@ -54,8 +54,9 @@ class LogisticRegression(Scenario):
     name = "LogisticRegression"
     lik_kind = _lib.LIK_NONE
 
-    def __init__(self, features, labels, **kwargs):
+    def __init__(self, features, labels, variant=None, **kwargs):
         import torch
+        self.variant = variant          # None: tensor cores (bf16 operands) for ensembles of n >= 2048, exact fp32 below
         f = np.ascontiguousarray(np.asarray(features, np.float32))
         t = np.ascontiguousarray(np.asarray(labels, np.float32))
         if f.ndim != 2 or t.shape != (f.shape[0],):
@@ -71,4 +72,5 @@ class LogisticRegression(Scenario):
     def _potential_grad_device(self, X, temperature):
         from . import engine
         pscale = 1.0 / self.prior_std if self.prior_pscale is None else self.prior_pscale
-        return engine.logistic_potential_grad(self.features, self.labels, self.prior_mean, pscale, temperature, X)
+        variant = engine.interaction_variant(X.shape[0], min(self.dim, 60), self.variant)
+        return engine.logistic_potential_grad(self.features, self.labels, self.prior_mean, pscale, temperature, X, variant)

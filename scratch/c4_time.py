@@ -18,8 +18,13 @@ def tm(f, reps=5):
     for _ in range(reps): f()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps
-print("logistic pg ms", tm(lambda: sc._potential_grad_device(X, 1.0)))
-U, G = sc._potential_grad_device(X, 1.0)
+Xs = X * 0.2
+print("logistic pg ms (auto variant)", tm(lambda: sc._potential_grad_device(Xs, 1.0)))
+U, G = sc._potential_grad_device(Xs, 1.0)
+U0, G0 = engine.logistic_potential_grad(sc.features, sc.labels, 0.0, 1.0, 1.0, Xs, 0)
+print("  tc vs fp32: max|dG|/max|G| = %.2e, rel rms = %.2e, max rel dU = %.2e" % (
+    (G - G0).abs().max().item() / G0.abs().max().item(), ((G - G0).pow(2).mean().sqrt() / G0.pow(2).mean().sqrt()).item(),
+    ((U - U0).abs() / U0.abs()).max().item()))
 h = torch.tensor([7.0], device='cuda')
 print("phi tc ms", tm(lambda: engine.svgd_phi(X, G, h, 1)))
 print("mean bw tc ms", tm(lambda: kernels.mean_bandwidth_update(X, 1), 5), kernels.mean_bandwidth_update(X, 1).item(), kernels.mean_bandwidth_update(X, 0).item())
