@@ -1,0 +1,96 @@
+"""Host-side mirror of the reference API, checked on CPU the way the reference's own tests do
+(mocat/src/tests/test_core.py: Testcdict, TestSampler) plus the small pieces of host logic that decide what runs."""
+import numpy as np
+import numpy.testing as npt
+import pytest
+
+import mocat_b200 as mocat
+from mocat_b200 import core, engine, sample
+
+
+class TestCdict:                                                        # test_core.py:17-76
+    def _make(self):
+        return core.cdict(test_arr=np.ones((10, 3)), test_float=3.)
+
+    def test_init(self):
+        c = self._make()
+        assert hasattr(c, 'test_arr') and hasattr(c, 'test_float')
+        npt.assert_array_equal(c.test_arr, np.ones((10, 3)))
+        assert c.test_float == 3.
+
+    def test_copy(self):
+        c = self._make()
+        c2 = c.copy()
+        assert isinstance(c2, core.cdict) and isinstance(c2.test_float, float)
+        c2.test_arr = np.zeros(5)
+        c2.test_float = 9.
+        npt.assert_array_equal(c.test_arr, np.ones((10, 3)))
+        assert c.test_float == 3.
+
+    def test_getitem(self):
+        c0 = self._make()[0]
+        assert isinstance(c0, core.cdict)
+        npt.assert_array_equal(c0.test_arr, np.ones(3))
+        assert c0.test_float == 3.
+        idx = self._make()[np.array([1, 1, 4])]                         # the ancestor gather of core.py:46-56
+        assert idx.test_arr.shape == (3, 3)
+
+    def test_additem(self):
+        c = self._make()
+        other = core.cdict(test_arr=np.ones((2, 3)), test_float=7., time=25.)
+        c.time = 10.
+        s = c + other
+        assert isinstance(s, core.cdict)
+        npt.assert_array_equal(s.test_arr, np.ones((12, 3)))
+        assert s.time == 35. and s.test_float == 3.
+        npt.assert_array_equal(c.test_arr, np.ones((10, 3)))
+        assert c.time == 10.
+
+    def test_save_load(self, tmp_path):                                 # core.py:91-121
+        c = self._make()
+        c.save(tmp_path / "state")
+        back = core.load_cdict(tmp_path / "state.cdict")
+        npt.assert_array_equal(back.test_arr, c.test_arr)
+        with pytest.raises(RuntimeError):
+            c.save(tmp_path / "state")
+
+
+class TestSampler:                                                      # test_core.py:79-99
+    def test_init_and_deepcopy(self):
+        s = sample.Sampler(name='test', other=np.zeros(2))
+        assert s.name == 'test' and hasattr(s, 'parameters')
+        npt.assert_array_equal(s.parameters.other, np.zeros(2))
+        s2 = s.deepcopy()
+        assert isinstance(s2, sample.Sampler)
+        s2.name = 'other'
+        s2.parameters.other = 10.
+        assert s.name == 'test'
+        npt.assert_array_equal(s.parameters.other, np.zeros(2))
+
+
+def test_key_to_seed_accepts_jax_style_keys():
+    assert core.key_to_seed(None) == 0
+    assert core.key_to_seed(7) == 7
+    assert core.key_to_seed(np.array([1, 2], dtype=np.uint32)) == (1 << 32) | 2      # jax PRNGKey layout uint32[2]
+    assert core.key_to_seed(np.array([5], dtype=np.uint32)) == 5
+
+
+def test_interaction_variant_policy():
+    # exact fp32 kernels for small ensembles, tcgen05 (bf16 operands) from n = 2048 when d fits one K panel
+    assert engine.interaction_variant(100, 2) == 0
+    assert engine.interaction_variant(2048, 50) == 1
+    assert engine.interaction_variant(32768, 64) == 0
+    assert engine.interaction_variant(32768, 50, 0) == 0 and engine.interaction_variant(10, 2, 1) == 1
+
+
+def test_samplers_reject_what_the_device_cannot_run():
+    with pytest.raises(mocat._lib.MocatB200Error):
+        mocat.MetropolisedSMCSampler(object())                          # not a compiled move
+    with pytest.raises(TypeError):
+        class MyScenario(mocat.Scenario):                               # per-particle Python potential: no CPU fallback
+            def likelihood_potential(self, x, random_key=None):
+                return 0.0
+        MyScenario()
+    s = mocat.RMMetropolisedSMCSampler(mocat.Underdamped(stepsize=0.1), rm_stepsize=0.5)
+    assert s.parameters.rm_stepsize == 0.5 and s.check_every == 1 and s.mcmc_sampler.tuning.target == 0.651
+    assert mocat.RandomWalk(stepsize=0.1).tuning.target == 0.234        # standard_mcmc.py:29,84
