@@ -94,3 +94,51 @@ def test_samplers_reject_what_the_device_cannot_run():
     s = mocat.RMMetropolisedSMCSampler(mocat.Underdamped(stepsize=0.1), rm_stepsize=0.5)
     assert s.parameters.rm_stepsize == 0.5 and s.check_every == 1 and s.mcmc_sampler.tuning.target == 0.651
     assert mocat.RandomWalk(stepsize=0.1).tuning.target == 0.234        # standard_mcmc.py:29,84
+
+
+class _Probe(sample.Sampler):
+    name = 'probe'
+    flag = 1
+
+    def __init__(self, **kw):
+        super().__init__(**kw)
+        self.tuning = core.cdict(target=0.5)
+
+    def _run_device(self, scenario, initial_state, initial_extra):
+        return core.cdict(value=np.zeros((1, 2)), extra_iter=initial_extra.iter)
+
+
+def test_sampler_option_routing_and_startup_merge():
+    """sample.py:24-72: options named like attributes set attributes, the others become tunable parameters; startup
+    kwargs update both, and fill the run's `extra.parameters` only where the caller left a gap"""
+    s = _Probe(flag=2, stepsize=0.3, max_iter=50, unset=None)
+    assert s.flag == 2 and s.max_iter == 50 and not hasattr(s.parameters, 'flag')
+    assert s.parameters.stepsize == 0.3 and s.parameters.unset is None
+    extra = core.cdict(parameters=core.cdict(stepsize=None, other=7))
+    st, ex = s.startup(None, 10, None, extra, flag=3, stepsize=0.4, not_known=1)
+    assert s.flag == 3 and s.parameters.stepsize == 0.4 and not hasattr(s.parameters, 'not_known')
+    assert ex is extra and ex.iter == 0
+    assert ex.parameters.stepsize == 0.4 and ex.parameters.other == 7 and ex.parameters.unset is None
+    ex.iter = 5
+    ex.parameters.stepsize = 9.0
+    _, ex2 = s.startup(None, 10, None, ex)
+    assert ex2.iter == 5 and ex2.parameters.stepsize == 9.0               # caller's values win
+    s.max_iter = 2.5
+    with pytest.raises(AttributeError):
+        s.startup(None, 10, None, core.cdict())
+
+
+def test_run_driver_protocol():
+    """sample.py:110-148: class or instance, n and random_key recorded, summary and wall time attached"""
+    sc = core.cdict(name='toy')
+    out = sample.run(sc, _Probe, 4, 11, flag=9)
+    assert out.summary.sampler == 'probe' and out.summary.scenario == 'toy'
+    assert out.summary.parameters is not None and out.summary.tuning.target == 0.5
+    assert out.time >= 0.0 and out.extra_iter == 0
+    s = _Probe(stepsize=1.0)
+    ex = core.cdict(iter=3)
+    out = sample.run(core.cdict(), s, 8, None, initial_extra=ex)
+    assert s.n == 8 and not hasattr(ex, 'random_key') and out.extra_iter == 3
+    assert not hasattr(out.summary, 'scenario') and ex.parameters.stepsize == 1.0
+    with pytest.raises(NotImplementedError):
+        sample.run(core.cdict(), sample.Sampler(name='serial'), 1, 0)
