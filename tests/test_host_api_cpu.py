@@ -142,3 +142,45 @@ def test_run_driver_protocol():
     assert not hasattr(out.summary, 'scenario') and ex.parameters.stepsize == 1.0
     with pytest.raises(NotImplementedError):
         sample.run(core.cdict(), sample.Sampler(name='serial'), 1, 0)
+
+
+def test_smc_sampler_startup_chain_without_device(monkeypatch):
+    """the whole host start-up path of a tempered SMC run (Sampler -> TransportSampler -> TemperedSMCSampler ->
+    MetropolisedSMCSampler) with the device engine replaced by a recorder: options routed, engine configured from
+    the sampler's parameters, temperature reset, chain cleaned"""
+    from mocat_b200 import transport, _lib
+
+    calls = {}
+
+    class FakeEngine:
+        def __init__(self, target, move, temper, n, seed, resampling, schedule):
+            calls.update(target=target, move=move, temper=temper, n=n, seed=seed, resampling=resampling, schedule=schedule)
+
+        def startup(self, x0):
+            calls['x0'] = x0
+
+    monkeypatch.setattr(engine.SMCEngine, 'acquire',
+                        classmethod(lambda cls, target, move, temper, n, seed, resampling=0, schedule=None:
+                                    FakeEngine(target, move, temper, n, seed, resampling, schedule)))
+
+    def fake_loop(self, scenario, state, extra):
+        assert extra.engine is state.engine and extra.iter == 0
+        return core.cdict(temperature=np.array([0.0, 0.4, 1.0]), value=np.zeros((3, 5, 2)))
+
+    monkeypatch.setattr(transport.MetropolisedSMCSampler, '_run_device', fake_loop)
+    sc = mocat.scenarios.Rastrigin(dim=2, a=1.0, prior_std=3.0)
+    smp = mocat.MetropolisedSMCSampler(mocat.Underdamped(stepsize=0.25, leapfrog_steps=3), mcmc_steps=2,
+                                       ess_threshold_retain=0.8, max_iter=77)
+    x0 = np.ones((5, 2), np.float32)
+    out = mocat.run(sc, smp, 5, np.array([0, 9], dtype=np.uint32), initial_state=mocat.cdict(value=x0),
+                    resampling='systematic', ess_threshold_resample=0.3)
+    assert calls['n'] == 5 and calls['seed'] == 9 and calls['x0'] is x0
+    assert calls['resampling'] == _lib.RESAMPLE_SYSTEMATIC and smp.resampling == 'systematic'        # attribute option
+    mv, tp = calls['move'], calls['temper']
+    assert mv.kind == _lib.MOVE_MALA and mv.mcmc_steps == 2 and mv.leapfrog_steps == 3
+    assert abs(mv.stepsize - 0.25) < 1e-7
+    assert tp.ess_retain == 0.8 and tp.ess_resample == 0.3 and tp.max_iter == 77                     # parameter option
+    assert calls['target'].dim == 2 and calls['target'].kind == _lib.LIK_RASTRIGIN
+    assert sc.temperature == 1.0                                         # clean_chain: smc.py:177-184
+    assert out.summary.sampler == smp.name and out.summary.scenario == 'Rastrigin'
+    assert out.summary.parameters.mcmc_steps == 2
