@@ -83,3 +83,37 @@ def test_svgd_gaussian_moments():
     x = s.run()
     npt.assert_array_almost_equal(x.mean(0), np.zeros(2), decimal=0)
     npt.assert_array_almost_equal(np.cov(x.T), POST_COV, decimal=1)
+
+
+def test_exact_cdf_is_order_and_sharding_independent():
+    """the claim behind bit-exact ancestors on any tile order / any number of GPUs: the quantised
+    weights are multiples of 2^-52 that sum below 2, so every fp64 partial sum is exact and ANY association of the
+    additions gives the same bits -- sequential cumsum, reversed, pairwise tree, per-shard scans + offsets"""
+    from fractions import Fraction
+    rng = np.random.default_rng(5)
+    for n in (1, 7, 1000, 65_537):
+        w = rng.random(n).astype(np.float32) ** 5
+        w[rng.random(n) < 0.2] = 0.0
+        w[0] = max(w[0], 1e-3)
+        w = (w / w.astype(np.float64).sum()).astype(np.float32)
+        q = core.quantise_weights(w)
+        assert np.all(q * 2.0 ** 52 == np.rint(q * 2.0 ** 52))              # multiples of 2^-52
+        total = np.cumsum(q)[-1]
+        assert total < 2.0
+        if n <= 1000:                                                       # exact rational check of the fp64 sum
+            assert Fraction(float(total)) == sum(Fraction(float(v)) for v in q)
+        assert np.cumsum(q[::-1])[-1] == total                              # reversed order
+        tree = q.copy()                                                     # pairwise tree reduction
+        while tree.size > 1:
+            if tree.size % 2:
+                tree = np.append(tree, 0.0)
+            tree = tree[0::2] + tree[1::2]
+        assert tree[0] == total
+        ref = np.cumsum(q)
+        for shards in (2, 3, 8):                                            # per-shard scans + exclusive offsets
+            parts = np.array_split(q, shards)
+            offs = np.concatenate([[0.0], np.cumsum([p.sum() for p in parts])])
+            glued = np.concatenate([o + np.cumsum(p) for o, p in zip(offs, parts) if p.size])
+            assert np.array_equal(glued, ref)
+        perm = rng.permutation(n)                                           # any permutation: same total bits
+        assert np.cumsum(q[perm])[-1] == total
