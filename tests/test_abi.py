@@ -65,3 +65,13 @@ def test_no_cpu_fallback_and_no_oracle_in_product(built):
             if f.endswith(".py"):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f"{f} imports the oracle"
+
+
+def test_integration_doc_names_every_entry_point():
+    """INTEGRATION.md must say, for every exported symbol, which reference function it stands in for"""
+    import os
+    from mocat_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "INTEGRATION.md")).read()
+    missing = [s for s in _lib.SIGNATURES if s not in text]
+    assert not missing, missing
