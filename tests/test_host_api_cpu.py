@@ -184,3 +184,31 @@ def test_smc_sampler_startup_chain_without_device(monkeypatch):
     assert sc.temperature == 1.0                                         # clean_chain: smc.py:177-184
     assert out.summary.sampler == smp.name and out.summary.scenario == 'Rastrigin'
     assert out.summary.parameters.mcmc_steps == 2
+
+
+def test_kalman_filter_host_matches_oracle_and_struct_mirror():
+    """run_kalman_filter_for_marginals (ssm/linear_gaussian/kalman.py:16-57; host NumPy, cross-check only) against the
+    oracle recursion, and the POD mirror of the model that the filter kernels receive"""
+    from oracle import models as omodels, pf as opf
+    F = np.array([[0.9, 0.1], [0.0, 0.8]])
+    Q = np.array([[0.5, 0.1], [0.1, 0.4]])
+    H = np.array([[1.0, 0.5]])
+    R = np.array([[0.3]])
+    P0 = np.array([[1.5, 0.2], [0.2, 0.7]])
+    m0 = np.array([0.3, -0.2])
+    sc = mocat.ssm.TimeHomogenousLinearGaussian(initial_mean=m0, initial_covariance=P0, transition_matrix=F,
+                                                transition_covariance=Q, likelihood_matrix=H, likelihood_covariance=R)
+    assert sc.dim == 2 and sc.dim_obs == 1
+    sim = sc.simulate(np.arange(15.0), 4)
+    assert sim.x.shape == (15, 2) and sim.y.shape == (15, 1)
+    mus, covs, ll = mocat.ssm.run_kalman_filter_for_marginals(sc, sim.y, sim.t, return_log_likelihood=True)
+    omus, ocovs, oll = opf.kalman_filter(omodels.LinearGaussianSSM(m0, P0, F, Q, H, R), sim.y)
+    npt.assert_allclose(mus, omus, rtol=1e-12, atol=1e-12)
+    npt.assert_allclose(covs, ocovs, rtol=1e-12, atol=1e-12)
+    npt.assert_allclose(ll, oll, rtol=1e-12)
+    s = sc._ssm()                                                        # what mb_pf_init / mb_pf_step receive
+    assert s.kind == mocat._lib.SSM_LINEAR_GAUSSIAN and s.dim == 2 and s.dim_obs == 1
+    stride = mocat._lib.MB_MAX_SMALL_DIM
+    npt.assert_allclose([s.F[0], s.F[1], s.F[stride], s.F[stride + 1]], F.ravel(), rtol=1e-7)
+    LQ = np.linalg.cholesky(Q)
+    npt.assert_allclose([s.LQ[0], s.LQ[stride], s.LQ[stride + 1]], [LQ[0, 0], LQ[1, 0], LQ[1, 1]], rtol=1e-6)
