@@ -140,6 +140,9 @@ int         mb_abi_version(void);
 mb_ctx*     mb_create(int device);
 void        mb_destroy(mb_ctx* ctx);
 int         mb_sm_count(mb_ctx* ctx);
+/* Generation of the context-owned workspaces (scratch, scan status): bumped whenever one of them is reallocated.
+ * A CUDA graph captured from these entry points embeds the old addresses and must be re-captured after a change. */
+unsigned long long mb_workspace_generation(mb_ctx* ctx);
 
 /* ---- K2: log-sum-exp / ESS reduction.  Replaces metrics.py:69-78 (log_ess_log_weight), the logsumexp
  *      calls at transport/smc.py:160,214-215,288 and MetropolisedSMCSampler.log_ess (smc.py:303-309).

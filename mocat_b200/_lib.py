@@ -129,6 +129,7 @@ SIGNATURES = {
     "mb_quantile": (C.c_int, [c_vp, c_vp, c_i64, c_d, c_vp, c_vp]),
     "mb_colstats": (C.c_int, [c_vp, c_vp, c_i64, c_i64, C.c_int, c_vp, c_vp, c_vp]),
     "mb_target_potential_grad": (C.c_int, [c_vp, C.POINTER(Target), c_d, c_vp, C.c_int, c_vp, c_vp, c_vp]),
+    "mb_workspace_generation": (C.c_uint64, [c_vp]),
     "mb_cond_begin": (C.c_int, [c_vp, c_vp, c_vp, c_vp]),
     "mb_cond_end": (C.c_int, [c_vp, c_vp]),
     "mb_prior_sample": (C.c_int, [c_vp, c_f, c_f, C.c_int, c_i64, c_u64, c_i64, c_vp, c_vp]),

@@ -73,6 +73,8 @@ extern "C" void mb_destroy(mb_ctx* ctx) {
 
 extern "C" int mb_sm_count(mb_ctx* ctx) { return ctx ? ctx->sms : 0; }
 
+extern "C" unsigned long long mb_workspace_generation(mb_ctx* ctx) { return ctx ? ctx->ws_generation : 0ull; }
+
 int mb_ensure_scratch(mb_ctx* ctx, size_t bytes) {
     if (bytes <= ctx->scratch_bytes) return MB_OK;
     MB_CUDA(cudaDeviceSynchronize());
@@ -82,6 +84,7 @@ int mb_ensure_scratch(mb_ctx* ctx, size_t bytes) {
     size_t nb = bytes + (bytes >> 1);
     MB_CUDA(cudaMalloc(&ctx->scratch, nb));
     ctx->scratch_bytes = nb;
+    ctx->ws_generation++;
     return MB_OK;
 }
 
@@ -96,6 +99,7 @@ int mb_ensure_scan(mb_ctx* ctx, int64_t tiles) {
     MB_CUDA(cudaMalloc(&ctx->scan_incl, sizeof(double) * cap));
     MB_CUDA(cudaMemset(ctx->scan_flag, 0, sizeof(int32_t) * cap));
     ctx->scan_tiles_cap = cap;
+    ctx->ws_generation++;
     ctx->scan_epoch = 0;
     return MB_OK;
 }

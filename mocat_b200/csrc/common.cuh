@@ -48,6 +48,7 @@ struct mb_ctx {
     // generic scratch
     void*     scratch;
     size_t    scratch_bytes;
+    unsigned long long ws_generation;   // bumped whenever scratch / scan buffers move: captured graphs hold the old pointers
     // intra-GPU flag-in-data exchange of the resident tempering kernel: [2][MB_LL_BLOCKS][8] words + sequence counter
     unsigned long long* ll_slots;
     // CUDA-graph conditional capture (mb_cond_begin / mb_cond_end)

@@ -199,6 +199,7 @@ class SMCEngine(_Resampler):
         self.enqueued = 0
         self.use_graphs = os.environ.get("MOCAT_B200_GRAPHS", "1") != "0"
         self._graphs = [None, None]
+        self._ws_gen = None
         self.comm = None          # mb_comm* when the population is sharded over several GPUs (parallel.py)
 
     def _shard_ref(self):
@@ -256,6 +257,12 @@ class SMCEngine(_Resampler):
         events: optional list of 4 torch.cuda.Event recorded before / between / after the kernel groups
         (forces the plain path)."""
         if events is None and self.use_graphs and self.enqueued >= 1:
+            # graphs embed the addresses of the context's workspaces: another engine (a larger population, an SVGD
+            # ensemble) may have made them grow since the capture
+            gen = self.L.dll.mb_workspace_generation(self.ctx)
+            if gen != self._ws_gen:
+                self._graphs = [None, None]
+                self._ws_gen = gen
             g = self._graphs[self.cur]
             if g is None:
                 g = self._capture()
