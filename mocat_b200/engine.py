@@ -259,7 +259,7 @@ class SMCEngine(_Resampler):
         if events is None and self.use_graphs and self.enqueued >= 1:
             # graphs embed the addresses of the context's workspaces: another engine (a larger population, an SVGD
             # ensemble) may have made them grow since the capture
-            gen = self.L.dll.mb_workspace_generation(self.ctx)
+            gen = int(self.L.dll.mb_workspace_generation(self.ctx))
             if gen != self._ws_gen:
                 self._graphs = [None, None]
                 self._ws_gen = gen
