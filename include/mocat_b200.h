@@ -132,6 +132,8 @@ typedef struct {
     const float*  x_peers[MB_MAX_WORLD];     /* input value block (d x ld) of every rank for this step   */
     const double* cdf_peers[MB_MAX_WORLD];   /* rank-relative exact fp64 CDF of every rank               */
     const double* totals;                    /* device [world]: quantised weight total of every rank     */
+    int32_t*      anc_peers[MB_MAX_WORLD];   /* ancestor array (n_local int32) of every rank: the fused   */
+                                             /* resampler writes an output's ancestor where the output lives */
 } mb_shard;
 
 /* ---- context ---------------------------------------------------------------------------------- */
@@ -227,6 +229,45 @@ int mb_pf_step(mb_ctx* ctx, const mb_ssm* ssm, const float* x_in, float* x_out, 
                int64_t n_total, const int32_t* anc, const float* y, float* lw, uint64_t seed, uint32_t t,
                int64_t gid0, double ess_threshold, mb_control* ctl, mb_hist* hist, const mb_shard* sh /*or NULL*/,
                mb_comm* comm /*or NULL*/, mb_stream_t stream);
+
+/* ---- K1b', Lorenz-96 (config C3): same contract as mb_pf_init / mb_pf_step for MB_SSM_LORENZ96 (dim 8, 16 or 40,
+ *      H = I, diagonal noise, `substeps` RK4 steps per observation interval; ssm/scenarios/lorenz96.py:14-44 on
+ *      ssm/nonlinear_gaussian.py:107-121) on the TILED layout: particle i, coordinate k lives at
+ *      x + (i >> 5) * (dim * 32) + k * 32 + (i & 31)  (32-particle tiles; allocate ceil(n/32) tiles, lw padded to a
+ *      multiple of 32).  A particle pair is spread over four lanes and advanced with packed fp32x2 arithmetic;
+ *      normals: Philox counter (gid >> 1, t, purpose << 20 | k / 2), words (2 (k & 1), 2 (k & 1) + 1), Box-Muller cos
+ *      branch -> even particle, sin branch -> odd particle (gid0 must be even).  anc holds GLOBAL ancestor ids. */
+int mb_pf_l96_init(mb_ctx* ctx, const mb_ssm* ssm, float* x_tiled, int64_t n, int64_t n_total, const float* y0,
+                   float* lw, uint64_t seed, int64_t gid0, double ess_threshold, mb_control* ctl, mb_hist* hist,
+                   mb_comm* comm /*or NULL*/, mb_stream_t stream);
+int mb_pf_l96_step(mb_ctx* ctx, const mb_ssm* ssm, const float* x_in_tiled, float* x_out_tiled, int64_t n,
+                   int64_t n_total, const int32_t* anc, const float* y, float* lw, uint64_t seed, uint32_t t,
+                   int64_t gid0, double ess_threshold, mb_control* ctl, mb_hist* hist, const mb_shard* sh /*or NULL*/,
+                   mb_comm* comm /*or NULL*/, mb_stream_t stream);
+/* gather of a tiled population by ancestor (cdict.__getitem__, core.py:46-56; resample_particles, filtering.py:202-217).
+ * staged != 0: when a 32-output tile's ancestors span <= 3 source tiles the window is staged in shared memory with
+ * cp.async.bulk (TMA bulk copies completing on an mbarrier); staged == 0: direct loads (comparison path). */
+int mb_gather_tiled(mb_ctx* ctx, const int32_t* anc, int64_t n_out, int d, const float* src_tiled, int64_t n_src,
+                    float* dst_tiled, int staged, mb_stream_t stream);
+/* weighted moments of a tiled population (per-step diagnostics instead of the stacked history, filtering.py:317-322) */
+int mb_weighted_moments_tiled(mb_ctx* ctx, const float* x_tiled, int64_t n, int d, const float* lw,
+                              const mb_control* ctl, double* mean, double* var, mb_stream_t stream);
+
+/* ---- K4+K5 fused: systematic resampling without a materialised CDF (transport/smc.py:61-71,
+ *      ssm/filtering.py:196-199).  Integer weights e_i = rint(w_i 2^K) (w_i = exp(lw_i - ctl->wmax) in log mode, the
+ *      caller's weight <= 1 in linear mode; K = min(40, 63 - ceil(log2 n_total))), exact uint64 cumulative sums C_j,
+ *      total S, u0 = k0 / 2^32, and in exact rational arithmetic  a_i = min{ j : (i + u0)/n_total < C_j / S }.
+ *      mb_rs_tile_sums: per-4096-particle sums + their exclusive scan into the caller's workspace `ws`
+ *      (mb_rs_workspace_bytes(n) bytes; its first 8 bytes are the shard total, the word to exchange between ranks);
+ *      mb_rs_ancestors: ancestors of the outputs fed by this shard's particles, written to anc (single shard) or to
+ *      sh->anc_peers[owner of the output] (sharded; totals = device [world] uint64 shard totals).  k0 >= 0: caller's
+ *      u0 bits; k0 < 0: Philox(ctl->seed, step ctl->iter + 1, P_RESAMPLE).x.  Predicated on ctl->resample unless force. */
+size_t mb_rs_workspace_bytes(int64_t n);
+int mb_rs_tile_sums(mb_ctx* ctx, void* ws, const float* in, int64_t n, int64_t n_total, int log_mode,
+                    const mb_control* ctl, int force, mb_stream_t stream);
+int mb_rs_ancestors(mb_ctx* ctx, void* ws, const float* in, int64_t n, int64_t n_total, int log_mode,
+                    const mb_control* ctl, int force, int64_t k0, const unsigned long long* totals,
+                    const mb_shard* sh /*or NULL*/, int32_t* anc, mb_stream_t stream);
 
 /* weighted mean / variance of every column under weights exp(lw - ctl->wmax)/s1  (diagnostics) */
 int mb_weighted_moments(mb_ctx* ctx, const float* x, int64_t ld, int64_t n, int d, const float* lw,

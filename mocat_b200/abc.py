@@ -138,27 +138,37 @@ class MetropolisedABCSMCSampler(ABCSMCSampler):
         import torch
         eng = initial_extra.engine
         keep = self.keep_history
-        if keep is None:
-            keep = eng.n * 12 * 4 * min(self.max_iter + 1, 64) <= HISTORY_AUTO_BYTES
-        snaps = [self._snapshot(eng)] if keep else None
-        steps = []
+        auto = keep is None
+        if auto:
+            keep = eng.n * 12 * 4 * 2 <= HISTORY_AUTO_BYTES
+        if self.max_iter > engine.MB_HIST_MAX - 1:
+            raise _lib.MocatB200Error(f"max_iter <= {engine.MB_HIST_MAX - 1} (device history ring)")
+        # snapshots go to the host at the end of every burst; an automatic history that outgrows the budget is dropped
+        host_snaps, pending, kept_bytes = [], ([self._snapshot(eng)] if keep else []), 0
         it = 0
         while it < self.max_iter:
             for _ in range(min(self.check_every, self.max_iter - it)):
                 eng.update()
                 it += 1
                 if keep:
-                    snaps.append(self._snapshot(eng))
-                    steps.append(eng.stepsize.clone())
-            if eng.ctl.read()['done']:
+                    pending.append(self._snapshot(eng))
+            done = bool(eng.ctl.read()['done'])
+            if keep:
+                for sn in pending:
+                    host_snaps.append({k: v.cpu().numpy() for k, v in sn.items()})
+                    kept_bytes += sum(v.nbytes for v in host_snaps[-1].values())
+                pending = []
+                if auto and kept_bytes > HISTORY_AUTO_BYTES:
+                    keep, host_snaps = False, []
+            if done:
                 break
-        c = eng.ctl.read()
+        c = eng.settle()                                                 # valid ping-pong buffers of the last real step
         iters = int(c['iter'])
         hist = eng.ctl.read_hist(iters + 1)
         chain = cdict()
         if keep:
             for k in self._FIELDS:
-                setattr(chain, k, torch.stack([s[k] for s in snaps[:iters + 1]]).cpu().numpy())
+                setattr(chain, k, np.stack([sn[k] for sn in host_snaps[:iters + 1]]))
         else:
             for k, v in self._snapshot(eng).items():
                 setattr(chain, k, v.cpu().numpy()[None])

@@ -15,83 +15,104 @@ from pathlib import Path
 import numpy as np
 
 
+def _stacked(value):
+    """array-like state fields take part in indexing / concatenation (core.py:46-56, 58-74)"""
+    return isinstance(value, np.ndarray) and value.ndim > 0
+
+
+def _nested(value):
+    return isinstance(value, cdict) and not isinstance(value, static_cdict)
+
+
 class cdict:
-    def __init__(self, **kwargs):
-        self.__dict__.update(kwargs)
+    """Attribute container for sampler state and results (interface of mocat/src/core.py:20-84, NumPy-backed).
 
-    def copy(self):
-        return cdict(**self.__dict__)
+    c.field / c['field'] read a field; c[index] applies `index` to every stacked array field (and to nested cdicts);
+    a + b appends b's stacked fields to a's along axis 0 (scalars named `time` add up); save/load go through pickle.
+    Fields flagged `_mocat_transient` (device engines, CUDA handles) belong to the live session only: they are shared
+    by copy() and dropped when the container is pickled."""
 
-    def deepcopy(self):
-        return copy.deepcopy(self)
+    def __init__(self, **fields):
+        vars(self).update(fields)
+
+    # -- mapping-like access
+    def keys(self):
+        return vars(self).keys()
+
+    def __iter__(self):
+        return iter(vars(self))
+
+    @property
+    def is_empty(self):
+        return len(vars(self)) == 0
 
     def __repr__(self):
-        return f"mocat.cdict({self.__dict__.__repr__()})"
+        return f"mocat.cdict({vars(self)!r})"
+
+    def __getitem__(self, item):
+        if isinstance(item, str):
+            return vars(self)[item]
+        picked = {k: (v[item] if (_stacked(v) or _nested(v)) else v) for k, v in vars(self).items()}
+        return type(self)(**picked) if type(self) is cdict else cdict(**picked)
+
+    # -- copies
+    def copy(self):
+        return cdict(**vars(self))
+
+    def deepcopy(self):
+        keep = {k: v for k, v in vars(self).items() if getattr(v, '_mocat_transient', False)}
+        rest = copy.deepcopy({k: v for k, v in vars(self).items() if k not in keep})
+        return cdict(**rest, **keep)
+
+    # -- concatenation along the leading (iteration) axis
+    def __add__(self, other):
+        merged = dict(vars(self))
+        if other is None:
+            return cdict(**merged)
+        theirs = vars(other)
+        for key in merged.keys() & theirs.keys():
+            mine, new = merged[key], theirs[key]
+            if isinstance(mine, np.ndarray) or isinstance(new, np.ndarray):
+                merged[key] = np.concatenate([np.atleast_1d(mine), np.atleast_1d(new)], axis=0)
+            elif (_nested(mine) and _nested(new)) or key == 'time':
+                merged[key] = mine + new
+        return cdict(**merged)
+
+    # -- persistence
+    def __getstate__(self):
+        return {k: v for k, v in vars(self).items() if not getattr(v, '_mocat_transient', False)}
+
+    def __setstate__(self, state):
+        vars(self).update(state)
 
     def save(self, path, overwrite=False):
         save_cdict(self, path, overwrite)
 
-    def __getitem__(self, item):
-        if isinstance(item, str):
-            return self.__dict__[item]
-        out = self.copy()
-        for key, attr in out.__dict__.items():
-            if (isinstance(attr, np.ndarray) and attr.ndim > 0) \
-                    or (isinstance(attr, cdict) and not isinstance(attr, static_cdict)):
-                out.__setattr__(key, attr[item])
-        return out
-
-    def __add__(self, other):
-        out = self.copy()
-        if other is None:
-            return out
-        for key, attr in out.__dict__.items():
-            if hasattr(other, key):
-                o = other.__dict__[key]
-                if isinstance(attr, np.ndarray) or isinstance(o, np.ndarray):
-                    out.__setattr__(key, np.append(np.atleast_1d(attr), np.atleast_1d(o), axis=0))
-                elif (isinstance(attr, cdict) and not isinstance(attr, static_cdict)
-                      and isinstance(o, cdict) and not isinstance(o, static_cdict)) or key == 'time':
-                    out.__setattr__(key, attr + o)
-        return out
-
-    @property
-    def is_empty(self):
-        return self.__dict__ == {}
-
-    def keys(self):
-        return self.__dict__.keys()
-
-    def __iter__(self):
-        return self.__dict__.__iter__()
-
 
 class static_cdict(cdict):
-    pass
+    """a cdict whose fields are NOT indexed or concatenated with the state (parameters, summaries)"""
+
+
+def _cdict_path(path):
+    path = Path(path)
+    return path if path.suffix == '.cdict' else path.with_suffix('.cdict')
 
 
 def save_cdict(in_cdict, path, overwrite=False):
-    path = Path(path)
-    if path.suffix != '.cdict':
-        path = path.with_suffix('.cdict')
-    path.parent.mkdir(parents=True, exist_ok=True)
-    if path.exists():
-        if overwrite:
-            path.unlink()
-        else:
-            raise RuntimeError(f'File {path} already exists.')
-    with open(path, 'wb') as file:
-        pickle.dump(in_cdict, file)
+    """pickle to `<path>.cdict` (core.py:91-108); refuses to clobber an existing file unless overwrite"""
+    target = _cdict_path(path)
+    if target.exists() and not overwrite:
+        raise RuntimeError(f"{target} exists; pass overwrite=True to replace it")
+    target.parent.mkdir(parents=True, exist_ok=True)
+    target.write_bytes(pickle.dumps(in_cdict))
 
 
 def load_cdict(path):
-    path = Path(path)
-    if not path.is_file():
-        raise ValueError(f'Not a file: {path}')
-    if path.suffix != '.cdict':
-        raise ValueError(f'Not a .cdict file: {path}')
-    with open(path, 'rb') as file:
-        return pickle.load(file)
+    """inverse of save_cdict (core.py:111-121)"""
+    source = Path(path)
+    if source.suffix != '.cdict' or not source.is_file():
+        raise ValueError(f"{source}: expected an existing .cdict file")
+    return pickle.loads(source.read_bytes())
 
 
 def key_to_seed(random_key):

@@ -1,0 +1,449 @@
+// pf_l96.cu -- bootstrap-filter step of the Lorenz-96 state-space model (config C3), the hot kernel of the bench.
+//
+// Replaces one body of the scan in run_particle_filter_for_marginals (ssm/filtering.py:280-311) for
+// Lorenz96(NonLinearGaussian) (ssm/scenarios/lorenz96.py:14-44, ssm/nonlinear_gaussian.py:107-121) with diagonal noise,
+// H = I and the fixed-step RK4 flow: ancestor gather (core.py:46-56), transition_sample, log-weight
+// increment -likelihood_potential, (max, sum, sumsq) of the weights, log-evidence and the next resample decision.
+//
+// Why a kernel of its own (round 1 ran this model through the generic one-thread-per-particle kernel at 54 % of the
+// HBM roofline, issue bound at 128 registers / 16 warps per SM, ~2100 SASS instructions per particle):
+//   * TILED layout (AoSoA): particle i, coordinate k lives at base + (i >> 5) * (D*32) + k*32 + (i & 31).  The D values
+//     of a particle sit in one D*128-byte tile, every column is reached with an IMMEDIATE offset from one base pointer
+//     (no 64-bit address arithmetic per column), and a gathered ancestor touches one tile instead of D pages.
+//   * A particle PAIR (2m, 2m+1) is spread over FOUR lanes, D/4 coordinates each: 3*D/4 packed registers of RK4 state
+//     per thread instead of 3*D (<= 64 registers, 32 warps per SM).  The cyclic stencil needs three neighbour values per
+//     stage; they come from the adjacent lanes by warp shuffle.
+//   * The two particles of a pair live in the two halves of 64-bit registers and every RK4 / noise / likelihood
+//     operation is a packed fp32x2 instruction (FFMA2 / FADD2: Blackwell), i.e. half the issue slots per flop.
+//   * Box-Muller naturally yields two normals per (u1, u2): the cos branch goes to the even particle of the pair, the
+//     sin branch to the odd one, so they arrive packed.  Philox counter = (pair id, step, purpose<<20 | coordinate/2):
+//     words (0,1) -> coordinate 2c, words (2,3) -> coordinate 2c+1  (mirrored by oracle/philox.py normals_pairwise).
+#include <stdlib.h>
+#include "common.cuh"
+#include "rng.cuh"
+#include "comm.cuh"
+#include "pf_common.cuh"
+
+const MbCommDev* mb_comm_dev(const mb_comm* c);
+
+typedef unsigned long long f2;      // two packed fp32: low half = even particle of the pair, high half = odd particle
+
+__device__ __forceinline__ f2 f2_pack(float lo, float hi) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void f2_unpack(f2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f2 f2_splat(float v) { return f2_pack(v, v); }
+__device__ __forceinline__ f2 f2_fma(f2 a, f2 b, f2 c) { f2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f2 f2_add(f2 a, f2 b) { f2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f2 f2_sub(f2 a, f2 b) { f2 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f2 f2_mul(f2 a, f2 b) { f2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+
+// Box-Muller pair scaled by `sd` (rng.cuh box_muller folded with the scaling and trimmed for issue slots):
+//   (zc, zs) = sd * sqrt(-2 ln u1) * (cos, sin)(2 pi u2),  u1 = u_open(xa) = (float(xa) + .5) 2^-32,  u2 = u24(xb).
+// lg2(u1) = lg2(float(xa) + .5) - 32 exactly, so the 2^-32 scaling and sd^2 fold into one FFMA under the square root;
+// the angle is evaluated on phi = 2 pi u2 - pi (cos(2 pi u2) = -cos(phi)), the sign is taken by the consumer's FMA.
+// returns rq = sd * sqrt(-2 ln u1) and (c, s) = (cos, sin)(phi):  zc = -rq c,  zs = -rq s.
+__device__ __forceinline__ void box_muller_scaled(uint32_t xa, uint32_t xb, float k1, float k0, float& rq, float& c, float& s) {
+    const float v = __fadd_rn(__uint2float_rn(xa), 0.5f);
+    float l2;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(v));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rq) : "f"(fmaf(l2, k1, k0)));      // k1 = -2 ln2 sd^2, k0 = 64 ln2 sd^2
+    const float phi = fmaf((float)(xb >> 8), 3.7450703e-7f, -3.141592653589793f);  // 2 pi 2^-24
+    __sincosf(phi, &s, &c);
+}
+
+#define L96_THREADS 256
+#define L96_WARPS (L96_THREADS / 32)
+
+struct L96Consts {                   // packed constants of the flow
+    f2 F, hh, hf, h6, two;
+};
+
+// slope of coordinate r of this lane: (x[r+1] - x[r-2]) * x[r-1] + (F - x[r]), lorenz96.py:18-19; indices outside
+// [0, CPL) are the halo values received from the neighbouring lanes
+#define L96_EXT(arr, r) ((r) == -2 ? hm2 : ((r) == -1 ? hm1 : ((r) == CPL ? hp1 : arr[((r) < 0 || (r) >= CPL) ? 0 : (r)])))
+#define L96_SLOPE(arr, r) f2_fma(f2_sub(L96_EXT(arr, (r) + 1), L96_EXT(arr, (r) - 2)), L96_EXT(arr, (r) - 1), f2_sub(c.F, arr[r]))
+#define L96_HALO(arr)                                                  \
+    const f2 hm2 = __shfl_sync(MB_FULL, arr[CPL - 2], prev);           \
+    const f2 hm1 = __shfl_sync(MB_FULL, arr[CPL - 1], prev);           \
+    const f2 hp1 = __shfl_sync(MB_FULL, arr[0], next);
+
+// one classical RK4 step (device definition of the L96 flow, SURVEY 8c / DESIGN.md)
+template <int CPL>
+__device__ __forceinline__ void l96_rk4(f2 (&x)[CPL], const L96Consts& c, int prev, int next) {
+    f2 acc[CPL], sa[CPL], sb[CPL];
+    {
+        L96_HALO(x)
+#pragma unroll
+        for (int r = 0; r < CPL; ++r) { const f2 k = L96_SLOPE(x, r); acc[r] = k; sa[r] = f2_fma(c.hh, k, x[r]); }
+    }
+    {
+        L96_HALO(sa)
+#pragma unroll
+        for (int r = 0; r < CPL; ++r) { const f2 k = L96_SLOPE(sa, r); acc[r] = f2_fma(c.two, k, acc[r]); sb[r] = f2_fma(c.hh, k, x[r]); }
+    }
+    {
+        L96_HALO(sb)
+#pragma unroll
+        for (int r = 0; r < CPL; ++r) { const f2 k = L96_SLOPE(sb, r); acc[r] = f2_fma(c.two, k, acc[r]); sa[r] = f2_fma(c.hf, k, x[r]); }
+    }
+    {
+        L96_HALO(sa)
+#pragma unroll
+        for (int r = 0; r < CPL; ++r) { const f2 k = L96_SLOPE(sa, r); x[r] = f2_fma(c.h6, f2_add(acc[r], k), x[r]); }
+    }
+}
+
+struct L96Args {
+    float forcing, h, ir, lik_const, zmean, bm_k1, bm_k0;   // zmean: initial mean; bm_k*: folded Box-Muller scale
+    int substeps;
+    const float* x_in; float* x_out; int64_t n;
+    const int32_t* anc; const float* y; float* lw;
+    int64_t gid0;
+    const float* x_peers[MB_MAX_WORLD]; int64_t n_local; int world; int sharded;
+    PfTail tail;
+};
+
+// OCC: resident blocks per SM the register allocation is tuned for; ROUNDS: Philox rounds (10 = production; the 7-round
+// variant exists only to measure how much of the step is RNG, MB_L96_VARIANT=37 / 47, and is never the default)
+template <int D, bool INIT, int OCC = 3, int ROUNDS = 10>
+__global__ void __launch_bounds__(L96_THREADS, INIT ? 2 : OCC) pf_l96_kernel(L96Args a) {
+    static_assert(D % 8 == 0, "the lane split needs an even number of coordinates per lane");
+    constexpr int CPL = D / 4;                       // coordinates per lane
+    constexpr int TILE = D * 32;                     // floats per 32-particle tile
+    mb_control* ctl = a.tail.ctl;
+    if (!INIT && ctl->done) return;
+    const bool resample = !INIT && ctl->resample != 0;
+    __shared__ Lse3 smem[L96_WARPS];
+    __shared__ f2 ysm[D];
+    __shared__ const float* peers[MB_MAX_WORLD];
+    __shared__ int64_t bounds[MB_MAX_WORLD];         // first global id of every rank (sharded gather)
+    if (threadIdx.x < D) ysm[threadIdx.x] = f2_splat(a.y[threadIdx.x] * a.ir);
+    if (threadIdx.x < MB_MAX_WORLD) {
+        peers[threadIdx.x] = a.sharded ? a.x_peers[threadIdx.x] : a.x_in;
+        bounds[threadIdx.x] = (threadIdx.x < a.world) ? (int64_t)threadIdx.x * a.n_local : INT64_MAX;
+    }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, p = lane & 3;
+    const int prev = (lane & ~3) | ((p + 3) & 3), next = (lane & ~3) | ((p + 1) & 3);
+    const uint64_t seed = a.tail.seed;
+    L96Consts c;
+    c.F = f2_splat(a.forcing); c.hh = f2_splat(0.5f * a.h); c.hf = f2_splat(a.h); c.h6 = f2_splat(a.h * (1.f / 6.f));
+    c.two = f2_splat(2.f);
+    const f2 nir = f2_splat(-a.ir), zmean = f2_splat(a.zmean);
+    const int coff = (CPL * p) * 32;                 // this lane's first coordinate inside a tile
+
+    float am = -INFINITY;                            // per-thread online (max, sum, sumsq); lanes with p != 0 stay empty
+    f2 as1 = f2_pack(0.f, 0.f), as2 = as1;           // packed fp32 partial sums (<= a few thousand terms per thread)
+    const int64_t nchunks = (a.n + 15) >> 4;         // a warp advances 16 particles (8 pairs x 4 lanes) per iteration
+    for (int64_t chunk = (int64_t)blockIdx.x * L96_WARPS + warp; chunk < nchunks; chunk += (int64_t)gridDim.x * L96_WARPS) {
+        const int64_t iP = chunk * 16 + 2 * g;       // even particle of the pair (local index); the odd one is iP + 1
+        const bool vP = iP < a.n, vQ = iP + 1 < a.n;
+        const int64_t off = (chunk >> 1) * TILE + coff + (int)(iP & 31);
+        f2 x[CPL];
+        if (!INIT) {
+            if (resample) {                          // fused ancestor gather (core.py:46-56); ancestors are GLOBAL ids
+                int64_t sP = vP ? (int64_t)a.anc[iP] : iP, sQ = vQ ? (int64_t)a.anc[iP + 1] : iP + 1;
+                const float* bP = a.x_in;
+                const float* bQ = a.x_in;
+                if (a.sharded) {                     // the ancestor lives on another rank: read it over NVLink
+                    int oP = 0, oQ = 0;
+#pragma unroll
+                    for (int r = 1; r < MB_MAX_WORLD; ++r) { oP += (sP >= bounds[r]); oQ += (sQ >= bounds[r]); }
+                    if (vP) { sP -= bounds[oP]; bP = peers[oP]; }
+                    if (vQ) { sQ -= bounds[oQ]; bQ = peers[oQ]; }
+                }
+                bP += (sP >> 5) * TILE + coff + (int)(sP & 31);
+                bQ += (sQ >> 5) * TILE + coff + (int)(sQ & 31);
+#pragma unroll
+                for (int r = 0; r < CPL; ++r) x[r] = f2_pack(__ldg(bP + r * 32), __ldg(bQ + r * 32));
+            } else {
+                const float2* b = reinterpret_cast<const float2*>(a.x_in + off);
+#pragma unroll
+                for (int r = 0; r < CPL; ++r) { const float2 v = __ldg(b + r * 16); x[r] = f2_pack(v.x, v.y); }
+            }
+            for (int s = 0; s < a.substeps; ++s) l96_rk4<CPL>(x, c, prev, next);
+        }
+        // process noise (nonlinear_gaussian.py:112-113) / initial sample, and -likelihood_potential (:115-121, H = I)
+        const uint64_t pair = (uint64_t)(a.gid0 + iP) >> 1;
+        f2 quad = f2_pack(0.f, 0.f);
+#pragma unroll
+        for (int r = 0; r < CPL; r += 2) {
+            const Philox4 w = philox_raw<ROUNDS>(seed, pair, a.tail.t, INIT ? MB_P_INIT : MB_P_MOVE, (uint32_t)((CPL * p + r) >> 1));
+            float rq0, c0, s0, rq1, c1, s1;
+            box_muller_scaled(w.x, w.y, a.bm_k1, a.bm_k0, rq0, c0, s0);
+            box_muller_scaled(w.z, w.w, a.bm_k1, a.bm_k0, rq1, c1, s1);
+            float xl, xh;
+            f2_unpack(INIT ? zmean : x[r], xl, xh);
+            x[r] = f2_pack(fmaf(-rq0, c0, xl), fmaf(-rq0, s0, xh));            // cos branch -> even, sin branch -> odd particle
+            f2_unpack(INIT ? zmean : x[r + 1], xl, xh);
+            x[r + 1] = f2_pack(fmaf(-rq1, c1, xl), fmaf(-rq1, s1, xh));
+            const f2 d0 = f2_fma(x[r], nir, ysm[CPL * p + r]);
+            const f2 d1 = f2_fma(x[r + 1], nir, ysm[CPL * p + r + 1]);
+            quad = f2_fma(d0, d0, quad);
+            quad = f2_fma(d1, d1, quad);
+        }
+        quad = f2_add(quad, __shfl_xor_sync(MB_FULL, quad, 1));
+        quad = f2_add(quad, __shfl_xor_sync(MB_FULL, quad, 2));
+        float* xo = a.x_out + off;
+#pragma unroll
+        for (int r = 0; r < CPL; ++r) { float lo, hi; f2_unpack(x[r], lo, hi); *reinterpret_cast<float2*>(xo + r * 32) = make_float2(lo, hi); }
+        if (p == 0) {
+            float qP, qQ;
+            f2_unpack(quad, qP, qQ);
+            float wP = -fmaf(0.5f, qP, a.lik_const), wQ = -fmaf(0.5f, qQ, a.lik_const);
+            if (!INIT && !resample) {                                  // filtering.py:292,303: weights carried
+                const float2 o = *reinterpret_cast<const float2*>(a.lw + iP);   // lw is padded to a multiple of 32
+                wP += o.x; wQ += o.y;
+            }
+            if (!vP) wP = -INFINITY;
+            if (!vQ) wQ = -INFINITY;
+            *reinterpret_cast<float2*>(a.lw + iP) = make_float2(wP, wQ);
+            // branch-free online (max, sum e, sum e^2): rescale by f = exp(old max - new max) (= 1 when unchanged)
+            const float amn = fmaxf(am, fmaxf(wP, wQ));
+            const float ref = (amn == -INFINITY) ? 0.f : amn;
+            const float f = __expf(am - ref);                          // am = -inf -> 0 (sums are still 0)
+            const f2 e = f2_pack(__expf(wP - ref), __expf(wQ - ref));  // NaN weights propagate into the sums
+            as1 = f2_fma(as1, f2_splat(f), e);
+            as2 = f2_fma(as2, f2_splat(f * f), f2_mul(e, e));
+            am = amn;
+        }
+    }
+    float s1l, s1h, s2l, s2h;
+    f2_unpack(as1, s1l, s1h);
+    f2_unpack(as2, s2l, s2h);
+    pf_finish<INIT>(a.tail, (p == 0) ? Lse3{(double)am, (double)s1l + (double)s1h, (double)s2l + (double)s2h} : lse3_empty(),
+                    resample, smem);
+}
+
+static int l96_dispatch(mb_ctx* ctx, const mb_ssm* ssm, L96Args& a, bool init, cudaStream_t st) {
+    a.forcing = ssm->forcing; a.h = ssm->dt / (float)ssm->substeps; a.ir = 1.f / ssm->r_std;
+    a.lik_const = ssm->lik_const; a.zmean = ssm->init_mean; a.substeps = ssm->substeps;
+    const double sd = init ? (double)ssm->init_std : (double)ssm->q_std;       // z * sd = sqrt(-2 ln u1 sd^2) * (cos, sin)
+    a.bm_k1 = (float)(-2.0 * 0.6931471805599453 * sd * sd);
+    a.bm_k0 = (float)(64.0 * 0.6931471805599453 * sd * sd);
+    a.tail.partials = ctx->partials;
+    a.tail.counter = ctx->counters + MB_CNT_MOVE;
+    const int64_t nchunks = (a.n + 15) >> 4;
+    int64_t grid = (nchunks + L96_WARPS - 1) / L96_WARPS;
+    static int variant = -1;                                           // experiment switch: <occupancy><rounds%10>, e.g. 40, 20, 37
+    if (variant < 0) { const char* v = getenv("MB_L96_VARIANT"); variant = v ? atoi(v) : 30; }
+    const int occ = init ? 2 : variant / 10;
+    const int64_t cap = (int64_t)ctx->sms * occ;                       // persistent: exactly the resident blocks
+    if (grid > cap) grid = cap;
+    if (grid > MB_MAX_PARTIAL_BLOCKS) grid = MB_MAX_PARTIAL_BLOCKS;
+#define L96_CASE(DD)                                                                                   \
+    if (ssm->dim == DD) {                                                                              \
+        if (init) pf_l96_kernel<DD, true><<<(unsigned)grid, L96_THREADS, 0, st>>>(a);                  \
+        else pf_l96_kernel<DD, false><<<(unsigned)grid, L96_THREADS, 0, st>>>(a);                      \
+        MB_CHECK_LAUNCH();                                                                             \
+        return MB_OK;                                                                                  \
+    }
+    if (!init && ssm->dim == 40 && variant != 30) {
+#define L96_VAR(V, O, R) if (variant == V) { pf_l96_kernel<40, false, O, R><<<(unsigned)grid, L96_THREADS, 0, st>>>(a); MB_CHECK_LAUNCH(); return MB_OK; }
+        L96_VAR(20, 2, 10) L96_VAR(40, 4, 10) L96_VAR(37, 3, 7) L96_VAR(47, 4, 7)
+        mb_set_error("pf_l96: unknown MB_L96_VARIANT %d", variant);
+        return MB_ERR_ARG;
+    }
+    L96_CASE(8) L96_CASE(16) L96_CASE(40)
+    mb_set_error("pf_l96: unsupported dimension %d (compiled: 8, 16, 40; no CPU fallback)", ssm->dim);
+    return MB_ERR_UNSUPPORTED;
+}
+
+extern "C" int mb_pf_l96_init(mb_ctx* ctx, const mb_ssm* ssm, float* x, int64_t n, int64_t n_total, const float* y0,
+                              float* lw, uint64_t seed, int64_t gid0, double ess_threshold, mb_control* ctl,
+                              mb_hist* hist, mb_comm* comm, mb_stream_t stream) {
+    MB_REQUIRE(ctx && ssm && x && y0 && lw && ctl && n > 0, "mb_pf_l96_init: bad arguments");
+    MB_REQUIRE(ssm->kind == MB_SSM_LORENZ96 && ssm->dim_obs == ssm->dim, "mb_pf_l96_init: Lorenz-96 with H = I only");
+    MB_REQUIRE((gid0 & 1) == 0, "mb_pf_l96_init: gid0 must be even (Philox streams are keyed on particle pairs)");
+    L96Args a{};
+    a.x_in = x; a.x_out = x; a.n = n; a.y = y0; a.lw = lw; a.gid0 = gid0;
+    a.tail.n_total = n_total; a.tail.t = 0; a.tail.ess_threshold = ess_threshold; a.tail.seed = seed;
+    a.tail.ctl = ctl; a.tail.hist = hist;
+    if (comm) { a.tail.comm = *mb_comm_dev(comm); a.tail.has_comm = a.tail.comm.world > 1; }
+    return l96_dispatch(ctx, ssm, a, true, mb_s(stream));
+}
+
+extern "C" int mb_pf_l96_step(mb_ctx* ctx, const mb_ssm* ssm, const float* x_in, float* x_out, int64_t n,
+                              int64_t n_total, const int32_t* anc, const float* y, float* lw, uint64_t seed, uint32_t t,
+                              int64_t gid0, double ess_threshold, mb_control* ctl, mb_hist* hist, const mb_shard* sh,
+                              mb_comm* comm, mb_stream_t stream) {
+    MB_REQUIRE(ctx && ssm && x_in && x_out && anc && y && lw && ctl && n > 0 && x_in != x_out,
+               "mb_pf_l96_step: bad arguments");
+    MB_REQUIRE(ssm->kind == MB_SSM_LORENZ96 && ssm->dim_obs == ssm->dim && ssm->substeps >= 1,
+               "mb_pf_l96_step: Lorenz-96 with H = I only");
+    MB_REQUIRE((gid0 & 1) == 0, "mb_pf_l96_step: gid0 must be even (Philox streams are keyed on particle pairs)");
+    L96Args a{};
+    a.x_in = x_in; a.x_out = x_out; a.n = n; a.anc = anc; a.y = y; a.lw = lw; a.gid0 = gid0;
+    a.tail.n_total = n_total; a.tail.t = t; a.tail.ess_threshold = ess_threshold; a.tail.seed = seed;
+    a.tail.ctl = ctl; a.tail.hist = hist;
+    if (sh && sh->world > 1) {
+        a.sharded = 1; a.n_local = sh->n_local; a.world = sh->world;
+        for (int r = 0; r < sh->world; ++r) a.x_peers[r] = sh->x_peers[r];
+    }
+    if (comm) { a.tail.comm = *mb_comm_dev(comm); a.tail.has_comm = a.tail.comm.world > 1; }
+    return l96_dispatch(ctx, ssm, a, false, mb_s(stream));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Weighted mean / variance of every coordinate of a TILED population under weights exp(lw - ctl->wmax) / s1
+// (diagnostics of the filter: the per-step moments returned instead of the reference's stacked (T, n, d) history,
+// ssm/filtering.py:317-322).  One warp per 32-particle tile, one lane per coordinate (two when D > 32); particles whose
+// weight underflows fp32 relative to the maximum (exp(lw - wmax) < 2^-50) are skipped together with their state,
+// so a collapsed population costs 4 B per particle instead of 4 (D + 1).
+#define TM_THREADS 256
+__global__ void __launch_bounds__(TM_THREADS)
+tiled_moments_kernel(const float* __restrict__ x, int64_t n, int d, const float* __restrict__ lw, const mb_control* ctl,
+                     double* partials /*[gridDim.x][1 + 2 d]*/) {
+    extern __shared__ double sm[];                   // [warps][1 + 2 d]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const float wmax = (float)ctl->wmax;
+    const int tile_f = d * 32;
+    const int c0 = lane, c1 = lane + 32;
+    const float sh0 = (c0 < d) ? x[c0 * 32] : 0.f, sh1 = (c1 < d) ? x[c1 * 32] : 0.f;   // shifts: particle 0
+    double s0 = 0.0, a0 = 0.0, b0 = 0.0, a1 = 0.0, b1 = 0.0;
+    const int64_t ntiles = (n + 31) >> 5;
+    for (int64_t tile = (int64_t)blockIdx.x * nw + warp; tile < ntiles; tile += (int64_t)gridDim.x * nw) {
+        const int64_t i = tile * 32 + lane;
+        float e = 0.f;
+        if (i < n) { const float dl = lw[i] - wmax; e = (dl > -34.6f || dl != dl) ? __expf(dl) : 0.f; }
+        unsigned mask = __ballot_sync(MB_FULL, e != 0.f);
+        const float* xt = x + tile * tile_f;
+        while (mask) {
+            const int j = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const double ej = (double)__shfl_sync(MB_FULL, e, j);
+            s0 += ej;
+            if (c0 < d) { const double v = (double)(xt[c0 * 32 + j] - sh0); a0 += ej * v; b0 += ej * v * v; }
+            if (c1 < d) { const double v = (double)(xt[c1 * 32 + j] - sh1); a1 += ej * v; b1 += ej * v * v; }
+        }
+    }
+    double* mine = sm + (size_t)warp * (1 + 2 * d);
+    if (lane == 0) mine[0] = s0;
+    if (c0 < d) { mine[1 + c0] = a0; mine[1 + d + c0] = b0; }
+    if (c1 < d) { mine[1 + c1] = a1; mine[1 + d + c1] = b1; }
+    __syncthreads();
+    for (int k = threadIdx.x; k < 1 + 2 * d; k += blockDim.x) {
+        double acc = 0.0;
+        for (int w = 0; w < nw; ++w) acc += sm[(size_t)w * (1 + 2 * d) + k];
+        partials[(size_t)blockIdx.x * (1 + 2 * d) + k] = acc;
+    }
+}
+
+__global__ void tiled_moments_finish_kernel(const float* __restrict__ x, int d, const double* partials, int nblocks,
+                                            double* mean, double* var) {
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= d) return;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    for (int b = 0; b < nblocks; ++b) {
+        const double* p = partials + (size_t)b * (1 + 2 * d);
+        s0 += p[0]; s1 += p[1 + col]; s2 += p[1 + d + col];
+    }
+    const double m = s1 / s0;
+    mean[col] = m + (double)x[col * 32];
+    if (var) var[col] = s2 / s0 - m * m;
+}
+
+extern "C" int mb_weighted_moments_tiled(mb_ctx* ctx, const float* x, int64_t n, int d, const float* lw,
+                                         const mb_control* ctl, double* mean, double* var, mb_stream_t stream) {
+    MB_REQUIRE(ctx && x && lw && ctl && mean && n > 0 && d > 0 && d <= 64, "mb_weighted_moments_tiled: bad arguments (d <= 64)");
+    const int64_t ntiles = (n + 31) >> 5;
+    int64_t grid = (ntiles + (TM_THREADS / 32) - 1) / (TM_THREADS / 32);
+    if (grid > (int64_t)ctx->sms * 8) grid = (int64_t)ctx->sms * 8;
+    const size_t bytes = (size_t)grid * (1 + 2 * d) * sizeof(double);
+    if (mb_ensure_scratch(ctx, bytes) != MB_OK) return MB_ERR_CUDA;
+    cudaStream_t st = mb_s(stream);
+    tiled_moments_kernel<<<(unsigned)grid, TM_THREADS, (TM_THREADS / 32) * (1 + 2 * d) * sizeof(double), st>>>(
+        x, n, d, lw, ctl, (double*)ctx->scratch);
+    MB_CHECK_LAUNCH();
+    tiled_moments_finish_kernel<<<(d + 63) / 64, 64, 0, st>>>(x, d, (const double*)ctx->scratch, (int)grid, mean, var);
+    MB_CHECK_LAUNCH();
+    return MB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Gather of a TILED population by ancestor (cdict.__getitem__, core.py:46-56, as used by resample_particles,
+// ssm/filtering.py:202-217).  One warp per 32-output tile.  When the 32 ancestors fall into a window of at most
+// GT_WIN source tiles (always the case after sorted-uniform resampling) the window is STAGED in shared memory with
+// bulk asynchronous copies (cp.async.bulk -> SASS UBLKCP, completion on an mbarrier): one instruction per source
+// tile instead of D loads per particle, and the column reads become conflict-free shared-memory loads
+// (bank = ancestor & 31).  Otherwise the lanes read their ancestor's columns directly.
+#define GT_WARPS 4
+#define GT_WIN 3
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <int D>
+__global__ void __launch_bounds__(GT_WARPS * 32)
+gather_tiled_kernel(const int32_t* __restrict__ anc, int64_t n_out, const float* __restrict__ src, int64_t n_src,
+                    float* __restrict__ dst, int staged_ok) {
+    constexpr int TILE = D * 32;
+    extern __shared__ __align__(128) float stage[];                  // [GT_WARPS][GT_WIN][TILE]
+    __shared__ __align__(8) unsigned long long bar[GT_WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* mine = stage + (size_t)warp * GT_WIN * TILE;
+    const uint32_t bar_a = smem_u32(&bar[warp]);
+    if (lane == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+    uint32_t phase = 0;
+    const int64_t ntiles = (n_out + 31) >> 5;
+    for (int64_t tile = (int64_t)blockIdx.x * GT_WARPS + warp; tile < ntiles; tile += (int64_t)gridDim.x * GT_WARPS) {
+        const int64_t i = tile * 32 + lane;
+        int64_t a = (i < n_out) ? (int64_t)anc[i] : -1;
+        int64_t amin = (a < 0) ? INT64_MAX : a, amax = a;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            amin = min(amin, (int64_t)__shfl_xor_sync(MB_FULL, amin, o));
+            amax = max(amax, (int64_t)__shfl_xor_sync(MB_FULL, amax, o));
+        }
+        if (amax < 0) continue;
+        const int64_t t0 = amin >> 5, t1 = amax >> 5;
+        float* out = dst + tile * TILE + lane;
+        if (staged_ok && t1 - t0 < GT_WIN) {
+            const int nt = (int)(t1 - t0) + 1;
+            if (lane == 0) {
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"((uint32_t)(nt * TILE * 4)) : "memory");
+                for (int q = 0; q < nt; ++q)
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(smem_u32(mine + (size_t)q * TILE)), "l"(src + (t0 + q) * TILE), "r"((uint32_t)(TILE * 4)), "r"(bar_a)
+                                 : "memory");
+            }
+            uint32_t done = 0;
+            while (!done)
+                asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                             : "=r"(done) : "r"(bar_a), "r"(phase) : "memory");
+            phase ^= 1;
+            if (a >= 0) {
+                const float* s = mine + (a - (t0 << 5) >> 5) * TILE + (a & 31);
+#pragma unroll
+                for (int k = 0; k < D; ++k) out[k * 32] = s[k * 32];
+            }
+            __syncwarp();                                            // the staging area is reused by the next tile
+        } else if (a >= 0) {
+            const float* s = src + (a >> 5) * TILE + (a & 31);
+#pragma unroll
+            for (int k = 0; k < D; ++k) out[k * 32] = __ldg(s + k * 32);
+        }
+    }
+}
+
+extern "C" int mb_gather_tiled(mb_ctx* ctx, const int32_t* anc, int64_t n_out, int d, const float* src_tiled,
+                               int64_t n_src, float* dst_tiled, int staged, mb_stream_t stream) {
+    MB_REQUIRE(ctx && anc && src_tiled && dst_tiled && n_out > 0 && n_src > 0 && src_tiled != dst_tiled,
+               "mb_gather_tiled: bad arguments");
+    const int64_t ntiles = (n_out + 31) >> 5;
+    int64_t grid = (ntiles + GT_WARPS - 1) / GT_WARPS;
+    if (grid > (int64_t)ctx->sms * 8) grid = (int64_t)ctx->sms * 8;
+    cudaStream_t st = mb_s(stream);
+#define GT_CASE(DD)                                                                                            \
+    if (d == DD) {                                                                                             \
+        const size_t smem = (size_t)GT_WARPS * GT_WIN * DD * 32 * sizeof(float);                               \
+        MB_CUDA(cudaFuncSetAttribute(gather_tiled_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        gather_tiled_kernel<DD><<<(unsigned)grid, GT_WARPS * 32, smem, st>>>(anc, n_out, src_tiled, n_src, dst_tiled, staged); \
+        MB_CHECK_LAUNCH();                                                                                     \
+        return MB_OK;                                                                                          \
+    }
+    GT_CASE(8) GT_CASE(16) GT_CASE(40)
+    mb_set_error("mb_gather_tiled: unsupported dimension %d (compiled: 8, 16, 40)", d);
+    return MB_ERR_UNSUPPORTED;
+}

@@ -4,8 +4,7 @@
 //                MALA/HMC (mcmc/standard_mcmc.py:72-153, utils.py:108-146) or random walk (:21-65) and the
 //                Metropolis correction (mcmc/metropolis.py:48-70), fused with the ancestor gather.
 //   pf_step    : bootstrap filter body (ssm/filtering.py:280-311, 154-170) for the linear-Gaussian model
-//                (ssm/linear_gaussian/linear_gaussian.py:86-94,118-128) and Lorenz-96 with a fixed-step
-//                RK4 flow (ssm/scenarios/lorenz96.py:14-26, ssm/nonlinear_gaussian.py:107-121), fused with
+//                (ssm/linear_gaussian/linear_gaussian.py:86-94,118-128; Lorenz-96: pf_l96.cu), fused with
 //                the ancestor gather, the LSE/ESS reduction and the log-evidence / resample bookkeeping.
 //
 // Layout: SoA, one thread per particle, every column access is a fully coalesced 128 B/warp request;
@@ -13,6 +12,7 @@
 #include "common.cuh"
 #include "rng.cuh"
 #include "comm.cuh"
+#include "pf_common.cuh"
 
 const MbCommDev* mb_comm_dev(const mb_comm* c);
 
@@ -336,35 +336,6 @@ struct PfArgs {
     MbCommDev comm; int has_comm;
 };
 
-template <int D>
-__device__ __forceinline__ void lorenz_rhs(const float (&x)[D], float forcing, float (&k)[D]) {
-#pragma unroll
-    for (int j = 0; j < D; ++j) {
-        const float xp1 = x[(j + 1) % D], xm1 = x[(j + D - 1) % D], xm2 = x[(j + D - 2) % D];
-        k[j] = fmaf(xp1 - xm2, xm1, forcing - x[j]);                  // lorenz96.py:18-19
-    }
-}
-
-template <int D>
-__device__ __forceinline__ float lorenz_rhs1(const float (&x)[D], float forcing, int j) {
-    return fmaf(x[(j + 1) % D] - x[(j + D - 2) % D], x[(j + D - 1) % D], forcing - x[j]);   // lorenz96.py:18-19
-}
-
-// one classical RK4 step of size h (device definition of the L96 flow).  Written stage by stage with a
-// scalar slope so that only x, the slope accumulator and two stage states are live (register budget: 128/thread).
-template <int D>
-__device__ __forceinline__ void lorenz_rk4(float (&x)[D], float h, float forcing) {
-    float acc[D], xa[D], xb[D];
-#pragma unroll
-    for (int j = 0; j < D; ++j) { const float k = lorenz_rhs1<D>(x, forcing, j); acc[j] = k; xa[j] = fmaf(0.5f * h, k, x[j]); }
-#pragma unroll
-    for (int j = 0; j < D; ++j) { const float k = lorenz_rhs1<D>(xa, forcing, j); acc[j] = fmaf(2.f, k, acc[j]); xb[j] = fmaf(0.5f * h, k, x[j]); }
-#pragma unroll
-    for (int j = 0; j < D; ++j) { const float k = lorenz_rhs1<D>(xb, forcing, j); acc[j] = fmaf(2.f, k, acc[j]); xa[j] = fmaf(h, k, x[j]); }
-#pragma unroll
-    for (int j = 0; j < D; ++j) { const float k = lorenz_rhs1<D>(xa, forcing, j); x[j] = fmaf(h * (1.f / 6.f), acc[j] + k, x[j]); }
-}
-
 // normals of one particle, produced four at a time where they are consumed (keeps them out of the register budget
 // of the Lorenz-96 flow): slot s holds normals 4s..4s+3 (rng.cuh)
 struct PfNormals {
@@ -428,42 +399,20 @@ __device__ __forceinline__ float pf_particle(const mb_ssm& m, float (&x)[D], con
             quad = fmaf(0.5f * acc, acc, quad);
         }
         return -(quad + m.lik_const);
-    } else {                                            // Lorenz-96, diagonal noise, H = I
-        if (!init) {
-            const float h = m.dt / (float)m.substeps;
-            for (int s = 0; s < m.substeps; ++s) lorenz_rk4<D>(x, h, m.forcing);
-        }
-        const float ir = 1.f / m.r_std;
-        float quad = 0.f;
-#pragma unroll
-        for (int s = 0; s < (D + 3) / 4; ++s) {         // noise and likelihood, four coordinates per Philox call
-            float z4[4];
-            rng.slot(s, z4);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const int j = 4 * s + c;
-                if (j < D) {
-                    x[j] = init ? fmaf(m.init_std, z4[c], m.init_mean)
-                                : fmaf(m.q_std, z4[c], x[j]);                  // nonlinear_gaussian.py:112-113
-                    const float r = (ys[j] - x[j]) * ir;
-                    quad = fmaf(r, r, quad);
-                }
-            }
-        }
-        return -(0.5f * quad + m.lik_const);
+    } else {
+        return 0.f;                                     // Lorenz-96 lives in pf_l96.cu (tiled layout, lane-split kernel)
     }
 }
 
-#define PF_THREADS(D) ((D) >= 32 ? 128 : MV_THREADS)
+#define PF_THREADS(D) MV_THREADS
 template <int KIND, int D, bool INIT>
-__global__ void __launch_bounds__(PF_THREADS(D), (D) >= 32 ? 4 : 1) pf_step_kernel(PfArgs a) {
+__global__ void __launch_bounds__(PF_THREADS(D)) pf_step_kernel(PfArgs a) {
     mb_control* ctl = a.ctl;
     constexpr bool init = INIT;                       // compile-time: the initial-sample variant is a separate (small) kernel
     if (!init && ctl->done) return;
     const bool resample = !init && ctl->resample != 0;
     __shared__ Lse3 smem[MV_THREADS / 32];
     __shared__ float ys[D];
-    __shared__ bool is_last;
     if (threadIdx.x < D) ys[threadIdx.x] = (threadIdx.x < a.ssm.dim_obs) ? a.y[threadIdx.x] : 0.f;
     __syncthreads();
 
@@ -499,50 +448,10 @@ __global__ void __launch_bounds__(PF_THREADS(D), (D) >= 32 ? 4 : 1) pf_step_kern
             as1 += (double)e; as2 += (double)e * (double)e;
         }
     }
-    const Lse3 b = lse3_block_reduce(Lse3{(double)am, as1, as2}, smem);
-    if (threadIdx.x == 0) {
-        a.partials[3 * blockIdx.x] = b.m; a.partials[3 * blockIdx.x + 1] = b.s1; a.partials[3 * blockIdx.x + 2] = b.s2;
-        __threadfence();
-        is_last = (atomicAdd(a.counter, 1u) == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence();
-    Lse3 v = lse3_empty();
-    for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x)
-        v = lse3_merge(v, Lse3{a.partials[3 * i], a.partials[3 * i + 1], a.partials[3 * i + 2]});
-    v = lse3_block_reduce(v, smem);
-    if (a.has_comm) {                                                  // global LSE/ESS: exchange the rank triples
-        __shared__ double xin[3], xout[3 * MB_MAX_WORLD];
-        if (threadIdx.x == 0) { xin[0] = v.m; xin[1] = v.s1; xin[2] = v.s2; }
-        __syncthreads();
-        if (threadIdx.x < 32) comm_allgather_warp(a.comm, xin, 3, xout);
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            v = lse3_empty();
-            for (int r = 0; r < a.comm.world; ++r) v = lse3_merge(v, Lse3{xout[3 * r], xout[3 * r + 1], xout[3 * r + 2]});
-        }
-    }
-    if (threadIdx.x == 0) {
-        *a.counter = 0;
-        mb_control c;
-        if (init) { memset(&c, 0, sizeof(c)); c.seed = a.seed; } else c = *ctl;
-        const double nd = (double)a.n_total;
-        const double lse_prev = (init || resample) ? log(nd) : c.lse;          // log Z convention, SURVEY 8c
-        ctl_set_weights(&c, v);
-        c.log_z = (init ? 0.0 : c.log_z) + (c.lse - lse_prev);
-        c.iter = (int32_t)a.t;
-        c.resampled = resample ? 1 : 0;
-        c.resample = (c.ess < a.ess_threshold * nd) ? 1 : 0;                   // filtering.py:287 (strict <)
-        c.done = 0;
-        *ctl = c;
-        if (a.hist && a.t < MB_HIST_MAX) {
-            mb_hist h;
-            h.beta = 0.0; h.ess = c.ess; h.log_z = c.log_z; h.alpha_mean = 0.0; h.lse = c.lse;
-            h.resampled = c.resampled; h.search_iters = 0;
-            a.hist[a.t] = h;
-        }
-    }
+    PfTail tl{};
+    tl.n_total = a.n_total; tl.t = a.t; tl.ess_threshold = a.ess_threshold; tl.seed = a.seed; tl.ctl = a.ctl; tl.hist = a.hist;
+    tl.partials = a.partials; tl.counter = a.counter; tl.comm = a.comm; tl.has_comm = a.has_comm;
+    pf_finish<INIT>(tl, Lse3{(double)am, as1, as2}, resample, smem);
 }
 
 static int64_t pf_grid(mb_ctx* ctx, int64_t n, int threads) {
@@ -558,9 +467,8 @@ static int pf_dispatch(mb_ctx* ctx, PfArgs& a, cudaStream_t st) {
     a.counter = ctx->counters + MB_CNT_MOVE;
     const int d = a.ssm.dim;
 #define PF_LG(DD) if (a.ssm.kind == MB_SSM_LINEAR_GAUSSIAN && d == DD) { PF_LAUNCH(MB_SSM_LINEAR_GAUSSIAN, DD)<<<(unsigned)pf_grid(ctx, a.n, PF_THREADS(DD)), PF_THREADS(DD), 0, st>>>(a); MB_CHECK_LAUNCH(); return MB_OK; }
-#define PF_L96(DD) if (a.ssm.kind == MB_SSM_LORENZ96 && d == DD) { PF_LAUNCH(MB_SSM_LORENZ96, DD)<<<(unsigned)pf_grid(ctx, a.n, PF_THREADS(DD)), PF_THREADS(DD), 0, st>>>(a); MB_CHECK_LAUNCH(); return MB_OK; }
     PF_LG(1) PF_LG(2) PF_LG(3) PF_LG(4) PF_LG(5) PF_LG(6) PF_LG(8)
-    PF_L96(8) PF_L96(40)
+    if (a.ssm.kind == MB_SSM_LORENZ96) { mb_set_error("pf: Lorenz-96 runs through mb_pf_l96_init / mb_pf_l96_step (tiled layout)"); return MB_ERR_UNSUPPORTED; }
     mb_set_error("pf: unsupported ssm kind %d / dim %d (built-in device models only; no CPU fallback)", a.ssm.kind, d);
     return MB_ERR_UNSUPPORTED;
 }

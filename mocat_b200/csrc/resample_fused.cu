@@ -1,0 +1,442 @@
+// resample_fused.cu -- systematic resampling without a materialised CDF (production path of the particle filter).
+//
+// Replaces `random.categorical` + gather index generation of the reference (transport/smc.py:61-71,
+// ssm/filtering.py:196-199) for sorted-uniform (systematic) resampling.  Round 1 wrote an fp64 CDF (8 B/particle),
+// read it back in a second kernel (8 B) and searched it per OUTPUT: 24 B/particle and two latency-bound kernels
+// (25 % / 14 % of the HBM roofline).  Here the weights are read twice (4 + 4 B) and the ancestors written once (4 B):
+//
+//   pass A  rf_tile_sums_kernel   integer weight e_i of every particle, summed per 4096-particle tile; the last block
+//                                 scans the tile sums (exclusive prefix) and publishes the shard total.
+//   (sharded: the shard totals are exchanged with mb_comm_allgather -- one fp64-sized word per rank)
+//   pass B  rf_ancestors_kernel   re-derives e_i, block-scans the tile, turns every particle's inclusive cumulative
+//                                 weight C_j into the NUMBER OF OUTPUTS BELOW IT c_j (closed form, see rf_count), drops
+//                                 a head marker at output c_{j-1} for every particle with offspring, max-scans the
+//                                 markers in shared memory and stores the ancestors of the tile's outputs with
+//                                 coalesced 128 B writes (peer-mapped pointers when the outputs belong to another GPU).
+//   pass C  rf_heavy_kernel       tiles with more than RF_INLINE outputs (collapsed weights: a handful of particles
+//                                 own all the offspring) are queued by pass B and their outputs are spread over the
+//                                 whole grid here.
+//
+// Exact arithmetic (DESIGN.md "resampling convention"): e_i = rint(w_i 2^K) as uint64 (w_i = exp(lw_i - max lw) <= 1
+// in log mode, the caller's weight in linear mode; K = min(40, 63 - ceil(log2 n_total)) so that the total S < 2^63).
+// Integer sums are associative: tile order, block scheduling and the sharding over GPUs cannot change a bit.
+// Systematic resampling is then evaluated in EXACT rational arithmetic: with u0 = k0 / 2^32,
+//     a_i = min{ j : (i + u0) / n < C_j / S }   <=>   c_j = #{ i : (i 2^32 + k0) S < C_j n 2^32 },  a_i = j for c_{j-1} <= i < c_j
+// (128-bit integer comparison; an fp64 estimate decides except within 1e-5 of an integer).  oracle/core.py
+// `ancestors_systematic_exact` restates this with Python integers; the two agree bit for bit.
+#include "common.cuh"
+#include "rng.cuh"
+#include "comm.cuh"
+
+#define RF_THREADS 256
+#define RF_ITEMS 16
+#define RF_TILE (RF_THREADS * RF_ITEMS)          // 4096 particles
+#define RF_CHUNK_ITEMS 24
+#define RF_CHUNK (RF_THREADS * RF_CHUNK_ITEMS)   // 6144 outputs filled per shared-memory pass
+#define RF_INLINE (3 * RF_CHUNK)                 // tiles with more outputs go to the heavy worklist
+#define RF_HEAVY_CHUNK 8192                      // outputs per work item of the heavy pass
+
+typedef unsigned long long u64;
+
+struct RfHeader {                                // first 64 bytes of the caller's workspace
+    u64 local_total;                             // sum of e_i over this shard (input of the totals exchange)
+    unsigned heavy_count;                        // worklist length, reset by pass A
+    unsigned done_counter;                       // last-block detection of pass A (self resetting)
+    u64 pad[6];
+};
+
+struct RfArgs {
+    RfHeader* hdr; u64* prefix; unsigned* worklist;   // prefix[ntiles + 1]: exclusive tile prefix, last = shard total
+    const float* in; int64_t n; int64_t ntiles;
+    int log_mode; float scale;                        // e = rint(w * scale), scale = 2^K
+    const mb_control* ctl; int predicated;
+    long long k0;                                     // >= 0: caller supplied u0 bits; < 0: Philox(ctl->seed, ctl->iter + 1)
+    const u64* totals; int rank, world;               // shard totals (device, [world]) or NULL (single shard)
+    int64_t n_local, n_total;
+    int32_t* anc_peers[MB_MAX_WORLD];
+};
+
+__device__ __forceinline__ float rf_wmax(const RfArgs& a) {
+    float wmax = 0.f;
+    if (a.log_mode) {
+        wmax = (float)a.ctl->wmax;
+        if (!(wmax > -INFINITY) || wmax == INFINITY) wmax = 0.f;      // jax logsumexp convention: non-finite max -> 0
+    }
+    return wmax;
+}
+
+__device__ __forceinline__ u64 rf_weight(float v, bool log_mode, float wmax, float scale) {
+    const float w = log_mode ? __expf(v - wmax) : v;
+    return __float2ull_rn(w * scale);                                 // NaN, negative -> 0
+}
+
+// 16 consecutive weights of this thread -> integer weights e[] (zero beyond n)
+__device__ __forceinline__ void rf_load(const RfArgs& a, int64_t base, float wmax, u64 (&e)[RF_ITEMS]) {
+    if (base + RF_ITEMS <= a.n && (((uintptr_t)a.in & 15) == 0)) {
+        const float4* p = reinterpret_cast<const float4*>(a.in + base);
+#pragma unroll
+        for (int k = 0; k < RF_ITEMS / 4; ++k) {
+            const float4 v = __ldg(p + k);
+            e[4 * k + 0] = rf_weight(v.x, a.log_mode, wmax, a.scale); e[4 * k + 1] = rf_weight(v.y, a.log_mode, wmax, a.scale);
+            e[4 * k + 2] = rf_weight(v.z, a.log_mode, wmax, a.scale); e[4 * k + 3] = rf_weight(v.w, a.log_mode, wmax, a.scale);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < RF_ITEMS; ++k) e[k] = (base + k < a.n) ? rf_weight(a.in[base + k], a.log_mode, wmax, a.scale) : 0ull;
+    }
+}
+
+__device__ __forceinline__ u64 warp_sum_u64(u64 v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(MB_FULL, v, o);
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------ pass A
+__global__ void __launch_bounds__(RF_THREADS) rf_tile_sums_kernel(RfArgs a) {
+    if (a.predicated && (a.ctl->done || !a.ctl->resample)) return;
+    __shared__ u64 wsum[RF_THREADS / 32];
+    __shared__ bool is_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float wmax = rf_wmax(a);
+    for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+        // coalesced: thread t takes float4 number t + 256 q of the tile (the sum does not care about the order)
+        u64 s = 0;
+        const int64_t tb = tile * RF_TILE;
+        if (tb + RF_TILE <= a.n && (((uintptr_t)a.in & 15) == 0)) {
+            const float4* p = reinterpret_cast<const float4*>(a.in + tb);
+#pragma unroll
+            for (int q = 0; q < RF_ITEMS / 4; ++q) {
+                const float4 v = __ldcs(p + q * RF_THREADS + threadIdx.x);
+                s += rf_weight(v.x, a.log_mode, wmax, a.scale) + rf_weight(v.y, a.log_mode, wmax, a.scale) +
+                     rf_weight(v.z, a.log_mode, wmax, a.scale) + rf_weight(v.w, a.log_mode, wmax, a.scale);
+            }
+        } else {
+            for (int q = 0; q < RF_ITEMS; ++q) {
+                const int64_t i = tb + q * RF_THREADS + threadIdx.x;
+                if (i < a.n) s += rf_weight(a.in[i], a.log_mode, wmax, a.scale);
+            }
+        }
+        s = warp_sum_u64(s);
+        if (lane == 0) wsum[warp] = s;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            u64 t = 0;
+#pragma unroll
+            for (int w = 0; w < RF_THREADS / 32; ++w) t += wsum[w];
+            a.prefix[tile] = t;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        __threadfence();
+        is_last = (atomicAdd(&a.hdr->done_counter, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    // exclusive scan of the tile sums by the last block: contiguous segment per thread
+    __shared__ u64 seg[RF_THREADS];
+    const int64_t per = (a.ntiles + RF_THREADS - 1) / RF_THREADS;
+    const int64_t lo = min((int64_t)threadIdx.x * per, a.ntiles), hi = min(lo + per, a.ntiles);
+    u64 s = 0;
+    for (int64_t k = lo; k < hi; ++k) s += a.prefix[k];
+    seg[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u64 run = 0;
+        for (int k = 0; k < RF_THREADS; ++k) { const u64 t = seg[k]; seg[k] = run; run += t; }
+        a.prefix[a.ntiles] = run;
+        a.hdr->local_total = run;
+        a.hdr->heavy_count = 0;
+        a.hdr->done_counter = 0;
+    }
+    __syncthreads();
+    u64 run = seg[threadIdx.x];
+    for (int64_t k = lo; k < hi; ++k) { const u64 t = a.prefix[k]; a.prefix[k] = run; run += t; }
+}
+
+// ------------------------------------------------------------------------------------------------ counts
+struct RfSys {                     // systematic grid seen from the cumulative weights
+    u64 S; u64 n; unsigned k0; double rho, u0;
+};
+
+// is (i 2^32 + k0) S < C n 2^32 ?   (exact, 128-bit)
+__device__ __forceinline__ bool rf_below(const RfSys& g, u64 i, u64 C) {
+    const u64 A = (i << 32) | (u64)g.k0;
+    const u64 lh = __umul64hi(A, g.S), ll = A * g.S;
+    const u64 xh = __umul64hi(C, g.n), xl = C * g.n;
+    const u64 rh = (xh << 32) | (xl >> 32), rl = xl << 32;
+    return lh < rh || (lh == rh && ll < rl);
+}
+
+// c(C) = #{ i in [0, n) : (i + u0)/n < C/S }: fp64 estimate, exact fix-up when the estimate is within 1e-5 of an integer
+__device__ __forceinline__ unsigned rf_count(const RfSys& g, u64 C) {
+    if (C == 0) return 0u;
+    if (C >= g.S) return (unsigned)g.n;
+    const double t = (double)C * g.rho - g.u0;            // outputs i < t lie below C
+    double ce = ceil(t);
+    if (ce < 0.0) ce = 0.0;
+    if (ce > (double)g.n) ce = (double)g.n;
+    u64 c = (u64)ce;
+    const double fr = t - floor(t);
+    if (fr < 1e-5 || fr > 1.0 - 1e-5) {                   // rare: settle with integers
+        while (c > 0 && !rf_below(g, c - 1, C)) --c;
+        while (c < g.n && rf_below(g, c, C)) ++c;
+    }
+    return (unsigned)c;
+}
+
+__device__ __forceinline__ RfSys rf_grid_setup(const RfArgs& a, u64& offset) {
+    RfSys g;
+    u64 S = 0;
+    offset = 0;
+    if (a.totals) {
+        for (int r = 0; r < a.world; ++r) { const u64 t = a.totals[r]; if (r < a.rank) offset += t; S += t; }
+    } else {
+        S = a.prefix[a.ntiles];
+    }
+    g.S = S; g.n = (u64)a.n_total;
+    if (a.k0 >= 0) g.k0 = (unsigned)a.k0;
+    else g.k0 = philox_raw(a.ctl->seed, 0ull, (uint32_t)(a.ctl->iter + 1), MB_P_RESAMPLE, 0u).x;
+    g.rho = (S > 0) ? (double)g.n / (double)S : 0.0;
+    g.u0 = (double)g.k0 * 2.3283064365386963e-10;
+    return g;
+}
+
+// destination of global output slot o: the owning rank's ancestor array (peer mapped)
+__device__ __forceinline__ void rf_store(const RfArgs& a, int32_t* const* peers, int64_t o, int32_t v) {
+    if (a.world <= 1) { a.anc_peers[0][o] = v; return; }
+    const int r = (int)(o / a.n_local);
+    peers[r][o - (int64_t)r * a.n_local] = v;
+}
+
+// block-wide scan of this thread's 16 integer weights -> exclusive offset of the thread inside the tile
+__device__ __forceinline__ u64 rf_block_exclusive(u64 thread_total, u64* warp_tot) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u64 incl = thread_total;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const u64 t = __shfl_up_sync(MB_FULL, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    u64 off = 0;
+#pragma unroll
+    for (int w = 0; w < RF_THREADS / 32; ++w) if (w < warp) off += warp_tot[w];
+    __syncthreads();
+    return off + incl - thread_total;
+}
+
+// ------------------------------------------------------------------------------------------------ pass B
+__global__ void __launch_bounds__(RF_THREADS) rf_ancestors_kernel(RfArgs a) {
+    if (a.predicated && (a.ctl->done || !a.ctl->resample)) return;
+    __shared__ u64 warp_tot[RF_THREADS / 32];
+    __shared__ int buf[RF_CHUNK];
+    __shared__ int wmaxs[RF_THREADS / 32];
+    __shared__ unsigned range[2];
+    __shared__ int32_t* peers[MB_MAX_WORLD];
+    if (threadIdx.x < MB_MAX_WORLD) peers[threadIdx.x] = a.anc_peers[threadIdx.x];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float wmax = rf_wmax(a);
+    u64 offset;
+    const RfSys g = rf_grid_setup(a, offset);
+    __syncthreads();
+    if (g.S == 0) {                                       // all weights zero: legacy convention cdf[n-1] = 1
+        const int64_t o0 = (int64_t)a.rank * a.n_local;
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x)
+            peers[a.world <= 1 ? 0 : a.rank][i] = (int32_t)(a.n_total - 1);
+        (void)o0;
+        return;
+    }
+    const int64_t gid0 = (int64_t)a.rank * a.n_local;     // global id of this shard's first particle
+
+    for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+        u64 e[RF_ITEMS];
+        rf_load(a, tile * RF_TILE + (int64_t)threadIdx.x * RF_ITEMS, wmax, e);
+        u64 tot = 0;
+#pragma unroll
+        for (int k = 0; k < RF_ITEMS; ++k) tot += e[k];
+        u64 C = offset + a.prefix[tile] + rf_block_exclusive(tot, warp_tot);
+        // outputs below the cumulative weight: c_prev at the thread's exclusive prefix, then after every particle
+        unsigned c[RF_ITEMS + 1];
+        c[0] = rf_count(g, C);
+#pragma unroll
+        for (int k = 0; k < RF_ITEMS; ++k) {
+            C += e[k];
+            c[k + 1] = (e[k] == 0) ? c[k] : rf_count(g, C);
+        }
+        if (threadIdx.x == 0) range[0] = c[0];
+        if (threadIdx.x == RF_THREADS - 1) range[1] = c[RF_ITEMS];
+        __syncthreads();
+        const unsigned o_lo = range[0], o_hi = range[1];
+        __syncthreads();
+        if (o_hi == o_lo) continue;                       // no offspring in this tile
+        if (o_hi - o_lo > RF_INLINE) {                    // collapsed weights: spread this tile's outputs over the grid later
+            if (threadIdx.x == 0) a.worklist[atomicAdd(&a.hdr->heavy_count, 1u)] = (unsigned)tile;
+            continue;
+        }
+        int carry = 0;
+        for (unsigned chunk_lo = o_lo; chunk_lo < o_hi; chunk_lo += RF_CHUNK) {
+#pragma unroll
+            for (int q = 0; q < RF_CHUNK_ITEMS; ++q) buf[q * RF_THREADS + threadIdx.x] = 0;
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < RF_ITEMS; ++k) {
+                const unsigned first = c[k];
+                if (c[k + 1] > first && first >= chunk_lo && first - chunk_lo < RF_CHUNK)
+                    buf[first - chunk_lo] = threadIdx.x * RF_ITEMS + k + 1;       // head marker: local particle index + 1
+            }
+            __syncthreads();
+            // max-scan of the markers (local indices increase with the output slot): thread t owns 24 consecutive slots
+            int v[RF_CHUNK_ITEMS];
+            int run = 0;
+#pragma unroll
+            for (int q = 0; q < RF_CHUNK_ITEMS; ++q) { run = max(run, buf[threadIdx.x * RF_CHUNK_ITEMS + q]); v[q] = run; }
+            int incl = run;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(MB_FULL, incl, o); if (lane >= o) incl = max(incl, t); }
+            if (lane == 31) wmaxs[warp] = incl;
+            int excl = __shfl_up_sync(MB_FULL, incl, 1);
+            if (lane == 0) excl = 0;
+            __syncthreads();
+            int before = carry;
+#pragma unroll
+            for (int w = 0; w < RF_THREADS / 32; ++w) if (w < warp) before = max(before, wmaxs[w]);
+            int last = carry;
+#pragma unroll
+            for (int w = 0; w < RF_THREADS / 32; ++w) last = max(last, wmaxs[w]);
+            excl = max(excl, before);
+#pragma unroll
+            for (int q = 0; q < RF_CHUNK_ITEMS; ++q) buf[threadIdx.x * RF_CHUNK_ITEMS + q] = max(v[q], excl);
+            carry = last;
+            __syncthreads();
+            const unsigned cnt = min((unsigned)RF_CHUNK, o_hi - chunk_lo);
+            const int32_t base = (int32_t)(gid0 + tile * RF_TILE) - 1;
+#pragma unroll
+            for (int q = 0; q < RF_CHUNK_ITEMS; ++q) {
+                const unsigned s = q * RF_THREADS + threadIdx.x;
+                if (s < cnt) rf_store(a, peers, (int64_t)chunk_lo + s, base + buf[s]);
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ pass C
+__global__ void __launch_bounds__(RF_THREADS) rf_heavy_kernel(RfArgs a) {
+    if (a.predicated && (a.ctl->done || !a.ctl->resample)) return;
+    const unsigned H = a.hdr->heavy_count;
+    if (H == 0) return;
+    __shared__ u64 warp_tot[RF_THREADS / 32];
+    __shared__ unsigned cs[RF_TILE + 1];                  // cs[j] = outputs below particle j's EXCLUSIVE prefix; cs[4096] = o_hi
+    __shared__ int32_t* peers[MB_MAX_WORLD];
+    if (threadIdx.x < MB_MAX_WORLD) peers[threadIdx.x] = a.anc_peers[threadIdx.x];
+    const float wmax = rf_wmax(a);
+    u64 offset;
+    const RfSys g = rf_grid_setup(a, offset);
+    const int64_t gid0 = (int64_t)a.rank * a.n_local;
+    __syncthreads();
+    u64 rot = 0;                                          // rotating block assignment: work item q of entry e -> block (rot + q) % grid
+    for (unsigned en = 0; en < H; ++en) {
+        const int64_t tile = a.worklist[en];
+        const u64 Cex = offset + a.prefix[tile], Cin = offset + a.prefix[tile + 1];
+        const unsigned o_lo = rf_count(g, Cex), o_hi = rf_count(g, Cin);
+        const u64 items = ((u64)(o_hi - o_lo) + RF_HEAVY_CHUNK - 1) / RF_HEAVY_CHUNK;
+        const u64 first = ((u64)blockIdx.x + gridDim.x - rot % gridDim.x) % gridDim.x;
+        rot += items;
+        if (first >= items) continue;                     // block-uniform
+        u64 e[RF_ITEMS];
+        rf_load(a, tile * RF_TILE + (int64_t)threadIdx.x * RF_ITEMS, wmax, e);
+        u64 tot = 0;
+#pragma unroll
+        for (int k = 0; k < RF_ITEMS; ++k) tot += e[k];
+        u64 C = Cex + rf_block_exclusive(tot, warp_tot);
+        unsigned cprev = rf_count(g, C);
+#pragma unroll
+        for (int k = 0; k < RF_ITEMS; ++k) {
+            cs[threadIdx.x * RF_ITEMS + k] = cprev;
+            C += e[k];
+            if (e[k] != 0) cprev = rf_count(g, C);
+        }
+        if (threadIdx.x == RF_THREADS - 1) cs[RF_TILE] = cprev;
+        __syncthreads();
+        const int32_t base = (int32_t)(gid0 + tile * RF_TILE);
+        for (u64 q = first; q < items; q += gridDim.x) {
+            const unsigned w_lo = o_lo + (unsigned)(q * RF_HEAVY_CHUNK);
+            const unsigned w_hi = (unsigned)min((u64)o_hi, (u64)w_lo + RF_HEAVY_CHUNK);
+            for (unsigned o = w_lo + threadIdx.x; o < w_hi; o += RF_THREADS) {
+                // ancestor = last particle j with cs[j] <= o among those with offspring: upper_bound(cs, o) - 1
+                int lo = 0, hi = RF_TILE;
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (cs[mid + 1] > o) hi = mid; else lo = mid + 1; }
+                rf_store(a, peers, (int64_t)o, base + lo);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host
+static int rf_scale_bits(int64_t n_total) {
+    int lg = 0;
+    while (((int64_t)1 << lg) < n_total) ++lg;
+    int K = 63 - lg;
+    return K > 40 ? 40 : K;
+}
+
+extern "C" size_t mb_rs_workspace_bytes(int64_t n) {
+    const int64_t ntiles = (n + RF_TILE - 1) / RF_TILE;
+    return sizeof(RfHeader) + sizeof(u64) * (size_t)(ntiles + 1) + sizeof(unsigned) * (size_t)(ntiles + 1);
+}
+
+static void rf_fill(RfArgs& a, void* ws, const float* in, int64_t n, int64_t n_total, int log_mode, const mb_control* ctl,
+                    int force) {
+    a.ntiles = (n + RF_TILE - 1) / RF_TILE;
+    a.hdr = (RfHeader*)ws;
+    a.prefix = (u64*)((char*)ws + sizeof(RfHeader));
+    a.worklist = (unsigned*)(a.prefix + a.ntiles + 1);
+    a.in = in; a.n = n; a.n_total = n_total; a.log_mode = log_mode;
+    a.scale = ldexpf(1.f, rf_scale_bits(n_total));
+    a.ctl = ctl; a.predicated = (ctl && !force) ? 1 : 0;
+}
+
+extern "C" int mb_rs_tile_sums(mb_ctx* ctx, void* ws, const float* in, int64_t n, int64_t n_total, int log_mode,
+                               const mb_control* ctl, int force, mb_stream_t stream) {
+    MB_REQUIRE(ctx && ws && in && n > 0 && n_total >= n && n_total < 0x7fffffffll, "mb_rs_tile_sums: bad arguments");
+    MB_REQUIRE(!log_mode || ctl, "mb_rs_tile_sums: log mode needs the control block (max log-weight)");
+    RfArgs a{};
+    rf_fill(a, ws, in, n, n_total, log_mode, ctl, force);
+    int64_t grid = a.ntiles;
+    if (grid > (int64_t)ctx->sms * 8) grid = (int64_t)ctx->sms * 8;
+    rf_tile_sums_kernel<<<(unsigned)grid, RF_THREADS, 0, mb_s(stream)>>>(a);
+    MB_CHECK_LAUNCH();
+    return MB_OK;
+}
+
+extern "C" int mb_rs_ancestors(mb_ctx* ctx, void* ws, const float* in, int64_t n, int64_t n_total, int log_mode,
+                               const mb_control* ctl, int force, int64_t k0, const unsigned long long* totals,
+                               const mb_shard* sh, int32_t* anc, mb_stream_t stream) {
+    MB_REQUIRE(ctx && ws && in && anc && n > 0 && n_total >= n && n_total < 0x7fffffffll, "mb_rs_ancestors: bad arguments");
+    MB_REQUIRE(!log_mode || ctl, "mb_rs_ancestors: log mode needs the control block");
+    MB_REQUIRE(k0 >= 0 || ctl, "mb_rs_ancestors: k0 < 0 draws u0 from Philox(ctl->seed, ctl->iter + 1)");
+    MB_REQUIRE(k0 <= 0xffffffffll, "mb_rs_ancestors: k0 is a 32-bit fraction");
+    RfArgs a{};
+    rf_fill(a, ws, in, n, n_total, log_mode, ctl, force);
+    a.k0 = k0;
+    a.rank = 0; a.world = 1; a.n_local = n; a.anc_peers[0] = anc;
+    if (sh && sh->world > 1) {
+        MB_REQUIRE(totals && sh->n_local == n && sh->n_total == n_total, "mb_rs_ancestors: sharded call needs the shard totals");
+        a.totals = totals; a.rank = sh->rank; a.world = sh->world; a.n_local = sh->n_local;
+        for (int r = 0; r < sh->world; ++r) {
+            MB_REQUIRE(sh->anc_peers[r] != nullptr, "mb_rs_ancestors: anc_peers missing");
+            a.anc_peers[r] = sh->anc_peers[r];
+        }
+    } else {
+        MB_REQUIRE(n_total == n, "mb_rs_ancestors: n_total != n needs a shard description");
+    }
+    int64_t grid = a.ntiles;
+    if (grid > (int64_t)ctx->sms * 6) grid = (int64_t)ctx->sms * 6;
+    rf_ancestors_kernel<<<(unsigned)grid, RF_THREADS, 0, mb_s(stream)>>>(a);
+    MB_CHECK_LAUNCH();
+    rf_heavy_kernel<<<(unsigned)(ctx->sms * 6), RF_THREADS, 0, mb_s(stream)>>>(a);
+    MB_CHECK_LAUNCH();
+    return MB_OK;
+}

@@ -11,11 +11,12 @@
 
 struct Philox4 { uint32_t x, y, z, w; };
 
+template <int ROUNDS = 10>
 __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                                  uint32_t k0, uint32_t k1) {
     const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < ROUNDS; ++r) {
         if (r > 0) { k0 += W0; k1 += W1; }
         // __umulhi + 32-bit product fuse into ONE IMAD.WIDE each; the (uint64_t) form costs two stray adds per round
         const uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
@@ -25,9 +26,10 @@ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint3
     return Philox4{c0, c1, c2, c3};
 }
 
+template <int ROUNDS = 10>
 __device__ __forceinline__ Philox4 philox_raw(uint64_t seed, uint64_t gid, uint32_t step, uint32_t purpose,
                                               uint32_t index) {
-    return philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), step, (purpose << 20) | index,
+    return philox4x32_10<ROUNDS>((uint32_t)gid, (uint32_t)(gid >> 32), step, (purpose << 20) | index,
                          (uint32_t)seed, (uint32_t)(seed >> 32));
 }
 

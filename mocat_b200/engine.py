@@ -3,8 +3,8 @@
 Layout in HBM: particle values are SoA `x[d][ld]` (a torch (d, ld) float32 tensor, ld = n
 rounded up to 32 elements so every column starts 128 B aligned), double buffered for the fused
 ancestor-gather; per-particle scalars (`lw`, `lik`, `up`, `alpha`, `dist`) are (n,) float32; the fp64 CDF
-(n,) and int32 ancestors (n,) are allocated on first resample; all per-iteration scalars live in one
-136-byte control block on the device plus a history ring of 48-byte records.
+(n,) (multinomial only) and int32 ancestors (n,); all per-iteration scalars live in one
+144-byte control block on the device plus a history ring of 48-byte records.
 """
 import ctypes as C
 import os
@@ -14,6 +14,9 @@ import torch
 
 from . import _lib
 from ._lib import ptr, stream
+
+
+MB_HIST_MAX = _lib.MB_HIST_MAX
 
 
 def _pad(n):
@@ -43,6 +46,9 @@ class ControlBlock:
         self.t.copy_(torch.from_numpy(buf.view(np.uint8)))
 
     def read_hist(self, count):
+        if count > self.hist.numel() // _lib.HIST_DTYPE.itemsize:
+            raise _lib.MocatB200Error(f"history ring holds {self.hist.numel() // _lib.HIST_DTYPE.itemsize} records, "
+                                      f"{count} requested (MB_HIST_MAX)")
         nbytes = count * _lib.HIST_DTYPE.itemsize
         return self.hist[:nbytes].cpu().numpy().view(_lib.HIST_DTYPE).copy()
 
@@ -143,11 +149,15 @@ class _Resampler:
 
     def _alloc_resampler(self):
         dev = _dev()
-        self.cdf = torch.empty(self.n, dtype=torch.float64, device=dev)
         self.anc = torch.zeros(self.n, dtype=torch.int32, device=dev)
-        self.B = int(self.L.dll.mb_strata_count(self.n_total))
-        self.hist = torch.zeros(self.B, dtype=torch.int32, device=dev)
-        self.offsets = torch.zeros(self.B + 1, dtype=torch.int32, device=dev)
+        # systematic: fused exact-integer resampler (csrc/resample_fused.cu), no CDF in memory, 8-byte-aligned workspace
+        self.rs_ws = torch.zeros((int(self.L.dll.mb_rs_workspace_bytes(self.n)) + 7) // 8, dtype=torch.int64, device=dev)
+        self.cdf = None
+        if self.resampling == _lib.RESAMPLE_MULTINOMIAL:
+            self.cdf = torch.empty(self.n, dtype=torch.float64, device=dev)
+            self.B = int(self.L.dll.mb_strata_count(self.n_total))
+            self.hist = torch.zeros(self.B, dtype=torch.int32, device=dev)
+            self.offsets = torch.zeros(self.B + 1, dtype=torch.int32, device=dev)
 
     def _cond_begin(self, st):
         """open the graph-conditional section (no-op outside capture); returns the stream to launch the body on"""
@@ -162,6 +172,11 @@ class _Resampler:
 
     def _resample_kernels(self, st):
         L = self.L
+        if self.resampling == _lib.RESAMPLE_SYSTEMATIC:
+            L.call("mb_rs_tile_sums", self.ctx, ptr(self.rs_ws), ptr(self.lw), self.n, self.n, 1, ptr(self.ctl.t), 0, st)
+            L.call("mb_rs_ancestors", self.ctx, ptr(self.rs_ws), ptr(self.lw), self.n, self.n, 1, ptr(self.ctl.t), 0, -1,
+                   None, None, ptr(self.anc), st)
+            return
         L.call("mb_cumsum_lw", self.ctx, ptr(self.lw), self.n, ptr(self.ctl.t), 0, ptr(self.cdf), st)
         if self.resampling == _lib.RESAMPLE_MULTINOMIAL:
             # clear = 0: allocated zeroed, and mb_ancestors_sorted zeroes the counts it consumed (no memset node per step)
@@ -228,6 +243,15 @@ class SMCEngine(_Resampler):
                     ptr(self.ctl.t), stream())
         self._temper(advance=False)
         self.enqueued = 0
+        self._cur0 = self.cur
+
+    def settle(self):
+        """Synchronise and point `cur` at the buffer of the LAST REAL step.  update() flips the ping-pong index on every
+        call, but once the device set `done` every kernel of a step exits early and writes nothing; the valid buffer is
+        fixed by the device iteration count.  Returns the control block."""
+        c = self.ctl.read()
+        self.cur = (self._cur0 + int(c['iter'])) & 1
+        return c
 
     def _enqueue(self, events=None):
         st = stream()
@@ -333,6 +357,7 @@ class SMCEngine(_Resampler):
 # ------------------------------------------------------------------------------------------- bootstrap PF
 class PFEngine(_Resampler):
     """Device state + kernel sequence of a bootstrap particle filter (ssm/filtering.py)."""
+    _mocat_transient = True          # cdict: live-session member, not pickled
 
     def __init__(self, ssm, n, seed, ess_threshold=0.5, resampling=_lib.RESAMPLE_MULTINOMIAL, gid0=0, n_total=None):
         self.L = _lib.get()
@@ -343,37 +368,89 @@ class PFEngine(_Resampler):
         self.seed, self.gid0, self.resampling = int(seed), int(gid0), int(resampling)
         self.ess_threshold = float(ess_threshold)
         dev = _dev()
-        self.xbuf = [torch.zeros((self.d, self.ld), dtype=torch.float32, device=dev) for _ in range(2)]
+        # Lorenz-96 runs on the TILED layout (32-particle tiles of d x 32 floats, csrc/pf_l96.cu); the small dense
+        # models keep plain SoA columns
+        self.tiled = int(ssm.kind) == _lib.SSM_LORENZ96
+        self.xbuf = [self._alloc_x(dev) for _ in range(2)]
         self.cur = 0
-        self.lw = torch.zeros(self.n, dtype=torch.float32, device=dev)
+        self._lw_full = torch.zeros(self.ld, dtype=torch.float32, device=dev)     # padded to a multiple of 32
+        self.lw = self._lw_full[:self.n]
         self._alloc_resampler()
         self.ctl = ControlBlock()
         self.t = 0
+
+    def _x_shape(self):
+        return (self.ld // 32, self.d, 32) if self.tiled else (self.d, self.ld)
+
+    def _alloc_x(self, dev):
+        return torch.zeros(self._x_shape(), dtype=torch.float32, device=dev)
 
     @property
     def x(self):
         return self.xbuf[self.cur]
 
+    def _comm(self):
+        return None
+
+    def _shard_ref(self):
+        return None
+
     def init(self, y0):
         """initiate_particles (ssm/filtering.py:173-193).  y0: device float32 (dim_obs,)"""
-        self.L.call("mb_pf_init", self.ctx, C.byref(self.ssm), ptr(self.x), self.ld, self.n, self.n_total, ptr(y0),
-                    ptr(self.lw), self.seed, self.gid0, self.ess_threshold, ptr(self.ctl.t), ptr(self.ctl.hist),
-                    None, stream())
+        if self.tiled:
+            self.L.call("mb_pf_l96_init", self.ctx, C.byref(self.ssm), ptr(self.x), self.n, self.n_total, ptr(y0),
+                        ptr(self.lw), self.seed, self.gid0, self.ess_threshold, ptr(self.ctl.t), ptr(self.ctl.hist),
+                        self._comm(), stream())
+        else:
+            self.L.call("mb_pf_init", self.ctx, C.byref(self.ssm), ptr(self.x), self.ld, self.n, self.n_total, ptr(y0),
+                        ptr(self.lw), self.seed, self.gid0, self.ess_threshold, ptr(self.ctl.t), ptr(self.ctl.hist),
+                        self._comm(), stream())
         self.t = 0
+
+    def _step_kernel(self, y, st):
+        src, dst = self.xbuf[self.cur], self.xbuf[self.cur ^ 1]
+        if self.tiled:
+            self.L.call("mb_pf_l96_step", self.ctx, C.byref(self.ssm), ptr(src), ptr(dst), self.n, self.n_total,
+                        ptr(self.anc), ptr(y), ptr(self.lw), self.seed, self.t, self.gid0, self.ess_threshold,
+                        ptr(self.ctl.t), ptr(self.ctl.hist), self._shard_ref(), self._comm(), st)
+        else:
+            self.L.call("mb_pf_step", self.ctx, C.byref(self.ssm), ptr(src), ptr(dst), self.ld, self.n, self.n_total,
+                        ptr(self.anc), ptr(y), ptr(self.lw), self.seed, self.t, self.gid0, self.ess_threshold,
+                        ptr(self.ctl.t), ptr(self.ctl.hist), self._shard_ref(), self._comm(), st)
+        self.cur ^= 1
 
     def step(self, y):
         """one body of the scan in run_particle_filter_for_marginals (ssm/filtering.py:280-311)"""
         st = stream()
         self.t += 1
         self._resample_kernels(st)
-        src, dst = self.xbuf[self.cur], self.xbuf[self.cur ^ 1]
-        self.L.call("mb_pf_step", self.ctx, C.byref(self.ssm), ptr(src), ptr(dst), self.ld, self.n, self.n_total,
-                    ptr(self.anc), ptr(y), ptr(self.lw), self.seed, self.t, self.gid0, self.ess_threshold,
-                    ptr(self.ctl.t), ptr(self.ctl.hist), None, None, st)
-        self.cur ^= 1
+        self._step_kernel(y, st)
 
     def values(self):
+        """(n, d) float32 device tensor of the current particle values (a copy for the tiled layout)"""
+        if self.tiled:
+            return self.x.permute(0, 2, 1).reshape(-1, self.d)[:self.n]
         return self.x[:, :self.n].t()
+
+    def gather_current(self):
+        """x <- x[anc] into the other buffer (resample_particles, ssm/filtering.py:202-217)"""
+        src, dst = self.xbuf[self.cur], self.xbuf[self.cur ^ 1]
+        if self.tiled:
+            self.L.call("mb_gather_tiled", self.ctx, ptr(self.anc), self.n, self.d, ptr(src), self.n, ptr(dst), 1, stream())
+        else:
+            self.L.call("mb_gather_state", self.ctx, ptr(self.anc), self.n, self.d, ptr(src), self.ld, ptr(dst), self.ld,
+                        stream())
+        self.cur ^= 1
+
+    def moments(self):
+        """weighted mean / variance of every coordinate under the current weights (device float64 (d,) tensors)"""
+        if self.tiled:
+            mean = torch.empty(self.d, dtype=torch.float64, device=self.x.device)
+            var = torch.empty(self.d, dtype=torch.float64, device=self.x.device)
+            self.L.call("mb_weighted_moments_tiled", self.ctx, ptr(self.x), self.n, self.d, ptr(self.lw), ptr(self.ctl.t),
+                        ptr(mean), ptr(var), stream())
+            return mean, var
+        return weighted_moments(self.x, self.n, self.lw, self.ctl)
 
 
 # ------------------------------------------------------------------------------------------- SMC-ABC
@@ -431,6 +508,13 @@ class ABCEngine(_Resampler):
                     self.gid0, ptr(self.ctl.t), stream())
         self._adapt(advance=False)
         self.enqueued = 0
+        self._cur0 = self.cur
+
+    def settle(self):
+        """see SMCEngine.settle: x / up / dist / alpha are all double buffered"""
+        c = self.ctl.read()
+        self.cur = (self._cur0 + int(c['iter'])) & 1
+        return c
 
     def update(self):
         st = stream()

@@ -105,40 +105,56 @@ class ShardContext:
         self.L.call("mb_comm_allgather", self.comm, _lib.ptr(src), int(nd), _lib.ptr(dst), None, _lib.stream())
 
 
-def _make_shard(sc, n_local, x_peers, cdf_peers, totals):
+def _make_shard(sc, n_local, x_peers, cdf_peers, totals, anc_peers):
     sh = _lib.Shard()
     sh.rank, sh.world, sh.n_local, sh.n_total = sc.rank, sc.world, int(n_local), int(n_local) * sc.world
     for r in range(sc.world):
         sh.x_peers[r] = x_peers[r]
-        sh.cdf_peers[r] = cdf_peers[r]
+        sh.cdf_peers[r] = cdf_peers[r] if cdf_peers is not None else None
+        sh.anc_peers[r] = anc_peers[r]
     sh.totals = totals.data_ptr()
     return sh
 
 
 def _sharded_alloc(eng, sc):
+    """IPC-shared buffers of a sharded engine: both particle buffers, the ancestor array (the fused systematic
+    resampler writes an output's ancestor into the owning rank's array) and, for multinomial resampling, the
+    rank-relative CDF and the strata histogram."""
     import torch
-    xs = [sc.alloc_shared((eng.d, eng.ld), torch.float32) for _ in range(2)]
+    xs = [sc.alloc_shared(tuple(eng.xbuf[0].shape), torch.float32) for _ in range(2)]
     eng.xbuf = [xs[0][0], xs[1][0]]
-    eng.cdf, cdf_peers = sc.alloc_shared((eng.n,), torch.float64)
-    eng.hist_local, hist_peers = sc.alloc_shared((eng.B,), torch.int32)
-    eng.hist_peers = (C.c_void_p * sc.world)(*hist_peers)
-    eng.totals = torch.zeros(sc.world, dtype=torch.float64, device=sc.device)
-    eng.shards = [_make_shard(sc, eng.n, xs[k][1], cdf_peers, eng.totals) for k in range(2)]
+    eng.anc, anc_peers = sc.alloc_shared((eng.n,), torch.int32)
+    cdf_peers = None
+    if eng.resampling == _lib.RESAMPLE_MULTINOMIAL:
+        eng.cdf, cdf_peers = sc.alloc_shared((eng.n,), torch.float64)
+        eng.hist_local, hist_peers = sc.alloc_shared((eng.B,), torch.int32)
+        eng.hist_peers = (C.c_void_p * sc.world)(*hist_peers)
+    eng.totals = torch.zeros(sc.world, dtype=torch.float64, device=sc.device)      # fp64 totals / uint64 bit patterns
+    eng._barrier_out = torch.zeros(sc.world, dtype=torch.float64, device=sc.device)
+    eng.shards = [_make_shard(sc, eng.n, xs[k][1], cdf_peers, eng.totals, anc_peers) for k in range(2)]
 
 
 def _sharded_resample_kernels(eng, sc, st):
-    """scan (rank-relative, exact) + local strata histogram -> ONE exchange (weight totals; also the barrier before
-    the peers read each other's histograms) -> histogram sum over ranks -> global sorted-uniform ancestor search over
-    the peer-mapped CDFs.  Every launch is predicated on the replicated control block."""
+    """Every launch is predicated on the replicated control block.
+    systematic : integer tile sums -> ONE exchange of the 8-byte shard totals -> fused ancestors, written straight into
+                 the array of the rank that owns each output (peer stores over NVLink) -> one more exchange as the
+                 barrier before the step kernel reads them.
+    multinomial: scan (rank-relative, exact) + local strata histogram -> one exchange (weight totals; also the barrier
+                 before the peers read each other's histograms) -> histogram sum over ranks -> global sorted-uniform
+                 ancestor search over the peer-mapped CDFs."""
     L, ptr = eng.L, _lib.ptr
     ctl = ptr(eng.ctl.t)
-    multinomial = eng.resampling == _lib.RESAMPLE_MULTINOMIAL
+    if eng.resampling == _lib.RESAMPLE_SYSTEMATIC:
+        L.call("mb_rs_tile_sums", eng.ctx, ptr(eng.rs_ws), ptr(eng.lw), eng.n, eng.n_total, 1, ctl, 0, st)
+        L.call("mb_comm_allgather", sc.comm, ptr(eng.rs_ws), 1, ptr(eng.totals), ctl, st)
+        L.call("mb_rs_ancestors", eng.ctx, ptr(eng.rs_ws), ptr(eng.lw), eng.n, eng.n_total, 1, ctl, 0, -1, ptr(eng.totals),
+               C.byref(eng.shards[eng.cur]), ptr(eng.anc), st)
+        L.call("mb_comm_allgather", sc.comm, ptr(eng.totals), 1, ptr(eng._barrier_out), ctl, st)
+        return
     L.call("mb_cumsum_lw", eng.ctx, ptr(eng.lw), eng.n, ctl, 2, ptr(eng.cdf), st)
-    if multinomial:
-        L.call("mb_strata_hist", eng.ctx, eng.n, eng.gid0, eng.B, eng.seed, 0, ctl, ptr(eng.hist_local), 1, st)
+    L.call("mb_strata_hist", eng.ctx, eng.n, eng.gid0, eng.B, eng.seed, 0, ctl, ptr(eng.hist_local), 1, st)
     L.call("mb_comm_allgather", sc.comm, ptr(eng.cdf[eng.n - 1:]), 1, ptr(eng.totals), ctl, st)
-    if multinomial:
-        L.call("mb_strata_reduce", eng.ctx, sc.comm, eng.hist_peers, sc.world, eng.B, ptr(eng.hist), 0, ctl, st)
+    L.call("mb_strata_reduce", eng.ctx, sc.comm, eng.hist_peers, sc.world, eng.B, ptr(eng.hist), 0, ctl, st)
     L.call("mb_ancestors_sorted", eng.ctx, None, eng.n_total, C.byref(eng.shards[eng.cur]), eng.resampling,
            ptr(eng.hist), ptr(eng.offsets), eng.B, eng.seed, 0, eng.gid0, eng.n_total, ptr(eng.anc), eng.n, ctl, st)
 
@@ -216,8 +232,9 @@ def acquire_sharded_smc(target, move, temper, n_local, seed, resampling, schedul
 
 def ShardedPFEngine(sc, ssm, n_local, seed, ess_threshold=0.5, resampling=_lib.RESAMPLE_MULTINOMIAL):
     """engine.PFEngine whose population is sharded over sc.world GPUs"""
-    import torch
     from . import engine
+    if n_local % 32:
+        raise _lib.MocatB200Error("sharded particle filter: n_local must be a multiple of 32 (tile / pair alignment)")
 
     class _Eng(engine.PFEngine):
         def __init__(self):
@@ -226,22 +243,13 @@ def ShardedPFEngine(sc, ssm, n_local, seed, ess_threshold=0.5, resampling=_lib.R
             self.sc = sc
             _sharded_alloc(self, sc)
 
-        def init(self, y0):
-            self.L.call("mb_pf_init", self.ctx, C.byref(self.ssm), _lib.ptr(self.x), self.ld, self.n, self.n_total,
-                        _lib.ptr(y0), _lib.ptr(self.lw), self.seed, self.gid0, self.ess_threshold, _lib.ptr(self.ctl.t),
-                        _lib.ptr(self.ctl.hist), sc.comm, _lib.stream())
-            self.t = 0
+        def _comm(self):
+            return sc.comm
 
-        def step(self, y):
-            st = _lib.stream()
-            L, ptr = self.L, _lib.ptr
-            self.t += 1
+        def _shard_ref(self):
+            return C.byref(self.shards[self.cur])
+
+        def _resample_kernels(self, st):
             _sharded_resample_kernels(self, sc, st)
-            sh = self.shards[self.cur]
-            src, dst = self.xbuf[self.cur], self.xbuf[self.cur ^ 1]
-            L.call("mb_pf_step", self.ctx, C.byref(self.ssm), ptr(src), ptr(dst), self.ld, self.n, self.n_total,
-                   ptr(self.anc), ptr(y), ptr(self.lw), self.seed, self.t, self.gid0, self.ess_threshold,
-                   ptr(self.ctl.t), ptr(self.ctl.hist), C.byref(sh), sc.comm, st)
-            self.cur ^= 1
 
     return _Eng()

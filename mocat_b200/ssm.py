@@ -99,6 +99,32 @@ class Lorenz96(StateSpaceModel):
         return models.make_lorenz96(self.dim, self.forcing_constant, 0.05 if dt is None else dt, self.substeps,
                                     self.transition_std, self.likelihood_std, self.initial_mean, self.initial_std)
 
+    def _flow(self, x, dt):
+        """host fp64 version of the device transition map (`substeps` RK4 steps); data generation only"""
+        F, h = self.forcing_constant, dt / self.substeps
+        rhs = lambda v: (np.roll(v, -1) - np.roll(v, 2)) * np.roll(v, 1) - v + F          # lorenz96.py:14-20
+        for _ in range(self.substeps):
+            k1 = rhs(x); k2 = rhs(x + 0.5 * h * k1); k3 = rhs(x + 0.5 * h * k2); k4 = rhs(x + h * k3)
+            x = x + (h / 6.0) * (k1 + 2 * k2 + 2 * k3 + k4)
+        return x
+
+    def simulate(self, t_all, random_key, spinup=1000):
+        """ssm/ssm.py:138-163 (host; data generation is not on the hot path): a trajectory started on the attractor
+        (`spinup` noise-free steps) with process noise, observed through y = x + likelihood_std * noise"""
+        rng = np.random.default_rng(key_to_seed(random_key))
+        t_all = np.asarray(t_all, np.float64)
+        dt = float(t_all[1] - t_all[0]) if len(t_all) > 1 else 0.05
+        x = self.initial_mean + self.initial_std * rng.standard_normal(self.dim) + self.forcing_constant
+        for _ in range(spinup):
+            x = self._flow(x, dt)
+        xs, ys = np.empty((len(t_all), self.dim)), np.empty((len(t_all), self.dim))
+        for i in range(len(t_all)):
+            if i > 0:
+                x = self._flow(x, dt) + self.transition_std * rng.standard_normal(self.dim)
+            xs[i] = x
+            ys[i] = x + self.likelihood_std * rng.standard_normal(self.dim)
+        return cdict(x=xs, y=ys, t=t_all, name=f'{self.name} simulation')
+
 
 class ParticleFilter:
     """ssm/filtering.py:20-139 (interface)."""
@@ -126,13 +152,29 @@ def _check_filter(pf):
 
 
 def _moments(eng):
-    mean, var = engine.weighted_moments(eng.x, eng.n, eng.lw, eng.ctl)
-    return mean, var
+    return eng.moments()
+
+
+def _engine_of(particles):
+    eng = getattr(particles, 'engine', None)
+    if eng is None:
+        raise _lib.MocatB200Error("this particle cdict has no live device engine (it was loaded from disk or created "
+                                  "elsewhere); start again with initiate_particles / run_particle_filter_for_marginals")
+    return eng
+
+
+def _host_value(eng):
+    """latest population as a host array, or None when it is too large to be worth a device->host copy by default
+    (n = 1e8, d = 40 is 16 GB); the engine keeps it on the device (`particles.engine.values()`)"""
+    if eng.n * (eng.d + 1) * 4 > HISTORY_AUTO_BYTES:
+        return None, None
+    return eng.values().cpu().numpy()[None], eng.lw.cpu().numpy()[None]
 
 
 def initiate_particles(ssm_scenario, particle_filter, n, random_key, y=None, t=None, ess_threshold=0.5,
                        resampling='multinomial'):
-    """ssm/filtering.py:173-193."""
+    """ssm/filtering.py:173-193.  The returned cdict carries the live device engine (`engine`, dropped on save): the
+    online API is STATEFUL -- propagate_particle_filter advances that engine in place."""
     torch = _torch()
     _check_filter(particle_filter)
     particle_filter.startup(ssm_scenario)
@@ -144,10 +186,40 @@ def initiate_particles(ssm_scenario, particle_filter, n, random_key, y=None, t=N
     eng.init(torch.as_tensor(y, device="cuda"))
     c = eng.ctl.read()
     mean, var = _moments(eng)
-    return cdict(value=eng.values().cpu().numpy()[None], log_weight=eng.lw.cpu().numpy()[None],
-                 t=np.atleast_1d(t) if t is not None else np.zeros(1), y=y[None],
-                 ess=np.atleast_1d(c['ess']), log_norm_constant=np.atleast_1d(c['log_z']),
-                 mean=mean.cpu().numpy()[None], var=var.cpu().numpy()[None], engine=eng)
+    out = cdict(t=np.atleast_1d(t) if t is not None else np.zeros(1), y=y[None],
+                ess=np.atleast_1d(c['ess']), log_norm_constant=np.atleast_1d(c['log_z']),
+                mean=mean.cpu().numpy()[None], var=var.cpu().numpy()[None], engine=eng)
+    out.value, out.log_weight = _host_value(eng)
+    return out
+
+
+def resample_particles(particles, random_key=None, resample_full=True):
+    """ssm/filtering.py:202-217: unconditional resampling of the latest population, log-weights reset to zero.
+    Runs the engine's resampler (ancestors) and a device gather (mb_gather_state / mb_gather_tiled); only the latest
+    time slice lives on the device, so `resample_full` (re-indexing the stored trajectories) applies to the host copy."""
+    torch = _torch()
+    eng = _engine_of(particles)
+    c = eng.ctl.read()
+    c['resample'] = 1
+    eng.ctl.write(c)
+    eng._resample_kernels(_lib.stream())
+    eng.gather_current()
+    anc = eng.anc.cpu().numpy() if particles.value is not None else None
+    eng._lw_full.zero_()
+    logn = float(np.log(eng.n_total))
+    c['wmax'], c['s1'], c['s2'] = 0.0, float(eng.n_total), float(eng.n_total)
+    c['lse'] = c['lse2'] = c['log_ess'] = logn
+    c['ess'], c['resample'], c['resampled'] = float(eng.n_total), 0, 1
+    eng.ctl.write(c)
+    out = particles.copy()
+    if particles.value is not None:
+        out.value = particles.value[:, anc] if resample_full else particles.value.copy()
+        out.value[-1] = eng.values().cpu().numpy()
+        out.log_weight = particles.log_weight.copy()
+        out.log_weight[-1] = 0.0
+    out.ess = particles.ess.copy()
+    out.ess[-1] = float(eng.n_total)
+    return out
 
 
 def propagate_particle_filter(ssm_scenario, particle_filter, particles, y_new, t_new, random_key=None,
@@ -155,7 +227,7 @@ def propagate_particle_filter(ssm_scenario, particle_filter, particles, y_new, t
     """ssm/filtering.py:220-252: resample iff ess[-1] < ess_threshold*n, propose, weight, append."""
     torch = _torch()
     _check_filter(particle_filter)
-    eng = particles.engine
+    eng = _engine_of(particles)
     eng.ess_threshold = float(ess_threshold)
     y_new = np.atleast_1d(np.asarray(y_new, np.float32))
     t_prev = float(particles.t[-1])
@@ -171,8 +243,9 @@ def propagate_particle_filter(ssm_scenario, particle_filter, particles, y_new, t
     c = eng.ctl.read()
     mean, var = _moments(eng)
     out = particles.copy()
-    out.value = np.append(particles.value, eng.values().cpu().numpy()[None], axis=0)
-    out.log_weight = np.append(particles.log_weight, eng.lw.cpu().numpy()[None], axis=0)
+    if particles.value is not None:
+        out.value = np.append(particles.value, eng.values().cpu().numpy()[None], axis=0)
+        out.log_weight = np.append(particles.log_weight, eng.lw.cpu().numpy()[None], axis=0)
     out.y = np.append(particles.y, y_new[None], axis=0)
     out.t = np.append(particles.t, t_new)
     out.ess = np.append(particles.ess, c['ess'])
@@ -185,53 +258,79 @@ def propagate_particle_filter(ssm_scenario, particle_filter, particles, y_new, t
 def run_particle_filter_for_marginals(ssm_scenario, particle_filter, y, t, random_key, n=None, initial_sample=None,
                                       ess_threshold=0.5, resampling='multinomial', keep_history=None,
                                       moments=True):
-    """ssm/filtering.py:255-324.  The time loop is enqueued without any host synchronisation."""
+    """ssm/filtering.py:255-324.  The time loop is enqueued without any host synchronisation; per-step ESS,
+    log-evidence and (moments=True) weighted means / variances are read back once at the end.  The stacked
+    (T, n, d) history of the reference is returned when it fits `HISTORY_AUTO_BYTES` (or keep_history=True);
+    otherwise `value` / `log_weight` hold the final population only, or None when even that exceeds the budget
+    (it stays on the device: `out.engine.values()`).  initial_sample: a cdict from initiate_particles / a previous
+    call -- every (y, t) is then a propagation step of its engine (filtering.py:266-276)."""
     torch = _torch()
     _check_filter(particle_filter)
     y = np.asarray(y, np.float32)
     if y.ndim == 1:
         y = y[..., np.newaxis]
     t = np.asarray(t, np.float64)
-    if initial_sample is not None:
-        raise _lib.MocatB200Error("initial_sample continuation: use propagate_particle_filter")
     T = len(y)
-    dt = float(t[1] - t[0]) if T > 1 else None
-    if T > 2 and not np.allclose(np.diff(t), dt):
+    if T > engine.MB_HIST_MAX:
+        raise _lib.MocatB200Error(f"at most {engine.MB_HIST_MAX} time steps per call (device history ring)")
+    if initial_sample is None:
+        dt = float(t[1] - t[0]) if T > 1 else None
+        t_all = t
+    else:
+        dt = float(t[0] - initial_sample.t[-1])
+        t_all = np.concatenate([[float(initial_sample.t[-1])], t])
+    if len(t_all) > 2 and not np.allclose(np.diff(t_all), dt):
         raise _lib.MocatB200Error("run_particle_filter_for_marginals needs equally spaced t (time-homogeneous model)")
-    eng = engine.PFEngine(ssm_scenario._ssm(dt), n, key_to_seed(random_key), ess_threshold=ess_threshold,
-                          resampling=_RESAMPLING[resampling])
-    d = eng.d
+    if initial_sample is None:
+        eng = engine.PFEngine(ssm_scenario._ssm(dt), n, key_to_seed(random_key), ess_threshold=ess_threshold,
+                              resampling=_RESAMPLING[resampling])
+    else:
+        eng = _engine_of(initial_sample)
+        eng.ess_threshold = float(ess_threshold)
+        eng.ssm = ssm_scenario._ssm(dt)
+        c = eng.ctl.read()
+        want = 1 if c['ess'] < ess_threshold * eng.n_total else 0
+        if want != c['resample']:
+            c['resample'] = want
+            eng.ctl.write(c)
+    n, d = eng.n, eng.d
     if keep_history is None:
         keep_history = T * n * (d + 1) * 4 <= HISTORY_AUTO_BYTES
     yd = torch.as_tensor(y, device="cuda")
-    vals, lws, means, vars_ = [], [], [], []
+    vals, lws = [], []
+    mom = torch.empty((T, 2, d), dtype=torch.float64, device="cuda") if moments else None
 
-    def record():
+    def record(i):
         if keep_history:
-            vals.append(eng.values().clone(memory_format=_torch().contiguous_format))
-            lws.append(eng.lw.clone())
+            vals.append(eng.values().clone(memory_format=torch.contiguous_format).cpu())   # streamed to the host per step
+            lws.append(eng.lw.cpu())
         if moments:
             m, v = _moments(eng)
-            means.append(m)
-            vars_.append(v)
+            mom[i, 0], mom[i, 1] = m, v
 
-    eng.init(yd[0])
-    record()
-    for i in range(1, T):
-        eng.step(yd[i])
-        record()
-    hist = eng.ctl.read_hist(T)
+    t0 = eng.t + 1 if initial_sample is not None else 0
+    for i in range(T):
+        if initial_sample is None and i == 0:
+            eng.init(yd[0])
+        else:
+            eng.step(yd[i])
+        record(i)
+    hist = eng.ctl.read_hist(t0 + T)[t0:]
     out = cdict(t=t, y=y, ess=hist['ess'].copy(), log_norm_constant=hist['log_z'].copy(),
                 resampled=hist['resampled'].copy(), engine=eng)
     if keep_history:
-        out.value = torch.stack(vals).cpu().numpy()
-        out.log_weight = torch.stack(lws).cpu().numpy()
+        out.value = torch.stack(vals).numpy()
+        out.log_weight = torch.stack(lws).numpy()
     else:
-        out.value = eng.values().cpu().numpy()[None]
-        out.log_weight = eng.lw.cpu().numpy()[None]
+        out.value, out.log_weight = _host_value(eng)
     if moments:
-        out.mean = torch.stack(means).cpu().numpy()
-        out.var = torch.stack(vars_).cpu().numpy()
+        mh = mom.cpu().numpy()
+        out.mean, out.var = mh[:, 0], mh[:, 1]
+    if initial_sample is not None:
+        for k in ('t', 'y', 'ess', 'log_norm_constant', 'mean', 'var', 'value', 'log_weight'):
+            prev, new = getattr(initial_sample, k, None), getattr(out, k, None)
+            if prev is not None and new is not None and (k not in ('value', 'log_weight') or keep_history):
+                setattr(out, k, np.concatenate([prev, new], axis=0))
     return out
 
 

@@ -166,7 +166,7 @@ class MetropolisedSMCSampler(TemperedSMCSampler):
     def fetch(self, ensemble_state):
         """materialise the current device population as a cdict of NumPy arrays"""
         eng = ensemble_state.engine
-        c = eng.ctl.read()
+        c = eng.settle()
         snap = {k: v.cpu().numpy() for k, v in self._snapshot(eng).items()}
         out = cdict(**snap)
         out.potential = out.prior_potential + c['beta'] * out.likelihood_potential
@@ -181,29 +181,42 @@ class MetropolisedSMCSampler(TemperedSMCSampler):
         eng = initial_extra.engine
         n, d = eng.n, eng.d
         keep = self.keep_history
-        if keep is None:
-            keep = n * (d + 4) * 4 * min(self.max_iter + 1, 64) <= HISTORY_AUTO_BYTES
-        snaps = [self._snapshot(eng)] if keep else None
+        auto = keep is None
+        if auto:
+            keep = n * (d + 4) * 4 * 2 <= HISTORY_AUTO_BYTES
+        # per-iteration snapshots are moved to the host at the end of every burst (the loop synchronises there anyway),
+        # so the device never holds more than `check_every` of them; an automatic history that outgrows
+        # HISTORY_AUTO_BYTES is dropped in favour of the final population
+        host_snaps, pending, kept_bytes = [], ([self._snapshot(eng)] if keep else []), 0
         it = 0
         while it < self.max_iter:
+            if self.max_iter > engine.MB_HIST_MAX - 1:
+                raise _lib.MocatB200Error(f"max_iter <= {engine.MB_HIST_MAX - 1} (device history ring)")
             burst = min(self.check_every, self.max_iter - it)
             for _ in range(burst):
                 eng.update()
                 it += 1
                 self._post_update(eng, initial_extra)
                 if keep:
-                    snaps.append(self._snapshot(eng))
-            if eng.ctl.read()['done']:
+                    pending.append(self._snapshot(eng))
+            done = bool(eng.ctl.read()['done'])
+            if keep:
+                for sn in pending:
+                    host_snaps.append({k: v.cpu().numpy() for k, v in sn.items()})
+                    kept_bytes += sum(v.nbytes for v in host_snaps[-1].values())
+                pending = []
+                if auto and kept_bytes > HISTORY_AUTO_BYTES:
+                    keep, host_snaps = False, []
+            if done:
                 break
-        c = eng.ctl.read()
+        c = eng.settle()
         iters = int(c['iter'])
         hist = eng.ctl.read_hist(iters + 1)
         chain = cdict()
         if keep:
-            snaps = snaps[:iters + 1]
-            host = _to_host({k: torch.stack([s[k] for s in snaps]) for k in self._FIELDS})
+            host_snaps = host_snaps[:iters + 1]
             for k in self._FIELDS:
-                setattr(chain, k, host[k])
+                setattr(chain, k, np.stack([sn[k] for sn in host_snaps]))
             betas = hist['beta'][:, None]
         else:
             # no device clones: only `value` needs a kernel (SoA -> row-major), the rest is copied from the engine buffers

@@ -72,12 +72,11 @@ class SMCABC:
         resample = ess < self.resample_thr * n                         # :152-155 strict
         anc = None
         if resample:
-            cdf = core.cdf_from_log_weights(lw)
-            if self.resampling == 'systematic':
-                u0 = philox.uniform53(self.seed, np.zeros(1, np.uint64), it, philox.P_RESAMPLE)[0]
-                anc = core.ancestors_systematic(cdf, u0)
+            if self.resampling == 'systematic':                        # exact-rational convention (resample_fused.cu)
+                k0 = int(philox.uniform32(self.seed, np.zeros(1, np.uint64), it, philox.P_RESAMPLE)[0])
+                anc = core.ancestors_systematic_exact(core.integer_weights_log(lw), k0)
             else:
-                anc = core.ancestors_multinomial_stratified(cdf, self.seed, it)[0]
+                anc = core.ancestors_multinomial_stratified(core.cdf_from_log_weights(lw), self.seed, it)[0]
             x, up, dist = x[anc], up[anc], dist[anc]
             lw, ess = np.zeros(n), float(n)
         alive = lw > -np.inf                                           # :210-219

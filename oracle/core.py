@@ -170,6 +170,74 @@ def ancestors_multinomial(cdf, u):
     return ancestors_from_uniforms(cdf, u)
 
 
+# ----------------------------------------------------------------------------- exact-rational systematic resampling
+# Convention of csrc/resample_fused.cu (the particle filter's production resampler).  The reference only fixes the LAW
+# of the ancestors (`random.categorical`, transport/smc.py:65-67, ssm/filtering.py:199); the device evaluates systematic
+# resampling on integer weights in exact rational arithmetic so that no scan order / GPU sharding can change a bit:
+#     e_i = rint(w_i * 2^K)  (uint64),  K = min(40, 63 - ceil(log2 n_total)),  C_j = sum_{i<=j} e_i,  S = C_{n-1},
+#     u0 = k0 / 2^32,   a_i = min{ j : (i + u0) / n_out < C_j / S }.
+def rs_scale_bits(n_total):
+    lg = 0
+    while (1 << lg) < int(n_total):
+        lg += 1
+    return min(40, 63 - lg)
+
+
+def integer_weights(w, n_total=None):
+    """e_i = rint(float32(w_i) * 2^K) as uint64 (linear weights <= 1; NaN / negative -> 0, as __float2ull_rn)."""
+    w = np.asarray(w, dtype=np.float32)
+    K = rs_scale_bits(w.shape[0] if n_total is None else n_total)
+    v = w.astype(np.float64) * float(2 ** K)                 # exact: power-of-two scaling of an fp32 value
+    v = np.where(np.isnan(v) | (v < 0), 0.0, v)
+    return np.rint(v).astype(np.uint64)
+
+
+def integer_weights_log(lw, n_total=None):
+    """log mode: w_i = exp(lw_i - max lw) evaluated in fp32 like the device (the device uses the MUFU ex2 approximation,
+    so individual e_i may differ in their last bits: parity of the ancestors from log-weights is statistical, the
+    bit-exact contract is the linear mode)."""
+    lw = np.asarray(lw, dtype=np.float32)
+    m = np.max(lw)
+    if not np.isfinite(m):
+        m = np.float32(0.0)
+    with np.errstate(invalid='ignore', over='ignore'):
+        e = np.exp((lw - m).astype(np.float32)).astype(np.float32)
+    return integer_weights(e, n_total)
+
+
+def systematic_counts_exact(C, S, n_out, k0):
+    """c_j = #{ i in [0, n_out) : (i * 2^32 + k0) * S < C_j * n_out * 2^32 } with Python integers (exact).
+    Vectorised through an extended-precision estimate; every estimate within 1e-6 of an integer is settled exactly."""
+    C = np.asarray(C, dtype=np.uint64)
+    S, n_out, k0 = int(S), int(n_out), int(k0)
+    if S == 0:
+        return np.zeros(C.shape, dtype=np.int64)
+    t = C.astype(np.longdouble) * (np.longdouble(n_out) / np.longdouble(S)) - np.longdouble(k0) / np.longdouble(2 ** 32)
+    c = np.clip(np.ceil(t), 0, n_out).astype(np.int64)
+    fr = t - np.floor(t)
+    doubt = np.nonzero((fr < 1e-6) | (fr > 1 - 1e-6) | (C.astype(np.float64) >= float(S)))[0]
+    for j in doubt:
+        num = int(C[j]) * n_out * (1 << 32) - k0 * S          # i < num / (S 2^32)
+        cj = 0 if num <= 0 else -((-num) // (S << 32))        # ceil division
+        c[j] = min(max(cj, 0), n_out)
+    return c
+
+
+def ancestors_systematic_exact(e, k0, n_out=None):
+    """ancestors of exact-rational systematic resampling from integer weights e (uint64) and the 32-bit offset k0.
+    All-zero weights: every output takes the last particle (legacy convention cdf[n-1] = 1)."""
+    e = np.asarray(e, dtype=np.uint64)
+    n = e.shape[0]
+    n_out = n if n_out is None else int(n_out)
+    C = np.cumsum(e, dtype=np.uint64)
+    S = int(C[-1])
+    if S == 0:
+        return np.full(n_out, n - 1, dtype=np.int64)
+    c = systematic_counts_exact(C, S, n_out, k0)
+    counts = np.diff(np.concatenate([[0], c]))
+    return np.repeat(np.arange(n, dtype=np.int64), counts)
+
+
 def strata_count(n_total_out):
     """B = largest power of two <= n/16 (at least 1, at most 2^24): ~16-32 outputs per stratum"""
     B = 1

@@ -199,6 +199,8 @@ class Lorenz96SSM:
     """Lorenz96(NonLinearGaussian) with diagonal noise: x' = Phi(x) + z * sq ; y ~ N(x, sr^2)
     (nonlinear_gaussian.py:107-121 with H = I and diagonal Q, R -- config C3 uses Q=R=I)."""
 
+    pairwise_normals = True      # csrc/pf_l96.cu draws the normals of a particle PAIR from one Philox stream
+
     def __init__(self, dim=40, forcing=8.0, dt=0.05, substeps=1, q_std=1.0, r_std=1.0,
                  init_mean=0.0, init_std=1.0):
         self.dim = self.dim_obs = dim

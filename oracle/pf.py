@@ -22,9 +22,11 @@ class BootstrapPF:
         self.thr, self.resampling = float(ess_threshold), resampling
         self.gid = np.arange(self.n, dtype=np.uint64)
         self.normal_dtype = normal_dtype
+        # Lorenz-96 runs through the lane-split kernel (csrc/pf_l96.cu): pairwise Philox streams
+        self.normals = philox.normals_pairwise if getattr(ssm, 'pairwise_normals', False) else philox.normals
 
     def init(self, y0):                                                # filtering.py:173-193
-        z = philox.normals(self.seed, self.gid, 0, philox.P_INIT, self.ssm.dim, dtype=self.normal_dtype)
+        z = self.normals(self.seed, self.gid, 0, philox.P_INIT, self.ssm.dim, dtype=self.normal_dtype)
         x = self.ssm.initial_sample(z)
         lw = -self.ssm.likelihood_potential(x, y0)                     # :49-54
         return dict(x=x, lw=lw, ess=core.ess_log_weight(lw), t=0,
@@ -37,15 +39,14 @@ class BootstrapPF:
         resample = st['ess'] < self.thr * n                            # :287 (strict)
         anc = None
         if resample:                                                   # :196-199
-            cdf = core.cdf_from_log_weights(lw)
-            if self.resampling == 'systematic':
-                u0 = philox.uniform53(self.seed, np.zeros(1, np.uint64), t, philox.P_RESAMPLE)[0]
-                anc = core.ancestors_systematic(cdf, u0)
+            if self.resampling == 'systematic':                        # exact-rational convention (resample_fused.cu)
+                k0 = int(philox.uniform32(self.seed, np.zeros(1, np.uint64), t, philox.P_RESAMPLE)[0])
+                anc = core.ancestors_systematic_exact(core.integer_weights_log(lw), k0)
             else:
-                anc = core.ancestors_multinomial_stratified(cdf, self.seed, t)[0]
+                anc = core.ancestors_multinomial_stratified(core.cdf_from_log_weights(lw), self.seed, t)[0]
             x = x[anc]
             lw = np.zeros(n)                                           # :292
-        z = philox.normals(self.seed, self.gid, t, philox.P_MOVE, self.ssm.dim, dtype=self.normal_dtype)
+        z = self.normals(self.seed, self.gid, t, philox.P_MOVE, self.ssm.dim, dtype=self.normal_dtype)
         x_new = self.ssm.transition_sample(x, z)                       # :154-161
         lw_new = lw - self.ssm.likelihood_potential(x_new, y)          # :163-170, :303
         return dict(x=x_new, lw=lw_new, ess=core.ess_log_weight(lw_new), t=t,

@@ -124,3 +124,27 @@ def uniform53(seed, gid, step, purpose, index=0):
     """One fp64 [0,1) uniform per gid from words (0,1) of the slot."""
     x0, x1, _, _ = raw(seed, gid, step, purpose, index)
     return u53(x0, x1)
+
+
+def normals_pairwise(seed, gid, step, purpose, count, dtype=np.float64):
+    """`count` standard normals per gid with the PAIRWISE convention of csrc/pf_l96.cu: particles 2m and 2m+1 share
+    the Philox stream of their pair id m; coordinate k comes from slot k//2, words (0,1) for even k and (2,3) for odd
+    k; the cos branch of Box-Muller goes to the even particle, the sin branch to the odd one."""
+    gid = np.atleast_1d(np.asarray(gid, dtype=np.uint64))
+    pair = gid >> np.uint64(1)
+    odd = (gid & np.uint64(1)).astype(bool)
+    out = np.empty((gid.shape[0], count), dtype=dtype)
+    for c in range((count + 1) // 2):
+        x0, x1, x2, x3 = raw(seed, pair, step, purpose, c)
+        zc, zs = box_muller(x0, x1, dtype)
+        out[:, 2 * c] = np.where(odd, zs, zc)
+        if 2 * c + 1 < count:
+            zc, zs = box_muller(x2, x3, dtype)
+            out[:, 2 * c + 1] = np.where(odd, zs, zc)
+    return out
+
+
+def uniform32(seed, gid, step, purpose, index=0):
+    """word 0 of the slot as an integer in [0, 2^32): the systematic offset u0 = k0 / 2^32 of resample_fused.cu"""
+    x0, _, _, _ = raw(seed, gid, step, purpose, index)
+    return x0.astype(np.uint64)

@@ -11,7 +11,7 @@ Randomness: Philox streams of oracle/philox.py (the reference's threefry streams
 unpinned, see oracle/__init__.py).  Per iteration `it` and particle `gid`:
   move normals   purpose P_MOVE, step it, slots s*S .. s*S+nz-1   (nz = ceil(d/4), S = nz+1)
   accept uniform purpose P_MOVE, step it, slot  s*S+nz, word 0 (u24)
-  resampling     purpose P_RESAMPLE, step it: systematic u0 = uniform53(gid 0);
+  resampling     purpose P_RESAMPLE, step it: systematic u0 = uniform32(gid 0) / 2^32;
                  multinomial u_i = uniform53(gid i)
 Deviation noted in DESIGN.md: the reference recomputes lik = (U - U_prior)/beta after the
 move (smc.py:362-364); here (and on the device) the likelihood potential of the accepted
@@ -113,12 +113,11 @@ class TemperedSMC:
         resample = ess <= self.resample_thr * n                        # :298-301
         anc = None
         if resample:                                                   # :61-71
-            cdf = core.cdf_from_log_weights(lw)
-            if self.resampling == 'systematic':
-                u0 = philox.uniform53(self.seed, np.zeros(1, np.uint64), it, philox.P_RESAMPLE)[0]
-                anc = core.ancestors_systematic(cdf, u0)
+            if self.resampling == 'systematic':                        # exact-rational convention (resample_fused.cu)
+                k0 = int(philox.uniform32(self.seed, np.zeros(1, np.uint64), it, philox.P_RESAMPLE)[0])
+                anc = core.ancestors_systematic_exact(core.integer_weights_log(lw), k0)
             else:
-                anc = core.ancestors_multinomial_stratified(cdf, self.seed, it)[0]
+                anc = core.ancestors_multinomial_stratified(core.cdf_from_log_weights(lw), self.seed, it)[0]
             x, up, lik = x[anc], up[anc], lik[anc]
             lw = np.zeros(n)
             ess = float(n)

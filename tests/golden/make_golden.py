@@ -1,4 +1,4 @@
-"""Generate tests/golden/oracle_v1.npz.
+"""Generate tests/golden/oracle_v2.npz.
 
 The reference (mocat on JAX) cannot be imported in the build container (jax is absent: DESIGN.md section 2), so no
 vectors could be produced by the reference itself.  These fixtures are seeded inputs together with the outputs of the
@@ -40,6 +40,12 @@ def build():
     g["cdf_w"], g["cdf"], g["anc_u"] = w, cdf, u
     g["anc_multinomial"] = core.ancestors_multinomial(cdf, u).astype(np.int32)
     g["anc_systematic"] = core.ancestors_systematic(cdf, 0.37).astype(np.int32)
+    # exact-rational systematic resampling on integer weights (csrc/resample_fused.cu, the engines' path)
+    g["anc_exact_k0"] = np.array([0, 1, 0x9E3779B9, 0xFFFFFFFF], dtype=np.uint64)
+    g["anc_systematic_exact"] = np.stack([core.ancestors_systematic_exact(core.integer_weights(w), int(k)).astype(np.int32)
+                                          for k in g["anc_exact_k0"]])
+    # pairwise normals of the Lorenz-96 kernel (csrc/pf_l96.cu)
+    g["philox_normals_pairwise"] = philox.normals_pairwise(11, gid, 3, philox.P_MOVE, 8, dtype=np.float64)
     # quantile (jnp.quantile linear interpolation)
     v = rng.standard_normal(777).astype(np.float32)
     g["quant_v"] = v
@@ -79,10 +85,20 @@ def build():
     g["pf_log_z"] = np.array([o["log_z"] for o in out])
     g["pf_ess"] = np.array([o["ess"] for o in out])
     g["kalman_loglik"] = np.float64(pf.kalman_filter(lg, y)[2])
+    # Lorenz-96 d = 8 bootstrap filter: initial population and one step (fp64 RK4 flow, resampling every step)
+    l96 = models.Lorenz96SSM(dim=8)
+    _, yl = l96.simulate(2, np.random.default_rng(4), spinup=100)
+    fl = pf.BootstrapPF(l96, 96, 13, ess_threshold=2.0, resampling="systematic")
+    s0 = fl.init(yl[0])
+    s1 = fl.step(s0, yl[1])
+    g["l96_y"] = yl
+    g["l96_x0"], g["l96_lw0"] = s0["x"], s0["lw"]
+    g["l96_anc"], g["l96_x1"], g["l96_lw1"] = s1["ancestors"].astype(np.int32), s1["x"], s1["lw"]
+    g["l96_log_z"] = np.array([s0["log_z"], s1["log_z"]])
     return g
 
 
 if __name__ == "__main__":
     g = build()
-    np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "oracle_v1.npz"), **g)
+    np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "oracle_v2.npz"), **g)
     print({k: (v.shape, str(v.dtype)) for k, v in g.items()})

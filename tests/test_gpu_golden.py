@@ -1,4 +1,4 @@
-"""CUDA path against the committed golden vectors (tests/golden/oracle_v1.npz) -- no import of `oracle/` here.
+"""CUDA path against the committed golden vectors (tests/golden/oracle_v2.npz) -- no import of `oracle/` here.
 Tolerances as in DESIGN.md section 2: bit-exact for integer / CDF work, fp32 transcendental tolerances otherwise."""
 import os
 
@@ -7,7 +7,7 @@ import numpy.testing as npt
 import pytest
 
 pytestmark = pytest.mark.gpu
-G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_v1.npz"))
+G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_v2.npz"))
 
 
 @pytest.fixture(scope="module")
@@ -96,3 +96,35 @@ def test_golden_particle_filter_c1(E):
     npt.assert_allclose(hist["log_z"][:3], G["pf_log_z"][:3], atol=2e-4)      # identical streams before ancestor flips
     assert abs(hist["log_z"][-1] - G["pf_log_z"][-1]) < 0.15
     assert abs(hist["log_z"][-1] - float(G["kalman_loglik"])) < 0.5
+
+
+def test_golden_exact_systematic_ancestors(E):
+    """fused resampler (linear mode, caller's u0 bits) against the stored exact-rational ancestors"""
+    import torch
+    e, m, l = E
+    L = l.get()
+    w = _t(G["cdf_w"])
+    n = w.numel()
+    ws = torch.zeros((int(L.dll.mb_rs_workspace_bytes(n)) + 7) // 8, dtype=torch.int64, device="cuda")
+    for k0, ref in zip(G["anc_exact_k0"], G["anc_systematic_exact"]):
+        anc = torch.empty(n, dtype=torch.int32, device="cuda")
+        L.call("mb_rs_tile_sums", L.ctx(), l.ptr(ws), l.ptr(w), n, n, 0, None, 1, l.stream())
+        L.call("mb_rs_ancestors", L.ctx(), l.ptr(ws), l.ptr(w), n, n, 0, None, 1, int(k0), None, None, l.ptr(anc), l.stream())
+        npt.assert_array_equal(anc.cpu().numpy(), ref)
+
+
+def test_golden_lorenz96_step(E):
+    import torch
+    e, m, l = E
+    s = m.make_lorenz96(dim=8)
+    y = torch.as_tensor(G["l96_y"].astype(np.float32), device="cuda")
+    eng = e.PFEngine(s, 96, 13, ess_threshold=2.0, resampling=l.RESAMPLE_SYSTEMATIC)
+    eng.init(y[0])
+    npt.assert_allclose(eng.values().cpu().numpy(), G["l96_x0"], atol=2e-5)
+    npt.assert_allclose(eng.lw.cpu().numpy(), G["l96_lw0"], rtol=2e-5, atol=1e-3)
+    eng.step(y[1])
+    same = eng.anc.cpu().numpy() == G["l96_anc"]
+    assert same.mean() > 0.97
+    npt.assert_allclose(eng.values().cpu().numpy()[same], G["l96_x1"][same], atol=6e-5, rtol=1e-5)
+    npt.assert_allclose(eng.lw.cpu().numpy()[same], G["l96_lw1"][same], rtol=3e-5, atol=2e-3)
+    npt.assert_allclose(eng.ctl.read()["log_z"], G["l96_log_z"][1], atol=5e-3)
