@@ -252,6 +252,12 @@ int mb_gather_tiled(mb_ctx* ctx, const int32_t* anc, int64_t n_out, int d, const
 /* weighted moments of a tiled population (per-step diagnostics instead of the stacked history, filtering.py:317-322) */
 int mb_weighted_moments_tiled(mb_ctx* ctx, const float* x_tiled, int64_t n, int d, const float* lw,
                               const mb_control* ctl, double* mean, double* var, mb_stream_t stream);
+/* the same sums left un-normalised, for one shard of a sharded population (ctl->wmax is the global maximum):
+ * sums[0] = sum e_i, sums[1+k] = sum e_i (x_ik - shift_k), sums[1+d+k] = sum e_i (x_ik - shift_k)^2, e_i = exp(lw_i - wmax);
+ * the caller adds the ranks' records and normalises (filtering.py:317-322 diagnostics over all GPUs). */
+int mb_weighted_moment_sums_tiled(mb_ctx* ctx, const float* x_tiled, int64_t n, int d, const float* lw,
+                                  const mb_control* ctl, const float* shift /*[d]*/, double* sums /*[1+2d]*/,
+                                  mb_stream_t stream);
 
 /* ---- K4+K5 fused: systematic resampling without a materialised CDF (transport/smc.py:61-71,
  *      ssm/filtering.py:196-199).  Integer weights e_i = rint(w_i 2^K) (w_i = exp(lw_i - ctl->wmax) in log mode, the

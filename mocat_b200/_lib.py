@@ -131,6 +131,7 @@ SIGNATURES = {
     "mb_pf_l96_step": (C.c_int, [c_vp, C.POINTER(SSM), c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_u64, c_u32, c_i64,
                                  c_d, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "mb_weighted_moments_tiled": (C.c_int, [c_vp, c_vp, c_i64, C.c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "mb_weighted_moment_sums_tiled": (C.c_int, [c_vp, c_vp, c_i64, C.c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "mb_gather_tiled": (C.c_int, [c_vp, c_vp, c_i64, C.c_int, c_vp, c_i64, c_vp, C.c_int, c_vp]),
     "mb_rs_workspace_bytes": (C.c_size_t, [c_i64]),
     "mb_rs_tile_sums": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, C.c_int, c_vp, C.c_int, c_vp]),

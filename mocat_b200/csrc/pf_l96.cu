@@ -38,14 +38,17 @@ __device__ __forceinline__ f2 f2_mul(f2 a, f2 b) { f2 d; asm("mul.rn.f32x2 %0, %
 
 // Box-Muller pair scaled by `sd` (rng.cuh box_muller folded with the scaling and trimmed for issue slots):
 //   (zc, zs) = sd * sqrt(-2 ln u1) * (cos, sin)(2 pi u2),  u1 = u_open(xa) = (float(xa) + .5) 2^-32,  u2 = u24(xb).
-// lg2(u1) = lg2(float(xa) + .5) - 32 exactly, so the 2^-32 scaling and sd^2 fold into one FFMA under the square root;
-// the angle is evaluated on phi = 2 pi u2 - pi (cos(2 pi u2) = -cos(phi)), the sign is taken by the consumer's FMA.
+// u1 comes out of ONE FFMA (float(xa) 2^-32 + 2^-33 rounds exactly like u_open: scaling by a power of two commutes
+// with rounding) and lg2 is taken on u1 in (0, 1], where lg2.approx has an ABSOLUTE error of 2^-22 near 1 -- taking it
+// on float(xa) + .5 (result ~ 32, relative error 2^-22) loses the small radii: 7e-5 absolute on the normals.
+// sd^2 and -2 ln 2 fold into the multiplier under the square root; the angle is evaluated on phi = 2 pi u2 - pi
+// (cos(2 pi u2) = -cos(phi)), the sign is taken by the consumer's FMA.
 // returns rq = sd * sqrt(-2 ln u1) and (c, s) = (cos, sin)(phi):  zc = -rq c,  zs = -rq s.
-__device__ __forceinline__ void box_muller_scaled(uint32_t xa, uint32_t xb, float k1, float k0, float& rq, float& c, float& s) {
-    const float v = __fadd_rn(__uint2float_rn(xa), 0.5f);
+__device__ __forceinline__ void box_muller_scaled(uint32_t xa, uint32_t xb, float k1, float& rq, float& c, float& s) {
+    const float u1 = fmaf(__uint2float_rn(xa), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
     float l2;
-    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(v));
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rq) : "f"(fmaf(l2, k1, k0)));      // k1 = -2 ln2 sd^2, k0 = 64 ln2 sd^2
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(u1));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rq) : "f"(l2 * k1));                 // k1 = -2 ln2 sd^2
     const float phi = fmaf((float)(xb >> 8), 3.7450703e-7f, -3.141592653589793f);  // 2 pi 2^-24
     __sincosf(phi, &s, &c);
 }
@@ -93,7 +96,7 @@ __device__ __forceinline__ void l96_rk4(f2 (&x)[CPL], const L96Consts& c, int pr
 }
 
 struct L96Args {
-    float forcing, h, ir, lik_const, zmean, bm_k1, bm_k0;   // zmean: initial mean; bm_k*: folded Box-Muller scale
+    float forcing, h, ir, lik_const, zmean, bm_k1;   // zmean: initial mean; bm_k*: folded Box-Muller scale
     int substeps;
     const float* x_in; float* x_out; int64_t n;
     const int32_t* anc; const float* y; float* lw;
@@ -170,8 +173,8 @@ __global__ void __launch_bounds__(L96_THREADS, INIT ? 2 : OCC) pf_l96_kernel(L96
         for (int r = 0; r < CPL; r += 2) {
             const Philox4 w = philox_raw<ROUNDS>(seed, pair, a.tail.t, INIT ? MB_P_INIT : MB_P_MOVE, (uint32_t)((CPL * p + r) >> 1));
             float rq0, c0, s0, rq1, c1, s1;
-            box_muller_scaled(w.x, w.y, a.bm_k1, a.bm_k0, rq0, c0, s0);
-            box_muller_scaled(w.z, w.w, a.bm_k1, a.bm_k0, rq1, c1, s1);
+            box_muller_scaled(w.x, w.y, a.bm_k1, rq0, c0, s0);
+            box_muller_scaled(w.z, w.w, a.bm_k1, rq1, c1, s1);
             float xl, xh;
             f2_unpack(INIT ? zmean : x[r], xl, xh);
             x[r] = f2_pack(fmaf(-rq0, c0, xl), fmaf(-rq0, s0, xh));            // cos branch -> even, sin branch -> odd particle
@@ -220,7 +223,6 @@ static int l96_dispatch(mb_ctx* ctx, const mb_ssm* ssm, L96Args& a, bool init, c
     a.lik_const = ssm->lik_const; a.zmean = ssm->init_mean; a.substeps = ssm->substeps;
     const double sd = init ? (double)ssm->init_std : (double)ssm->q_std;       // z * sd = sqrt(-2 ln u1 sd^2) * (cos, sin)
     a.bm_k1 = (float)(-2.0 * 0.6931471805599453 * sd * sd);
-    a.bm_k0 = (float)(64.0 * 0.6931471805599453 * sd * sd);
     a.tail.partials = ctx->partials;
     a.tail.counter = ctx->counters + MB_CNT_MOVE;
     const int64_t nchunks = (a.n + 15) >> 4;
@@ -293,13 +295,14 @@ extern "C" int mb_pf_l96_step(mb_ctx* ctx, const mb_ssm* ssm, const float* x_in,
 #define TM_THREADS 256
 __global__ void __launch_bounds__(TM_THREADS)
 tiled_moments_kernel(const float* __restrict__ x, int64_t n, int d, const float* __restrict__ lw, const mb_control* ctl,
-                     double* partials /*[gridDim.x][1 + 2 d]*/) {
+                     const float* __restrict__ shift, double* partials /*[gridDim.x][1 + 2 d]*/) {
     extern __shared__ double sm[];                   // [warps][1 + 2 d]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const float wmax = (float)ctl->wmax;
     const int tile_f = d * 32;
     const int c0 = lane, c1 = lane + 32;
-    const float sh0 = (c0 < d) ? x[c0 * 32] : 0.f, sh1 = (c1 < d) ? x[c1 * 32] : 0.f;   // shifts: particle 0
+    // shifts (numerical conditioning of the second moment): the caller's, or particle 0 of this population
+    const float sh0 = (c0 < d) ? (shift ? shift[c0] : x[c0 * 32]) : 0.f, sh1 = (c1 < d) ? (shift ? shift[c1] : x[c1 * 32]) : 0.f;
     double s0 = 0.0, a0 = 0.0, b0 = 0.0, a1 = 0.0, b1 = 0.0;
     const int64_t ntiles = (n + 31) >> 5;
     for (int64_t tile = (int64_t)blockIdx.x * nw + warp; tile < ntiles; tile += (int64_t)gridDim.x * nw) {
@@ -343,6 +346,34 @@ __global__ void tiled_moments_finish_kernel(const float* __restrict__ x, int d, 
     if (var) var[col] = s2 / s0 - m * m;
 }
 
+// raw sums of one shard: sums[0] = sum e, sums[1 + k] = sum e (x_k - shift_k), sums[1 + d + k] = sum e (x_k - shift_k)^2
+// with e = exp(lw - ctl->wmax) (ctl->wmax is the GLOBAL maximum of a sharded population), blocks merged in fixed order
+__global__ void tiled_moment_sums_finish_kernel(int d, const double* partials, int nblocks, double* sums) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= 1 + 2 * d) return;
+    double acc = 0.0;
+    for (int b = 0; b < nblocks; ++b) acc += partials[(size_t)b * (1 + 2 * d) + k];
+    sums[k] = acc;
+}
+
+extern "C" int mb_weighted_moment_sums_tiled(mb_ctx* ctx, const float* x, int64_t n, int d, const float* lw,
+                                             const mb_control* ctl, const float* shift, double* sums, mb_stream_t stream) {
+    MB_REQUIRE(ctx && x && lw && ctl && shift && sums && n > 0 && d > 0 && d <= 64,
+               "mb_weighted_moment_sums_tiled: bad arguments (d <= 64, shift required)");
+    const int64_t ntiles = (n + 31) >> 5;
+    int64_t grid = (ntiles + (TM_THREADS / 32) - 1) / (TM_THREADS / 32);
+    if (grid > (int64_t)ctx->sms * 8) grid = (int64_t)ctx->sms * 8;
+    const size_t bytes = (size_t)grid * (1 + 2 * d) * sizeof(double);
+    if (mb_ensure_scratch(ctx, bytes) != MB_OK) return MB_ERR_CUDA;
+    cudaStream_t st = mb_s(stream);
+    tiled_moments_kernel<<<(unsigned)grid, TM_THREADS, (TM_THREADS / 32) * (1 + 2 * d) * sizeof(double), st>>>(
+        x, n, d, lw, ctl, shift, (double*)ctx->scratch);
+    MB_CHECK_LAUNCH();
+    tiled_moment_sums_finish_kernel<<<(1 + 2 * d + 63) / 64, 64, 0, st>>>(d, (const double*)ctx->scratch, (int)grid, sums);
+    MB_CHECK_LAUNCH();
+    return MB_OK;
+}
+
 extern "C" int mb_weighted_moments_tiled(mb_ctx* ctx, const float* x, int64_t n, int d, const float* lw,
                                          const mb_control* ctl, double* mean, double* var, mb_stream_t stream) {
     MB_REQUIRE(ctx && x && lw && ctl && mean && n > 0 && d > 0 && d <= 64, "mb_weighted_moments_tiled: bad arguments (d <= 64)");
@@ -353,7 +384,7 @@ extern "C" int mb_weighted_moments_tiled(mb_ctx* ctx, const float* x, int64_t n,
     if (mb_ensure_scratch(ctx, bytes) != MB_OK) return MB_ERR_CUDA;
     cudaStream_t st = mb_s(stream);
     tiled_moments_kernel<<<(unsigned)grid, TM_THREADS, (TM_THREADS / 32) * (1 + 2 * d) * sizeof(double), st>>>(
-        x, n, d, lw, ctl, (double*)ctx->scratch);
+        x, n, d, lw, ctl, nullptr, (double*)ctx->scratch);
     MB_CHECK_LAUNCH();
     tiled_moments_finish_kernel<<<(d + 63) / 64, 64, 0, st>>>(x, d, (const double*)ctx->scratch, (int)grid, mean, var);
     MB_CHECK_LAUNCH();
