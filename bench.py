@@ -1,13 +1,16 @@
 #!/usr/bin/env python
-"""bench.py -- particle-steps/s of the tempered-SMC population step (BASELINE.json configs[1]:
-adaptive likelihood tempering on Rastrigin d=5, n=1e6 particles per GPU, MALA moves).
+"""bench.py -- particle-steps/s of the bootstrap particle filter on Lorenz-96 (BASELINE.json configs[2], "C3"):
+d = 40, ONE population of n = 1e8 particles in total, systematic resampling every step, sharded over the GPUs of the
+node (strong scaling: the total is fixed, each of N ranks owns n/N particles).
 
-  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-  python bench.py --impl reference --gpus N --steps K ...  # CPU restatement of the reference (oracle/)
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (torchrun for N > 1)
+  python bench.py --impl reference --gpus N --steps K ...  # CPU restatement of the reference (oracle/), rank 0 only
 
-One "step" = one SMCSampler.update (transport/smc.py:73-99): resample-if-needed (fp64 CDF scan, ancestor
-search, gather fused into the move), MALA move with potential/gradient evaluation, adaptive temperature
-search (regula falsi on device), weight update, ESS/log-evidence.  Prints ONE JSON line (rank 0).
+One "step" = one body of the scan in run_particle_filter_for_marginals (ssm/filtering.py:280-311): systematic
+resampling (exact-integer, no CDF in memory: csrc/resample_fused.cu), ancestor gather fused into the propagate
+kernel, RK4 Lorenz-96 flow + process noise, log-weight increment, (max, sum, sumsq) -> ESS / log-evidence
+(csrc/pf_l96.cu).  Prints ONE JSON line (rank 0).  N = 1 also reports the other configurations as sub-records:
+"svgd" (C4, iterations/s -- the second half of BASELINE.json's metric), "c2" (tempered SMC) and "c5" (SMC-ABC step).
 """
 import argparse
 import json
@@ -22,27 +25,43 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 METRIC = "particle-steps/sec"
-D = 5
-ALGO_BYTES_MOVE = 64.0          # x(5)+w+l+U_prior read + write
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the two step kernels at n = 1e6, one `ncu --set full`
-# capture of this command (profiles/ncu_step_r1d.md); scaled linearly for other n.  The state is L2 resident, the
-# writes of both kernels stay in L2, so the traffic is BELOW the algorithmic bytes (no wasted re-reads).
-NCU_DRAM_BYTES_PER_PARTICLE = {"temper_adapt_kernel<resident>": 8.10, "smc_move_kernel<Rastrigin,5,MALA>": 24.27}
-WORKLOAD = "C2 tempered SMC, Rastrigin d=5 a=1, prior N(0,3^2 I), MALA eps=0.1 (1 leapfrog), adaptive " \
-           "tempering retain 0.9 / resample 0.5, multinomial resampling"
+UNIT = "particle-steps/s"
+D = 40
+N_TOTAL = 100_000_000
+ESS_THRESHOLD = 2.0             # ess < 2 n always holds: resample at every step
+CONTRACT_BYTES = 2 * 4 * D + 16  # x[a_i] read + x' write + w write/read + ancestor write/read = 336 B
+STEP_KERNEL_BYTES = 2 * 4 * D + 8  # pf_l96_kernel alone: x[a_i] read, x' write, ancestor read, w write = 328 B
+WORKLOAD = "C3 bootstrap particle filter, Lorenz-96 d=40 F=8, Q=R=P0=I, H=I, dt=0.05 (one RK4 step), systematic " \
+           "resampling every step, n=1e8 particles in total"
 
 
 def parse():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=200)
+    p.add_argument("--steps", type=int, default=100)
     p.add_argument("--warmup", type=int, default=5)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    p.add_argument("--n", type=int, default=1_000_000, help="particles per GPU")
+    p.add_argument("--n", type=int, default=N_TOTAL, help="TOTAL number of particles (all GPUs together)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--no-extras", action="store_true", help="skip the C4 / C2 / C5 sub-records")
     p.add_argument("--seed", type=int, default=0)
     return p.parse_args()
+
+
+def config_of(a):
+    """identical for both arms (the driver compares them)"""
+    return {"workload": WORKLOAD, "n_total": int(a.n), "dim": D, "resampling": "systematic, every step",
+            "observations": "fp64 RK4 simulation, seed 0, 1000-step spin-up"}
+
+
+def observations(T, seed=0):
+    """synthetic data of SURVEY 8d: a noisy trajectory on the attractor, observed through y = x + N(0, I)"""
+    import numpy as np
+    from mocat_b200 import ssm
+    sc = ssm.Lorenz96(dim=D)
+    sim = sc.simulate(0.05 * np.arange(T), seed)
+    return sc, sim.y.astype(np.float32), sim.t
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -65,19 +84,21 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        sm, mx, pw, reasons = [], [], [], set()
+        for ts, ln in self.lines:
+            if t0 is not None and not (t0 <= ts <= t1 + 0.15):
+                continue
             f = [s.strip() for s in ln.split(",")]
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
             except ValueError:
                 continue
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
@@ -85,46 +106,189 @@ class ClockSampler:
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
 def cpu_arm(n, steps, warmup, seed, workers=None):
-    """times oracle.parallel.ParallelTemperedSMC (NumPy restatement of transport/smc.py, all host cores)"""
+    """times oracle.parallel.ParallelBootstrapPF: the reference's filter body (ssm/filtering.py:280-311) restated in
+    NumPy fp32, propagate + weight mapped over all host cores, inverse-CDF systematic resampling in the parent"""
     from oracle import models as om, parallel
     workers = workers or os.cpu_count() or 1
-    s = parallel.ParallelTemperedSMC(om.IsoGaussianPrior(D, 0.0, 3.0), om.Rastrigin(D, 1.0), n, seed, move='mala',
-                                     stepsize=0.1, max_iter=10000, workers=workers)
-    st = s.startup()
-    for _ in range(warmup):
-        st = s.update(st) if not s.terminated(st) else s.startup()
+    _, y, _ = observations(warmup + steps + 1, 0)
+    pf = parallel.ParallelBootstrapPF(om.Lorenz96SSM(dim=D), n, seed, ess_threshold=ESS_THRESHOLD, workers=workers)
+    pf.init(y[0])
+    for t in range(1, warmup + 1):
+        pf.step(y[t])
     t0 = time.perf_counter()
-    done = 0
-    for _ in range(steps):
-        if s.terminated(st):
-            st = s.startup()
-        st = s.update(st)
-        done += 1
+    for t in range(warmup + 1, warmup + steps + 1):
+        pf.step(y[t])
     dt = time.perf_counter() - t0
-    s.close()
-    return n * done / dt, dt / done, workers
+    pf.close()
+    return n * steps / dt, dt / steps, workers
 
 
 def reference_main(a, rank, world):
     if rank != 0:
         return
-    n_sample = min(a.n, 1_000_000)
-    steps = max(1, min(a.steps, 8))
-    val, sec, workers = cpu_arm(n_sample, steps, min(a.warmup, 1), a.seed)
-    sample = f"n={n_sample} particles x {steps} population steps of the same workload, NumPy restatement of the " \
-             f"reference algorithm (mocat's JAX path cannot run: jax absent), {workers} worker processes"
-    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "particle-steps/s", "n_gpus": a.gpus,
-            "steps": steps, "warmup": min(a.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "n_per_step": n_sample, "dim": D},
-            "cpu_baseline": {"value": val, "unit": "particle-steps/s", "cores": workers, "kind": "port", "sample": sample},
-            "e2e": {"value": val, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    # bounded sample: the full --steps and --warmup are honoured, the population is cut so that one step is ~0.1 s
+    n_sample = min(a.n, 200_000)
+    val, sec, workers = cpu_arm(n_sample, a.steps, a.warmup, a.seed)
+    sample = f"n={n_sample} particles x {a.steps} filter steps (+{a.warmup} warm-up) of the same workload; NumPy fp32 " \
+             f"restatement of the reference's filter body over {workers} worker processes, inverse-CDF systematic " \
+             f"resampling (mocat's own JAX path cannot run here: jax is not installed; its n^2 Gumbel-max " \
+             f"random.categorical is infeasible beyond n~2e4)"
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_of(a),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ helpers
+def load_json(path):
+    try:
+        with open(path) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
+def ev():
+    import torch
+    return torch.cuda.Event(enable_timing=True)
+
+
+# ------------------------------------------------------------------------------------------------ extras (N = 1)
+def svgd_record(iters, peaks, ncu):
+    """C4: SVGD on 50-d Bayesian logistic regression, n = 32768, median heuristic re-adapted every iteration
+    (transport/svgd.py:122-146 with the adapt of tests/test_transport.py:76-89), through mocat_b200.run"""
+    import numpy as np
+    import torch
+    import mocat_b200 as mocat
+    from mocat_b200 import engine, kernels
+    n, d, N = 32768, 50, 1024
+    rng = np.random.default_rng(0)
+    A = rng.standard_normal((N, d)).astype(np.float32)
+    lab = (rng.random(N) < 1.0 / (1.0 + np.exp(-(A @ rng.standard_normal(d))))).astype(np.float32)
+    sc = mocat.scenarios.LogisticRegression(A, lab)
+
+    class SVGDMedian(mocat.SVGD):
+        def adapt(self, st, extra):
+            extra.parameters.kernel_params.bandwidth = kernels.median_bandwidth_update(st.value)
+            return st, extra
+
+    def run_once(key):
+        smp = SVGDMedian(max_iter=iters, stepsize=0.05, keep_history=False)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out = mocat.run(sc, smp, n=n, random_key=key)
+        torch.cuda.synchronize()
+        return time.perf_counter() - t0, out
+    run_once(1)
+    dt, out = run_once(2)
+
+    def timed(fn, reps=20):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = ev(), ev()
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    X = torch.as_tensor(np.ascontiguousarray(out.value[-1] if out.value.ndim == 3 else out.value, dtype=np.float32),
+                        device="cuda")
+    h = kernels.median_bandwidth_update(X)
+    _, G = sc._potential_grad_device(X, 1.0)
+    bw_ms = timed(lambda: kernels.median_bandwidth_update(X))
+    g_ms = timed(lambda: sc._potential_grad_device(X, 1.0))
+    phi_ms = timed(lambda: engine.svgd_phi(X, G, h))
+    flops = 2.0 * n * n * (3 * d + 1)
+    tf = flops / (phi_ms * 1e-3) / 1e12
+    burst = float(peaks.get("bf16_tflops", 1590.0))
+    k = ncu.get("svgd_phi_tc_kernel", {})
+    return {"workload": "C4 SVGD, Bayesian logistic regression d=50, 1024 synthetic data points, n=32768 particles, "
+                        "RBF kernel, median heuristic every iteration, adagrad; tcgen05 kernels (bf16 operands, fp32 "
+                        "accumulation in TMEM)",
+            "iters_per_s": iters / dt, "ms_per_iter": dt / iters * 1e3, "iters": iters,
+            "api": "mocat_b200.run(LogisticRegression, SVGD(max_iter, stepsize=0.05) + median adapt, n=32768) -> host cdict",
+            "split_ms": {"median_bandwidth": bw_ms, "logistic_potential_grad": g_ms, "phi": phi_ms},
+            "roofline": {"bound": "tensor", "kernel": "svgd_phi_tc_kernel", "achieved": tf, "peak": burst,
+                         "unit": "TFLOP/s", "frac": tf / burst, "algorithmic_flops_per_launch": flops,
+                         "ms_per_launch": phi_ms,
+                         "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst: the kernel is timed alone)"
+                         if "bf16_tflops" in peaks else "fallback 1590 TFLOP/s (B200_PROFILING.md)",
+                         "tensor_pipe_pct_ncu": k.get("tensor_pipe_pct"), "ncu_source": k.get("source")}}
+
+
+def c2_record(steps):
+    """C2: tempered SMC, Rastrigin d=5, n=1e6, MALA, adaptive tempering, multinomial resampling (one graph replay/step)"""
+    import torch
+    from mocat_b200 import _lib, engine, models
+    n = 1_000_000
+    tgt = models.make_target(_lib.LIK_RASTRIGIN, 5, prior_std=3.0, a=1.0)
+    eng = engine.SMCEngine(tgt, models.make_move(_lib.MOVE_MALA, 0.1), models.make_temper(max_iter=1 << 30), n, 0,
+                           resampling=_lib.RESAMPLE_MULTINOMIAL)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+    eng.startup()
+    eng.update()
+    tot, done = 0.0, 0
+    for i in range(steps + 10):
+        if eng.ctl.read()['done']:
+            eng.startup()
+            eng.update()
+        flush.zero_()
+        e0, e1 = ev(), ev()
+        e0.record()
+        eng.update()
+        e1.record()
+        torch.cuda.synchronize()
+        if i >= 10:
+            tot += e0.elapsed_time(e1)
+            done += 1
+    ms = tot / done
+    return {"workload": "C2 tempered SMC, Rastrigin d=5, n=1e6, MALA eps=0.1, adaptive tempering 0.9/0.5, multinomial "
+                        "resampling; one CUDA-graph replay per step, L2 flushed between steps",
+            "particle_steps_per_s": n / (ms * 1e-3), "ms_per_step": ms, "steps_timed": done}
+
+
+def c5_record(steps, peaks):
+    """C5: one SMC-ABC population step on the g-and-k model (m = 8 draws), n = 1e8 on one GPU"""
+    import numpy as np
+    import torch
+    from mocat_b200 import _lib, engine, models
+    n = 100_000_000
+    rng = np.random.default_rng(0)
+    z = rng.standard_normal(8)
+    A_, B_, g_, k_ = 3.0, 1.0, 2.0, 0.5
+    data = np.sort(A_ + B_ * (1 + 0.8 * np.tanh(g_ * z / 2)) * z * (1 + z * z) ** k_)
+    eng = engine.ABCEngine(models.make_gk(data), n, 0, max_iter=1 << 30, resampling=_lib.RESAMPLE_MULTINOMIAL)
+    eng.startup()
+    for _ in range(3):
+        eng.update()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(steps):
+        e0, e1 = ev(), ev()
+        e0.record()
+        eng.update()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ms = float(np.median(ts))
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    c = eng.ctl.read()
+    return {"workload": "C5 SMC-ABC, g-and-k (m=8 sorted draws), RW-ABC move, n=1e8 on one GPU, ESS-triggered "
+                        "multinomial resampling",
+            "particle_steps_per_s": n / (ms * 1e-3), "ms_per_step": ms, "steps_timed": steps,
+            "hbm_frac_of_60B_contract": 60.0 * n / (ms * 1e-3) / 1e9 / hbm, "iter": int(c['iter']),
+            "note": "the propagate kernel is simulator (ALU/MUFU) bound: 8 x (ndtri + exp + pow) per particle"}
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -136,6 +300,7 @@ def main():
     if a.impl == "reference":
         return reference_main(a, rank, world)
 
+    import numpy as np
     import torch
     import torch.distributed as dist
     import mocat_b200 as mocat
@@ -146,28 +311,28 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
-    n = a.n
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
+    if a.n % (32 * world):
+        raise SystemExit(f"--n must be a multiple of 32 x the number of GPUs ({32 * world})")
+    n_total, n_local = a.n, a.n // world
+    peaks = load_json(os.path.join(ROOT, "MEASURED_PEAKS.json"))
+    ncu = load_json(os.path.join(ROOT, "profiles", "ncu_r2.json"))
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
 
-    tgt = models.make_target(_lib.LIK_RASTRIGIN, D, prior_std=3.0, a=1.0)
+    T = a.warmup + a.steps + 24
+    scen, y_host, t_host = observations(T, 0)
+    yd = torch.as_tensor(y_host, device=dev)
+    ssm = models.make_lorenz96(dim=D)
     if world > 1:
-        # ONE population of world*n particles sharded over the GPUs (mocat_b200/parallel.py): LSE/ESS triples and
-        # weight totals exchanged through peer-mapped mailboxes, ancestors gathered over NVLink peer reads
+        # ONE population of n_total particles sharded over the GPUs (mocat_b200/parallel.py): integer weight totals and
+        # (max, sum, sumsq) triples exchanged through peer-mapped mailboxes inside the kernels, ancestors written to the
+        # owning rank over NVLink, ancestor state read from the owning rank by the fused gather
         from mocat_b200 import parallel
         sc = parallel.shard_context()
-        eng = parallel.ShardedSMCEngine(sc, tgt, models.make_move(_lib.MOVE_MALA, 0.1),
-                                        models.make_temper(max_iter=1 << 30), n, a.seed,
-                                        resampling=_lib.RESAMPLE_MULTINOMIAL)
+        pf = parallel.ShardedPFEngine(sc, ssm, n_local, a.seed, ess_threshold=ESS_THRESHOLD,
+                                      resampling=_lib.RESAMPLE_SYSTEMATIC)
     else:
-        eng = engine.SMCEngine(tgt, models.make_move(_lib.MOVE_MALA, 0.1), models.make_temper(max_iter=1 << 30), n,
-                               a.seed, resampling=_lib.RESAMPLE_MULTINOMIAL)
-    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
+        pf = engine.PFEngine(ssm, n_local, a.seed, ess_threshold=ESS_THRESHOLD, resampling=_lib.RESAMPLE_SYSTEMATIC)
 
     def sync():
         torch.cuda.synchronize()
@@ -175,152 +340,159 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    def ev():
-        return torch.cuda.Event(enable_timing=True)
-
-    def one_step(inner):
-        """one population step bracketed by events; inner=True records per-kernel-group events (plain
-        launches), inner=False replays the captured CUDA graph of the step (the production path)."""
-        if eng.ctl.read()['done']:
-            eng.startup()                                               # population reached beta = 1: start over (untimed)
-            eng.update()                                                # first update after a restart is never graph-replayed
-        flush.zero_()                                                   # L2 flush between timed iterations
-        if inner:
-            marks = [ev() for _ in range(4)]
-            eng.update(events=marks)
-            return marks
-        e0, e1 = ev(), ev()
-        e0.record()
-        eng.update()
-        e1.record()
-        return [e0, e1]
-
-    eng.startup()
-    eng.update()
+    pf.init(yd[0])
     sync()
     clocks = ClockSampler(local)
     clocks.start()
-    t_w = time.perf_counter()
-    nw = 0
-    while True:                                                         # >= 1 s of warm-up so clocks settle
-        for _ in range(max(a.warmup, 3) if nw == 0 else 100):
-            one_step(False)
-            nw += 1
-        # the step count must be IDENTICAL on every rank (each step is a cross-GPU exchange): decide collectively
-        el = torch.tensor([time.perf_counter() - t_w], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(el, op=dist.ReduceOp.MIN)
-        if float(el.item()) >= 1.0:
-            break
+    nw = max(a.warmup, 3)
+    for t in range(1, nw + 1):
+        pf.step(yd[t])
     sync()
-    all_marks = []
+    # ---- timed region: EXACTLY --steps filter steps, one event pair, barrier + synchronize on both sides
+    e0, e1 = ev(), ev()
     t_wall0 = time.perf_counter()
-    for _ in range(a.steps):
-        all_marks.append(one_step(False))
+    e0.record()
+    for t in range(nw + 1, nw + a.steps + 1):
+        pf.step(yd[t])
+    e1.record()
     sync()
-    t_wall = time.perf_counter() - t_wall0
-    # second region: same steps with plain launches and per-kernel-group events (roofline of the kernels)
-    inner_marks = [one_step(True) for _ in range(min(a.steps, 50))]
+    t_wall1 = time.perf_counter()
+    tot = e0.elapsed_time(e1)
+    # ---- second region: the same steps with events between the kernel groups (per-kernel roofline)
+    st = _lib.stream()
+    marks = []
+    for t in range(nw + a.steps + 1, nw + a.steps + 21):
+        m = [ev() for _ in range(3)]
+        pf.t += 1
+        m[0].record()
+        pf._resample_kernels(st)
+        m[1].record()
+        pf._step_kernel(yd[t], st)
+        m[2].record()
+        marks.append(m)
     sync()
-    clk = clocks.stop()
-    it_now = int(eng.ctl.read()['iter'])
-    hist = eng.ctl.read_hist(it_now + 1)
-    mean_search = float(hist['search_iters'][1:].mean()) if it_now >= 1 else 0.0
-    # device time: per-step event pairs (flush excluded), summed
-    tot = sum(m[0].elapsed_time(m[1]) for m in all_marks)              # ms
-    ni = len(inner_marks)
-    t_resample = sum(m[0].elapsed_time(m[1]) for m in inner_marks) / ni
-    t_move = sum(m[1].elapsed_time(m[2]) for m in inner_marks) / ni
-    t_temper = sum(m[2].elapsed_time(m[3]) for m in inner_marks) / ni
-    tt = torch.tensor([tot], dtype=torch.float64, device=dev)
+    clk = clocks.stop(t_wall0, t_wall1)
+    t_res = float(np.median([m[0].elapsed_time(m[1]) for m in marks]))
+    t_step = float(np.median([m[1].elapsed_time(m[2]) for m in marks]))
+    ctl = pf.ctl.read()
+    red = torch.tensor([tot, t_res, t_step], dtype=torch.float64, device=dev)
     if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    tot = float(tt.item())
+        dist.all_reduce(red, op=dist.ReduceOp.MAX)
+    tot, t_res, t_step = (float(v) for v in red.tolist())
     ms_per_step = tot / a.steps
-    value = world * n / (ms_per_step * 1e-3)
+    value = n_total / (ms_per_step * 1e-3)
+    state_bytes = int(sum(t.numel() * t.element_size() for t in (pf.xbuf[0], pf.xbuf[1], pf._lw_full, pf.anc)))
+    del pf
+    if world > 1:
+        dist.barrier()
+    torch.cuda.empty_cache()
 
-    # ---- end to end through the public API: host buffers in, host arrays out -------------------------
+    # ---- end to end through the public API: host observations in, host diagnostics out ---------------------------
     e2e = None
     if not a.no_e2e:
-        import numpy as np
-        x0 = torch.empty((n, D), dtype=torch.float32).pin_memory()
-        x0.copy_(torch.randn(n, D) * 3.0)
-        sc = mocat.scenarios.Rastrigin(dim=D, a=1.0, prior_std=3.0)
+        Te = a.steps + 1                                              # initial weighting + --steps propagation steps
+        ye, te = y_host[:Te], t_host[:Te]
 
-        def e2e_run(iters):
-            smp = mocat.MetropolisedSMCSampler(mocat.Underdamped(stepsize=0.1), max_iter=iters, keep_history=False,
-                                               check_every=16)
+        def e2e_run(key):
             t0 = time.perf_counter()
-            out = mocat.run(sc, smp, n * world, random_key=a.seed, initial_state=mocat.cdict(value=x0.numpy()))
+            out = mocat.ssm.run_particle_filter_for_marginals(scen, mocat.ssm.BootstrapFilter(), ye, te, key, n=n_total,
+                                                          ess_threshold=ESS_THRESHOLD, resampling='systematic')
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
-            d2h = sum(v.nbytes for v in out.__dict__.values() if isinstance(v, np.ndarray))
-            return dt, len(out.temperature) - 1, d2h
-        e2e_run(a.steps)                                             # warm-up: same configuration (engine pool, graphs)
+            d2h = sum(v.nbytes for k, v in vars(out).items() if isinstance(v, np.ndarray) and k not in ('y', 't'))
+            return dt, d2h, out
+        dt_first, _, _ = e2e_run(a.seed + 1)                          # first call: allocates the population (2 x 16 GB)
         sync()
-        dt, iters, d2h = e2e_run(a.steps)
-        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        dt, d2h, out = e2e_run(a.seed + 2)
+        red = torch.tensor([dt, dt_first], dtype=torch.float64, device=dev)
         if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt.item())
-        e2e = {"value": world * n * iters / dt, "unit": "particle-steps/s",
-               "h2d_bytes_per_step": n * D * 4 / max(iters, 1), "d2h_bytes_per_step": d2h / max(iters, 1),
-               "iters": iters, "wall_s": dt, "api": "mocat_b200.run(scenario, MetropolisedSMCSampler, n, key, "
-               "initial_state=cdict(value=<host ndarray>)) -> host cdict"}
+            dist.all_reduce(red, op=dist.ReduceOp.MAX)
+        dt, dt_first = (float(v) for v in red.tolist())
+        e2e = {"value": n_total * a.steps / dt, "unit": UNIT,
+               "h2d_bytes_per_step": int(ye.nbytes / Te), "d2h_bytes_per_step": int(d2h / Te),
+               "wall_s": dt, "first_call_wall_s": dt_first, "steps": a.steps,
+               "api": "mocat_b200.ssm.run_particle_filter_for_marginals(Lorenz96(40), BootstrapFilter(), y, t, key, n=1e8, "
+                      "ess_threshold=2.0, resampling='systematic') -> host cdict(ess, log_norm_constant, resampled, "
+                      "mean, var per step)",
+               "conditions": "y: pageable host ndarray (T x 40 fp32) copied in inside the timed call; the particles "
+                             "are drawn on the device (initiate_particles, as upstream); per-step weighted mean/"
+                             "variance computed on the device and read back once; the (T, n, d) history of the "
+                             "reference is NOT returned at this size (T x 16 GB); reported call = second call of the "
+                             "configuration (pooled engine: HBM already allocated), first call in first_call_wall_s",
+               "final_ess": float(out.ess[-1]), "final_log_norm_constant": float(out.log_norm_constant[-1])}
+        del out
+    if world > 1:
+        from mocat_b200 import parallel
+        parallel.release_pools()
+    else:
+        engine.PFEngine._POOL.clear()
+    torch.cuda.empty_cache()
 
     if rank != 0:
         if world > 1:
+            dist.barrier()
             dist.destroy_process_group()
         return
 
-    cpu = None
-    if not a.no_cpu_baseline and world >= 1:
-        n_s, k_s = 1_000_000, 5
-        v, sec, workers = cpu_arm(n_s, k_s, 1, a.seed)
-        cpu = {"value": v, "unit": "particle-steps/s", "cores": workers, "kind": "port",
-               "sample": f"n={n_s} x {k_s} steps of the same workload; NumPy restatement of the reference "
-                         f"(oracle/), {workers} processes; mocat's own JAX path cannot run here (jax absent)"}
+    extras = {}
+    if world == 1 and not a.no_extras:
+        for name, fn in (("svgd", lambda: svgd_record(200, peaks, ncu)), ("c2", lambda: c2_record(100)),
+                         ("c5", lambda: c5_record(10, peaks))):
+            try:
+                extras[name] = fn()
+            except Exception as exc:                                  # a sub-record must not take the headline down
+                extras[name] = {"error": f"{type(exc).__name__}: {exc}"}
+            torch.cuda.empty_cache()
 
-    # roofline of the dominant kernel (by measured time) and of the move kernel.  Algorithmic bytes
-    # (SURVEY 8d, C2): move 64 B/particle; tempering search 8 B x evaluations (w, l reads) + 12 B for the
-    # weight update (read w, l; write w).
-    evals = mean_search + 1.0
-    bytes_temper = (8.0 * evals + 12.0) * n
-    ach_move = ALGO_BYTES_MOVE * n / (t_move * 1e-3) / 1e9
-    ach_temper = bytes_temper / (t_temper * 1e-3) / 1e9
-    kernels = {
-        "scan_cdf+ancestors (device-predicated)": {"ms": t_resample},
-        "smc_move_kernel<Rastrigin,5,MALA>": {"ms": t_move, "algorithmic_bytes": ALGO_BYTES_MOVE * n,
-                                              "achieved_gbs": ach_move, "frac": ach_move / hbm_peak},
-        "temper_adapt_kernel<resident>": {"ms": t_temper, "algorithmic_bytes": bytes_temper,
-                                          "achieved_gbs": ach_temper, "frac": ach_temper / hbm_peak,
-                                          "mean_evaluations": evals},
-    }
-    dom = "temper_adapt_kernel<resident>" if t_temper >= t_move else "smc_move_kernel<Rastrigin,5,MALA>"
+    cpu = None
+    if not a.no_cpu_baseline and world == 1:
+        n_s, k_s = 200_000, 20
+        v, sec, workers = cpu_arm(n_s, k_s, 2, a.seed)
+        cpu = {"value": v, "unit": UNIT, "cores": workers, "kind": "port",
+               "sample": f"n={n_s} particles x {k_s} filter steps of the same workload; NumPy fp32 restatement of the "
+                         f"reference's filter body (oracle/parallel.py) over {workers} processes; mocat's own JAX "
+                         f"path cannot run here (jax absent)"}
+
+    ach_step = STEP_KERNEL_BYTES * n_local / (t_step * 1e-3) / 1e9
+    ach_contract = CONTRACT_BYTES * n_local / (ms_per_step * 1e-3) / 1e9
+    k_ncu = ncu.get("pf_l96_kernel", {})
+    traffic = k_ncu.get("dram_bytes_per_particle")
+    launches_per_step = 4 if world == 1 else 6
     line = {
-        "metric": METRIC, "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": a.steps,
-        "warmup": nw, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "n_per_gpu": n, "dim": D, "parallelism": f"one population of {world * n} particles sharded over {world} GPUs "
-                   "(peer-memory mailbox exchange + NVLink ancestor gather)" if world > 1 else "single GPU", "l2": "flushed between timed steps (512 MiB memset)",
-                   "launch": "one CUDA-graph replay per step",
-                   "state_bytes_resident": int(sum(t.numel() * t.element_size() for t in
-                                                   (eng.xbuf[0], eng.xbuf[1], eng.lw, eng.lik, eng.up, eng.alpha,
-                                                    eng.cdf, eng.anc)))},
-        "roofline": {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"],
-                     "peak": hbm_peak, "unit": "GB/s", "frac": kernels[dom]["frac"],
-                     "traffic": NCU_DRAM_BYTES_PER_PARTICLE[dom] * n,
-                     "peak_source": peak_src, "algorithmic_bytes_per_launch": kernels[dom]["algorithmic_bytes"],
-                     "ms_per_launch": kernels[dom]["ms"],
-                     "note": "n=1e6: the whole state (68 MB) is smaller than L2 and every kernel is "
-                             "latency/issue bound, not HBM bound; see DESIGN.md for the n=1e8 figures"},
-        "kernels": kernels,
-        "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": (6 if world == 1 else 8) * a.steps,   # kernels per step: scan, strata hist, offsets scan, ancestors, move, temper (+ exchange, histogram sum when sharded)
-        "clocks": clk,
-        "wall_s_timed_region": t_wall,
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": nw,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": config_of(a),
+        "details": {"n_per_gpu": n_local,
+                    "parallelism": f"one population of {n_total} particles sharded over {world} GPUs (peer-memory "
+                                   "mailbox exchange of the weight totals / LSE triples, ancestors stored to and "
+                                   "ancestor state read from the owning GPU over NVLink; no NCCL on the data path)"
+                    if world > 1 else "single GPU",
+                    "l2": f"inputs larger than L2: {state_bytes / 1e9:.1f} GB of state per GPU streams through every step",
+                    "launch": f"{launches_per_step} kernel launches per step (tile sums, ancestors, heavy-tile pass, "
+                              "propagate" + (", 2 mailbox exchanges)" if world > 1 else ")"),
+                    "layout": "tiled AoSoA: 32-particle tiles of 40 x 32 fp32 (csrc/pf_l96.cu)",
+                    "final_ess": float(ctl['ess']), "final_log_z": float(ctl['log_z'])},
+        "roofline": {"bound": "hbm", "kernel": "pf_l96_kernel<40>", "achieved": ach_step, "peak": hbm_peak,
+                     "unit": "GB/s", "frac": ach_step / hbm_peak,
+                     "traffic": None if traffic is None else traffic * n_local,
+                     "traffic_source": k_ncu.get("source"), "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": STEP_KERNEL_BYTES * n_local,
+                     "algorithmic_bytes_per_particle": STEP_KERNEL_BYTES, "ms_per_launch": t_step,
+                     "whole_step": {"contract_bytes_per_particle": CONTRACT_BYTES, "achieved": ach_contract,
+                                    "frac": ach_contract / hbm_peak, "ms": ms_per_step},
+                     "note": "ancestor gather + RK4 + Philox noise + weights in one kernel; issue bound (ncu: "
+                             "profiles/), the population collapses at d=40 so the gathered reads mostly hit L2"},
+        "kernels": {"resample (rf_tile_sums + rf_ancestors + rf_heavy)": {"ms": t_res,
+                                                                        "algorithmic_bytes_per_particle": 12},
+                    "pf_l96_kernel<40>": {"ms": t_step, "algorithmic_bytes_per_particle": STEP_KERNEL_BYTES,
+                                          "achieved_gbs": ach_step, "frac": ach_step / hbm_peak}},
+        "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * a.steps, "clocks": clk,
+        "wall_s_timed_region": t_wall1 - t_wall0,
     }
+    line.update(extras)
     print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -383,7 +383,29 @@ class PFEngine(_Resampler):
         return (self.ld // 32, self.d, 32) if self.tiled else (self.d, self.ld)
 
     def _alloc_x(self, dev):
-        return torch.zeros(self._x_shape(), dtype=torch.float32, device=dev)
+        # tiled layout: the init kernel writes every chunk the step kernels ever touch, no memset of 16 GB needed
+        return (torch.empty if self.tiled else torch.zeros)(self._x_shape(), dtype=torch.float32, device=dev)
+
+    # -- engine pool: repeated filters of one configuration reuse the HBM buffers (2 x 16 GB at config C3) -------
+    _POOL = {}
+    generation = 0
+
+    @classmethod
+    def acquire(cls, ssm, n, seed, ess_threshold=0.5, resampling=_lib.RESAMPLE_MULTINOMIAL):
+        """pooled engine; `generation` is bumped on every hand-out so that a result cdict of an EARLIER run can tell
+        that its engine has been re-used (ssm._engine_of raises instead of continuing from foreign state)"""
+        key = (int(ssm.kind), int(ssm.dim), int(n), int(resampling), torch.cuda.current_device())
+        if os.environ.get("MOCAT_B200_ENGINE_POOL", "1") == "0":
+            eng = cls(ssm, n, seed, ess_threshold=ess_threshold, resampling=resampling)
+        else:
+            eng = cls._POOL.get(key)
+            if eng is None:
+                cls._POOL.clear()                                  # one pooled filter: populations are large
+                eng = cls(ssm, n, seed, ess_threshold=ess_threshold, resampling=resampling)
+                cls._POOL[key] = eng
+        eng.ssm, eng.seed, eng.ess_threshold = ssm, int(seed), float(ess_threshold)
+        eng.generation += 1
+        return eng
 
     @property
     def x(self):
@@ -441,6 +463,16 @@ class PFEngine(_Resampler):
             self.L.call("mb_gather_state", self.ctx, ptr(self.anc), self.n, self.d, ptr(src), self.ld, ptr(dst), self.ld,
                         stream())
         self.cur ^= 1
+
+    def moment_sums(self, shift, out=None):
+        """un-normalised weighted sums of THIS shard, (1 + 2d,) float64: sum e, sum e (x - shift), sum e (x - shift)^2 with
+        e = exp(lw - global max); the ranks' records add up to the moments of the whole population"""
+        if not self.tiled:
+            raise _lib.MocatB200Error("moment_sums: tiled (Lorenz-96) populations only")
+        sums = out if out is not None else torch.empty(1 + 2 * self.d, dtype=torch.float64, device=self.x.device)
+        self.L.call("mb_weighted_moment_sums_tiled", self.ctx, ptr(self.x), self.n, self.d, ptr(self.lw), ptr(self.ctl.t),
+                    ptr(shift), ptr(sums), stream())
+        return sums
 
     def moments(self):
         """weighted mean / variance of every coordinate under the current weights (device float64 (d,) tensors)"""

@@ -101,6 +101,27 @@ class ShardContext:
         self._allocs.append((p, peers))
         return t, peers
 
+    def free_shared(self, tensors):
+        """collective release of alloc_shared() buffers (every rank passes its tensors in the same order): the peer
+        mappings are closed first, then -- after a barrier, so that no rank still maps it -- the local allocation"""
+        import torch
+        import torch.distributed as dist
+        torch.cuda.synchronize()
+        mine = []
+        for t in tensors:
+            for k, (p, peers) in enumerate(self._allocs):
+                if p.value == t.data_ptr():
+                    mine.append(self._allocs.pop(k))
+                    break
+        for p, peers in mine:
+            for r, q in enumerate(peers):
+                if r != self.rank:
+                    self.L.call("mb_ipc_close", self.ctx, C.c_void_p(q))
+        if dist.is_initialized() and self.world > 1:
+            dist.barrier(self.group)
+        for p, peers in mine:
+            self.L.call("mb_free", self.ctx, p)
+
     def allgather(self, src, nd, dst):
         self.L.call("mb_comm_allgather", self.comm, _lib.ptr(src), int(nd), _lib.ptr(dst), None, _lib.stream())
 
@@ -121,13 +142,16 @@ def _sharded_alloc(eng, sc):
     resampler writes an output's ancestor into the owning rank's array) and, for multinomial resampling, the
     rank-relative CDF and the strata histogram."""
     import torch
-    xs = [sc.alloc_shared(tuple(eng.xbuf[0].shape), torch.float32) for _ in range(2)]
+    shape = tuple(eng._x_shape()) if hasattr(eng, "_x_shape") else tuple(eng.xbuf[0].shape)
+    xs = [sc.alloc_shared(shape, torch.float32) for _ in range(2)]
     eng.xbuf = [xs[0][0], xs[1][0]]
     eng.anc, anc_peers = sc.alloc_shared((eng.n,), torch.int32)
+    eng._shared = [eng.xbuf[0], eng.xbuf[1], eng.anc]
     cdf_peers = None
     if eng.resampling == _lib.RESAMPLE_MULTINOMIAL:
         eng.cdf, cdf_peers = sc.alloc_shared((eng.n,), torch.float64)
         eng.hist_local, hist_peers = sc.alloc_shared((eng.B,), torch.int32)
+        eng._shared += [eng.cdf, eng.hist_local]
         eng.hist_peers = (C.c_void_p * sc.world)(*hist_peers)
     eng.totals = torch.zeros(sc.world, dtype=torch.float64, device=sc.device)      # fp64 totals / uint64 bit patterns
     eng._barrier_out = torch.zeros(sc.world, dtype=torch.float64, device=sc.device)
@@ -171,6 +195,13 @@ def ShardedSMCEngine(sc, target, move, temper, n_local, seed, resampling=_lib.RE
             self.sc = sc
             self.comm = sc.comm
             _sharded_alloc(self, sc)
+
+        def close(self):
+            """collective: release the IPC-shared buffers"""
+            shared, self._shared = self._shared, []
+            self._graphs = [None, None]
+            self.xbuf, self.anc, self.cdf = [None, None], None, None
+            sc.free_shared(shared)
 
         def _shard_ref(self):
             return C.byref(self.shards[self.cur])
@@ -223,11 +254,40 @@ def acquire_sharded_smc(target, move, temper, n_local, seed, resampling, schedul
     eng = _SMC_POOL.get(key)
     if eng is None:
         if len(_SMC_POOL) >= 2:
-            _SMC_POOL.pop(next(iter(_SMC_POOL)))
+            _SMC_POOL.pop(next(iter(_SMC_POOL))).close()           # collective: frees its IPC-shared HBM
         eng = ShardedSMCEngine(sc, target, move, temper, n_local, seed, resampling=resampling, schedule=schedule)
         _SMC_POOL[key] = eng
     eng.seed = int(seed)
     return eng
+
+
+_PF_POOL = {}
+
+
+def acquire_sharded_pf(ssm, n_local, seed, ess_threshold, resampling):
+    """pooled ShardedPFEngine (one entry: config C3 holds 2 x 16 GB / world per rank).  Collective; every rank takes the
+    same decisions.  `generation` is bumped per hand-out (see engine.PFEngine.acquire)."""
+    sc = shard_context()
+    key = (int(ssm.kind), int(ssm.dim), int(n_local), int(resampling))
+    eng = _PF_POOL.get(key)
+    if eng is None:
+        for old in list(_PF_POOL.values()):
+            old.close()
+        _PF_POOL.clear()
+        eng = ShardedPFEngine(sc, ssm, n_local, seed, ess_threshold=ess_threshold, resampling=resampling)
+        _PF_POOL[key] = eng
+    eng.ssm, eng.seed, eng.ess_threshold = ssm, int(seed), float(ess_threshold)
+    eng.generation += 1
+    return eng
+
+
+def release_pools():
+    """collective: close every pooled sharded engine (frees their IPC-shared HBM)"""
+    for pool in (_PF_POOL, _SMC_POOL):
+        for eng in list(pool.values()):
+            if hasattr(eng, "close"):
+                eng.close()
+        pool.clear()
 
 
 def ShardedPFEngine(sc, ssm, n_local, seed, ess_threshold=0.5, resampling=_lib.RESAMPLE_MULTINOMIAL):
@@ -243,8 +303,17 @@ def ShardedPFEngine(sc, ssm, n_local, seed, ess_threshold=0.5, resampling=_lib.R
             self.sc = sc
             _sharded_alloc(self, sc)
 
+        def _alloc_x(self, dev):
+            return None                                     # the IPC-shared buffers of _sharded_alloc replace them
+
         def _comm(self):
             return sc.comm
+
+        def close(self):
+            """collective: release the IPC-shared buffers (they are not owned by torch)"""
+            shared, self._shared = self._shared, []
+            self.xbuf, self.anc = [None, None], None
+            sc.free_shared(shared)
 
         def _shard_ref(self):
             return C.byref(self.shards[self.cur])

@@ -160,7 +160,33 @@ def _engine_of(particles):
     if eng is None:
         raise _lib.MocatB200Error("this particle cdict has no live device engine (it was loaded from disk or created "
                                   "elsewhere); start again with initiate_particles / run_particle_filter_for_marginals")
+    if getattr(particles, 'engine_generation', eng.generation) != eng.generation:
+        raise _lib.MocatB200Error("the device engine of this particle cdict has since been re-used by another filter run "
+                                  "of the same configuration (engines are pooled); continue from the latest result or "
+                                  "set MOCAT_B200_ENGINE_POOL=0")
     return eng
+
+
+def _world():
+    """(rank, world) of the torch.distributed job this process belongs to ((0, 1) outside torchrun)"""
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(), dist.get_world_size()
+    except Exception:
+        pass
+    return 0, 1
+
+
+def _make_engine(ssm, n, seed, ess_threshold, resampling):
+    """single-GPU engine, or -- under torchrun, where `n` is the GLOBAL population size -- this rank's shard of one
+    population spread over the GPUs of the node (mocat_b200/parallel.py)"""
+    rank, world = _world()
+    if world > 1:
+        from . import parallel
+        _, n_local = parallel.shard_range(n, rank, world)
+        return parallel.acquire_sharded_pf(ssm, n_local, seed, ess_threshold, resampling)
+    return engine.PFEngine.acquire(ssm, n, seed, ess_threshold=ess_threshold, resampling=resampling)
 
 
 def _host_value(eng):
@@ -181,14 +207,15 @@ def initiate_particles(ssm_scenario, particle_filter, n, random_key, y=None, t=N
     if y is None:
         raise _lib.MocatB200Error("initiate_particles needs the first observation y")
     y = np.atleast_1d(np.asarray(y, np.float32))
-    eng = engine.PFEngine(ssm_scenario._ssm(), n, key_to_seed(random_key), ess_threshold=ess_threshold,
-                          resampling=_RESAMPLING[resampling])
+    eng = engine.PFEngine.acquire(ssm_scenario._ssm(), n, key_to_seed(random_key), ess_threshold=ess_threshold,
+                                  resampling=_RESAMPLING[resampling])
     eng.init(torch.as_tensor(y, device="cuda"))
     c = eng.ctl.read()
     mean, var = _moments(eng)
     out = cdict(t=np.atleast_1d(t) if t is not None else np.zeros(1), y=y[None],
                 ess=np.atleast_1d(c['ess']), log_norm_constant=np.atleast_1d(c['log_z']),
-                mean=mean.cpu().numpy()[None], var=var.cpu().numpy()[None], engine=eng)
+                mean=mean.cpu().numpy()[None], var=var.cpu().numpy()[None], engine=eng,
+                engine_generation=eng.generation)
     out.value, out.log_weight = _host_value(eng)
     return out
 
@@ -282,8 +309,7 @@ def run_particle_filter_for_marginals(ssm_scenario, particle_filter, y, t, rando
     if len(t_all) > 2 and not np.allclose(np.diff(t_all), dt):
         raise _lib.MocatB200Error("run_particle_filter_for_marginals needs equally spaced t (time-homogeneous model)")
     if initial_sample is None:
-        eng = engine.PFEngine(ssm_scenario._ssm(dt), n, key_to_seed(random_key), ess_threshold=ess_threshold,
-                              resampling=_RESAMPLING[resampling])
+        eng = _make_engine(ssm_scenario._ssm(dt), n, key_to_seed(random_key), ess_threshold, _RESAMPLING[resampling])
     else:
         eng = _engine_of(initial_sample)
         eng.ess_threshold = float(ess_threshold)
@@ -298,13 +324,19 @@ def run_particle_filter_for_marginals(ssm_scenario, particle_filter, y, t, rando
         keep_history = T * n * (d + 1) * 4 <= HISTORY_AUTO_BYTES
     yd = torch.as_tensor(y, device="cuda")
     vals, lws = [], []
-    mom = torch.empty((T, 2, d), dtype=torch.float64, device="cuda") if moments else None
+    sharded = _world()[1] > 1
+    if sharded and not eng.tiled:
+        moments = False                                   # per-shard moment sums exist for the tiled layout only
+    mom = torch.empty((T, 2, d), dtype=torch.float64, device="cuda") if moments and not sharded else None
+    msum = torch.empty((T, 1 + 2 * d), dtype=torch.float64, device="cuda") if moments and sharded else None
 
     def record(i):
         if keep_history:
             vals.append(eng.values().clone(memory_format=torch.contiguous_format).cpu())   # streamed to the host per step
             lws.append(eng.lw.cpu())
-        if moments:
+        if msum is not None:                              # this shard's raw sums, shifted by the observation (H = I)
+            eng.moment_sums(yd[i], out=msum[i])
+        elif moments:
             m, v = _moments(eng)
             mom[i, 0], mom[i, 1] = m, v
 
@@ -317,13 +349,19 @@ def run_particle_filter_for_marginals(ssm_scenario, particle_filter, y, t, rando
         record(i)
     hist = eng.ctl.read_hist(t0 + T)[t0:]
     out = cdict(t=t, y=y, ess=hist['ess'].copy(), log_norm_constant=hist['log_z'].copy(),
-                resampled=hist['resampled'].copy(), engine=eng)
+                resampled=hist['resampled'].copy(), engine=eng, engine_generation=eng.generation)
     if keep_history:
         out.value = torch.stack(vals).numpy()
         out.log_weight = torch.stack(lws).numpy()
     else:
         out.value, out.log_weight = _host_value(eng)
-    if moments:
+    if msum is not None:                                  # one all-reduce of T (1 + 2d) doubles for the whole run
+        import torch.distributed as dist
+        dist.all_reduce(msum)
+        sh = msum.cpu().numpy()
+        m1 = sh[:, 1:1 + d] / sh[:, :1]
+        out.mean, out.var = m1 + y.astype(np.float64), sh[:, 1 + d:] / sh[:, :1] - m1 * m1
+    elif moments:
         mh = mom.cpu().numpy()
         out.mean, out.var = mh[:, 0], mh[:, 1]
     if initial_sample is not None:
