@@ -91,7 +91,7 @@ def main():
     _, y = omodels.Lorenz96SSM(dim=d).simulate(8, np.random.default_rng(0), spinup=200)
     yd = torch.as_tensor(y.astype(np.float32), device="cuda")
     s = models.make_lorenz96(dim=d)
-    pf = parallel.ShardedPFEngine(sc, s, 30_000, 5, ess_threshold=2.0, resampling=_lib.RESAMPLE_SYSTEMATIC)
+    pf = parallel.ShardedPFEngine(sc, s, 32_000, 5, ess_threshold=2.0, resampling=_lib.RESAMPLE_SYSTEMATIC)
     pf.init(yd[0])
     for t in range(1, len(y)):
         pf.step(yd[t])
@@ -100,7 +100,7 @@ def main():
     gathered = [torch.empty_like(xs) for _ in range(world)]
     dist.all_gather(gathered, xs)
     if rank == 0:
-        ref = engine.PFEngine(s, 30_000 * world, 5, ess_threshold=2.0, resampling=_lib.RESAMPLE_SYSTEMATIC)
+        ref = engine.PFEngine(s, 32_000 * world, 5, ess_threshold=2.0, resampling=_lib.RESAMPLE_SYSTEMATIC)
         ref.init(yd[0])
         for t in range(1, len(y)):
             ref.step(yd[t])
