@@ -19,6 +19,7 @@
 //     sin branch to the odd one, so they arrive packed.  Philox counter = (pair id, step, purpose<<20 | coordinate/2):
 //     words (0,1) -> coordinate 2c, words (2,3) -> coordinate 2c+1  (mirrored by oracle/philox.py normals_pairwise).
 #include <stdlib.h>
+#include <string.h>
 #include "common.cuh"
 #include "rng.cuh"
 #include "comm.cuh"
@@ -53,6 +54,8 @@ __device__ __forceinline__ void box_muller_scaled(uint32_t xa, uint32_t xb, floa
     __sincosf(phi, &s, &c);
 }
 
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
 #define L96_THREADS 256
 #define L96_WARPS (L96_THREADS / 32)
 
@@ -69,34 +72,44 @@ struct L96Consts {                   // packed constants of the flow
     const f2 hm1 = __shfl_sync(MB_FULL, arr[CPL - 1], prev);           \
     const f2 hp1 = __shfl_sync(MB_FULL, arr[0], next);
 
-// one classical RK4 step (device definition of the L96 flow, SURVEY 8c / DESIGN.md)
+// one classical RK4 step (device definition of the L96 flow, SURVEY 8c / DESIGN.md).  Three arrays of CPL packed
+// registers (state x, slope accumulator, stage state s): stages 2 and 3 update s IN PLACE -- coordinates are swept
+// upwards and the two old values a later slope still needs (s[r-1], s[r-2]) ride along in two temporaries -- so the
+// kernel fits 80 registers (3 blocks of 256 threads per SM) without spilling.
 template <int CPL>
 __device__ __forceinline__ void l96_rk4(f2 (&x)[CPL], const L96Consts& c, int prev, int next) {
-    f2 acc[CPL], sa[CPL], sb[CPL];
+    f2 acc[CPL], s[CPL];
     {
         L96_HALO(x)
 #pragma unroll
-        for (int r = 0; r < CPL; ++r) { const f2 k = L96_SLOPE(x, r); acc[r] = k; sa[r] = f2_fma(c.hh, k, x[r]); }
+        for (int r = 0; r < CPL; ++r) { const f2 k = L96_SLOPE(x, r); acc[r] = k; s[r] = f2_fma(c.hh, k, x[r]); }
+    }
+#pragma unroll
+    for (int stage = 0; stage < 2; ++stage) {
+        const f2 hm2 = __shfl_sync(MB_FULL, s[CPL - 2], prev);
+        const f2 hp1 = __shfl_sync(MB_FULL, s[0], next);
+        f2 o2 = hm2, o1 = __shfl_sync(MB_FULL, s[CPL - 1], prev);
+        const f2 step = stage == 0 ? c.hh : c.hf;
+#pragma unroll
+        for (int r = 0; r < CPL; ++r) {
+            const f2 cur = s[r];
+            const f2 k = f2_fma(f2_sub(r + 1 < CPL ? s[r + 1] : hp1, o2), o1, f2_sub(c.F, cur));
+            acc[r] = f2_fma(c.two, k, acc[r]);
+            s[r] = f2_fma(step, k, x[r]);
+            o2 = o1; o1 = cur;
+        }
     }
     {
-        L96_HALO(sa)
+        L96_HALO(s)
 #pragma unroll
-        for (int r = 0; r < CPL; ++r) { const f2 k = L96_SLOPE(sa, r); acc[r] = f2_fma(c.two, k, acc[r]); sb[r] = f2_fma(c.hh, k, x[r]); }
-    }
-    {
-        L96_HALO(sb)
-#pragma unroll
-        for (int r = 0; r < CPL; ++r) { const f2 k = L96_SLOPE(sb, r); acc[r] = f2_fma(c.two, k, acc[r]); sa[r] = f2_fma(c.hf, k, x[r]); }
-    }
-    {
-        L96_HALO(sa)
-#pragma unroll
-        for (int r = 0; r < CPL; ++r) { const f2 k = L96_SLOPE(sa, r); x[r] = f2_fma(c.h6, f2_add(acc[r], k), x[r]); }
+        for (int r = 0; r < CPL; ++r) { const f2 k = L96_SLOPE(s, r); x[r] = f2_fma(c.h6, f2_add(acc[r], k), x[r]); }
     }
 }
 
 struct L96Args {
-    float forcing, h, ir, lik_const, zmean, bm_k1;   // zmean: initial mean; bm_k*: folded Box-Muller scale
+    L96Consts c;                                     // packed constants of the flow (constant bank, not registers)
+    f2 nir2, zmean2;                                 // (-1/r_std, -1/r_std), (initial mean, initial mean)
+    float forcing, h, ir, lik_const, zmean, bm_k1;   // zmean: initial mean; bm_k1: folded Box-Muller scale
     int substeps;
     const float* x_in; float* x_out; int64_t n;
     const int32_t* anc; const float* y; float* lw;
@@ -105,111 +118,185 @@ struct L96Args {
     PfTail tail;
 };
 
+// Staging of the source window (north_star (3): TMA-staged ancestor gather).  A warp advances one 32-particle OUTPUT
+// tile per iteration.  The ancestors of 32 consecutive outputs of a sorted-uniform resampler (or the tile itself when no
+// resampling happens) lie in a window of one or two SOURCE tiles of D*128 contiguous bytes each: lane 0 fetches the
+// window with cp.async.bulk (SASS UBLKCP; completion counted on the warp's mbarrier) -- one instruction per tile, no
+// destination registers, no scoreboard -- and the copy for tile k+1 is issued as soon as tile k has been read into
+// registers, so it lands while tile k is being integrated.  ncu (round 2, direct LDG version): 28 % of the warp time sat
+// in the 12 % of instructions that wait for anc[i] and then for x[anc[i]].  A window wider than L96_WIN tiles, or one
+// that straddles two GPUs' shards, falls back to per-lane loads.
+#define L96_WIN 2
+
+template <int D, int W>
+struct L96Smem {
+    static constexpr int TILE = D * 32;
+    static constexpr size_t stage_bytes = (size_t)W * L96_WIN * TILE * sizeof(float);
+};
+
 // OCC: resident blocks per SM the register allocation is tuned for; ROUNDS: Philox rounds (10 = production; the 7-round
-// variant exists only to measure how much of the step is RNG, MB_L96_VARIANT=37 / 47, and is never the default)
-template <int D, bool INIT, int OCC = 3, int ROUNDS = 10>
-__global__ void __launch_bounds__(L96_THREADS, INIT ? 2 : OCC) pf_l96_kernel(L96Args a) {
+// variant exists only to measure how much of the step is RNG, MB_L96_VARIANT=27, and is never the default)
+template <int D, bool INIT, int OCC = 2, int ROUNDS = 10, int W = L96_WARPS>
+__global__ void __launch_bounds__(W * 32, OCC) pf_l96_kernel(L96Args a) {
     static_assert(D % 8 == 0, "the lane split needs an even number of coordinates per lane");
     constexpr int CPL = D / 4;                       // coordinates per lane
     constexpr int TILE = D * 32;                     // floats per 32-particle tile
     mb_control* ctl = a.tail.ctl;
     if (!INIT && ctl->done) return;
     const bool resample = !INIT && ctl->resample != 0;
-    __shared__ Lse3 smem[L96_WARPS];
+    extern __shared__ __align__(128) float stage_all[];            // [W][L96_WIN][TILE]
+    __shared__ __align__(8) unsigned long long bars[W];
+    __shared__ Lse3 smem[W];
     __shared__ f2 ysm[D];
     __shared__ const float* peers[MB_MAX_WORLD];
-    __shared__ int64_t bounds[MB_MAX_WORLD];         // first global id of every rank (sharded gather)
     if (threadIdx.x < D) ysm[threadIdx.x] = f2_splat(a.y[threadIdx.x] * a.ir);
-    if (threadIdx.x < MB_MAX_WORLD) {
-        peers[threadIdx.x] = a.sharded ? a.x_peers[threadIdx.x] : a.x_in;
-        bounds[threadIdx.x] = (threadIdx.x < a.world) ? (int64_t)threadIdx.x * a.n_local : INT64_MAX;
-    }
+    if (threadIdx.x < MB_MAX_WORLD) peers[threadIdx.x] = a.sharded ? a.x_peers[threadIdx.x] : a.x_in;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, p = lane & 3;
+    const uint32_t bar_a = smem_u32(&bars[warp]);
+    if (!INIT && lane == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+    if (!INIT) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
 
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, p = lane & 3;
     const int prev = (lane & ~3) | ((p + 3) & 3), next = (lane & ~3) | ((p + 1) & 3);
     const uint64_t seed = a.tail.seed;
-    L96Consts c;
-    c.F = f2_splat(a.forcing); c.hh = f2_splat(0.5f * a.h); c.hf = f2_splat(a.h); c.h6 = f2_splat(a.h * (1.f / 6.f));
-    c.two = f2_splat(2.f);
-    const f2 nir = f2_splat(-a.ir), zmean = f2_splat(a.zmean);
+    const L96Consts& c = a.c;
+    const f2 nir = a.nir2, zmean = a.zmean2;
     const int coff = (CPL * p) * 32;                 // this lane's first coordinate inside a tile
+    float* const mine = stage_all + (size_t)warp * L96_WIN * TILE;
+    const int64_t gid0 = a.gid0;
 
     float am = -INFINITY;                            // per-thread online (max, sum, sumsq); lanes with p != 0 stay empty
     f2 as1 = f2_pack(0.f, 0.f), as2 = as1;           // packed fp32 partial sums (<= a few thousand terms per thread)
-    const int64_t nchunks = (a.n + 15) >> 4;         // a warp advances 16 particles (8 pairs x 4 lanes) per iteration
-    for (int64_t chunk = (int64_t)blockIdx.x * L96_WARPS + warp; chunk < nchunks; chunk += (int64_t)gridDim.x * L96_WARPS) {
-        const int64_t iP = chunk * 16 + 2 * g;       // even particle of the pair (local index); the odd one is iP + 1
-        const bool vP = iP < a.n, vQ = iP + 1 < a.n;
-        const int64_t off = (chunk >> 1) * TILE + coff + (int)(iP & 31);
-        f2 x[CPL];
-        if (!INIT) {
-            if (resample) {                          // fused ancestor gather (core.py:46-56); ancestors are GLOBAL ids
-                int64_t sP = vP ? (int64_t)a.anc[iP] : iP, sQ = vQ ? (int64_t)a.anc[iP + 1] : iP + 1;
-                const float* bP = a.x_in;
-                const float* bQ = a.x_in;
-                if (a.sharded) {                     // the ancestor lives on another rank: read it over NVLink
-                    int oP = 0, oQ = 0;
+    const int64_t ntiles = (a.n + 31) >> 5;
+    const int64_t stride = (int64_t)gridDim.x * W;
+
+    // descriptor of a tile's source window, warp-uniform except `src` (this lane's source particle, owner-relative):
+    //   mode 0: staged, window = tiles [t0, t0 + nt) of `base`;  mode 1: direct loads from `base_l` (per lane)
+    struct Win { int64_t src; const float* base; int64_t t0; int mode, nt; };
+    auto describe = [&](int64_t tile) -> Win {
+        Win w;
+        const int64_t i = tile * 32 + lane;
+        w.base = a.x_in; w.mode = 0;
+        int64_t s_ = i;                              // not resampling / beyond n: the particle's own slot
+        if (resample && i < a.n) {
+            s_ = (int64_t)__ldg(a.anc + i);          // GLOBAL id of the ancestor
+            if (a.sharded) {                         // owner-relative index + the owner's (peer-mapped) buffer
+                const int o = (int)(s_ / a.n_local);
+                s_ -= (int64_t)o * a.n_local;
+                w.base = peers[o];
+            }
+        }
+        w.src = s_;
+        int64_t lo = s_, hi = s_;
+        unsigned long long b0 = (unsigned long long)w.base, b1 = b0;
 #pragma unroll
-                    for (int r = 1; r < MB_MAX_WORLD; ++r) { oP += (sP >= bounds[r]); oQ += (sQ >= bounds[r]); }
-                    if (vP) { sP -= bounds[oP]; bP = peers[oP]; }
-                    if (vQ) { sQ -= bounds[oQ]; bQ = peers[oQ]; }
+        for (int o = 16; o > 0; o >>= 1) {
+            lo = min(lo, (int64_t)__shfl_xor_sync(MB_FULL, lo, o));
+            hi = max(hi, (int64_t)__shfl_xor_sync(MB_FULL, hi, o));
+            b0 = min(b0, (unsigned long long)__shfl_xor_sync(MB_FULL, b0, o));
+            b1 = max(b1, (unsigned long long)__shfl_xor_sync(MB_FULL, b1, o));
+        }
+        w.t0 = lo >> 5;
+        w.nt = (int)((hi >> 5) - w.t0) + 1;
+        if (w.nt > L96_WIN || b0 != b1) w.mode = 1;                    // wide window, or ancestors on two GPUs
+        return w;
+    };
+    auto fetch = [&](const Win& w, int64_t tile) {                     // lane 0: start the bulk copies of a staged window
+        if (w.mode != 0 || lane != 0) return;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"((uint32_t)(w.nt * TILE * 4)) : "memory");
+        for (int q = 0; q < w.nt; ++q)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_u32(mine + (size_t)q * TILE)), "l"(w.base + (w.t0 + q) * TILE), "r"((uint32_t)(TILE * 4)), "r"(bar_a)
+                         : "memory");
+    };
+
+    int64_t tile = (int64_t)blockIdx.x * W + warp;
+    Win cur{}, nxtw{};
+    uint32_t phase = 0;
+    if (!INIT && tile < ntiles) { cur = describe(tile); fetch(cur, tile); }
+    for (; tile < ntiles; tile += stride) {
+        const bool more = tile + stride < ntiles;
+        if (!INIT && more) nxtw = describe(tile + stride);             // ancestors of the next tile: loaded a tile ahead
+        if (!INIT && cur.mode == 0) {
+            uint32_t done = 0;
+            while (!done)
+                asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                             : "=r"(done) : "r"(bar_a), "r"(phase) : "memory");
+            phase ^= 1;
+        }
+#pragma unroll 1
+        for (int sub = 0; sub < 2; ++sub) {
+            const int64_t iP = tile * 32 + sub * 16 + 2 * g;           // even particle of the pair; the odd one is iP + 1
+            const bool vP = iP < a.n, vQ = iP + 1 < a.n;
+            f2 x[CPL];
+            if (!INIT) {
+                const int lP = sub * 16 + 2 * g;
+                const int64_t sP = __shfl_sync(MB_FULL, cur.src, lP), sQ = __shfl_sync(MB_FULL, cur.src, lP + 1);
+                if (cur.mode == 0) {
+                    const float* bP = mine + (sP - (cur.t0 << 5) >> 5) * TILE + coff + (int)(sP & 31);
+                    const float* bQ = mine + (sQ - (cur.t0 << 5) >> 5) * TILE + coff + (int)(sQ & 31);
+#pragma unroll
+                    for (int r = 0; r < CPL; ++r) x[r] = f2_pack(bP[r * 32], bQ[r * 32]);
+                } else {
+                    const unsigned long long uP = __shfl_sync(MB_FULL, (unsigned long long)cur.base, lP);
+                    const unsigned long long uQ = __shfl_sync(MB_FULL, (unsigned long long)cur.base, lP + 1);
+                    const float* bP = reinterpret_cast<const float*>(uP) + (sP >> 5) * TILE + coff + (int)(sP & 31);
+                    const float* bQ = reinterpret_cast<const float*>(uQ) + (sQ >> 5) * TILE + coff + (int)(sQ & 31);
+#pragma unroll
+                    for (int r = 0; r < CPL; ++r) x[r] = f2_pack(__ldg(bP + r * 32), __ldg(bQ + r * 32));
                 }
-                bP += (sP >> 5) * TILE + coff + (int)(sP & 31);
-                bQ += (sQ >> 5) * TILE + coff + (int)(sQ & 31);
-#pragma unroll
-                for (int r = 0; r < CPL; ++r) x[r] = f2_pack(__ldg(bP + r * 32), __ldg(bQ + r * 32));
-            } else {
-                const float2* b = reinterpret_cast<const float2*>(a.x_in + off);
-#pragma unroll
-                for (int r = 0; r < CPL; ++r) { const float2 v = __ldg(b + r * 16); x[r] = f2_pack(v.x, v.y); }
+                if (sub == 1) {                                        // the window is in registers: refill the buffer
+                    __syncwarp();
+                    if (more) fetch(nxtw, tile + stride);
+                }
+                for (int s = 0; s < a.substeps; ++s) l96_rk4<CPL>(x, c, prev, next);
             }
-            for (int s = 0; s < a.substeps; ++s) l96_rk4<CPL>(x, c, prev, next);
-        }
-        // process noise (nonlinear_gaussian.py:112-113) / initial sample, and -likelihood_potential (:115-121, H = I)
-        const uint64_t pair = (uint64_t)(a.gid0 + iP) >> 1;
-        f2 quad = f2_pack(0.f, 0.f);
+            // process noise (nonlinear_gaussian.py:112-113) / initial sample, and -likelihood_potential (:115-121, H = I)
+            const uint64_t pair = (uint64_t)(gid0 + iP) >> 1;
+            f2 quad = f2_pack(0.f, 0.f);
 #pragma unroll
-        for (int r = 0; r < CPL; r += 2) {
-            const Philox4 w = philox_raw<ROUNDS>(seed, pair, a.tail.t, INIT ? MB_P_INIT : MB_P_MOVE, (uint32_t)((CPL * p + r) >> 1));
-            float rq0, c0, s0, rq1, c1, s1;
-            box_muller_scaled(w.x, w.y, a.bm_k1, rq0, c0, s0);
-            box_muller_scaled(w.z, w.w, a.bm_k1, rq1, c1, s1);
-            float xl, xh;
-            f2_unpack(INIT ? zmean : x[r], xl, xh);
-            x[r] = f2_pack(fmaf(-rq0, c0, xl), fmaf(-rq0, s0, xh));            // cos branch -> even, sin branch -> odd particle
-            f2_unpack(INIT ? zmean : x[r + 1], xl, xh);
-            x[r + 1] = f2_pack(fmaf(-rq1, c1, xl), fmaf(-rq1, s1, xh));
-            const f2 d0 = f2_fma(x[r], nir, ysm[CPL * p + r]);
-            const f2 d1 = f2_fma(x[r + 1], nir, ysm[CPL * p + r + 1]);
-            quad = f2_fma(d0, d0, quad);
-            quad = f2_fma(d1, d1, quad);
-        }
-        quad = f2_add(quad, __shfl_xor_sync(MB_FULL, quad, 1));
-        quad = f2_add(quad, __shfl_xor_sync(MB_FULL, quad, 2));
-        float* xo = a.x_out + off;
-#pragma unroll
-        for (int r = 0; r < CPL; ++r) { float lo, hi; f2_unpack(x[r], lo, hi); *reinterpret_cast<float2*>(xo + r * 32) = make_float2(lo, hi); }
-        if (p == 0) {
-            float qP, qQ;
-            f2_unpack(quad, qP, qQ);
-            float wP = -fmaf(0.5f, qP, a.lik_const), wQ = -fmaf(0.5f, qQ, a.lik_const);
-            if (!INIT && !resample) {                                  // filtering.py:292,303: weights carried
-                const float2 o = *reinterpret_cast<const float2*>(a.lw + iP);   // lw is padded to a multiple of 32
-                wP += o.x; wQ += o.y;
+            for (int r = 0; r < CPL; r += 2) {
+                const Philox4 w = philox_raw<ROUNDS>(seed, pair, a.tail.t, INIT ? MB_P_INIT : MB_P_MOVE, (uint32_t)((CPL * p + r) >> 1));
+                float rq0, c0, s0, rq1, c1, s1;
+                box_muller_scaled(w.x, w.y, a.bm_k1, rq0, c0, s0);
+                box_muller_scaled(w.z, w.w, a.bm_k1, rq1, c1, s1);
+                float xl, xh;
+                f2_unpack(INIT ? zmean : x[r], xl, xh);
+                x[r] = f2_pack(fmaf(-rq0, c0, xl), fmaf(-rq0, s0, xh));        // cos branch -> even, sin branch -> odd particle
+                f2_unpack(INIT ? zmean : x[r + 1], xl, xh);
+                x[r + 1] = f2_pack(fmaf(-rq1, c1, xl), fmaf(-rq1, s1, xh));
+                const f2 d0 = f2_fma(x[r], nir, ysm[CPL * p + r]);
+                const f2 d1 = f2_fma(x[r + 1], nir, ysm[CPL * p + r + 1]);
+                quad = f2_fma(d0, d0, quad);
+                quad = f2_fma(d1, d1, quad);
             }
-            if (!vP) wP = -INFINITY;
-            if (!vQ) wQ = -INFINITY;
-            *reinterpret_cast<float2*>(a.lw + iP) = make_float2(wP, wQ);
-            // branch-free online (max, sum e, sum e^2): rescale by f = exp(old max - new max) (= 1 when unchanged)
-            const float amn = fmaxf(am, fmaxf(wP, wQ));
-            const float ref = (amn == -INFINITY) ? 0.f : amn;
-            const float f = __expf(am - ref);                          // am = -inf -> 0 (sums are still 0)
-            const f2 e = f2_pack(__expf(wP - ref), __expf(wQ - ref));  // NaN weights propagate into the sums
-            as1 = f2_fma(as1, f2_splat(f), e);
-            as2 = f2_fma(as2, f2_splat(f * f), f2_mul(e, e));
-            am = amn;
+            quad = f2_add(quad, __shfl_xor_sync(MB_FULL, quad, 1));
+            quad = f2_add(quad, __shfl_xor_sync(MB_FULL, quad, 2));
+            float* xo = a.x_out + tile * TILE + coff + (sub * 16 + 2 * g);
+#pragma unroll
+            for (int r = 0; r < CPL; ++r) { float lo, hi; f2_unpack(x[r], lo, hi); *reinterpret_cast<float2*>(xo + r * 32) = make_float2(lo, hi); }
+            if (p == 0) {
+                float qP, qQ;
+                f2_unpack(quad, qP, qQ);
+                float wP = -fmaf(0.5f, qP, a.lik_const), wQ = -fmaf(0.5f, qQ, a.lik_const);
+                if (!INIT && !resample) {                              // filtering.py:292,303: weights carried
+                    const float2 o = *reinterpret_cast<const float2*>(a.lw + iP);   // lw is padded to a multiple of 32
+                    wP += o.x; wQ += o.y;
+                }
+                if (!vP) wP = -INFINITY;
+                if (!vQ) wQ = -INFINITY;
+                *reinterpret_cast<float2*>(a.lw + iP) = make_float2(wP, wQ);
+                // branch-free online (max, sum e, sum e^2): rescale by f = exp(old max - new max) (= 1 when unchanged)
+                const float amn = fmaxf(am, fmaxf(wP, wQ));
+                const float ref = (amn == -INFINITY) ? 0.f : amn;
+                const float f = __expf(am - ref);                      // am = -inf -> 0 (sums are still 0)
+                const f2 e = f2_pack(__expf(wP - ref), __expf(wQ - ref));  // NaN weights propagate into the sums
+                as1 = f2_fma(as1, f2_splat(f), e);
+                as2 = f2_fma(as2, f2_splat(f * f), f2_mul(e, e));
+                am = amn;
+            }
         }
+        cur = nxtw;
     }
     float s1l, s1h, s2l, s2h;
     f2_unpack(as1, s1l, s1h);
@@ -218,34 +305,48 @@ __global__ void __launch_bounds__(L96_THREADS, INIT ? 2 : OCC) pf_l96_kernel(L96
                     resample, smem);
 }
 
+template <int D, bool INIT, int OCC, int ROUNDS, int W = L96_WARPS>
+static int l96_launch(mb_ctx* ctx, const L96Args& a, cudaStream_t st) {
+    const size_t smem = INIT ? 0 : L96Smem<D, W>::stage_bytes;
+    static bool configured = false;                                    // per instantiation
+    if (!configured && smem > 0) {
+        MB_CUDA(cudaFuncSetAttribute(pf_l96_kernel<D, INIT, OCC, ROUNDS, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    const int64_t ntiles = (a.n + 31) >> 5;
+    int64_t grid = (ntiles + W - 1) / W;
+    const int64_t cap = (int64_t)ctx->sms * OCC;                       // persistent: exactly the resident blocks
+    if (grid > cap) grid = cap;
+    if (grid > MB_MAX_PARTIAL_BLOCKS) grid = MB_MAX_PARTIAL_BLOCKS;
+    pf_l96_kernel<D, INIT, OCC, ROUNDS, W><<<(unsigned)grid, W * 32, smem, st>>>(a);
+    MB_CHECK_LAUNCH();
+    return MB_OK;
+}
+
 static int l96_dispatch(mb_ctx* ctx, const mb_ssm* ssm, L96Args& a, bool init, cudaStream_t st) {
     a.forcing = ssm->forcing; a.h = ssm->dt / (float)ssm->substeps; a.ir = 1.f / ssm->r_std;
     a.lik_const = ssm->lik_const; a.zmean = ssm->init_mean; a.substeps = ssm->substeps;
     const double sd = init ? (double)ssm->init_std : (double)ssm->q_std;       // z * sd = sqrt(-2 ln u1 sd^2) * (cos, sin)
     a.bm_k1 = (float)(-2.0 * 0.6931471805599453 * sd * sd);
+    auto splat = [](float v) { uint32_t b; memcpy(&b, &v, 4); return (f2)b | ((f2)b << 32); };
+    a.c.F = splat(a.forcing); a.c.hh = splat(0.5f * a.h); a.c.hf = splat(a.h); a.c.h6 = splat(a.h * (1.f / 6.f));
+    a.c.two = splat(2.f);
+    a.nir2 = splat(-a.ir); a.zmean2 = splat(a.zmean);
     a.tail.partials = ctx->partials;
     a.tail.counter = ctx->counters + MB_CNT_MOVE;
-    const int64_t nchunks = (a.n + 15) >> 4;
-    int64_t grid = (nchunks + L96_WARPS - 1) / L96_WARPS;
-    static int variant = -1;                                           // experiment switch: <occupancy><rounds%10>, e.g. 40, 20, 37
-    if (variant < 0) { const char* v = getenv("MB_L96_VARIANT"); variant = v ? atoi(v) : 30; }
-    const int occ = init ? 2 : variant / 10;
-    const int64_t cap = (int64_t)ctx->sms * occ;                       // persistent: exactly the resident blocks
-    if (grid > cap) grid = cap;
-    if (grid > MB_MAX_PARTIAL_BLOCKS) grid = MB_MAX_PARTIAL_BLOCKS;
-#define L96_CASE(DD)                                                                                   \
-    if (ssm->dim == DD) {                                                                              \
-        if (init) pf_l96_kernel<DD, true><<<(unsigned)grid, L96_THREADS, 0, st>>>(a);                  \
-        else pf_l96_kernel<DD, false><<<(unsigned)grid, L96_THREADS, 0, st>>>(a);                      \
-        MB_CHECK_LAUNCH();                                                                             \
-        return MB_OK;                                                                                  \
-    }
-    if (!init && ssm->dim == 40 && variant != 30) {
-#define L96_VAR(V, O, R) if (variant == V) { pf_l96_kernel<40, false, O, R><<<(unsigned)grid, L96_THREADS, 0, st>>>(a); MB_CHECK_LAUNCH(); return MB_OK; }
-        L96_VAR(20, 2, 10) L96_VAR(40, 4, 10) L96_VAR(37, 3, 7) L96_VAR(47, 4, 7)
+    static int variant = -1;                                           // experiment switch (scratch/l96_variants.sh)
+    if (variant < 0) { const char* v = getenv("MB_L96_VARIANT"); variant = v ? atoi(v) : 20; }
+    if (!init && ssm->dim == 40 && variant != 20) {
+        if (variant == 10) return l96_launch<40, false, 1, 10>(ctx, a, st);
+        if (variant == 27) return l96_launch<40, false, 2, 7>(ctx, a, st);
+        if (variant == 36) return l96_launch<40, false, 3, 10, 6>(ctx, a, st);     // 3 blocks of 6 warps
+        if (variant == 54) return l96_launch<40, false, 5, 10, 4>(ctx, a, st);     // 5 blocks of 4 warps
+        if (variant == 44) return l96_launch<40, false, 4, 10, 4>(ctx, a, st);     // 4 blocks of 4 warps
         mb_set_error("pf_l96: unknown MB_L96_VARIANT %d", variant);
         return MB_ERR_ARG;
     }
+#define L96_CASE(DD)                                                                                   \
+    if (ssm->dim == DD) return init ? l96_launch<DD, true, 2, 10>(ctx, a, st) : l96_launch<DD, false, 2, 10>(ctx, a, st);
     L96_CASE(8) L96_CASE(16) L96_CASE(40)
     mb_set_error("pf_l96: unsupported dimension %d (compiled: 8, 16, 40; no CPU fallback)", ssm->dim);
     return MB_ERR_UNSUPPORTED;
@@ -400,8 +501,6 @@ extern "C" int mb_weighted_moments_tiled(mb_ctx* ctx, const float* x, int64_t n,
 // (bank = ancestor & 31).  Otherwise the lanes read their ancestor's columns directly.
 #define GT_WARPS 4
 #define GT_WIN 3
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 template <int D>
 __global__ void __launch_bounds__(GT_WARPS * 32)

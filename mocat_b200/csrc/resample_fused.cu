@@ -204,12 +204,23 @@ __device__ __forceinline__ RfSys rf_grid_setup(const RfArgs& a, u64& offset) {
     return g;
 }
 
-// destination of global output slot o: the owning rank's ancestor array (peer mapped)
-__device__ __forceinline__ void rf_store(const RfArgs& a, int32_t* const* peers, int64_t o, int32_t v) {
-    if (a.world <= 1) { a.anc_peers[0][o] = v; return; }
-    const int r = (int)(o / a.n_local);
-    peers[r][o - (int64_t)r * a.n_local] = v;
+// destination of a RUN of global output slots [o_first, o_last] (at most one shard boundary inside: the host requires
+// n_local >= RF_HEAVY_CHUNK for sharded calls): the owning rank's ancestor array (peer mapped), pre-offset so that the
+// store is p[o]; one 64-bit division per run instead of one per output
+struct RfDst { int32_t* p0; int32_t* p1; int64_t split; };
+
+__device__ __forceinline__ RfDst rf_dst(const RfArgs& a, int32_t* const* peers, int64_t o_first) {
+    RfDst d;
+    if (a.world <= 1) { d.p0 = d.p1 = a.anc_peers[0]; d.split = INT64_MAX; return d; }
+    const int r0 = (int)(o_first / a.n_local);
+    const int r1 = min(r0 + 1, a.world - 1);
+    d.split = (int64_t)(r0 + 1) * a.n_local;
+    d.p0 = peers[r0] - (int64_t)r0 * a.n_local;
+    d.p1 = peers[r1] - (int64_t)r1 * a.n_local;
+    return d;
 }
+
+__device__ __forceinline__ void rf_store(const RfDst& d, int64_t o, int32_t v) { (o < d.split ? d.p0 : d.p1)[o] = v; }
 
 // block-wide scan of this thread's 16 integer weights -> exclusive offset of the thread inside the tile
 __device__ __forceinline__ u64 rf_block_exclusive(u64 thread_total, u64* warp_tot) {
@@ -311,10 +322,11 @@ __global__ void __launch_bounds__(RF_THREADS) rf_ancestors_kernel(RfArgs a) {
             __syncthreads();
             const unsigned cnt = min((unsigned)RF_CHUNK, o_hi - chunk_lo);
             const int32_t base = (int32_t)(gid0 + tile * RF_TILE) - 1;
+            const RfDst dst = rf_dst(a, peers, (int64_t)chunk_lo);
 #pragma unroll
             for (int q = 0; q < RF_CHUNK_ITEMS; ++q) {
                 const unsigned s = q * RF_THREADS + threadIdx.x;
-                if (s < cnt) rf_store(a, peers, (int64_t)chunk_lo + s, base + buf[s]);
+                if (s < cnt) rf_store(dst, (int64_t)chunk_lo + s, base + buf[s]);
             }
             __syncthreads();
         }
@@ -363,11 +375,19 @@ __global__ void __launch_bounds__(RF_THREADS) rf_heavy_kernel(RfArgs a) {
         for (u64 q = first; q < items; q += gridDim.x) {
             const unsigned w_lo = o_lo + (unsigned)(q * RF_HEAVY_CHUNK);
             const unsigned w_hi = (unsigned)min((u64)o_hi, (u64)w_lo + RF_HEAVY_CHUNK);
+            // ancestor = last particle j with cs[j] <= o among those with offspring: upper_bound(cs, o) - 1.  A thread's
+            // outputs increase, so does j: the previous answer is tried first (one shared-memory read) -- with collapsed
+            // weights a handful of particles own nearly every output and the binary search runs once per work item
+            int lo = 0;
+            bool have = false;
+            const RfDst dst = rf_dst(a, peers, (int64_t)w_lo);
             for (unsigned o = w_lo + threadIdx.x; o < w_hi; o += RF_THREADS) {
-                // ancestor = last particle j with cs[j] <= o among those with offspring: upper_bound(cs, o) - 1
-                int lo = 0, hi = RF_TILE;
-                while (lo < hi) { const int mid = (lo + hi) >> 1; if (cs[mid + 1] > o) hi = mid; else lo = mid + 1; }
-                rf_store(a, peers, (int64_t)o, base + lo);
+                if (!have || cs[lo + 1] <= o) {
+                    int hi = RF_TILE;
+                    while (lo < hi) { const int mid = (lo + hi) >> 1; if (cs[mid + 1] > o) hi = mid; else lo = mid + 1; }
+                    have = true;
+                }
+                rf_store(dst, (int64_t)o, base + lo);
             }
         }
         __syncthreads();
@@ -424,6 +444,7 @@ extern "C" int mb_rs_ancestors(mb_ctx* ctx, void* ws, const float* in, int64_t n
     a.rank = 0; a.world = 1; a.n_local = n; a.anc_peers[0] = anc;
     if (sh && sh->world > 1) {
         MB_REQUIRE(totals && sh->n_local == n && sh->n_total == n_total, "mb_rs_ancestors: sharded call needs the shard totals");
+        MB_REQUIRE(n >= RF_HEAVY_CHUNK, "mb_rs_ancestors: shards of a sharded population hold at least 8192 particles");
         a.totals = totals; a.rank = sh->rank; a.world = sh->world; a.n_local = sh->n_local;
         for (int r = 0; r < sh->world; ++r) {
             MB_REQUIRE(sh->anc_peers[r] != nullptr, "mb_rs_ancestors: anc_peers missing");
