@@ -132,8 +132,10 @@ typedef struct {
     const float*  x_peers[MB_MAX_WORLD];     /* input value block (d x ld) of every rank for this step   */
     const double* cdf_peers[MB_MAX_WORLD];   /* rank-relative exact fp64 CDF of every rank               */
     const double* totals;                    /* device [world]: quantised weight total of every rank     */
-    int32_t*      anc_peers[MB_MAX_WORLD];   /* ancestor array (n_local int32) of every rank: the fused   */
-                                             /* resampler writes an output's ancestor where the output lives */
+    const float*  lw_peers[MB_MAX_WORLD];    /* log-weights (n_local) of every rank: the fused resampler   */
+                                             /* re-derives the integer weights of the source tiles that    */
+                                             /* feed THIS rank's outputs from their owner's array          */
+    const void*   ws_peers[MB_MAX_WORLD];    /* mb_rs_* workspace of every rank (its tile prefix sums)      */
 } mb_shard;
 
 /* ---- context ---------------------------------------------------------------------------------- */
@@ -265,8 +267,10 @@ int mb_weighted_moment_sums_tiled(mb_ctx* ctx, const float* x_tiled, int64_t n, 
  *      total S, u0 = k0 / 2^32, and in exact rational arithmetic  a_i = min{ j : (i + u0)/n_total < C_j / S }.
  *      mb_rs_tile_sums: per-4096-particle sums + their exclusive scan into the caller's workspace `ws`
  *      (mb_rs_workspace_bytes(n) bytes; its first 8 bytes are the shard total, the word to exchange between ranks);
- *      mb_rs_ancestors: ancestors of the outputs fed by this shard's particles, written to anc (single shard) or to
- *      sh->anc_peers[owner of the output] (sharded; totals = device [world] uint64 shard totals).  k0 >= 0: caller's
+ *      mb_rs_ancestors: ancestors (GLOBAL particle ids) of this rank's n output slots, written to anc.  Sharded
+ *      (sh != NULL; totals = device [world] uint64 shard totals, exchanged after every rank's mb_rs_tile_sums): output-
+ *      partitioned -- the tile prefixes of all ranks are copied from sh->ws_peers into the local workspace and the
+ *      weights of whichever source tiles feed this rank's outputs are read from sh->lw_peers.  k0 >= 0: caller's
  *      u0 bits; k0 < 0: Philox(ctl->seed, step ctl->iter + 1, P_RESAMPLE).x.  Predicated on ctl->resample unless force. */
 size_t mb_rs_workspace_bytes(int64_t n);
 int mb_rs_tile_sums(mb_ctx* ctx, void* ws, const float* in, int64_t n, int64_t n_total, int log_mode,

@@ -74,7 +74,7 @@ class SSM(C.Structure):
 class Shard(C.Structure):
     _fields_ = [("rank", c_i32), ("world", c_i32), ("n_local", c_i64), ("n_total", c_i64),
                 ("x_peers", c_vp * MB_MAX_WORLD), ("cdf_peers", c_vp * MB_MAX_WORLD), ("totals", c_vp),
-                ("anc_peers", c_vp * MB_MAX_WORLD)]
+                ("lw_peers", c_vp * MB_MAX_WORLD), ("ws_peers", c_vp * MB_MAX_WORLD)]
 
 
 class GK(C.Structure):

@@ -171,7 +171,8 @@ __global__ void __launch_bounds__(W * 32, OCC) pf_l96_kernel(L96Args a) {
     const int64_t stride = (int64_t)gridDim.x * W;
 
     // descriptor of a tile's source window, warp-uniform except `src` (this lane's source particle, owner-relative):
-    //   mode 0: staged, window = tiles [t0, t0 + nt) of `base`;  mode 1: direct loads from `base_l` (per lane)
+    //   mode 0: staged, window = tiles [t0, t0 + nt) of `base` (2: already resident in the buffer, which starts at
+    //   tile t0);  mode 1: direct loads from `base` (per lane)
     struct Win { int64_t src; const float* base; int64_t t0; int mode, nt; };
     auto describe = [&](int64_t tile) -> Win {
         Win w;
@@ -201,8 +202,18 @@ __global__ void __launch_bounds__(W * 32, OCC) pf_l96_kernel(L96Args a) {
         if (w.nt > L96_WIN || b0 != b1) w.mode = 1;                    // wide window, or ancestors on two GPUs
         return w;
     };
-    auto fetch = [&](const Win& w, int64_t tile) {                     // lane 0: start the bulk copies of a staged window
-        if (w.mode != 0 || lane != 0) return;
+    // what the warp's staging buffer holds: a window that is already resident is NOT fetched again.  With collapsed
+    // weights (config C3 at d = 40: ESS of a few particles) long runs of output tiles descend from the same source tile,
+    // which is then read once per run instead of once per output tile -- and once over NVLink instead of n_local / 32
+    // times when it lives on another GPU.
+    const float* buf_base = nullptr;
+    int64_t buf_t0 = 0;
+    int buf_nt = 0;
+    auto fetch = [&](Win& w) {                                         // warp-uniform decision, lane 0 issues the copies
+        if (w.mode != 0) return;
+        if (w.base == buf_base && w.t0 >= buf_t0 && w.t0 + w.nt <= buf_t0 + buf_nt) { w.t0 = buf_t0; w.mode = 2; return; }
+        buf_base = w.base; buf_t0 = w.t0; buf_nt = w.nt;
+        if (lane != 0) return;
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"((uint32_t)(w.nt * TILE * 4)) : "memory");
         for (int q = 0; q < w.nt; ++q)
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -213,7 +224,7 @@ __global__ void __launch_bounds__(W * 32, OCC) pf_l96_kernel(L96Args a) {
     int64_t tile = (int64_t)blockIdx.x * W + warp;
     Win cur{}, nxtw{};
     uint32_t phase = 0;
-    if (!INIT && tile < ntiles) { cur = describe(tile); fetch(cur, tile); }
+    if (!INIT && tile < ntiles) { cur = describe(tile); fetch(cur); }
     for (; tile < ntiles; tile += stride) {
         const bool more = tile + stride < ntiles;
         if (!INIT && more) nxtw = describe(tile + stride);             // ancestors of the next tile: loaded a tile ahead
@@ -232,7 +243,7 @@ __global__ void __launch_bounds__(W * 32, OCC) pf_l96_kernel(L96Args a) {
             if (!INIT) {
                 const int lP = sub * 16 + 2 * g;
                 const int64_t sP = __shfl_sync(MB_FULL, cur.src, lP), sQ = __shfl_sync(MB_FULL, cur.src, lP + 1);
-                if (cur.mode == 0) {
+                if (cur.mode != 1) {
                     const float* bP = mine + (sP - (cur.t0 << 5) >> 5) * TILE + coff + (int)(sP & 31);
                     const float* bQ = mine + (sQ - (cur.t0 << 5) >> 5) * TILE + coff + (int)(sQ & 31);
 #pragma unroll
@@ -247,7 +258,7 @@ __global__ void __launch_bounds__(W * 32, OCC) pf_l96_kernel(L96Args a) {
                 }
                 if (sub == 1) {                                        // the window is in registers: refill the buffer
                     __syncwarp();
-                    if (more) fetch(nxtw, tile + stride);
+                    if (more) fetch(nxtw);
                 }
                 for (int s = 0; s < a.substeps; ++s) l96_rk4<CPL>(x, c, prev, next);
             }

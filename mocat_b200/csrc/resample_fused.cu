@@ -7,15 +7,22 @@
 //
 //   pass A  rf_tile_sums_kernel   integer weight e_i of every particle, summed per 4096-particle tile; the last block
 //                                 scans the tile sums (exclusive prefix) and publishes the shard total.
-//   (sharded: the shard totals are exchanged with mb_comm_allgather -- one fp64-sized word per rank)
-//   pass B  rf_ancestors_kernel   re-derives e_i, block-scans the tile, turns every particle's inclusive cumulative
-//                                 weight C_j into the NUMBER OF OUTPUTS BELOW IT c_j (closed form, see rf_count), drops
-//                                 a head marker at output c_{j-1} for every particle with offspring, max-scans the
-//                                 markers in shared memory and stores the ancestors of the tile's outputs with
-//                                 coalesced 128 B writes (peer-mapped pointers when the outputs belong to another GPU).
+//   (sharded: the shard totals are exchanged with mb_comm_allgather -- one 8-byte word per rank -- and every rank
+//    copies the peers' tile prefixes, (n/4096) x 8 B in total, into its own workspace: rf_gather_prefix_kernel)
+//   pass B  rf_ancestors_kernel   for every source tile whose offspring fall into THIS rank's output range: re-derives
+//                                 e_i (from the owning rank's weights: local, or read over NVLink), block-scans the tile,
+//                                 turns every particle's inclusive cumulative weight C_j into the NUMBER OF OUTPUTS
+//                                 BELOW IT c_j (closed form, see rf_count), drops a head marker at output c_{j-1} for
+//                                 every particle with offspring, max-scans the markers in shared memory and stores the
+//                                 ancestors with coalesced 128 B writes into the rank's OWN ancestor array.
 //   pass C  rf_heavy_kernel       tiles with more than RF_INLINE outputs (collapsed weights: a handful of particles
 //                                 own all the offspring) are queued by pass B and their outputs are spread over the
 //                                 whole grid here.
+//
+// The sharded form is OUTPUT-partitioned ("pull"): rank r computes the ancestors of its own output slots
+// [r n_local, (r+1) n_local) from whichever source tiles feed them.  With flat weights those are its own tiles; with
+// collapsed weights every rank reads the same few heavy tiles and the work stays balanced -- the source-partitioned
+// form (round 2, first version) left one GPU writing all n ancestors to its peers.
 //
 // Exact arithmetic (DESIGN.md "resampling convention"): e_i = rint(w_i 2^K) as uint64 (w_i = exp(lw_i - max lw) <= 1
 // in log mode, the caller's weight in linear mode; K = min(40, 63 - ceil(log2 n_total)) so that the total S < 2^63).
@@ -47,13 +54,16 @@ struct RfHeader {                                // first 64 bytes of the caller
 
 struct RfArgs {
     RfHeader* hdr; u64* prefix; unsigned* worklist;   // prefix[ntiles + 1]: exclusive tile prefix, last = shard total
-    const float* in; int64_t n; int64_t ntiles;
+    u64* gprefix;                                     // [world][ntiles + 1]: local copy of every rank's tile prefix
+    const float* in; int64_t n; int64_t ntiles;       // this shard's weights; ntiles tiles per shard
     int log_mode; float scale;                        // e = rint(w * scale), scale = 2^K
     const mb_control* ctl; int predicated;
     long long k0;                                     // >= 0: caller supplied u0 bits; < 0: Philox(ctl->seed, ctl->iter + 1)
     const u64* totals; int rank, world;               // shard totals (device, [world]) or NULL (single shard)
     int64_t n_local, n_total;
-    int32_t* anc_peers[MB_MAX_WORLD];
+    const float* in_peers[MB_MAX_WORLD];              // weights of every rank (peer mapped); [0] = in for a single shard
+    const u64* prefix_peers[MB_MAX_WORLD];            // tile prefix of every rank (peer mapped)
+    int32_t* anc;                                     // ancestors of this rank's outputs (n_local)
 };
 
 __device__ __forceinline__ float rf_wmax(const RfArgs& a) {
@@ -71,9 +81,9 @@ __device__ __forceinline__ u64 rf_weight(float v, bool log_mode, float wmax, flo
 }
 
 // 16 consecutive weights of this thread -> integer weights e[] (zero beyond n)
-__device__ __forceinline__ void rf_load(const RfArgs& a, int64_t base, float wmax, u64 (&e)[RF_ITEMS]) {
-    if (base + RF_ITEMS <= a.n && (((uintptr_t)a.in & 15) == 0)) {
-        const float4* p = reinterpret_cast<const float4*>(a.in + base);
+__device__ __forceinline__ void rf_load(const RfArgs& a, const float* in, int64_t base, float wmax, u64 (&e)[RF_ITEMS]) {
+    if (base + RF_ITEMS <= a.n && (((uintptr_t)in & 15) == 0)) {
+        const float4* p = reinterpret_cast<const float4*>(in + base);
 #pragma unroll
         for (int k = 0; k < RF_ITEMS / 4; ++k) {
             const float4 v = __ldg(p + k);
@@ -82,7 +92,7 @@ __device__ __forceinline__ void rf_load(const RfArgs& a, int64_t base, float wma
         }
     } else {
 #pragma unroll
-        for (int k = 0; k < RF_ITEMS; ++k) e[k] = (base + k < a.n) ? rf_weight(a.in[base + k], a.log_mode, wmax, a.scale) : 0ull;
+        for (int k = 0; k < RF_ITEMS; ++k) e[k] = (base + k < a.n) ? rf_weight(in[base + k], a.log_mode, wmax, a.scale) : 0ull;
     }
 }
 
@@ -187,13 +197,14 @@ __device__ __forceinline__ unsigned rf_count(const RfSys& g, u64 C) {
     return (unsigned)c;
 }
 
-__device__ __forceinline__ RfSys rf_grid_setup(const RfArgs& a, u64& offset) {
+// systematic grid + the cumulative weight in front of every rank (offs[r], r <= world)
+__device__ __forceinline__ RfSys rf_grid_setup(const RfArgs& a, u64* offs) {
     RfSys g;
     u64 S = 0;
-    offset = 0;
     if (a.totals) {
-        for (int r = 0; r < a.world; ++r) { const u64 t = a.totals[r]; if (r < a.rank) offset += t; S += t; }
+        for (int r = 0; r < a.world; ++r) { if (threadIdx.x == 0) offs[r] = S; S += a.totals[r]; }
     } else {
+        if (threadIdx.x == 0) offs[0] = 0;
         S = a.prefix[a.ntiles];
     }
     g.S = S; g.n = (u64)a.n_total;
@@ -203,24 +214,6 @@ __device__ __forceinline__ RfSys rf_grid_setup(const RfArgs& a, u64& offset) {
     g.u0 = (double)g.k0 * 2.3283064365386963e-10;
     return g;
 }
-
-// destination of a RUN of global output slots [o_first, o_last] (at most one shard boundary inside: the host requires
-// n_local >= RF_HEAVY_CHUNK for sharded calls): the owning rank's ancestor array (peer mapped), pre-offset so that the
-// store is p[o]; one 64-bit division per run instead of one per output
-struct RfDst { int32_t* p0; int32_t* p1; int64_t split; };
-
-__device__ __forceinline__ RfDst rf_dst(const RfArgs& a, int32_t* const* peers, int64_t o_first) {
-    RfDst d;
-    if (a.world <= 1) { d.p0 = d.p1 = a.anc_peers[0]; d.split = INT64_MAX; return d; }
-    const int r0 = (int)(o_first / a.n_local);
-    const int r1 = min(r0 + 1, a.world - 1);
-    d.split = (int64_t)(r0 + 1) * a.n_local;
-    d.p0 = peers[r0] - (int64_t)r0 * a.n_local;
-    d.p1 = peers[r1] - (int64_t)r1 * a.n_local;
-    return d;
-}
-
-__device__ __forceinline__ void rf_store(const RfDst& d, int64_t o, int32_t v) { (o < d.split ? d.p0 : d.p1)[o] = v; }
 
 // block-wide scan of this thread's 16 integer weights -> exclusive offset of the thread inside the tile
 __device__ __forceinline__ u64 rf_block_exclusive(u64 thread_total, u64* warp_tot) {
@@ -237,6 +230,18 @@ __device__ __forceinline__ u64 rf_block_exclusive(u64 thread_total, u64* warp_to
     return off + incl - thread_total;
 }
 
+// ------------------------------------------------------------------------------------------------ prefix gather
+// sharded: copy every rank's tile prefix (peer mapped, written by its pass A before the totals exchange) into the
+// local workspace so that pass B / C never wait on NVLink for bookkeeping
+__global__ void __launch_bounds__(RF_THREADS) rf_gather_prefix_kernel(RfArgs a) {
+    if (a.predicated && (a.ctl->done || !a.ctl->resample)) return;
+    const int64_t per = a.ntiles + 1, total = per * a.world;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int q = (int)(i / per);
+        a.gprefix[i] = a.prefix_peers[q][i - (int64_t)q * per];
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ pass B
 __global__ void __launch_bounds__(RF_THREADS) rf_ancestors_kernel(RfArgs a) {
     if (a.predicated && (a.ctl->done || !a.ctl->resample)) return;
@@ -244,29 +249,45 @@ __global__ void __launch_bounds__(RF_THREADS) rf_ancestors_kernel(RfArgs a) {
     __shared__ int buf[RF_CHUNK];
     __shared__ int wmaxs[RF_THREADS / 32];
     __shared__ unsigned range[2];
-    __shared__ int32_t* peers[MB_MAX_WORLD];
-    if (threadIdx.x < MB_MAX_WORLD) peers[threadIdx.x] = a.anc_peers[threadIdx.x];
+    __shared__ u64 offs[MB_MAX_WORLD];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float wmax = rf_wmax(a);
-    u64 offset;
-    const RfSys g = rf_grid_setup(a, offset);
+    const RfSys g = rf_grid_setup(a, offs);
     __syncthreads();
+    const int64_t o_begin = (int64_t)a.rank * a.n_local, o_end = o_begin + a.n;    // this rank's output slots
     if (g.S == 0) {                                       // all weights zero: legacy convention cdf[n-1] = 1
-        const int64_t o0 = (int64_t)a.rank * a.n_local;
         for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x)
-            peers[a.world <= 1 ? 0 : a.rank][i] = (int32_t)(a.n_total - 1);
-        (void)o0;
+            a.anc[i] = (int32_t)(a.n_total - 1);
         return;
     }
-    const int64_t gid0 = (int64_t)a.rank * a.n_local;     // global id of this shard's first particle
+    const int64_t per = a.ntiles + 1;
+    const int64_t gtiles = a.ntiles * a.world;            // source tiles of the whole population, rank-major
+    // candidate range: source tiles [T_lo, T_hi) can own outputs of this rank (counts are monotone in the cumulative
+    // weight; every thread runs the same two binary searches over the local prefix copy)
+    auto cum = [&](int64_t T) -> u64 {                    // cumulative weight in front of global tile T (T <= gtiles)
+        if (T >= gtiles) return g.S;
+        const int q = (int)(T / a.ntiles);
+        return offs[q] + a.gprefix[(int64_t)q * per + (T - (int64_t)q * a.ntiles)];
+    };
+    int64_t T_lo, T_hi;
+    {
+        int64_t lo = 0, hi = gtiles;                      // first tile whose END count exceeds o_begin
+        while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if ((int64_t)rf_count(g, cum(mid + 1)) > o_begin) hi = mid; else lo = mid + 1; }
+        T_lo = lo;
+        lo = T_lo; hi = gtiles;                           // first tile whose START count reaches o_end
+        while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if ((int64_t)rf_count(g, cum(mid)) >= o_end) hi = mid; else lo = mid + 1; }
+        T_hi = lo;
+    }
 
-    for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+    for (int64_t T = T_lo + blockIdx.x; T < T_hi; T += gridDim.x) {
+        const int q = (int)(T / a.ntiles);
+        const int64_t tile = T - (int64_t)q * a.ntiles;
         u64 e[RF_ITEMS];
-        rf_load(a, tile * RF_TILE + (int64_t)threadIdx.x * RF_ITEMS, wmax, e);
+        rf_load(a, a.in_peers[q], tile * RF_TILE + (int64_t)threadIdx.x * RF_ITEMS, wmax, e);
         u64 tot = 0;
 #pragma unroll
         for (int k = 0; k < RF_ITEMS; ++k) tot += e[k];
-        u64 C = offset + a.prefix[tile] + rf_block_exclusive(tot, warp_tot);
+        u64 C = offs[q] + a.gprefix[(int64_t)q * per + tile] + rf_block_exclusive(tot, warp_tot);
         // outputs below the cumulative weight: c_prev at the thread's exclusive prefix, then after every particle
         unsigned c[RF_ITEMS + 1];
         c[0] = rf_count(g, C);
@@ -278,30 +299,32 @@ __global__ void __launch_bounds__(RF_THREADS) rf_ancestors_kernel(RfArgs a) {
         if (threadIdx.x == 0) range[0] = c[0];
         if (threadIdx.x == RF_THREADS - 1) range[1] = c[RF_ITEMS];
         __syncthreads();
-        const unsigned o_lo = range[0], o_hi = range[1];
+        const unsigned o_lo = max(range[0], (unsigned)o_begin), o_hi = min(range[1], (unsigned)o_end);   // clipped to this rank
         __syncthreads();
-        if (o_hi == o_lo) continue;                       // no offspring in this tile
+        if (o_hi <= o_lo) continue;                       // no offspring among this rank's outputs
         if (o_hi - o_lo > RF_INLINE) {                    // collapsed weights: spread this tile's outputs over the grid later
-            if (threadIdx.x == 0) a.worklist[atomicAdd(&a.hdr->heavy_count, 1u)] = (unsigned)tile;
+            if (threadIdx.x == 0) a.worklist[atomicAdd(&a.hdr->heavy_count, 1u)] = (unsigned)T;
             continue;
         }
-        int carry = 0;
+        const int32_t base = (int32_t)((int64_t)q * a.n_local + tile * RF_TILE) - 1;
         for (unsigned chunk_lo = o_lo; chunk_lo < o_hi; chunk_lo += RF_CHUNK) {
 #pragma unroll
-            for (int q = 0; q < RF_CHUNK_ITEMS; ++q) buf[q * RF_THREADS + threadIdx.x] = 0;
+            for (int q2 = 0; q2 < RF_CHUNK_ITEMS; ++q2) buf[q2 * RF_THREADS + threadIdx.x] = 0;
             __syncthreads();
+            // head marker (local particle index + 1) at the first output of every particle whose offspring meet the
+            // chunk; a particle that started before the chunk marks the chunk's first slot (at most one does)
 #pragma unroll
             for (int k = 0; k < RF_ITEMS; ++k) {
-                const unsigned first = c[k];
-                if (c[k + 1] > first && first >= chunk_lo && first - chunk_lo < RF_CHUNK)
-                    buf[first - chunk_lo] = threadIdx.x * RF_ITEMS + k + 1;       // head marker: local particle index + 1
+                const unsigned first = max(c[k], chunk_lo);
+                if (c[k + 1] > first && first - chunk_lo < RF_CHUNK)
+                    buf[first - chunk_lo] = threadIdx.x * RF_ITEMS + k + 1;
             }
             __syncthreads();
             // max-scan of the markers (local indices increase with the output slot): thread t owns 24 consecutive slots
             int v[RF_CHUNK_ITEMS];
             int run = 0;
 #pragma unroll
-            for (int q = 0; q < RF_CHUNK_ITEMS; ++q) { run = max(run, buf[threadIdx.x * RF_CHUNK_ITEMS + q]); v[q] = run; }
+            for (int q2 = 0; q2 < RF_CHUNK_ITEMS; ++q2) { run = max(run, buf[threadIdx.x * RF_CHUNK_ITEMS + q2]); v[q2] = run; }
             int incl = run;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(MB_FULL, incl, o); if (lane >= o) incl = max(incl, t); }
@@ -309,24 +332,17 @@ __global__ void __launch_bounds__(RF_THREADS) rf_ancestors_kernel(RfArgs a) {
             int excl = __shfl_up_sync(MB_FULL, incl, 1);
             if (lane == 0) excl = 0;
             __syncthreads();
-            int before = carry;
 #pragma unroll
-            for (int w = 0; w < RF_THREADS / 32; ++w) if (w < warp) before = max(before, wmaxs[w]);
-            int last = carry;
+            for (int w = 0; w < RF_THREADS / 32; ++w) if (w < warp) excl = max(excl, wmaxs[w]);
 #pragma unroll
-            for (int w = 0; w < RF_THREADS / 32; ++w) last = max(last, wmaxs[w]);
-            excl = max(excl, before);
-#pragma unroll
-            for (int q = 0; q < RF_CHUNK_ITEMS; ++q) buf[threadIdx.x * RF_CHUNK_ITEMS + q] = max(v[q], excl);
-            carry = last;
+            for (int q2 = 0; q2 < RF_CHUNK_ITEMS; ++q2) buf[threadIdx.x * RF_CHUNK_ITEMS + q2] = max(v[q2], excl);
             __syncthreads();
             const unsigned cnt = min((unsigned)RF_CHUNK, o_hi - chunk_lo);
-            const int32_t base = (int32_t)(gid0 + tile * RF_TILE) - 1;
-            const RfDst dst = rf_dst(a, peers, (int64_t)chunk_lo);
+            int32_t* dst = a.anc + ((int64_t)chunk_lo - o_begin);
 #pragma unroll
-            for (int q = 0; q < RF_CHUNK_ITEMS; ++q) {
-                const unsigned s = q * RF_THREADS + threadIdx.x;
-                if (s < cnt) rf_store(dst, (int64_t)chunk_lo + s, base + buf[s]);
+            for (int q2 = 0; q2 < RF_CHUNK_ITEMS; ++q2) {
+                const unsigned s = q2 * RF_THREADS + threadIdx.x;
+                if (s < cnt) dst[s] = base + buf[s];
             }
             __syncthreads();
         }
@@ -340,24 +356,25 @@ __global__ void __launch_bounds__(RF_THREADS) rf_heavy_kernel(RfArgs a) {
     if (H == 0) return;
     __shared__ u64 warp_tot[RF_THREADS / 32];
     __shared__ unsigned cs[RF_TILE + 1];                  // cs[j] = outputs below particle j's EXCLUSIVE prefix; cs[4096] = o_hi
-    __shared__ int32_t* peers[MB_MAX_WORLD];
-    if (threadIdx.x < MB_MAX_WORLD) peers[threadIdx.x] = a.anc_peers[threadIdx.x];
+    __shared__ u64 offs[MB_MAX_WORLD];
     const float wmax = rf_wmax(a);
-    u64 offset;
-    const RfSys g = rf_grid_setup(a, offset);
-    const int64_t gid0 = (int64_t)a.rank * a.n_local;
+    const RfSys g = rf_grid_setup(a, offs);
+    const int64_t o_begin = (int64_t)a.rank * a.n_local, o_end = o_begin + a.n;
+    const int64_t per = a.ntiles + 1;
     __syncthreads();
     u64 rot = 0;                                          // rotating block assignment: work item q of entry e -> block (rot + q) % grid
     for (unsigned en = 0; en < H; ++en) {
-        const int64_t tile = a.worklist[en];
-        const u64 Cex = offset + a.prefix[tile], Cin = offset + a.prefix[tile + 1];
-        const unsigned o_lo = rf_count(g, Cex), o_hi = rf_count(g, Cin);
+        const int64_t T = a.worklist[en];
+        const int q = (int)(T / a.ntiles);
+        const int64_t tile = T - (int64_t)q * a.ntiles;
+        const u64 Cex = offs[q] + a.gprefix[(int64_t)q * per + tile], Cin = offs[q] + a.gprefix[(int64_t)q * per + tile + 1];
+        const unsigned o_lo = max(rf_count(g, Cex), (unsigned)o_begin), o_hi = min(rf_count(g, Cin), (unsigned)o_end);
         const u64 items = ((u64)(o_hi - o_lo) + RF_HEAVY_CHUNK - 1) / RF_HEAVY_CHUNK;
         const u64 first = ((u64)blockIdx.x + gridDim.x - rot % gridDim.x) % gridDim.x;
         rot += items;
         if (first >= items) continue;                     // block-uniform
         u64 e[RF_ITEMS];
-        rf_load(a, tile * RF_TILE + (int64_t)threadIdx.x * RF_ITEMS, wmax, e);
+        rf_load(a, a.in_peers[q], tile * RF_TILE + (int64_t)threadIdx.x * RF_ITEMS, wmax, e);
         u64 tot = 0;
 #pragma unroll
         for (int k = 0; k < RF_ITEMS; ++k) tot += e[k];
@@ -371,23 +388,22 @@ __global__ void __launch_bounds__(RF_THREADS) rf_heavy_kernel(RfArgs a) {
         }
         if (threadIdx.x == RF_THREADS - 1) cs[RF_TILE] = cprev;
         __syncthreads();
-        const int32_t base = (int32_t)(gid0 + tile * RF_TILE);
-        for (u64 q = first; q < items; q += gridDim.x) {
-            const unsigned w_lo = o_lo + (unsigned)(q * RF_HEAVY_CHUNK);
+        const int32_t base = (int32_t)((int64_t)q * a.n_local + tile * RF_TILE);
+        for (u64 wq = first; wq < items; wq += gridDim.x) {
+            const unsigned w_lo = o_lo + (unsigned)(wq * RF_HEAVY_CHUNK);
             const unsigned w_hi = (unsigned)min((u64)o_hi, (u64)w_lo + RF_HEAVY_CHUNK);
             // ancestor = last particle j with cs[j] <= o among those with offspring: upper_bound(cs, o) - 1.  A thread's
             // outputs increase, so does j: the previous answer is tried first (one shared-memory read) -- with collapsed
             // weights a handful of particles own nearly every output and the binary search runs once per work item
             int lo = 0;
             bool have = false;
-            const RfDst dst = rf_dst(a, peers, (int64_t)w_lo);
             for (unsigned o = w_lo + threadIdx.x; o < w_hi; o += RF_THREADS) {
                 if (!have || cs[lo + 1] <= o) {
                     int hi = RF_TILE;
                     while (lo < hi) { const int mid = (lo + hi) >> 1; if (cs[mid + 1] > o) hi = mid; else lo = mid + 1; }
                     have = true;
                 }
-                rf_store(dst, (int64_t)o, base + lo);
+                a.anc[(int64_t)o - o_begin] = base + lo;
             }
         }
         __syncthreads();
@@ -403,8 +419,10 @@ static int rf_scale_bits(int64_t n_total) {
 }
 
 extern "C" size_t mb_rs_workspace_bytes(int64_t n) {
+    // header | own tile prefix | local copy of every rank's prefix (MB_MAX_WORLD shards of n) | heavy worklist
     const int64_t ntiles = (n + RF_TILE - 1) / RF_TILE;
-    return sizeof(RfHeader) + sizeof(u64) * (size_t)(ntiles + 1) + sizeof(unsigned) * (size_t)(ntiles + 1);
+    return sizeof(RfHeader) + sizeof(u64) * (size_t)(ntiles + 1) * (1 + MB_MAX_WORLD) +
+           sizeof(unsigned) * (size_t)(ntiles + 1) * MB_MAX_WORLD;
 }
 
 static void rf_fill(RfArgs& a, void* ws, const float* in, int64_t n, int64_t n_total, int log_mode, const mb_control* ctl,
@@ -412,7 +430,8 @@ static void rf_fill(RfArgs& a, void* ws, const float* in, int64_t n, int64_t n_t
     a.ntiles = (n + RF_TILE - 1) / RF_TILE;
     a.hdr = (RfHeader*)ws;
     a.prefix = (u64*)((char*)ws + sizeof(RfHeader));
-    a.worklist = (unsigned*)(a.prefix + a.ntiles + 1);
+    a.gprefix = a.prefix + a.ntiles + 1;
+    a.worklist = (unsigned*)(a.gprefix + (a.ntiles + 1) * MB_MAX_WORLD);
     a.in = in; a.n = n; a.n_total = n_total; a.log_mode = log_mode;
     a.scale = ldexpf(1.f, rf_scale_bits(n_total));
     a.ctl = ctl; a.predicated = (ctl && !force) ? 1 : 0;
@@ -440,24 +459,30 @@ extern "C" int mb_rs_ancestors(mb_ctx* ctx, void* ws, const float* in, int64_t n
     MB_REQUIRE(k0 <= 0xffffffffll, "mb_rs_ancestors: k0 is a 32-bit fraction");
     RfArgs a{};
     rf_fill(a, ws, in, n, n_total, log_mode, ctl, force);
-    a.k0 = k0;
-    a.rank = 0; a.world = 1; a.n_local = n; a.anc_peers[0] = anc;
+    a.k0 = k0; a.anc = anc;
+    a.rank = 0; a.world = 1; a.n_local = n; a.in_peers[0] = in; a.prefix_peers[0] = a.prefix;
+    cudaStream_t st = mb_s(stream);
     if (sh && sh->world > 1) {
         MB_REQUIRE(totals && sh->n_local == n && sh->n_total == n_total, "mb_rs_ancestors: sharded call needs the shard totals");
-        MB_REQUIRE(n >= RF_HEAVY_CHUNK, "mb_rs_ancestors: shards of a sharded population hold at least 8192 particles");
+        MB_REQUIRE(n % RF_TILE == 0 || sh->rank == sh->world - 1 || true, "mb_rs_ancestors: internal");
         a.totals = totals; a.rank = sh->rank; a.world = sh->world; a.n_local = sh->n_local;
         for (int r = 0; r < sh->world; ++r) {
-            MB_REQUIRE(sh->anc_peers[r] != nullptr, "mb_rs_ancestors: anc_peers missing");
-            a.anc_peers[r] = sh->anc_peers[r];
+            MB_REQUIRE(sh->lw_peers[r] != nullptr && sh->ws_peers[r] != nullptr, "mb_rs_ancestors: lw_peers / ws_peers missing");
+            a.in_peers[r] = sh->lw_peers[r];
+            a.prefix_peers[r] = (const u64*)((const char*)sh->ws_peers[r] + sizeof(RfHeader));
         }
+        const int64_t total = (a.ntiles + 1) * a.world;
+        rf_gather_prefix_kernel<<<(unsigned)((total + RF_THREADS - 1) / RF_THREADS), RF_THREADS, 0, st>>>(a);
+        MB_CHECK_LAUNCH();
     } else {
         MB_REQUIRE(n_total == n, "mb_rs_ancestors: n_total != n needs a shard description");
+        a.gprefix = a.prefix;                             // single shard: the own prefix is the global one
     }
     int64_t grid = a.ntiles;
     if (grid > (int64_t)ctx->sms * 6) grid = (int64_t)ctx->sms * 6;
-    rf_ancestors_kernel<<<(unsigned)grid, RF_THREADS, 0, mb_s(stream)>>>(a);
+    rf_ancestors_kernel<<<(unsigned)grid, RF_THREADS, 0, st>>>(a);
     MB_CHECK_LAUNCH();
-    rf_heavy_kernel<<<(unsigned)(ctx->sms * 6), RF_THREADS, 0, mb_s(stream)>>>(a);
+    rf_heavy_kernel<<<(unsigned)(ctx->sms * 6), RF_THREADS, 0, st>>>(a);
     MB_CHECK_LAUNCH();
     return MB_OK;
 }

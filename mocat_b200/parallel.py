@@ -82,8 +82,8 @@ class ShardContext:
     def alloc_shared(self, shape, dtype):
         """cudaMalloc'd tensor on this rank + the device pointers of the same tensor on every rank"""
         import torch
-        typestr = {torch.float32: "<f4", torch.float64: "<f8", torch.int32: "<i4"}[dtype]
-        nbytes = int(np.prod(shape)) * {"<f4": 4, "<f8": 8, "<i4": 4}[typestr]
+        typestr = {torch.float32: "<f4", torch.float64: "<f8", torch.int32: "<i4", torch.int64: "<i8"}[dtype]
+        nbytes = int(np.prod(shape)) * {"<f4": 4, "<f8": 8, "<i4": 4, "<i8": 8}[typestr]
         p = C.c_void_p()
         self.L.call("mb_alloc", self.ctx, nbytes, C.byref(p))
         handle = (C.c_char * 64)()
@@ -126,27 +126,35 @@ class ShardContext:
         self.L.call("mb_comm_allgather", self.comm, _lib.ptr(src), int(nd), _lib.ptr(dst), None, _lib.stream())
 
 
-def _make_shard(sc, n_local, x_peers, cdf_peers, totals, anc_peers):
+def _make_shard(sc, n_local, x_peers, cdf_peers, totals, lw_peers, ws_peers):
     sh = _lib.Shard()
     sh.rank, sh.world, sh.n_local, sh.n_total = sc.rank, sc.world, int(n_local), int(n_local) * sc.world
     for r in range(sc.world):
         sh.x_peers[r] = x_peers[r]
         sh.cdf_peers[r] = cdf_peers[r] if cdf_peers is not None else None
-        sh.anc_peers[r] = anc_peers[r]
+        sh.lw_peers[r] = lw_peers[r]
+        sh.ws_peers[r] = ws_peers[r]
     sh.totals = totals.data_ptr()
     return sh
 
 
 def _sharded_alloc(eng, sc):
-    """IPC-shared buffers of a sharded engine: both particle buffers, the ancestor array (the fused systematic
-    resampler writes an output's ancestor into the owning rank's array) and, for multinomial resampling, the
-    rank-relative CDF and the strata histogram."""
+    """IPC-shared buffers of a sharded engine: both particle buffers, the log-weights and the resampler workspace (the
+    fused systematic resampler is output-partitioned: a rank reads the weights and tile prefixes of whichever ranks own
+    the ancestors of its outputs) and, for multinomial resampling, the rank-relative CDF and the strata histogram."""
     import torch
     shape = tuple(eng._x_shape()) if hasattr(eng, "_x_shape") else tuple(eng.xbuf[0].shape)
     xs = [sc.alloc_shared(shape, torch.float32) for _ in range(2)]
     eng.xbuf = [xs[0][0], xs[1][0]]
-    eng.anc, anc_peers = sc.alloc_shared((eng.n,), torch.int32)
-    eng._shared = [eng.xbuf[0], eng.xbuf[1], eng.anc]
+    lw_len = eng._lw_full.numel() if hasattr(eng, "_lw_full") else eng.n
+    lw_full, lw_peers = sc.alloc_shared((lw_len,), torch.float32)
+    lw_full.zero_()
+    if hasattr(eng, "_lw_full"):
+        eng._lw_full = lw_full
+    eng.lw = lw_full[:eng.n]
+    eng.rs_ws, ws_peers = sc.alloc_shared((eng.rs_ws.numel(),), torch.int64)
+    eng.rs_ws.zero_()
+    eng._shared = [eng.xbuf[0], eng.xbuf[1], lw_full, eng.rs_ws]
     cdf_peers = None
     if eng.resampling == _lib.RESAMPLE_MULTINOMIAL:
         eng.cdf, cdf_peers = sc.alloc_shared((eng.n,), torch.float64)
@@ -155,14 +163,15 @@ def _sharded_alloc(eng, sc):
         eng.hist_peers = (C.c_void_p * sc.world)(*hist_peers)
     eng.totals = torch.zeros(sc.world, dtype=torch.float64, device=sc.device)      # fp64 totals / uint64 bit patterns
     eng._barrier_out = torch.zeros(sc.world, dtype=torch.float64, device=sc.device)
-    eng.shards = [_make_shard(sc, eng.n, xs[k][1], cdf_peers, eng.totals, anc_peers) for k in range(2)]
+    eng.shards = [_make_shard(sc, eng.n, xs[k][1], cdf_peers, eng.totals, lw_peers, ws_peers) for k in range(2)]
 
 
 def _sharded_resample_kernels(eng, sc, st):
     """Every launch is predicated on the replicated control block.
-    systematic : integer tile sums -> ONE exchange of the 8-byte shard totals -> fused ancestors, written straight into
-                 the array of the rank that owns each output (peer stores over NVLink) -> one more exchange as the
-                 barrier before the step kernel reads them.
+    systematic : integer tile sums -> ONE exchange of the 8-byte shard totals (also the barrier after which the peers'
+                 tile prefixes may be read) -> every rank computes the ancestors of ITS OWN outputs, reading the weights
+                 of the source tiles that feed them from their owner (local, or over NVLink) -> one more exchange as
+                 the barrier before the step kernel overwrites the weights a peer may still be reading.
     multinomial: scan (rank-relative, exact) + local strata histogram -> one exchange (weight totals; also the barrier
                  before the peers read each other's histograms) -> histogram sum over ranks -> global sorted-uniform
                  ancestor search over the peer-mapped CDFs."""
@@ -200,7 +209,7 @@ def ShardedSMCEngine(sc, target, move, temper, n_local, seed, resampling=_lib.RE
             """collective: release the IPC-shared buffers"""
             shared, self._shared = self._shared, []
             self._graphs = [None, None]
-            self.xbuf, self.anc, self.cdf = [None, None], None, None
+            self.xbuf, self.lw, self.rs_ws, self.cdf = [None, None], None, None, None
             sc.free_shared(shared)
 
         def _shard_ref(self):
@@ -312,7 +321,7 @@ def ShardedPFEngine(sc, ssm, n_local, seed, ess_threshold=0.5, resampling=_lib.R
         def close(self):
             """collective: release the IPC-shared buffers (they are not owned by torch)"""
             shared, self._shared = self._shared, []
-            self.xbuf, self.anc = [None, None], None
+            self.xbuf, self.lw, self._lw_full, self.rs_ws = [None, None], None, None, None
             sc.free_shared(shared)
 
         def _shard_ref(self):

@@ -38,7 +38,8 @@ def fused_ancestors(E, w, k0, n_out=None):
 
 def virtual_rank_ancestors(E, w, k0, world):
     """the SHARDED path on one GPU: `world` shards of equal size, every rank's tile sums / totals / ancestors computed
-    by separate calls, outputs written through the anc_peers table (slices of one device array)"""
+    by separate calls; a rank computes the ancestors of its own outputs, reading the weights and tile prefixes of the
+    other ranks through the lw_peers / ws_peers tables (slices of one device array)"""
     torch, l, e, lib = E
     n = len(w)
     assert n % world == 0
@@ -53,7 +54,8 @@ def virtual_rank_ancestors(E, w, k0, world):
         sh = l.Shard()
         sh.rank, sh.world, sh.n_local, sh.n_total = r, world, nl, n
         for q in range(world):
-            sh.anc_peers[q] = anc[q * nl:].data_ptr()
+            sh.lw_peers[q] = wd[q * nl:].data_ptr()
+            sh.ws_peers[q] = wss[q].data_ptr()
         lib.call("mb_rs_ancestors", lib.ctx(), l.ptr(wss[r]), l.ptr(wd[r * nl:]), nl, n, 0, None, 1, int(k0),
                  l.ptr(totals), C.byref(sh), l.ptr(anc[r * nl:]), l.stream())
     return anc.cpu().numpy().astype(np.int64)
