@@ -132,10 +132,16 @@ typedef struct {
     const float*  x_peers[MB_MAX_WORLD];     /* input value block (d x ld) of every rank for this step   */
     const double* cdf_peers[MB_MAX_WORLD];   /* rank-relative exact fp64 CDF of every rank               */
     const double* totals;                    /* device [world]: quantised weight total of every rank     */
-    const float*  lw_peers[MB_MAX_WORLD];    /* log-weights (n_local) of every rank: the fused resampler   */
-                                             /* re-derives the integer weights of the source tiles that    */
-                                             /* feed THIS rank's outputs from their owner's array          */
-    const void*   ws_peers[MB_MAX_WORLD];    /* mb_rs_* workspace of every rank (its tile prefix sums)      */
+    int32_t*      anc_peers[MB_MAX_WORLD];   /* ancestor array (n_local int32) of every rank: the fused   */
+                                             /* resampler writes an output's ancestor where the output lives */
+    const float*  lw_peers[MB_MAX_WORLD];    /* log-weights (n_local) of every rank: heavy source tiles are */
+                                             /* re-derived by every rank whose outputs they feed            */
+    const void*   ws_peers[MB_MAX_WORLD];    /* mb_rs_* workspace of every rank (its heavy-tile records)    */
+    float*        import_peers[MB_MAX_WORLD];/* state import buffer of every rank, [n_local][import_stride]: */
+                                             /* when an output lives on another GPU the resampler ships the  */
+                                             /* ancestor's state (state_dim floats) and the step index       */
+                                             /* (int32 at [state_dim]) with the ancestor id; tiled layout    */
+    int32_t       import_stride, state_dim;  /* floats per import row (0: no import), coordinates per state  */
 } mb_shard;
 
 /* ---- context ---------------------------------------------------------------------------------- */
@@ -267,10 +273,12 @@ int mb_weighted_moment_sums_tiled(mb_ctx* ctx, const float* x_tiled, int64_t n, 
  *      total S, u0 = k0 / 2^32, and in exact rational arithmetic  a_i = min{ j : (i + u0)/n_total < C_j / S }.
  *      mb_rs_tile_sums: per-4096-particle sums + their exclusive scan into the caller's workspace `ws`
  *      (mb_rs_workspace_bytes(n) bytes; its first 8 bytes are the shard total, the word to exchange between ranks);
- *      mb_rs_ancestors: ancestors (GLOBAL particle ids) of this rank's n output slots, written to anc.  Sharded
- *      (sh != NULL; totals = device [world] uint64 shard totals, exchanged after every rank's mb_rs_tile_sums): output-
- *      partitioned -- the tile prefixes of all ranks are copied from sh->ws_peers into the local workspace and the
- *      weights of whichever source tiles feed this rank's outputs are read from sh->lw_peers.  k0 >= 0: caller's
+ *      mb_rs_ancestors: ancestors (GLOBAL particle ids) of the outputs fed by this shard's particles, written to anc
+ *      (single shard) or to sh->anc_peers[owner of the output] (sharded; totals = device [world] uint64 shard totals,
+ *      exchanged after every rank's mb_rs_tile_sums) -- together with the ancestor's state when the output lives on
+ *      another GPU and sh->import_stride > 0 (the redistribution after resampling, fused).  Source tiles with more than
+ *      18432 outputs (collapsed weights) are only RECORDED; mb_rs_heavy, called after a barrier over the ranks, lets
+ *      every rank fill its own share of their outputs (a single shard does both in mb_rs_ancestors).  k0 >= 0: caller's
  *      u0 bits; k0 < 0: Philox(ctl->seed, step ctl->iter + 1, P_RESAMPLE).x.  Predicated on ctl->resample unless force. */
 size_t mb_rs_workspace_bytes(int64_t n);
 int mb_rs_tile_sums(mb_ctx* ctx, void* ws, const float* in, int64_t n, int64_t n_total, int log_mode,
@@ -278,6 +286,9 @@ int mb_rs_tile_sums(mb_ctx* ctx, void* ws, const float* in, int64_t n, int64_t n
 int mb_rs_ancestors(mb_ctx* ctx, void* ws, const float* in, int64_t n, int64_t n_total, int log_mode,
                     const mb_control* ctl, int force, int64_t k0, const unsigned long long* totals,
                     const mb_shard* sh /*or NULL*/, int32_t* anc, mb_stream_t stream);
+int mb_rs_heavy(mb_ctx* ctx, void* ws, const float* in, int64_t n, int64_t n_total, int log_mode,
+                const mb_control* ctl, int force, int64_t k0, const unsigned long long* totals,
+                const mb_shard* sh, int32_t* anc, mb_stream_t stream);
 
 /* weighted mean / variance of every column under weights exp(lw - ctl->wmax)/s1  (diagnostics) */
 int mb_weighted_moments(mb_ctx* ctx, const float* x, int64_t ld, int64_t n, int d, const float* lw,

@@ -74,7 +74,8 @@ class SSM(C.Structure):
 class Shard(C.Structure):
     _fields_ = [("rank", c_i32), ("world", c_i32), ("n_local", c_i64), ("n_total", c_i64),
                 ("x_peers", c_vp * MB_MAX_WORLD), ("cdf_peers", c_vp * MB_MAX_WORLD), ("totals", c_vp),
-                ("lw_peers", c_vp * MB_MAX_WORLD), ("ws_peers", c_vp * MB_MAX_WORLD)]
+                ("anc_peers", c_vp * MB_MAX_WORLD), ("lw_peers", c_vp * MB_MAX_WORLD), ("ws_peers", c_vp * MB_MAX_WORLD),
+                ("import_peers", c_vp * MB_MAX_WORLD), ("import_stride", c_i32), ("state_dim", c_i32)]
 
 
 class GK(C.Structure):
@@ -136,6 +137,7 @@ SIGNATURES = {
     "mb_rs_workspace_bytes": (C.c_size_t, [c_i64]),
     "mb_rs_tile_sums": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, C.c_int, c_vp, C.c_int, c_vp]),
     "mb_rs_ancestors": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, C.c_int, c_vp, C.c_int, c_i64, c_vp, c_vp, c_vp, c_vp]),
+    "mb_rs_heavy": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, C.c_int, c_vp, C.c_int, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "mb_weighted_moments": (C.c_int, [c_vp, c_vp, c_i64, c_i64, C.c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "mb_quantile": (C.c_int, [c_vp, c_vp, c_i64, c_d, c_vp, c_vp]),
     "mb_colstats": (C.c_int, [c_vp, c_vp, c_i64, c_i64, C.c_int, c_vp, c_vp, c_vp]),

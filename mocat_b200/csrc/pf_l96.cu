@@ -114,7 +114,8 @@ struct L96Args {
     const float* x_in; float* x_out; int64_t n;
     const int32_t* anc; const float* y; float* lw;
     int64_t gid0;
-    const float* x_peers[MB_MAX_WORLD]; int64_t n_local; int world; int sharded;
+    const float* x_peers[MB_MAX_WORLD]; int64_t n_local; int world; int sharded; int rank;
+    const float* import_local; int import_stride;    // state rows shipped by the resampler for remote ancestors (or NULL)
     PfTail tail;
 };
 
@@ -173,23 +174,26 @@ __global__ void __launch_bounds__(W * 32, OCC) pf_l96_kernel(L96Args a) {
     // descriptor of a tile's source window, warp-uniform except `src` (this lane's source particle, owner-relative):
     //   mode 0: staged, window = tiles [t0, t0 + nt) of `base` (2: already resident in the buffer, which starts at
     //   tile t0);  mode 1: direct loads from `base` (per lane)
-    struct Win { int64_t src; const float* base; int64_t t0; int mode, nt; };
+    struct Win { int64_t src; const float* base; int64_t t0; int mode, nt, imp; };
     auto describe = [&](int64_t tile) -> Win {
         Win w;
         const int64_t i = tile * 32 + lane;
-        w.base = a.x_in; w.mode = 0;
+        w.base = a.x_in; w.mode = 0; w.imp = 0;
         int64_t s_ = i;                              // not resampling / beyond n: the particle's own slot
         if (resample && i < a.n) {
             s_ = (int64_t)__ldg(a.anc + i);          // GLOBAL id of the ancestor
             if (a.sharded) {                         // owner-relative index + the owner's (peer-mapped) buffer
                 const int o = (int)(s_ / a.n_local);
+                // the resampler of the owning rank shipped the state with the index (tag = this step): read it locally
+                if (o != a.rank && a.import_stride > 0 &&
+                    reinterpret_cast<const int*>(a.import_local + i * a.import_stride)[D] == (int)a.tail.t) w.imp = 1;
                 s_ -= (int64_t)o * a.n_local;
                 w.base = peers[o];
             }
         }
         w.src = s_;
-        int64_t lo = s_, hi = s_;
-        unsigned long long b0 = (unsigned long long)w.base, b1 = b0;
+        int64_t lo = w.imp ? INT64_MAX : s_, hi = w.imp ? INT64_MIN : s_;     // imported lanes need no window
+        unsigned long long b0 = w.imp ? ~0ull : (unsigned long long)w.base, b1 = w.imp ? 0ull : (unsigned long long)w.base;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             lo = min(lo, (int64_t)__shfl_xor_sync(MB_FULL, lo, o));
@@ -197,6 +201,8 @@ __global__ void __launch_bounds__(W * 32, OCC) pf_l96_kernel(L96Args a) {
             b0 = min(b0, (unsigned long long)__shfl_xor_sync(MB_FULL, b0, o));
             b1 = max(b1, (unsigned long long)__shfl_xor_sync(MB_FULL, b1, o));
         }
+        if (hi < lo) { w.mode = 3; w.t0 = 0; w.nt = 0; return w; }     // every lane imports: nothing to stage
+        if (w.imp) w.base = reinterpret_cast<const float*>(b0);        // keep `base` warp-uniform for the staged window
         w.t0 = lo >> 5;
         w.nt = (int)((hi >> 5) - w.t0) + 1;
         if (w.nt > L96_WIN || b0 != b1) w.mode = 1;                    // wide window, or ancestors on two GPUs
@@ -243,18 +249,37 @@ __global__ void __launch_bounds__(W * 32, OCC) pf_l96_kernel(L96Args a) {
             if (!INIT) {
                 const int lP = sub * 16 + 2 * g;
                 const int64_t sP = __shfl_sync(MB_FULL, cur.src, lP), sQ = __shfl_sync(MB_FULL, cur.src, lP + 1);
-                if (cur.mode != 1) {
-                    const float* bP = mine + (sP - (cur.t0 << 5) >> 5) * TILE + coff + (int)(sP & 31);
-                    const float* bQ = mine + (sQ - (cur.t0 << 5) >> 5) * TILE + coff + (int)(sQ & 31);
+                const int impP = __shfl_sync(MB_FULL, cur.imp, lP), impQ = __shfl_sync(MB_FULL, cur.imp, lP + 1);
+                unsigned long long uP = 0, uQ = 0;                     // per-lane source buffers of a direct-load tile: the
+                if (cur.mode == 1) {                                   // shuffles stay outside the lane-divergent branches
+                    uP = __shfl_sync(MB_FULL, (unsigned long long)cur.base, lP);
+                    uQ = __shfl_sync(MB_FULL, (unsigned long long)cur.base, lP + 1);
+                }
+                if ((impP | impQ) == 0) {
+                    if (cur.mode != 1) {
+                        const float* bP = mine + (sP - (cur.t0 << 5) >> 5) * TILE + coff + (int)(sP & 31);
+                        const float* bQ = mine + (sQ - (cur.t0 << 5) >> 5) * TILE + coff + (int)(sQ & 31);
 #pragma unroll
-                    for (int r = 0; r < CPL; ++r) x[r] = f2_pack(bP[r * 32], bQ[r * 32]);
+                        for (int r = 0; r < CPL; ++r) x[r] = f2_pack(bP[r * 32], bQ[r * 32]);
+                    } else {
+                        const float* bP = reinterpret_cast<const float*>(uP) + (sP >> 5) * TILE + coff + (int)(sP & 31);
+                        const float* bQ = reinterpret_cast<const float*>(uQ) + (sQ >> 5) * TILE + coff + (int)(sQ & 31);
+#pragma unroll
+                        for (int r = 0; r < CPL; ++r) x[r] = f2_pack(__ldg(bP + r * 32), __ldg(bQ + r * 32));
+                    }
                 } else {
-                    const unsigned long long uP = __shfl_sync(MB_FULL, (unsigned long long)cur.base, lP);
-                    const unsigned long long uQ = __shfl_sync(MB_FULL, (unsigned long long)cur.base, lP + 1);
-                    const float* bP = reinterpret_cast<const float*>(uP) + (sP >> 5) * TILE + coff + (int)(sP & 31);
-                    const float* bQ = reinterpret_cast<const float*>(uQ) + (sQ >> 5) * TILE + coff + (int)(sQ & 31);
+                    // at least one particle of the pair was shipped by the resampler of the rank that owns its ancestor:
+                    // its state is a contiguous row of this rank's import buffer (coordinate stride 1 instead of 32)
+                    const float* bP; const float* bQ;
+                    int stP = 32, stQ = 32;
+                    if (impP) { bP = a.import_local + (tile * 32 + lP) * a.import_stride + CPL * p; stP = 1; }
+                    else if (cur.mode != 1) bP = mine + (sP - (cur.t0 << 5) >> 5) * TILE + coff + (int)(sP & 31);
+                    else bP = reinterpret_cast<const float*>(uP) + (sP >> 5) * TILE + coff + (int)(sP & 31);
+                    if (impQ) { bQ = a.import_local + (tile * 32 + lP + 1) * a.import_stride + CPL * p; stQ = 1; }
+                    else if (cur.mode != 1) bQ = mine + (sQ - (cur.t0 << 5) >> 5) * TILE + coff + (int)(sQ & 31);
+                    else bQ = reinterpret_cast<const float*>(uQ) + (sQ >> 5) * TILE + coff + (int)(sQ & 31);
 #pragma unroll
-                    for (int r = 0; r < CPL; ++r) x[r] = f2_pack(__ldg(bP + r * 32), __ldg(bQ + r * 32));
+                    for (int r = 0; r < CPL; ++r) x[r] = f2_pack(bP[r * stP], bQ[r * stQ]);
                 }
                 if (sub == 1) {                                        // the window is in registers: refill the buffer
                     __syncwarp();
@@ -391,8 +416,12 @@ extern "C" int mb_pf_l96_step(mb_ctx* ctx, const mb_ssm* ssm, const float* x_in,
     a.tail.n_total = n_total; a.tail.t = t; a.tail.ess_threshold = ess_threshold; a.tail.seed = seed;
     a.tail.ctl = ctl; a.tail.hist = hist;
     if (sh && sh->world > 1) {
-        a.sharded = 1; a.n_local = sh->n_local; a.world = sh->world;
+        a.sharded = 1; a.n_local = sh->n_local; a.world = sh->world; a.rank = sh->rank;
         for (int r = 0; r < sh->world; ++r) a.x_peers[r] = sh->x_peers[r];
+        if (sh->import_stride > 0 && sh->import_peers[sh->rank]) {
+            MB_REQUIRE(sh->state_dim == ssm->dim, "mb_pf_l96_step: import rows must hold the model's state dimension");
+            a.import_local = sh->import_peers[sh->rank]; a.import_stride = sh->import_stride;
+        }
     }
     if (comm) { a.tail.comm = *mb_comm_dev(comm); a.tail.has_comm = a.tail.comm.world > 1; }
     return l96_dispatch(ctx, ssm, a, false, mb_s(stream));

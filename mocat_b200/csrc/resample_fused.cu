@@ -7,22 +7,22 @@
 //
 //   pass A  rf_tile_sums_kernel   integer weight e_i of every particle, summed per 4096-particle tile; the last block
 //                                 scans the tile sums (exclusive prefix) and publishes the shard total.
-//   (sharded: the shard totals are exchanged with mb_comm_allgather -- one 8-byte word per rank -- and every rank
-//    copies the peers' tile prefixes, (n/4096) x 8 B in total, into its own workspace: rf_gather_prefix_kernel)
-//   pass B  rf_ancestors_kernel   for every source tile whose offspring fall into THIS rank's output range: re-derives
-//                                 e_i (from the owning rank's weights: local, or read over NVLink), block-scans the tile,
-//                                 turns every particle's inclusive cumulative weight C_j into the NUMBER OF OUTPUTS
-//                                 BELOW IT c_j (closed form, see rf_count), drops a head marker at output c_{j-1} for
-//                                 every particle with offspring, max-scans the markers in shared memory and stores the
-//                                 ancestors with coalesced 128 B writes into the rank's OWN ancestor array.
-//   pass C  rf_heavy_kernel       tiles with more than RF_INLINE outputs (collapsed weights: a handful of particles
-//                                 own all the offspring) are queued by pass B and their outputs are spread over the
-//                                 whole grid here.
-//
-// The sharded form is OUTPUT-partitioned ("pull"): rank r computes the ancestors of its own output slots
-// [r n_local, (r+1) n_local) from whichever source tiles feed them.  With flat weights those are its own tiles; with
-// collapsed weights every rank reads the same few heavy tiles and the work stays balanced -- the source-partitioned
-// form (round 2, first version) left one GPU writing all n ancestors to its peers.
+//   (sharded: the shard totals are exchanged with mb_comm_allgather -- one 8-byte word per rank)
+//   pass B  rf_ancestors_kernel   every rank scans ITS OWN source tiles: re-derives e_i, block-scans the tile, turns every
+//                                 particle's inclusive cumulative weight C_j into the NUMBER OF OUTPUTS BELOW IT c_j
+//                                 (closed form, see rf_count), drops a head marker at output c_{j-1} for every particle
+//                                 with offspring, max-scans the markers in shared memory and stores the ancestors with
+//                                 coalesced 128 B writes -- into the ancestor array of the rank that OWNS the output
+//                                 (peer stores over NVLink).  When the output lives on another GPU and the caller
+//                                 provides an import buffer, the ancestor's STATE travels with the index (one
+//                                 contiguous row per output): the redistribution all-to-all of the north star, fused
+//                                 into the resampler -- the step kernel then finds the particle in its own HBM.
+//   pass C  rf_heavy_kernel       tiles with more than RF_INLINE outputs (collapsed weights: a handful of particles own
+//                                 all the offspring) are queued by pass B as records {tile, C before, C after}.  After
+//                                 a barrier every rank collects the records of ALL ranks and fills the part of each
+//                                 heavy tile's output range that falls into its own slots ("pull": the work is
+//                                 balanced however few particles own the offspring; their state is fetched by the step
+//                                 kernel, once per run of equal ancestors).
 //
 // Exact arithmetic (DESIGN.md "resampling convention"): e_i = rint(w_i 2^K) as uint64 (w_i = exp(lw_i - max lw) <= 1
 // in log mode, the caller's weight in linear mode; K = min(40, 63 - ceil(log2 n_total)) so that the total S < 2^63).
@@ -47,23 +47,32 @@ typedef unsigned long long u64;
 
 struct RfHeader {                                // first 64 bytes of the caller's workspace
     u64 local_total;                             // sum of e_i over this shard (input of the totals exchange)
-    unsigned heavy_count;                        // worklist length, reset by pass A
+    unsigned heavy_count;                        // number of heavy records of this shard, reset by pass A
     unsigned done_counter;                       // last-block detection of pass A (self resetting)
-    u64 pad[6];
+    unsigned heavy_total;                        // records gathered from all ranks (pass C)
+    unsigned pad0;
+    u64 pad[5];
+};
+
+struct RfHeavy {                                 // a source tile with more than RF_INLINE outputs
+    u64 Cex, Cin;                                // cumulative weight before / after the tile (global)
+    unsigned T, pad;                             // global tile id: owner rank * ntiles + local tile
 };
 
 struct RfArgs {
-    RfHeader* hdr; u64* prefix; unsigned* worklist;   // prefix[ntiles + 1]: exclusive tile prefix, last = shard total
-    u64* gprefix;                                     // [world][ntiles + 1]: local copy of every rank's tile prefix
+    RfHeader* hdr; u64* prefix;                       // prefix[ntiles + 1]: exclusive tile prefix, last = shard total
+    RfHeavy* heavy; RfHeavy* gheavy;                  // own records [ntiles + 1]; records of all ranks [world (ntiles + 1)]
     const float* in; int64_t n; int64_t ntiles;       // this shard's weights; ntiles tiles per shard
     int log_mode; float scale;                        // e = rint(w * scale), scale = 2^K
     const mb_control* ctl; int predicated;
     long long k0;                                     // >= 0: caller supplied u0 bits; < 0: Philox(ctl->seed, ctl->iter + 1)
     const u64* totals; int rank, world;               // shard totals (device, [world]) or NULL (single shard)
     int64_t n_local, n_total;
-    const float* in_peers[MB_MAX_WORLD];              // weights of every rank (peer mapped); [0] = in for a single shard
-    const u64* prefix_peers[MB_MAX_WORLD];            // tile prefix of every rank (peer mapped)
-    int32_t* anc;                                     // ancestors of this rank's outputs (n_local)
+    int32_t* anc_peers[MB_MAX_WORLD];                 // ancestor array of every rank (peer mapped); [0] = anc for one shard
+    const float* in_peers[MB_MAX_WORLD];              // weights of every rank (pass C reads the heavy tiles of any rank)
+    const void* ws_peers[MB_MAX_WORLD];               // workspace of every rank (its heavy records)
+    // state import (tiled populations): ancestor state pushed with the index when the output lives on another rank
+    const float* x_own; float* import_peers[MB_MAX_WORLD]; int state_dim, import_stride;
 };
 
 __device__ __forceinline__ float rf_wmax(const RfArgs& a) {
@@ -197,7 +206,7 @@ __device__ __forceinline__ unsigned rf_count(const RfSys& g, u64 C) {
     return (unsigned)c;
 }
 
-// systematic grid + the cumulative weight in front of every rank (offs[r], r <= world)
+// systematic grid + the cumulative weight in front of every rank (offs[r], r < world; written by thread 0)
 __device__ __forceinline__ RfSys rf_grid_setup(const RfArgs& a, u64* offs) {
     RfSys g;
     u64 S = 0;
@@ -230,18 +239,6 @@ __device__ __forceinline__ u64 rf_block_exclusive(u64 thread_total, u64* warp_to
     return off + incl - thread_total;
 }
 
-// ------------------------------------------------------------------------------------------------ prefix gather
-// sharded: copy every rank's tile prefix (peer mapped, written by its pass A before the totals exchange) into the
-// local workspace so that pass B / C never wait on NVLink for bookkeeping
-__global__ void __launch_bounds__(RF_THREADS) rf_gather_prefix_kernel(RfArgs a) {
-    if (a.predicated && (a.ctl->done || !a.ctl->resample)) return;
-    const int64_t per = a.ntiles + 1, total = per * a.world;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int q = (int)(i / per);
-        a.gprefix[i] = a.prefix_peers[q][i - (int64_t)q * per];
-    }
-}
-
 // ------------------------------------------------------------------------------------------------ pass B
 __global__ void __launch_bounds__(RF_THREADS) rf_ancestors_kernel(RfArgs a) {
     if (a.predicated && (a.ctl->done || !a.ctl->resample)) return;
@@ -254,40 +251,23 @@ __global__ void __launch_bounds__(RF_THREADS) rf_ancestors_kernel(RfArgs a) {
     const float wmax = rf_wmax(a);
     const RfSys g = rf_grid_setup(a, offs);
     __syncthreads();
-    const int64_t o_begin = (int64_t)a.rank * a.n_local, o_end = o_begin + a.n;    // this rank's output slots
     if (g.S == 0) {                                       // all weights zero: legacy convention cdf[n-1] = 1
         for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x)
-            a.anc[i] = (int32_t)(a.n_total - 1);
+            a.anc_peers[a.world <= 1 ? 0 : a.rank][i] = (int32_t)(a.n_total - 1);
         return;
     }
-    const int64_t per = a.ntiles + 1;
-    const int64_t gtiles = a.ntiles * a.world;            // source tiles of the whole population, rank-major
-    // candidate range: source tiles [T_lo, T_hi) can own outputs of this rank (counts are monotone in the cumulative
-    // weight; every thread runs the same two binary searches over the local prefix copy)
-    auto cum = [&](int64_t T) -> u64 {                    // cumulative weight in front of global tile T (T <= gtiles)
-        if (T >= gtiles) return g.S;
-        const int q = (int)(T / a.ntiles);
-        return offs[q] + a.gprefix[(int64_t)q * per + (T - (int64_t)q * a.ntiles)];
-    };
-    int64_t T_lo, T_hi;
-    {
-        int64_t lo = 0, hi = gtiles;                      // first tile whose END count exceeds o_begin
-        while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if ((int64_t)rf_count(g, cum(mid + 1)) > o_begin) hi = mid; else lo = mid + 1; }
-        T_lo = lo;
-        lo = T_lo; hi = gtiles;                           // first tile whose START count reaches o_end
-        while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if ((int64_t)rf_count(g, cum(mid)) >= o_end) hi = mid; else lo = mid + 1; }
-        T_hi = lo;
-    }
+    const int64_t gid0 = (int64_t)a.rank * a.n_local;     // global id of this shard's first particle
+    const u64 offset = offs[a.rank];
+    const int import_tag = a.ctl ? a.ctl->iter + 1 : 0;   // the filter step these ancestors are for (pf_l96.cu checks it)
+    const int D = a.state_dim;
 
-    for (int64_t T = T_lo + blockIdx.x; T < T_hi; T += gridDim.x) {
-        const int q = (int)(T / a.ntiles);
-        const int64_t tile = T - (int64_t)q * a.ntiles;
+    for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
         u64 e[RF_ITEMS];
-        rf_load(a, a.in_peers[q], tile * RF_TILE + (int64_t)threadIdx.x * RF_ITEMS, wmax, e);
+        rf_load(a, a.in, tile * RF_TILE + (int64_t)threadIdx.x * RF_ITEMS, wmax, e);
         u64 tot = 0;
 #pragma unroll
         for (int k = 0; k < RF_ITEMS; ++k) tot += e[k];
-        u64 C = offs[q] + a.gprefix[(int64_t)q * per + tile] + rf_block_exclusive(tot, warp_tot);
+        u64 C = offset + a.prefix[tile] + rf_block_exclusive(tot, warp_tot);
         // outputs below the cumulative weight: c_prev at the thread's exclusive prefix, then after every particle
         unsigned c[RF_ITEMS + 1];
         c[0] = rf_count(g, C);
@@ -299,14 +279,19 @@ __global__ void __launch_bounds__(RF_THREADS) rf_ancestors_kernel(RfArgs a) {
         if (threadIdx.x == 0) range[0] = c[0];
         if (threadIdx.x == RF_THREADS - 1) range[1] = c[RF_ITEMS];
         __syncthreads();
-        const unsigned o_lo = max(range[0], (unsigned)o_begin), o_hi = min(range[1], (unsigned)o_end);   // clipped to this rank
+        const unsigned o_lo = range[0], o_hi = range[1];
         __syncthreads();
-        if (o_hi <= o_lo) continue;                       // no offspring among this rank's outputs
-        if (o_hi - o_lo > RF_INLINE) {                    // collapsed weights: spread this tile's outputs over the grid later
-            if (threadIdx.x == 0) a.worklist[atomicAdd(&a.hdr->heavy_count, 1u)] = (unsigned)T;
+        if (o_hi == o_lo) continue;                       // no offspring in this tile
+        if (o_hi - o_lo > RF_INLINE) {                    // collapsed weights: every rank fills its own share later (pass C)
+            if (threadIdx.x == 0) {
+                RfHeavy h;
+                h.Cex = offset + a.prefix[tile]; h.Cin = offset + a.prefix[tile + 1];
+                h.T = (unsigned)((int64_t)a.rank * a.ntiles + tile); h.pad = 0;
+                a.heavy[atomicAdd(&a.hdr->heavy_count, 1u)] = h;
+            }
             continue;
         }
-        const int32_t base = (int32_t)((int64_t)q * a.n_local + tile * RF_TILE) - 1;
+        const int32_t base = (int32_t)(gid0 + tile * RF_TILE) - 1;
         for (unsigned chunk_lo = o_lo; chunk_lo < o_hi; chunk_lo += RF_CHUNK) {
 #pragma unroll
             for (int q2 = 0; q2 < RF_CHUNK_ITEMS; ++q2) buf[q2 * RF_THREADS + threadIdx.x] = 0;
@@ -338,11 +323,30 @@ __global__ void __launch_bounds__(RF_THREADS) rf_ancestors_kernel(RfArgs a) {
             for (int q2 = 0; q2 < RF_CHUNK_ITEMS; ++q2) buf[threadIdx.x * RF_CHUNK_ITEMS + q2] = max(v[q2], excl);
             __syncthreads();
             const unsigned cnt = min((unsigned)RF_CHUNK, o_hi - chunk_lo);
-            int32_t* dst = a.anc + ((int64_t)chunk_lo - o_begin);
-#pragma unroll
+            // destination of the run of outputs [chunk_lo, chunk_lo + cnt): at most one shard boundary inside (the host
+            // requires n_local >= RF_CHUNK for sharded calls); one 64-bit division per chunk instead of one per output
+            int r0 = 0;
+            int64_t split = INT64_MAX;
+            if (a.world > 1) { r0 = (int)((int64_t)chunk_lo / a.n_local); split = (int64_t)(r0 + 1) * a.n_local; }
+#pragma unroll 4
             for (int q2 = 0; q2 < RF_CHUNK_ITEMS; ++q2) {
-                const unsigned s = q2 * RF_THREADS + threadIdx.x;
-                if (s < cnt) dst[s] = base + buf[s];
+                const unsigned sl = q2 * RF_THREADS + threadIdx.x;
+                if (sl >= cnt) continue;
+                const int64_t o = (int64_t)chunk_lo + sl;
+                const int r = (o < split) ? r0 : r0 + 1;
+                const int64_t ol = o - (int64_t)r * a.n_local;        // slot inside the owner's arrays
+                a.anc_peers[r][ol] = base + buf[sl];
+                if (r != a.rank && a.import_stride > 0) {             // the output lives on another GPU: ship the state too
+                    const int64_t jl = tile * RF_TILE + (buf[sl] - 1);
+                    const float* src = a.x_own + (jl >> 5) * ((int64_t)D * 32) + (jl & 31);
+                    float* dst = a.import_peers[r] + ol * a.import_stride;
+                    for (int k = 0; k < D; k += 4) {
+                        float4 v4;
+                        v4.x = src[(k + 0) * 32]; v4.y = src[(k + 1) * 32]; v4.z = src[(k + 2) * 32]; v4.w = src[(k + 3) * 32];
+                        *reinterpret_cast<float4*>(dst + k) = v4;
+                    }
+                    reinterpret_cast<int*>(dst)[D] = import_tag;
+                }
             }
             __syncthreads();
         }
@@ -350,35 +354,59 @@ __global__ void __launch_bounds__(RF_THREADS) rf_ancestors_kernel(RfArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------ pass C
+// collect the heavy records of every rank (written by their pass B, complete after the caller's barrier) into the
+// local workspace, rank by rank
+__global__ void __launch_bounds__(RF_THREADS) rf_gather_heavy_kernel(RfArgs a) {
+    if (a.predicated && (a.ctl->done || !a.ctl->resample)) return;
+    __shared__ unsigned cnt[MB_MAX_WORLD + 1];
+    if (threadIdx.x == 0) {
+        unsigned run = 0;
+        for (int q = 0; q < a.world; ++q) {
+            cnt[q] = run;
+            run += reinterpret_cast<const RfHeader*>(a.ws_peers[q])->heavy_count;
+        }
+        cnt[a.world] = run;
+        a.hdr->heavy_total = run;
+    }
+    __syncthreads();
+    const int64_t off_heavy = (int64_t)sizeof(RfHeader) + (int64_t)sizeof(u64) * (a.ntiles + 1);
+    for (int q = 0; q < a.world; ++q) {
+        const RfHeavy* src = reinterpret_cast<const RfHeavy*>(reinterpret_cast<const char*>(a.ws_peers[q]) + off_heavy);
+        const unsigned hq = cnt[q + 1] - cnt[q];
+        for (unsigned i = threadIdx.x; i < hq; i += blockDim.x) a.gheavy[cnt[q] + i] = src[i];
+    }
+}
+
 __global__ void __launch_bounds__(RF_THREADS) rf_heavy_kernel(RfArgs a) {
     if (a.predicated && (a.ctl->done || !a.ctl->resample)) return;
-    const unsigned H = a.hdr->heavy_count;
+    const unsigned H = a.hdr->heavy_total;
     if (H == 0) return;
     __shared__ u64 warp_tot[RF_THREADS / 32];
     __shared__ unsigned cs[RF_TILE + 1];                  // cs[j] = outputs below particle j's EXCLUSIVE prefix; cs[4096] = o_hi
     __shared__ u64 offs[MB_MAX_WORLD];
     const float wmax = rf_wmax(a);
     const RfSys g = rf_grid_setup(a, offs);
-    const int64_t o_begin = (int64_t)a.rank * a.n_local, o_end = o_begin + a.n;
-    const int64_t per = a.ntiles + 1;
+    const int64_t o_begin = (int64_t)a.rank * a.n_local, o_end = o_begin + a.n;      // this rank's output slots
+    int32_t* anc = a.anc_peers[a.world <= 1 ? 0 : a.rank];
     __syncthreads();
     u64 rot = 0;                                          // rotating block assignment: work item q of entry e -> block (rot + q) % grid
     for (unsigned en = 0; en < H; ++en) {
-        const int64_t T = a.worklist[en];
-        const int q = (int)(T / a.ntiles);
-        const int64_t tile = T - (int64_t)q * a.ntiles;
-        const u64 Cex = offs[q] + a.gprefix[(int64_t)q * per + tile], Cin = offs[q] + a.gprefix[(int64_t)q * per + tile + 1];
-        const unsigned o_lo = max(rf_count(g, Cex), (unsigned)o_begin), o_hi = min(rf_count(g, Cin), (unsigned)o_end);
+        const RfHeavy h = a.gheavy[en];
+        const unsigned c_lo = rf_count(g, h.Cex), c_hi = rf_count(g, h.Cin);
+        const unsigned o_lo = max(c_lo, (unsigned)o_begin), o_hi = min(c_hi, (unsigned)o_end);
+        if (o_hi <= o_lo) continue;                       // none of this tile's offspring live here (block-uniform)
         const u64 items = ((u64)(o_hi - o_lo) + RF_HEAVY_CHUNK - 1) / RF_HEAVY_CHUNK;
         const u64 first = ((u64)blockIdx.x + gridDim.x - rot % gridDim.x) % gridDim.x;
         rot += items;
         if (first >= items) continue;                     // block-uniform
+        const int q = (int)(h.T / (unsigned)a.ntiles);
+        const int64_t tile = (int64_t)h.T - (int64_t)q * a.ntiles;
         u64 e[RF_ITEMS];
         rf_load(a, a.in_peers[q], tile * RF_TILE + (int64_t)threadIdx.x * RF_ITEMS, wmax, e);
         u64 tot = 0;
 #pragma unroll
         for (int k = 0; k < RF_ITEMS; ++k) tot += e[k];
-        u64 C = Cex + rf_block_exclusive(tot, warp_tot);
+        u64 C = h.Cex + rf_block_exclusive(tot, warp_tot);
         unsigned cprev = rf_count(g, C);
 #pragma unroll
         for (int k = 0; k < RF_ITEMS; ++k) {
@@ -403,7 +431,7 @@ __global__ void __launch_bounds__(RF_THREADS) rf_heavy_kernel(RfArgs a) {
                     while (lo < hi) { const int mid = (lo + hi) >> 1; if (cs[mid + 1] > o) hi = mid; else lo = mid + 1; }
                     have = true;
                 }
-                a.anc[(int64_t)o - o_begin] = base + lo;
+                anc[(int64_t)o - o_begin] = base + lo;
             }
         }
         __syncthreads();
@@ -419,10 +447,9 @@ static int rf_scale_bits(int64_t n_total) {
 }
 
 extern "C" size_t mb_rs_workspace_bytes(int64_t n) {
-    // header | own tile prefix | local copy of every rank's prefix (MB_MAX_WORLD shards of n) | heavy worklist
+    // header | own tile prefix | own heavy records | heavy records of all ranks (MB_MAX_WORLD shards of n)
     const int64_t ntiles = (n + RF_TILE - 1) / RF_TILE;
-    return sizeof(RfHeader) + sizeof(u64) * (size_t)(ntiles + 1) * (1 + MB_MAX_WORLD) +
-           sizeof(unsigned) * (size_t)(ntiles + 1) * MB_MAX_WORLD;
+    return sizeof(RfHeader) + sizeof(u64) * (size_t)(ntiles + 1) + sizeof(RfHeavy) * (size_t)(ntiles + 1) * (1 + MB_MAX_WORLD);
 }
 
 static void rf_fill(RfArgs& a, void* ws, const float* in, int64_t n, int64_t n_total, int log_mode, const mb_control* ctl,
@@ -430,8 +457,8 @@ static void rf_fill(RfArgs& a, void* ws, const float* in, int64_t n, int64_t n_t
     a.ntiles = (n + RF_TILE - 1) / RF_TILE;
     a.hdr = (RfHeader*)ws;
     a.prefix = (u64*)((char*)ws + sizeof(RfHeader));
-    a.gprefix = a.prefix + a.ntiles + 1;
-    a.worklist = (unsigned*)(a.gprefix + (a.ntiles + 1) * MB_MAX_WORLD);
+    a.heavy = (RfHeavy*)(a.prefix + a.ntiles + 1);
+    a.gheavy = a.heavy + (a.ntiles + 1);
     a.in = in; a.n = n; a.n_total = n_total; a.log_mode = log_mode;
     a.scale = ldexpf(1.f, rf_scale_bits(n_total));
     a.ctl = ctl; a.predicated = (ctl && !force) ? 1 : 0;
@@ -450,6 +477,31 @@ extern "C" int mb_rs_tile_sums(mb_ctx* ctx, void* ws, const float* in, int64_t n
     return MB_OK;
 }
 
+static int rf_shard_args(RfArgs& a, void* ws, const float* in, int64_t n, int64_t n_total, int64_t k0,
+                         const unsigned long long* totals, const mb_shard* sh, int32_t* anc, const char* who) {
+    a.k0 = k0;
+    a.rank = 0; a.world = 1; a.n_local = n; a.anc_peers[0] = anc; a.in_peers[0] = in; a.ws_peers[0] = ws;
+    if (sh && sh->world > 1) {
+        if (!(totals && sh->n_local == n && sh->n_total == n_total)) { mb_set_error("%s: sharded call needs the shard totals", who); return MB_ERR_ARG; }
+        if (n < RF_HEAVY_CHUNK) { mb_set_error("%s: shards of a sharded population hold at least 8192 particles", who); return MB_ERR_ARG; }
+        a.totals = totals; a.rank = sh->rank; a.world = sh->world; a.n_local = sh->n_local;
+        for (int r = 0; r < sh->world; ++r) {
+            if (!sh->anc_peers[r] || !sh->lw_peers[r] || !sh->ws_peers[r]) { mb_set_error("%s: anc_peers / lw_peers / ws_peers missing", who); return MB_ERR_ARG; }
+            a.anc_peers[r] = sh->anc_peers[r]; a.in_peers[r] = sh->lw_peers[r]; a.ws_peers[r] = sh->ws_peers[r];
+            a.import_peers[r] = sh->import_peers[r];
+        }
+        if (sh->import_stride > 0) {
+            if (!(sh->state_dim > 0 && sh->state_dim % 4 == 0 && sh->import_stride > sh->state_dim && sh->import_stride % 4 == 0 &&
+                  sh->x_peers[sh->rank])) { mb_set_error("%s: bad import description", who); return MB_ERR_ARG; }
+            a.x_own = sh->x_peers[sh->rank]; a.state_dim = sh->state_dim; a.import_stride = sh->import_stride;
+        }
+    } else if (n_total != n) {
+        mb_set_error("%s: n_total != n needs a shard description", who);
+        return MB_ERR_ARG;
+    }
+    return MB_OK;
+}
+
 extern "C" int mb_rs_ancestors(mb_ctx* ctx, void* ws, const float* in, int64_t n, int64_t n_total, int log_mode,
                                const mb_control* ctl, int force, int64_t k0, const unsigned long long* totals,
                                const mb_shard* sh, int32_t* anc, mb_stream_t stream) {
@@ -459,28 +511,31 @@ extern "C" int mb_rs_ancestors(mb_ctx* ctx, void* ws, const float* in, int64_t n
     MB_REQUIRE(k0 <= 0xffffffffll, "mb_rs_ancestors: k0 is a 32-bit fraction");
     RfArgs a{};
     rf_fill(a, ws, in, n, n_total, log_mode, ctl, force);
-    a.k0 = k0; a.anc = anc;
-    a.rank = 0; a.world = 1; a.n_local = n; a.in_peers[0] = in; a.prefix_peers[0] = a.prefix;
+    int rc = rf_shard_args(a, ws, in, n, n_total, k0, totals, sh, anc, "mb_rs_ancestors");
+    if (rc != MB_OK) return rc;
     cudaStream_t st = mb_s(stream);
-    if (sh && sh->world > 1) {
-        MB_REQUIRE(totals && sh->n_local == n && sh->n_total == n_total, "mb_rs_ancestors: sharded call needs the shard totals");
-        MB_REQUIRE(n % RF_TILE == 0 || sh->rank == sh->world - 1 || true, "mb_rs_ancestors: internal");
-        a.totals = totals; a.rank = sh->rank; a.world = sh->world; a.n_local = sh->n_local;
-        for (int r = 0; r < sh->world; ++r) {
-            MB_REQUIRE(sh->lw_peers[r] != nullptr && sh->ws_peers[r] != nullptr, "mb_rs_ancestors: lw_peers / ws_peers missing");
-            a.in_peers[r] = sh->lw_peers[r];
-            a.prefix_peers[r] = (const u64*)((const char*)sh->ws_peers[r] + sizeof(RfHeader));
-        }
-        const int64_t total = (a.ntiles + 1) * a.world;
-        rf_gather_prefix_kernel<<<(unsigned)((total + RF_THREADS - 1) / RF_THREADS), RF_THREADS, 0, st>>>(a);
-        MB_CHECK_LAUNCH();
-    } else {
-        MB_REQUIRE(n_total == n, "mb_rs_ancestors: n_total != n needs a shard description");
-        a.gprefix = a.prefix;                             // single shard: the own prefix is the global one
-    }
     int64_t grid = a.ntiles;
     if (grid > (int64_t)ctx->sms * 6) grid = (int64_t)ctx->sms * 6;
     rf_ancestors_kernel<<<(unsigned)grid, RF_THREADS, 0, st>>>(a);
+    MB_CHECK_LAUNCH();
+    if (a.world > 1) return MB_OK;                        // sharded: mb_rs_heavy after a barrier over the ranks
+    rf_gather_heavy_kernel<<<1, RF_THREADS, 0, st>>>(a);
+    MB_CHECK_LAUNCH();
+    rf_heavy_kernel<<<(unsigned)(ctx->sms * 6), RF_THREADS, 0, st>>>(a);
+    MB_CHECK_LAUNCH();
+    return MB_OK;
+}
+
+extern "C" int mb_rs_heavy(mb_ctx* ctx, void* ws, const float* in, int64_t n, int64_t n_total, int log_mode,
+                           const mb_control* ctl, int force, int64_t k0, const unsigned long long* totals,
+                           const mb_shard* sh, int32_t* anc, mb_stream_t stream) {
+    MB_REQUIRE(ctx && ws && in && anc && sh && sh->world > 1, "mb_rs_heavy: sharded populations only (a single shard is finished by mb_rs_ancestors)");
+    RfArgs a{};
+    rf_fill(a, ws, in, n, n_total, log_mode, ctl, force);
+    int rc = rf_shard_args(a, ws, in, n, n_total, k0, totals, sh, anc, "mb_rs_heavy");
+    if (rc != MB_OK) return rc;
+    cudaStream_t st = mb_s(stream);
+    rf_gather_heavy_kernel<<<1, RF_THREADS, 0, st>>>(a);
     MB_CHECK_LAUNCH();
     rf_heavy_kernel<<<(unsigned)(ctx->sms * 6), RF_THREADS, 0, st>>>(a);
     MB_CHECK_LAUNCH();

@@ -126,22 +126,31 @@ class ShardContext:
         self.L.call("mb_comm_allgather", self.comm, _lib.ptr(src), int(nd), _lib.ptr(dst), None, _lib.stream())
 
 
-def _make_shard(sc, n_local, x_peers, cdf_peers, totals, lw_peers, ws_peers):
+IMPORT_PAD = 8          # floats appended to an import row: [state_dim] = step tag (int32), rest keeps rows 32-byte aligned
+
+
+def _make_shard(sc, n_local, x_peers, cdf_peers, totals, anc_peers, lw_peers, ws_peers, import_peers=None, state_dim=0):
     sh = _lib.Shard()
     sh.rank, sh.world, sh.n_local, sh.n_total = sc.rank, sc.world, int(n_local), int(n_local) * sc.world
     for r in range(sc.world):
         sh.x_peers[r] = x_peers[r]
         sh.cdf_peers[r] = cdf_peers[r] if cdf_peers is not None else None
+        sh.anc_peers[r] = anc_peers[r]
         sh.lw_peers[r] = lw_peers[r]
         sh.ws_peers[r] = ws_peers[r]
+        sh.import_peers[r] = import_peers[r] if import_peers is not None else None
+    sh.import_stride = (state_dim + IMPORT_PAD) if import_peers is not None else 0
+    sh.state_dim = int(state_dim)
     sh.totals = totals.data_ptr()
     return sh
 
 
 def _sharded_alloc(eng, sc):
-    """IPC-shared buffers of a sharded engine: both particle buffers, the log-weights and the resampler workspace (the
-    fused systematic resampler is output-partitioned: a rank reads the weights and tile prefixes of whichever ranks own
-    the ancestors of its outputs) and, for multinomial resampling, the rank-relative CDF and the strata histogram."""
+    """IPC-shared buffers of a sharded engine: both particle buffers, the ancestor array (the fused systematic resampler
+    writes an output's ancestor into the owning rank's array), the log-weights and the resampler workspace (every rank
+    fills its own share of the outputs of heavy source tiles, reading their weights from the owner), for tiled
+    populations the state import buffer (ancestor state shipped with the index when the output lives on another GPU)
+    and, for multinomial resampling, the rank-relative CDF and the strata histogram."""
     import torch
     shape = tuple(eng._x_shape()) if hasattr(eng, "_x_shape") else tuple(eng.xbuf[0].shape)
     xs = [sc.alloc_shared(shape, torch.float32) for _ in range(2)]
@@ -154,7 +163,14 @@ def _sharded_alloc(eng, sc):
     eng.lw = lw_full[:eng.n]
     eng.rs_ws, ws_peers = sc.alloc_shared((eng.rs_ws.numel(),), torch.int64)
     eng.rs_ws.zero_()
-    eng._shared = [eng.xbuf[0], eng.xbuf[1], lw_full, eng.rs_ws]
+    eng.anc, anc_peers = sc.alloc_shared((eng.n,), torch.int32)
+    eng._shared = [eng.xbuf[0], eng.xbuf[1], lw_full, eng.rs_ws, eng.anc]
+    import_peers, state_dim = None, 0
+    if getattr(eng, "tiled", False) and eng.resampling == _lib.RESAMPLE_SYSTEMATIC:
+        state_dim = eng.d
+        eng.import_buf, import_peers = sc.alloc_shared((eng.n, eng.d + IMPORT_PAD), torch.float32)
+        eng.import_buf.zero_()
+        eng._shared.append(eng.import_buf)
     cdf_peers = None
     if eng.resampling == _lib.RESAMPLE_MULTINOMIAL:
         eng.cdf, cdf_peers = sc.alloc_shared((eng.n,), torch.float64)
@@ -163,15 +179,17 @@ def _sharded_alloc(eng, sc):
         eng.hist_peers = (C.c_void_p * sc.world)(*hist_peers)
     eng.totals = torch.zeros(sc.world, dtype=torch.float64, device=sc.device)      # fp64 totals / uint64 bit patterns
     eng._barrier_out = torch.zeros(sc.world, dtype=torch.float64, device=sc.device)
-    eng.shards = [_make_shard(sc, eng.n, xs[k][1], cdf_peers, eng.totals, lw_peers, ws_peers) for k in range(2)]
+    eng.shards = [_make_shard(sc, eng.n, xs[k][1], cdf_peers, eng.totals, anc_peers, lw_peers, ws_peers, import_peers,
+                              state_dim) for k in range(2)]
 
 
 def _sharded_resample_kernels(eng, sc, st):
     """Every launch is predicated on the replicated control block.
-    systematic : integer tile sums -> ONE exchange of the 8-byte shard totals (also the barrier after which the peers'
-                 tile prefixes may be read) -> every rank computes the ancestors of ITS OWN outputs, reading the weights
-                 of the source tiles that feed them from their owner (local, or over NVLink) -> one more exchange as
-                 the barrier before the step kernel overwrites the weights a peer may still be reading.
+    systematic : integer tile sums -> exchange of the 8-byte shard totals -> every rank scans ITS OWN source tiles and
+                 writes ancestors (and, for tiled populations, the ancestors' state) into the arrays of the ranks that
+                 own the outputs; tiles with collapsed weight are only recorded -> exchange (barrier) -> every rank
+                 fills ITS OWN share of the heavy tiles' outputs, reading their weights from the owner -> exchange
+                 (barrier) before the step kernel overwrites the weights a peer may still be reading.
     multinomial: scan (rank-relative, exact) + local strata histogram -> one exchange (weight totals; also the barrier
                  before the peers read each other's histograms) -> histogram sum over ranks -> global sorted-uniform
                  ancestor search over the peer-mapped CDFs."""
@@ -181,6 +199,9 @@ def _sharded_resample_kernels(eng, sc, st):
         L.call("mb_rs_tile_sums", eng.ctx, ptr(eng.rs_ws), ptr(eng.lw), eng.n, eng.n_total, 1, ctl, 0, st)
         L.call("mb_comm_allgather", sc.comm, ptr(eng.rs_ws), 1, ptr(eng.totals), ctl, st)
         L.call("mb_rs_ancestors", eng.ctx, ptr(eng.rs_ws), ptr(eng.lw), eng.n, eng.n_total, 1, ctl, 0, -1, ptr(eng.totals),
+               C.byref(eng.shards[eng.cur]), ptr(eng.anc), st)
+        L.call("mb_comm_allgather", sc.comm, ptr(eng.totals), 1, ptr(eng._barrier_out), ctl, st)
+        L.call("mb_rs_heavy", eng.ctx, ptr(eng.rs_ws), ptr(eng.lw), eng.n, eng.n_total, 1, ctl, 0, -1, ptr(eng.totals),
                C.byref(eng.shards[eng.cur]), ptr(eng.anc), st)
         L.call("mb_comm_allgather", sc.comm, ptr(eng.totals), 1, ptr(eng._barrier_out), ctl, st)
         return
@@ -209,7 +230,7 @@ def ShardedSMCEngine(sc, target, move, temper, n_local, seed, resampling=_lib.RE
             """collective: release the IPC-shared buffers"""
             shared, self._shared = self._shared, []
             self._graphs = [None, None]
-            self.xbuf, self.lw, self.rs_ws, self.cdf = [None, None], None, None, None
+            self.xbuf, self.lw, self.rs_ws, self.cdf, self.anc = [None, None], None, None, None, None
             sc.free_shared(shared)
 
         def _shard_ref(self):
@@ -315,13 +336,18 @@ def ShardedPFEngine(sc, ssm, n_local, seed, ess_threshold=0.5, resampling=_lib.R
         def _alloc_x(self, dev):
             return None                                     # the IPC-shared buffers of _sharded_alloc replace them
 
+        def init(self, y0):
+            if getattr(self, "import_buf", None) is not None:
+                self.import_buf[:, self.d].zero_()          # step tags of an earlier run on this (pooled) engine
+            super().init(y0)
+
         def _comm(self):
             return sc.comm
 
         def close(self):
             """collective: release the IPC-shared buffers (they are not owned by torch)"""
             shared, self._shared = self._shared, []
-            self.xbuf, self.lw, self._lw_full, self.rs_ws = [None, None], None, None, None
+            self.xbuf, self.lw, self._lw_full, self.rs_ws, self.anc, self.import_buf = [None, None], None, None, None, None, None
             sc.free_shared(shared)
 
         def _shard_ref(self):

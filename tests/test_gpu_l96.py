@@ -159,36 +159,69 @@ def test_gather_tiled_staged_and_direct(E, d):
 
 
 def test_l96_sharded_step_virtual_ranks(E):
-    """the sharded branch of the step kernel (ancestor's owner from the rank bounds, state read through the peer table)
-    run as 4 virtual ranks on one GPU reproduces the single-population step bit for bit"""
+    """the whole sharded filter step as 4 virtual ranks on one GPU -- per-rank tile sums, totals, pass B (ancestors AND the
+    ancestors' state pushed to the rank that owns the output), pass C, then the step kernel (state of a remote ancestor
+    taken from the import row, or from the owner's tiles through the peer table) -- reproduces the single-population
+    step bit for bit, for a spread-out and for a collapsed weight profile"""
     torch, l, e, m, lib = E
-    d, world, nl, seed = 40, 4, 32 * 37, 9
+    d, world, nl, seed = 40, 4, 32 * 320, 9
     n = world * nl
     s = m.make_lorenz96(dim=d)
     _, y = omodels.Lorenz96SSM(dim=d).simulate(2, np.random.default_rng(0), spinup=100)
     yd = torch.as_tensor(y.astype(np.float32), device="cuda")
-    eng = e.PFEngine(s, n, seed, ess_threshold=2.0, resampling=l.RESAMPLE_SYSTEMATIC)
-    eng.init(yd[0])
-    x0 = eng.x.clone()
-    lw0 = eng._lw_full.clone()
-    ctl0 = eng.ctl.t.clone()
-    eng.step(yd[1])
-    x_ref, anc, lw_ref = eng.x.clone(), eng.anc.clone(), eng._lw_full.clone()
-    x_out = torch.zeros_like(x0)
-    tiles = nl // 32
-    for r in range(world):
-        ctl = e.ControlBlock()
-        ctl.t.copy_(ctl0)
+    for collapse in (False, True):
+        eng = e.PFEngine(s, n, seed, ess_threshold=2.0, resampling=l.RESAMPLE_SYSTEMATIC)
+        eng.init(yd[0])
+        if not collapse:                                   # flatten the weights: every particle keeps ~1 offspring, the
+            eng._lw_full.mul_(0.02)                        # ancestors near the shard boundaries live on the neighbour
+            o = e.lse_ess(eng.lw).cpu().numpy()
+            c = eng.ctl.read(); c['wmax'], c['s1'], c['s2'] = o[0], o[1], o[2]; eng.ctl.write(c)
+        x0, lw0, ctl0 = eng.x.clone(), eng._lw_full.clone(), eng.ctl.t.clone()
+        eng.step(yd[1])
+        x_ref, anc_ref, lw_ref = eng.x.clone(), eng.anc.clone(), eng._lw_full.clone()
+        tiles = nl // 32
+        stride = d + 8
+        anc = torch.full((n,), -7, dtype=torch.int32, device="cuda")
+        imp = torch.zeros((n, stride), dtype=torch.float32, device="cuda")
+        wss = [torch.zeros((int(lib.dll.mb_rs_workspace_bytes(nl)) + 7) // 8, dtype=torch.int64, device="cuda") for _ in range(world)]
+        ctls = []
+        for r in range(world):
+            ctl = e.ControlBlock(); ctl.t.copy_(ctl0); ctls.append(ctl)
+            lib.call("mb_rs_tile_sums", lib.ctx(), l.ptr(wss[r]), l.ptr(lw0[r * nl:]), nl, n, 1, l.ptr(ctl.t), 0, l.stream())
+        totals = torch.stack([ws[0] for ws in wss]).contiguous()
+        shards = []
+        for r in range(world):
+            sh = l.Shard()
+            sh.rank, sh.world, sh.n_local, sh.n_total = r, world, nl, n
+            for q in range(world):
+                sh.x_peers[q] = x0[q * tiles:].data_ptr()
+                sh.anc_peers[q] = anc[q * nl:].data_ptr()
+                sh.lw_peers[q] = lw0[q * nl:].data_ptr()
+                sh.ws_peers[q] = wss[q].data_ptr()
+                sh.import_peers[q] = imp[q * nl:].data_ptr()
+            sh.import_stride, sh.state_dim = stride, d
+            shards.append(sh)
+        for r in range(world):
+            lib.call("mb_rs_ancestors", lib.ctx(), l.ptr(wss[r]), l.ptr(lw0[r * nl:]), nl, n, 1, l.ptr(ctls[r].t), 0, -1,
+                     l.ptr(totals), C.byref(shards[r]), l.ptr(anc[r * nl:]), l.stream())
+        for r in range(world):
+            lib.call("mb_rs_heavy", lib.ctx(), l.ptr(wss[r]), l.ptr(lw0[r * nl:]), nl, n, 1, l.ptr(ctls[r].t), 0, -1,
+                     l.ptr(totals), C.byref(shards[r]), l.ptr(anc[r * nl:]), l.stream())
+        assert torch.equal(anc, anc_ref)
+        owner = (anc.cpu().numpy().astype(np.int64) // nl)
+        remote = owner != (np.arange(n) // nl)
+        tags = imp[:, d].view(torch.int32).cpu().numpy()
+        assert remote.any()
+        if not collapse:
+            assert np.all(tags[remote] == 1) and np.all(tags[~remote] == 0)     # every remote output had its state shipped
+        x_out = torch.zeros_like(x0)
         lw = lw0.clone()
-        sh = l.Shard()
-        sh.rank, sh.world, sh.n_local, sh.n_total = r, world, nl, n
-        for q in range(world):
-            sh.x_peers[q] = x0[q * tiles:].data_ptr()
-        lib.call("mb_pf_l96_step", lib.ctx(), C.byref(s), l.ptr(x0[r * tiles:]), l.ptr(x_out[r * tiles:]), nl, n,
-                 l.ptr(anc[r * nl:]), l.ptr(yd[1]), l.ptr(lw[r * nl:]), seed, 1, r * nl, 2.0, l.ptr(ctl.t), None,
-                 C.byref(sh), None, l.stream())
-        assert torch.equal(lw[r * nl:(r + 1) * nl], lw_ref[r * nl:(r + 1) * nl])
-    assert torch.equal(x_out, x_ref)
+        for r in range(world):
+            lib.call("mb_pf_l96_step", lib.ctx(), C.byref(s), l.ptr(x0[r * tiles:]), l.ptr(x_out[r * tiles:]), nl, n,
+                     l.ptr(anc[r * nl:]), l.ptr(yd[1]), l.ptr(lw[r * nl:]), seed, 1, r * nl, 2.0, l.ptr(ctls[r].t), None,
+                     C.byref(shards[r]), None, l.stream())
+        assert torch.equal(lw[:n], lw_ref[:n])
+        assert torch.equal(x_out, x_ref)
 
 
 def test_pf_api_resample_continue_and_pickle(E, tmp_path):

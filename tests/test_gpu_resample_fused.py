@@ -37,9 +37,10 @@ def fused_ancestors(E, w, k0, n_out=None):
 
 
 def virtual_rank_ancestors(E, w, k0, world):
-    """the SHARDED path on one GPU: `world` shards of equal size, every rank's tile sums / totals / ancestors computed
-    by separate calls; a rank computes the ancestors of its own outputs, reading the weights and tile prefixes of the
-    other ranks through the lw_peers / ws_peers tables (slices of one device array)"""
+    """the SHARDED path on one GPU: `world` shards of equal size.  Pass A per rank, the totals, pass B per rank (own source
+    tiles; ancestors written through the anc_peers table = slices of one device array; heavy tiles recorded), then --
+    after what is a barrier on real ranks -- pass C per rank (every rank fills its own share of ALL ranks' heavy tiles,
+    reading their weights / records through lw_peers / ws_peers)"""
     torch, l, e, lib = E
     n = len(w)
     assert n % world == 0
@@ -50,14 +51,21 @@ def virtual_rank_ancestors(E, w, k0, world):
     for r in range(world):
         lib.call("mb_rs_tile_sums", lib.ctx(), l.ptr(wss[r]), l.ptr(wd[r * nl:]), nl, n, 0, None, 1, l.stream())
     totals = torch.stack([ws[0] for ws in wss]).contiguous()             # uint64 bit patterns in int64
+    shards = []
     for r in range(world):
         sh = l.Shard()
         sh.rank, sh.world, sh.n_local, sh.n_total = r, world, nl, n
         for q in range(world):
+            sh.anc_peers[q] = anc[q * nl:].data_ptr()
             sh.lw_peers[q] = wd[q * nl:].data_ptr()
             sh.ws_peers[q] = wss[q].data_ptr()
+        shards.append(sh)
+    for r in range(world):
         lib.call("mb_rs_ancestors", lib.ctx(), l.ptr(wss[r]), l.ptr(wd[r * nl:]), nl, n, 0, None, 1, int(k0),
-                 l.ptr(totals), C.byref(sh), l.ptr(anc[r * nl:]), l.stream())
+                 l.ptr(totals), C.byref(shards[r]), l.ptr(anc[r * nl:]), l.stream())
+    for r in range(world):
+        lib.call("mb_rs_heavy", lib.ctx(), l.ptr(wss[r]), l.ptr(wd[r * nl:]), nl, n, 0, None, 1, int(k0),
+                 l.ptr(totals), C.byref(shards[r]), l.ptr(anc[r * nl:]), l.stream())
     return anc.cpu().numpy().astype(np.int64)
 
 
@@ -104,7 +112,7 @@ def test_fused_all_zero_weights(E):
 def test_virtual_ranks_match_single_shard(E, world, kind):
     """SURVEY 8e 'independent of P': the sharded resampler (tile sums per rank, totals exchange, outputs written to
     the owning rank) gives the SAME BITS as one shard and as the oracle."""
-    n = 8 * 32 * 1021
+    n = 8 * 32 * 1021                                # 32672 particles per shard at world = 8 (>= 8192)
     rng = np.random.default_rng(world * 100 + len(kind))
     w = _weights(kind, n, rng)
     k0 = int(rng.integers(1 << 32))
