@@ -137,11 +137,6 @@ typedef struct {
     const float*  lw_peers[MB_MAX_WORLD];    /* log-weights (n_local) of every rank: heavy source tiles are */
                                              /* re-derived by every rank whose outputs they feed            */
     const void*   ws_peers[MB_MAX_WORLD];    /* mb_rs_* workspace of every rank (its heavy-tile records)    */
-    float*        import_peers[MB_MAX_WORLD];/* state import buffer of every rank, [n_local][import_stride]: */
-                                             /* when an output lives on another GPU the resampler ships the  */
-                                             /* ancestor's state (state_dim floats) and the step index       */
-                                             /* (int32 at [state_dim]) with the ancestor id; tiled layout    */
-    int32_t       import_stride, state_dim;  /* floats per import row (0: no import), coordinates per state  */
 } mb_shard;
 
 /* ---- context ---------------------------------------------------------------------------------- */
@@ -240,32 +235,34 @@ int mb_pf_step(mb_ctx* ctx, const mb_ssm* ssm, const float* x_in, float* x_out, 
 
 /* ---- K1b', Lorenz-96 (config C3): same contract as mb_pf_init / mb_pf_step for MB_SSM_LORENZ96 (dim 8, 16 or 40,
  *      H = I, diagonal noise, `substeps` RK4 steps per observation interval; ssm/scenarios/lorenz96.py:14-44 on
- *      ssm/nonlinear_gaussian.py:107-121) on the TILED layout: particle i, coordinate k lives at
- *      x + (i >> 5) * (dim * 32) + k * 32 + (i & 31)  (32-particle tiles; allocate ceil(n/32) tiles, lw padded to a
- *      multiple of 32).  A particle pair is spread over four lanes and advanced with packed fp32x2 arithmetic;
+ *      ssm/nonlinear_gaussian.py:107-121) on the ROW-MAJOR layout of the reference's `value` array: particle i,
+ *      coordinate k lives at x[i * dim + k] (allocate ceil(n/32)*32 rows; lw padded to a multiple of 32).  Source rows
+ *      are staged by the TMA engine (one span, or one row per scattered / remote ancestor), finished rows leave by
+ *      bulk store.  A particle pair is spread over four lanes and advanced with packed fp32x2 arithmetic;
  *      normals: Philox counter (gid >> 1, t, purpose << 20 | k / 2), words (2 (k & 1), 2 (k & 1) + 1), Box-Muller cos
  *      branch -> even particle, sin branch -> odd particle (gid0 must be even).  anc holds GLOBAL ancestor ids. */
-int mb_pf_l96_init(mb_ctx* ctx, const mb_ssm* ssm, float* x_tiled, int64_t n, int64_t n_total, const float* y0,
+int mb_pf_l96_init(mb_ctx* ctx, const mb_ssm* ssm, float* x_rows, int64_t n, int64_t n_total, const float* y0,
                    float* lw, uint64_t seed, int64_t gid0, double ess_threshold, mb_control* ctl, mb_hist* hist,
                    mb_comm* comm /*or NULL*/, mb_stream_t stream);
-int mb_pf_l96_step(mb_ctx* ctx, const mb_ssm* ssm, const float* x_in_tiled, float* x_out_tiled, int64_t n,
+int mb_pf_l96_step(mb_ctx* ctx, const mb_ssm* ssm, const float* x_in_rows, float* x_out_rows, int64_t n,
                    int64_t n_total, const int32_t* anc, const float* y, float* lw, uint64_t seed, uint32_t t,
                    int64_t gid0, double ess_threshold, mb_control* ctl, mb_hist* hist, const mb_shard* sh /*or NULL*/,
                    mb_comm* comm /*or NULL*/, mb_stream_t stream);
-/* gather of a tiled population by ancestor (cdict.__getitem__, core.py:46-56; resample_particles, filtering.py:202-217).
- * staged != 0: when a 32-output tile's ancestors span <= 3 source tiles the window is staged in shared memory with
- * cp.async.bulk (TMA bulk copies completing on an mbarrier); staged == 0: direct loads (comparison path). */
-int mb_gather_tiled(mb_ctx* ctx, const int32_t* anc, int64_t n_out, int d, const float* src_tiled, int64_t n_src,
-                    float* dst_tiled, int staged, mb_stream_t stream);
-/* weighted moments of a tiled population (per-step diagnostics instead of the stacked history, filtering.py:317-322) */
-int mb_weighted_moments_tiled(mb_ctx* ctx, const float* x_tiled, int64_t n, int d, const float* lw,
-                              const mb_control* ctl, double* mean, double* var, mb_stream_t stream);
+/* gather of a row-major (n, d) population by ancestor (cdict.__getitem__, core.py:46-56; resample_particles,
+ * filtering.py:202-217).  staged != 0: source rows fetched by the TMA engine -- one cp.async.bulk of the span when the
+ * 32 ancestors of a warp are close, else one d*4-byte copy per ancestor -- and the gathered rows leave with one bulk
+ * store; staged == 0: per-element loads (comparison path). */
+int mb_gather_rows(mb_ctx* ctx, const int32_t* anc, int64_t n_out, int d, const float* src_rows, int64_t n_src,
+                   float* dst_rows, int staged, mb_stream_t stream);
+/* weighted moments of a row-major population (per-step diagnostics instead of the stacked history, filtering.py:317-322) */
+int mb_weighted_moments_rows(mb_ctx* ctx, const float* x_rows, int64_t n, int d, const float* lw,
+                             const mb_control* ctl, double* mean, double* var, mb_stream_t stream);
 /* the same sums left un-normalised, for one shard of a sharded population (ctl->wmax is the global maximum):
  * sums[0] = sum e_i, sums[1+k] = sum e_i (x_ik - shift_k), sums[1+d+k] = sum e_i (x_ik - shift_k)^2, e_i = exp(lw_i - wmax);
  * the caller adds the ranks' records and normalises (filtering.py:317-322 diagnostics over all GPUs). */
-int mb_weighted_moment_sums_tiled(mb_ctx* ctx, const float* x_tiled, int64_t n, int d, const float* lw,
-                                  const mb_control* ctl, const float* shift /*[d]*/, double* sums /*[1+2d]*/,
-                                  mb_stream_t stream);
+int mb_weighted_moment_sums_rows(mb_ctx* ctx, const float* x_rows, int64_t n, int d, const float* lw,
+                                 const mb_control* ctl, const float* shift /*[d]*/, double* sums /*[1+2d]*/,
+                                 mb_stream_t stream);
 
 /* ---- K4+K5 fused: systematic resampling without a materialised CDF (transport/smc.py:61-71,
  *      ssm/filtering.py:196-199).  Integer weights e_i = rint(w_i 2^K) (w_i = exp(lw_i - ctl->wmax) in log mode, the
@@ -275,8 +272,7 @@ int mb_weighted_moment_sums_tiled(mb_ctx* ctx, const float* x_tiled, int64_t n, 
  *      (mb_rs_workspace_bytes(n) bytes; its first 8 bytes are the shard total, the word to exchange between ranks);
  *      mb_rs_ancestors: ancestors (GLOBAL particle ids) of the outputs fed by this shard's particles, written to anc
  *      (single shard) or to sh->anc_peers[owner of the output] (sharded; totals = device [world] uint64 shard totals,
- *      exchanged after every rank's mb_rs_tile_sums) -- together with the ancestor's state when the output lives on
- *      another GPU and sh->import_stride > 0 (the redistribution after resampling, fused).  Source tiles with more than
+ *      exchanged after every rank's mb_rs_tile_sums).  Source tiles with more than
  *      18432 outputs (collapsed weights) are only RECORDED; mb_rs_heavy, called after a barrier over the ranks, lets
  *      every rank fill its own share of their outputs (a single shard does both in mb_rs_ancestors).  k0 >= 0: caller's
  *      u0 bits; k0 < 0: Philox(ctl->seed, step ctl->iter + 1, P_RESAMPLE).x.  Predicated on ctl->resample unless force. */

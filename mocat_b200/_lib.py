@@ -74,8 +74,7 @@ class SSM(C.Structure):
 class Shard(C.Structure):
     _fields_ = [("rank", c_i32), ("world", c_i32), ("n_local", c_i64), ("n_total", c_i64),
                 ("x_peers", c_vp * MB_MAX_WORLD), ("cdf_peers", c_vp * MB_MAX_WORLD), ("totals", c_vp),
-                ("anc_peers", c_vp * MB_MAX_WORLD), ("lw_peers", c_vp * MB_MAX_WORLD), ("ws_peers", c_vp * MB_MAX_WORLD),
-                ("import_peers", c_vp * MB_MAX_WORLD), ("import_stride", c_i32), ("state_dim", c_i32)]
+                ("anc_peers", c_vp * MB_MAX_WORLD), ("lw_peers", c_vp * MB_MAX_WORLD), ("ws_peers", c_vp * MB_MAX_WORLD)]
 
 
 class GK(C.Structure):
@@ -131,9 +130,9 @@ SIGNATURES = {
                                  c_vp]),
     "mb_pf_l96_step": (C.c_int, [c_vp, C.POINTER(SSM), c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_u64, c_u32, c_i64,
                                  c_d, c_vp, c_vp, c_vp, c_vp, c_vp]),
-    "mb_weighted_moments_tiled": (C.c_int, [c_vp, c_vp, c_i64, C.c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
-    "mb_weighted_moment_sums_tiled": (C.c_int, [c_vp, c_vp, c_i64, C.c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
-    "mb_gather_tiled": (C.c_int, [c_vp, c_vp, c_i64, C.c_int, c_vp, c_i64, c_vp, C.c_int, c_vp]),
+    "mb_weighted_moments_rows": (C.c_int, [c_vp, c_vp, c_i64, C.c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "mb_weighted_moment_sums_rows": (C.c_int, [c_vp, c_vp, c_i64, C.c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "mb_gather_rows": (C.c_int, [c_vp, c_vp, c_i64, C.c_int, c_vp, c_i64, c_vp, C.c_int, c_vp]),
     "mb_rs_workspace_bytes": (C.c_size_t, [c_i64]),
     "mb_rs_tile_sums": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, C.c_int, c_vp, C.c_int, c_vp]),
     "mb_rs_ancestors": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, C.c_int, c_vp, C.c_int, c_i64, c_vp, c_vp, c_vp, c_vp]),

@@ -7,9 +7,13 @@
 //
 // Why a kernel of its own (round 1 ran this model through the generic one-thread-per-particle kernel at 54 % of the
 // HBM roofline, issue bound at 128 registers / 16 warps per SM, ~2100 SASS instructions per particle):
-//   * TILED layout (AoSoA): particle i, coordinate k lives at base + (i >> 5) * (D*32) + k*32 + (i & 31).  The D values
-//     of a particle sit in one D*128-byte tile, every column is reached with an IMMEDIATE offset from one base pointer
-//     (no 64-bit address arithmetic per column), and a gathered ancestor touches one tile instead of D pages.
+//   * ROW-MAJOR layout, the reference's own (n, d) `value` array: particle i is one contiguous row of D floats
+//     (160 B at D = 40).  All traffic between HBM and the SM is done by the TMA engine in whole rows: a window of
+//     consecutive rows, or -- when the ancestors of 32 outputs are scattered -- one 160-byte bulk copy per ancestor,
+//     local or over NVLink alike; results leave through a bulk store of 16 finished rows.  (The first version of this
+//     round used 32-particle AoSoA tiles: a scattered ancestor then costs D sectors of 32 B, 8x its size -- with the
+//     collapsed weights of config C3 about 3 % of the outputs descend from such scattered light particles, 25 % of the
+//     population read for them, and over NVLink that dominated the sharded step.)
 //   * A particle PAIR (2m, 2m+1) is spread over FOUR lanes, D/4 coordinates each: 3*D/4 packed registers of RK4 state
 //     per thread instead of 3*D (<= 64 registers, 32 warps per SM).  The cyclic stencil needs three neighbour values per
 //     stage; they come from the adjacent lanes by warp shuffle.
@@ -111,28 +115,30 @@ struct L96Args {
     f2 nir2, zmean2;                                 // (-1/r_std, -1/r_std), (initial mean, initial mean)
     float forcing, h, ir, lik_const, zmean, bm_k1;   // zmean: initial mean; bm_k1: folded Box-Muller scale
     int substeps;
-    const float* x_in; float* x_out; int64_t n;
+    const float* x_in; float* x_out; int64_t n;      // (n, D) row-major
     const int32_t* anc; const float* y; float* lw;
     int64_t gid0;
     const float* x_peers[MB_MAX_WORLD]; int64_t n_local; int world; int sharded; int rank;
-    const float* import_local; int import_stride;    // state rows shipped by the resampler for remote ancestors (or NULL)
     PfTail tail;
 };
 
-// Staging of the source window (north_star (3): TMA-staged ancestor gather).  A warp advances one 32-particle OUTPUT
-// tile per iteration.  The ancestors of 32 consecutive outputs of a sorted-uniform resampler (or the tile itself when no
-// resampling happens) lie in a window of one or two SOURCE tiles of D*128 contiguous bytes each: lane 0 fetches the
-// window with cp.async.bulk (SASS UBLKCP; completion counted on the warp's mbarrier) -- one instruction per tile, no
-// destination registers, no scoreboard -- and the copy for tile k+1 is issued as soon as tile k has been read into
-// registers, so it lands while tile k is being integrated.  ncu (round 2, direct LDG version): 28 % of the warp time sat
-// in the 12 % of instructions that wait for anc[i] and then for x[anc[i]].  A window wider than L96_WIN tiles, or one
-// that straddles two GPUs' shards, falls back to per-lane loads.
-#define L96_WIN 2
+// Staging (north_star (3): TMA-staged ancestor gather).  A warp advances 32 OUTPUT particles per iteration, in two halves
+// of 16 (8 particle pairs x 4 lanes).  Their source rows are fetched into the warp's shared-memory window by the TMA
+// engine (cp.async.bulk -> SASS UBLKCP, completion counted on the warp's mbarrier; no destination registers, no
+// scoreboard), one iteration ahead, so the copy lands while the previous 32 particles are being integrated:
+//   WINDOW  the 32 sources span at most L96_ROWS consecutive rows (no resampling; flat weights; a run of outputs that
+//           descend from one heavy particle): ONE copy of the span.  A span that is already resident is not fetched
+//           again -- with collapsed weights a heavy ancestor is read once per run of outputs, not once per output.
+//   ROWS    scattered sources (the light tail of a collapsed population; ancestors on several GPUs): every lane copies
+//           its own ancestor's row, D*4 contiguous bytes, from whichever GPU owns it.
+// Finished rows are collected in shared memory and leave with one bulk store per 16 particles.
+#define L96_ROWS 64
 
 template <int D, int W>
 struct L96Smem {
-    static constexpr int TILE = D * 32;
-    static constexpr size_t stage_bytes = (size_t)W * L96_WIN * TILE * sizeof(float);
+    static constexpr int IN_FLOATS = L96_ROWS * D;                     // source window of one warp
+    static constexpr int OUT_FLOATS = 16 * D;                          // 16 finished rows of one warp
+    static constexpr size_t bytes = (size_t)W * (IN_FLOATS + OUT_FLOATS) * sizeof(float);
 };
 
 // OCC: resident blocks per SM the register allocation is tuned for; ROUNDS: Philox rounds (10 = production; the 7-round
@@ -141,11 +147,10 @@ template <int D, bool INIT, int OCC = 2, int ROUNDS = 10, int W = L96_WARPS>
 __global__ void __launch_bounds__(W * 32, OCC) pf_l96_kernel(L96Args a) {
     static_assert(D % 8 == 0, "the lane split needs an even number of coordinates per lane");
     constexpr int CPL = D / 4;                       // coordinates per lane
-    constexpr int TILE = D * 32;                     // floats per 32-particle tile
     mb_control* ctl = a.tail.ctl;
     if (!INIT && ctl->done) return;
     const bool resample = !INIT && ctl->resample != 0;
-    extern __shared__ __align__(128) float stage_all[];            // [W][L96_WIN][TILE]
+    extern __shared__ __align__(128) float stage_all[];            // [W][L96_ROWS + 16][D]
     __shared__ __align__(8) unsigned long long bars[W];
     __shared__ Lse3 smem[W];
     __shared__ f2 ysm[D];
@@ -162,38 +167,36 @@ __global__ void __launch_bounds__(W * 32, OCC) pf_l96_kernel(L96Args a) {
     const uint64_t seed = a.tail.seed;
     const L96Consts& c = a.c;
     const f2 nir = a.nir2, zmean = a.zmean2;
-    const int coff = (CPL * p) * 32;                 // this lane's first coordinate inside a tile
-    float* const mine = stage_all + (size_t)warp * L96_WIN * TILE;
+    float* const win = stage_all + (size_t)warp * (L96Smem<D, W>::IN_FLOATS + L96Smem<D, W>::OUT_FLOATS);
+    float* const outb = win + L96Smem<D, W>::IN_FLOATS;
+    const uint32_t win_a = smem_u32(win), outb_a = smem_u32(outb);
     const int64_t gid0 = a.gid0;
 
     float am = -INFINITY;                            // per-thread online (max, sum, sumsq); lanes with p != 0 stay empty
     f2 as1 = f2_pack(0.f, 0.f), as2 = as1;           // packed fp32 partial sums (<= a few thousand terms per thread)
-    const int64_t ntiles = (a.n + 31) >> 5;
+    const int64_t ntiles = (a.n + 31) >> 5;          // groups of 32 outputs
     const int64_t stride = (int64_t)gridDim.x * W;
 
-    // descriptor of a tile's source window, warp-uniform except `src` (this lane's source particle, owner-relative):
-    //   mode 0: staged, window = tiles [t0, t0 + nt) of `base` (2: already resident in the buffer, which starts at
-    //   tile t0);  mode 1: direct loads from `base` (per lane)
-    struct Win { int64_t src; const float* base; int64_t t0; int mode, nt, imp; };
+    // source of the 32 outputs of a group: `src` = this lane's source row (owner-relative), `base` = the owner's buffer
+    // (per lane); warp-uniform: mode 0 = WINDOW [r0, r0 + nr) of the (common) base, 2 = the same but already resident
+    // (the buffer starts at row r0), 1 = ROWS (lane l's row sits in slot l)
+    struct Win { int64_t src; const float* base; int64_t r0; int mode, nr; };
     auto describe = [&](int64_t tile) -> Win {
         Win w;
         const int64_t i = tile * 32 + lane;
-        w.base = a.x_in; w.mode = 0; w.imp = 0;
-        int64_t s_ = i;                              // not resampling / beyond n: the particle's own slot
+        w.base = a.x_in; w.mode = 0;
+        int64_t s_ = i;                              // not resampling / beyond n: the particle's own row
         if (resample && i < a.n) {
             s_ = (int64_t)__ldg(a.anc + i);          // GLOBAL id of the ancestor
-            if (a.sharded) {                         // owner-relative index + the owner's (peer-mapped) buffer
+            if (a.sharded) {                         // owner-relative row + the owner's (peer-mapped) buffer
                 const int o = (int)(s_ / a.n_local);
-                // the resampler of the owning rank shipped the state with the index (tag = this step): read it locally
-                if (o != a.rank && a.import_stride > 0 &&
-                    reinterpret_cast<const int*>(a.import_local + i * a.import_stride)[D] == (int)a.tail.t) w.imp = 1;
                 s_ -= (int64_t)o * a.n_local;
                 w.base = peers[o];
             }
         }
         w.src = s_;
-        int64_t lo = w.imp ? INT64_MAX : s_, hi = w.imp ? INT64_MIN : s_;     // imported lanes need no window
-        unsigned long long b0 = w.imp ? ~0ull : (unsigned long long)w.base, b1 = w.imp ? 0ull : (unsigned long long)w.base;
+        int64_t lo = s_, hi = s_;
+        unsigned long long b0 = (unsigned long long)w.base, b1 = b0;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             lo = min(lo, (int64_t)__shfl_xor_sync(MB_FULL, lo, o));
@@ -201,30 +204,32 @@ __global__ void __launch_bounds__(W * 32, OCC) pf_l96_kernel(L96Args a) {
             b0 = min(b0, (unsigned long long)__shfl_xor_sync(MB_FULL, b0, o));
             b1 = max(b1, (unsigned long long)__shfl_xor_sync(MB_FULL, b1, o));
         }
-        if (hi < lo) { w.mode = 3; w.t0 = 0; w.nt = 0; return w; }     // every lane imports: nothing to stage
-        if (w.imp) w.base = reinterpret_cast<const float*>(b0);        // keep `base` warp-uniform for the staged window
-        w.t0 = lo >> 5;
-        w.nt = (int)((hi >> 5) - w.t0) + 1;
-        if (w.nt > L96_WIN || b0 != b1) w.mode = 1;                    // wide window, or ancestors on two GPUs
+        w.r0 = lo;
+        w.nr = (int)min(hi - lo + 1, (int64_t)(L96_ROWS + 1));
+        if (w.nr > L96_ROWS || b0 != b1) w.mode = 1;                   // scattered sources, or ancestors on several GPUs
         return w;
     };
-    // what the warp's staging buffer holds: a window that is already resident is NOT fetched again.  With collapsed
-    // weights (config C3 at d = 40: ESS of a few particles) long runs of output tiles descend from the same source tile,
-    // which is then read once per run instead of once per output tile -- and once over NVLink instead of n_local / 32
-    // times when it lives on another GPU.
-    const float* buf_base = nullptr;
-    int64_t buf_t0 = 0;
-    int buf_nt = 0;
-    auto fetch = [&](Win& w) {                                         // warp-uniform decision, lane 0 issues the copies
-        if (w.mode != 0) return;
-        if (w.base == buf_base && w.t0 >= buf_t0 && w.t0 + w.nt <= buf_t0 + buf_nt) { w.t0 = buf_t0; w.mode = 2; return; }
-        buf_base = w.base; buf_t0 = w.t0; buf_nt = w.nt;
-        if (lane != 0) return;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"((uint32_t)(w.nt * TILE * 4)) : "memory");
-        for (int q = 0; q < w.nt; ++q)
+    const float* buf_base = nullptr;                                   // what the window holds (WINDOW mode)
+    int64_t buf_r0 = 0;
+    int buf_nr = 0;
+    auto fetch = [&](Win& w) {
+        if (w.mode == 0) {
+            if (w.base == buf_base && w.r0 >= buf_r0 && w.r0 + w.nr <= buf_r0 + buf_nr) { w.r0 = buf_r0; w.mode = 2; return; }
+            buf_base = w.base; buf_r0 = w.r0; buf_nr = w.nr;
+            if (lane == 0) {
+                const uint32_t bytes = (uint32_t)(w.nr * D * 4);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(win_a), "l"(w.base + w.r0 * D), "r"(bytes), "r"(bar_a) : "memory");
+            }
+        } else {
+            buf_base = nullptr;                                        // the window no longer holds a span
+            if (lane == 0)
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"((uint32_t)(32 * D * 4)) : "memory");
+            __syncwarp();
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(smem_u32(mine + (size_t)q * TILE)), "l"(w.base + (w.t0 + q) * TILE), "r"((uint32_t)(TILE * 4)), "r"(bar_a)
-                         : "memory");
+                         ::"r"(win_a + (uint32_t)(lane * D * 4)), "l"(w.base + w.src * D), "r"((uint32_t)(D * 4)), "r"(bar_a) : "memory");
+        }
     };
 
     int64_t tile = (int64_t)blockIdx.x * W + warp;
@@ -233,8 +238,8 @@ __global__ void __launch_bounds__(W * 32, OCC) pf_l96_kernel(L96Args a) {
     if (!INIT && tile < ntiles) { cur = describe(tile); fetch(cur); }
     for (; tile < ntiles; tile += stride) {
         const bool more = tile + stride < ntiles;
-        if (!INIT && more) nxtw = describe(tile + stride);             // ancestors of the next tile: loaded a tile ahead
-        if (!INIT && cur.mode == 0) {
+        if (!INIT && more) nxtw = describe(tile + stride);             // ancestors of the next group: loaded a group ahead
+        if (!INIT && cur.mode != 2) {
             uint32_t done = 0;
             while (!done)
                 asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
@@ -248,40 +253,16 @@ __global__ void __launch_bounds__(W * 32, OCC) pf_l96_kernel(L96Args a) {
             f2 x[CPL];
             if (!INIT) {
                 const int lP = sub * 16 + 2 * g;
-                const int64_t sP = __shfl_sync(MB_FULL, cur.src, lP), sQ = __shfl_sync(MB_FULL, cur.src, lP + 1);
-                const int impP = __shfl_sync(MB_FULL, cur.imp, lP), impQ = __shfl_sync(MB_FULL, cur.imp, lP + 1);
-                unsigned long long uP = 0, uQ = 0;                     // per-lane source buffers of a direct-load tile: the
-                if (cur.mode == 1) {                                   // shuffles stay outside the lane-divergent branches
-                    uP = __shfl_sync(MB_FULL, (unsigned long long)cur.base, lP);
-                    uQ = __shfl_sync(MB_FULL, (unsigned long long)cur.base, lP + 1);
+                int rowP = lP, rowQ = lP + 1;                          // ROWS mode: the slot is the lane that fetched it
+                if (cur.mode != 1) {
+                    rowP = (int)(__shfl_sync(MB_FULL, cur.src, lP) - cur.r0);
+                    rowQ = (int)(__shfl_sync(MB_FULL, cur.src, lP + 1) - cur.r0);
                 }
-                if ((impP | impQ) == 0) {
-                    if (cur.mode != 1) {
-                        const float* bP = mine + (sP - (cur.t0 << 5) >> 5) * TILE + coff + (int)(sP & 31);
-                        const float* bQ = mine + (sQ - (cur.t0 << 5) >> 5) * TILE + coff + (int)(sQ & 31);
+                const float* bP = win + rowP * D + CPL * p;
+                const float* bQ = win + rowQ * D + CPL * p;
 #pragma unroll
-                        for (int r = 0; r < CPL; ++r) x[r] = f2_pack(bP[r * 32], bQ[r * 32]);
-                    } else {
-                        const float* bP = reinterpret_cast<const float*>(uP) + (sP >> 5) * TILE + coff + (int)(sP & 31);
-                        const float* bQ = reinterpret_cast<const float*>(uQ) + (sQ >> 5) * TILE + coff + (int)(sQ & 31);
-#pragma unroll
-                        for (int r = 0; r < CPL; ++r) x[r] = f2_pack(__ldg(bP + r * 32), __ldg(bQ + r * 32));
-                    }
-                } else {
-                    // at least one particle of the pair was shipped by the resampler of the rank that owns its ancestor:
-                    // its state is a contiguous row of this rank's import buffer (coordinate stride 1 instead of 32)
-                    const float* bP; const float* bQ;
-                    int stP = 32, stQ = 32;
-                    if (impP) { bP = a.import_local + (tile * 32 + lP) * a.import_stride + CPL * p; stP = 1; }
-                    else if (cur.mode != 1) bP = mine + (sP - (cur.t0 << 5) >> 5) * TILE + coff + (int)(sP & 31);
-                    else bP = reinterpret_cast<const float*>(uP) + (sP >> 5) * TILE + coff + (int)(sP & 31);
-                    if (impQ) { bQ = a.import_local + (tile * 32 + lP + 1) * a.import_stride + CPL * p; stQ = 1; }
-                    else if (cur.mode != 1) bQ = mine + (sQ - (cur.t0 << 5) >> 5) * TILE + coff + (int)(sQ & 31);
-                    else bQ = reinterpret_cast<const float*>(uQ) + (sQ >> 5) * TILE + coff + (int)(sQ & 31);
-#pragma unroll
-                    for (int r = 0; r < CPL; ++r) x[r] = f2_pack(bP[r * stP], bQ[r * stQ]);
-                }
-                if (sub == 1) {                                        // the window is in registers: refill the buffer
+                for (int r = 0; r < CPL; ++r) x[r] = f2_pack(bP[r], bQ[r]);
+                if (sub == 1) {                                        // the window is in registers: refill it
                     __syncwarp();
                     if (more) fetch(nxtw);
                 }
@@ -308,9 +289,30 @@ __global__ void __launch_bounds__(W * 32, OCC) pf_l96_kernel(L96Args a) {
             }
             quad = f2_add(quad, __shfl_xor_sync(MB_FULL, quad, 1));
             quad = f2_add(quad, __shfl_xor_sync(MB_FULL, quad, 2));
-            float* xo = a.x_out + tile * TILE + coff + (sub * 16 + 2 * g);
+            // finished rows -> shared memory -> one bulk store of 16 rows.  The previous store of this buffer (one half
+            // group ago) must have READ it before it is overwritten.
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncwarp();
+            {
+                float* oP = outb + (2 * g) * D + CPL * p;
+                float* oQ = oP + D;
 #pragma unroll
-            for (int r = 0; r < CPL; ++r) { float lo, hi; f2_unpack(x[r], lo, hi); *reinterpret_cast<float2*>(xo + r * 32) = make_float2(lo, hi); }
+                for (int r = 0; r < CPL; r += 2) {
+                    float l0, h0, l1, h1;
+                    f2_unpack(x[r], l0, h0);
+                    f2_unpack(x[r + 1], l1, h1);
+                    *reinterpret_cast<float2*>(oP + r) = make_float2(l0, l1);
+                    *reinterpret_cast<float2*>(oQ + r) = make_float2(h0, h1);
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the TMA engine
+            __syncwarp();
+            if (lane == 0) {
+                const int64_t row0 = tile * 32 + sub * 16;
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                             ::"l"(a.x_out + row0 * D), "r"(outb_a), "r"((uint32_t)(16 * D * 4)) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
             if (p == 0) {
                 float qP, qQ;
                 f2_unpack(quad, qP, qQ);
@@ -334,6 +336,7 @@ __global__ void __launch_bounds__(W * 32, OCC) pf_l96_kernel(L96Args a) {
         }
         cur = nxtw;
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the last rows have left shared memory
     float s1l, s1h, s2l, s2h;
     f2_unpack(as1, s1l, s1h);
     f2_unpack(as2, s2l, s2h);
@@ -343,9 +346,9 @@ __global__ void __launch_bounds__(W * 32, OCC) pf_l96_kernel(L96Args a) {
 
 template <int D, bool INIT, int OCC, int ROUNDS, int W = L96_WARPS>
 static int l96_launch(mb_ctx* ctx, const L96Args& a, cudaStream_t st) {
-    const size_t smem = INIT ? 0 : L96Smem<D, W>::stage_bytes;
+    const size_t smem = L96Smem<D, W>::bytes;
     static bool configured = false;                                    // per instantiation
-    if (!configured && smem > 0) {
+    if (!configured) {
         MB_CUDA(cudaFuncSetAttribute(pf_l96_kernel<D, INIT, OCC, ROUNDS, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
@@ -375,9 +378,6 @@ static int l96_dispatch(mb_ctx* ctx, const mb_ssm* ssm, L96Args& a, bool init, c
     if (!init && ssm->dim == 40 && variant != 20) {
         if (variant == 10) return l96_launch<40, false, 1, 10>(ctx, a, st);
         if (variant == 27) return l96_launch<40, false, 2, 7>(ctx, a, st);
-        if (variant == 36) return l96_launch<40, false, 3, 10, 6>(ctx, a, st);     // 3 blocks of 6 warps
-        if (variant == 54) return l96_launch<40, false, 5, 10, 4>(ctx, a, st);     // 5 blocks of 4 warps
-        if (variant == 44) return l96_launch<40, false, 4, 10, 4>(ctx, a, st);     // 4 blocks of 4 warps
         mb_set_error("pf_l96: unknown MB_L96_VARIANT %d", variant);
         return MB_ERR_ARG;
     }
@@ -418,47 +418,42 @@ extern "C" int mb_pf_l96_step(mb_ctx* ctx, const mb_ssm* ssm, const float* x_in,
     if (sh && sh->world > 1) {
         a.sharded = 1; a.n_local = sh->n_local; a.world = sh->world; a.rank = sh->rank;
         for (int r = 0; r < sh->world; ++r) a.x_peers[r] = sh->x_peers[r];
-        if (sh->import_stride > 0 && sh->import_peers[sh->rank]) {
-            MB_REQUIRE(sh->state_dim == ssm->dim, "mb_pf_l96_step: import rows must hold the model's state dimension");
-            a.import_local = sh->import_peers[sh->rank]; a.import_stride = sh->import_stride;
-        }
     }
     if (comm) { a.tail.comm = *mb_comm_dev(comm); a.tail.has_comm = a.tail.comm.world > 1; }
     return l96_dispatch(ctx, ssm, a, false, mb_s(stream));
 }
 
 // ------------------------------------------------------------------------------------------------
-// Weighted mean / variance of every coordinate of a TILED population under weights exp(lw - ctl->wmax) / s1
+// Weighted mean / variance of every coordinate of a ROW-MAJOR (n, d) population under weights exp(lw - ctl->wmax) / s1
 // (diagnostics of the filter: the per-step moments returned instead of the reference's stacked (T, n, d) history,
-// ssm/filtering.py:317-322).  One warp per 32-particle tile, one lane per coordinate (two when D > 32); particles whose
-// weight underflows fp32 relative to the maximum (exp(lw - wmax) < 2^-50) are skipped together with their state,
+// ssm/filtering.py:317-322).  One warp per 32 particles, one lane per coordinate (two when D > 32); particles whose
+// weight underflows fp32 relative to the maximum (exp(lw - wmax) < 2^-50) are skipped together with their row,
 // so a collapsed population costs 4 B per particle instead of 4 (D + 1).
 #define TM_THREADS 256
 __global__ void __launch_bounds__(TM_THREADS)
-tiled_moments_kernel(const float* __restrict__ x, int64_t n, int d, const float* __restrict__ lw, const mb_control* ctl,
-                     const float* __restrict__ shift, double* partials /*[gridDim.x][1 + 2 d]*/) {
+rows_moments_kernel(const float* __restrict__ x, int64_t n, int d, const float* __restrict__ lw, const mb_control* ctl,
+                    const float* __restrict__ shift, double* partials /*[gridDim.x][1 + 2 d]*/) {
     extern __shared__ double sm[];                   // [warps][1 + 2 d]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const float wmax = (float)ctl->wmax;
-    const int tile_f = d * 32;
     const int c0 = lane, c1 = lane + 32;
     // shifts (numerical conditioning of the second moment): the caller's, or particle 0 of this population
-    const float sh0 = (c0 < d) ? (shift ? shift[c0] : x[c0 * 32]) : 0.f, sh1 = (c1 < d) ? (shift ? shift[c1] : x[c1 * 32]) : 0.f;
+    const float sh0 = (c0 < d) ? (shift ? shift[c0] : x[c0]) : 0.f, sh1 = (c1 < d) ? (shift ? shift[c1] : x[c1]) : 0.f;
     double s0 = 0.0, a0 = 0.0, b0 = 0.0, a1 = 0.0, b1 = 0.0;
-    const int64_t ntiles = (n + 31) >> 5;
-    for (int64_t tile = (int64_t)blockIdx.x * nw + warp; tile < ntiles; tile += (int64_t)gridDim.x * nw) {
-        const int64_t i = tile * 32 + lane;
+    const int64_t ngroups = (n + 31) >> 5;
+    for (int64_t grp = (int64_t)blockIdx.x * nw + warp; grp < ngroups; grp += (int64_t)gridDim.x * nw) {
+        const int64_t i = grp * 32 + lane;
         float e = 0.f;
         if (i < n) { const float dl = lw[i] - wmax; e = (dl > -34.6f || dl != dl) ? __expf(dl) : 0.f; }
         unsigned mask = __ballot_sync(MB_FULL, e != 0.f);
-        const float* xt = x + tile * tile_f;
         while (mask) {
             const int j = __ffs(mask) - 1;
             mask &= mask - 1;
             const double ej = (double)__shfl_sync(MB_FULL, e, j);
+            const float* row = x + (grp * 32 + j) * d;
             s0 += ej;
-            if (c0 < d) { const double v = (double)(xt[c0 * 32 + j] - sh0); a0 += ej * v; b0 += ej * v * v; }
-            if (c1 < d) { const double v = (double)(xt[c1 * 32 + j] - sh1); a1 += ej * v; b1 += ej * v * v; }
+            if (c0 < d) { const double v = (double)(row[c0] - sh0); a0 += ej * v; b0 += ej * v * v; }
+            if (c1 < d) { const double v = (double)(row[c1] - sh1); a1 += ej * v; b1 += ej * v * v; }
         }
     }
     double* mine = sm + (size_t)warp * (1 + 2 * d);
@@ -473,8 +468,8 @@ tiled_moments_kernel(const float* __restrict__ x, int64_t n, int d, const float*
     }
 }
 
-__global__ void tiled_moments_finish_kernel(const float* __restrict__ x, int d, const double* partials, int nblocks,
-                                            double* mean, double* var) {
+__global__ void rows_moments_finish_kernel(const float* __restrict__ x, int d, const double* partials, int nblocks,
+                                           double* mean, double* var) {
     const int col = blockIdx.x * blockDim.x + threadIdx.x;
     if (col >= d) return;
     double s0 = 0.0, s1 = 0.0, s2 = 0.0;
@@ -483,13 +478,13 @@ __global__ void tiled_moments_finish_kernel(const float* __restrict__ x, int d, 
         s0 += p[0]; s1 += p[1 + col]; s2 += p[1 + d + col];
     }
     const double m = s1 / s0;
-    mean[col] = m + (double)x[col * 32];
+    mean[col] = m + (double)x[col];
     if (var) var[col] = s2 / s0 - m * m;
 }
 
 // raw sums of one shard: sums[0] = sum e, sums[1 + k] = sum e (x_k - shift_k), sums[1 + d + k] = sum e (x_k - shift_k)^2
 // with e = exp(lw - ctl->wmax) (ctl->wmax is the GLOBAL maximum of a sharded population), blocks merged in fixed order
-__global__ void tiled_moment_sums_finish_kernel(int d, const double* partials, int nblocks, double* sums) {
+__global__ void rows_moment_sums_finish_kernel(int d, const double* partials, int nblocks, double* sums) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= 1 + 2 * d) return;
     double acc = 0.0;
@@ -497,123 +492,134 @@ __global__ void tiled_moment_sums_finish_kernel(int d, const double* partials, i
     sums[k] = acc;
 }
 
-extern "C" int mb_weighted_moment_sums_tiled(mb_ctx* ctx, const float* x, int64_t n, int d, const float* lw,
-                                             const mb_control* ctl, const float* shift, double* sums, mb_stream_t stream) {
-    MB_REQUIRE(ctx && x && lw && ctl && shift && sums && n > 0 && d > 0 && d <= 64,
-               "mb_weighted_moment_sums_tiled: bad arguments (d <= 64, shift required)");
-    const int64_t ntiles = (n + 31) >> 5;
-    int64_t grid = (ntiles + (TM_THREADS / 32) - 1) / (TM_THREADS / 32);
+static int rows_moments_launch(mb_ctx* ctx, const float* x, int64_t n, int d, const float* lw, const mb_control* ctl,
+                               const float* shift, cudaStream_t st, int64_t* grid_out) {
+    const int64_t ngroups = (n + 31) >> 5;
+    int64_t grid = (ngroups + (TM_THREADS / 32) - 1) / (TM_THREADS / 32);
     if (grid > (int64_t)ctx->sms * 8) grid = (int64_t)ctx->sms * 8;
     const size_t bytes = (size_t)grid * (1 + 2 * d) * sizeof(double);
     if (mb_ensure_scratch(ctx, bytes) != MB_OK) return MB_ERR_CUDA;
-    cudaStream_t st = mb_s(stream);
-    tiled_moments_kernel<<<(unsigned)grid, TM_THREADS, (TM_THREADS / 32) * (1 + 2 * d) * sizeof(double), st>>>(
+    rows_moments_kernel<<<(unsigned)grid, TM_THREADS, (TM_THREADS / 32) * (1 + 2 * d) * sizeof(double), st>>>(
         x, n, d, lw, ctl, shift, (double*)ctx->scratch);
     MB_CHECK_LAUNCH();
-    tiled_moment_sums_finish_kernel<<<(1 + 2 * d + 63) / 64, 64, 0, st>>>(d, (const double*)ctx->scratch, (int)grid, sums);
+    *grid_out = grid;
+    return MB_OK;
+}
+
+extern "C" int mb_weighted_moment_sums_rows(mb_ctx* ctx, const float* x, int64_t n, int d, const float* lw,
+                                            const mb_control* ctl, const float* shift, double* sums, mb_stream_t stream) {
+    MB_REQUIRE(ctx && x && lw && ctl && shift && sums && n > 0 && d > 0 && d <= 64,
+               "mb_weighted_moment_sums_rows: bad arguments (d <= 64, shift required)");
+    int64_t grid;
+    cudaStream_t st = mb_s(stream);
+    int rc = rows_moments_launch(ctx, x, n, d, lw, ctl, shift, st, &grid);
+    if (rc != MB_OK) return rc;
+    rows_moment_sums_finish_kernel<<<(1 + 2 * d + 63) / 64, 64, 0, st>>>(d, (const double*)ctx->scratch, (int)grid, sums);
     MB_CHECK_LAUNCH();
     return MB_OK;
 }
 
-extern "C" int mb_weighted_moments_tiled(mb_ctx* ctx, const float* x, int64_t n, int d, const float* lw,
-                                         const mb_control* ctl, double* mean, double* var, mb_stream_t stream) {
-    MB_REQUIRE(ctx && x && lw && ctl && mean && n > 0 && d > 0 && d <= 64, "mb_weighted_moments_tiled: bad arguments (d <= 64)");
-    const int64_t ntiles = (n + 31) >> 5;
-    int64_t grid = (ntiles + (TM_THREADS / 32) - 1) / (TM_THREADS / 32);
-    if (grid > (int64_t)ctx->sms * 8) grid = (int64_t)ctx->sms * 8;
-    const size_t bytes = (size_t)grid * (1 + 2 * d) * sizeof(double);
-    if (mb_ensure_scratch(ctx, bytes) != MB_OK) return MB_ERR_CUDA;
+extern "C" int mb_weighted_moments_rows(mb_ctx* ctx, const float* x, int64_t n, int d, const float* lw,
+                                        const mb_control* ctl, double* mean, double* var, mb_stream_t stream) {
+    MB_REQUIRE(ctx && x && lw && ctl && mean && n > 0 && d > 0 && d <= 64, "mb_weighted_moments_rows: bad arguments (d <= 64)");
+    int64_t grid;
     cudaStream_t st = mb_s(stream);
-    tiled_moments_kernel<<<(unsigned)grid, TM_THREADS, (TM_THREADS / 32) * (1 + 2 * d) * sizeof(double), st>>>(
-        x, n, d, lw, ctl, nullptr, (double*)ctx->scratch);
-    MB_CHECK_LAUNCH();
-    tiled_moments_finish_kernel<<<(d + 63) / 64, 64, 0, st>>>(x, d, (const double*)ctx->scratch, (int)grid, mean, var);
+    int rc = rows_moments_launch(ctx, x, n, d, lw, ctl, nullptr, st, &grid);
+    if (rc != MB_OK) return rc;
+    rows_moments_finish_kernel<<<(d + 63) / 64, 64, 0, st>>>(x, d, (const double*)ctx->scratch, (int)grid, mean, var);
     MB_CHECK_LAUNCH();
     return MB_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
-// Gather of a TILED population by ancestor (cdict.__getitem__, core.py:46-56, as used by resample_particles,
-// ssm/filtering.py:202-217).  One warp per 32-output tile.  When the 32 ancestors fall into a window of at most
-// GT_WIN source tiles (always the case after sorted-uniform resampling) the window is STAGED in shared memory with
-// bulk asynchronous copies (cp.async.bulk -> SASS UBLKCP, completion on an mbarrier): one instruction per source
-// tile instead of D loads per particle, and the column reads become conflict-free shared-memory loads
-// (bank = ancestor & 31).  Otherwise the lanes read their ancestor's columns directly.
-#define GT_WARPS 4
-#define GT_WIN 3
+// Gather of a ROW-MAJOR population by ancestor (cdict.__getitem__, core.py:46-56, as used by resample_particles,
+// ssm/filtering.py:202-217): x_out[i, :] = x_in[anc[i], :].  One warp per 32 outputs, the same two TMA modes as the
+// step kernel: one bulk copy of the span of source rows when it is short (sorted ancestors), else one D*4-byte bulk
+// copy per ancestor; every lane then bulk-stores its row from the window.  staged == 0: plain per-element loads and stores
+// (comparison path of the tests and of scratch/c3_bench.py).
+#define GR_WARPS 4
+#define GR_ROWS 64
 
 template <int D>
-__global__ void __launch_bounds__(GT_WARPS * 32)
-gather_tiled_kernel(const int32_t* __restrict__ anc, int64_t n_out, const float* __restrict__ src, int64_t n_src,
-                    float* __restrict__ dst, int staged_ok) {
-    constexpr int TILE = D * 32;
-    extern __shared__ __align__(128) float stage[];                  // [GT_WARPS][GT_WIN][TILE]
-    __shared__ __align__(8) unsigned long long bar[GT_WARPS];
+__global__ void __launch_bounds__(GR_WARPS * 32)
+gather_rows_kernel(const int32_t* __restrict__ anc, int64_t n_out, const float* __restrict__ src, int64_t n_src,
+                   float* __restrict__ dst, int staged) {
+    extern __shared__ __align__(128) float stage[];                  // [GR_WARPS][GR_ROWS][D]
+    __shared__ __align__(8) unsigned long long bar[GR_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float* mine = stage + (size_t)warp * GT_WIN * TILE;
-    const uint32_t bar_a = smem_u32(&bar[warp]);
+    float* win = stage + (size_t)warp * GR_ROWS * D;
+    const uint32_t bar_a = smem_u32(&bar[warp]), win_a = smem_u32(win);
     if (lane == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncwarp();
     uint32_t phase = 0;
-    const int64_t ntiles = (n_out + 31) >> 5;
-    for (int64_t tile = (int64_t)blockIdx.x * GT_WARPS + warp; tile < ntiles; tile += (int64_t)gridDim.x * GT_WARPS) {
-        const int64_t i = tile * 32 + lane;
-        int64_t a = (i < n_out) ? (int64_t)anc[i] : -1;
-        int64_t amin = (a < 0) ? INT64_MAX : a, amax = a;
+    const int64_t ngroups = (n_out + 31) >> 5;
+    for (int64_t grp = (int64_t)blockIdx.x * GR_WARPS + warp; grp < ngroups; grp += (int64_t)gridDim.x * GR_WARPS) {
+        const int64_t i = grp * 32 + lane;
+        const int64_t a = (i < n_out) ? (int64_t)anc[i] : -1;
+        if (!staged) {
+            if (a >= 0) for (int k = 0; k < D; ++k) dst[i * D + k] = __ldg(src + a * D + k);
+            continue;
+        }
+        int64_t lo = (a < 0) ? INT64_MAX : a, hi = a;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
-            amin = min(amin, (int64_t)__shfl_xor_sync(MB_FULL, amin, o));
-            amax = max(amax, (int64_t)__shfl_xor_sync(MB_FULL, amax, o));
+            lo = min(lo, (int64_t)__shfl_xor_sync(MB_FULL, lo, o));
+            hi = max(hi, (int64_t)__shfl_xor_sync(MB_FULL, hi, o));
         }
-        if (amax < 0) continue;
-        const int64_t t0 = amin >> 5, t1 = amax >> 5;
-        float* out = dst + tile * TILE + lane;
-        if (staged_ok && t1 - t0 < GT_WIN) {
-            const int nt = (int)(t1 - t0) + 1;
+        if (hi < 0) continue;
+        const bool window = hi - lo < GR_ROWS;
+        const int nvalid = __popc(__ballot_sync(MB_FULL, a >= 0));
+        if (window) {
             if (lane == 0) {
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"((uint32_t)(nt * TILE * 4)) : "memory");
-                for (int q = 0; q < nt; ++q)
-                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                                 ::"r"(smem_u32(mine + (size_t)q * TILE)), "l"(src + (t0 + q) * TILE), "r"((uint32_t)(TILE * 4)), "r"(bar_a)
-                                 : "memory");
+                const uint32_t bytes = (uint32_t)((hi - lo + 1) * D * 4);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(win_a), "l"(src + lo * D), "r"(bytes), "r"(bar_a) : "memory");
             }
-            uint32_t done = 0;
-            while (!done)
-                asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                             : "=r"(done) : "r"(bar_a), "r"(phase) : "memory");
-            phase ^= 1;
-            if (a >= 0) {
-                const float* s = mine + (a - (t0 << 5) >> 5) * TILE + (a & 31);
-#pragma unroll
-                for (int k = 0; k < D; ++k) out[k * 32] = s[k * 32];
-            }
-            __syncwarp();                                            // the staging area is reused by the next tile
-        } else if (a >= 0) {
-            const float* s = src + (a >> 5) * TILE + (a & 31);
-#pragma unroll
-            for (int k = 0; k < D; ++k) out[k * 32] = __ldg(s + k * 32);
+        } else {
+            if (lane == 0)
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"((uint32_t)(nvalid * D * 4)) : "memory");
+            __syncwarp();
+            if (a >= 0)
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(win_a + (uint32_t)(lane * D * 4)), "l"(src + a * D), "r"((uint32_t)(D * 4)), "r"(bar_a) : "memory");
         }
+        uint32_t done = 0;
+        while (!done)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(done) : "r"(bar_a), "r"(phase) : "memory");
+        phase ^= 1;
+        // every lane stores its own ancestor's row straight from the window (no shuffle through registers)
+        if (a >= 0) {
+            const uint32_t row_a = win_a + (uint32_t)((window ? (int)(a - lo) : lane) * D * 4);
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                         ::"l"(dst + i * D), "r"(row_a), "r"((uint32_t)(D * 4)) : "memory");
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the window is refilled by the next group
+        __syncwarp();
     }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
-extern "C" int mb_gather_tiled(mb_ctx* ctx, const int32_t* anc, int64_t n_out, int d, const float* src_tiled,
-                               int64_t n_src, float* dst_tiled, int staged, mb_stream_t stream) {
-    MB_REQUIRE(ctx && anc && src_tiled && dst_tiled && n_out > 0 && n_src > 0 && src_tiled != dst_tiled,
-               "mb_gather_tiled: bad arguments");
-    const int64_t ntiles = (n_out + 31) >> 5;
-    int64_t grid = (ntiles + GT_WARPS - 1) / GT_WARPS;
-    if (grid > (int64_t)ctx->sms * 8) grid = (int64_t)ctx->sms * 8;
+extern "C" int mb_gather_rows(mb_ctx* ctx, const int32_t* anc, int64_t n_out, int d, const float* src_rows,
+                              int64_t n_src, float* dst_rows, int staged, mb_stream_t stream) {
+    MB_REQUIRE(ctx && anc && src_rows && dst_rows && n_out > 0 && n_src > 0 && src_rows != dst_rows,
+               "mb_gather_rows: bad arguments");
+    const int64_t ngroups = (n_out + 31) >> 5;
+    int64_t grid = (ngroups + GR_WARPS - 1) / GR_WARPS;
+    if (grid > (int64_t)ctx->sms * 4) grid = (int64_t)ctx->sms * 4;
     cudaStream_t st = mb_s(stream);
-#define GT_CASE(DD)                                                                                            \
+#define GR_CASE(DD)                                                                                            \
     if (d == DD) {                                                                                             \
-        const size_t smem = (size_t)GT_WARPS * GT_WIN * DD * 32 * sizeof(float);                               \
-        MB_CUDA(cudaFuncSetAttribute(gather_tiled_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        gather_tiled_kernel<DD><<<(unsigned)grid, GT_WARPS * 32, smem, st>>>(anc, n_out, src_tiled, n_src, dst_tiled, staged); \
+        const size_t smem = (size_t)GR_WARPS * GR_ROWS * DD * sizeof(float);                                   \
+        MB_CUDA(cudaFuncSetAttribute(gather_rows_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        gather_rows_kernel<DD><<<(unsigned)grid, GR_WARPS * 32, smem, st>>>(anc, n_out, src_rows, n_src, dst_rows, staged); \
         MB_CHECK_LAUNCH();                                                                                     \
         return MB_OK;                                                                                          \
     }
-    GT_CASE(8) GT_CASE(16) GT_CASE(40)
-    mb_set_error("mb_gather_tiled: unsupported dimension %d (compiled: 8, 16, 40)", d);
+    GR_CASE(8) GR_CASE(16) GR_CASE(40)
+    mb_set_error("mb_gather_rows: unsupported dimension %d (compiled: 8, 16, 40)", d);
     return MB_ERR_UNSUPPORTED;
 }

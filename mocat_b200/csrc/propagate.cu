@@ -400,7 +400,7 @@ __device__ __forceinline__ float pf_particle(const mb_ssm& m, float (&x)[D], con
         }
         return -(quad + m.lik_const);
     } else {
-        return 0.f;                                     // Lorenz-96 lives in pf_l96.cu (tiled layout, lane-split kernel)
+        return 0.f;                                     // Lorenz-96 lives in pf_l96.cu (row-major layout, lane-split kernel)
     }
 }
 
@@ -468,7 +468,7 @@ static int pf_dispatch(mb_ctx* ctx, PfArgs& a, cudaStream_t st) {
     const int d = a.ssm.dim;
 #define PF_LG(DD) if (a.ssm.kind == MB_SSM_LINEAR_GAUSSIAN && d == DD) { PF_LAUNCH(MB_SSM_LINEAR_GAUSSIAN, DD)<<<(unsigned)pf_grid(ctx, a.n, PF_THREADS(DD)), PF_THREADS(DD), 0, st>>>(a); MB_CHECK_LAUNCH(); return MB_OK; }
     PF_LG(1) PF_LG(2) PF_LG(3) PF_LG(4) PF_LG(5) PF_LG(6) PF_LG(8)
-    if (a.ssm.kind == MB_SSM_LORENZ96) { mb_set_error("pf: Lorenz-96 runs through mb_pf_l96_init / mb_pf_l96_step (tiled layout)"); return MB_ERR_UNSUPPORTED; }
+    if (a.ssm.kind == MB_SSM_LORENZ96) { mb_set_error("pf: Lorenz-96 runs through mb_pf_l96_init / mb_pf_l96_step (row-major layout)"); return MB_ERR_UNSUPPORTED; }
     mb_set_error("pf: unsupported ssm kind %d / dim %d (built-in device models only; no CPU fallback)", a.ssm.kind, d);
     return MB_ERR_UNSUPPORTED;
 }

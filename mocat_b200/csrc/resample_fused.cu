@@ -13,10 +13,9 @@
 //                                 (closed form, see rf_count), drops a head marker at output c_{j-1} for every particle
 //                                 with offspring, max-scans the markers in shared memory and stores the ancestors with
 //                                 coalesced 128 B writes -- into the ancestor array of the rank that OWNS the output
-//                                 (peer stores over NVLink).  When the output lives on another GPU and the caller
-//                                 provides an import buffer, the ancestor's STATE travels with the index (one
-//                                 contiguous row per output): the redistribution all-to-all of the north star, fused
-//                                 into the resampler -- the step kernel then finds the particle in its own HBM.
+//                                 (peer stores over NVLink; the step kernel then fetches the ancestor's row, one
+//                                 contiguous TMA copy, from whichever GPU owns it: the redistribution all-to-all of
+//                                 the north star is fused into the gather).
 //   pass C  rf_heavy_kernel       tiles with more than RF_INLINE outputs (collapsed weights: a handful of particles own
 //                                 all the offspring) are queued by pass B as records {tile, C before, C after}.  After
 //                                 a barrier every rank collects the records of ALL ranks and fills the part of each
@@ -59,9 +58,15 @@ struct RfHeavy {                                 // a source tile with more than
     unsigned T, pad;                             // global tile id: owner rank * ntiles + local tile
 };
 
+struct RfHeavyJob {                              // a heavy tile as seen by ONE rank: its share of the tile's outputs
+    u64 Cex;                                     // cumulative weight before the tile
+    u64 rot;                                     // work items of the jobs in front of this one (block rotation)
+    unsigned T, o_lo, o_hi, pad;                 // global tile id; output slots [o_lo, o_hi) of this rank
+};
+
 struct RfArgs {
     RfHeader* hdr; u64* prefix;                       // prefix[ntiles + 1]: exclusive tile prefix, last = shard total
-    RfHeavy* heavy; RfHeavy* gheavy;                  // own records [ntiles + 1]; records of all ranks [world (ntiles + 1)]
+    RfHeavy* heavy; RfHeavyJob* jobs;                 // own records [ntiles + 1]; this rank's jobs [world (ntiles + 1)]
     const float* in; int64_t n; int64_t ntiles;       // this shard's weights; ntiles tiles per shard
     int log_mode; float scale;                        // e = rint(w * scale), scale = 2^K
     const mb_control* ctl; int predicated;
@@ -71,8 +76,6 @@ struct RfArgs {
     int32_t* anc_peers[MB_MAX_WORLD];                 // ancestor array of every rank (peer mapped); [0] = anc for one shard
     const float* in_peers[MB_MAX_WORLD];              // weights of every rank (pass C reads the heavy tiles of any rank)
     const void* ws_peers[MB_MAX_WORLD];               // workspace of every rank (its heavy records)
-    // state import (tiled populations): ancestor state pushed with the index when the output lives on another rank
-    const float* x_own; float* import_peers[MB_MAX_WORLD]; int state_dim, import_stride;
 };
 
 __device__ __forceinline__ float rf_wmax(const RfArgs& a) {
@@ -258,8 +261,6 @@ __global__ void __launch_bounds__(RF_THREADS) rf_ancestors_kernel(RfArgs a) {
     }
     const int64_t gid0 = (int64_t)a.rank * a.n_local;     // global id of this shard's first particle
     const u64 offset = offs[a.rank];
-    const int import_tag = a.ctl ? a.ctl->iter + 1 : 0;   // the filter step these ancestors are for (pf_l96.cu checks it)
-    const int D = a.state_dim;
 
     for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
         u64 e[RF_ITEMS];
@@ -328,25 +329,13 @@ __global__ void __launch_bounds__(RF_THREADS) rf_ancestors_kernel(RfArgs a) {
             int r0 = 0;
             int64_t split = INT64_MAX;
             if (a.world > 1) { r0 = (int)((int64_t)chunk_lo / a.n_local); split = (int64_t)(r0 + 1) * a.n_local; }
-#pragma unroll 4
+#pragma unroll
             for (int q2 = 0; q2 < RF_CHUNK_ITEMS; ++q2) {
                 const unsigned sl = q2 * RF_THREADS + threadIdx.x;
                 if (sl >= cnt) continue;
                 const int64_t o = (int64_t)chunk_lo + sl;
                 const int r = (o < split) ? r0 : r0 + 1;
-                const int64_t ol = o - (int64_t)r * a.n_local;        // slot inside the owner's arrays
-                a.anc_peers[r][ol] = base + buf[sl];
-                if (r != a.rank && a.import_stride > 0) {             // the output lives on another GPU: ship the state too
-                    const int64_t jl = tile * RF_TILE + (buf[sl] - 1);
-                    const float* src = a.x_own + (jl >> 5) * ((int64_t)D * 32) + (jl & 31);
-                    float* dst = a.import_peers[r] + ol * a.import_stride;
-                    for (int k = 0; k < D; k += 4) {
-                        float4 v4;
-                        v4.x = src[(k + 0) * 32]; v4.y = src[(k + 1) * 32]; v4.z = src[(k + 2) * 32]; v4.w = src[(k + 3) * 32];
-                        *reinterpret_cast<float4*>(dst + k) = v4;
-                    }
-                    reinterpret_cast<int*>(dst)[D] = import_tag;
-                }
+                a.anc_peers[r][o - (int64_t)r * a.n_local] = base + buf[sl];   // slot inside the owner's array
             }
             __syncthreads();
         }
@@ -354,26 +343,43 @@ __global__ void __launch_bounds__(RF_THREADS) rf_ancestors_kernel(RfArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------ pass C
-// collect the heavy records of every rank (written by their pass B, complete after the caller's barrier) into the
-// local workspace, rank by rank
+// collect the heavy records of every rank (written by their pass B, complete after the caller's barrier) and turn them
+// into this rank's JOBS: the part of each heavy tile's output range that falls into the rank's own slots, with the
+// counts evaluated once here instead of by every block of pass C
 __global__ void __launch_bounds__(RF_THREADS) rf_gather_heavy_kernel(RfArgs a) {
     if (a.predicated && (a.ctl->done || !a.ctl->resample)) return;
     __shared__ unsigned cnt[MB_MAX_WORLD + 1];
-    if (threadIdx.x == 0) {
-        unsigned run = 0;
-        for (int q = 0; q < a.world; ++q) {
-            cnt[q] = run;
-            run += reinterpret_cast<const RfHeader*>(a.ws_peers[q])->heavy_count;
-        }
-        cnt[a.world] = run;
-        a.hdr->heavy_total = run;
-    }
+    __shared__ u64 offs[MB_MAX_WORLD];
+    __shared__ unsigned njobs;
+    const RfSys g = rf_grid_setup(a, offs);
+    if (threadIdx.x < a.world)
+        cnt[threadIdx.x + 1] = reinterpret_cast<const RfHeader*>(a.ws_peers[threadIdx.x])->heavy_count;   // peer reads in parallel
+    if (threadIdx.x == 0) { cnt[0] = 0; njobs = 0; }
     __syncthreads();
+    if (threadIdx.x == 0) for (int q = 0; q < a.world; ++q) cnt[q + 1] += cnt[q];
+    __syncthreads();
+    const int64_t o_begin = (int64_t)a.rank * a.n_local, o_end = o_begin + a.n;      // this rank's output slots
     const int64_t off_heavy = (int64_t)sizeof(RfHeader) + (int64_t)sizeof(u64) * (a.ntiles + 1);
     for (int q = 0; q < a.world; ++q) {
         const RfHeavy* src = reinterpret_cast<const RfHeavy*>(reinterpret_cast<const char*>(a.ws_peers[q]) + off_heavy);
         const unsigned hq = cnt[q + 1] - cnt[q];
-        for (unsigned i = threadIdx.x; i < hq; i += blockDim.x) a.gheavy[cnt[q] + i] = src[i];
+        for (unsigned i = threadIdx.x; i < hq; i += blockDim.x) {
+            const RfHeavy h = src[i];
+            const unsigned o_lo = max(rf_count(g, h.Cex), (unsigned)o_begin), o_hi = min(rf_count(g, h.Cin), (unsigned)o_end);
+            if (o_hi <= o_lo) continue;                   // none of this tile's offspring live here
+            RfHeavyJob j;
+            j.Cex = h.Cex; j.rot = 0; j.T = h.T; j.o_lo = o_lo; j.o_hi = o_hi; j.pad = 0;
+            a.jobs[atomicAdd(&njobs, 1u)] = j;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {                               // rotation offsets (the order of the jobs is irrelevant: every
+        u64 rot = 0;                                      // output slot is written exactly once, with an exact value)
+        for (unsigned i = 0; i < njobs; ++i) {
+            a.jobs[i].rot = rot;
+            rot += ((u64)(a.jobs[i].o_hi - a.jobs[i].o_lo) + RF_HEAVY_CHUNK - 1) / RF_HEAVY_CHUNK;
+        }
+        a.hdr->heavy_total = njobs;
     }
 }
 
@@ -386,18 +392,15 @@ __global__ void __launch_bounds__(RF_THREADS) rf_heavy_kernel(RfArgs a) {
     __shared__ u64 offs[MB_MAX_WORLD];
     const float wmax = rf_wmax(a);
     const RfSys g = rf_grid_setup(a, offs);
-    const int64_t o_begin = (int64_t)a.rank * a.n_local, o_end = o_begin + a.n;      // this rank's output slots
+    const int64_t o_begin = (int64_t)a.rank * a.n_local;
     int32_t* anc = a.anc_peers[a.world <= 1 ? 0 : a.rank];
     __syncthreads();
-    u64 rot = 0;                                          // rotating block assignment: work item q of entry e -> block (rot + q) % grid
     for (unsigned en = 0; en < H; ++en) {
-        const RfHeavy h = a.gheavy[en];
-        const unsigned c_lo = rf_count(g, h.Cex), c_hi = rf_count(g, h.Cin);
-        const unsigned o_lo = max(c_lo, (unsigned)o_begin), o_hi = min(c_hi, (unsigned)o_end);
-        if (o_hi <= o_lo) continue;                       // none of this tile's offspring live here (block-uniform)
+        const RfHeavyJob h = a.jobs[en];
+        const unsigned o_lo = h.o_lo, o_hi = h.o_hi;
         const u64 items = ((u64)(o_hi - o_lo) + RF_HEAVY_CHUNK - 1) / RF_HEAVY_CHUNK;
-        const u64 first = ((u64)blockIdx.x + gridDim.x - rot % gridDim.x) % gridDim.x;
-        rot += items;
+        // rotating block assignment: work item w of this job -> block (rot + w) % grid
+        const u64 first = ((u64)blockIdx.x + gridDim.x - h.rot % gridDim.x) % gridDim.x;
         if (first >= items) continue;                     // block-uniform
         const int q = (int)(h.T / (unsigned)a.ntiles);
         const int64_t tile = (int64_t)h.T - (int64_t)q * a.ntiles;
@@ -447,9 +450,10 @@ static int rf_scale_bits(int64_t n_total) {
 }
 
 extern "C" size_t mb_rs_workspace_bytes(int64_t n) {
-    // header | own tile prefix | own heavy records | heavy records of all ranks (MB_MAX_WORLD shards of n)
+    // header | own tile prefix | own heavy records | this rank's jobs on the heavy tiles of all ranks (MB_MAX_WORLD shards)
     const int64_t ntiles = (n + RF_TILE - 1) / RF_TILE;
-    return sizeof(RfHeader) + sizeof(u64) * (size_t)(ntiles + 1) + sizeof(RfHeavy) * (size_t)(ntiles + 1) * (1 + MB_MAX_WORLD);
+    return sizeof(RfHeader) + sizeof(u64) * (size_t)(ntiles + 1) + sizeof(RfHeavy) * (size_t)(ntiles + 1) +
+           sizeof(RfHeavyJob) * (size_t)(ntiles + 1) * MB_MAX_WORLD;
 }
 
 static void rf_fill(RfArgs& a, void* ws, const float* in, int64_t n, int64_t n_total, int log_mode, const mb_control* ctl,
@@ -458,7 +462,7 @@ static void rf_fill(RfArgs& a, void* ws, const float* in, int64_t n, int64_t n_t
     a.hdr = (RfHeader*)ws;
     a.prefix = (u64*)((char*)ws + sizeof(RfHeader));
     a.heavy = (RfHeavy*)(a.prefix + a.ntiles + 1);
-    a.gheavy = a.heavy + (a.ntiles + 1);
+    a.jobs = (RfHeavyJob*)(a.heavy + (a.ntiles + 1));
     a.in = in; a.n = n; a.n_total = n_total; a.log_mode = log_mode;
     a.scale = ldexpf(1.f, rf_scale_bits(n_total));
     a.ctl = ctl; a.predicated = (ctl && !force) ? 1 : 0;
@@ -488,12 +492,6 @@ static int rf_shard_args(RfArgs& a, void* ws, const float* in, int64_t n, int64_
         for (int r = 0; r < sh->world; ++r) {
             if (!sh->anc_peers[r] || !sh->lw_peers[r] || !sh->ws_peers[r]) { mb_set_error("%s: anc_peers / lw_peers / ws_peers missing", who); return MB_ERR_ARG; }
             a.anc_peers[r] = sh->anc_peers[r]; a.in_peers[r] = sh->lw_peers[r]; a.ws_peers[r] = sh->ws_peers[r];
-            a.import_peers[r] = sh->import_peers[r];
-        }
-        if (sh->import_stride > 0) {
-            if (!(sh->state_dim > 0 && sh->state_dim % 4 == 0 && sh->import_stride > sh->state_dim && sh->import_stride % 4 == 0 &&
-                  sh->x_peers[sh->rank])) { mb_set_error("%s: bad import description", who); return MB_ERR_ARG; }
-            a.x_own = sh->x_peers[sh->rank]; a.state_dim = sh->state_dim; a.import_stride = sh->import_stride;
         }
     } else if (n_total != n) {
         mb_set_error("%s: n_total != n needs a shard description", who);

@@ -368,9 +368,9 @@ class PFEngine(_Resampler):
         self.seed, self.gid0, self.resampling = int(seed), int(gid0), int(resampling)
         self.ess_threshold = float(ess_threshold)
         dev = _dev()
-        # Lorenz-96 runs on the TILED layout (32-particle tiles of d x 32 floats, csrc/pf_l96.cu); the small dense
-        # models keep plain SoA columns
-        self.tiled = int(ssm.kind) == _lib.SSM_LORENZ96
+        # Lorenz-96 runs on the reference's own ROW-MAJOR (n, d) layout (whole rows move through the TMA engine,
+        # csrc/pf_l96.cu); the small dense models keep SoA columns
+        self.rowmajor = int(ssm.kind) == _lib.SSM_LORENZ96
         self.xbuf = [self._alloc_x(dev) for _ in range(2)]
         self.cur = 0
         self._lw_full = torch.zeros(self.ld, dtype=torch.float32, device=dev)     # padded to a multiple of 32
@@ -380,11 +380,11 @@ class PFEngine(_Resampler):
         self.t = 0
 
     def _x_shape(self):
-        return (self.ld // 32, self.d, 32) if self.tiled else (self.d, self.ld)
+        return (self.ld, self.d) if self.rowmajor else (self.d, self.ld)
 
     def _alloc_x(self, dev):
-        # tiled layout: the init kernel writes every chunk the step kernels ever touch, no memset of 16 GB needed
-        return (torch.empty if self.tiled else torch.zeros)(self._x_shape(), dtype=torch.float32, device=dev)
+        # row-major layout: the init kernel writes every row the step kernels ever touch, no memset of 16 GB needed
+        return (torch.empty if self.rowmajor else torch.zeros)(self._x_shape(), dtype=torch.float32, device=dev)
 
     # -- engine pool: repeated filters of one configuration reuse the HBM buffers (2 x 16 GB at config C3) -------
     _POOL = {}
@@ -419,7 +419,7 @@ class PFEngine(_Resampler):
 
     def init(self, y0):
         """initiate_particles (ssm/filtering.py:173-193).  y0: device float32 (dim_obs,)"""
-        if self.tiled:
+        if self.rowmajor:
             self.L.call("mb_pf_l96_init", self.ctx, C.byref(self.ssm), ptr(self.x), self.n, self.n_total, ptr(y0),
                         ptr(self.lw), self.seed, self.gid0, self.ess_threshold, ptr(self.ctl.t), ptr(self.ctl.hist),
                         self._comm(), stream())
@@ -431,7 +431,7 @@ class PFEngine(_Resampler):
 
     def _step_kernel(self, y, st):
         src, dst = self.xbuf[self.cur], self.xbuf[self.cur ^ 1]
-        if self.tiled:
+        if self.rowmajor:
             self.L.call("mb_pf_l96_step", self.ctx, C.byref(self.ssm), ptr(src), ptr(dst), self.n, self.n_total,
                         ptr(self.anc), ptr(y), ptr(self.lw), self.seed, self.t, self.gid0, self.ess_threshold,
                         ptr(self.ctl.t), ptr(self.ctl.hist), self._shard_ref(), self._comm(), st)
@@ -449,16 +449,16 @@ class PFEngine(_Resampler):
         self._step_kernel(y, st)
 
     def values(self):
-        """(n, d) float32 device tensor of the current particle values (a copy for the tiled layout)"""
-        if self.tiled:
-            return self.x.permute(0, 2, 1).reshape(-1, self.d)[:self.n]
+        """(n, d) float32 device tensor view of the current particle values"""
+        if self.rowmajor:
+            return self.x[:self.n]
         return self.x[:, :self.n].t()
 
     def gather_current(self):
         """x <- x[anc] into the other buffer (resample_particles, ssm/filtering.py:202-217)"""
         src, dst = self.xbuf[self.cur], self.xbuf[self.cur ^ 1]
-        if self.tiled:
-            self.L.call("mb_gather_tiled", self.ctx, ptr(self.anc), self.n, self.d, ptr(src), self.n, ptr(dst), 1, stream())
+        if self.rowmajor:
+            self.L.call("mb_gather_rows", self.ctx, ptr(self.anc), self.n, self.d, ptr(src), self.n, ptr(dst), 1, stream())
         else:
             self.L.call("mb_gather_state", self.ctx, ptr(self.anc), self.n, self.d, ptr(src), self.ld, ptr(dst), self.ld,
                         stream())
@@ -467,19 +467,19 @@ class PFEngine(_Resampler):
     def moment_sums(self, shift, out=None):
         """un-normalised weighted sums of THIS shard, (1 + 2d,) float64: sum e, sum e (x - shift), sum e (x - shift)^2 with
         e = exp(lw - global max); the ranks' records add up to the moments of the whole population"""
-        if not self.tiled:
-            raise _lib.MocatB200Error("moment_sums: tiled (Lorenz-96) populations only")
+        if not self.rowmajor:
+            raise _lib.MocatB200Error("moment_sums: row-major (Lorenz-96) populations only")
         sums = out if out is not None else torch.empty(1 + 2 * self.d, dtype=torch.float64, device=self.x.device)
-        self.L.call("mb_weighted_moment_sums_tiled", self.ctx, ptr(self.x), self.n, self.d, ptr(self.lw), ptr(self.ctl.t),
+        self.L.call("mb_weighted_moment_sums_rows", self.ctx, ptr(self.x), self.n, self.d, ptr(self.lw), ptr(self.ctl.t),
                     ptr(shift), ptr(sums), stream())
         return sums
 
     def moments(self):
         """weighted mean / variance of every coordinate under the current weights (device float64 (d,) tensors)"""
-        if self.tiled:
+        if self.rowmajor:
             mean = torch.empty(self.d, dtype=torch.float64, device=self.x.device)
             var = torch.empty(self.d, dtype=torch.float64, device=self.x.device)
-            self.L.call("mb_weighted_moments_tiled", self.ctx, ptr(self.x), self.n, self.d, ptr(self.lw), ptr(self.ctl.t),
+            self.L.call("mb_weighted_moments_rows", self.ctx, ptr(self.x), self.n, self.d, ptr(self.lw), ptr(self.ctl.t),
                         ptr(mean), ptr(var), stream())
             return mean, var
         return weighted_moments(self.x, self.n, self.lw, self.ctl)

@@ -126,10 +126,7 @@ class ShardContext:
         self.L.call("mb_comm_allgather", self.comm, _lib.ptr(src), int(nd), _lib.ptr(dst), None, _lib.stream())
 
 
-IMPORT_PAD = 8          # floats appended to an import row: [state_dim] = step tag (int32), rest keeps rows 32-byte aligned
-
-
-def _make_shard(sc, n_local, x_peers, cdf_peers, totals, anc_peers, lw_peers, ws_peers, import_peers=None, state_dim=0):
+def _make_shard(sc, n_local, x_peers, cdf_peers, totals, anc_peers, lw_peers, ws_peers):
     sh = _lib.Shard()
     sh.rank, sh.world, sh.n_local, sh.n_total = sc.rank, sc.world, int(n_local), int(n_local) * sc.world
     for r in range(sc.world):
@@ -138,9 +135,6 @@ def _make_shard(sc, n_local, x_peers, cdf_peers, totals, anc_peers, lw_peers, ws
         sh.anc_peers[r] = anc_peers[r]
         sh.lw_peers[r] = lw_peers[r]
         sh.ws_peers[r] = ws_peers[r]
-        sh.import_peers[r] = import_peers[r] if import_peers is not None else None
-    sh.import_stride = (state_dim + IMPORT_PAD) if import_peers is not None else 0
-    sh.state_dim = int(state_dim)
     sh.totals = totals.data_ptr()
     return sh
 
@@ -148,9 +142,8 @@ def _make_shard(sc, n_local, x_peers, cdf_peers, totals, anc_peers, lw_peers, ws
 def _sharded_alloc(eng, sc):
     """IPC-shared buffers of a sharded engine: both particle buffers, the ancestor array (the fused systematic resampler
     writes an output's ancestor into the owning rank's array), the log-weights and the resampler workspace (every rank
-    fills its own share of the outputs of heavy source tiles, reading their weights from the owner), for tiled
-    populations the state import buffer (ancestor state shipped with the index when the output lives on another GPU)
-    and, for multinomial resampling, the rank-relative CDF and the strata histogram."""
+    fills its own share of the outputs of heavy source tiles, reading their weights from the owner) and, for
+    multinomial resampling, the rank-relative CDF and the strata histogram."""
     import torch
     shape = tuple(eng._x_shape()) if hasattr(eng, "_x_shape") else tuple(eng.xbuf[0].shape)
     xs = [sc.alloc_shared(shape, torch.float32) for _ in range(2)]
@@ -165,12 +158,6 @@ def _sharded_alloc(eng, sc):
     eng.rs_ws.zero_()
     eng.anc, anc_peers = sc.alloc_shared((eng.n,), torch.int32)
     eng._shared = [eng.xbuf[0], eng.xbuf[1], lw_full, eng.rs_ws, eng.anc]
-    import_peers, state_dim = None, 0
-    if getattr(eng, "tiled", False) and eng.resampling == _lib.RESAMPLE_SYSTEMATIC:
-        state_dim = eng.d
-        eng.import_buf, import_peers = sc.alloc_shared((eng.n, eng.d + IMPORT_PAD), torch.float32)
-        eng.import_buf.zero_()
-        eng._shared.append(eng.import_buf)
     cdf_peers = None
     if eng.resampling == _lib.RESAMPLE_MULTINOMIAL:
         eng.cdf, cdf_peers = sc.alloc_shared((eng.n,), torch.float64)
@@ -179,15 +166,14 @@ def _sharded_alloc(eng, sc):
         eng.hist_peers = (C.c_void_p * sc.world)(*hist_peers)
     eng.totals = torch.zeros(sc.world, dtype=torch.float64, device=sc.device)      # fp64 totals / uint64 bit patterns
     eng._barrier_out = torch.zeros(sc.world, dtype=torch.float64, device=sc.device)
-    eng.shards = [_make_shard(sc, eng.n, xs[k][1], cdf_peers, eng.totals, anc_peers, lw_peers, ws_peers, import_peers,
-                              state_dim) for k in range(2)]
+    eng.shards = [_make_shard(sc, eng.n, xs[k][1], cdf_peers, eng.totals, anc_peers, lw_peers, ws_peers) for k in range(2)]
 
 
 def _sharded_resample_kernels(eng, sc, st):
     """Every launch is predicated on the replicated control block.
     systematic : integer tile sums -> exchange of the 8-byte shard totals -> every rank scans ITS OWN source tiles and
-                 writes ancestors (and, for tiled populations, the ancestors' state) into the arrays of the ranks that
-                 own the outputs; tiles with collapsed weight are only recorded -> exchange (barrier) -> every rank
+                 writes the ancestors into the arrays of the ranks that own the outputs; tiles with collapsed weight are
+                 only recorded -> exchange (barrier) -> every rank
                  fills ITS OWN share of the heavy tiles' outputs, reading their weights from the owner -> exchange
                  (barrier) before the step kernel overwrites the weights a peer may still be reading.
     multinomial: scan (rank-relative, exact) + local strata histogram -> one exchange (weight totals; also the barrier
@@ -336,18 +322,13 @@ def ShardedPFEngine(sc, ssm, n_local, seed, ess_threshold=0.5, resampling=_lib.R
         def _alloc_x(self, dev):
             return None                                     # the IPC-shared buffers of _sharded_alloc replace them
 
-        def init(self, y0):
-            if getattr(self, "import_buf", None) is not None:
-                self.import_buf[:, self.d].zero_()          # step tags of an earlier run on this (pooled) engine
-            super().init(y0)
-
         def _comm(self):
             return sc.comm
 
         def close(self):
             """collective: release the IPC-shared buffers (they are not owned by torch)"""
             shared, self._shared = self._shared, []
-            self.xbuf, self.lw, self._lw_full, self.rs_ws, self.anc, self.import_buf = [None, None], None, None, None, None, None
+            self.xbuf, self.lw, self._lw_full, self.rs_ws, self.anc = [None, None], None, None, None, None
             sc.free_shared(shared)
 
         def _shard_ref(self):

@@ -222,7 +222,7 @@ def initiate_particles(ssm_scenario, particle_filter, n, random_key, y=None, t=N
 
 def resample_particles(particles, random_key=None, resample_full=True):
     """ssm/filtering.py:202-217: unconditional resampling of the latest population, log-weights reset to zero.
-    Runs the engine's resampler (ancestors) and a device gather (mb_gather_state / mb_gather_tiled); only the latest
+    Runs the engine's resampler (ancestors) and a device gather (mb_gather_state / mb_gather_rows); only the latest
     time slice lives on the device, so `resample_full` (re-indexing the stored trajectories) applies to the host copy."""
     torch = _torch()
     eng = _engine_of(particles)
@@ -325,8 +325,8 @@ def run_particle_filter_for_marginals(ssm_scenario, particle_filter, y, t, rando
     yd = torch.as_tensor(y, device="cuda")
     vals, lws = [], []
     sharded = _world()[1] > 1
-    if sharded and not eng.tiled:
-        moments = False                                   # per-shard moment sums exist for the tiled layout only
+    if sharded and not eng.rowmajor:
+        moments = False                                   # per-shard moment sums exist for the row-major layout only
     mom = torch.empty((T, 2, d), dtype=torch.float64, device="cuda") if moments and not sharded else None
     msum = torch.empty((T, 1 + 2 * d), dtype=torch.float64, device="cuda") if moments and sharded else None
 

@@ -69,9 +69,9 @@ rec = pf.ctl.read(); rec['resample'] = 1; pf.ctl.write(rec)
 report("pf_l96 step, gather by flat ancestors", timeit(sf), 8 * d + 12)
 # gather kernels
 src, dst = pf.xbuf[pf.cur], pf.xbuf[pf.cur ^ 1]
-report("gather_tiled staged (flat anc)", timeit(lambda: L.call("mb_gather_tiled", ctx, ptr(pf.anc), n, d, ptr(src), n, ptr(dst), 1, st)), 8 * d + 4)
-report("gather_tiled direct (flat anc)", timeit(lambda: L.call("mb_gather_tiled", ctx, ptr(pf.anc), n, d, ptr(src), n, ptr(dst), 0, st)), 8 * d + 4)
-report("weighted_moments_tiled (flat)", timeit(lambda: pf.moments()), 4 * d + 4)
+report("gather_rows staged (flat anc)", timeit(lambda: L.call("mb_gather_rows", ctx, ptr(pf.anc), n, d, ptr(src), n, ptr(dst), 1, st)), 8 * d + 4)
+report("gather_rows direct (flat anc)", timeit(lambda: L.call("mb_gather_rows", ctx, ptr(pf.anc), n, d, ptr(src), n, ptr(dst), 0, st)), 8 * d + 4)
+report("weighted_moments_rows (flat)", timeit(lambda: pf.moments()), 4 * d + 4)
 # full steps
 for thr, nm in ((2.0, "every step"),):
     ms = []

@@ -26,19 +26,24 @@ for t in range(6, 26):
     import ctypes as C
     L.call("mb_rs_ancestors", pf.ctx, ptr(pf.rs_ws), ptr(pf.lw), pf.n, pf.n_total, 1, ctl, 0, -1, ptr(pf.totals), C.byref(pf.shards[pf.cur]), ptr(pf.anc), st); m[3].record()
     L.call("mb_comm_allgather", sc.comm, ptr(pf.totals), 1, ptr(pf._barrier_out), ctl, st); m[4].record()
+    L.call("mb_rs_heavy", pf.ctx, ptr(pf.rs_ws), ptr(pf.lw), pf.n, pf.n_total, 1, ctl, 0, -1, ptr(pf.totals), C.byref(pf.shards[pf.cur]), ptr(pf.anc), st)
     L.call("mb_comm_allgather", sc.comm, ptr(pf.totals), 1, ptr(pf._barrier_out), ctl, st); m[5].record()
     pf._step_kernel(yd[t], st); m[6].record()
     rows.append(m)
 torch.cuda.synchronize()
-names = ["tile_sums", "exch1", "ancestors+heavy", "exch2", "exch3", "pf_step"]
+names = ["tile_sums", "exch1", "passB", "exch2", "passC+exch3", "pf_step", "imported", "remote"]
 med = [float(np.median([r[k].elapsed_time(r[k + 1]) for r in rows])) for k in range(6)]
 per_step = [[r[k].elapsed_time(r[k + 1]) for k in range(6)] for r in rows[:6]]
 out = [None] * world
+nimp = int((pf.anc < 0).sum().item())
+owner = pf.anc.to(torch.int64) // pf.n
+nrem = int((owner != rank).sum().item())
+med = med + [nimp, nrem]
 dist.all_gather_object(out, (rank, med, float(pf.ctl.read()['ess']), per_step))
 if rank == 0:
     print("n_total", n_total, "world", world, "thr", thr)
     for r, md, ess, ps in out:
-        print("rank %d: " % r + "  ".join("%s %.3f" % (nm, v) for nm, v in zip(names, md)) + "  | sum %.3f  ess %.2f" % (sum(md), ess))
+        print("rank %d: " % r + "  ".join("%s %.3f" % (nm, v) for nm, v in zip(names, md)) + "  | sum %.3f  ess %.2f" % (sum(md[:6]), ess))
     for k in range(6):
-        print("step", k, " anc+heavy per rank:", " ".join("%.3f" % o[3][k][2] for o in out), " exch2:", " ".join("%.3f" % o[3][k][3] for o in out), " pf:", " ".join("%.3f" % o[3][k][5] for o in out))
+        print("step", k, " passB per rank:", " ".join("%.3f" % o[3][k][2] for o in out), " passC+x3:", " ".join("%.3f" % o[3][k][4] for o in out), " pf:", " ".join("%.3f" % o[3][k][5] for o in out))
 dist.barrier(); dist.destroy_process_group()
