@@ -328,6 +328,22 @@ int mb_svgd_phi(mb_ctx* ctx, const float* X, const float* G, int n, int d, const
 int mb_pairdist_bandwidth(mb_ctx* ctx, const float* X, int n, int d, int mode /*0 median, 1 mean*/,
                           float* h, int variant /*0 exact fp32 SIMT, 1 tcgen05 (bf16 coordinates)*/,
                           mb_stream_t stream);
+/* Ensemble sharded over GPUs (tcgen05 variant): X, G hold the WHOLE all-gathered ensemble.
+ * mb_svgd_phi_rows writes rows [row_begin, row_begin + row_count) of phi (row_begin a multiple of 128).
+ * mb_pairdist_partial accumulates share `share` of `shares` (128-row tiles share, share + shares, ...: interleaved,
+ * the symmetric evaluation gives tile row i only T - i tiles of work) into acc (MB_PAIRDIST_ACC_BYTES of device memory):
+ * [0] bracket of the median (identical on every rank), [64] u64 entries below it, [72] fp64 sum of distances,
+ * [1024] 2048 u32 histogram counters.  After the ranks' counters / sums have been added (any all-reduce),
+ * mb_pairdist_finish turns them into the bandwidth h (device float). */
+#define MB_PAIRDIST_ACC_BYTES (1024 + 2048 * 4)
+int mb_svgd_phi_rows(mb_ctx* ctx, const float* X, const float* G, int n, int d, const float* bandwidth,
+                     float* phi, int row_begin, int row_count, mb_stream_t stream);
+int mb_pairdist_partial(mb_ctx* ctx, const float* X, int n, int d, int mode, int share, int shares, void* acc,
+                        mb_stream_t stream);
+int mb_pairdist_finish(mb_ctx* ctx, int mode, int n, const void* acc, float* h, mb_stream_t stream);
+/* k(x, y) of one pair (Kernel.__call__, kernels.py:90-95); x, y device float[d], out device float */
+int mb_gaussian_kernel(mb_ctx* ctx, const float* x, const float* y, int d, float bandwidth, float* out,
+                       mb_stream_t stream);
 int mb_adagrad(mb_ctx* ctx, float* X, float* gsq, float* mom, const float* phi, int64_t len, float step,
                float momentum, mb_stream_t stream);
 /* x ~ N(prior_mean, prior_std^2 I) at row-major X (n x d), any d: transport/sampler.py:24-30 (vmap(prior_sample));

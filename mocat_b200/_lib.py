@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libmocat_b200.so")
 MB_MAX_SMALL_DIM = 8
 MB_HIST_MAX = 16384
 MB_MAX_WORLD = 8
+MB_PAIRDIST_ACC_BYTES = 1024 + 2048 * 4
 
 LIK_RASTRIGIN, LIK_GAUSSIAN, LIK_NONE = 0, 1, 2
 MOVE_MALA, MOVE_RW = 0, 1
@@ -155,6 +156,10 @@ SIGNATURES = {
                                C.c_int, c_vp, C.c_int, c_vp, c_vp, c_vp]),
     "mb_svgd_phi": (C.c_int, [c_vp, c_vp, c_vp, C.c_int, C.c_int, c_vp, c_vp, C.c_int, c_vp]),
     "mb_pairdist_bandwidth": (C.c_int, [c_vp, c_vp, C.c_int, C.c_int, C.c_int, c_vp, C.c_int, c_vp]),
+    "mb_svgd_phi_rows": (C.c_int, [c_vp, c_vp, c_vp, C.c_int, C.c_int, c_vp, c_vp, C.c_int, C.c_int, c_vp]),
+    "mb_pairdist_partial": (C.c_int, [c_vp, c_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_vp, c_vp]),
+    "mb_pairdist_finish": (C.c_int, [c_vp, C.c_int, C.c_int, c_vp, c_vp, c_vp]),
+    "mb_gaussian_kernel": (C.c_int, [c_vp, c_vp, c_vp, C.c_int, c_f, c_vp, c_vp]),
     "mb_adagrad": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_f, c_f, c_vp]),
 }
 

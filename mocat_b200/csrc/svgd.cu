@@ -309,18 +309,41 @@ static int svgd_dispatch(mb_ctx* ctx, int what, const float* X, const float* G, 
 }
 
 int mb_svgd_phi_tc(mb_ctx* ctx, const float* X, const float* G, int n, int d, const float* bandwidth, float* phi,
-                   cudaStream_t st);
+                   int row_begin, int row_count, cudaStream_t st);
 
 extern "C" int mb_svgd_phi(mb_ctx* ctx, const float* X, const float* G, int n, int d, const float* bandwidth,
                            float* phi, int variant, mb_stream_t stream) {
     MB_REQUIRE(ctx && X && G && bandwidth && phi && n > 0 && d > 0, "mb_svgd_phi: bad arguments");
     if (variant == 0) return svgd_dispatch(ctx, 0, X, G, n, d, bandwidth, phi, mb_s(stream));
-    if (variant == 1) return mb_svgd_phi_tc(ctx, X, G, n, d, bandwidth, phi, mb_s(stream));
+    if (variant == 1) return mb_svgd_phi_tc(ctx, X, G, n, d, bandwidth, phi, 0, n, mb_s(stream));
     mb_set_error("mb_svgd_phi: variant %d not built", variant);
     return MB_ERR_UNSUPPORTED;
 }
 
+// rows [row_begin, row_begin + row_count) of phi only: one rank's share of an ensemble sharded over GPUs (X and G are
+// the whole, all-gathered ensemble; tensor-core variant, row_begin a multiple of 128)
+extern "C" int mb_svgd_phi_rows(mb_ctx* ctx, const float* X, const float* G, int n, int d, const float* bandwidth,
+                                float* phi, int row_begin, int row_count, mb_stream_t stream) {
+    MB_REQUIRE(ctx && X && G && bandwidth && phi && n > 0 && d > 0, "mb_svgd_phi_rows: bad arguments");
+    return mb_svgd_phi_tc(ctx, X, G, n, d, bandwidth, phi, row_begin, row_count, mb_s(stream));
+}
+
 int mb_pairdist_bandwidth_tc(mb_ctx* ctx, const float* X, int n, int d, int mode, float* h, cudaStream_t st);
+int mb_pairdist_partial_tc(mb_ctx* ctx, const float* X, int n, int d, int mode, int itile_first, int itile_step, void* acc,
+                           cudaStream_t st);
+int mb_pairdist_finish_tc(mb_ctx* ctx, int mode, int n, const void* acc, float* h, cudaStream_t st);
+
+extern "C" int mb_pairdist_partial(mb_ctx* ctx, const float* X, int n, int d, int mode, int share, int shares, void* acc,
+                                   mb_stream_t stream) {
+    MB_REQUIRE(ctx && X && acc && n > 1 && d > 0 && (mode == 0 || mode == 1) && shares >= 1 && share >= 0 && share < shares,
+               "mb_pairdist_partial: bad arguments");
+    return mb_pairdist_partial_tc(ctx, X, n, d, mode, share, shares, acc, mb_s(stream));
+}
+
+extern "C" int mb_pairdist_finish(mb_ctx* ctx, int mode, int n, const void* acc, float* h, mb_stream_t stream) {
+    MB_REQUIRE(ctx && acc && h && n > 1 && (mode == 0 || mode == 1), "mb_pairdist_finish: bad arguments");
+    return mb_pairdist_finish_tc(ctx, mode, n, acc, h, mb_s(stream));
+}
 
 extern "C" int mb_pairdist_bandwidth(mb_ctx* ctx, const float* X, int n, int d, int mode, float* h, int variant,
                                      mb_stream_t stream) {
@@ -328,6 +351,23 @@ extern "C" int mb_pairdist_bandwidth(mb_ctx* ctx, const float* X, int n, int d, 
     if (variant == 1) return mb_pairdist_bandwidth_tc(ctx, X, n, d, mode, h, mb_s(stream));
     MB_REQUIRE(variant == 0, "mb_pairdist_bandwidth: variant not built");
     return svgd_dispatch(ctx, mode == 0 ? 1 : 2, X, nullptr, n, d, nullptr, h, mb_s(stream));
+}
+
+// Gaussian kernel value k(x, y) = exp(-|x - y|^2 / (2 h^2)) of ONE pair (kernels.py:90-95, the scalar Kernel.__call__ of
+// the reference API); fp32 differences, fp64 accumulation, one warp
+__global__ void gaussian_pair_kernel(const float* __restrict__ x, const float* __restrict__ y, int d, float h, float* out) {
+    double s = 0.0;
+    for (int k = threadIdx.x; k < d; k += 32) { const float df = (x[k] - y[k]) / h; s += (double)df * (double)df; }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) out[0] = (float)exp(-0.5 * s);
+}
+
+extern "C" int mb_gaussian_kernel(mb_ctx* ctx, const float* x, const float* y, int d, float bandwidth, float* out,
+                                  mb_stream_t stream) {
+    MB_REQUIRE(ctx && x && y && out && d > 0 && bandwidth > 0.f, "mb_gaussian_kernel: bad arguments");
+    gaussian_pair_kernel<<<1, 32, 0, mb_s(stream)>>>(x, y, d, bandwidth, out);
+    MB_CHECK_LAUNCH();
+    return MB_OK;
 }
 
 // ------------------------------------------------------------------------------------------------ K10

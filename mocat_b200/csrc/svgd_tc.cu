@@ -259,6 +259,8 @@ struct TcArgs {
     float* opart;            // [TC_SPLIT][n_pad][NV] partial O
     float* upart;            // logistic mode: [TC_SPLIT][n_pad][4] partial row sums of softplus
     int ncols_pad;           // padded number of columns (j): = n_pad for the SVGD interaction, the data count for the logits
+    int itile0;              // first 128-row tile of this launch (a rank of a sharded ensemble computes its own rows only)
+    int row_begin, row_end;  // rows whose phi is written by the finish kernel
 };
 
 // MODE 0: P = exp2(S) (SVGD interaction).  MODE 1: S is the logit w_i . a_j of a logistic regression; P = sigmoid(S)
@@ -283,7 +285,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) svgd_phi_tc_kernel(TcArgs a) {
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int T_all = a.ncols_pad / TC_BN;
-    const int itile = blockIdx.x / TC_SPLIT, part = blockIdx.x % TC_SPLIT;
+    const int itile = a.itile0 + blockIdx.x / TC_SPLIT, part = blockIdx.x % TC_SPLIT;
     const int t_begin = (int)(((int64_t)T_all * part) / TC_SPLIT), t_end = (int)(((int64_t)T_all * (part + 1)) / TC_SPLIT);
     const int T = t_end - t_begin;                                     // this CTA's j tiles: [t_begin, t_end)
 
@@ -450,8 +452,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) svgd_phi_tc_kernel(TcArgs a) {
 // phi_i = ( -O_G + (x_i O_1 - O_X)/h^2 ) / n  with O = sum of the TC_SPLIT partials (fixed order: deterministic).
 // O columns follow the W^T rows: [0,d) = sum_j P x_j (scaled by sc), d+2 = sum_j P, [d+4, 2d+4) = sum_j P g_j.
 __global__ void __launch_bounds__(256) svgd_tc_finish_kernel(TcArgs a) {
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (int64_t)a.n * a.d) return;
+    const int64_t idx = (int64_t)a.row_begin * a.d + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)a.row_end * a.d) return;
     const int i = (int)(idx / a.d), k = (int)(idx % a.d);
     float og = 0.f, ox = 0.f, o1 = 0.f;
 #pragma unroll
@@ -467,8 +469,10 @@ __global__ void __launch_bounds__(256) svgd_tc_finish_kernel(TcArgs a) {
 
 // ---- host ---------------------------------------------------------------------------------------
 int mb_svgd_phi_tc(mb_ctx* ctx, const float* X, const float* G, int n, int d, const float* bandwidth, float* phi,
-                   cudaStream_t st) {
+                   int row_begin, int row_count, cudaStream_t st) {
     MB_REQUIRE(d >= 1 && d + 4 <= TC_K, "svgd tcgen05 variant needs d <= 60");
+    MB_REQUIRE(row_begin >= 0 && row_count > 0 && row_begin + row_count <= n && row_begin % TC_BM == 0,
+               "svgd tcgen05 variant: the row range must start on a multiple of 128");
     int NV = ((2 * d + 4 + 15) / 16) * 16;
     if (NV < TC_K) NV = TC_K;                          // MMA1 reads rows 0..63 of every W^T tile
     const int n_pad = ((n + TC_BM - 1) / TC_BM) * TC_BM;
@@ -494,10 +498,12 @@ int mb_svgd_phi_tc(mb_ctx* ctx, const float* X, const float* G, int n, int d, co
     MB_CHECK_LAUNCH();
     const size_t smem = 1024 + TC_TILE_X_BYTES + (size_t)TC_STAGES * NV * 256 + 256;
     MB_CUDA(cudaFuncSetAttribute(svgd_phi_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    TcArgs a{XA, WT, xs, bandwidth, phi, n, d, n_pad, NV, opart, nullptr, n_pad};
-    svgd_phi_tc_kernel<0><<<tiles * TC_SPLIT, TC_THREADS, smem, st>>>(a);
+    const int row_end = row_begin + row_count;
+    const int itile0 = row_begin / TC_BM, itiles = (row_end + TC_BM - 1) / TC_BM - itile0;
+    TcArgs a{XA, WT, xs, bandwidth, phi, n, d, n_pad, NV, opart, nullptr, n_pad, itile0, row_begin, row_end};
+    svgd_phi_tc_kernel<0><<<itiles * TC_SPLIT, TC_THREADS, smem, st>>>(a);
     MB_CHECK_LAUNCH();
-    svgd_tc_finish_kernel<<<(unsigned)(((int64_t)n * d + 255) / 256), 256, 0, st>>>(a);
+    svgd_tc_finish_kernel<<<(unsigned)(((int64_t)row_count * d + 255) / 256), 256, 0, st>>>(a);
     MB_CHECK_LAUNCH();
     return MB_OK;
 }
@@ -522,6 +528,7 @@ struct DtBracket { float bin_off, inv_bw; double lo_w, bw_d2, fallback_d2; };
 struct DtArgs {
     const uint8_t* XA; const uint8_t* WT; int n, n_pad;
     const DtBracket* br; uint32_t* hist; unsigned long long* below; double* partials;
+    int itile_first, itile_step;     // this launch covers the 128-row tiles itile_first + k itile_step (a rank's share)
 };
 
 __device__ __forceinline__ float sqrt_approx(float x) {
@@ -549,8 +556,12 @@ __global__ void __launch_bounds__(DT_THREADS, 1) svgd_dist_tc_kernel(DtArgs a) {
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int T_all = a.n_pad / TC_BN;
-    const int itile = blockIdx.x / TC_SPLIT, part = blockIdx.x % TC_SPLIT;
-    const int t_begin = (int)(((int64_t)T_all * part) / TC_SPLIT), t_end = (int)(((int64_t)T_all * (part + 1)) / TC_SPLIT);
+    // SYMMETRY: D_ij = D_ji, so only the j tiles at or right of the diagonal are evaluated and every off-diagonal tile
+    // counts twice -- half the n^2 distance evaluations of the full matrix.  CTA (itile, part) takes the part-th quarter
+    // of [itile, T_all); CTAs are launched in order of decreasing work (longest first), which keeps the tail short.
+    const int itile = a.itile_first + (blockIdx.x / TC_SPLIT) * a.itile_step, part = blockIdx.x % TC_SPLIT;
+    const int T_row = T_all - itile;
+    const int t_begin = itile + (int)(((int64_t)T_row * part) / TC_SPLIT), t_end = itile + (int)(((int64_t)T_row * (part + 1)) / TC_SPLIT);
     const int T = t_end - t_begin;
 
     if (threadIdx.x == 0) {
@@ -608,7 +619,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) svgd_dist_tc_kernel(DtArgs a) {
         const bool row_valid = itile * TC_BM + wq * 32 + lane < a.n;     // padded rows of the last i tile count nothing
         float bin_scale = 0.f, bin_off = 0.f;
         if (MODE == 0) { bin_scale = -a.br->inv_bw; bin_off = a.br->bin_off; }
-        uint32_t cnt = 0;
+        unsigned long long cnt = 0;
         double dsum = 0.0;
         for (int t = grp; t < T; t += 2) {
             const int u = t >> 1;
@@ -622,15 +633,18 @@ __global__ void __launch_bounds__(DT_THREADS, 1) svgd_dist_tc_kernel(DtArgs a) {
             tc_fence_before();
             mbar_arrive(s_empty + grp);
             if (!row_valid) continue;
+            const uint32_t wgt = (t_begin + t == itile) ? 1u : 2u;     // the diagonal tile holds both (i, j) and (j, i)
             if (MODE == 0) {
                 // bin = round(D^2/bw - k0) through the 1.5*2^23 trick (one FFMA, no F2I on the XU pipe):
                 // bin < 0: below the bracket (counted), 0 <= bin < DT_BINS: histogrammed, otherwise above (padding: +huge)
+                uint32_t tcnt = 0;
 #pragma unroll
                 for (int e = 0; e < 64; ++e) {
                     const int b = __float_as_int(fmaf(__uint_as_float(va[e]), bin_scale, bin_off)) - 0x4B400000;
-                    cnt += (uint32_t)b >> 31;
-                    if ((uint32_t)b < (uint32_t)DT_BINS) atomicAdd(&shist[b], 1u);
+                    tcnt += (uint32_t)b >> 31;
+                    if ((uint32_t)b < (uint32_t)DT_BINS) atomicAdd(&shist[b], wgt);
                 }
+                cnt += tcnt * wgt;
             } else {
                 float ts = 0.f;
 #pragma unroll
@@ -639,7 +653,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) svgd_dist_tc_kernel(DtArgs a) {
                     const float dd = sqrt_approx(fmaxf(-2.f * v, 0.f));
                     ts += (v > -1.0e29f) ? dd : 0.f;                   // padded columns carry -1e30
                 }
-                dsum += (double)ts;
+                dsum += (double)ts * (double)wgt;
             }
         }
         if (MODE == 0) {
@@ -746,6 +760,14 @@ __global__ void __launch_bounds__(256) svgd_dist_median_finish(const DtBracket* 
         h[0] = (float)(med / sqrt(2.0 * log((double)n)));
     }
 }
+__global__ void __launch_bounds__(256) svgd_dist_partial_sum(const double* partials, int nblocks, double* out) {
+    __shared__ double sm[256];
+    double s = 0.0;
+    for (int b = threadIdx.x; b < nblocks; b += 256) s += partials[b];
+    sm[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) { double t = 0.0; for (int k = 0; k < 256; ++k) t += sm[k]; out[0] = t; }
+}
 __global__ void __launch_bounds__(256) svgd_dist_mean_finish(const double* partials, int nblocks, int n, float* h) {
     __shared__ double sm[256];
     double s = 0.0;
@@ -761,18 +783,33 @@ __global__ void __launch_bounds__(256) svgd_dist_mean_finish(const double* parti
 
 int mb_quantile_impl(mb_ctx* ctx, const float* v, int64_t n, const double* q_dev, double q_host, double* out3, cudaStream_t st);
 
-int mb_pairdist_bandwidth_tc(mb_ctx* ctx, const float* X, int n, int d, int mode, float* h, cudaStream_t st) {
+static size_t dt_scratch_need(int n, int d) {
+    const int n_pad = ((n + TC_BM - 1) / TC_BM) * TC_BM, tiles = n_pad / TC_BM;
+    return (4u << 20) + 1024 + (size_t)tiles * TC_TILE_X_BYTES + (size_t)tiles * TC_K * 256 + (size_t)n_pad * d * 4 +
+           (size_t)n_pad * 8 + (size_t)DT_SAMPLES * 4 + 1024 + (size_t)(tiles * TC_SPLIT) * 8 + 8192;
+}
+
+// One rank's share of the statistics: the 128-row tiles itile_first, itile_first + itile_step, ... (interleaved, because
+// the symmetric evaluation gives tile row i only T_all - i tiles of work).  acc (caller-owned device memory,
+// MB_PAIRDIST_ACC_BYTES): [0] bracket (identical on every rank: same hashed sample pairs), [64] entries below the
+// bracket (u64), [72] sum of distances (fp64, mean mode), [1024] 2048 histogram counters (u32).  The ranks' `below`,
+// `sum` and histogram add up (any all-reduce); mb_pairdist_finish turns the totals into the bandwidth.
+int mb_pairdist_partial_tc(mb_ctx* ctx, const float* X, int n, int d, int mode, int itile_first, int itile_step,
+                           void* acc, cudaStream_t st) {
     MB_REQUIRE(d >= 1 && d + 4 <= TC_K, "pairwise-distance tcgen05 variant needs d <= 60");
     MB_REQUIRE((int64_t)n * n >= 4 * (int64_t)DT_SAMPLES, "pairwise-distance tcgen05 variant needs n >= 1024 (use variant 0)");
     const int NV = TC_K;
     const int n_pad = ((n + TC_BM - 1) / TC_BM) * TC_BM;
     const int tiles = n_pad / TC_BM;
-    const int grid = tiles * TC_SPLIT;
+    MB_REQUIRE(itile_step >= 1 && itile_first >= 0 && itile_first < itile_step, "mb_pairdist_partial: bad tile assignment");
+    const int my_tiles = itile_first < tiles ? (tiles - itile_first + itile_step - 1) / itile_step : 0;
+    const int grid = my_tiles * TC_SPLIT;
     const size_t bx = (size_t)tiles * TC_TILE_X_BYTES, bw = (size_t)tiles * NV * 256;
     const size_t bs = (size_t)n_pad * d * 4, ba = (size_t)n_pad * 2 * 4, bsmp = (size_t)DT_SAMPLES * 4;
-    const size_t bmisc = 1024 + DT_BINS * 4 + (size_t)grid * 8;
+    const size_t bmisc = 1024 + (size_t)(tiles * TC_SPLIT) * 8;
     const size_t need = 1024 + bx + bw + bs + ba + bsmp + bmisc + 8192;
-    if (mb_ensure_scratch(ctx, (4u << 20) + need) != MB_OK) return MB_ERR_CUDA;
+    (void)need;
+    if (mb_ensure_scratch(ctx, dt_scratch_need(n, d)) != MB_OK) return MB_ERR_CUDA;
     uint8_t* base = (uint8_t*)ctx->scratch + (4u << 20);
     auto align = [](uint8_t* p) { return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~(uintptr_t)1023); };
     float* mean = reinterpret_cast<float*>(align(base));
@@ -783,10 +820,11 @@ int mb_pairdist_bandwidth_tc(mb_ctx* ctx, const float* X, int n, int d, int mode
     float* smp = reinterpret_cast<float*>(align(reinterpret_cast<uint8_t*>(saux) + ba));
     uint8_t* misc = align(reinterpret_cast<uint8_t*>(smp) + bsmp);
     double* qout = reinterpret_cast<double*>(misc);                    // [2][3]
-    DtBracket* br = reinterpret_cast<DtBracket*>(misc + 64);
-    unsigned long long* below = reinterpret_cast<unsigned long long*>(misc + 192);
-    uint32_t* hist = reinterpret_cast<uint32_t*>(misc + 1024);
-    double* partials = reinterpret_cast<double*>(misc + 1024 + DT_BINS * 4);
+    double* partials = reinterpret_cast<double*>(misc + 1024);
+    DtBracket* br = reinterpret_cast<DtBracket*>(acc);
+    unsigned long long* below = reinterpret_cast<unsigned long long*>((char*)acc + 64);
+    double* dsum = reinterpret_cast<double*>((char*)acc + 72);
+    uint32_t* hist = reinterpret_cast<uint32_t*>((char*)acc + 1024);
     double* cpart = reinterpret_cast<double*>((char*)ctx->scratch + (3u << 20) + (64u << 10));
     svgd_tc_colsum_kernel<<<ctx->sms, 256, 0, st>>>(X, n, d, cpart);
     svgd_tc_colmean_kernel<<<1, 1024, 0, st>>>(cpart, ctx->sms, n, d, mean);
@@ -794,7 +832,7 @@ int mb_pairdist_bandwidth_tc(mb_ctx* ctx, const float* X, int n, int d, int mode
     svgd_tc_rows_kernel<<<(unsigned)(((int64_t)n_pad * 8 + 255) / 256), 256, 0, st>>>(p);
     svgd_tc_wt_kernel<<<(unsigned)(((int64_t)tiles * NV * 16 + 255) / 256), 256, 0, st>>>(p);
     MB_CHECK_LAUNCH();
-    DtArgs a{XA, WT, n, n_pad, br, hist, below, partials};
+    DtArgs a{XA, WT, n, n_pad, br, hist, below, partials, itile_first, itile_step};
     const size_t smem = 1024 + TC_TILE_X_BYTES + (size_t)DT_STAGES * NV * 256 + DT_BINS * 4 + 512;
     if (mode == 0) {
         svgd_dist_sample_kernel<<<DT_SAMPLES / 256, 256, 0, st>>>(X, n, d, smp);
@@ -804,18 +842,42 @@ int mb_pairdist_bandwidth_tc(mb_ctx* ctx, const float* X, int n, int d, int mode
         rc = mb_quantile_impl(ctx, smp, DT_SAMPLES, nullptr, 0.5 + delta, qout + 3, st);
         if (rc != MB_OK) return rc;
         svgd_dist_bracket_kernel<<<1, 256, 0, st>>>(qout, br, hist, below);
-        MB_CUDA(cudaFuncSetAttribute(svgd_dist_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        svgd_dist_tc_kernel<0><<<grid, DT_THREADS, smem, st>>>(a);
-        MB_CHECK_LAUNCH();
-        svgd_dist_median_finish<<<1, 256, 0, st>>>(br, hist, below, n, h, (unsigned long long*)(ctx->counters + MB_CNT_BW_FALLBACK));
+        if (grid > 0) {
+            MB_CUDA(cudaFuncSetAttribute(svgd_dist_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            svgd_dist_tc_kernel<0><<<grid, DT_THREADS, smem, st>>>(a);
+        }
     } else {
-        MB_CUDA(cudaFuncSetAttribute(svgd_dist_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        svgd_dist_tc_kernel<1><<<grid, DT_THREADS, smem, st>>>(a);
-        MB_CHECK_LAUNCH();
-        svgd_dist_mean_finish<<<1, 256, 0, st>>>(partials, grid, n, h);
+        if (grid > 0) {
+            MB_CUDA(cudaFuncSetAttribute(svgd_dist_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            svgd_dist_tc_kernel<1><<<grid, DT_THREADS, smem, st>>>(a);
+        }
+        svgd_dist_partial_sum<<<1, 256, 0, st>>>(partials, grid, dsum);
     }
     MB_CHECK_LAUNCH();
     return MB_OK;
+}
+
+int mb_pairdist_finish_tc(mb_ctx* ctx, int mode, int n, const void* acc, float* h, cudaStream_t st) {
+    const DtBracket* br = reinterpret_cast<const DtBracket*>(acc);
+    const unsigned long long* below = reinterpret_cast<const unsigned long long*>((const char*)acc + 64);
+    const double* dsum = reinterpret_cast<const double*>((const char*)acc + 72);
+    const uint32_t* hist = reinterpret_cast<const uint32_t*>((const char*)acc + 1024);
+    if (mode == 0)
+        svgd_dist_median_finish<<<1, 256, 0, st>>>(br, hist, below, n, h, (unsigned long long*)(ctx->counters + MB_CNT_BW_FALLBACK));
+    else
+        svgd_dist_mean_finish<<<1, 256, 0, st>>>(dsum, 1, n, h);
+    MB_CHECK_LAUNCH();
+    return MB_OK;
+}
+
+int mb_pairdist_bandwidth_tc(mb_ctx* ctx, const float* X, int n, int d, int mode, float* h, cudaStream_t st) {
+    // single GPU: the whole matrix in one share; the accumulator lives in the context's scratch at [3.5 MiB, +10 KiB)
+    // (sized first, so that the pointer survives the call below)
+    if (mb_ensure_scratch(ctx, dt_scratch_need(n, d)) != MB_OK) return MB_ERR_CUDA;
+    void* acc = (char*)ctx->scratch + (3u << 20) + (512u << 10);
+    int rc = mb_pairdist_partial_tc(ctx, X, n, d, mode, 0, 1, acc, st);
+    if (rc != MB_OK) return rc;
+    return mb_pairdist_finish_tc(ctx, mode, n, acc, h, st);
 }
 
 // =================================================================================================

@@ -576,6 +576,16 @@ def interaction_variant(n, d, variant=None):
     return int(variant)
 
 
+def svgd_phi_rows(X, G, bandwidth, row_begin, row_end):
+    """rows [row_begin, row_end) of phi (tensor-core variant; X, G the whole ensemble) -> (row_end - row_begin, d)"""
+    L = _lib.get()
+    n, d = X.shape
+    phi = torch.empty_like(X)
+    L.call("mb_svgd_phi_rows", L.ctx(), ptr(X), ptr(G), n, d, ptr(bandwidth), ptr(phi), int(row_begin),
+           int(row_end - row_begin), stream())
+    return phi[row_begin:row_end]
+
+
 def svgd_phi(X, G, bandwidth, variant=None):
     """X, G: (n, d) row-major float32; bandwidth: device float32 scalar tensor -> phi (n, d)"""
     L = _lib.get()
@@ -586,11 +596,43 @@ def svgd_phi(X, G, bandwidth, variant=None):
     return phi
 
 
+def ensemble_shard(n, d, variant=None):
+    """(rank, world, row_begin, row_end) of this process's share of an SVGD ensemble, or None when the ensemble is not
+    sharded: under torchrun the tensor-core kernels split the n x n interaction by rows of 128 over the ranks
+    (SURVEY 8e item 5); every rank holds the whole (n, d) ensemble, all-gathered once per iteration."""
+    try:
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return None
+    except Exception:
+        return None
+    world, rank = dist.get_world_size(), dist.get_rank()
+    if interaction_variant(n, d, variant) != 1 or n % (128 * world):
+        return None
+    per = n // world
+    return rank, world, rank * per, (rank + 1) * per
+
+
 def pairdist_bandwidth(X, mode, variant=None):
     """mode 'median' | 'mean' -> device float32 (1,) tensor h = stat(D)/sqrt(2 log n)  (kernels.py:220-229)"""
     L = _lib.get()
     n, d = X.shape
     h = torch.empty(1, dtype=torch.float32, device=X.device)
+    sh = ensemble_shard(n, d, variant) if os.environ.get("MOCAT_B200_SVGD_SHARD", "1") != "0" else None
+    if sh is not None:
+        # this rank's share of the (symmetric) distance matrix, all-reduce of the counters, the same finish everywhere
+        import torch.distributed as dist
+        rank, world = sh[0], sh[1]
+        m = 0 if mode == "median" else 1
+        acc = torch.zeros(_lib.MB_PAIRDIST_ACC_BYTES // 4, dtype=torch.int32, device=X.device)
+        L.call("mb_pairdist_partial", L.ctx(), ptr(X), n, d, m, rank, world, ptr(acc), stream())
+        if m == 0:
+            dist.all_reduce(acc[256:])                                 # 2048 histogram counters (< 2^31 in total)
+            dist.all_reduce(acc[16:18].view(torch.int64))              # entries below the bracket
+        else:
+            dist.all_reduce(acc[18:20].view(torch.float64))            # sum of distances
+        L.call("mb_pairdist_finish", L.ctx(), m, n, ptr(acc), ptr(h), stream())
+        return h
     L.call("mb_pairdist_bandwidth", L.ctx(), ptr(X), n, d, 0 if mode == "median" else 1, ptr(h),
            interaction_variant(n, d, variant), stream())
     return h

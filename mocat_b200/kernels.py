@@ -23,15 +23,15 @@ class Gaussian(Kernel):
         super().__init__(bandwidth=bandwidth)
 
     def _pair(self, x, y, bandwidth):
-        # evaluate through the interaction kernel: phi with G = 0, X = [x; y] gives grad terms; for the
-        # scalar API a two-point problem is tiny, so use the closed form on the host scalars returned by
-        # the device distance kernel.
+        """k(x, y) of one pair, evaluated on the device (mb_gaussian_kernel)"""
         torch = _torch()
-        X = torch.as_tensor(np.stack([np.asarray(x, np.float32), np.asarray(y, np.float32)]), device="cuda")
-        # mean distance over the 2x2 matrix (two zeros on the diagonal) * sqrt(2 log 2) = |x - y| / 2
-        h = engine.pairdist_bandwidth(X, "mean").item()
-        dist = h * np.sqrt(2.0 * np.log(2.0)) * 2.0
-        return float(np.exp(-0.5 * (dist / bandwidth) ** 2))
+        L = _lib.get()
+        xd = torch.as_tensor(np.atleast_1d(np.asarray(x, np.float32)), device="cuda").contiguous()
+        yd = torch.as_tensor(np.atleast_1d(np.asarray(y, np.float32)), device="cuda").contiguous()
+        out = torch.empty(1, dtype=torch.float32, device="cuda")
+        L.call("mb_gaussian_kernel", L.ctx(), _lib.ptr(xd), _lib.ptr(yd), xd.numel(), float(bandwidth), _lib.ptr(out),
+               _lib.stream())
+        return float(out.item())
 
     def __call__(self, x, y, bandwidth=None):
         return self._pair(x, y, self.parameters.bandwidth if bandwidth is None else bandwidth)

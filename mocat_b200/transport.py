@@ -291,7 +291,7 @@ class SVGD(TransportSampler):
     name = 'SVGD'
 
     def __init__(self, stepsize, max_iter=1000, kernel=None, kernel_params=None, ensemble_batchsize=None,
-                 optimiser=adagrad, keep_history=None, phi_variant=None, **optim_params):
+                 optimiser=adagrad, keep_history=None, phi_variant=None, sharded=True, **optim_params):
         super().__init__(max_iter=max_iter)
         from .kernels import Gaussian
         self._default_adapt = False
@@ -312,6 +312,7 @@ class SVGD(TransportSampler):
         self.parameters.optim_params = optim_params
         self.keep_history = keep_history
         self.phi_variant = phi_variant
+        self.sharded = bool(sharded)             # under torchrun: split the interaction over the ranks (False: replicate)
 
     def adapt(self, ensemble_state, extra):                             # svgd.py:109-113
         if self._default_adapt:
@@ -344,23 +345,49 @@ class SVGD(TransportSampler):
         else:
             X = torch.as_tensor(np.asarray(initial_state.value, np.float32), device=dev).contiguous()
         st = cdict(value=X)
-        st.potential, st.grad_potential = scenario._potential_grad_device(X, scenario.temperature)
+        # under torchrun the ensemble is sharded by rows over the GPUs (every rank holds all of X; engine.ensemble_shard)
+        self._shard = engine.ensemble_shard(n, scenario.dim, self.phi_variant) if self.sharded else None
+        st.potential, st.grad_potential = self._potential_grad(scenario, X)
         initial_extra.parameters.kernel_params = self.parameters.kernel_params
         st, initial_extra = self.adapt(st, initial_extra)                # svgd.py:102
         initial_extra.gsq = torch.zeros_like(X)
         initial_extra.mom = torch.zeros_like(X)
         return st, initial_extra
 
+    def _potential_grad(self, scenario, X):
+        """vmap(scenario.potential_and_grad) (svgd.py:99,141); sharded: own rows, then one all-gather of (U, G)"""
+        sh = getattr(self, '_shard', None)
+        if sh is None:
+            return scenario._potential_grad_device(X, scenario.temperature)
+        torch = _torch()
+        import torch.distributed as dist
+        _, _, r0, r1 = sh
+        U, G = scenario._potential_grad_device(X[r0:r1], scenario.temperature)
+        n, d = X.shape
+        UG = torch.empty((n, d + 1), dtype=torch.float32, device=X.device)
+        dist.all_gather_into_tensor(UG, torch.cat([G, U[:, None]], dim=1).contiguous())
+        return UG[:, d].contiguous(), UG[:, :d].contiguous()
+
     def update(self, scenario, ensemble_state, extra):                  # svgd.py:122-146
         extra.iter = extra.iter + 1
         X = ensemble_state.value
         h = self._bandwidth_tensor(extra, X.device)
-        phi = engine.svgd_phi(X, ensemble_state.grad_potential, h, self.phi_variant)
         step = self.parameters.stepsize
         step = float(step(extra.iter)) if callable(step) else float(step)
-        engine.adagrad_step(X, extra.gsq, extra.mom, phi, step, self.parameters.optim_params.get('momentum', 0.9))
-        ensemble_state.potential, ensemble_state.grad_potential = \
-            scenario._potential_grad_device(X, scenario.temperature)
+        momentum = self.parameters.optim_params.get('momentum', 0.9)
+        sh = getattr(self, '_shard', None)
+        if sh is None:
+            phi = engine.svgd_phi(X, ensemble_state.grad_potential, h, self.phi_variant)
+            engine.adagrad_step(X, extra.gsq, extra.mom, phi, step, momentum)
+        else:
+            # this rank's rows of the interaction and of the optimiser step, then one all-gather of the new ensemble
+            import torch.distributed as dist
+            _, _, r0, r1 = sh
+            phi = engine.svgd_phi_rows(X, ensemble_state.grad_potential, h, r0, r1)
+            mine = X[r0:r1].clone()
+            engine.adagrad_step(mine, extra.gsq[r0:r1], extra.mom[r0:r1], phi.contiguous(), step, momentum)
+            dist.all_gather_into_tensor(X, mine)
+        ensemble_state.potential, ensemble_state.grad_potential = self._potential_grad(scenario, X)
         ensemble_state, extra = self.adapt(ensemble_state, extra)
         return ensemble_state, extra
 
