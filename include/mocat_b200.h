@@ -310,6 +310,25 @@ int mb_abc_adapt(mb_ctx* ctx, const float* x, int64_t ld, int64_t n, int64_t n_t
                  float* lw, const float* alpha, float* stepsize /*device [d]*/, double ess_retain, double ess_resample,
                  double termination_alpha, int max_iter, const double* schedule, int advance_iter,
                  mb_control* ctl, mb_hist* hist, mb_stream_t stream);
+/* SMC-ABC population sharded over GPUs.  mb_abc_move_sharded: anc holds GLOBAL ancestor ids; the
+ * value block and the prior-potential / distance / acceptance arrays of every rank (this step's input buffers) are read
+ * through peer-mapped pointers ([world] each; entry `rank` is this rank's own input).  mb_abc_adapt_stage: the
+ * adaptation of mb_abc_adapt split into stages that work on the local shard and leave small records in `ws`
+ * (MB_ABC_WS_BYTES of device memory) for the caller to add over the ranks between stages:
+ *   0 begin (-> all-reduce ws+128: 1 + 2d fp64 column sums)       1..3 radix histogram of pass p (-> all-reduce
+ *   ws+1024: 2048 u32)   11..13 pick of pass p   4 count / next-larger pass (-> all-reduce SUM of the i64 at ws+640, MIN of
+ *   the i64 at ws+648)   5 threshold + weights (-> all-reduce ws+64: 3 u64 counts)   6 control block and step sizes.
+ * With a threshold schedule stages 1-4 and 11-13 are skipped. */
+#define MB_ABC_WS_BYTES (1024 + 2048 * 4)
+int mb_abc_move_sharded(mb_ctx* ctx, const mb_gk* gk, int mcmc_steps, float* x_out, int64_t ld, int64_t n,
+                        const int32_t* anc, float* up_out, float* dist_out, float* lw, float* alpha_out,
+                        const float* stepsize, uint64_t seed, int rank, int world, const void* const* x_peers,
+                        const void* const* up_peers, const void* const* dist_peers, const void* const* alpha_peers,
+                        mb_control* ctl, mb_stream_t stream);
+int mb_abc_adapt_stage(mb_ctx* ctx, int stage, const float* x, int64_t ld, int64_t n, int64_t n_total, int d,
+                       const float* dist, float* lw, const float* alpha, float* stepsize, double ess_retain,
+                       double ess_resample, double termination_alpha, int max_iter, const double* schedule,
+                       int advance_iter, void* ws, mb_control* ctl, mb_hist* hist, mb_stream_t stream);
 
 /* ---- conditional section of a captured step.  Every resampling kernel is predicated on the control block, so
  *      enqueueing them unconditionally is always correct (reference: `cond(resample_bool, ...)`,

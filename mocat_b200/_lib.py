@@ -16,6 +16,7 @@ MB_MAX_SMALL_DIM = 8
 MB_HIST_MAX = 16384
 MB_MAX_WORLD = 8
 MB_PAIRDIST_ACC_BYTES = 1024 + 2048 * 4
+MB_ABC_WS_BYTES = 1024 + 2048 * 4
 
 LIK_RASTRIGIN, LIK_GAUSSIAN, LIK_NONE = 0, 1, 2
 MOVE_MALA, MOVE_RW = 0, 1
@@ -154,6 +155,10 @@ SIGNATURES = {
                               c_vp, c_vp, c_vp, c_vp, c_u64, c_i64, c_vp, c_vp]),
     "mb_abc_adapt": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, C.c_int, c_vp, c_vp, c_vp, c_vp, c_d, c_d, c_d,
                                C.c_int, c_vp, C.c_int, c_vp, c_vp, c_vp]),
+    "mb_abc_move_sharded": (C.c_int, [c_vp, C.POINTER(GK), C.c_int, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
+                                      c_u64, C.c_int, C.c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "mb_abc_adapt_stage": (C.c_int, [c_vp, C.c_int, c_vp, c_i64, c_i64, c_i64, C.c_int, c_vp, c_vp, c_vp, c_vp, c_d, c_d,
+                                     c_d, C.c_int, c_vp, C.c_int, c_vp, c_vp, c_vp, c_vp]),
     "mb_svgd_phi": (C.c_int, [c_vp, c_vp, c_vp, C.c_int, C.c_int, c_vp, c_vp, C.c_int, c_vp]),
     "mb_pairdist_bandwidth": (C.c_int, [c_vp, c_vp, C.c_int, C.c_int, C.c_int, c_vp, C.c_int, c_vp]),
     "mb_svgd_phi_rows": (C.c_int, [c_vp, c_vp, c_vp, C.c_int, C.c_int, c_vp, c_vp, C.c_int, C.c_int, c_vp]),

@@ -114,10 +114,29 @@ class MetropolisedABCSMCSampler(ABCSMCSampler):
     def startup(self, abc_scenario, n, initial_state, initial_extra, **kwargs):
         initial_state, initial_extra = super().startup(abc_scenario, n, initial_state, initial_extra, **kwargs)
         P = self.parameters
-        eng = engine.ABCEngine(abc_scenario._device(), n, key_to_seed(getattr(initial_extra, 'random_key', None)),
-                               mcmc_steps=P.mcmc_steps, max_iter=self.max_iter, ess_retain=P.ess_threshold_retain,
-                               ess_resample=P.ess_threshold_resample, termination_alpha=P.termination_alpha,
-                               threshold_schedule=self.threshold_schedule, resampling=_RESAMPLING[self.resampling])
+        kw = dict(mcmc_steps=P.mcmc_steps, max_iter=self.max_iter, ess_retain=P.ess_threshold_retain,
+                  ess_resample=P.ess_threshold_resample, termination_alpha=P.termination_alpha,
+                  threshold_schedule=self.threshold_schedule, resampling=_RESAMPLING[self.resampling])
+        seed = key_to_seed(getattr(initial_extra, 'random_key', None))
+        world = 1
+        try:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                world = dist.get_world_size()
+        except Exception:
+            world = 1
+        if world > 1:
+            # under torchrun `n` is the GLOBAL population size: every rank holds n / world particles and the returned
+            # chain carries this rank's shard of the per-particle fields (thresholds, ESS, ... are global)
+            from . import parallel
+            _, n_local = parallel.shard_range(n, dist.get_rank(), world)
+            eng = parallel.ShardedABCEngine(parallel.shard_context(), abc_scenario._device(), n_local, seed, **kw)
+            if initial_state is not None and getattr(initial_state, 'value', None) is not None:
+                r0 = dist.get_rank() * n_local                     # a global initial population: keep this rank's rows
+                initial_state = initial_state.copy()
+                initial_state.value = np.asarray(initial_state.value)[r0:r0 + n_local]
+        else:
+            eng = engine.ABCEngine(abc_scenario._device(), n, seed, **kw)
         x0 = None if initial_state is None else getattr(initial_state, 'value', None)
         eng.startup(x0)                                                  # abc/smc.py:44-79,128-150
         if initial_state is None:

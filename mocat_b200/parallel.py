@@ -338,3 +338,78 @@ def ShardedPFEngine(sc, ssm, n_local, seed, ess_threshold=0.5, resampling=_lib.R
             _sharded_resample_kernels(self, sc, st)
 
     return _Eng()
+
+
+def ShardedABCEngine(sc, gk, n_local, seed, **kw):
+    """engine.ABCEngine whose population is sharded over sc.world GPUs: global quantile threshold
+    (radix histograms added over the ranks), global column variances and acceptance statistics (NCCL all-reduce of
+    small records between the stages of mb_abc_adapt_stage), sharded resampling, ancestor state read over NVLink."""
+    import torch
+    import torch.distributed as dist
+    from . import engine
+    ptr = _lib.ptr
+
+    class _Eng(engine.ABCEngine):
+        def __init__(self):
+            super().__init__(gk, n_local, seed, gid0=sc.rank * n_local, n_total=sc.world * n_local, **kw)
+            self.sc = sc
+            _sharded_alloc(self, sc)
+            self._peer = {}
+            for name in ("upbuf", "distbuf", "alphabuf"):
+                bufs, peers = [], []
+                for k in range(2):
+                    t, p = sc.alloc_shared((self.n,), torch.float32)
+                    t.zero_()
+                    bufs.append(t); peers.append((C.c_void_p * sc.world)(*p))
+                    self._shared.append(t)
+                setattr(self, name, bufs)
+                self._peer[name] = peers
+            self._peer["xbuf"] = [(C.c_void_p * sc.world)(*[self.shards[k].x_peers[r] for r in range(sc.world)])
+                                  for k in range(2)]
+            self.ws = torch.zeros(_lib.MB_ABC_WS_BYTES // 8, dtype=torch.int64, device=sc.device)
+            self._ws_f64, self._ws_i32 = self.ws.view(torch.float64), self.ws.view(torch.int32)
+
+        def _resample_kernels(self, st):
+            _sharded_resample_kernels(self, sc, st)
+
+        def _stage(self, stage, advance):
+            self.L.call("mb_abc_adapt_stage", self.ctx, stage, ptr(self.x), self.ld, self.n, self.n_total, self.d,
+                        ptr(self.dist), ptr(self.lw), ptr(self.alpha), ptr(self.stepsize), self.ess_retain,
+                        self.ess_resample, self.termination_alpha, self.max_iter, ptr(self._schedule),
+                        1 if advance else 0, ptr(self.ws), ptr(self.ctl.t), ptr(self.ctl.hist), _lib.stream())
+
+        def _adapt(self, advance):
+            d = self.d
+            self._stage(0, advance)
+            dist.all_reduce(self._ws_f64[16:16 + 1 + 2 * d])               # column sums (ws + 128)
+            if self._schedule is None:
+                for p_ in (1, 2, 3):
+                    self._stage(p_, advance)
+                    dist.all_reduce(self._ws_i32[256:256 + 2048])          # radix histogram of this pass (ws + 1024)
+                    self._stage(10 + p_, advance)
+                self._stage(4, advance)
+                dist.all_reduce(self.ws[80:81])                            # entries <= selected (ws + 640)
+                dist.all_reduce(self.ws[81:82], op=dist.ReduceOp.MIN)      # smallest key above it (ws + 648)
+            self._stage(5, advance)
+            dist.all_reduce(self.ws[8:11])                                 # alive / previously alive / acceptance (ws + 64)
+            self._stage(6, advance)
+
+        def update(self):
+            st = _lib.stream()
+            self._resample_kernels(st)
+            c, o = self.cur, self.cur ^ 1
+            self.L.call("mb_abc_move_sharded", self.ctx, C.byref(self.gk), self.mcmc_steps, ptr(self.xbuf[o]), self.ld, self.n,
+                        ptr(self.anc), ptr(self.upbuf[o]), ptr(self.distbuf[o]), ptr(self.lw), ptr(self.alphabuf[o]),
+                        ptr(self.stepsize), self.seed, sc.rank, sc.world, self._peer["xbuf"][c], self._peer["upbuf"][c],
+                        self._peer["distbuf"][c], self._peer["alphabuf"][c], ptr(self.ctl.t), st)
+            self.cur = o
+            # nobody may overwrite the buffers of parity c (next update's output) while a peer still reads them: the
+            # first collective of the adaptation below orders this step's moves of all ranks before the next step's
+            self._adapt(advance=True)
+            self.enqueued += 1
+
+        def close(self):
+            shared, self._shared = self._shared, []
+            sc.free_shared(shared)
+
+    return _Eng()
