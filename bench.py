@@ -326,7 +326,7 @@ def main():
     if world > 1:
         # ONE population of n_total particles sharded over the GPUs (mocat_b200/parallel.py): integer weight totals and
         # (max, sum, sumsq) triples exchanged through peer-mapped mailboxes inside the kernels, ancestors written to the
-        # owning rank over NVLink, ancestor state read from the owning rank by the fused gather
+        # owning rank over NVLink, ancestor rows fetched from the owning rank by the TMA gather of the step kernel
         from mocat_b200 import parallel
         sc = parallel.shard_context()
         pf = parallel.ShardedPFEngine(sc, ssm, n_local, a.seed, ess_threshold=ESS_THRESHOLD,
@@ -457,7 +457,7 @@ def main():
     ach_contract = CONTRACT_BYTES * n_local / (ms_per_step * 1e-3) / 1e9
     k_ncu = ncu.get("pf_l96_kernel", {})
     traffic = k_ncu.get("dram_bytes_per_particle")
-    launches_per_step = 4 if world == 1 else 6
+    launches_per_step = 5 if world == 1 else 8
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": nw,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -468,9 +468,9 @@ def main():
                                    "ancestor state read from the owning GPU over NVLink; no NCCL on the data path)"
                     if world > 1 else "single GPU",
                     "l2": f"inputs larger than L2: {state_bytes / 1e9:.1f} GB of state per GPU streams through every step",
-                    "launch": f"{launches_per_step} kernel launches per step (tile sums, ancestors, heavy-tile pass, "
-                              "propagate" + (", 2 mailbox exchanges)" if world > 1 else ")"),
-                    "layout": "tiled AoSoA: 32-particle tiles of 40 x 32 fp32 (csrc/pf_l96.cu)",
+                    "launch": f"{launches_per_step} kernel launches per step (tile sums, ancestors, heavy-job gather, "
+                              "heavy-tile pass, propagate" + (", 3 mailbox exchanges)" if world > 1 else ")"),
+                    "layout": "row-major (n, 40) fp32, rows moved by the TMA engine (csrc/pf_l96.cu)",
                     "final_ess": float(ctl['ess']), "final_log_z": float(ctl['log_z'])},
         "roofline": {"bound": "hbm", "kernel": "pf_l96_kernel<40>", "achieved": ach_step, "peak": hbm_peak,
                      "unit": "GB/s", "frac": ach_step / hbm_peak,
@@ -480,8 +480,8 @@ def main():
                      "algorithmic_bytes_per_particle": STEP_KERNEL_BYTES, "ms_per_launch": t_step,
                      "whole_step": {"contract_bytes_per_particle": CONTRACT_BYTES, "achieved": ach_contract,
                                     "frac": ach_contract / hbm_peak, "ms": ms_per_step},
-                     "note": "ancestor gather + RK4 + Philox noise + weights in one kernel; issue bound (ncu: "
-                             "profiles/), the population collapses at d=40 so the gathered reads mostly hit L2"},
+                     "note": "TMA row gather + RK4 + Philox noise + weights + bulk store in one kernel; issue bound (ncu: "
+                             "profiles/ncu_c3_r2f.md), the population collapses at d=40 so the gathered reads mostly hit L2"},
         "kernels": {"resample (rf_tile_sums + rf_ancestors + rf_heavy)": {"ms": t_res,
                                                                         "algorithmic_bytes_per_particle": 12},
                     "pf_l96_kernel<40>": {"ms": t_step, "algorithmic_bytes_per_particle": STEP_KERNEL_BYTES,
