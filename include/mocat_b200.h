@@ -233,6 +233,13 @@ int mb_pf_step(mb_ctx* ctx, const mb_ssm* ssm, const float* x_in, float* x_out, 
                int64_t gid0, double ess_threshold, mb_control* ctl, mb_hist* hist, const mb_shard* sh /*or NULL*/,
                mb_comm* comm /*or NULL*/, mb_stream_t stream);
 
+/* Kalman filter of the time-homogeneous linear-Gaussian model (ssm/linear_gaussian/kalman.py:16-57): exact filtering
+ * means [T][dim] and covariances [T][dim][dim] (device fp64) and the innovation log-likelihood (loglik, may be NULL)
+ * the particle filter's log-evidence is checked against (config C1).  y: device float [T][dim_obs].
+ * cov_0 = L0 L0^T (kalman.py:20 passes the Cholesky factor instead; identical when P0 = I). */
+int mb_kalman_filter(mb_ctx* ctx, const mb_ssm* ssm, const float* y, int T, double* means, double* covs,
+                     double* loglik /*or NULL*/, mb_stream_t stream);
+
 /* ---- K1b', Lorenz-96 (config C3): same contract as mb_pf_init / mb_pf_step for MB_SSM_LORENZ96 (dim 8, 16 or 40,
  *      H = I, diagonal noise, `substeps` RK4 steps per observation interval; ssm/scenarios/lorenz96.py:14-44 on
  *      ssm/nonlinear_gaussian.py:107-121) on the ROW-MAJOR layout of the reference's `value` array: particle i,

@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(MV_THREADS, (D <= 6 ? 4 : (D <= 10 ? 3 : 2))) 
     const uint32_t step = (uint32_t)(ctl->iter + 1);
     const uint64_t seed = ctl->seed;                   // device-resident key: the captured graph is seed-agnostic
     const float eps = a.mv.stepsize;
-    constexpr uint32_t NZ = (D + 3) / 4, S = NZ + 1;
+    constexpr uint32_t S = MB_MOVE_SLOTS(D);            // Philox slots per Metropolised move (normals + accept uniform)
     __shared__ double red[MV_THREADS / 32];
     long long nan_local = 0;
     double alpha_local = 0.0;
@@ -161,9 +161,8 @@ __global__ void __launch_bounds__(MV_THREADS, (D <= 6 ? 4 : (D <= 10 ? 3 : 2))) 
         float alpha_sum = 0.f;
         const uint64_t gid = (uint64_t)(a.gid0 + i);
         for (int s = 0; s < a.mv.mcmc_steps; ++s) {
-            float z[D];
-            philox_normals<D>(z, seed, gid, step, MB_P_MOVE, (uint32_t)s * S);
-            const float uacc = u24(philox_raw(seed, gid, step, MB_P_MOVE, (uint32_t)s * S + NZ).x);
+            float z[D], uacc;
+            philox_normals_accept<D>(z, uacc, seed, gid, step, MB_P_MOVE, (uint32_t)s * S);
             float xp[D], gpn[D], upn, uln, Un, alpha;
             if (MOVE == MB_MOVE_MALA) {
                 // always(): p = z (friction = inf, :116-122); leapfrog (utils.py:117-134); p' = -p' (:141)
@@ -522,6 +521,127 @@ extern "C" int mb_prior_sample(mb_ctx* ctx, float prior_mean, float prior_std, i
     MB_REQUIRE(ctx && X && d > 0 && n > 0, "mb_prior_sample: bad arguments");
     const int64_t total = n * ((d + 3) / 4);
     prior_sample_kernel<<<(unsigned)((total + 255) / 256), 256, 0, mb_s(stream)>>>(prior_mean, prior_std, d, n, seed, gid0, X);
+    MB_CHECK_LAUNCH();
+    return MB_OK;
+}
+
+
+// =================================================================================================
+// Kalman filter of the time-homogeneous linear-Gaussian model (ssm/linear_gaussian/kalman.py:16-57): exact
+// filtering means / covariances and the innovation log-likelihood the particle filter's log-evidence is checked
+// against.  O(T d^3) sequential algebra on matrices of at most 8 x 8: ONE warp, fp64, lane l owns the matrix entries
+// l and l + 32; nothing here is bandwidth- or throughput-relevant, it exists so that the cross-check runs where the
+// filter runs.  cov_0 = L0 L0^T (the reference passes the Cholesky factor, kalman.py:20 -- identical when P0 = I).
+#define KF_D MB_MAX_SMALL_DIM
+struct KfArgs { mb_ssm ssm; const float* y; int T; double* means; double* covs; double* loglik; };
+
+__device__ __forceinline__ void kf_sync() { __syncwarp(); }
+
+// C = A B (or A B^T) for KF_D x KF_D matrices in shared memory, rows/cols beyond (r, c) ignored; lane-parallel over entries
+__device__ __forceinline__ void kf_mul(const double* A, const double* B, double* Cm, int r, int k, int c, bool bt) {
+    const int lane = threadIdx.x;
+    for (int e = lane; e < KF_D * KF_D; e += 32) {
+        const int i = e / KF_D, j = e % KF_D;
+        double acc = 0.0;
+        if (i < r && j < c)
+            for (int q = 0; q < k; ++q) acc += A[i * KF_D + q] * (bt ? B[j * KF_D + q] : B[q * KF_D + j]);
+        Cm[e] = acc;
+    }
+    kf_sync();
+}
+
+__global__ void __launch_bounds__(32) kalman_kernel(KfArgs a) {
+    __shared__ double F[KF_D * KF_D], H[KF_D * KF_D], Q[KF_D * KF_D], R[KF_D * KF_D], P[KF_D * KF_D], T1[KF_D * KF_D],
+        T2[KF_D * KF_D], S[KF_D * KF_D], Si[KF_D * KF_D], K[KF_D * KF_D], mu[KF_D], innov[KF_D], tmp[KF_D];
+    __shared__ double ll, logdet;
+    const int lane = threadIdx.x, d = a.ssm.dim, dy = a.ssm.dim_obs;
+    for (int e = lane; e < KF_D * KF_D; e += 32) { F[e] = a.ssm.F[e]; H[e] = a.ssm.H[e]; T1[e] = a.ssm.L0[e]; T2[e] = a.ssm.LQ[e]; K[e] = a.ssm.Rps[e]; }
+    if (lane < KF_D) mu[lane] = a.ssm.m0[lane];
+    if (lane == 0) ll = 0.0;
+    kf_sync();
+    kf_mul(T1, T1, P, d, d, d, true);                                   // P0 = L0 L0^T
+    kf_mul(T2, T2, Q, d, d, d, true);                                   // Q = LQ LQ^T
+    // R = (Rps^T Rps)^-1 with Rps = inv(chol(R)):  R = L L^T, L = Rps^-1 (lower triangular): forward substitution
+    for (int e = lane; e < KF_D * KF_D; e += 32) T1[e] = 0.0;
+    kf_sync();
+    if (lane < dy) {                                                    // column `lane` of L = Rps^-1
+        for (int i = 0; i < dy; ++i) {
+            double v = (i == lane) ? 1.0 : 0.0;
+            for (int q = 0; q < i; ++q) v -= K[i * KF_D + q] * T1[q * KF_D + lane];
+            T1[i * KF_D + lane] = v / K[i * KF_D + i];
+        }
+    }
+    kf_sync();
+    kf_mul(T1, T1, R, dy, dy, dy, true);
+    for (int t = 0; t < a.T; ++t) {
+        if (t > 0) {                                                    // predict, kalman.py:34-35
+            if (lane < d) { double v = 0.0; for (int q = 0; q < d; ++q) v += F[lane * KF_D + q] * mu[q]; tmp[lane] = v; }
+            kf_sync();
+            if (lane < d) mu[lane] = tmp[lane];
+            kf_mul(F, P, T1, d, d, d, false);
+            kf_mul(T1, F, T2, d, d, d, true);
+            for (int e = lane; e < KF_D * KF_D; e += 32) P[e] = T2[e] + Q[e];
+            kf_sync();
+        }
+        kf_mul(H, P, T1, dy, d, d, false);                              // H P
+        kf_mul(T1, H, S, dy, d, dy, true);                              // S = H P H^T + R
+        for (int e = lane; e < KF_D * KF_D; e += 32) S[e] += R[e];
+        if (lane < dy) {
+            double v = (double)a.y[(int64_t)t * dy + lane];
+            for (int q = 0; q < d; ++q) v -= H[lane * KF_D + q] * mu[q];
+            innov[lane] = v;
+        }
+        kf_sync();
+        // S^-1 and log det S by Gauss-Jordan without pivoting (S is symmetric positive definite); serial on lane 0
+        if (lane == 0) {
+            double A[KF_D][2 * KF_D];
+            for (int i = 0; i < dy; ++i)
+                for (int j = 0; j < dy; ++j) { A[i][j] = S[i * KF_D + j]; A[i][dy + j] = (i == j) ? 1.0 : 0.0; }
+            double ld = 0.0;
+            for (int c = 0; c < dy; ++c) {
+                const double piv = A[c][c];
+                ld += log(piv);
+                for (int j = 0; j < 2 * dy; ++j) A[c][j] /= piv;
+                for (int i = 0; i < dy; ++i) {
+                    if (i == c) continue;
+                    const double f = A[i][c];
+                    for (int j = 0; j < 2 * dy; ++j) A[i][j] -= f * A[c][j];
+                }
+            }
+            for (int i = 0; i < KF_D; ++i)
+                for (int j = 0; j < KF_D; ++j) Si[i * KF_D + j] = (i < dy && j < dy) ? A[i][dy + j] : 0.0;
+            logdet = ld;
+        }
+        kf_sync();
+        if (lane == 0) {
+            double quad = 0.0;
+            for (int i = 0; i < dy; ++i) for (int j = 0; j < dy; ++j) quad += innov[i] * Si[i * KF_D + j] * innov[j];
+            ll += -0.5 * (quad + logdet + (double)dy * 1.8378770664093453);
+        }
+        kf_mul(P, H, T1, d, d, dy, true);                               // P H^T
+        kf_mul(T1, Si, K, d, dy, dy, false);                            // K = P H^T S^-1, kalman.py:42
+        if (lane < d) { double v = mu[lane]; for (int q = 0; q < dy; ++q) v += K[lane * KF_D + q] * innov[q]; tmp[lane] = v; }
+        kf_sync();
+        if (lane < d) { mu[lane] = tmp[lane]; a.means[(int64_t)t * d + lane] = tmp[lane]; }
+        kf_mul(K, H, T1, d, dy, d, false);                              // K H
+        kf_mul(T1, P, T2, d, d, d, false);                              // K H P
+        for (int e = lane; e < KF_D * KF_D; e += 32) {
+            P[e] -= T2[e];
+            const int i = e / KF_D, j = e % KF_D;
+            if (i < d && j < d) a.covs[((int64_t)t * d + i) * d + j] = P[e];
+        }
+        kf_sync();
+    }
+    if (lane == 0 && a.loglik) a.loglik[0] = ll;
+}
+
+extern "C" int mb_kalman_filter(mb_ctx* ctx, const mb_ssm* ssm, const float* y, int T, double* means, double* covs,
+                                double* loglik, mb_stream_t stream) {
+    MB_REQUIRE(ctx && ssm && y && means && covs && T > 0, "mb_kalman_filter: bad arguments");
+    MB_REQUIRE(ssm->kind == MB_SSM_LINEAR_GAUSSIAN && ssm->dim >= 1 && ssm->dim <= KF_D && ssm->dim_obs >= 1 && ssm->dim_obs <= ssm->dim,
+               "mb_kalman_filter: time-homogeneous linear-Gaussian model with dim_obs <= dim <= 8");
+    KfArgs a{*ssm, y, T, means, covs, loglik};
+    kalman_kernel<<<1, 32, 0, mb_s(stream)>>>(a);
     MB_CHECK_LAUNCH();
     return MB_OK;
 }

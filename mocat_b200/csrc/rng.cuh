@@ -76,3 +76,30 @@ __device__ __forceinline__ void philox_normals(float (&z)[D], uint64_t seed, uin
         if (4 * s + 3 < D) z[4 * s + 3] = d;
     }
 }
+
+// D standard normals AND the accept uniform of one Metropolised move.  When D mod 4 is 1 or 2 the last normal slot has two
+// unused words: the uniform is word 2 of that slot (no extra Philox call); otherwise it is word 0 of the next slot.
+// Slots consumed per move: MB_MOVE_SLOTS(D).  Mirrored by oracle/smc.py.
+#define MB_MOVE_SPARE(D) ((D) % 4 == 1 || (D) % 4 == 2)
+#define MB_MOVE_SLOTS(D) (((D) + 3) / 4 + (MB_MOVE_SPARE(D) ? 0 : 1))
+template <int D>
+__device__ __forceinline__ void philox_normals_accept(float (&z)[D], float& uacc, uint64_t seed, uint64_t gid, uint32_t step,
+                                                      uint32_t purpose, uint32_t index0) {
+    constexpr int NZ = (D + 3) / 4;
+#pragma unroll
+    for (int s = 0; s < NZ; ++s) {
+        const Philox4 r = philox_raw(seed, gid, step, purpose, index0 + s);
+        float a, b, c, d;
+        box_muller(r.x, r.y, a, b);
+        if (4 * s + 0 < D) z[4 * s + 0] = a;
+        if (4 * s + 1 < D) z[4 * s + 1] = b;
+        if (4 * s + 2 < D) {
+            box_muller(r.z, r.w, c, d);
+            z[4 * s + 2] = c;
+            if (4 * s + 3 < D) z[4 * s + 3] = d;
+        } else if (MB_MOVE_SPARE(D) && s == NZ - 1) {
+            uacc = u24(r.z);
+        }
+    }
+    if (!MB_MOVE_SPARE(D)) uacc = u24(philox_raw(seed, gid, step, purpose, index0 + NZ).x);
+}

@@ -373,9 +373,33 @@ def run_particle_filter_for_marginals(ssm_scenario, particle_filter, y, t, rando
 
 
 def run_kalman_filter_for_marginals(lgssm_scenario, y, t, return_log_likelihood=False):
-    """ssm/linear_gaussian/kalman.py:16-57 (exact filtering means/covariances; O(T d^3) host control-plane
-    algebra used only as a cross-check, not part of the particle hot path).  Fixes kalman.py:20 (cov_0 is
-    L0 L0^T here; identical when P0 = I) and can also return the innovation log-likelihood."""
+    """ssm/linear_gaussian/kalman.py:16-57: exact filtering means / covariances of a TimeHomogenousLinearGaussian model,
+    evaluated on the device (mb_kalman_filter: one warp, fp64, matrices of at most 8 x 8) so that the cross-check of
+    the particle filter runs where the filter runs.  Fixes kalman.py:20 (cov_0 is L0 L0^T here; identical when P0 = I)
+    and can also return the innovation log-likelihood."""
+    torch = _torch()
+    y = np.asarray(y, np.float32)
+    if y.ndim == 1:
+        y = y[:, None]
+    s = lgssm_scenario._ssm()
+    if int(s.kind) != _lib.SSM_LINEAR_GAUSSIAN:
+        raise _lib.MocatB200Error("run_kalman_filter_for_marginals needs a TimeHomogenousLinearGaussian model")
+    L = _lib.get()
+    T, d = len(y), lgssm_scenario.dim
+    yd = torch.as_tensor(np.ascontiguousarray(y), device="cuda")
+    means = torch.empty((T, d), dtype=torch.float64, device="cuda")
+    covs = torch.empty((T, d, d), dtype=torch.float64, device="cuda")
+    ll = torch.empty(1, dtype=torch.float64, device="cuda")
+    import ctypes as C
+    L.call("mb_kalman_filter", L.ctx(), C.byref(s), _lib.ptr(yd), T, _lib.ptr(means), _lib.ptr(covs), _lib.ptr(ll),
+           _lib.stream())
+    mus, cv = means.cpu().numpy(), covs.cpu().numpy()
+    return (mus, cv, float(ll.item())) if return_log_likelihood else (mus, cv)
+
+
+def kalman_filter_host(lgssm_scenario, y, t=None, return_log_likelihood=False):
+    """the same recursion in NumPy fp64 on the host (used by the CPU-only tests of the host API; the product path is
+    run_kalman_filter_for_marginals on the device)"""
     y = np.asarray(y, np.float64)
     if y.ndim == 1:
         y = y[:, None]

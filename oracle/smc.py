@@ -9,8 +9,9 @@ and transport/sampler.py:24-30 (particles initialised from vmap(prior_sample)).
 
 Randomness: Philox streams of oracle/philox.py (the reference's threefry streams are
 unpinned, see oracle/__init__.py).  Per iteration `it` and particle `gid`:
-  move normals   purpose P_MOVE, step it, slots s*S .. s*S+nz-1   (nz = ceil(d/4), S = nz+1)
-  accept uniform purpose P_MOVE, step it, slot  s*S+nz, word 0 (u24)
+  move normals   purpose P_MOVE, step it, slots s*S .. s*S+nz-1   (nz = ceil(d/4))
+  accept uniform purpose P_MOVE, step it: d mod 4 in {1, 2} leaves two unused words in the last normal slot -> word 2 of
+                 slot s*S+nz-1 (u24), S = nz; otherwise word 0 of slot s*S+nz, S = nz+1  (csrc/rng.cuh MB_MOVE_SLOTS)
   resampling     purpose P_RESAMPLE, step it: systematic u0 = uniform32(gid 0) / 2^32;
                  multinomial u_i = uniform53(gid i)
 Deviation noted in DESIGN.md: the reference recomputes lik = (U - U_prior)/beta after the
@@ -86,12 +87,16 @@ class TemperedSMC:
         d = self.d
         n = x.shape[0]
         nz = (d + 3) // 4
-        S = nz + 1
+        spare = d % 4 in (1, 2)                                         # unused words in the last normal slot
+        S = nz if spare else nz + 1
         alphas = np.zeros(n)
         up_c, lik_c, U, g = self._eval(x, beta)
         for s in range(self.mcmc_steps):
             z = philox.normals(self.seed, gid, it, philox.P_MOVE, d, index0=s * S, dtype=self.normal_dtype)
-            u = philox.u24(philox.raw(self.seed, gid, it, philox.P_MOVE, s * S + nz)[0]).astype(np.float64)
+            if spare:
+                u = philox.u24(philox.raw(self.seed, gid, it, philox.P_MOVE, s * S + nz - 1)[2]).astype(np.float64)
+            else:
+                u = philox.u24(philox.raw(self.seed, gid, it, philox.P_MOVE, s * S + nz)[0]).astype(np.float64)
             if self.move == 'mala':
                 pg = lambda xx: self._eval(xx, beta)[2:]
                 x, U, g, alpha, _ = mcmc.hmc_step(pg, x, U, g, z, u, self.stepsize, self.L)

@@ -1,4 +1,4 @@
-"""Generate tests/golden/oracle_v2.npz.
+"""Generate tests/golden/oracle_v3.npz.
 
 The reference (mocat on JAX) cannot be imported in the build container (jax is absent: DESIGN.md section 2), so no
 vectors could be produced by the reference itself.  These fixtures are seeded inputs together with the outputs of the
@@ -100,5 +100,5 @@ def build():
 
 if __name__ == "__main__":
     g = build()
-    np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "oracle_v2.npz"), **g)
+    np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "oracle_v3.npz"), **g)
     print({k: (v.shape, str(v.dtype)) for k, v in g.items()})

@@ -248,3 +248,28 @@ def test_rm_metropolised_smc_stepsize_adaptation(mocat):
     assert abs(len(out.stepsize) - len(ref)) <= 3
     assert np.all(np.diff(np.log(out.stepsize)) <= 1.0 * (1 - 0.651) + 1e-6)   # |log step| <= rm * (1 - target)
     assert out.temperature[-1] == 1.0
+
+
+@pytest.mark.parametrize("d,dy", [(1, 1), (3, 2), (8, 8)])
+def test_kalman_filter_device_matches_oracle(mocat, d, dy):
+    """mb_kalman_filter (ssm/linear_gaussian/kalman.py:16-57 on the device, fp64) against the oracle's recursion:
+    means, covariances and the innovation log-likelihood, for full and partial observation"""
+    from oracle import models as omodels, pf as opf
+    rng = np.random.default_rng(d * 10 + dy)
+    A = rng.standard_normal((d, d)); F = 0.9 * A / np.max(np.abs(np.linalg.eigvals(A)))
+    B = rng.standard_normal((d, d)); Q = B @ B.T / d + 0.1 * np.eye(d)
+    Cm = rng.standard_normal((d, d)); P0 = Cm @ Cm.T / d + 0.5 * np.eye(d)
+    H = rng.standard_normal((dy, d))
+    E_ = rng.standard_normal((dy, dy)); R = E_ @ E_.T / dy + 0.2 * np.eye(dy)
+    m0 = rng.standard_normal(d)
+    sc = mocat.ssm.TimeHomogenousLinearGaussian(m0, P0, F, Q, H, R)
+    sim = sc.simulate(np.arange(60.0), 5)
+    mus, covs, ll = mocat.ssm.run_kalman_filter_for_marginals(sc, sim.y, sim.t, return_log_likelihood=True)
+    y32 = sim.y.astype(np.float32).astype(np.float64)                   # the device reads the observations in fp32
+    omus, ocovs, oll = opf.kalman_filter(omodels.LinearGaussianSSM(m0, P0, F, Q, H, R), y32)
+    # the POD model struct carries fp32 matrices (Cholesky factors of P0, Q; precision root of R): 1e-7 relative inputs
+    npt.assert_allclose(mus, omus, rtol=5e-5, atol=5e-5)
+    npt.assert_allclose(covs, ocovs, rtol=5e-5, atol=5e-6)
+    npt.assert_allclose(ll, oll, rtol=2e-5)
+    hm, hc, hl = mocat.ssm.kalman_filter_host(sc, y32, sim.t, return_log_likelihood=True)
+    npt.assert_allclose(mus, hm, rtol=5e-5, atol=5e-5)

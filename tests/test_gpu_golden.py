@@ -1,4 +1,4 @@
-"""CUDA path against the committed golden vectors (tests/golden/oracle_v2.npz) -- no import of `oracle/` here.
+"""CUDA path against the committed golden vectors (tests/golden/oracle_v3.npz) -- no import of `oracle/` here.
 Tolerances as in DESIGN.md section 2: bit-exact for integer / CDF work, fp32 transcendental tolerances otherwise."""
 import os
 
@@ -7,7 +7,7 @@ import numpy.testing as npt
 import pytest
 
 pytestmark = pytest.mark.gpu
-G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_v2.npz"))
+G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_v3.npz"))
 
 
 @pytest.fixture(scope="module")

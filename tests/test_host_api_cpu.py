@@ -187,7 +187,7 @@ def test_smc_sampler_startup_chain_without_device(monkeypatch):
 
 
 def test_kalman_filter_host_matches_oracle_and_struct_mirror():
-    """run_kalman_filter_for_marginals (ssm/linear_gaussian/kalman.py:16-57; host NumPy, cross-check only) against the
+    """kalman_filter_host (ssm/linear_gaussian/kalman.py:16-57 in NumPy; the device version is tested on the GPU) against the
     oracle recursion, and the POD mirror of the model that the filter kernels receive"""
     from oracle import models as omodels, pf as opf
     F = np.array([[0.9, 0.1], [0.0, 0.8]])
@@ -201,7 +201,7 @@ def test_kalman_filter_host_matches_oracle_and_struct_mirror():
     assert sc.dim == 2 and sc.dim_obs == 1
     sim = sc.simulate(np.arange(15.0), 4)
     assert sim.x.shape == (15, 2) and sim.y.shape == (15, 1)
-    mus, covs, ll = mocat.ssm.run_kalman_filter_for_marginals(sc, sim.y, sim.t, return_log_likelihood=True)
+    mus, covs, ll = mocat.ssm.kalman_filter_host(sc, sim.y, sim.t, return_log_likelihood=True)
     omus, ocovs, oll = opf.kalman_filter(omodels.LinearGaussianSSM(m0, P0, F, Q, H, R), sim.y)
     npt.assert_allclose(mus, omus, rtol=1e-12, atol=1e-12)
     npt.assert_allclose(covs, ocovs, rtol=1e-12, atol=1e-12)
