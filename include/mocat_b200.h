@@ -240,6 +240,15 @@ int mb_pf_step(mb_ctx* ctx, const mb_ssm* ssm, const float* x_in, float* x_out, 
 int mb_kalman_filter(mb_ctx* ctx, const mb_ssm* ssm, const float* y, int T, double* means, double* covs,
                      double* loglik /*or NULL*/, mb_stream_t stream);
 
+/* Backward simulation (FFBSi; ssm/backward.py:20-40 full_resampling, :241-272 backward_simulation_full) for the
+ * Gaussian-transition models: for every backward sample x1_j (n_s, d) draw idx_j ~ Cat(lw0_i - transition_potential(
+ * x0_i -> x1_j)) over the n_pf filter particles x0 (n_pf, d) by Gumbel-max (Philox counter: gid = j, step, slot i / 4)
+ * and return x_out_j = x0[idx_j].  x1 == NULL: no transition term (the final-time categorical draw from the weights).
+ * All arrays device, row-major; work: n_pf * d floats. */
+int mb_backward_sample(mb_ctx* ctx, const mb_ssm* ssm, float dt, const float* x0, const float* lw0, int64_t n_pf,
+                       const float* x1 /*or NULL*/, int64_t n_s, float* work, uint64_t seed, uint32_t step, int32_t* idx,
+                       float* x_out, mb_stream_t stream);
+
 /* ---- K1b', Lorenz-96 (config C3): same contract as mb_pf_init / mb_pf_step for MB_SSM_LORENZ96 (dim 8, 16 or 40,
  *      H = I, diagonal noise, `substeps` RK4 steps per observation interval; ssm/scenarios/lorenz96.py:14-44 on
  *      ssm/nonlinear_gaussian.py:107-121) on the ROW-MAJOR layout of the reference's `value` array: particle i,

@@ -114,6 +114,8 @@ SIGNATURES = {
     "mb_pf_step": (C.c_int, [c_vp, C.POINTER(SSM), c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_u64, c_u32,
                              c_i64, c_d, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "mb_kalman_filter": (C.c_int, [c_vp, C.POINTER(SSM), c_vp, C.c_int, c_vp, c_vp, c_vp, c_vp]),
+    "mb_backward_sample": (C.c_int, [c_vp, C.POINTER(SSM), c_f, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_u64, c_u32, c_vp,
+                                     c_vp, c_vp]),
     "mb_ancestors_sharded": (C.c_int, [c_vp, c_vp, C.c_int, c_u64, c_u32, c_vp, c_i64, c_vp, c_vp]),
     "mb_strata_count": (C.c_int, [c_i64]),
     "mb_strata_hist": (C.c_int, [c_vp, c_i64, c_i64, C.c_int, c_u64, c_u32, c_vp, c_vp, C.c_int, c_vp]),

@@ -372,6 +372,71 @@ def run_particle_filter_for_marginals(ssm_scenario, particle_filter, y, t, rando
     return out
 
 
+def backward_simulation(ssm_scenario, marginal_particles, random_key, n_samps=None, maximum_rejections=0,
+                        transition_dens_bound_parameter=0., bound_inflation=1.01):
+    """ssm/backward.py:275-300: backward simulation (FFBSi) from stacked filter output `marginal_particles` (value
+    (T, n_pf, d), log_weight (T, n_pf), t (T,): run the filter with keep_history=True).  Every time step is one device
+    contraction of the n_samps backward samples against the n_pf filter particles with a Gumbel-max categorical draw
+    (mb_backward_sample, csrc/backward.cu) -- `backward_simulation_full`, backward.py:241-272.  The rejection variant
+    (maximum_rejections > 0, :170-238) draws from the SAME law with data-dependent work; it is served by the full
+    contraction here and `num_transition_evals` reports the n_pf * n_samps evaluations actually made."""
+    torch = _torch()
+    import ctypes as C
+    vals = getattr(marginal_particles, 'value', None)
+    lws = getattr(marginal_particles, 'log_weight', None)
+    if vals is None or lws is None or np.ndim(vals) != 3:
+        raise _lib.MocatB200Error("backward_simulation needs the stacked filter history: value (T, n_pf, d) and log_weight "
+                                  "(T, n_pf) -- run the filter with keep_history=True")
+    vals, lws = np.asarray(vals, np.float32), np.asarray(lws, np.float32)
+    T, n_pf, d = vals.shape
+    n_s = n_pf if n_samps is None else int(n_samps)
+    times = np.asarray(marginal_particles.t, np.float64)
+    seed = key_to_seed(random_key)
+    L = _lib.get()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    work = torch.empty((n_pf, d), dtype=torch.float32, device=dev)
+    idx = torch.empty(n_s, dtype=torch.int32, device=dev)
+    out = torch.empty((T, n_s, d), dtype=torch.float32, device=dev)
+
+    def draw(ind, x1):
+        x0 = torch.as_tensor(vals[ind], device=dev).contiguous()
+        lw0 = torch.as_tensor(lws[ind], device=dev).contiguous()
+        dt = float(times[ind + 1] - times[ind]) if x1 is not None else 0.0
+        s = ssm_scenario._ssm(dt if x1 is not None else None)
+        L.call("mb_backward_sample", L.ctx(), C.byref(s), dt, _lib.ptr(x0), _lib.ptr(lw0), n_pf, _lib.ptr(x1), n_s,
+               _lib.ptr(work), seed, ind, _lib.ptr(idx), _lib.ptr(out[ind]), _lib.stream())
+
+    draw(T - 1, None)                                                   # backward.py:254-256
+    for ind in range(T - 2, -1, -1):                                    # :258-266
+        draw(ind, out[ind + 1])
+    res = marginal_particles.copy()
+    res.value = out.cpu().numpy()
+    res.num_transition_evals = np.append(0, np.ones(T - 1) * n_pf * n_s)
+    if hasattr(res, 'log_weight'):
+        del res.log_weight
+    return res
+
+
+def forward_filtering_backward_simulation(ssm_scenario, particle_filter, y, t, n_samps, random_key, n_pf=None,
+                                          ess_threshold=0.5, maximum_rejections=0, transition_dens_bound_parameter=0.,
+                                          bound_inflation=1.01):
+    """ssm/backward.py:303-350"""
+    import time
+    if n_pf is None:
+        n_pf = n_samps
+    seed = key_to_seed(random_key)
+    t0 = time.time()
+    pf_samps = run_particle_filter_for_marginals(ssm_scenario, particle_filter, y, t, seed, n=n_pf,
+                                                 ess_threshold=ess_threshold, keep_history=True)
+    _torch().cuda.synchronize()
+    t1 = time.time()
+    out = backward_simulation(ssm_scenario, pf_samps, seed + 1, n_samps, maximum_rejections,
+                              transition_dens_bound_parameter, bound_inflation)
+    t2 = time.time()
+    out.time, out.pf_time, out.bsi_time = t2 - t0, t1 - t0, t2 - t1
+    return out
+
+
 def run_kalman_filter_for_marginals(lgssm_scenario, y, t, return_log_likelihood=False):
     """ssm/linear_gaussian/kalman.py:16-57: exact filtering means / covariances of a TimeHomogenousLinearGaussian model,
     evaluated on the device (mb_kalman_filter: one warp, fp64, matrices of at most 8 x 8) so that the cross-check of
