@@ -63,50 +63,61 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 #define L96_THREADS 256
 #define L96_WARPS (L96_THREADS / 32)
 
-struct L96Consts {                   // packed constants of the flow
-    f2 F, hh, hf, h6, two;
+struct L96Consts {                   // packed constants of the flow: h/2 F, -h/2, -h, -h/6, 2
+    f2 hhF, nhh, nhf, nh6, two;
 };
 
-// slope of coordinate r of this lane: (x[r+1] - x[r-2]) * x[r-1] + (F - x[r]), lorenz96.py:18-19; indices outside
-// [0, CPL) are the halo values received from the neighbouring lanes
+// NEGATED slope of coordinate r without the forcing: n = (x[r-2] - x[r+1]) * x[r-1] + x[r] = F - dx_r/dt
+// (lorenz96.py:18-19) -- one FADD2 + one FFMA2; indices outside [0, CPL) are the halo values received from the
+// neighbouring lanes
 #define L96_EXT(arr, r) ((r) == -2 ? hm2 : ((r) == -1 ? hm1 : ((r) == CPL ? hp1 : arr[((r) < 0 || (r) >= CPL) ? 0 : (r)])))
-#define L96_SLOPE(arr, r) f2_fma(f2_sub(L96_EXT(arr, (r) + 1), L96_EXT(arr, (r) - 2)), L96_EXT(arr, (r) - 1), f2_sub(c.F, arr[r]))
+#define L96_NSLOPE(arr, r) f2_fma(f2_sub(L96_EXT(arr, (r) - 2), L96_EXT(arr, (r) + 1)), L96_EXT(arr, (r) - 1), arr[r])
 #define L96_HALO(arr)                                                  \
     const f2 hm2 = __shfl_sync(MB_FULL, arr[CPL - 2], prev);           \
     const f2 hm1 = __shfl_sync(MB_FULL, arr[CPL - 1], prev);           \
     const f2 hp1 = __shfl_sync(MB_FULL, arr[0], next);
 
-// one classical RK4 step (device definition of the L96 flow, SURVEY 8c / DESIGN.md).  Three arrays of CPL packed
-// registers (state x, slope accumulator, stage state s): stages 2 and 3 update s IN PLACE -- coordinates are swept
-// upwards and the two old values a later slope still needs (s[r-1], s[r-2]) ride along in two temporaries -- so the
-// kernel fits 80 registers (3 blocks of 256 threads per SM) without spilling.
+// one classical RK4 step (device definition of the L96 flow, SURVEY 8c / DESIGN.md).  With k = F - n the forcing leaves
+// the slopes: the stage states are  x + c h k = (x + c h F) - c h n  and  x' = (x + h F) - h/6 (n1 + 2 n2 + 2 n3 + n4),
+// so x is advanced IN PLACE to x + h/2 F (stage 1) and x + h F (stage 3) and every stage costs 4 packed instructions per
+// coordinate (5 in stage 3) instead of 5.  Three arrays of CPL packed registers (state x, accumulator, stage state s);
+// the in-place sweeps go upwards and the two old values a later slope still needs ride along in two temporaries.
 template <int CPL>
 __device__ __forceinline__ void l96_rk4(f2 (&x)[CPL], const L96Consts& c, int prev, int next) {
     f2 acc[CPL], s[CPL];
     {
-        L96_HALO(x)
+        const f2 hm2 = __shfl_sync(MB_FULL, x[CPL - 2], prev);
+        const f2 hp1 = __shfl_sync(MB_FULL, x[0], next);
+        f2 o2 = hm2, o1 = __shfl_sync(MB_FULL, x[CPL - 1], prev);
 #pragma unroll
-        for (int r = 0; r < CPL; ++r) { const f2 k = L96_SLOPE(x, r); acc[r] = k; s[r] = f2_fma(c.hh, k, x[r]); }
+        for (int r = 0; r < CPL; ++r) {
+            const f2 cur = x[r];
+            const f2 nn = f2_fma(f2_sub(o2, r + 1 < CPL ? x[r + 1] : hp1), o1, cur);
+            acc[r] = nn;
+            x[r] = f2_add(cur, c.hhF);                                 // x + h/2 F
+            s[r] = f2_fma(c.nhh, nn, x[r]);
+            o2 = o1; o1 = cur;
+        }
     }
 #pragma unroll
     for (int stage = 0; stage < 2; ++stage) {
         const f2 hm2 = __shfl_sync(MB_FULL, s[CPL - 2], prev);
         const f2 hp1 = __shfl_sync(MB_FULL, s[0], next);
         f2 o2 = hm2, o1 = __shfl_sync(MB_FULL, s[CPL - 1], prev);
-        const f2 step = stage == 0 ? c.hh : c.hf;
 #pragma unroll
         for (int r = 0; r < CPL; ++r) {
             const f2 cur = s[r];
-            const f2 k = f2_fma(f2_sub(r + 1 < CPL ? s[r + 1] : hp1, o2), o1, f2_sub(c.F, cur));
-            acc[r] = f2_fma(c.two, k, acc[r]);
-            s[r] = f2_fma(step, k, x[r]);
+            const f2 nn = f2_fma(f2_sub(o2, r + 1 < CPL ? s[r + 1] : hp1), o1, cur);
+            acc[r] = f2_fma(c.two, nn, acc[r]);
+            if (stage == 1) x[r] = f2_add(x[r], c.hhF);                // x + h F
+            s[r] = f2_fma(stage == 0 ? c.nhh : c.nhf, nn, x[r]);
             o2 = o1; o1 = cur;
         }
     }
     {
         L96_HALO(s)
 #pragma unroll
-        for (int r = 0; r < CPL; ++r) { const f2 k = L96_SLOPE(s, r); x[r] = f2_fma(c.h6, f2_add(acc[r], k), x[r]); }
+        for (int r = 0; r < CPL; ++r) { const f2 nn = L96_NSLOPE(s, r); x[r] = f2_fma(c.nh6, f2_add(acc[r], nn), x[r]); }
     }
 }
 
@@ -132,19 +143,20 @@ struct L96Args {
 //   ROWS    scattered sources (the light tail of a collapsed population; ancestors on several GPUs): every lane copies
 //           its own ancestor's row, D*4 contiguous bytes, from whichever GPU owns it.
 // Finished rows are collected in shared memory and leave with one bulk store per 16 particles.
-#define L96_ROWS 64
+#define L96_ROWS 64                  // default window (rows) of a warp; a template parameter of the kernel
 
-template <int D, int W>
+template <int D, int W, int ROWS = L96_ROWS>
 struct L96Smem {
-    static constexpr int IN_FLOATS = L96_ROWS * D;                     // source window of one warp
+    static constexpr int IN_FLOATS = ROWS * D;                     // source window of one warp
     static constexpr int OUT_FLOATS = 16 * D;                          // 16 finished rows of one warp
     static constexpr size_t bytes = (size_t)W * (IN_FLOATS + OUT_FLOATS) * sizeof(float);
 };
 
 // OCC: resident blocks per SM the register allocation is tuned for; ROUNDS: Philox rounds (10 = production; the 7-round
 // variant exists only to measure how much of the step is RNG, MB_L96_VARIANT=27, and is never the default)
-template <int D, bool INIT, int OCC = 2, int ROUNDS = 10, int W = L96_WARPS>
-__global__ void __launch_bounds__(W * 32, OCC) pf_l96_kernel(L96Args a) {
+template <int D, bool INIT, int ROUNDS, int W, int ROWS = L96_ROWS>
+__device__ __forceinline__ void l96_body(const L96Args& a) {
+    static_assert(ROWS >= 32, "ROWS mode needs one slot per lane");
     static_assert(D % 8 == 0, "the lane split needs an even number of coordinates per lane");
     constexpr int CPL = D / 4;                       // coordinates per lane
     mb_control* ctl = a.tail.ctl;
@@ -156,7 +168,9 @@ __global__ void __launch_bounds__(W * 32, OCC) pf_l96_kernel(L96Args a) {
     __shared__ f2 ysm[D];
     __shared__ const float* peers[MB_MAX_WORLD];
     if (threadIdx.x < D) ysm[threadIdx.x] = f2_splat(a.y[threadIdx.x] * a.ir);
-    if (threadIdx.x < MB_MAX_WORLD) peers[threadIdx.x] = a.sharded ? a.x_peers[threadIdx.x] : a.x_in;
+    const int own = a.sharded ? a.rank : 0;                         // index of this GPU's own buffer in peers[]
+    if (threadIdx.x < MB_MAX_WORLD)
+        peers[threadIdx.x] = (a.sharded && (int)threadIdx.x != a.rank) ? a.x_peers[threadIdx.x] : a.x_in;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, p = lane & 3;
     const uint32_t bar_a = smem_u32(&bars[warp]);
     if (!INIT && lane == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
@@ -167,68 +181,55 @@ __global__ void __launch_bounds__(W * 32, OCC) pf_l96_kernel(L96Args a) {
     const uint64_t seed = a.tail.seed;
     const L96Consts& c = a.c;
     const f2 nir = a.nir2, zmean = a.zmean2;
-    float* const win = stage_all + (size_t)warp * (L96Smem<D, W>::IN_FLOATS + L96Smem<D, W>::OUT_FLOATS);
-    float* const outb = win + L96Smem<D, W>::IN_FLOATS;
+    float* const win = stage_all + (size_t)warp * (L96Smem<D, W, ROWS>::IN_FLOATS + L96Smem<D, W, ROWS>::OUT_FLOATS);
+    float* const outb = win + L96Smem<D, W, ROWS>::IN_FLOATS;
     const uint32_t win_a = smem_u32(win), outb_a = smem_u32(outb);
     const int64_t gid0 = a.gid0;
 
-    float am = -INFINITY;                            // per-thread online (max, sum, sumsq); lanes with p != 0 stay empty
-    f2 as1 = f2_pack(0.f, 0.f), as2 = as1;           // packed fp32 partial sums (<= a few thousand terms per thread)
+    float am = -INFINITY, as1 = 0.f, as2 = 0.f;      // per-thread online (max, sum, sumsq): one weight per lane and group
     const int64_t ntiles = (a.n + 31) >> 5;          // groups of 32 outputs
     const int64_t stride = (int64_t)gridDim.x * W;
+    const int n_local = (int)a.n_local;
 
-    // source of the 32 outputs of a group: `src` = this lane's source row (owner-relative), `base` = the owner's buffer
-    // (per lane); warp-uniform: mode 0 = WINDOW [r0, r0 + nr) of the (common) base, 2 = the same but already resident
-    // (the buffer starts at row r0), 1 = ROWS (lane l's row sits in slot l)
-    struct Win { int64_t src; const float* base; int64_t r0; int mode, nr; };
+    // source of the 32 outputs of a group: `src` = this lane's source row (owner-relative), `owner` = the GPU that holds
+    // it (per lane); warp-uniform: mode 0 = WINDOW [r0, r0 + nr) of the (common) owner, 2 = the same but already resident
+    // (the buffer starts at row r0), 1 = ROWS (lane l's row sits in slot l).  Rows and GPUs are 32-bit quantities
+    // (ancestors are int32), so the span of the group is four warp reductions (REDUX), not shuffle trees.
+    struct Win { int src, owner, r0, mode, nr; };
     auto describe = [&](int64_t tile) -> Win {
         Win w;
         const int64_t i = tile * 32 + lane;
-        w.base = a.x_in; w.mode = 0;
-        int64_t s_ = i;                              // not resampling / beyond n: the particle's own row
+        int s_ = (int)i, o = own;                    // not resampling / beyond n: the particle's own row
         if (resample && i < a.n) {
-            s_ = (int64_t)__ldg(a.anc + i);          // GLOBAL id of the ancestor
-            if (a.sharded) {                         // owner-relative row + the owner's (peer-mapped) buffer
-                const int o = (int)(s_ / a.n_local);
-                s_ -= (int64_t)o * a.n_local;
-                w.base = peers[o];
-            }
+            s_ = __ldg(a.anc + i);                   // GLOBAL id of the ancestor
+            if (a.sharded) { o = s_ / n_local; s_ -= o * n_local; }    // owner + owner-relative row
         }
-        w.src = s_;
-        int64_t lo = s_, hi = s_;
-        unsigned long long b0 = (unsigned long long)w.base, b1 = b0;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            lo = min(lo, (int64_t)__shfl_xor_sync(MB_FULL, lo, o));
-            hi = max(hi, (int64_t)__shfl_xor_sync(MB_FULL, hi, o));
-            b0 = min(b0, (unsigned long long)__shfl_xor_sync(MB_FULL, b0, o));
-            b1 = max(b1, (unsigned long long)__shfl_xor_sync(MB_FULL, b1, o));
-        }
+        w.src = s_; w.owner = o; w.mode = 0;
+        const int lo = __reduce_min_sync(MB_FULL, s_), hi = __reduce_max_sync(MB_FULL, s_);
         w.r0 = lo;
-        w.nr = (int)min(hi - lo + 1, (int64_t)(L96_ROWS + 1));
-        if (w.nr > L96_ROWS || b0 != b1) w.mode = 1;                   // scattered sources, or ancestors on several GPUs
+        w.nr = (int)min((unsigned)(hi - lo), (unsigned)ROWS) + 1;
+        if (w.nr > ROWS) w.mode = 1;                               // scattered sources
+        if (a.sharded && __reduce_min_sync(MB_FULL, o) != __reduce_max_sync(MB_FULL, o)) w.mode = 1;   // several GPUs
         return w;
     };
-    const float* buf_base = nullptr;                                   // what the window holds (WINDOW mode)
-    int64_t buf_r0 = 0;
-    int buf_nr = 0;
+    int buf_owner = -1, buf_r0 = 0, buf_nr = 0;                        // what the window holds (WINDOW mode)
     auto fetch = [&](Win& w) {
         if (w.mode == 0) {
-            if (w.base == buf_base && w.r0 >= buf_r0 && w.r0 + w.nr <= buf_r0 + buf_nr) { w.r0 = buf_r0; w.mode = 2; return; }
-            buf_base = w.base; buf_r0 = w.r0; buf_nr = w.nr;
+            if (w.owner == buf_owner && w.r0 >= buf_r0 && w.r0 + w.nr <= buf_r0 + buf_nr) { w.r0 = buf_r0; w.mode = 2; return; }
+            buf_owner = w.owner; buf_r0 = w.r0; buf_nr = w.nr;
             if (lane == 0) {
                 const uint32_t bytes = (uint32_t)(w.nr * D * 4);
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
                 asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                             ::"r"(win_a), "l"(w.base + w.r0 * D), "r"(bytes), "r"(bar_a) : "memory");
+                             ::"r"(win_a), "l"(peers[w.owner] + (int64_t)w.r0 * D), "r"(bytes), "r"(bar_a) : "memory");
             }
         } else {
-            buf_base = nullptr;                                        // the window no longer holds a span
+            buf_owner = -1;                                            // the window no longer holds a span
             if (lane == 0)
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"((uint32_t)(32 * D * 4)) : "memory");
             __syncwarp();
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(win_a + (uint32_t)(lane * D * 4)), "l"(w.base + w.src * D), "r"((uint32_t)(D * 4)), "r"(bar_a) : "memory");
+                         ::"r"(win_a + (uint32_t)(lane * D * 4)), "l"(peers[w.owner] + (int64_t)w.src * D), "r"((uint32_t)(D * 4)), "r"(bar_a) : "memory");
         }
     };
 
@@ -246,17 +247,17 @@ __global__ void __launch_bounds__(W * 32, OCC) pf_l96_kernel(L96Args a) {
                              : "=r"(done) : "r"(bar_a), "r"(phase) : "memory");
             phase ^= 1;
         }
+        float wq = 0.f;                                                // quadratic form of THIS lane's particle of the group
 #pragma unroll 1
         for (int sub = 0; sub < 2; ++sub) {
             const int64_t iP = tile * 32 + sub * 16 + 2 * g;           // even particle of the pair; the odd one is iP + 1
-            const bool vP = iP < a.n, vQ = iP + 1 < a.n;
             f2 x[CPL];
             if (!INIT) {
                 const int lP = sub * 16 + 2 * g;
                 int rowP = lP, rowQ = lP + 1;                          // ROWS mode: the slot is the lane that fetched it
                 if (cur.mode != 1) {
-                    rowP = (int)(__shfl_sync(MB_FULL, cur.src, lP) - cur.r0);
-                    rowQ = (int)(__shfl_sync(MB_FULL, cur.src, lP + 1) - cur.r0);
+                    rowP = __shfl_sync(MB_FULL, cur.src, lP) - cur.r0;
+                    rowQ = __shfl_sync(MB_FULL, cur.src, lP + 1) - cur.r0;
                 }
                 const float* bP = win + rowP * D + CPL * p;
                 const float* bQ = win + rowQ * D + CPL * p;
@@ -313,35 +314,51 @@ __global__ void __launch_bounds__(W * 32, OCC) pf_l96_kernel(L96Args a) {
                              ::"l"(a.x_out + row0 * D), "r"(outb_a), "r"((uint32_t)(16 * D * 4)) : "memory");
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
-            if (p == 0) {
+            {                                                          // lane p of the quad keeps particle 16 (p >> 1) + 2 g + (p & 1)
                 float qP, qQ;
                 f2_unpack(quad, qP, qQ);
-                float wP = -fmaf(0.5f, qP, a.lik_const), wQ = -fmaf(0.5f, qQ, a.lik_const);
-                if (!INIT && !resample) {                              // filtering.py:292,303: weights carried
-                    const float2 o = *reinterpret_cast<const float2*>(a.lw + iP);   // lw is padded to a multiple of 32
-                    wP += o.x; wQ += o.y;
-                }
-                if (!vP) wP = -INFINITY;
-                if (!vQ) wQ = -INFINITY;
-                *reinterpret_cast<float2*>(a.lw + iP) = make_float2(wP, wQ);
-                // branch-free online (max, sum e, sum e^2): rescale by f = exp(old max - new max) (= 1 when unchanged)
-                const float amn = fmaxf(am, fmaxf(wP, wQ));
-                const float ref = (amn == -INFINITY) ? 0.f : amn;
-                const float f = __expf(am - ref);                      // am = -inf -> 0 (sums are still 0)
-                const f2 e = f2_pack(__expf(wP - ref), __expf(wQ - ref));  // NaN weights propagate into the sums
-                as1 = f2_fma(as1, f2_splat(f), e);
-                as2 = f2_fma(as2, f2_splat(f * f), f2_mul(e, e));
-                am = amn;
+                if ((p >> 1) == sub) wq = (p & 1) ? qQ : qP;
             }
+        }
+        {   // log-weights of the group, one per lane: -likelihood_potential (+ the carried weight, filtering.py:292,303)
+            const int64_t iw = tile * 32 + ((p >> 1) << 4) + 2 * g + (p & 1);
+            float w = -fmaf(0.5f, wq, a.lik_const);
+            if (!INIT && !resample) w += a.lw[iw];                     // lw is padded to a multiple of 32
+            if (iw >= a.n) w = -INFINITY;
+            a.lw[iw] = w;
+            // branch-free online (max, sum e, sum e^2): rescale by f = exp(old max - new max) (= 1 when unchanged)
+            const float amn = fmaxf(am, w);
+            const float ref = (amn == -INFINITY) ? 0.f : amn;
+            const float f = __expf(am - ref);                          // am = -inf -> 0 (sums are still 0)
+            const float e = __expf(w - ref);                           // a NaN weight propagates into the sums
+            as1 = fmaf(as1, f, e);
+            as2 = fmaf(as2, f * f, e * e);
+            am = amn;
         }
         cur = nxtw;
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the last rows have left shared memory
-    float s1l, s1h, s2l, s2h;
-    f2_unpack(as1, s1l, s1h);
-    f2_unpack(as2, s2l, s2h);
-    pf_finish<INIT>(a.tail, (p == 0) ? Lse3{(double)am, (double)s1l + (double)s1h, (double)s2l + (double)s2h} : lse3_empty(),
-                    resample, smem);
+    pf_finish<INIT>(a.tail, Lse3{(double)am, (double)as1, (double)as2}, resample, smem);
+}
+
+template <int D, bool INIT, int OCC = 2, int ROUNDS = 10, int W = L96_WARPS>
+__global__ void __launch_bounds__(W * 32, OCC) pf_l96_kernel(const __grid_constant__ L96Args a) { l96_body<D, INIT, ROUNDS, W>(a); }
+
+// experiment (MB_L96_VARIANT=36x): explicit register cap instead of the occupancy hint
+template <int D, int NREG, int W, int ROWS>
+__global__ void __maxnreg__(NREG) pf_l96_kernel_r(const __grid_constant__ L96Args a) { l96_body<D, false, 10, W, ROWS>(a); }
+
+template <int D, int NREG, int W, int OCC, int ROWS>
+static int l96_launch_r(mb_ctx* ctx, const L96Args& a, cudaStream_t st) {
+    const size_t smem = L96Smem<D, W, ROWS>::bytes;
+    MB_CUDA(cudaFuncSetAttribute(pf_l96_kernel_r<D, NREG, W, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t ntiles = (a.n + 31) >> 5;
+    int64_t grid = (ntiles + W - 1) / W;
+    if (grid > (int64_t)ctx->sms * OCC) grid = (int64_t)ctx->sms * OCC;
+    if (grid > MB_MAX_PARTIAL_BLOCKS) grid = MB_MAX_PARTIAL_BLOCKS;
+    pf_l96_kernel_r<D, NREG, W, ROWS><<<(unsigned)grid, W * 32, smem, st>>>(a);
+    MB_CHECK_LAUNCH();
+    return MB_OK;
 }
 
 template <int D, bool INIT, int OCC, int ROUNDS, int W = L96_WARPS>
@@ -368,8 +385,8 @@ static int l96_dispatch(mb_ctx* ctx, const mb_ssm* ssm, L96Args& a, bool init, c
     const double sd = init ? (double)ssm->init_std : (double)ssm->q_std;       // z * sd = sqrt(-2 ln u1 sd^2) * (cos, sin)
     a.bm_k1 = (float)(-2.0 * 0.6931471805599453 * sd * sd);
     auto splat = [](float v) { uint32_t b; memcpy(&b, &v, 4); return (f2)b | ((f2)b << 32); };
-    a.c.F = splat(a.forcing); a.c.hh = splat(0.5f * a.h); a.c.hf = splat(a.h); a.c.h6 = splat(a.h * (1.f / 6.f));
-    a.c.two = splat(2.f);
+    a.c.hhF = splat(0.5f * a.h * a.forcing); a.c.nhh = splat(-0.5f * a.h); a.c.nhf = splat(-a.h);
+    a.c.nh6 = splat(-a.h * (1.f / 6.f)); a.c.two = splat(2.f);
     a.nir2 = splat(-a.ir); a.zmean2 = splat(a.zmean);
     a.tail.partials = ctx->partials;
     a.tail.counter = ctx->counters + MB_CNT_MOVE;
@@ -378,6 +395,11 @@ static int l96_dispatch(mb_ctx* ctx, const mb_ssm* ssm, L96Args& a, bool init, c
     if (!init && ssm->dim == 40 && variant != 20) {
         if (variant == 10) return l96_launch<40, false, 1, 10>(ctx, a, st);
         if (variant == 27) return l96_launch<40, false, 2, 7>(ctx, a, st);
+        if (variant == 36) return l96_launch_r<40, 112, 6, 3, 48>(ctx, a, st);     // 18 warps
+        if (variant == 45) return l96_launch_r<40, 104, 5, 4, 40>(ctx, a, st);     // 20 warps
+        if (variant == 37) return l96_launch_r<40, 96, 7, 3, 40>(ctx, a, st);      // 21 warps
+        if (variant == 38) return l96_launch_r<40, 80, 8, 3, 40>(ctx, a, st);      // 24 warps
+
         mb_set_error("pf_l96: unknown MB_L96_VARIANT %d", variant);
         return MB_ERR_ARG;
     }

@@ -65,6 +65,56 @@ class BootstrapPF:
         return out
 
 
+class OptimalPF(BootstrapPF):
+    """OptimalNonLinearGaussianParticleFilter (ssm/nonlinear_gaussian.py:134-276) for the device family H = I with
+    diagonal Q = q^2 I, R = r^2 I, P0 = p0^2 I (the Lorenz-96 scenario of config C3), where every matrix of `startup`
+    (:152-186) is a scalar:
+      initial_kalman_gain K0 = p0^2 / (p0^2 + r^2)                      (:161, utils kalman_gain)
+      initial conditioned covariance 1 / (1/p0^2 + 1/r^2)               (:163-166)
+      proposal_kalman_gain Kp = q^2 / (q^2 + r^2)                       (:169-172)
+      proposal covariance q^2 - Kp q^2 = q^2 r^2 / (q^2 + r^2)          (:174-177)
+      weight precision 1 / (q^2 + r^2)                                  (:170-171, 181-182)
+    Initial weights are zero (:209-214); the step samples x' = mx + Kp (y - mx) + sd_p z and adds
+    log N(y; mx, (q^2 + r^2) I) to the log-weight (:257-271), mx = transition_function(x)."""
+
+    def init(self, y0):
+        s = self.ssm
+        y0 = np.asarray(y0, np.float64)
+        z = self.normals(self.seed, self.gid, 0, philox.P_INIT, s.dim, dtype=self.normal_dtype)
+        k0 = s.init_std ** 2 / (s.init_std ** 2 + s.r_std ** 2)
+        sd0 = np.sqrt(1.0 / (1.0 / s.init_std ** 2 + 1.0 / s.r_std ** 2))
+        x = s.init_mean + k0 * (y0 - s.init_mean) + sd0 * np.asarray(z, np.float64)     # :191-203
+        lw = np.zeros(self.n)
+        return dict(x=x, lw=lw, ess=core.ess_log_weight(lw), t=0,
+                    log_z=core.logsumexp(lw) - np.log(self.n), resampled=False, ancestors=None)
+
+    def step(self, st, y):
+        s, n = self.ssm, self.n
+        y = np.asarray(y, np.float64)
+        t = st['t'] + 1
+        x, lw = st['x'], st['lw']
+        resample = st['ess'] < self.thr * n
+        anc = None
+        if resample:
+            if self.resampling == 'systematic':
+                k0 = int(philox.uniform32(self.seed, np.zeros(1, np.uint64), t, philox.P_RESAMPLE)[0])
+                anc = core.ancestors_systematic_exact(core.integer_weights_log(lw), k0)
+            else:
+                anc = core.ancestors_multinomial_stratified(core.cdf_from_log_weights(lw), self.seed, t)[0]
+            x = x[anc]
+            lw = np.zeros(n)
+        z = self.normals(self.seed, self.gid, t, philox.P_MOVE, s.dim, dtype=self.normal_dtype)
+        mx = s.transition_function(x)
+        v = s.q_std ** 2 + s.r_std ** 2
+        kp = s.q_std ** 2 / v
+        sdp = s.q_std * s.r_std / np.sqrt(v)
+        x_new = mx + kp * (y - mx) + sdp * np.asarray(z, np.float64)                   # :262-266
+        lw_new = lw - (0.5 * np.sum((y - mx) ** 2, axis=-1) / v + 0.5 * s.dim * np.log(2.0 * np.pi * v))   # :268-271
+        return dict(x=x_new, lw=lw_new, ess=core.ess_log_weight(lw_new), t=t,
+                    log_z=st['log_z'] + core.logsumexp(lw_new) - core.logsumexp(lw),
+                    resampled=bool(resample), ancestors=anc)
+
+
 def weighted_moments(x, lw):
     w = np.exp(lw - np.max(lw))
     w = w / w.sum()
