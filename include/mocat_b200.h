@@ -101,6 +101,8 @@ typedef struct {             /* adaptive likelihood tempering, transport/smc.py:
 
 enum { MB_SSM_LINEAR_GAUSSIAN = 0,  /* ssm/linear_gaussian/linear_gaussian.py:142-261 */
        MB_SSM_LORENZ96 = 1 };       /* ssm/scenarios/lorenz96.py:14-44 on ssm/nonlinear_gaussian.py:19-131 */
+enum { MB_PROPOSAL_BOOTSTRAP = 0,   /* ssm/filtering.py:142-170 */
+       MB_PROPOSAL_OPTIMAL = 1 };   /* ssm/nonlinear_gaussian.py:134-276 (H = I, diagonal noise) */
 
 typedef struct {
     int32_t kind, dim, dim_obs, substeps;
@@ -114,6 +116,9 @@ typedef struct {
     float lik_const;                                    /* .5 (d_y log 2pi - log det R^-1) */
     /* Lorenz-96 with diagonal noise */
     float forcing, dt, q_std, r_std, init_mean, init_std;
+    /* proposal of the filter (Lorenz-96 kernels): MB_PROPOSAL_BOOTSTRAP = transition (ssm/filtering.py:142-170),
+     * MB_PROPOSAL_OPTIMAL = OptimalNonLinearGaussianParticleFilter (ssm/nonlinear_gaussian.py:134-276) */
+    int32_t proposal;
 } mb_ssm;
 
 typedef struct {              /* g-and-k, abc/scenarios/gk.py:68-96 */

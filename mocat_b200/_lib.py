@@ -22,6 +22,7 @@ LIK_RASTRIGIN, LIK_GAUSSIAN, LIK_NONE = 0, 1, 2
 MOVE_MALA, MOVE_RW = 0, 1
 RESAMPLE_SYSTEMATIC, RESAMPLE_MULTINOMIAL = 0, 1
 SSM_LINEAR_GAUSSIAN, SSM_LORENZ96 = 0, 1
+PROPOSAL_BOOTSTRAP, PROPOSAL_OPTIMAL = 0, 1
 
 c_f, c_d, c_i32, c_i64, c_u32, c_u64, c_vp = C.c_float, C.c_double, C.c_int32, C.c_int64, C.c_uint32, C.c_uint64, C.c_void_p
 
@@ -70,7 +71,7 @@ class SSM(C.Structure):
     _fields_ = [("kind", c_i32), ("dim", c_i32), ("dim_obs", c_i32), ("substeps", c_i32),
                 ("m0", c_f * MB_MAX_SMALL_DIM), ("L0", _M2), ("F", _M2), ("LQ", _M2), ("H", _M2), ("Rps", _M2),
                 ("lik_const", c_f), ("forcing", c_f), ("dt", c_f), ("q_std", c_f), ("r_std", c_f),
-                ("init_mean", c_f), ("init_std", c_f)]
+                ("init_mean", c_f), ("init_std", c_f), ("proposal", c_i32)]
 
 
 class Shard(C.Structure):

@@ -60,7 +60,7 @@ struct RfHeavy {                                 // a source tile with more than
 
 struct RfHeavyJob {                              // a heavy tile as seen by ONE rank: its share of the tile's outputs
     u64 Cex;                                     // cumulative weight before the tile
-    u64 rot;                                     // work items of the jobs in front of this one (block rotation)
+    u64 rot;                                     // heavy outputs of the jobs in front of this one (block partition)
     unsigned T, o_lo, o_hi, pad;                 // global tile id; output slots [o_lo, o_hi) of this rank
 };
 
@@ -248,7 +248,6 @@ __global__ void __launch_bounds__(RF_THREADS) rf_ancestors_kernel(RfArgs a) {
     __shared__ u64 warp_tot[RF_THREADS / 32];
     __shared__ int buf[RF_CHUNK];
     __shared__ int wmaxs[RF_THREADS / 32];
-    __shared__ unsigned range[2];
     __shared__ u64 offs[MB_MAX_WORLD];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float wmax = rf_wmax(a);
@@ -263,12 +262,26 @@ __global__ void __launch_bounds__(RF_THREADS) rf_ancestors_kernel(RfArgs a) {
     const u64 offset = offs[a.rank];
 
     for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+        // the tile's output range follows from the tile prefix alone (block-uniform): a tile without offspring -- nearly
+        // every tile of a collapsed population -- is skipped WITHOUT reading its weights, a heavy one is only recorded
+        const u64 Cex = offset + a.prefix[tile], Cin = offset + a.prefix[tile + 1];
+        const unsigned o_lo = rf_count(g, Cex), o_hi = rf_count(g, Cin);
+        if (o_hi == o_lo) continue;                       // no offspring in this tile
+        if (o_hi - o_lo > RF_INLINE) {                    // collapsed weights: every rank fills its own share later (pass C)
+            if (threadIdx.x == 0) {
+                RfHeavy h;
+                h.Cex = Cex; h.Cin = Cin;
+                h.T = (unsigned)((int64_t)a.rank * a.ntiles + tile); h.pad = 0;
+                a.heavy[atomicAdd(&a.hdr->heavy_count, 1u)] = h;
+            }
+            continue;
+        }
         u64 e[RF_ITEMS];
         rf_load(a, a.in, tile * RF_TILE + (int64_t)threadIdx.x * RF_ITEMS, wmax, e);
         u64 tot = 0;
 #pragma unroll
         for (int k = 0; k < RF_ITEMS; ++k) tot += e[k];
-        u64 C = offset + a.prefix[tile] + rf_block_exclusive(tot, warp_tot);
+        u64 C = Cex + rf_block_exclusive(tot, warp_tot);
         // outputs below the cumulative weight: c_prev at the thread's exclusive prefix, then after every particle
         unsigned c[RF_ITEMS + 1];
         c[0] = rf_count(g, C);
@@ -276,21 +289,6 @@ __global__ void __launch_bounds__(RF_THREADS) rf_ancestors_kernel(RfArgs a) {
         for (int k = 0; k < RF_ITEMS; ++k) {
             C += e[k];
             c[k + 1] = (e[k] == 0) ? c[k] : rf_count(g, C);
-        }
-        if (threadIdx.x == 0) range[0] = c[0];
-        if (threadIdx.x == RF_THREADS - 1) range[1] = c[RF_ITEMS];
-        __syncthreads();
-        const unsigned o_lo = range[0], o_hi = range[1];
-        __syncthreads();
-        if (o_hi == o_lo) continue;                       // no offspring in this tile
-        if (o_hi - o_lo > RF_INLINE) {                    // collapsed weights: every rank fills its own share later (pass C)
-            if (threadIdx.x == 0) {
-                RfHeavy h;
-                h.Cex = offset + a.prefix[tile]; h.Cin = offset + a.prefix[tile + 1];
-                h.T = (unsigned)((int64_t)a.rank * a.ntiles + tile); h.pad = 0;
-                a.heavy[atomicAdd(&a.hdr->heavy_count, 1u)] = h;
-            }
-            continue;
         }
         const int32_t base = (int32_t)(gid0 + tile * RF_TILE) - 1;
         for (unsigned chunk_lo = o_lo; chunk_lo < o_hi; chunk_lo += RF_CHUNK) {
@@ -373,17 +371,18 @@ __global__ void __launch_bounds__(RF_THREADS) rf_gather_heavy_kernel(RfArgs a) {
         }
     }
     __syncthreads();
-    if (threadIdx.x == 0) {                               // rotation offsets (the order of the jobs is irrelevant: every
-        u64 rot = 0;                                      // output slot is written exactly once, with an exact value)
+    if (threadIdx.x == 0) {                               // running count of heavy outputs (the order of the jobs is
+        u64 rot = 0;                                      // irrelevant: every slot is written once, with an exact value)
         for (unsigned i = 0; i < njobs; ++i) {
             a.jobs[i].rot = rot;
-            rot += ((u64)(a.jobs[i].o_hi - a.jobs[i].o_lo) + RF_HEAVY_CHUNK - 1) / RF_HEAVY_CHUNK;
+            rot += (u64)(a.jobs[i].o_hi - a.jobs[i].o_lo);
         }
         a.hdr->heavy_total = njobs;
+        a.hdr->pad[0] = rot;                              // heavy outputs of this rank in total
     }
 }
 
-__global__ void __launch_bounds__(RF_THREADS) rf_heavy_kernel(RfArgs a) {
+__global__ void __launch_bounds__(RF_THREADS, 4) rf_heavy_kernel(RfArgs a) {
     if (a.predicated && (a.ctl->done || !a.ctl->resample)) return;
     const unsigned H = a.hdr->heavy_total;
     if (H == 0) return;
@@ -395,13 +394,16 @@ __global__ void __launch_bounds__(RF_THREADS) rf_heavy_kernel(RfArgs a) {
     const int64_t o_begin = (int64_t)a.rank * a.n_local;
     int32_t* anc = a.anc_peers[a.world <= 1 ? 0 : a.rank];
     __syncthreads();
+    // every block fills ONE contiguous share of this rank's heavy outputs (in the order of the jobs): it meets one or two
+    // jobs and derives their tiles once -- the first version rotated 8192-output work items over the blocks, so that
+    // every block re-derived (load, scan, counts) nearly every heavy tile for a single item of work
+    const u64 Htot = a.hdr->pad[0];
+    const u64 R_lo = Htot * blockIdx.x / gridDim.x, R_hi = Htot * (blockIdx.x + 1) / gridDim.x;
     for (unsigned en = 0; en < H; ++en) {
         const RfHeavyJob h = a.jobs[en];
-        const unsigned o_lo = h.o_lo, o_hi = h.o_hi;
-        const u64 items = ((u64)(o_hi - o_lo) + RF_HEAVY_CHUNK - 1) / RF_HEAVY_CHUNK;
-        // rotating block assignment: work item w of this job -> block (rot + w) % grid
-        const u64 first = ((u64)blockIdx.x + gridDim.x - h.rot % gridDim.x) % gridDim.x;
-        if (first >= items) continue;                     // block-uniform
+        const u64 s_lo = max(R_lo, h.rot), s_hi = min(R_hi, h.rot + (u64)(h.o_hi - h.o_lo));
+        if (s_lo >= s_hi) continue;                       // block-uniform
+        const unsigned w_lo = h.o_lo + (unsigned)(s_lo - h.rot), w_hi = h.o_lo + (unsigned)(s_hi - h.rot);
         const int q = (int)(h.T / (unsigned)a.ntiles);
         const int64_t tile = (int64_t)h.T - (int64_t)q * a.ntiles;
         u64 e[RF_ITEMS];
@@ -420,22 +422,18 @@ __global__ void __launch_bounds__(RF_THREADS) rf_heavy_kernel(RfArgs a) {
         if (threadIdx.x == RF_THREADS - 1) cs[RF_TILE] = cprev;
         __syncthreads();
         const int32_t base = (int32_t)((int64_t)q * a.n_local + tile * RF_TILE);
-        for (u64 wq = first; wq < items; wq += gridDim.x) {
-            const unsigned w_lo = o_lo + (unsigned)(wq * RF_HEAVY_CHUNK);
-            const unsigned w_hi = (unsigned)min((u64)o_hi, (u64)w_lo + RF_HEAVY_CHUNK);
-            // ancestor = last particle j with cs[j] <= o among those with offspring: upper_bound(cs, o) - 1.  A thread's
-            // outputs increase, so does j: the previous answer is tried first (one shared-memory read) -- with collapsed
-            // weights a handful of particles own nearly every output and the binary search runs once per work item
-            int lo = 0;
-            bool have = false;
-            for (unsigned o = w_lo + threadIdx.x; o < w_hi; o += RF_THREADS) {
-                if (!have || cs[lo + 1] <= o) {
-                    int hi = RF_TILE;
-                    while (lo < hi) { const int mid = (lo + hi) >> 1; if (cs[mid + 1] > o) hi = mid; else lo = mid + 1; }
-                    have = true;
-                }
-                anc[(int64_t)o - o_begin] = base + lo;
+        // ancestor = last particle j with cs[j] <= o among those with offspring: upper_bound(cs, o) - 1.  A thread's
+        // outputs increase, so does j: the previous answer is tried first (one shared-memory read) -- with collapsed
+        // weights a handful of particles own nearly every output and the binary search runs a few times per share
+        int lo = 0;
+        bool have = false;
+        for (unsigned o = w_lo + threadIdx.x; o < w_hi; o += RF_THREADS) {
+            if (!have || cs[lo + 1] <= o) {
+                int hi = RF_TILE;
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (cs[mid + 1] > o) hi = mid; else lo = mid + 1; }
+                have = true;
             }
+            anc[(int64_t)o - o_begin] = base + lo;
         }
         __syncthreads();
     }
@@ -519,7 +517,7 @@ extern "C" int mb_rs_ancestors(mb_ctx* ctx, void* ws, const float* in, int64_t n
     if (a.world > 1) return MB_OK;                        // sharded: mb_rs_heavy after a barrier over the ranks
     rf_gather_heavy_kernel<<<1, RF_THREADS, 0, st>>>(a);
     MB_CHECK_LAUNCH();
-    rf_heavy_kernel<<<(unsigned)(ctx->sms * 6), RF_THREADS, 0, st>>>(a);
+    rf_heavy_kernel<<<(unsigned)(ctx->sms * 4), RF_THREADS, 0, st>>>(a);
     MB_CHECK_LAUNCH();
     return MB_OK;
 }
@@ -535,7 +533,7 @@ extern "C" int mb_rs_heavy(mb_ctx* ctx, void* ws, const float* in, int64_t n, in
     cudaStream_t st = mb_s(stream);
     rf_gather_heavy_kernel<<<1, RF_THREADS, 0, st>>>(a);
     MB_CHECK_LAUNCH();
-    rf_heavy_kernel<<<(unsigned)(ctx->sms * 6), RF_THREADS, 0, st>>>(a);
+    rf_heavy_kernel<<<(unsigned)(ctx->sms * 4), RF_THREADS, 0, st>>>(a);
     MB_CHECK_LAUNCH();
     return MB_OK;
 }

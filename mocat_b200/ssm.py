@@ -146,9 +146,42 @@ class BootstrapFilter(ParticleFilter):
     name = 'Bootstrap Filter'
 
 
+class OptimalNonLinearGaussianParticleFilter(ParticleFilter):
+    """ssm/nonlinear_gaussian.py:134-276: the locally optimal proposal p(x_t | x_{t-1}, y_t) of a non-linear Gaussian
+    model with a linear-Gaussian observation, weight increment log N(y_t; H f(x_{t-1}), H Q H^T + R).  Compiled into
+    the Lorenz-96 step kernel (H = I, isotropic Q, R, P0: every matrix of `startup` :152-186 is a scalar, kept here
+    under the reference's attribute names)."""
+    name = 'Optimal Non-linear Gaussian Particle Filter'
+
+    def startup(self, ssm_scenario):
+        if not isinstance(ssm_scenario, Lorenz96):
+            raise _lib.MocatB200Error("OptimalNonLinearGaussianParticleFilter is compiled for Lorenz96 (H = I, isotropic "
+                                      "noise) only; no CPU fallback")
+        q2, r2, p2 = ssm_scenario.transition_std ** 2, ssm_scenario.likelihood_std ** 2, ssm_scenario.initial_std ** 2
+        eye = np.eye(ssm_scenario.dim)
+        self.initial_kalman_gain = p2 / (p2 + r2) * eye
+        self.initial_conditioned_covariance_sqrt = np.sqrt(1.0 / (1.0 / p2 + 1.0 / r2)) * eye
+        self.initial_conditioned_precision_sqrt = eye / np.sqrt(1.0 / (1.0 / p2 + 1.0 / r2))
+        self.proposal_kalman_gain = q2 / (q2 + r2) * eye
+        self.proposal_covariance_sqrt = np.sqrt(q2 * r2 / (q2 + r2)) * eye
+        self.proposal_precision_sqrt = eye / np.sqrt(q2 * r2 / (q2 + r2))
+        self.weight_precision_sqrt = eye / np.sqrt(q2 + r2)
+
+
 def _check_filter(pf):
-    if not isinstance(pf, BootstrapFilter):
-        raise _lib.MocatB200Error("only BootstrapFilter is compiled into the device step (no CPU fallback)")
+    if not isinstance(pf, (BootstrapFilter, OptimalNonLinearGaussianParticleFilter)):
+        raise _lib.MocatB200Error("only BootstrapFilter and OptimalNonLinearGaussianParticleFilter are compiled into the "
+                                  "device step (no CPU fallback)")
+
+
+def _device_ssm(ssm_scenario, particle_filter, dt=None):
+    """POD model of the scenario with the filter's proposal folded in"""
+    s = ssm_scenario._ssm() if dt is None else ssm_scenario._ssm(dt)
+    if isinstance(particle_filter, OptimalNonLinearGaussianParticleFilter):
+        if int(s.kind) != _lib.SSM_LORENZ96:
+            raise _lib.MocatB200Error("OptimalNonLinearGaussianParticleFilter: Lorenz96 only (no CPU fallback)")
+        s.proposal = _lib.PROPOSAL_OPTIMAL
+    return s
 
 
 def _moments(eng):
@@ -207,7 +240,7 @@ def initiate_particles(ssm_scenario, particle_filter, n, random_key, y=None, t=N
     if y is None:
         raise _lib.MocatB200Error("initiate_particles needs the first observation y")
     y = np.atleast_1d(np.asarray(y, np.float32))
-    eng = engine.PFEngine.acquire(ssm_scenario._ssm(), n, key_to_seed(random_key), ess_threshold=ess_threshold,
+    eng = engine.PFEngine.acquire(_device_ssm(ssm_scenario, particle_filter), n, key_to_seed(random_key), ess_threshold=ess_threshold,
                                   resampling=_RESAMPLING[resampling])
     eng.init(torch.as_tensor(y, device="cuda"))
     c = eng.ctl.read()
@@ -258,7 +291,7 @@ def propagate_particle_filter(ssm_scenario, particle_filter, particles, y_new, t
     eng.ess_threshold = float(ess_threshold)
     y_new = np.atleast_1d(np.asarray(y_new, np.float32))
     t_prev = float(particles.t[-1])
-    eng.ssm = ssm_scenario._ssm(float(t_new) - t_prev)
+    eng.ssm = _device_ssm(ssm_scenario, particle_filter, float(t_new) - t_prev)
     # the resample decision for this step was taken on the device with the threshold stored in the control
     # block by the previous step; refresh it if the caller changed ess_threshold
     c = eng.ctl.read()
@@ -309,11 +342,11 @@ def run_particle_filter_for_marginals(ssm_scenario, particle_filter, y, t, rando
     if len(t_all) > 2 and not np.allclose(np.diff(t_all), dt):
         raise _lib.MocatB200Error("run_particle_filter_for_marginals needs equally spaced t (time-homogeneous model)")
     if initial_sample is None:
-        eng = _make_engine(ssm_scenario._ssm(dt), n, key_to_seed(random_key), ess_threshold, _RESAMPLING[resampling])
+        eng = _make_engine(_device_ssm(ssm_scenario, particle_filter, dt), n, key_to_seed(random_key), ess_threshold, _RESAMPLING[resampling])
     else:
         eng = _engine_of(initial_sample)
         eng.ess_threshold = float(ess_threshold)
-        eng.ssm = ssm_scenario._ssm(dt)
+        eng.ssm = _device_ssm(ssm_scenario, particle_filter, dt)
         c = eng.ctl.read()
         want = 1 if c['ess'] < ess_threshold * eng.n_total else 0
         if want != c['resample']:

@@ -117,3 +117,48 @@ def test_exact_cdf_is_order_and_sharding_independent():
             assert np.array_equal(glued, ref)
         perm = rng.permutation(n)                                           # any permutation: same total bits
         assert np.cumsum(q[perm])[-1] == total
+
+
+def test_optimal_proposal_oracle_agrees_with_bootstrap_and_reference_matrices():
+    """oracle.pf.OptimalPF (scalar form of OptimalNonLinearGaussianParticleFilter, ssm/nonlinear_gaussian.py:134-276):
+    (i) its scalars equal the matrices the reference's `startup` (:152-186) builds for Q = q^2 I, R = r^2 I, H = I;
+    (ii) it estimates the same log-evidence / filtering mean as the bootstrap filter, with a larger ESS"""
+    import numpy as np
+    from oracle import models as om, pf as opf
+    q, r, p0, d = 0.7, 1.3, 2.0, 4
+    Q, R, P0, H = q * q * np.eye(d), r * r * np.eye(d), p0 * p0 * np.eye(d), np.eye(d)
+    Wp = np.linalg.inv(H @ Q @ H.T + R)                                   # weight_precision :170-171
+    Kp = Q @ H.T @ Wp                                                     # proposal_kalman_gain (utils kalman_gain)
+    Pc = Q - Kp @ H @ Q                                                   # proposal_cov :174-176
+    K0 = P0 @ H.T @ np.linalg.inv(H @ P0 @ H.T + R)
+    P0c = np.linalg.inv(np.linalg.inv(P0) + H.T @ np.linalg.inv(R) @ H)   # inverse of init_cond_prec :163-164
+    v = q * q + r * r
+    np.testing.assert_allclose(Kp, q * q / v * np.eye(d), atol=1e-12)
+    np.testing.assert_allclose(Pc, q * q * r * r / v * np.eye(d), atol=1e-12)
+    np.testing.assert_allclose(Wp, np.eye(d) / v, atol=1e-12)
+    np.testing.assert_allclose(K0, p0 * p0 / (p0 * p0 + r * r) * np.eye(d), atol=1e-12)
+    np.testing.assert_allclose(P0c, np.eye(d) / (1 / p0 ** 2 + 1 / r ** 2), atol=1e-12)
+    ssm = om.Lorenz96SSM(dim=8, init_mean=3.0)
+    rng = np.random.default_rng(0)                                        # data consistent with the prior (x_0 ~ N(m0, P0)):
+    x = ssm.initial_sample(rng.standard_normal(ssm.dim))                  # the bootstrap estimate is then reliable too
+    ys = []
+    for t in range(5):
+        if t > 0:
+            x = ssm.transition_sample(x, rng.standard_normal(ssm.dim))
+        ys.append(x + ssm.r_std * rng.standard_normal(ssm.dim))
+    ys = np.array(ys)
+    res = {}
+    for name, cls in (("boot", opf.BootstrapPF), ("opt", opf.OptimalPF)):
+        lz, ess, mean = [], [], []
+        for seed in range(3):
+            out = cls(ssm, 60000, seed, ess_threshold=0.5, resampling='systematic', normal_dtype=np.float32).run(ys)
+            lz.append(out[-1]['log_z']); ess.append(np.mean([s['ess'] for s in out[1:]]))
+            mean.append(opf.weighted_moments(out[-1]['x'], out[-1]['lw'])[0])
+        res[name] = (np.mean(lz), np.std(lz), np.mean(ess), np.mean(mean, axis=0))
+    assert res["opt"][2] > 2.0 * res["boot"][2]
+    # the reference's optimal filter starts from ZERO log-weights (:209-214), i.e. its running evidence lacks the factor
+    # p(y_0) = N(y_0; m_0, (p0^2 + r^2) I) the bootstrap weights carry
+    v0 = ssm.init_std ** 2 + ssm.r_std ** 2
+    lp_y0 = -0.5 * np.sum((ys[0] - ssm.init_mean) ** 2) / v0 - 0.5 * ssm.dim * np.log(2 * np.pi * v0)
+    assert abs(res["opt"][0] + lp_y0 - res["boot"][0]) < 0.5 + 3 * (res["opt"][1] + res["boot"][1])
+    np.testing.assert_allclose(res["opt"][3], res["boot"][3], atol=0.25)
