@@ -283,12 +283,15 @@ __global__ void __launch_bounds__(RF_THREADS) rf_ancestors_kernel(RfArgs a) {
         for (int k = 0; k < RF_ITEMS; ++k) tot += e[k];
         u64 C = Cex + rf_block_exclusive(tot, warp_tot);
         // outputs below the cumulative weight: c_prev at the thread's exclusive prefix, then after every particle
+        // (a thread whose 16 particles have no offspring between them -- the rule in the light tail of a collapsed
+        // population -- settles with the two counts at the ends of its range)
         unsigned c[RF_ITEMS + 1];
         c[0] = rf_count(g, C);
+        const bool barren = tot == 0 || rf_count(g, C + tot) == c[0];
 #pragma unroll
         for (int k = 0; k < RF_ITEMS; ++k) {
             C += e[k];
-            c[k + 1] = (e[k] == 0) ? c[k] : rf_count(g, C);
+            c[k + 1] = (barren || e[k] == 0) ? c[k] : rf_count(g, C);
         }
         const int32_t base = (int32_t)(gid0 + tile * RF_TILE) - 1;
         for (unsigned chunk_lo = o_lo; chunk_lo < o_hi; chunk_lo += RF_CHUNK) {
@@ -399,10 +402,17 @@ __global__ void __launch_bounds__(RF_THREADS, 4) rf_heavy_kernel(RfArgs a) {
     // every block re-derived (load, scan, counts) nearly every heavy tile for a single item of work
     const u64 Htot = a.hdr->pad[0];
     const u64 R_lo = Htot * blockIdx.x / gridDim.x, R_hi = Htot * (blockIdx.x + 1) / gridDim.x;
-    for (unsigned en = 0; en < H; ++en) {
+    if (R_lo >= R_hi) return;
+    unsigned en = 0;                                      // last job that starts at or before R_lo (rot increases with the job)
+    for (unsigned lo_j = 0, hi_j = H; lo_j < hi_j;) {
+        const unsigned mid = (lo_j + hi_j) >> 1;
+        if (a.jobs[mid].rot <= R_lo) { en = mid; lo_j = mid + 1; } else hi_j = mid;
+    }
+    for (; en < H; ++en) {
         const RfHeavyJob h = a.jobs[en];
+        if (h.rot >= R_hi) break;                         // block-uniform
         const u64 s_lo = max(R_lo, h.rot), s_hi = min(R_hi, h.rot + (u64)(h.o_hi - h.o_lo));
-        if (s_lo >= s_hi) continue;                       // block-uniform
+        if (s_lo >= s_hi) continue;
         const unsigned w_lo = h.o_lo + (unsigned)(s_lo - h.rot), w_hi = h.o_lo + (unsigned)(s_hi - h.rot);
         const int q = (int)(h.T / (unsigned)a.ntiles);
         const int64_t tile = (int64_t)h.T - (int64_t)q * a.ntiles;

@@ -168,8 +168,18 @@ __global__ void __launch_bounds__(256) svgd_tc_colsum_kernel(const float* __rest
     __shared__ double sm[4][64];
     const int c = threadIdx.x & 63, rg = threadIdx.x >> 6;
     double s = 0.0;
-    if (c < d)
-        for (int i = blockIdx.x * 4 + rg; i < n; i += gridDim.x * 4) s += (double)X[(int64_t)i * d + c];
+    if (c < d) {                                                       // 8 independent loads in flight per thread
+        int i = blockIdx.x * 4 + rg;
+        const int step = gridDim.x * 4;
+        for (; i + 7 * step < n; i += 8 * step) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = X[(int64_t)(i + u * step) * d + c];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s += (double)v[u];
+        }
+        for (; i < n; i += step) s += (double)X[(int64_t)i * d + c];
+    }
     sm[rg][c] = s;
     __syncthreads();
     if (rg == 0) part[blockIdx.x * 64 + c] = sm[0][c] + sm[1][c] + sm[2][c] + sm[3][c];
@@ -489,9 +499,9 @@ int mb_svgd_phi_tc(mb_ctx* ctx, const float* X, const float* G, int n, int d, co
     float* xs = reinterpret_cast<float*>(align(WT + bw));
     float* saux = reinterpret_cast<float*>(align(reinterpret_cast<uint8_t*>(xs) + bs));
     float* opart = reinterpret_cast<float*>(align(reinterpret_cast<uint8_t*>(saux) + ba));
-    double* cpart = reinterpret_cast<double*>((char*)ctx->scratch + (3u << 20) + (64u << 10));   // 148 x 64 doubles
-    svgd_tc_colsum_kernel<<<ctx->sms, 256, 0, st>>>(X, n, d, cpart);
-    svgd_tc_colmean_kernel<<<1, 1024, 0, st>>>(cpart, ctx->sms, n, d, mean);
+    double* cpart = reinterpret_cast<double*>((char*)ctx->scratch + (3u << 20) + (64u << 10));   // 4 x 148 x 64 doubles
+    svgd_tc_colsum_kernel<<<ctx->sms * 4, 256, 0, st>>>(X, n, d, cpart);
+    svgd_tc_colmean_kernel<<<1, 1024, 0, st>>>(cpart, ctx->sms * 4, n, d, mean);
     TcPrepArgs p{X, G, mean, bandwidth, n, d, n_pad, NV, XA, WT, xs, saux};
     svgd_tc_rows_kernel<<<(unsigned)(((int64_t)n_pad * 8 + 255) / 256), 256, 0, st>>>(p);
     svgd_tc_wt_kernel<<<(unsigned)(((int64_t)tiles * NV * 16 + 255) / 256), 256, 0, st>>>(p);
@@ -701,6 +711,60 @@ __global__ void __launch_bounds__(256) svgd_dist_sample_kernel(const float* __re
     for (int k = 0; k < d; ++k) { const float t = xi[k] - xj[k]; s = fmaf(t, t, s); }
     out[p] = s;
 }
+// Bracket of the median from the sample distances by ONE block (replaces two radix selects, 16 launches): min / max,
+// a DT_SBINS-bin histogram of the samples over [min, max] in shared memory, and the outer edges of the bins that hold
+// the sample quantiles q_lo, q_hi (one bin of slack on either side: the bin of a sample is computed in fp32); the
+// result goes to q[0] (lo) and q[3] (hi), the inputs of svgd_dist_bracket_kernel.
+#define DT_SBINS 16384
+__global__ void __launch_bounds__(1024) svgd_dist_sample_bracket_kernel(const float* __restrict__ smp, int ns, double q_lo,
+                                                                        double q_hi, double* q /*[2][3]*/) {
+    extern __shared__ uint32_t sh[];                                   // [DT_SBINS]
+    __shared__ float wmn[32], wmx[32];
+    __shared__ uint32_t wsum[32];
+    __shared__ int bins[2];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    float mn = INFINITY, mx = -INFINITY;
+    for (int i = tid; i < ns; i += 1024) { const float v = smp[i]; mn = fminf(mn, v); mx = fmaxf(mx, v); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { mn = fminf(mn, __shfl_xor_sync(MB_FULL, mn, o)); mx = fmaxf(mx, __shfl_xor_sync(MB_FULL, mx, o)); }
+    if (lane == 0) { wmn[w] = mn; wmx[w] = mx; }
+    if (tid == 0) { bins[0] = 0; bins[1] = DT_SBINS - 1; }
+    for (int b = tid; b < DT_SBINS; b += 1024) sh[b] = 0;
+    __syncthreads();
+    mn = wmn[0]; mx = wmx[0];
+#pragma unroll
+    for (int k = 1; k < 32; ++k) { mn = fminf(mn, wmn[k]); mx = fmaxf(mx, wmx[k]); }
+    const float scale = (mx > mn) ? (float)DT_SBINS / (mx - mn) : 0.f;
+    for (int i = tid; i < ns; i += 1024) {
+        const int b = min(DT_SBINS - 1, (int)((smp[i] - mn) * scale));
+        atomicAdd(&sh[b], 1u);
+    }
+    __syncthreads();
+    // exclusive scan: 16 consecutive bins per thread
+    uint32_t c[16], loc = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) { c[k] = sh[tid * 16 + k]; loc += c[k]; }
+    uint32_t inc = loc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(MB_FULL, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) wsum[w] = inc;
+    __syncthreads();
+    uint32_t cum = inc - loc;
+    for (int k = 0; k < w; ++k) cum += wsum[k];
+    const uint32_t ranks[2] = {(uint32_t)floor(q_lo * (double)(ns - 1)), (uint32_t)ceil(q_hi * (double)(ns - 1))};
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        for (int r = 0; r < 2; ++r)
+            if (ranks[r] >= cum && ranks[r] < cum + c[k]) bins[r] = tid * 16 + k;
+        cum += c[k];
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const double bw = (mx > mn) ? ((double)mx - (double)mn) / (double)DT_SBINS : 0.0;
+        q[0] = fmax((double)mn + (double)(bins[0] - 1) * bw, 0.0);
+        q[3] = (double)mn + (double)(bins[1] + 2) * bw;
+    }
+}
 __global__ void svgd_dist_bracket_kernel(const double* q /*[2][3]*/, DtBracket* br, uint32_t* hist, unsigned long long* below) {
     const int i = threadIdx.x;
     for (int b = i; b < DT_BINS; b += blockDim.x) hist[b] = 0;
@@ -826,8 +890,8 @@ int mb_pairdist_partial_tc(mb_ctx* ctx, const float* X, int n, int d, int mode, 
     double* dsum = reinterpret_cast<double*>((char*)acc + 72);
     uint32_t* hist = reinterpret_cast<uint32_t*>((char*)acc + 1024);
     double* cpart = reinterpret_cast<double*>((char*)ctx->scratch + (3u << 20) + (64u << 10));
-    svgd_tc_colsum_kernel<<<ctx->sms, 256, 0, st>>>(X, n, d, cpart);
-    svgd_tc_colmean_kernel<<<1, 1024, 0, st>>>(cpart, ctx->sms, n, d, mean);
+    svgd_tc_colsum_kernel<<<ctx->sms * 4, 256, 0, st>>>(X, n, d, cpart);
+    svgd_tc_colmean_kernel<<<1, 1024, 0, st>>>(cpart, ctx->sms * 4, n, d, mean);
     TcPrepArgs p{X, nullptr, mean, nullptr, n, d, n_pad, NV, XA, WT, xs, saux};
     svgd_tc_rows_kernel<<<(unsigned)(((int64_t)n_pad * 8 + 255) / 256), 256, 0, st>>>(p);
     svgd_tc_wt_kernel<<<(unsigned)(((int64_t)tiles * NV * 16 + 255) / 256), 256, 0, st>>>(p);
@@ -837,10 +901,8 @@ int mb_pairdist_partial_tc(mb_ctx* ctx, const float* X, int n, int d, int mode, 
     if (mode == 0) {
         svgd_dist_sample_kernel<<<DT_SAMPLES / 256, 256, 0, st>>>(X, n, d, smp);
         const double delta = 3.0 / sqrt((double)DT_SAMPLES);           // 6 sigma of the sample median's quantile level
-        int rc = mb_quantile_impl(ctx, smp, DT_SAMPLES, nullptr, 0.5 - delta, qout, st);
-        if (rc != MB_OK) return rc;
-        rc = mb_quantile_impl(ctx, smp, DT_SAMPLES, nullptr, 0.5 + delta, qout + 3, st);
-        if (rc != MB_OK) return rc;
+        MB_CUDA(cudaFuncSetAttribute(svgd_dist_sample_bracket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DT_SBINS * 4));
+        svgd_dist_sample_bracket_kernel<<<1, 1024, DT_SBINS * 4, st>>>(smp, DT_SAMPLES, 0.5 - delta, 0.5 + delta, qout);
         svgd_dist_bracket_kernel<<<1, 256, 0, st>>>(qout, br, hist, below);
         if (grid > 0) {
             MB_CUDA(cudaFuncSetAttribute(svgd_dist_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -911,32 +973,51 @@ __global__ void __launch_bounds__(256) logit_wt_kernel(const float* __restrict__
     const uint32_t off = (uint32_t)(q >> 3) * (uint32_t)(TC_K * 128) + sw128_off(c, (q & 7) * 8);
     *reinterpret_cast<uint4*>(WT + (int64_t)tile * (TC_K * 256) + off) = *reinterpret_cast<uint4*>(v);
 }
-__global__ void logit_b_kernel(const float* __restrict__ A, const float* __restrict__ t, int N, int d, float* b) {
-    const int k = threadIdx.x;
-    if (k >= d) return;
+// b = A^T t (exact fp32, constant of the scenario): 16 row groups x 64 columns, fixed-order merge
+__global__ void __launch_bounds__(1024) logit_b_kernel(const float* __restrict__ A, const float* __restrict__ t, int N, int d, float* b) {
+    __shared__ float sm[16][64];
+    const int k = threadIdx.x & 63, g = threadIdx.x >> 6;
     float s = 0.f;
-    for (int j = 0; j < N; ++j) s = fmaf(t[j], A[(int64_t)j * d + k], s);
-    b[k] = s;
+    if (k < d)
+        for (int j = g; j < N; j += 16) s = fmaf(t[j], A[(int64_t)j * d + k], s);
+    sm[g][k] = s;
+    __syncthreads();
+    if (g == 0 && k < d) {
+        float acc = 0.f;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) acc += sm[q][k];
+        b[k] = acc;
+    }
 }
 struct LogitFinishArgs {
     const float* W; const float* b; const float* opart; const float* upart; int n, d, n_pad, N, N_pad;
     float prior_mean, prior_pscale, beta; float* U; float* G;
 };
-__global__ void __launch_bounds__(128) logit_finish_kernel(LogitFinishArgs a) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.n) return;
+// one thread per (particle, coordinate): 4 particles x 64 coordinates per block, every access coalesced; the potential's
+// sums over the coordinates are reduced by shuffles (fixed order)
+__global__ void __launch_bounds__(256) logit_finish_kernel(LogitFinishArgs a) {
+    __shared__ float red[4][2][2];
+    const int k = threadIdx.x & 63, r = threadIdx.x >> 6, half = (threadIdx.x >> 5) & 1;
+    const int i = blockIdx.x * 4 + r;
     float up = 0.f, wb = 0.f;
-    for (int k = 0; k < a.d; ++k) {
-        const float w = a.W[(int64_t)i * a.d + k];
+    if (i < a.n && k < a.d) {
+        const float w = a.W[(int64_t)i * a.d + k], bk = a.b[k];
         float o = 0.f;
 #pragma unroll
         for (int p = 0; p < TC_SPLIT; ++p) o += a.opart[((int64_t)p * a.n_pad + i) * TC_K + k];
-        const float r = (w - a.prior_mean) * a.prior_pscale;
-        up = fmaf(0.5f * r, r, up);
-        wb = fmaf(w, a.b[k], wb);
-        a.G[(int64_t)i * a.d + k] = fmaf(a.beta, o - a.b[k], r * a.prior_pscale);
+        const float rr = (w - a.prior_mean) * a.prior_pscale;
+        up = 0.5f * rr * rr;
+        wb = w * bk;
+        a.G[(int64_t)i * a.d + k] = fmaf(a.beta, o - bk, rr * a.prior_pscale);
     }
-    if (a.U) {
+    if (!a.U) return;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { up += __shfl_xor_sync(MB_FULL, up, o); wb += __shfl_xor_sync(MB_FULL, wb, o); }
+    if ((threadIdx.x & 31) == 0) { red[r][half][0] = up; red[r][half][1] = wb; }
+    __syncthreads();
+    if (k == 0 && i < a.n) {
+        up = red[r][0][0] + red[r][1][0];
+        wb = red[r][0][1] + red[r][1][1];
         float sp = 0.f;
         for (int p = 0; p < TC_SPLIT; ++p)
             for (int q = 0; q < 4; ++q) sp += a.upart[(((int64_t)p * a.n_pad + i) << 2) + q];
@@ -962,7 +1043,7 @@ int mb_logistic_potential_grad_tc(mb_ctx* ctx, const float* features, const floa
     uint8_t* WT = align(XA + bx);
     float* opart = reinterpret_cast<float*>(align(WT + bw));
     float* upart = reinterpret_cast<float*>(align(reinterpret_cast<uint8_t*>(opart) + bo));
-    logit_b_kernel<<<1, 64, 0, st>>>(features, labels, N, d, b);
+    logit_b_kernel<<<1, 1024, 0, st>>>(features, labels, N, d, b);
     logit_rows_kernel<<<(unsigned)(((int64_t)n_pad * 8 + 255) / 256), 256, 0, st>>>(W, n, d, n_pad, XA);
     logit_wt_kernel<<<(unsigned)(((int64_t)jtiles * NV * 16 + 255) / 256), 256, 0, st>>>(features, N, d, N_pad, WT);
     MB_CHECK_LAUNCH();
@@ -972,7 +1053,7 @@ int mb_logistic_potential_grad_tc(mb_ctx* ctx, const float* features, const floa
     svgd_phi_tc_kernel<1><<<tiles * TC_SPLIT, TC_THREADS, smem, st>>>(a);
     MB_CHECK_LAUNCH();
     LogitFinishArgs f{W, b, opart, upart, n, d, n_pad, N, N_pad, prior_mean, prior_pscale, beta, U, G};
-    logit_finish_kernel<<<(n + 127) / 128, 128, 0, st>>>(f);
+    logit_finish_kernel<<<(n + 3) / 4, 256, 0, st>>>(f);
     MB_CHECK_LAUNCH();
     return MB_OK;
 }
