@@ -102,7 +102,9 @@ typedef struct {             /* adaptive likelihood tempering, transport/smc.py:
 enum { MB_SSM_LINEAR_GAUSSIAN = 0,  /* ssm/linear_gaussian/linear_gaussian.py:142-261 */
        MB_SSM_LORENZ96 = 1 };       /* ssm/scenarios/lorenz96.py:14-44 on ssm/nonlinear_gaussian.py:19-131 */
 enum { MB_PROPOSAL_BOOTSTRAP = 0,   /* ssm/filtering.py:142-170 */
-       MB_PROPOSAL_OPTIMAL = 1 };   /* ssm/nonlinear_gaussian.py:134-276 (H = I, diagonal noise) */
+       MB_PROPOSAL_OPTIMAL = 1,     /* ssm/nonlinear_gaussian.py:134-276 (H = I, diagonal noise) */
+       MB_PROPOSAL_ENKF = 2 };      /* ssm/nonlinear_gaussian.py:279-350: conditioned initial sample as OPTIMAL, forecast =
+                                       the bootstrap step, analysis = mb_enkf_analysis */
 
 typedef struct {
     int32_t kind, dim, dim_obs, substeps;
@@ -269,6 +271,20 @@ int mb_pf_l96_step(mb_ctx* ctx, const mb_ssm* ssm, const float* x_in_rows, float
                    int64_t n_total, const int32_t* anc, const float* y, float* lw, uint64_t seed, uint32_t t,
                    int64_t gid0, double ess_threshold, mb_control* ctl, mb_hist* hist, const mb_shard* sh /*or NULL*/,
                    mb_comm* comm /*or NULL*/, mb_stream_t stream);
+/* ---- ensemble Kalman filter (EnsembleKalmanFilter, ssm/nonlinear_gaussian.py:279-350; H = I, R = r_std^2 I) on the
+ *      row-major population of the Lorenz-96 engine.
+ *      mb_rows_mean_cov: ensemble mean[d] and unbiased covariance cov[d][d] (device fp64; either may be NULL) of the
+ *      rows (spread_matrix spread_matrix^T, :339) and the Kalman gain K = P (P + r_std^2 I)^-1 (:341-343,
+ *      utils.py:477-484) as device float gain[d][d] (fp64 Cholesky on one block).
+ *      mb_enkf_analysis: the same, then x_i <- x_i + K (y - x_i - r_std z_i) for every row (:345-348; z_i: Philox
+ *      normals of particle gid0 + i, purpose MB_P_SIM = 3, step t), log-weights zero (:350), control block / history
+ *      record t set to equal weights (ess = n).  x_rows holds the FORECAST ensemble f(x) + q z, i.e. the output of
+ *      mb_pf_l96_step without resampling.  d in {8, 16, 40}. */
+int mb_rows_mean_cov(mb_ctx* ctx, const float* x_rows, int64_t n, int d, float r_std, double* mean /*or NULL*/,
+                     double* cov /*or NULL*/, float* gain, mb_stream_t stream);
+int mb_enkf_analysis(mb_ctx* ctx, const mb_ssm* ssm, float* x_rows, int64_t n, const float* y, float* lw, uint64_t seed,
+                     uint32_t t, int64_t gid0, mb_control* ctl, mb_hist* hist /*or NULL*/, float* gain,
+                     double* mean /*or NULL*/, double* cov /*or NULL*/, mb_stream_t stream);
 /* gather of a row-major (n, d) population by ancestor (cdict.__getitem__, core.py:46-56; resample_particles,
  * filtering.py:202-217).  staged != 0: source rows fetched by the TMA engine -- one cp.async.bulk of the span when the
  * 32 ancestors of a warp are close, else one d*4-byte copy per ancestor -- and the gathered rows leave with one bulk

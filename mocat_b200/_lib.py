@@ -22,7 +22,7 @@ LIK_RASTRIGIN, LIK_GAUSSIAN, LIK_NONE = 0, 1, 2
 MOVE_MALA, MOVE_RW = 0, 1
 RESAMPLE_SYSTEMATIC, RESAMPLE_MULTINOMIAL = 0, 1
 SSM_LINEAR_GAUSSIAN, SSM_LORENZ96 = 0, 1
-PROPOSAL_BOOTSTRAP, PROPOSAL_OPTIMAL = 0, 1
+PROPOSAL_BOOTSTRAP, PROPOSAL_OPTIMAL, PROPOSAL_ENKF = 0, 1, 2
 
 c_f, c_d, c_i32, c_i64, c_u32, c_u64, c_vp = C.c_float, C.c_double, C.c_int32, C.c_int64, C.c_uint32, C.c_uint64, C.c_void_p
 
@@ -139,6 +139,9 @@ SIGNATURES = {
     "mb_weighted_moments_rows": (C.c_int, [c_vp, c_vp, c_i64, C.c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "mb_weighted_moment_sums_rows": (C.c_int, [c_vp, c_vp, c_i64, C.c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "mb_gather_rows": (C.c_int, [c_vp, c_vp, c_i64, C.c_int, c_vp, c_i64, c_vp, C.c_int, c_vp]),
+    "mb_rows_mean_cov": (C.c_int, [c_vp, c_vp, c_i64, C.c_int, c_f, c_vp, c_vp, c_vp, c_vp]),
+    "mb_enkf_analysis": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_u64, C.c_uint32, c_i64, c_vp, c_vp, c_vp, c_vp,
+                                   c_vp, c_vp]),
     "mb_rs_workspace_bytes": (C.c_size_t, [c_i64]),
     "mb_rs_tile_sums": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, C.c_int, c_vp, C.c_int, c_vp]),
     "mb_rs_ancestors": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, C.c_int, c_vp, C.c_int, c_i64, c_vp, c_vp, c_vp, c_vp]),

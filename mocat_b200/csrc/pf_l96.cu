@@ -410,7 +410,8 @@ static int l96_dispatch(mb_ctx* ctx, const mb_ssm* ssm, L96Args& a, bool init, c
     a.forcing = ssm->forcing; a.h = ssm->dt / (float)ssm->substeps; a.ir = 1.f / ssm->r_std;
     a.lik_const = ssm->lik_const; a.zmean = ssm->init_mean; a.substeps = ssm->substeps;
     double sd = init ? (double)ssm->init_std : (double)ssm->q_std;             // z * sd = sqrt(-2 ln u1 sd^2) * (cos, sin)
-    const bool opt = ssm->proposal == MB_PROPOSAL_OPTIMAL;
+    // the ensemble Kalman filter draws its initial ensemble like the optimal filter (:313-323); its forecast is the bootstrap step
+    const bool opt = ssm->proposal == MB_PROPOSAL_OPTIMAL || (init && ssm->proposal == MB_PROPOSAL_ENKF);
     if (opt) {                                                                 // scalars of the optimal proposal (see l96_body)
         const double q2 = (double)ssm->q_std * ssm->q_std, r2 = (double)ssm->r_std * ssm->r_std;
         const double p2 = (double)ssm->init_std * ssm->init_std, v = q2 + r2;

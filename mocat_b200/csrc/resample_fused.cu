@@ -87,9 +87,21 @@ __device__ __forceinline__ float rf_wmax(const RfArgs& a) {
     return wmax;
 }
 
+// rint(x) as uint64 without the 64-bit F2I (an XU-pipe instruction at 1/8 rate -- it bound pass A at 47 % of the HBM
+// peak): below 2^23 the add of 2^23 rounds to nearest-even into the mantissa, above it x already is an integer and the
+// mantissa is shifted into place.  NaN, negative, zero -> 0, as the saturating conversion gave.
+__device__ __forceinline__ u64 rf_rint_u64(float x) {
+    if (!(x > 0.f)) return 0ull;
+    if (x < 8388608.f) return (u64)(__float_as_uint(x + 8388608.f) - 0x4B000000u);
+    const uint32_t bits = __float_as_uint(x);
+    const int sh = (int)(bits >> 23) - 150;
+    if (sh >= 40) return __float2ull_rn(x);                           // >= 2^63: saturating conversion (never in log mode)
+    return (u64)((bits & 0x7fffffu) | 0x800000u) << sh;
+}
+
 __device__ __forceinline__ u64 rf_weight(float v, bool log_mode, float wmax, float scale) {
     const float w = log_mode ? __expf(v - wmax) : v;
-    return __float2ull_rn(w * scale);                                 // NaN, negative -> 0
+    return rf_rint_u64(w * scale);                                    // NaN, negative -> 0
 }
 
 // 16 consecutive weights of this thread -> integer weights e[] (zero beyond n)
@@ -117,39 +129,31 @@ __device__ __forceinline__ u64 warp_sum_u64(u64 v) {
 // ------------------------------------------------------------------------------------------------ pass A
 __global__ void __launch_bounds__(RF_THREADS) rf_tile_sums_kernel(RfArgs a) {
     if (a.predicated && (a.ctl->done || !a.ctl->resample)) return;
-    __shared__ u64 wsum[RF_THREADS / 32];
     __shared__ bool is_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float wmax = rf_wmax(a);
-    for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-        // coalesced: thread t takes float4 number t + 256 q of the tile (the sum does not care about the order)
+    // one WARP per tile (32 float4 per lane, 8 in flight): no block barrier, no shared memory in the streaming part
+    for (int64_t tile = (int64_t)blockIdx.x * (RF_THREADS / 32) + warp; tile < a.ntiles; tile += (int64_t)gridDim.x * (RF_THREADS / 32)) {
         u64 s = 0;
         const int64_t tb = tile * RF_TILE;
         if (tb + RF_TILE <= a.n && (((uintptr_t)a.in & 15) == 0)) {
-            const float4* p = reinterpret_cast<const float4*>(a.in + tb);
-#pragma unroll
-            for (int q = 0; q < RF_ITEMS / 4; ++q) {
-                const float4 v = __ldcs(p + q * RF_THREADS + threadIdx.x);
+            const float4* p = reinterpret_cast<const float4*>(a.in + tb) + lane;
+#pragma unroll 8
+            for (int q = 0; q < RF_TILE / 128; ++q) {
+                const float4 v = __ldcs(p + q * 32);
                 s += rf_weight(v.x, a.log_mode, wmax, a.scale) + rf_weight(v.y, a.log_mode, wmax, a.scale) +
                      rf_weight(v.z, a.log_mode, wmax, a.scale) + rf_weight(v.w, a.log_mode, wmax, a.scale);
             }
         } else {
-            for (int q = 0; q < RF_ITEMS; ++q) {
-                const int64_t i = tb + q * RF_THREADS + threadIdx.x;
+            for (int q = 0; q < RF_TILE / 32; ++q) {
+                const int64_t i = tb + q * 32 + lane;
                 if (i < a.n) s += rf_weight(a.in[i], a.log_mode, wmax, a.scale);
             }
         }
         s = warp_sum_u64(s);
-        if (lane == 0) wsum[warp] = s;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            u64 t = 0;
-#pragma unroll
-            for (int w = 0; w < RF_THREADS / 32; ++w) t += wsum[w];
-            a.prefix[tile] = t;
-        }
-        __syncthreads();
+        if (lane == 0) a.prefix[tile] = s;
     }
+    __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
         is_last = (atomicAdd(&a.hdr->done_counter, 1u) == gridDim.x - 1);
@@ -157,25 +161,44 @@ __global__ void __launch_bounds__(RF_THREADS) rf_tile_sums_kernel(RfArgs a) {
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    // exclusive scan of the tile sums by the last block: contiguous segment per thread
-    __shared__ u64 seg[RF_THREADS];
-    const int64_t per = (a.ntiles + RF_THREADS - 1) / RF_THREADS;
-    const int64_t lo = min((int64_t)threadIdx.x * per, a.ntiles), hi = min(lo + per, a.ntiles);
-    u64 s = 0;
-    for (int64_t k = lo; k < hi; ++k) s += a.prefix[k];
-    seg[threadIdx.x] = s;
-    __syncthreads();
+    // exclusive scan of the tile sums by the last block, in place: coalesced chunks of 256 x 8 sums (the loads of the
+    // next chunk are in flight while this one is scanned); integer sums, so the association is free
+    __shared__ u64 wtot[RF_THREADS / 32];
+    constexpr int PER = 8;
+    u64 carry = 0, v[PER], nx[PER];
+    auto load = [&](int64_t base, u64 (&dst)[PER]) {
+        const int64_t idx = base + (int64_t)threadIdx.x * PER;
+#pragma unroll
+        for (int k = 0; k < PER; ++k) dst[k] = (idx + k < a.ntiles) ? __ldcg(a.prefix + idx + k) : 0ull;
+    };
+    load(0, v);
+    for (int64_t base = 0; base < a.ntiles; base += RF_THREADS * PER) {
+        if (base + RF_THREADS * PER < a.ntiles) load(base + RF_THREADS * PER, nx);
+        u64 tsum = 0;
+#pragma unroll
+        for (int k = 0; k < PER; ++k) tsum += v[k];
+        u64 incl = tsum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const u64 t = __shfl_up_sync(MB_FULL, incl, o); if (lane >= o) incl += t; }
+        if (lane == 31) wtot[warp] = incl;
+        __syncthreads();
+        u64 run = carry + incl - tsum, total = 0;
+#pragma unroll
+        for (int w = 0; w < RF_THREADS / 32; ++w) { const u64 t = wtot[w]; if (w < warp) run += t; total += t; }
+        const int64_t idx = base + (int64_t)threadIdx.x * PER;
+#pragma unroll
+        for (int k = 0; k < PER; ++k) { if (idx + k < a.ntiles) a.prefix[idx + k] = run; run += v[k]; }
+        carry += total;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < PER; ++k) v[k] = nx[k];
+    }
     if (threadIdx.x == 0) {
-        u64 run = 0;
-        for (int k = 0; k < RF_THREADS; ++k) { const u64 t = seg[k]; seg[k] = run; run += t; }
-        a.prefix[a.ntiles] = run;
-        a.hdr->local_total = run;
+        a.prefix[a.ntiles] = carry;
+        a.hdr->local_total = carry;
         a.hdr->heavy_count = 0;
         a.hdr->done_counter = 0;
     }
-    __syncthreads();
-    u64 run = seg[threadIdx.x];
-    for (int64_t k = lo; k < hi; ++k) { const u64 t = a.prefix[k]; a.prefix[k] = run; run += t; }
 }
 
 // ------------------------------------------------------------------------------------------------ counts
@@ -435,15 +458,27 @@ __global__ void __launch_bounds__(RF_THREADS, 4) rf_heavy_kernel(RfArgs a) {
         // ancestor = last particle j with cs[j] <= o among those with offspring: upper_bound(cs, o) - 1.  A thread's
         // outputs increase, so does j: the previous answer is tried first (one shared-memory read) -- with collapsed
         // weights a handful of particles own nearly every output and the binary search runs a few times per share
+        // `nb` = first output that no longer belongs to the current answer: the loop body is a compare and a store
         int lo = 0;
-        bool have = false;
-        for (unsigned o = w_lo + threadIdx.x; o < w_hi; o += RF_THREADS) {
-            if (!have || cs[lo + 1] <= o) {
+        unsigned nb = 0;                                  // forces the first search
+        int32_t val = 0;
+        int32_t* const out = anc - (int64_t)(unsigned)o_begin;
+        unsigned o = w_lo + threadIdx.x;
+        for (; o < w_hi; ) {
+            if (o >= nb) {
                 int hi = RF_TILE;
                 while (lo < hi) { const int mid = (lo + hi) >> 1; if (cs[mid + 1] > o) hi = mid; else lo = mid + 1; }
-                have = true;
+                nb = cs[lo + 1];
+                val = base + lo;
             }
-            anc[(int64_t)o - o_begin] = base + lo;
+            const unsigned o3 = o + 3 * RF_THREADS;
+            if (o3 < nb && o3 < w_hi) {                   // four outputs of the same ancestor
+                out[o] = val; out[o + RF_THREADS] = val; out[o + 2 * RF_THREADS] = val; out[o3] = val;
+                o += 4 * RF_THREADS;
+            } else {
+                out[o] = val;
+                o += RF_THREADS;
+            }
         }
         __syncthreads();
     }
@@ -482,7 +517,7 @@ extern "C" int mb_rs_tile_sums(mb_ctx* ctx, void* ws, const float* in, int64_t n
     MB_REQUIRE(!log_mode || ctl, "mb_rs_tile_sums: log mode needs the control block (max log-weight)");
     RfArgs a{};
     rf_fill(a, ws, in, n, n_total, log_mode, ctl, force);
-    int64_t grid = a.ntiles;
+    int64_t grid = (a.ntiles + RF_THREADS / 32 - 1) / (RF_THREADS / 32);   // one warp per tile
     if (grid > (int64_t)ctx->sms * 8) grid = (int64_t)ctx->sms * 8;
     rf_tile_sums_kernel<<<(unsigned)grid, RF_THREADS, 0, mb_s(stream)>>>(a);
     MB_CHECK_LAUNCH();

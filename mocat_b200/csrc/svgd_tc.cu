@@ -188,7 +188,8 @@ __global__ void __launch_bounds__(1024) svgd_tc_colmean_kernel(const double* par
     __shared__ double sm[16][64];
     const int c = threadIdx.x & 63, g = threadIdx.x >> 6;              // 16 block groups per column, fixed order
     double s = 0.0;
-    for (int b = g; b < nblocks; b += 16) s += part[b * 64 + c];
+#pragma unroll 8
+    for (int b = g; b < nblocks; b += 16) s += __ldcg(part + b * 64 + c);
     sm[g][c] = s;
     __syncthreads();
     if (g == 0 && c < d) {
@@ -500,8 +501,8 @@ int mb_svgd_phi_tc(mb_ctx* ctx, const float* X, const float* G, int n, int d, co
     float* saux = reinterpret_cast<float*>(align(reinterpret_cast<uint8_t*>(xs) + bs));
     float* opart = reinterpret_cast<float*>(align(reinterpret_cast<uint8_t*>(saux) + ba));
     double* cpart = reinterpret_cast<double*>((char*)ctx->scratch + (3u << 20) + (64u << 10));   // 4 x 148 x 64 doubles
-    svgd_tc_colsum_kernel<<<ctx->sms * 4, 256, 0, st>>>(X, n, d, cpart);
-    svgd_tc_colmean_kernel<<<1, 1024, 0, st>>>(cpart, ctx->sms * 4, n, d, mean);
+    svgd_tc_colsum_kernel<<<ctx->sms * 2, 256, 0, st>>>(X, n, d, cpart);
+    svgd_tc_colmean_kernel<<<1, 1024, 0, st>>>(cpart, ctx->sms * 2, n, d, mean);
     TcPrepArgs p{X, G, mean, bandwidth, n, d, n_pad, NV, XA, WT, xs, saux};
     svgd_tc_rows_kernel<<<(unsigned)(((int64_t)n_pad * 8 + 255) / 256), 256, 0, st>>>(p);
     svgd_tc_wt_kernel<<<(unsigned)(((int64_t)tiles * NV * 16 + 255) / 256), 256, 0, st>>>(p);
@@ -724,7 +725,8 @@ __global__ void __launch_bounds__(1024) svgd_dist_sample_bracket_kernel(const fl
     __shared__ int bins[2];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     float mn = INFINITY, mx = -INFINITY;
-    for (int i = tid; i < ns; i += 1024) { const float v = smp[i]; mn = fminf(mn, v); mx = fmaxf(mx, v); }
+#pragma unroll 16
+    for (int i = tid; i < ns; i += 1024) { const float v = __ldcg(smp + i); mn = fminf(mn, v); mx = fmaxf(mx, v); }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { mn = fminf(mn, __shfl_xor_sync(MB_FULL, mn, o)); mx = fmaxf(mx, __shfl_xor_sync(MB_FULL, mx, o)); }
     if (lane == 0) { wmn[w] = mn; wmx[w] = mx; }
@@ -735,8 +737,9 @@ __global__ void __launch_bounds__(1024) svgd_dist_sample_bracket_kernel(const fl
 #pragma unroll
     for (int k = 1; k < 32; ++k) { mn = fminf(mn, wmn[k]); mx = fmaxf(mx, wmx[k]); }
     const float scale = (mx > mn) ? (float)DT_SBINS / (mx - mn) : 0.f;
+#pragma unroll 16
     for (int i = tid; i < ns; i += 1024) {
-        const int b = min(DT_SBINS - 1, (int)((smp[i] - mn) * scale));
+        const int b = min(DT_SBINS - 1, (int)((__ldcg(smp + i) - mn) * scale));
         atomicAdd(&sh[b], 1u);
     }
     __syncthreads();
@@ -890,8 +893,8 @@ int mb_pairdist_partial_tc(mb_ctx* ctx, const float* X, int n, int d, int mode, 
     double* dsum = reinterpret_cast<double*>((char*)acc + 72);
     uint32_t* hist = reinterpret_cast<uint32_t*>((char*)acc + 1024);
     double* cpart = reinterpret_cast<double*>((char*)ctx->scratch + (3u << 20) + (64u << 10));
-    svgd_tc_colsum_kernel<<<ctx->sms * 4, 256, 0, st>>>(X, n, d, cpart);
-    svgd_tc_colmean_kernel<<<1, 1024, 0, st>>>(cpart, ctx->sms * 4, n, d, mean);
+    svgd_tc_colsum_kernel<<<ctx->sms * 2, 256, 0, st>>>(X, n, d, cpart);
+    svgd_tc_colmean_kernel<<<1, 1024, 0, st>>>(cpart, ctx->sms * 2, n, d, mean);
     TcPrepArgs p{X, nullptr, mean, nullptr, n, d, n_pad, NV, XA, WT, xs, saux};
     svgd_tc_rows_kernel<<<(unsigned)(((int64_t)n_pad * 8 + 255) / 256), 256, 0, st>>>(p);
     svgd_tc_wt_kernel<<<(unsigned)(((int64_t)tiles * NV * 16 + 255) / 256), 256, 0, st>>>(p);

@@ -445,8 +445,25 @@ class PFEngine(_Resampler):
         """one body of the scan in run_particle_filter_for_marginals (ssm/filtering.py:280-311)"""
         st = stream()
         self.t += 1
+        if int(getattr(self.ssm, 'proposal', 0)) == _lib.PROPOSAL_ENKF:
+            return self._enkf_step(y, st)
         self._resample_kernels(st)
         self._step_kernel(y, st)
+
+    def _enkf_step(self, y, st):
+        """EnsembleKalmanFilter.propose_and_intermediate_weight_vectorised (ssm/nonlinear_gaussian.py:325-350): forecast
+        f(x) + q z by the step kernel (weights are equal, so it never resamples), then the analysis update in place"""
+        if self._comm() is not None:
+            raise _lib.MocatB200Error("the ensemble Kalman filter runs on one GPU (the ensemble covariance is not sharded)")
+        if not hasattr(self, '_enkf_gain'):
+            dev = _dev()
+            self._enkf_gain = torch.empty((self.d, self.d), dtype=torch.float32, device=dev)
+            self._enkf_mean = torch.empty(self.d, dtype=torch.float64, device=dev)
+            self._enkf_cov = torch.empty((self.d, self.d), dtype=torch.float64, device=dev)
+        self._step_kernel(y, st)
+        self.L.call("mb_enkf_analysis", self.ctx, C.byref(self.ssm), ptr(self.x), self.n, ptr(y), ptr(self.lw), self.seed,
+                    self.t, self.gid0, ptr(self.ctl.t), ptr(self.ctl.hist), ptr(self._enkf_gain), ptr(self._enkf_mean),
+                    ptr(self._enkf_cov), st)
 
     def values(self):
         """(n, d) float32 device tensor view of the current particle values"""

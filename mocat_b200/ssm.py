@@ -168,19 +168,35 @@ class OptimalNonLinearGaussianParticleFilter(ParticleFilter):
         self.weight_precision_sqrt = eye / np.sqrt(q2 + r2)
 
 
+class EnsembleKalmanFilter(ParticleFilter):
+    """ssm/nonlinear_gaussian.py:279-350: conditioned initial ensemble (as the optimal filter), forecast through the
+    transition, ensemble covariance -> Kalman gain -> perturbed-observation update; log-weights stay zero (no
+    resampling, no evidence).  Device path: Lorenz96 (H = I, isotropic R), one GPU; the forecast is the Lorenz-96 step
+    kernel, the analysis mb_enkf_analysis (csrc/enkf.cu)."""
+    name = 'Ensemble Kalman Filter'
+
+    def startup(self, ssm_scenario):
+        if not isinstance(ssm_scenario, Lorenz96):
+            raise _lib.MocatB200Error("EnsembleKalmanFilter is compiled for Lorenz96 (H = I, isotropic noise) only; "
+                                      "no CPU fallback")
+        r2, p2 = ssm_scenario.likelihood_std ** 2, ssm_scenario.initial_std ** 2
+        eye = np.eye(ssm_scenario.dim)
+        self.initial_kalman_gain = p2 / (p2 + r2) * eye
+        self.initial_conditioned_covariance_sqrt = np.sqrt(1.0 / (1.0 / p2 + 1.0 / r2)) * eye
+
+
 def _check_filter(pf):
-    if not isinstance(pf, (BootstrapFilter, OptimalNonLinearGaussianParticleFilter)):
-        raise _lib.MocatB200Error("only BootstrapFilter and OptimalNonLinearGaussianParticleFilter are compiled into the "
-                                  "device step (no CPU fallback)")
+    if not isinstance(pf, (BootstrapFilter, OptimalNonLinearGaussianParticleFilter, EnsembleKalmanFilter)):
+        raise _lib.MocatB200Error("only BootstrapFilter, OptimalNonLinearGaussianParticleFilter and EnsembleKalmanFilter "
+                                  "are compiled into the device step (no CPU fallback)")
 
 
 def _device_ssm(ssm_scenario, particle_filter, dt=None):
     """POD model of the scenario with the filter's proposal folded in"""
     s = ssm_scenario._ssm() if dt is None else ssm_scenario._ssm(dt)
-    if isinstance(particle_filter, OptimalNonLinearGaussianParticleFilter):
-        if int(s.kind) != _lib.SSM_LORENZ96:
-            raise _lib.MocatB200Error("OptimalNonLinearGaussianParticleFilter: Lorenz96 only (no CPU fallback)")
-        s.proposal = _lib.PROPOSAL_OPTIMAL
+    if isinstance(particle_filter, (OptimalNonLinearGaussianParticleFilter, EnsembleKalmanFilter)):
+        particle_filter.startup(ssm_scenario)                         # raises for anything but Lorenz96
+        s.proposal = _lib.PROPOSAL_ENKF if isinstance(particle_filter, EnsembleKalmanFilter) else _lib.PROPOSAL_OPTIMAL
     return s
 
 

@@ -115,6 +115,27 @@ class OptimalPF(BootstrapPF):
                     resampled=bool(resample), ancestors=anc)
 
 
+class EnKF(OptimalPF):
+    """EnsembleKalmanFilter (ssm/nonlinear_gaussian.py:279-350) for H = I, R = r^2 I: initial ensemble as the optimal
+    filter (:313-323); step: mx = f(x) + q z1 (:335-337), P = cov(mx) with 1/(n-1) (:339), K = P (P + r^2 I)^-1
+    (:341-343, utils.py:477-484), y_prop = mx + r z2 (:345-346), x' = mx + (y - y_prop) K^T, zero log-weights (:348-350).
+    z1: the step kernel's pairwise stream (purpose P_MOVE); z2: the particle's own stream (purpose P_SIM)."""
+
+    def step(self, st, y):
+        s, n = self.ssm, self.n
+        y = np.asarray(y, np.float64)
+        t = st['t'] + 1
+        z1 = self.normals(self.seed, self.gid, t, philox.P_MOVE, s.dim, dtype=self.normal_dtype)
+        mx = s.transition_sample(st['x'], z1)
+        P = np.atleast_2d(np.cov(mx.T, ddof=1))
+        K = P @ np.linalg.inv(P + s.r_std ** 2 * np.eye(s.dim))
+        z2 = philox.normals(self.seed, self.gid, t, philox.P_SIM, s.dim, dtype=self.normal_dtype)
+        x_new = mx + (y - mx - s.r_std * np.asarray(z2, np.float64)) @ K.T
+        lw = np.zeros(n)
+        return dict(x=x_new, lw=lw, ess=float(n), t=t, log_z=0.0, resampled=False, ancestors=None,
+                    forecast=mx, gain=K, cov=P, mean=mx.mean(0))
+
+
 def weighted_moments(x, lw):
     w = np.exp(lw - np.max(lw))
     w = w / w.sum()

@@ -318,3 +318,50 @@ def test_l96_optimal_proposal_api_beats_bootstrap(E):
     with pytest.raises(Exception):
         ssm.run_particle_filter_for_marginals(ssm.TimeHomogenousLinearGaussian(dim=1), ssm.OptimalNonLinearGaussianParticleFilter(),
                                               sim.y[:, :1], sim.t, 5, n=1000)
+
+
+@pytest.mark.parametrize("d,n", [(8, 3000), (40, 4097), (16, 501)])
+def test_enkf_step_parity(E, d, n):
+    """EnsembleKalmanFilter (ssm/nonlinear_gaussian.py:279-350) on the device: ensemble mean / covariance / gain and the
+    analysed ensemble of two steps against oracle.pf.EnKF on the same Philox streams"""
+    torch, l, e, m, lib = E
+    seed = 5
+    ssm_o = omodels.Lorenz96SSM(dim=d, dt=0.05, r_std=0.8, init_mean=1.0, init_std=2.0)
+    _, y = ssm_o.simulate(3, np.random.default_rng(0), spinup=200)
+    s = m.make_lorenz96(dim=d, dt=0.05, r_std=0.8, init_mean=1.0, init_std=2.0)
+    s.proposal = l.PROPOSAL_ENKF
+    eng = e.PFEngine(s, n, seed, ess_threshold=0.5, resampling=l.RESAMPLE_SYSTEMATIC)
+    orc = opf.EnKF(ssm_o, n, seed)
+    yd = torch.as_tensor(y.astype(np.float32), device="cuda")
+    eng.init(yd[0])
+    st = orc.init(y[0])
+    npt.assert_allclose(eng.values().cpu().numpy(), st['x'], atol=3e-5)
+    for t in (1, 2):
+        eng.step(yd[t])
+        st = orc.step(st, y[t])
+        npt.assert_allclose(eng._enkf_mean.cpu().numpy(), st['mean'], atol=2e-5 * (1 + np.abs(st['mean']).max()))
+        npt.assert_allclose(eng._enkf_cov.cpu().numpy(), st['cov'], atol=2e-5 * np.abs(st['cov']).max())
+        npt.assert_allclose(eng._enkf_gain.cpu().numpy(), st['gain'], atol=2e-5)
+        x1 = eng.values().cpu().numpy()
+        npt.assert_allclose(x1, st['x'], atol=2e-4, rtol=1e-5)
+        assert np.all(eng.lw.cpu().numpy() == 0.0)
+        c = eng.ctl.read()
+        assert c['ess'] == n and c['resample'] == 0 and c['log_z'] == 0.0
+        st = dict(st, x=x1.astype(np.float64))
+
+
+def test_enkf_api_tracks_lorenz96(E):
+    """through the reference API: the ensemble Kalman filter with 2000 members tracks a 40-dimensional Lorenz-96
+    trajectory (where the bootstrap filter of the same size degenerates): the ensemble-mean error stays below the
+    observation noise and the ensemble spread is commensurate with it"""
+    from mocat_b200 import ssm
+    sc = ssm.Lorenz96(dim=40)
+    tt = np.arange(40) * 0.05
+    sim = sc.simulate(tt, 1, spinup=500)
+    out = ssm.run_particle_filter_for_marginals(sc, ssm.EnsembleKalmanFilter(), sim.y, sim.t, 2, n=2000)
+    rmse = np.sqrt(np.mean((out.mean[10:] - sim.x[10:]) ** 2))
+    assert rmse < 0.8, rmse                                            # observation noise std is 1
+    spread = np.sqrt(np.mean(out.var[10:]))
+    assert 0.3 * rmse < spread < 3.0 * rmse, (spread, rmse)
+    npt.assert_allclose(out.ess, 2000.0)
+    assert not np.any(out.resampled)
