@@ -271,6 +271,13 @@ int mb_pf_l96_step(mb_ctx* ctx, const mb_ssm* ssm, const float* x_in_rows, float
                    int64_t n_total, const int32_t* anc, const float* y, float* lw, uint64_t seed, uint32_t t,
                    int64_t gid0, double ess_threshold, mb_control* ctl, mb_hist* hist, const mb_shard* sh /*or NULL*/,
                    mb_comm* comm /*or NULL*/, mb_stream_t stream);
+/* ---- kernelised Stein discrepancy (metrics.ksd, metrics.py:88-130) under the Gaussian kernel (kernels.py:82-116):
+ *      out3[0] = sqrt(sum_ij k0(x_i, x_j) w_i w_j) / sum_i w_i, out3[1] = the double sum, out3[2] = sum w (device fp64);
+ *      w = exp(log_weight) or 1 (log_weight NULL).  k0 as metrics.py:116-124; reference_sign != 0 contracts the kernel
+ *      gradients with grad_potential exactly as the reference does, 0 uses the score -grad_potential (the Stein kernel
+ *      whose KSD vanishes for an exact sample).  X, grad_potential: device float (n, d) row-major, d <= 128. */
+int mb_ksd(mb_ctx* ctx, const float* X, const float* grad_potential, const float* log_weight /*or NULL*/, int n, int d,
+           float bandwidth, int reference_sign, double* out3, mb_stream_t stream);
 /* ---- ensemble Kalman filter (EnsembleKalmanFilter, ssm/nonlinear_gaussian.py:279-350; H = I, R = r_std^2 I) on the
  *      row-major population of the Lorenz-96 engine.
  *      mb_rows_mean_cov: ensemble mean[d] and unbiased covariance cov[d][d] (device fp64; either may be NULL) of the

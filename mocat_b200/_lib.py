@@ -139,6 +139,7 @@ SIGNATURES = {
     "mb_weighted_moments_rows": (C.c_int, [c_vp, c_vp, c_i64, C.c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "mb_weighted_moment_sums_rows": (C.c_int, [c_vp, c_vp, c_i64, C.c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "mb_gather_rows": (C.c_int, [c_vp, c_vp, c_i64, C.c_int, c_vp, c_i64, c_vp, C.c_int, c_vp]),
+    "mb_ksd": (C.c_int, [c_vp, c_vp, c_vp, c_vp, C.c_int, C.c_int, c_f, C.c_int, c_vp, c_vp]),
     "mb_rows_mean_cov": (C.c_int, [c_vp, c_vp, c_i64, C.c_int, c_f, c_vp, c_vp, c_vp, c_vp]),
     "mb_enkf_analysis": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_u64, C.c_uint32, c_i64, c_vp, c_vp, c_vp, c_vp,
                                    c_vp, c_vp]),

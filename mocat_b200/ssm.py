@@ -333,13 +333,16 @@ def propagate_particle_filter(ssm_scenario, particle_filter, particles, y_new, t
 
 def run_particle_filter_for_marginals(ssm_scenario, particle_filter, y, t, random_key, n=None, initial_sample=None,
                                       ess_threshold=0.5, resampling='multinomial', keep_history=None,
-                                      moments=True):
+                                      moments=True, history_every=None):
     """ssm/filtering.py:255-324.  The time loop is enqueued without any host synchronisation; per-step ESS,
     log-evidence and (moments=True) weighted means / variances are read back once at the end.  The stacked
     (T, n, d) history of the reference is returned when it fits `HISTORY_AUTO_BYTES` (or keep_history=True);
     otherwise `value` / `log_weight` hold the final population only, or None when even that exceeds the budget
     (it stays on the device: `out.engine.values()`).  initial_sample: a cdict from initiate_particles / a previous
-    call -- every (y, t) is then a propagation step of its engine (filtering.py:266-276)."""
+    call -- every (y, t) is then a propagation step of its engine (filtering.py:266-276).
+    history_every=k: a THINNED history -- the populations of steps 0, k, 2k, ... and of the last step -- streamed to
+    pinned host memory while the filter runs (mocat_b200.history.HistoryStream); `value` / `log_weight` then hold those
+    records and `history_index` their positions in `t`."""
     torch = _torch()
     _check_filter(particle_filter)
     y = np.asarray(y, np.float32)
@@ -372,17 +375,21 @@ def run_particle_filter_for_marginals(ssm_scenario, particle_filter, y, t, rando
     if keep_history is None:
         keep_history = T * n * (d + 1) * 4 <= HISTORY_AUTO_BYTES
     yd = torch.as_tensor(y, device="cuda")
-    vals, lws = [], []
     sharded = _world()[1] > 1
+    hs = None
+    if history_every is not None or keep_history:
+        from .history import HistoryStream
+        every = 1 if history_every is None else max(1, int(history_every))
+        hs = HistoryStream((n, d), every, (T + every - 1) // every + 1)
     if sharded and not eng.rowmajor:
         moments = False                                   # per-shard moment sums exist for the row-major layout only
     mom = torch.empty((T, 2, d), dtype=torch.float64, device="cuda") if moments and not sharded else None
     msum = torch.empty((T, 1 + 2 * d), dtype=torch.float64, device="cuda") if moments and sharded else None
 
     def record(i):
-        if keep_history:
-            vals.append(eng.values().clone(memory_format=torch.contiguous_format).cpu())   # streamed to the host per step
-            lws.append(eng.lw.cpu())
+        if hs is not None and (hs.wants(i) or i == T - 1):                # streamed to pinned host memory, no host sync
+            v = eng.values()
+            hs.push(i, v if v.is_contiguous() else v.contiguous(), eng.lw, force=True)
         if msum is not None:                              # this shard's raw sums, shifted by the observation (H = I)
             eng.moment_sums(yd[i], out=msum[i])
         elif moments:
@@ -391,6 +398,8 @@ def run_particle_filter_for_marginals(ssm_scenario, particle_filter, y, t, rando
 
     t0 = eng.t + 1 if initial_sample is not None else 0
     for i in range(T):
+        if hs is not None:
+            hs.before_overwrite(i)
         if initial_sample is None and i == 0:
             eng.init(yd[0])
         else:
@@ -399,9 +408,10 @@ def run_particle_filter_for_marginals(ssm_scenario, particle_filter, y, t, rando
     hist = eng.ctl.read_hist(t0 + T)[t0:]
     out = cdict(t=t, y=y, ess=hist['ess'].copy(), log_norm_constant=hist['log_z'].copy(),
                 resampled=hist['resampled'].copy(), engine=eng, engine_generation=eng.generation)
-    if keep_history:
-        out.value = torch.stack(vals).numpy()
-        out.log_weight = torch.stack(lws).numpy()
+    if hs is not None:
+        out.value, out.log_weight, kept = hs.finish()
+        if history_every is not None:                                  # else: the full stacked history of the reference
+            out.history_index = kept
     else:
         out.value, out.log_weight = _host_value(eng)
     if msum is not None:                                  # one all-reduce of T (1 + 2d) doubles for the whole run
@@ -416,7 +426,7 @@ def run_particle_filter_for_marginals(ssm_scenario, particle_filter, y, t, rando
     if initial_sample is not None:
         for k in ('t', 'y', 'ess', 'log_norm_constant', 'mean', 'var', 'value', 'log_weight'):
             prev, new = getattr(initial_sample, k, None), getattr(out, k, None)
-            if prev is not None and new is not None and (k not in ('value', 'log_weight') or keep_history):
+            if prev is not None and new is not None and (k not in ('value', 'log_weight') or (keep_history and history_every is None)):
                 setattr(out, k, np.concatenate([prev, new], axis=0))
     return out
 

@@ -273,3 +273,38 @@ def test_kalman_filter_device_matches_oracle(mocat, d, dy):
     npt.assert_allclose(ll, oll, rtol=2e-5)
     hm, hc, hl = mocat.ssm.kalman_filter_host(sc, y32, sim.t, return_log_likelihood=True)
     npt.assert_allclose(mus, hm, rtol=5e-5, atol=5e-5)
+
+
+def test_thinned_history_stream_and_checkpoint_resume(tmp_path):
+    """(i) history_every streams a thinned history to pinned host memory and its records equal the
+    corresponding records of the full stacked history; (ii) a filter continued from a checkpoint file is bit-identical
+    to the uninterrupted run (Philox counters are keyed on particle and time index)"""
+    import numpy as np
+    import numpy.testing as npt
+    from mocat_b200 import ssm, history
+    sc = ssm.Lorenz96(dim=8)
+    tt = np.arange(12) * 0.05
+    sim = sc.simulate(tt, 3, spinup=200)
+    kw = dict(n=3001, ess_threshold=0.5, resampling='systematic')
+    full = ssm.run_particle_filter_for_marginals(sc, ssm.BootstrapFilter(), sim.y, sim.t, 9, keep_history=True, **kw)
+    assert full.value.shape == (12, 3001, 8) and not hasattr(full, 'history_index')
+    thin = ssm.run_particle_filter_for_marginals(sc, ssm.BootstrapFilter(), sim.y, sim.t, 9, history_every=5, **kw)
+    npt.assert_array_equal(thin.history_index, [0, 5, 10, 11])
+    npt.assert_array_equal(thin.value, full.value[[0, 5, 10, 11]])
+    npt.assert_array_equal(thin.log_weight, full.log_weight[[0, 5, 10, 11]])
+    npt.assert_array_equal(thin.ess, full.ess)
+    # checkpoint after 7 observations, continue from the file
+    part = ssm.run_particle_filter_for_marginals(sc, ssm.BootstrapFilter(), sim.y[:7], sim.t[:7], 9, keep_history=False, **kw)
+    path = tmp_path / "pf.cdict"
+    history.save_checkpoint(part, path)
+    with pytest.raises(RuntimeError):
+        history.save_checkpoint(part, path)                            # core.py:99-103: no silent overwrite
+    # disturb the pooled engine, then resume
+    ssm.run_particle_filter_for_marginals(sc, ssm.BootstrapFilter(), sim.y[:3], sim.t[:3], 1, keep_history=False, **kw)
+    res = history.load_checkpoint(path)
+    cont = ssm.run_particle_filter_for_marginals(sc, ssm.BootstrapFilter(), sim.y[7:], sim.t[7:], 9, initial_sample=res,
+                                                 keep_history=False, ess_threshold=0.5, resampling='systematic')
+    npt.assert_array_equal(cont.engine.values().cpu().numpy(), full.value[-1])
+    npt.assert_array_equal(cont.engine.lw.cpu().numpy(), full.log_weight[-1])
+    npt.assert_array_equal(cont.ess, full.ess)
+    npt.assert_allclose(cont.log_norm_constant, full.log_norm_constant, rtol=0, atol=0)

@@ -213,3 +213,29 @@ def test_stratified_multinomial_is_multinomial(eng):
     big = w > np.median(w)
     ratio = counts[big].var() / counts[big].mean()
     assert 0.8 < ratio < 1.4
+
+
+@pytest.mark.parametrize("n,d,h", [(700, 3, 1.0), (300, 50, 7.0), (65, 2, 10.0), (2049, 5, 2.5)])
+def test_ksd_parity(lib, n, d, h):
+    """mb_ksd (metrics.ksd, metrics.py:88-130) against the fp64 restatement: unweighted / weighted, reference sign /
+    score sign, ragged tile edges"""
+    import torch
+    import mocat_b200 as mocat
+    from mocat_b200 import metrics, kernels
+    from mocat_b200.core import cdict
+    from oracle import metrics as om
+    rng = np.random.default_rng(n)
+    x = rng.standard_normal((n, d)).astype(np.float32) * 1.3
+    g = (x + 0.3 * rng.standard_normal((n, d))).astype(np.float32)
+    lw = (0.5 * rng.standard_normal(n)).astype(np.float32)
+    kern = kernels.Gaussian(bandwidth=h)
+    samp = cdict(value=x, grad_potential=g)
+    for ref in (True, False):
+        sign = 'reference' if ref else 'score'
+        npt.assert_allclose(metrics.ksd(samp, kern, stein_sign=sign), om.ksd(x, g, h, reference_sign=ref), rtol=3e-4)
+        npt.assert_allclose(metrics.ksd(torch.as_tensor(x, device="cuda"), kern, grad_potential=g, log_weight=lw,
+                                        stein_sign=sign),
+                            om.ksd(x, g, h, log_weight=lw, reference_sign=ref), rtol=3e-4)
+    npt.assert_allclose(metrics.ksd(samp, kern, bandwidth=2 * h), om.ksd(x, g, 2 * h), rtol=3e-4)
+    with pytest.raises(TypeError):
+        metrics.ksd(x, kern)

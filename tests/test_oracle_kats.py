@@ -145,3 +145,24 @@ def test_logistic_regression_oracle_gradient():
     # saturated logits stay finite
     u, g = lr.potential_and_grad(np.full((1, 6), 200.0))
     assert np.all(np.isfinite(u)) and np.all(np.isfinite(g))
+
+
+def test_ksd_reference_fixture_properties():
+    """tests/test_metrics.py:90-115: standard-normal draws with grad_potential = x; the discrepancy of 1000 draws is
+    below that of 10 draws for bandwidths 1 and 10 (the assertion the reference makes), and -- with the score
+    convention -- it decays like n^-1/2, which the literal reference sign does not"""
+    import numpy as np
+    from oracle import metrics as om
+    rng = np.random.default_rng(0)
+    xs, xl = rng.standard_normal((10, 2)), rng.standard_normal((1000, 2))
+    for h in (1.0, 10.0):
+        assert om.ksd(xl, xl, h) < om.ksd(xs, xs, h)
+        assert om.ksd(xl, xl, h, reference_sign=False) < 0.2 * om.ksd(xs, xs, h, reference_sign=False)
+    assert om.ksd(xl, xl, 1.0, reference_sign=False) < 0.1 < 0.5 < om.ksd(xl, xl, 1.0)
+    # pair formula against the kernel functions at one pair (kernels.py:90-116)
+    x, y, g, q, h = np.array([0.3, -1.0]), np.array([1.1, 0.4]), np.array([0.5, 2.0]), np.array([-1.5, 0.25]), 1.7
+    k = om.gaussian_call(x, y, h)
+    k0 = (np.sum(om.gaussian_diag_grad_xy(x, y, h)) + om.gaussian_grad_x(x, y, h) @ q + g @ om.gaussian_grad_y(x, y, h)
+          + k * (g @ q))
+    diff, r2 = x - y, np.sum((x - y) ** 2)
+    np.testing.assert_allclose(k0, k * ((2 * h * h - r2) / h ** 4 + (diff @ g - diff @ q) / h ** 2 + g @ q), rtol=1e-12)
