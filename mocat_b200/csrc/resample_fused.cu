@@ -87,16 +87,21 @@ __device__ __forceinline__ float rf_wmax(const RfArgs& a) {
     return wmax;
 }
 
-// rint(x) as uint64 without the 64-bit F2I (an XU-pipe instruction at 1/8 rate -- it bound pass A at 47 % of the HBM
-// peak): below 2^23 the add of 2^23 rounds to nearest-even into the mantissa, above it x already is an integer and the
-// mantissa is shifted into place.  NaN, negative, zero -> 0, as the saturating conversion gave.
+// rint(x) as uint64 without the 64-bit F2I (an XU-pipe instruction at quarter rate: with the exp it bound pass A at 47 %
+// of the HBM peak).  x = hr 2^20 + lo with hr = rint(x 2^-20) and lo = x - hr 2^20 EXACT in fp32 (|lo| <= 2^19), both
+// turned into integers by adding 1.5 * 2^23 (round-to-nearest-even lands in the mantissa); hr 2^20 is even, so the tie
+// rule of rint(lo) is that of rint(x).  Branch-free, FMA / ALU pipes only.  NaN, negative, zero -> 0 (as the saturating
+// conversion gave); x >= 2^42 (never in log mode, where x <= 2^40) takes the conversion instruction.
 __device__ __forceinline__ u64 rf_rint_u64(float x) {
-    if (!(x > 0.f)) return 0ull;
-    if (x < 8388608.f) return (u64)(__float_as_uint(x + 8388608.f) - 0x4B000000u);
-    const uint32_t bits = __float_as_uint(x);
-    const int sh = (int)(bits >> 23) - 150;
-    if (sh >= 40) return __float2ull_rn(x);                           // >= 2^63: saturating conversion (never in log mode)
-    return (u64)((bits & 0x7fffffu) | 0x800000u) << sh;
+    if (x >= 4398046511104.f) return __float2ull_rn(x);
+    const float MAGIC = 12582912.f;                                   // 1.5 * 2^23
+    const float th = fmaf(x, 9.5367431640625e-7f, MAGIC);             // x 2^-20 + magic (one rounding: RNE to an integer)
+    const int hi = (int)(__float_as_uint(th) - 0x4B400000u);
+    const float hr = th - MAGIC;
+    const float lo = fmaf(-hr, 1048576.f, x);
+    const int li = (int)(__float_as_uint(lo + MAGIC) - 0x4B400000u);
+    const long long e = ((long long)hi << 20) + (long long)li;
+    return (x > 0.f) ? (u64)e : 0ull;
 }
 
 __device__ __forceinline__ u64 rf_weight(float v, bool log_mode, float wmax, float scale) {
