@@ -255,6 +255,16 @@ int mb_kalman_filter(mb_ctx* ctx, const mb_ssm* ssm, const float* y, int T, doub
 int mb_backward_sample(mb_ctx* ctx, const mb_ssm* ssm, float dt, const float* x0, const float* lw0, int64_t n_pf,
                        const float* x1 /*or NULL*/, int64_t n_s, float* work, uint64_t seed, uint32_t step, int32_t* idx,
                        float* x_out, mb_stream_t stream);
+/* Fixed-lag stitching (ssm/online_smoothing.py:21-44 full_stitch, :167-207 fixed_lag_stitching): for every fixed
+ * trajectory end x0_i (n_s, d) draw idx_i ~ Cat(lw1_j - transition_potential(x0_i -> x1_j)) over the n_c candidate
+ * continuations x1 (n_c, d) by Gumbel-max (Philox counter: gid = i, step, purpose 5, slot j / 4).  work: (n_s + n_c) * d
+ * floats.  mb_transition_potential: pot_i = transition_potential(x0_i -> x1_i) of n matched pairs, normalising constant
+ * included (linear_gaussian.py:73-84, nonlinear_gaussian.py:98-105, utils.py:49-79); work: n * d floats. */
+int mb_stitch_sample(mb_ctx* ctx, const mb_ssm* ssm, float dt, const float* x0, int64_t n_s, const float* x1,
+                     const float* lw1, int64_t n_c, float* work, uint64_t seed, uint32_t step, int32_t* idx,
+                     mb_stream_t stream);
+int mb_transition_potential(mb_ctx* ctx, const mb_ssm* ssm, float dt, const float* x0, const float* x1, int64_t n,
+                            float* work, float* pot, mb_stream_t stream);
 
 /* ---- K1b', Lorenz-96 (config C3): same contract as mb_pf_init / mb_pf_step for MB_SSM_LORENZ96 (dim 8, 16 or 40,
  *      H = I, diagonal noise, `substeps` RK4 steps per observation interval; ssm/scenarios/lorenz96.py:14-44 on

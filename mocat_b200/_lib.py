@@ -117,6 +117,8 @@ SIGNATURES = {
     "mb_kalman_filter": (C.c_int, [c_vp, C.POINTER(SSM), c_vp, C.c_int, c_vp, c_vp, c_vp, c_vp]),
     "mb_backward_sample": (C.c_int, [c_vp, C.POINTER(SSM), c_f, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_u64, c_u32, c_vp,
                                      c_vp, c_vp]),
+    "mb_stitch_sample": (C.c_int, [c_vp, C.POINTER(SSM), c_f, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_u64, c_u32, c_vp, c_vp]),
+    "mb_transition_potential": (C.c_int, [c_vp, C.POINTER(SSM), c_f, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "mb_ancestors_sharded": (C.c_int, [c_vp, c_vp, C.c_int, c_u64, c_u32, c_vp, c_i64, c_vp, c_vp]),
     "mb_strata_count": (C.c_int, [c_i64]),
     "mb_strata_hist": (C.c_int, [c_vp, c_i64, c_i64, C.c_int, c_u64, c_u32, c_vp, c_vp, C.c_int, c_vp]),

@@ -291,10 +291,17 @@ def resample_particles(particles, random_key=None, resample_full=True):
     if particles.value is not None:
         out.value = particles.value[:, anc] if resample_full else particles.value.copy()
         out.value[-1] = eng.values().cpu().numpy()
-        out.log_weight = particles.log_weight.copy()
-        out.log_weight[-1] = 0.0
-    out.ess = particles.ess.copy()
-    out.ess[-1] = float(eng.n_total)
+        lw = np.asarray(particles.log_weight)
+        if lw.ndim == 1:                                            # the smoother keeps the latest weights only
+            out.log_weight = np.zeros_like(lw)
+        else:
+            out.log_weight = lw.copy()
+            out.log_weight[-1] = 0.0
+    if np.ndim(particles.ess) == 0:
+        out.ess = float(eng.n_total)
+    else:
+        out.ess = np.array(particles.ess, dtype=np.float64)
+        out.ess[-1] = float(eng.n_total)
     return out
 
 
@@ -542,3 +549,21 @@ def kalman_filter_host(lgssm_scenario, y, t=None, return_log_likelihood=False):
         mu, cov = mu + K @ innov, cov - K @ H @ cov
         mus[i], covs[i] = mu, cov
     return (mus, covs, ll) if return_log_likelihood else (mus, covs)
+
+
+def propagate_particle_smoother(*args, **kwargs):
+    """ssm/online_smoothing.py:364-386 (mocat_b200/online_smoothing.py)"""
+    from .online_smoothing import propagate_particle_smoother as f
+    return f(*args, **kwargs)
+
+
+def propagate_particle_smoother_pf(*args, **kwargs):
+    """ssm/online_smoothing.py:211-282"""
+    from .online_smoothing import propagate_particle_smoother_pf as f
+    return f(*args, **kwargs)
+
+
+def propagate_particle_smoother_bs(*args, **kwargs):
+    """ssm/online_smoothing.py:285-361"""
+    from .online_smoothing import propagate_particle_smoother_bs as f
+    return f(*args, **kwargs)
