@@ -384,6 +384,38 @@ int mb_abc_adapt_stage(mb_ctx* ctx, int stage, const float* x, int64_t ld, int64
                        double ess_resample, double termination_alpha, int max_iter, const double* schedule,
                        int advance_iter, void* ws, mb_control* ctl, mb_hist* hist, mb_stream_t stream);
 
+/* ---- tempered ensemble Kalman inversion (TemperedEKI / AdaptiveTemperedEKI, transport/teki.py:38-185) on the g-and-k
+ *      simulator: x (n, 4) and simulated_data sim (n, m) ROW-MAJOR device floats.  mb_teki is the device-resident record
+ *      of the ensemble (what the reference keeps in ensemble_state / extra); every kernel is predicated on done.
+ *      mb_teki_init: prior sample (or the caller's x), first simulation, prior_stds (teki.py:94-101).
+ *      mb_teki_update: termination_criterion (:104-111) on the current ensemble, then one update (:117-150):
+ *      covariances, next temperature (mode 0: schedule[min(iter, len - 1)]; 1: round(2^(iter/50) - 1, 4), :91-92;
+ *      2: AdaptiveTemperedEKI.next_temperature, :168-185, through mb_temper_adapt), Kalman gain, perturbed update,
+ *      re-simulation.  partials: mb_teki_workspace_doubles(m) doubles; scratch: 2 * roundup(n, 32) floats and search_ctl (mode 2);
+ *      temp_hist (or NULL): device doubles [max_iter + 1], temp_hist[iter] = temperature after update iter.
+ *      Normals: Philox (gid0 + i, step = iter, purpose 1); simulator draws: purpose 3, step = iter (0 at init). */
+#define MB_TEKI_MAX_DY 16
+typedef struct {
+    double temperature, prev_temperature, alph, ess;
+    double cov_x[16], cov_xy[4 * MB_TEKI_MAX_DY], cov_y[MB_TEKI_MAX_DY * MB_TEKI_MAX_DY];  /* row stride 4 / 16 / 16 */
+    double cov_y_given_x[MB_TEKI_MAX_DY * MB_TEKI_MAX_DY], chol[MB_TEKI_MAX_DY * MB_TEKI_MAX_DY];
+    double prec[MB_TEKI_MAX_DY * MB_TEKI_MAX_DY], gain[4 * MB_TEKI_MAX_DY];
+    double stds[4], prior_stds[4];  /* std (ddof 1) of constrain(value) now / of the initial unconstrained value */
+    int64_t value_nan, perturb_nan;
+    int32_t iter, done, search_iters, pad;
+} mb_teki;
+typedef struct {
+    double max_temperature, nugget, term_std, ess_threshold, tol;
+    int32_t max_search_iter, max_iter, mode, schedule_len;
+    const double* schedule;   /* device, mode 0 */
+} mb_teki_prm;
+int mb_teki_workspace_doubles(int m);
+int mb_teki_init(mb_ctx* ctx, const mb_gk* gk, float* x, float* sim, int64_t n, int sample_prior, uint64_t seed,
+                 int64_t gid0, double* partials, double* temp_hist /*or NULL*/, mb_teki* state, mb_stream_t stream);
+int mb_teki_update(mb_ctx* ctx, const mb_gk* gk, const mb_teki_prm* prm, float* x, float* sim, int64_t n, uint64_t seed,
+                   int64_t gid0, double* partials, float* scratch, mb_control* search_ctl, double* temp_hist /*or NULL*/,
+                   mb_teki* state, mb_stream_t stream);
+
 /* ---- conditional section of a captured step.  Every resampling kernel is predicated on the control block, so
  *      enqueueing them unconditionally is always correct (reference: `cond(resample_bool, ...)`,
  *      transport/smc.py:76-78, ssm/filtering.py:287-293).  While `stream` is under CUDA-graph capture, launches made

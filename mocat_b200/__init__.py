@@ -10,6 +10,7 @@ from .sample import Sampler, run  # noqa: F401
 from .mcmc import MCMCSampler, RandomWalk, Underdamped, Overdamped, Metropolis  # noqa: F401
 from .transport import (TransportSampler, SMCSampler, TemperedSMCSampler, MetropolisedSMCSampler,  # noqa: F401
                         RMMetropolisedSMCSampler, SVGD, adagrad)
+from .teki import TemperedEKI, AdaptiveTemperedEKI  # noqa: F401
 from . import scenarios, kernels, metrics, ssm, abc, transport, history, online_smoothing  # noqa: F401
 from .metrics import log_ess_log_weight, ess_log_weight  # noqa: F401
 from ._lib import MocatB200Error  # noqa: F401

@@ -84,6 +84,21 @@ class GK(C.Structure):
     _fields_ = [("m", c_i32), ("c", c_f), ("prior_min", c_f), ("prior_max", c_f), ("buffer", c_f), ("data", c_f * 16)]
 
 
+class Teki(C.Structure):
+    """mb_teki: device-resident record of a tempered-EKI ensemble (include/mocat_b200.h)"""
+    _fields_ = [("temperature", c_d), ("prev_temperature", c_d), ("alph", c_d), ("ess", c_d),
+                ("cov_x", c_d * 16), ("cov_xy", c_d * 64), ("cov_y", c_d * 256), ("cov_y_given_x", c_d * 256),
+                ("chol", c_d * 256), ("prec", c_d * 256), ("gain", c_d * 64), ("stds", c_d * 4), ("prior_stds", c_d * 4),
+                ("value_nan", c_i64), ("perturb_nan", c_i64), ("iter", c_i32), ("done", c_i32), ("search_iters", c_i32),
+                ("pad", c_i32)]
+
+
+class TekiPrm(C.Structure):
+    _fields_ = [("max_temperature", c_d), ("nugget", c_d), ("term_std", c_d), ("ess_threshold", c_d), ("tol", c_d),
+                ("max_search_iter", c_i32), ("max_iter", c_i32), ("mode", c_i32), ("schedule_len", c_i32),
+                ("schedule", c_vp)]
+
+
 def fill_matrix(dst, mat):
     """row-major (r, c) -> padded MB_MAX_SMALL_DIM x MB_MAX_SMALL_DIM ctypes array"""
     mat = np.atleast_2d(np.asarray(mat, dtype=np.float64))
@@ -159,6 +174,10 @@ SIGNATURES = {
     "mb_prior_sample": (C.c_int, [c_vp, c_f, c_f, C.c_int, c_i64, c_u64, c_i64, c_vp, c_vp]),
     "mb_logistic_potential_grad": (C.c_int, [c_vp, c_vp, c_vp, C.c_int, C.c_int, c_f, c_f, c_d, c_vp, C.c_int, c_vp, c_vp,
                                              C.c_int, c_vp]),
+    "mb_teki_workspace_doubles": (C.c_int, [C.c_int]),
+    "mb_teki_init": (C.c_int, [c_vp, C.POINTER(GK), c_vp, c_vp, c_i64, C.c_int, c_u64, c_i64, c_vp, c_vp, c_vp, c_vp]),
+    "mb_teki_update": (C.c_int, [c_vp, C.POINTER(GK), C.POINTER(TekiPrm), c_vp, c_vp, c_i64, c_u64, c_i64, c_vp, c_vp,
+                                 c_vp, c_vp, c_vp, c_vp]),
     "mb_abc_init": (C.c_int, [c_vp, C.POINTER(GK), c_vp, c_i64, c_i64, c_i64, C.c_int, c_vp, c_vp, c_vp, c_vp, c_u64,
                               c_i64, c_vp, c_vp]),
     "mb_abc_move": (C.c_int, [c_vp, C.POINTER(GK), C.c_int, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp,

@@ -6,9 +6,9 @@ NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="$MB_EXTRA_FLAGS -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xptxas -v --expt-relaxed-constexpr"
 mkdir -p build
 pids=()
-for f in abi comm reduce resample resample_fused propagate pf_l96 enkf backward abc svgd svgd_tc ksd; do
+for f in abi comm reduce resample resample_fused propagate pf_l96 enkf backward abc svgd svgd_tc ksd teki; do
   [ -f $f.cu ] || continue
-  if [ ! -f build/$f.o ] || [ $f.cu -nt build/$f.o ] || [ common.cuh -nt build/$f.o ] || [ select.cuh -nt build/$f.o ] || [ comm.cuh -nt build/$f.o ] || [ rng.cuh -nt build/$f.o ] || [ pf_common.cuh -nt build/$f.o ] || [ ../../include/mocat_b200.h -nt build/$f.o ]; then
+  if [ ! -f build/$f.o ] || [ $f.cu -nt build/$f.o ] || [ common.cuh -nt build/$f.o ] || [ select.cuh -nt build/$f.o ] || [ comm.cuh -nt build/$f.o ] || [ rng.cuh -nt build/$f.o ] || [ pf_common.cuh -nt build/$f.o ] || [ gk.cuh -nt build/$f.o ] || [ ../../include/mocat_b200.h -nt build/$f.o ]; then
     ( $NVCC $FLAGS -c $f.cu -o build/$f.o > build/$f.log 2>&1 || { cat build/$f.log; exit 1; } ) &
     pids+=($!)
   fi

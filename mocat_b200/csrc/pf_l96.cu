@@ -255,7 +255,13 @@ __device__ __forceinline__ void l96_body(const L96Args& a) {
     if (!INIT && tile < ntiles) { cur = describe(tile); fetch(cur); }
     for (; tile < ntiles; tile += stride) {
         const bool more = tile + stride < ntiles;
-        if (!INIT && more) nxtw = describe(tile + stride);             // ancestors of the next group: loaded a group ahead
+        // ancestors of the next group: the line is pulled into L1 now and read half a group later, right before the
+        // window is refilled (read here, the span reductions waited for the load: 60 % of the long-scoreboard stalls of
+        // the kernel sat on the first REDUX, profiles/ncu_c3_r2h.md)
+        if (!INIT && more && resample) {
+            const int64_t inext = (tile + stride) * 32 + lane;
+            if (inext < a.n) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.anc + inext));
+        }
         if (!INIT && cur.mode != 2) {
             uint32_t done = 0;
             while (!done)
@@ -281,7 +287,7 @@ __device__ __forceinline__ void l96_body(const L96Args& a) {
                 for (int r = 0; r < CPL; ++r) x[r] = f2_pack(bP[r], bQ[r]);
                 if (sub == 1) {                                        // the window is in registers: refill it
                     __syncwarp();
-                    if (more) fetch(nxtw);
+                    if (more) { nxtw = describe(tile + stride); fetch(nxtw); }
                 }
                 for (int s = 0; s < a.substeps; ++s) l96_rk4<CPL>(x, c, prev, next);
             }
@@ -501,6 +507,7 @@ extern "C" int mb_pf_l96_step(mb_ctx* ctx, const mb_ssm* ssm, const float* x_in,
 // weight underflows fp32 relative to the maximum (exp(lw - wmax) < 2^-50) are skipped together with their row,
 // so a collapsed population costs 4 B per particle instead of 4 (D + 1).
 #define TM_THREADS 256
+#define TM_UNROLL 8
 __global__ void __launch_bounds__(TM_THREADS)
 rows_moments_kernel(const float* __restrict__ x, int64_t n, int d, const float* __restrict__ lw, const mb_control* ctl,
                     const float* __restrict__ shift, double* partials /*[gridDim.x][1 + 2 d]*/) {
@@ -512,19 +519,34 @@ rows_moments_kernel(const float* __restrict__ x, int64_t n, int d, const float* 
     const float sh0 = (c0 < d) ? (shift ? shift[c0] : x[c0]) : 0.f, sh1 = (c1 < d) ? (shift ? shift[c1] : x[c1]) : 0.f;
     double s0 = 0.0, a0 = 0.0, b0 = 0.0, a1 = 0.0, b1 = 0.0;
     const int64_t ngroups = (n + 31) >> 5;
-    for (int64_t grp = (int64_t)blockIdx.x * nw + warp; grp < ngroups; grp += (int64_t)gridDim.x * nw) {
-        const int64_t i = grp * 32 + lane;
-        float e = 0.f;
-        if (i < n) { const float dl = lw[i] - wmax; e = (dl > -34.6f || dl != dl) ? __expf(dl) : 0.f; }
-        unsigned mask = __ballot_sync(MB_FULL, e != 0.f);
-        while (mask) {
-            const int j = __ffs(mask) - 1;
-            mask &= mask - 1;
-            const double ej = (double)__shfl_sync(MB_FULL, e, j);
-            const float* row = x + (grp * 32 + j) * d;
-            s0 += ej;
-            if (c0 < d) { const double v = (double)(row[c0] - sh0); a0 += ej * v; b0 += ej * v * v; }
-            if (c1 < d) { const double v = (double)(row[c1] - sh1); a1 += ej * v; b1 += ej * v * v; }
+    // TM_UNROLL groups per trip: their weight loads are issued back to back (a collapsed population is nothing but this
+    // 4-byte stream, and one 128-byte load in flight per warp left the kernel latency bound at 10 % of the HBM peak);
+    // the groups are then consumed in the same order as before, so the sums are bit-identical to the one-group loop
+    const int64_t gstride = (int64_t)gridDim.x * nw;
+    for (int64_t grp0 = (int64_t)blockIdx.x * nw + warp; grp0 < ngroups; grp0 += gstride * TM_UNROLL) {
+        float ev[TM_UNROLL];
+#pragma unroll
+        for (int u = 0; u < TM_UNROLL; ++u) {
+            const int64_t grp = grp0 + (int64_t)u * gstride;
+            const int64_t i = grp * 32 + lane;
+            ev[u] = (grp < ngroups && i < n) ? __ldcs(lw + i) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < TM_UNROLL; ++u) {
+            const int64_t grp = grp0 + (int64_t)u * gstride;
+            const float dl = ev[u] - wmax;
+            const bool in_range = grp < ngroups && grp * 32 + lane < n;
+            const float e = (in_range && (dl > -34.6f || dl != dl)) ? __expf(dl) : 0.f;
+            unsigned mask = __ballot_sync(MB_FULL, e != 0.f);
+            while (mask) {
+                const int j = __ffs(mask) - 1;
+                mask &= mask - 1;
+                const double ej = (double)__shfl_sync(MB_FULL, e, j);
+                const float* row = x + (grp * 32 + j) * d;
+                s0 += ej;
+                if (c0 < d) { const double v = (double)(row[c0] - sh0); a0 += ej * v; b0 += ej * v * v; }
+                if (c1 < d) { const double v = (double)(row[c1] - sh1); a1 += ej * v; b1 += ej * v * v; }
+            }
         }
     }
     double* mine = sm + (size_t)warp * (1 + 2 * d);

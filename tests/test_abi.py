@@ -42,13 +42,13 @@ def test_python_signatures_cover_header(built):
 def test_struct_sizes_match_c(built, tmp_path):
     from mocat_b200 import _lib
     src = tmp_path / "sz.c"
-    src.write_text('#include <stdio.h>\n#include "mocat_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n",'
+    src.write_text('#include <stdio.h>\n#include "mocat_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
                    'sizeof(mb_control),sizeof(mb_hist),sizeof(mb_target),sizeof(mb_move),sizeof(mb_temper),'
-                   'sizeof(mb_ssm),sizeof(mb_gk));return 0;}')
+                   'sizeof(mb_ssm),sizeof(mb_gk),sizeof(mb_teki),sizeof(mb_teki_prm));return 0;}')
     exe = tmp_path / "sz"
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
     sizes = [int(s) for s in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
-    py = [ctypes.sizeof(c) for c in (_lib.Control, _lib.Hist, _lib.Target, _lib.Move, _lib.Temper, _lib.SSM, _lib.GK)]
+    py = [ctypes.sizeof(c) for c in (_lib.Control, _lib.Hist, _lib.Target, _lib.Move, _lib.Temper, _lib.SSM, _lib.GK, _lib.Teki, _lib.TekiPrm)]
     assert sizes == py
 
 
