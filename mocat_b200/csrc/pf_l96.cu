@@ -198,8 +198,8 @@ __device__ __forceinline__ void l96_body(const L96Args& a) {
     const int64_t gid0 = a.gid0;
 
     float am = -INFINITY, as1 = 0.f, as2 = 0.f;      // per-thread online (max, sum, sumsq): one weight per lane and group
-    const int64_t ntiles = (a.n + 31) >> 5;          // groups of 32 outputs
-    const int64_t stride = (int64_t)gridDim.x * W;
+    const int ntiles = (int)((a.n + 31) >> 5);       // groups of 32 outputs (n < 2^31 per GPU: ancestors are int32)
+    const int stride = (int)gridDim.x * W;
     const int n_local = (int)a.n_local;
 
     // source of the 32 outputs of a group: `src` = this lane's source row (owner-relative), `owner` = the GPU that holds
@@ -207,9 +207,9 @@ __device__ __forceinline__ void l96_body(const L96Args& a) {
     // (the buffer starts at row r0), 1 = ROWS (lane l's row sits in slot l).  Rows and GPUs are 32-bit quantities
     // (ancestors are int32), so the span of the group is four warp reductions (REDUX), not shuffle trees.
     struct Win { int src, owner, r0, mode, nr; };
-    auto describe = [&](int64_t tile) -> Win {
+    auto describe = [&](int tile) -> Win {
         Win w;
-        const int64_t i = tile * 32 + lane;
+        const int64_t i = (int64_t)tile * 32 + lane;
         int s_ = (int)i, o = own;                    // not resampling / beyond n: the particle's own row
         if (resample && i < a.n) {
             s_ = __ldg(a.anc + i);                   // GLOBAL id of the ancestor
@@ -249,7 +249,7 @@ __device__ __forceinline__ void l96_body(const L96Args& a) {
         const long long t0 = clock64();
         while (clock64() - t0 < skew) {}
     }
-    int64_t tile = (int64_t)blockIdx.x * W + warp;
+    int tile = (int)blockIdx.x * W + warp;
     Win cur{}, nxtw{};
     uint32_t phase = 0;
     if (!INIT && tile < ntiles) { cur = describe(tile); fetch(cur); }
@@ -259,7 +259,7 @@ __device__ __forceinline__ void l96_body(const L96Args& a) {
         // window is refilled (read here, the span reductions waited for the load: 60 % of the long-scoreboard stalls of
         // the kernel sat on the first REDUX, profiles/ncu_c3_r2h.md)
         if (!INIT && more && resample) {
-            const int64_t inext = (tile + stride) * 32 + lane;
+            const int64_t inext = (int64_t)(tile + stride) * 32 + lane;
             if (inext < a.n) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.anc + inext));
         }
         if (!INIT && cur.mode != 2) {
@@ -272,7 +272,7 @@ __device__ __forceinline__ void l96_body(const L96Args& a) {
         float wq = 0.f;                                                // quadratic form of THIS lane's particle of the group
 #pragma unroll 1
         for (int sub = 0; sub < 2; ++sub) {
-            const int64_t iP = tile * 32 + sub * 16 + 2 * g;           // even particle of the pair; the odd one is iP + 1
+            const int64_t iP = (int64_t)tile * 32 + sub * 16 + 2 * g;           // even particle of the pair; the odd one is iP + 1
             f2 x[CPL];
             if (!INIT) {
                 const int lP = sub * 16 + 2 * g;
@@ -342,7 +342,7 @@ __device__ __forceinline__ void l96_body(const L96Args& a) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the TMA engine
             __syncwarp();
             if (lane == 0) {
-                const int64_t row0 = tile * 32 + sub * 16;
+                const int64_t row0 = (int64_t)tile * 32 + sub * 16;
                 asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                              ::"l"(a.x_out + row0 * D), "r"(outb_a), "r"((uint32_t)(16 * D * 4)) : "memory");
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -354,7 +354,7 @@ __device__ __forceinline__ void l96_body(const L96Args& a) {
             }
         }
         {   // log-weights of the group, one per lane: -likelihood_potential (+ the carried weight, filtering.py:292,303)
-            const int64_t iw = tile * 32 + ((p >> 1) << 4) + 2 * g + (p & 1);
+            const int64_t iw = (int64_t)tile * 32 + ((p >> 1) << 4) + 2 * g + (p & 1);
             float w = (OPT && INIT) ? 0.f : -fmaf(0.5f, wq, a.lik_const);
             if (!INIT && !resample) w += a.lw[iw];                     // lw is padded to a multiple of 32
             if (iw >= a.n) w = -INFINITY;

@@ -30,6 +30,7 @@
 //     a_i = min{ j : (i + u0) / n < C_j / S }   <=>   c_j = #{ i : (i 2^32 + k0) S < C_j n 2^32 },  a_i = j for c_{j-1} <= i < c_j
 // (128-bit integer comparison; an fp64 estimate decides except within 1e-5 of an integer).  oracle/core.py
 // `ancestors_systematic_exact` restates this with Python integers; the two agree bit for bit.
+#include <stdlib.h>
 #include "common.cuh"
 #include "rng.cuh"
 #include "comm.cuh"
@@ -87,11 +88,16 @@ __device__ __forceinline__ float rf_wmax(const RfArgs& a) {
     return wmax;
 }
 
-// rint(x) as uint64 without the 64-bit F2I (an XU-pipe instruction at quarter rate: with the exp it bound pass A at 47 %
-// of the HBM peak).  x = hr 2^20 + lo with hr = rint(x 2^-20) and lo = x - hr 2^20 EXACT in fp32 (|lo| <= 2^19), both
+// Integer weight e = rint(x) as uint64.  Three bit-identical formulations, measured at n = 1e8 (pass A / pass B + C, ms;
+// gpurun_out/call6, profiles/README.md):  0 = the 64-bit conversion instruction (XU pipe)        0.128 / 0.63 (collapsed), 0.68 (flat)
+//                                          1 = mantissa shift (branchy, ALU)                      0.176 / 0.62, 0.72
+//                                          2 = the split below (branch-free, FMA / ALU pipes)     0.172 / 0.62, 0.72
+// The conversion wins pass A by 45 us -- the XU pipe is not what bounds it -- and is the default; the others stay
+// selectable with -DMB_RF_RINT_MODE for the record.
+// Split: x = hr 2^20 + lo with hr = rint(x 2^-20) and lo = x - hr 2^20 EXACT in fp32 (|lo| <= 2^19), both
 // turned into integers by adding 1.5 * 2^23 (round-to-nearest-even lands in the mantissa); hr 2^20 is even, so the tie
-// rule of rint(lo) is that of rint(x).  Branch-free, FMA / ALU pipes only.  NaN, negative, zero -> 0 (as the saturating
-// conversion gave); x >= 2^42 (never in log mode, where x <= 2^40) takes the conversion instruction.
+// rule of rint(lo) is that of rint(x).  NaN, negative, zero -> 0 (as the saturating conversion gives); x >= 2^42 (never
+// in log mode, where x <= 2^40) takes the conversion instruction.
 __device__ __forceinline__ u64 rf_rint_u64(float x) {
     if (x >= 4398046511104.f) return __float2ull_rn(x);
     const float MAGIC = 12582912.f;                                   // 1.5 * 2^23
@@ -104,9 +110,29 @@ __device__ __forceinline__ u64 rf_rint_u64(float x) {
     return (x > 0.f) ? (u64)e : 0ull;
 }
 
+// compile-time experiment switch -DMB_RF_RINT_MODE (0: the conversion instruction, 1: mantissa shift, 2: the split above);
+// the three agree bit for bit
+__device__ __forceinline__ u64 rf_rint_shift(float x) {
+    if (!(x > 0.f)) return 0ull;
+    if (x < 8388608.f) return (u64)(__float_as_uint(x + 8388608.f) - 0x4B000000u);
+    const uint32_t bits = __float_as_uint(x);
+    const int sh = (int)(bits >> 23) - 150;
+    if (sh >= 40) return __float2ull_rn(x);
+    return (u64)((bits & 0x7fffffu) | 0x800000u) << sh;
+}
+#ifndef MB_RF_RINT_MODE
+#define MB_RF_RINT_MODE 0
+#endif
 __device__ __forceinline__ u64 rf_weight(float v, bool log_mode, float wmax, float scale) {
     const float w = log_mode ? __expf(v - wmax) : v;
-    return rf_rint_u64(w * scale);                                    // NaN, negative -> 0
+    const float x = w * scale;
+#if MB_RF_RINT_MODE == 0
+    return __float2ull_rn(x);                                         // NaN, negative -> 0 (saturating conversion)
+#elif MB_RF_RINT_MODE == 1
+    return rf_rint_shift(x);
+#else
+    return rf_rint_u64(x);                                            // NaN, negative -> 0
+#endif
 }
 
 // 16 consecutive weights of this thread -> integer weights e[] (zero beyond n)
