@@ -228,6 +228,13 @@ int mb_smc_move(mb_ctx* ctx, const mb_target* tgt, const mb_move* mv, const floa
                 float* alpha_out, uint64_t seed, int64_t gid0, mb_control* ctl, const mb_shard* sh /*or NULL*/,
                 mb_stream_t stream);
 
+/* Robbins-Monro stepsize adaptation (RMMetropolisedSMCSampler.adapt, transport/smc.py:406-421) on the device:
+ * alpha_mean = sum softmax(lw)_i alpha_i, log stepsize += rm_stepsize (alpha_mean - target).  The stepsize lives in
+ * ctl->aux1 and is read by mb_smc_move when mb_move.stepsize <= 0; init_stepsize > 0 sets it (after mb_smc_init) instead
+ * of adapting.  stepsize_hist (device doubles [MB_HIST_MAX], or NULL): stepsize_hist[ctl->iter] after every adaptation. */
+int mb_rm_adapt(mb_ctx* ctx, const float* alpha, const float* lw, int64_t n, double rm_stepsize, double target,
+                double init_stepsize, mb_control* ctl, double* stepsize_hist /*or NULL*/, mb_stream_t stream);
+
 /* ---- K1b: bootstrap particle filter.  Replaces initiate_particles (ssm/filtering.py:173-193) and one
  *      body of the scan in run_particle_filter_for_marginals (:280-311): optional ancestor gather,
  *      transition_sample, log-weight increment -likelihood_potential, ESS, log-evidence, and the

@@ -132,6 +132,7 @@ SIGNATURES = {
     "mb_kalman_filter": (C.c_int, [c_vp, C.POINTER(SSM), c_vp, C.c_int, c_vp, c_vp, c_vp, c_vp]),
     "mb_backward_sample": (C.c_int, [c_vp, C.POINTER(SSM), c_f, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_u64, c_u32, c_vp,
                                      c_vp, c_vp]),
+    "mb_rm_adapt": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_d, c_d, c_d, c_vp, c_vp, c_vp]),
     "mb_stitch_sample": (C.c_int, [c_vp, C.POINTER(SSM), c_f, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_u64, c_u32, c_vp, c_vp]),
     "mb_transition_potential": (C.c_int, [c_vp, C.POINTER(SSM), c_f, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "mb_ancestors_sharded": (C.c_int, [c_vp, c_vp, C.c_int, c_u64, c_u32, c_vp, c_i64, c_vp, c_vp]),

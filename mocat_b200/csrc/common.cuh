@@ -66,6 +66,7 @@ struct mb_ctx {
 #define MB_CNT_MISC     4
 #define MB_CNT_SCAN_EPOCH 5
 #define MB_CNT_BW_FALLBACK 8 // (64-bit, slots 8-9) median-bracket misses of the tcgen05 bandwidth kernel
+#define MB_CNT_RM_MEAN 16      // (fp64) weighted mean acceptance of the Robbins-Monro adaptation
 #define MB_NUM_COUNTERS 64
 
 int mb_ensure_scratch(mb_ctx* ctx, size_t bytes);

@@ -538,8 +538,8 @@ rows_moments_kernel(const float* __restrict__ x, int64_t n, int d, const float* 
             const bool in_range = grp < ngroups && grp * 32 + lane < n;
             const float e = (in_range && (dl > -34.6f || dl != dl)) ? __expf(dl) : 0.f;
             unsigned mask = __ballot_sync(MB_FULL, e != 0.f);
-            while (mask) {
-                const int j = __ffs(mask) - 1;
+            while (mask) {                                             // (rows of four particles in flight at once: slower,
+                const int j = __ffs(mask) - 1;                         //  0.64 vs 0.54 ms at n = 1e8 -- 80 registers)
                 mask &= mask - 1;
                 const double ej = (double)__shfl_sync(MB_FULL, e, j);
                 const float* row = x + (grp * 32 + j) * d;

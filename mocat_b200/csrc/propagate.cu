@@ -138,7 +138,8 @@ __global__ void __launch_bounds__(MV_THREADS, (D <= 6 ? 4 : (D <= 10 ? 3 : 2))) 
     const float beta = (float)ctl->beta;
     const uint32_t step = (uint32_t)(ctl->iter + 1);
     const uint64_t seed = ctl->seed;                   // device-resident key: the captured graph is seed-agnostic
-    const float eps = a.mv.stepsize;
+    // stepsize <= 0: the device-resident stepsize of the Robbins-Monro adaptation (mb_rm_adapt keeps it in ctl->aux1)
+    const float eps = a.mv.stepsize > 0.f ? a.mv.stepsize : (float)ctl->aux1;
     constexpr uint32_t S = MB_MOVE_SLOTS(D);            // Philox slots per Metropolised move (normals + accept uniform)
     __shared__ double red[MV_THREADS / 32];
     long long nan_local = 0;

@@ -598,6 +598,38 @@ extern "C" int mb_colstats(mb_ctx* ctx, const float* x, int64_t ld, int64_t n, i
     return colstats_impl(ctx, x, ld, n, d, nullptr, nullptr, mean, var, mb_s(stream));
 }
 
+// Robbins-Monro stepsize adaptation of RMMetropolisedSMCSampler.adapt (transport/smc.py:406-421) on the device:
+//   alpha_mean = sum_i softmax(log_weight)_i alpha_i ;  log stepsize += rm_stepsize (alpha_mean - target)
+// The stepsize lives in ctl->aux1 (the move kernel reads it when mb_move.stepsize <= 0), ctl->aux0 remembers the
+// iteration already adapted so that replays after termination change nothing; stepsize_hist[iter] records the chain.
+__global__ void rm_adapt_kernel(mb_control* ctl, const double* alpha_mean, double rm_stepsize, double target,
+                                double init_stepsize, double* stepsize_hist) {
+    if (init_stepsize > 0.0) {
+        ctl->aux1 = init_stepsize; ctl->aux0 = (double)ctl->iter;
+        if (stepsize_hist) stepsize_hist[ctl->iter] = init_stepsize;
+        return;
+    }
+    const int it = ctl->iter;
+    if ((int)ctl->aux0 == it) return;                                  // this iteration has been adapted (run is over)
+    const double eps = exp(log(ctl->aux1) + rm_stepsize * (*alpha_mean - target));
+    ctl->aux1 = eps; ctl->aux0 = (double)it;
+    if (stepsize_hist && it >= 0 && it < MB_HIST_MAX) stepsize_hist[it] = eps;
+}
+
+extern "C" int mb_rm_adapt(mb_ctx* ctx, const float* alpha, const float* lw, int64_t n, double rm_stepsize, double target,
+                           double init_stepsize, mb_control* ctl, double* stepsize_hist, mb_stream_t stream) {
+    MB_REQUIRE(ctx && ctl && (init_stepsize > 0.0 || (alpha && lw && n > 0)), "mb_rm_adapt: bad arguments");
+    cudaStream_t st = mb_s(stream);
+    double* mean = reinterpret_cast<double*>(ctx->counters + MB_CNT_RM_MEAN);
+    if (!(init_stepsize > 0.0)) {
+        const int rc = colstats_impl(ctx, alpha, n, n, 1, lw, ctl, mean, nullptr, st);
+        if (rc != MB_OK) return rc;
+    }
+    rm_adapt_kernel<<<1, 1, 0, st>>>(ctl, mean, rm_stepsize, target, init_stepsize, stepsize_hist);
+    MB_CHECK_LAUNCH();
+    return MB_OK;
+}
+
 extern "C" int mb_weighted_moments(mb_ctx* ctx, const float* x, int64_t ld, int64_t n, int d, const float* lw,
                                    const mb_control* ctl, double* mean, double* var, mb_stream_t stream) {
     MB_REQUIRE(ctx && x && lw && ctl && mean && n > 0 && d > 0, "mb_weighted_moments: bad arguments");

@@ -216,6 +216,21 @@ class SMCEngine(_Resampler):
         self._graphs = [None, None]
         self._ws_gen = None
         self.comm = None          # mb_comm* when the population is sharded over several GPUs (parallel.py)
+        self.rm = None            # (rm_stepsize, target, initial stepsize): Robbins-Monro adaptation on the device
+        self.stepsize_hist = None
+
+    def enable_rm(self, rm_stepsize, target):
+        """RMMetropolisedSMCSampler (transport/smc.py:376-428): the stepsize becomes device-resident (ctl->aux1) and is
+        adapted by mb_rm_adapt at the end of every update -- part of the captured step, no host round trip"""
+        if self.comm is not None:
+            raise _lib.MocatB200Error("the Robbins-Monro adaptation runs on one GPU")
+        self.rm = (float(rm_stepsize), float(target), float(self.move.stepsize))
+        self.stepsize_hist = torch.zeros(MB_HIST_MAX, dtype=torch.float64, device=self.lw.device)
+        self.move.stepsize = -1.0                                     # the move kernel reads ctl->aux1
+
+    def _rm_adapt(self, init):
+        self.L.call("mb_rm_adapt", self.ctx, ptr(self.alpha), ptr(self.lw), self.n, self.rm[0], self.rm[1],
+                    self.rm[2] if init else 0.0, ptr(self.ctl.t), ptr(self.stepsize_hist), stream())
 
     def _shard_ref(self):
         return None
@@ -242,6 +257,8 @@ class SMCEngine(_Resampler):
                     0 if x0 is not None else 1, ptr(self.up), ptr(self.lik), ptr(self.lw), self.seed, self.gid0,
                     ptr(self.ctl.t), stream())
         self._temper(advance=False)
+        if self.rm is not None:
+            self._rm_adapt(init=True)                                   # smc.py:403: the stepsize of iteration 0
         self.enqueued = 0
         self._cur0 = self.cur
 
@@ -271,6 +288,8 @@ class SMCEngine(_Resampler):
         if events:
             events[2].record()
         self._temper(advance=True)
+        if self.rm is not None:
+            self._rm_adapt(init=False)
         if events:
             events[3].record()
 
@@ -491,15 +510,22 @@ class PFEngine(_Resampler):
                     ptr(shift), ptr(sums), stream())
         return sums
 
-    def moments(self):
-        """weighted mean / variance of every coordinate under the current weights (device float64 (d,) tensors)"""
+    def moments(self, out=None):
+        """weighted mean / variance of every coordinate under the current weights (device float64 (d,) tensors, or the
+        two rows of `out` (2, d))"""
         if self.rowmajor:
-            mean = torch.empty(self.d, dtype=torch.float64, device=self.x.device)
-            var = torch.empty(self.d, dtype=torch.float64, device=self.x.device)
+            if out is not None:
+                mean, var = out[0], out[1]
+            else:
+                mean = torch.empty(self.d, dtype=torch.float64, device=self.x.device)
+                var = torch.empty(self.d, dtype=torch.float64, device=self.x.device)
             self.L.call("mb_weighted_moments_rows", self.ctx, ptr(self.x), self.n, self.d, ptr(self.lw), ptr(self.ctl.t),
                         ptr(mean), ptr(var), stream())
             return mean, var
-        return weighted_moments(self.x, self.n, self.lw, self.ctl)
+        mean, var = weighted_moments(self.x, self.n, self.lw, self.ctl)
+        if out is not None:
+            out[0], out[1] = mean, var
+        return mean, var
 
 
 # ------------------------------------------------------------------------------------------- SMC-ABC

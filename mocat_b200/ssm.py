@@ -400,8 +400,7 @@ def run_particle_filter_for_marginals(ssm_scenario, particle_filter, y, t, rando
         if msum is not None:                              # this shard's raw sums, shifted by the observation (H = I)
             eng.moment_sums(yd[i], out=msum[i])
         elif moments:
-            m, v = _moments(eng)
-            mom[i, 0], mom[i, 1] = m, v
+            eng.moments(out=mom[i])                                    # written in place: no per-step copies
 
     t0 = eng.t + 1 if initial_sample is not None else 0
     for i in range(T):

@@ -129,7 +129,7 @@ class MetropolisedSMCSampler(TemperedSMCSampler):
         except Exception:
             world = 1
         if world > 1 and getattr(self, '_private_engine', False):
-            raise _lib.MocatB200Error("RMMetropolisedSMCSampler is single-GPU for now (stepsize is a host-side launch parameter)")
+            raise _lib.MocatB200Error("RMMetropolisedSMCSampler is single-GPU for now (the acceptance mean is not sharded)")
         if world > 1 and getattr(self, 'sharded', True):
             # under torchrun `n` is the GLOBAL population size; every rank holds n/world particles, passes its
             # own shard of initial_state.value and gets its own shard back (mocat_b200/parallel.py)
@@ -138,14 +138,14 @@ class MetropolisedSMCSampler(TemperedSMCSampler):
             eng = parallel.acquire_sharded_smc(target, move, temper, n_local, seed, _RESAMPLING[self.resampling],
                                                schedule=self.temperature_schedule)
         else:
-            if getattr(self, '_private_engine', False):                  # launch parameters change between iterations
+            if getattr(self, '_private_engine', False):                  # engine with sampler-specific device state
                 eng = engine.SMCEngine(target, move, temper, n, seed, resampling=_RESAMPLING[self.resampling],
                                        schedule=self.temperature_schedule)
-                eng.use_graphs = False
             else:
                 eng = engine.SMCEngine.acquire(target, move, temper, n, seed, resampling=_RESAMPLING[self.resampling],
                                                schedule=self.temperature_schedule)
         x0 = None if initial_state is None else getattr(initial_state, 'value', None)
+        self._configure_engine(eng)
         eng.startup(x0)                                                 # smc.py:128-164, 267-296 on the device
         scenario.temperature = 0.
         initial_extra.engine = eng
@@ -172,6 +172,9 @@ class MetropolisedSMCSampler(TemperedSMCSampler):
         out.potential = out.prior_potential + c['beta'] * out.likelihood_potential
         out.temperature, out.ess, out.log_norm_constant = c['beta'], c['ess'], c['log_z']
         return out
+
+    def _configure_engine(self, eng):
+        pass
 
     def _post_update(self, eng, extra):
         """hook between population steps (the reference's `adapt` extensions); nothing for the plain sampler"""
@@ -251,30 +254,22 @@ def _to_host(tensors):
 class RMMetropolisedSMCSampler(MetropolisedSMCSampler):
     """transport/smc.py:376-428: Robbins-Monro adaptation of the MCMC stepsize between iterations,
     log eps += rm_stepsize * (alpha_mean - target), alpha_mean = average acceptance weighted by exp(w - max w).
-    The weighted mean is reduced on the device (mb_weighted_moments); the stepsize is a launch parameter of the move
-    kernel, so this sampler enqueues plain launches (no graph replay) and reads one double per iteration."""
+    Runs entirely on the device (mb_rm_adapt): the stepsize lives in the control block, the adaptation is part of the
+    captured step, and the chain of stepsizes is read back once at the end."""
     _private_engine = True
 
     def __init__(self, *args, rm_stepsize=1., **kwargs):
         super().__init__(*args, **kwargs)
         self.parameters.rm_stepsize = rm_stepsize
-        self.check_every = 1
 
-    def startup(self, scenario, n, initial_state, initial_extra, **kwargs):
-        initial_state, initial_extra = super().startup(scenario, n, initial_state, initial_extra, **kwargs)
-        self._stepsizes = [float(initial_extra.engine.move.stepsize)]   # smc.py:403: state.stepsize at iteration 0
-        return initial_state, initial_extra
-
-    def _post_update(self, eng, extra):                                # smc.py:406-421
-        alpha_mean = float(engine.weighted_moments(eng.alpha.view(1, eng.n), eng.n, eng.lw, eng.ctl)[0].item())
-        log_eps = np.log(float(eng.move.stepsize)) + self.parameters.rm_stepsize * (alpha_mean - self.mcmc_sampler.tuning.target)
-        eng.move.stepsize = float(np.exp(log_eps))
-        extra.parameters.stepsize = eng.move.stepsize
-        self._stepsizes.append(eng.move.stepsize)
+    def _configure_engine(self, eng):
+        eng.enable_rm(self.parameters.rm_stepsize, self.mcmc_sampler.tuning.target)
 
     def _run_device(self, scenario, initial_state, initial_extra):
         chain = super()._run_device(scenario, initial_state, initial_extra)
-        chain.stepsize = np.asarray(self._stepsizes[:len(chain.temperature)])      # clean_chain :423-428
+        eng = initial_extra.engine
+        chain.stepsize = eng.stepsize_hist[:len(chain.temperature)].cpu().numpy()  # clean_chain :423-428
+        initial_extra.parameters.stepsize = float(chain.stepsize[-1])
         return chain
 
 

@@ -92,7 +92,7 @@ def test_samplers_reject_what_the_device_cannot_run():
                 return 0.0
         MyScenario()
     s = mocat.RMMetropolisedSMCSampler(mocat.Underdamped(stepsize=0.1), rm_stepsize=0.5)
-    assert s.parameters.rm_stepsize == 0.5 and s.check_every == 1 and s.mcmc_sampler.tuning.target == 0.651
+    assert s.parameters.rm_stepsize == 0.5 and s.check_every == 8 and s.mcmc_sampler.tuning.target == 0.651   # adapted on the device: no per-iteration poll
     assert mocat.RandomWalk(stepsize=0.1).tuning.target == 0.234        # standard_mcmc.py:29,84
 
 
