@@ -258,7 +258,7 @@ def c2_record(steps):
             "particle_steps_per_s": n / (ms * 1e-3), "ms_per_step": ms, "steps_timed": done}
 
 
-def c5_record(steps, peaks):
+def c5_record(steps, peaks, ncu=None):
     """C5: one SMC-ABC population step on the g-and-k model (m = 8 draws), n = 1e8 on one GPU"""
     import numpy as np
     import torch
@@ -284,11 +284,26 @@ def c5_record(steps, peaks):
     ms = float(np.median(ts))
     hbm = float(peaks.get("hbm_gbs", 6650.0))
     c = eng.ctl.read()
-    return {"workload": "C5 SMC-ABC, g-and-k (m=8 sorted draws), RW-ABC move, n=1e8 on one GPU, ESS-triggered "
-                        "multinomial resampling",
-            "particle_steps_per_s": n / (ms * 1e-3), "ms_per_step": ms, "steps_timed": steps,
-            "hbm_frac_of_60B_contract": 60.0 * n / (ms * 1e-3) / 1e9 / hbm, "iter": int(c['iter']),
-            "note": "the propagate kernel is simulator (ALU/MUFU) bound: 8 x (ndtri + exp + pow) per particle"}
+    rec = {"workload": "C5 SMC-ABC, g-and-k (m=8 sorted draws), RW-ABC move, n=1e8 on one GPU, ESS-triggered "
+                       "multinomial resampling",
+           "particle_steps_per_s": n / (ms * 1e-3), "ms_per_step": ms, "steps_timed": steps,
+           "hbm_frac_of_60B_contract": 60.0 * n / (ms * 1e-3) / 1e9 / hbm, "iter": int(c['iter']),
+           "note": "the propagate kernel is simulator (ALU/MUFU) bound: 8 x (ndtri + exp + pow) per particle"}
+    k = (ncu or {}).get("abc_move_kernel")
+    if k and k.get("thread_instructions_per_particle"):
+        # the simulator-bound kernel against the instruction-issue ceiling (148 SMs x 4 schedulers x 32 lanes
+        # per clock) instead of HBM; instruction count and pipe shares from the ncu capture of the same build
+        props = torch.cuda.get_device_properties(0)
+        clock_hz = 1965e6
+        peak = props.multi_processor_count * 4 * 32 * clock_hz
+        share = (k.get("duration_s_under_ncu") or 0.0) * (n / k["units_per_launch"]) / (ms * 1e-3) if k.get("units_per_launch") else None
+        rec["issue_roofline"] = {"kernel": "abc_move_kernel<8>", "bound": "issue (fp32 / MUFU)",
+                                 "thread_instructions_per_particle": k["thread_instructions_per_particle"],
+                                 "peak_thread_instructions_per_s": peak,
+                                 "frac_of_issue_peak_whole_step": k["thread_instructions_per_particle"] * n / (ms * 1e-3) / peak,
+                                 "xu_pipe_pct_ncu": k.get("xu_pipe_pct"), "issue_active_pct_ncu": k.get("issue_active_pct"),
+                                 "kernel_share_of_step_ncu": share, "source": k.get("source")}
+    return rec
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -437,7 +452,7 @@ def main():
     extras = {}
     if world == 1 and not a.no_extras:
         for name, fn in (("svgd", lambda: svgd_record(200, peaks, ncu)), ("c2", lambda: c2_record(100)),
-                         ("c5", lambda: c5_record(10, peaks))):
+                         ("c5", lambda: c5_record(10, peaks, ncu))):
             try:
                 extras[name] = fn()
             except Exception as exc:                                  # a sub-record must not take the headline down
