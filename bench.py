@@ -108,6 +108,9 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(sm)}
 
+    def count_since(self, t0):
+        return sum(1 for ts, _ in self.lines if ts >= t0)
+
 
 # ------------------------------------------------------------------------------------------------ CPU arm
 def cpu_arm(n, steps, warmup, seed, workers=None):
@@ -355,10 +358,10 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    clocks = ClockSampler(local)
+    clocks.start()                                   # nvidia-smi needs a moment to come up: started before the warm-up
     pf.init(yd[0])
     sync()
-    clocks = ClockSampler(local)
-    clocks.start()
     nw = max(a.warmup, 3)
     for t in range(1, nw + 1):
         pf.step(yd[t])
@@ -386,13 +389,25 @@ def main():
         m[2].record()
         marks.append(m)
     sync()
-    clk = clocks.stop(t_wall0, t_wall1)
     t_res = float(np.median([m[0].elapsed_time(m[1]) for m in marks]))
     t_step = float(np.median([m[1].elapsed_time(m[2]) for m in marks]))
     ctl = pf.ctl.read()
     red = torch.tensor([tot, t_res, t_step], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(red, op=dist.ReduceOp.MAX)
+    # a short timed region (many GPUs) can end before nvidia-smi's 100 ms period delivers a sample: every rank then keeps
+    # the same loop running, untimed, for the same number of further steps (the count follows from the all-reduced time,
+    # so the ranks of a sharded population stay in lock step), and the clocks record says that the window was widened
+    extra_steps = 0
+    if float(red[0]) < 500.0:
+        extra_steps = int((500.0 - float(red[0])) / max(float(red[0]) / a.steps, 1e-3)) + 1
+        for k in range(extra_steps):
+            pf.step(yd[nw + 1 + (k % a.steps)])
+        sync()
+    clk = clocks.stop(t_wall0, time.perf_counter())
+    if extra_steps:
+        clk["window"] = ("timed region + %d further untimed steps of the same loop (the timed region is shorter than "
+                         "the sampling period)" % extra_steps)
     tot, t_res, t_step = (float(v) for v in red.tolist())
     ms_per_step = tot / a.steps
     value = n_total / (ms_per_step * 1e-3)
