@@ -212,3 +212,37 @@ def test_kalman_filter_host_matches_oracle_and_struct_mirror():
     npt.assert_allclose([s.F[0], s.F[1], s.F[stride], s.F[stride + 1]], F.ravel(), rtol=1e-7)
     LQ = np.linalg.cholesky(Q)
     npt.assert_allclose([s.LQ[0], s.LQ[stride], s.LQ[stride + 1]], [LQ[0, 0], LQ[1, 0], LQ[1, 1]], rtol=1e-6)
+
+
+def test_teki_samplers_route_options_like_the_reference():
+    """transport/teki.py:41-72,155-166: a schedule fixes max_temperature / max_iter, the adaptive sampler keeps its search
+    parameters in `parameters`; a Python next_temperature callable cannot run on the device"""
+    s = mocat.TemperedEKI(temperature_schedule=np.linspace(0.0, 0.8, 9), nugget=1e-4)
+    assert s.max_iter == 9 and s.max_temperature == pytest.approx(0.8) and s._mode() == 0
+    assert s.parameters.nugget == 1e-4 and s.parameters.term_std == 0.0
+    d = mocat.TemperedEKI()
+    assert d._mode() == 1 and d.max_iter == 10000 and d.max_temperature == 1.0
+    a = mocat.AdaptiveTemperedEKI(ess_threshold=0.7, bisection_tol=1e-4, max_bisection_iter=50, max_iter=30)
+    assert a._mode() == 2 and a.max_iter == 30
+    assert a._engine_kwargs() == dict(ess_threshold=0.7, tol=1e-4, max_search_iter=50)
+    with pytest.raises(mocat._lib.MocatB200Error):
+        mocat.TemperedEKI(next_temperature=lambda state, extra: 0.5)
+    with pytest.raises(AttributeError):                                     # teki.py:77-78: the scenario needs data
+        class NoData:
+            data = None
+        s.startup(NoData(), 10, None, mocat.cdict())
+
+
+def test_online_smoothing_host_helpers():
+    """the smoother's ESS test (online_smoothing.py:227: resample iff ess < n - 1e-3) and the namespace of the reference
+    (mocat/ssm.py exports propagate_particle_smoother{,_pf,_bs})"""
+    from mocat_b200 import online_smoothing as osm
+    assert osm._ess(np.zeros(100)) == pytest.approx(100.0)
+    assert osm._ess(np.log(np.r_[1.0, np.zeros(99) + 1e-300])) == pytest.approx(1.0)
+    for name in ("propagate_particle_smoother", "propagate_particle_smoother_pf", "propagate_particle_smoother_bs",
+                 "backward_simulation", "forward_filtering_backward_simulation"):
+        assert callable(getattr(mocat.ssm, name))
+    with pytest.raises(mocat._lib.MocatB200Error):                          # no live engine: loaded from disk
+        osm.propagate_particle_smoother_pf(mocat.ssm.TimeHomogenousLinearGaussian(dim=1), mocat.ssm.BootstrapFilter(),
+                                           mocat.cdict(value=np.zeros((1, 4, 1)), log_weight=np.zeros((1, 4)), t=np.zeros(1)),
+                                           np.zeros(1), 1.0, 0, 2)
