@@ -4,9 +4,10 @@
 // x1_j at time t+1 draw an index i ~ Cat(lw_i - transition_potential(x0_i -> x1_j)) over the n_pf filter particles at
 // time t (random.categorical = Gumbel-max) and take x0_i.  An n_samples x n_pf contraction with a categorical-sample
 // epilogue; the transition is Gaussian (linear_gaussian.py:73-84, nonlinear_gaussian.py:98-105), so after whitening
-// (a_i = L_Q^-1 mean(x0_i), b_j = L_Q^-1 x1_j) the potential is |a_i - b_j|^2 / 2 + const and the constant cancels.
+// (a_i = mean(x0_i) L_Q^-1, b_j = x1_j L_Q^-1: the reference's row-vector convention, see bs_whiten_lg) the potential is
+// |a_i - b_j|^2 / 2 + const and the constant cancels.
 //
-//   bs_means_kernel    a_i for every filter particle: F x0 (linear-Gaussian, forward substitution with L_Q) or the RK4
+//   bs_means_kernel    a_i for every filter particle: F x0 (linear-Gaussian, times L_Q^-1 from the right) or the RK4
 //                      flow of Lorenz-96 scaled by 1 / q_std; one thread per particle, row-major (n, d).
 //   bs_sample_kernel   one thread per backward sample j, tiles of 128 filter particles staged in shared memory;
 //                      s_ij = lw_i - |a_i - b_j|^2 / 2 (fp32) + Gumbel noise from Philox (counter: gid = j, step = time
@@ -44,6 +45,21 @@ __device__ __forceinline__ void bs_l96_rhs(const float (&x)[D], float F, float (
     for (int r = 0; r < D; ++r) k[r] = (x[(r + 1) % D] - x[(r + D - 2) % D]) * x[(r + D - 1) % D] + (F - x[r]);
 }
 
+// Whitening of the linear-Gaussian transition AS THE REFERENCE DOES IT: gaussian_potential evaluates
+// 0.5 |(x - mean) @ sqrt_prec|^2 with sqrt_prec = inv(chol(Q)) (utils.py:26-30, reset_covariance utils.py:257-258) -- the
+// ROW vector times L^-1, i.e. the precision (L^T L)^-1, which is Q^-1 for diagonal Q only.  Mirrored exactly (the
+// likelihood potential of the filter kernels does the same with R): z = v L^-1 by back substitution with L^T.
+template <int D>
+__device__ __forceinline__ void bs_whiten_lg(const mb_ssm& m, float (&v)[D]) {
+#pragma unroll
+    for (int j = D - 1; j >= 0; --j) {
+        float acc = v[j];
+#pragma unroll
+        for (int i = j + 1; i < D; ++i) acc = fmaf(-m.LQ[i * MB_MAX_SMALL_DIM + j], v[i], acc);
+        v[j] = acc / m.LQ[j * MB_MAX_SMALL_DIM + j];
+    }
+}
+
 template <int D>
 __global__ void __launch_bounds__(BS_THREADS) bs_means_kernel(BsArgs a) {
     const mb_ssm& m = a.ssm;
@@ -59,13 +75,7 @@ __global__ void __launch_bounds__(BS_THREADS) bs_means_kernel(BsArgs a) {
                 for (int c = 0; c < D; ++c) acc = fmaf(m.F[r * MB_MAX_SMALL_DIM + c], x[c], acc);
                 v[r] = acc;
             }
-#pragma unroll
-            for (int r = 0; r < D; ++r) {                              // L_Q z = mean (forward substitution)
-                float acc = v[r];
-#pragma unroll
-                for (int c = 0; c < r; ++c) acc = fmaf(-m.LQ[r * MB_MAX_SMALL_DIM + c], v[c], acc);
-                v[r] = acc / m.LQ[r * MB_MAX_SMALL_DIM + r];
-            }
+            bs_whiten_lg<D>(m, v);                                     // z = mean L_Q^-1 (the reference's convention)
         } else {                                                       // Lorenz-96: `substeps` RK4 steps, then / q_std
             const float h = a.dt / (float)m.substeps;
             for (int s = 0; s < m.substeps; ++s) {
@@ -110,13 +120,7 @@ __global__ void __launch_bounds__(BS_THREADS) bs_sample_kernel(BsArgs a) {
 #pragma unroll
         for (int k = 0; k < D; ++k) v[k] = a.x1[j * D + k];
         if (m.kind == MB_SSM_LINEAR_GAUSSIAN) {
-#pragma unroll
-            for (int r = 0; r < D; ++r) {
-                float acc = v[r];
-#pragma unroll
-                for (int c = 0; c < r; ++c) acc = fmaf(-m.LQ[r * MB_MAX_SMALL_DIM + c], v[c], acc);
-                v[r] = acc / m.LQ[r * MB_MAX_SMALL_DIM + r];
-            }
+            bs_whiten_lg<D>(m, v);
         } else {
             const float iq = 1.f / m.q_std;
 #pragma unroll
@@ -191,13 +195,7 @@ extern "C" int mb_backward_sample(mb_ctx* ctx, const mb_ssm* ssm, float dt, cons
 template <int D>
 __device__ __forceinline__ void bs_whiten(const mb_ssm& m, float (&v)[D]) {
     if (m.kind == MB_SSM_LINEAR_GAUSSIAN) {
-#pragma unroll
-        for (int r = 0; r < D; ++r) {
-            float acc = v[r];
-#pragma unroll
-            for (int c = 0; c < r; ++c) acc = fmaf(-m.LQ[r * MB_MAX_SMALL_DIM + c], v[c], acc);
-            v[r] = acc / m.LQ[r * MB_MAX_SMALL_DIM + r];
-        }
+        bs_whiten_lg<D>(m, v);
     } else {
         const float iq = 1.f / m.q_std;
 #pragma unroll

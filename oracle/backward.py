@@ -37,8 +37,10 @@ def full_resampling(ssm, x0, lw0, x1, seed, step):
     x1 = np.asarray(x1, np.float64)
     if hasattr(ssm, 'LQ'):                                              # linear Gaussian: mean F x0, whiten with chol(Q)
         mean = x0 @ ssm.F.T
-        a = np.linalg.solve(ssm.LQ, mean.T).T
-        b = np.linalg.solve(ssm.LQ, x1.T).T
+        # the reference evaluates 0.5 |(x1 - mean) @ inv(chol(Q))|^2 (utils.py:26-30, reset_covariance :257-258): row
+        # vector times L^-1, i.e. the precision (L^T L)^-1 -- equal to Q^-1 for diagonal Q only.  Mirrored exactly.
+        a = np.linalg.solve(ssm.LQ.T, mean.T).T
+        b = np.linalg.solve(ssm.LQ.T, x1.T).T
     else:                                                               # Lorenz-96: RK4 flow, isotropic process noise
         mean = ssm.transition_function(x0)
         a, b = mean / ssm.q_std, x1 / ssm.q_std

@@ -30,11 +30,12 @@ def gumbel(seed, n_s, n_c, step, purpose=P_STITCH):
 
 
 def _whitened(ssm, x0, x1):
-    """(L_Q^-1 transition_mean(x0), L_Q^-1 x1, log det L_Q)"""
+    """(transition_mean(x0) @ L_Q^-1, x1 @ L_Q^-1, log det L_Q) -- the reference's row-vector convention"""
     x0, x1 = np.asarray(x0, np.float64), np.asarray(x1, np.float64)
     if hasattr(ssm, 'LQ'):
-        a = np.linalg.solve(ssm.LQ, (x0 @ ssm.F.T).T).T
-        b = np.linalg.solve(ssm.LQ, x1.T).T
+        # (x - mean) @ inv(chol(Q)) as the reference (utils.py:26-30, :257-258): see oracle/backward.py
+        a = np.linalg.solve(ssm.LQ.T, (x0 @ ssm.F.T).T).T
+        b = np.linalg.solve(ssm.LQ.T, x1.T).T
         logdet = float(np.sum(np.log(np.diag(ssm.LQ))))
     else:
         a, b = ssm.transition_function(x0) / ssm.q_std, x1 / ssm.q_std
@@ -43,7 +44,7 @@ def _whitened(ssm, x0, x1):
 
 
 def transition_potential(ssm, x0, x1):
-    """matched pairs (x0_i -> x1_i): |L_Q^-1 (x1 - mean(x0))|^2 / 2 + (d log 2 pi - log det prec) / 2 (utils.py:79)"""
+    """matched pairs (x0_i -> x1_i): |(x1 - mean(x0)) @ L_Q^-1|^2 / 2 + (d log 2 pi - log det prec) / 2 (utils.py:26-30,79)"""
     a, b, logdet = _whitened(ssm, x0, x1)
     d = a.shape[-1]
     return 0.5 * np.sum((a - b) ** 2, axis=-1) + 0.5 * d * np.log(2 * np.pi) + logdet

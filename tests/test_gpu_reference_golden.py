@@ -1,0 +1,77 @@
+"""CUDA path against outputs of the REFERENCE ITSELF (tests/golden/reference_v1.npz: /root/reference/mocat executed under a
+NumPy stand-in for jax, tests/golden/make_reference_golden.py) -- neither `oracle/` nor the reference is imported here.
+fp32 kernels against the reference's algorithms in fp64: tolerances are fp32 round-off of the respective formula."""
+import os
+
+import numpy as np
+import numpy.testing as npt
+import pytest
+
+pytestmark = pytest.mark.gpu
+R = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_v1.npz"))
+
+
+@pytest.fixture(scope="module")
+def mocat(lib):
+    import mocat_b200
+    return mocat_b200
+
+
+def _t(a):
+    import torch
+    return torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32), device="cuda")
+
+
+def test_reference_ess(mocat):                                             # metrics.py:69-78
+    assert mocat.log_ess_log_weight(R["ess_lw"].astype(np.float32)) == pytest.approx(float(R["ess_log"]), abs=5e-6)
+    assert mocat.ess_log_weight(R["ess_lw"].astype(np.float32)) == pytest.approx(float(R["ess_lin"]), rel=1e-5)
+
+
+def test_reference_gaussian_kernel_and_bandwidths(mocat):                  # kernels.py:82-116,220-229
+    k = mocat.kernels.Gaussian(bandwidth=1.3)
+    a, b = R["k_a"], R["k_b"]
+    assert k(a, b) == pytest.approx(float(R["k_val"]), rel=1e-5)
+    npt.assert_allclose(k.grad_x(a, b), R["k_grad_x"], rtol=2e-5)
+    npt.assert_allclose(k.grad_y(a, b), R["k_grad_y"], rtol=2e-5)
+    X = R["bw_X"].astype(np.float32)
+    assert mocat.kernels.median_bandwidth_update(X, 0) == pytest.approx(float(R["bw_median"]), rel=2e-5)
+    assert mocat.kernels.mean_bandwidth_update(X, 0) == pytest.approx(float(R["bw_mean"]), rel=2e-5)
+
+
+def test_reference_svgd_interaction(mocat):                                # transport/svgd.py:18-32
+    import torch
+    from mocat_b200 import engine
+    h = torch.tensor([0.9], dtype=torch.float32, device="cuda")
+    phi = engine.svgd_phi(_t(R["bw_X"]), _t(R["svgd_G"]), h, 0).cpu().numpy()
+    npt.assert_allclose(phi, R["svgd_phi"], atol=3e-5 * np.abs(R["svgd_phi"]).max(), rtol=1e-4)
+
+
+def test_reference_ksd(mocat):                                             # metrics.py:88-130
+    k = mocat.kernels.Gaussian(bandwidth=1.1)
+    X, G = R["bw_X"].astype(np.float32), R["svgd_G"].astype(np.float32)
+    assert mocat.metrics.ksd(X, k, grad_potential=G, bandwidth=1.1) == pytest.approx(float(R["ksd_plain"]), rel=3e-4)
+    got = mocat.metrics.ksd(X, k, grad_potential=G, log_weight=R["ksd_lw"].astype(np.float32), bandwidth=1.1)
+    assert got == pytest.approx(float(R["ksd_weighted"]), rel=3e-4)
+
+
+def test_reference_linear_gaussian_potentials_and_kalman(mocat):          # linear_gaussian.py:73-84; kalman.py:16-57
+    sc = mocat.ssm.TimeHomogenousLinearGaussian(np.zeros(3), np.eye(3), R["lg_F"], R["lg_Q"], R["lg_H"], R["lg_R"])
+    pot = mocat.online_smoothing.transition_potential(sc, R["lg_x0"], 0.0, R["lg_x1"], 1.0)
+    npt.assert_allclose(pot, R["lg_transition_potential"], rtol=2e-5, atol=2e-5)     # full Q: the reference's convention
+    means, covs = mocat.ssm.run_kalman_filter_for_marginals(sc, R["kalman_y"], np.arange(15.0))[:2]
+    npt.assert_allclose(means, R["kalman_mean"], rtol=5e-5, atol=5e-5)      # the model struct and y are fp32
+    npt.assert_allclose(covs, R["kalman_cov"], rtol=5e-5, atol=5e-6)
+
+
+def test_reference_lorenz96_transition_potential(mocat):                  # lorenz96.py:14-44; nonlinear_gaussian.py:98-105
+    """five RK4 substeps are within 5e-5 of the reference's adaptive Dormand-Prince flow, so the
+    potentials agree to |x' - flow| * 5e-5"""
+    sc = mocat.ssm.Lorenz96(dim=8, substeps=5)
+    pot = mocat.online_smoothing.transition_potential(sc, R["l96_x"], 0.0, R["l96_xnew"], 0.05)
+    npt.assert_allclose(pot, R["l96_transition_potential"], atol=2e-3)
+
+
+def test_reference_rastrigin_potential(mocat):                            # scenarios/toy_examples.py:135-149
+    sc = mocat.scenarios.Rastrigin(dim=5, a=1.3, prior_std=3.0)
+    got = np.asarray(sc.likelihood_potential(R["ras_x"].astype(np.float32)))
+    npt.assert_allclose(got, R["ras_likelihood_potential"], rtol=2e-5, atol=2e-4)

@@ -13,10 +13,22 @@ def _lg(d, rng):
 
 
 def test_transition_potential_is_negative_log_density():
+    """diagonal process noise: the reference's potential (utils.py:26-30,49-79) is the negative log transition density;
+    FULL covariance: the reference multiplies the ROW vector by inv(chol(Q)) (reset_covariance, utils.py:257-258), which
+    is the density of the precision (L^T L)^-1, not Q^-1 -- mirrored exactly by the oracle and the device (and pinned on
+    the reference's own output by tests/test_reference_golden_cpu.py)"""
     rng = np.random.default_rng(0)
-    o, F, Q = _lg(3, rng)
+    F = 0.5 * rng.standard_normal((3, 3))
+    Qd = np.diag([0.4, 1.1, 2.0])
+    o = om.LinearGaussianSSM(np.zeros(3), np.eye(3), F, Qd, np.eye(3), np.eye(3))
     x0, x1 = rng.standard_normal((6, 3)), rng.standard_normal((6, 3))
-    ref = [-mvn.logpdf(x1[i], F @ x0[i], Q) for i in range(6)]
+    ref = [-mvn.logpdf(x1[i], F @ x0[i], Qd) for i in range(6)]
+    np.testing.assert_allclose(oos.transition_potential(o, x0, x1), ref, rtol=1e-12)
+    o, F, Q = _lg(3, rng)                                              # full Q
+    L = np.linalg.cholesky(Q)
+    quirk = np.linalg.inv(L.T @ L)                                     # the precision the reference's formula implies
+    ref = [0.5 * (x1[i] - F @ x0[i]) @ quirk @ (x1[i] - F @ x0[i]) + 1.5 * np.log(2 * np.pi) + np.log(np.diag(L)).sum()
+           for i in range(6)]
     np.testing.assert_allclose(oos.transition_potential(o, x0, x1), ref, rtol=1e-12)
     l96 = om.Lorenz96SSM(dim=8, q_std=0.7)
     x0 = rng.standard_normal((4, 8)) + 3
