@@ -28,7 +28,8 @@ def _stack(outs):
         aux = flat[0][1]
         n = len(flat[0][0])
         return type(first).tree_unflatten(aux, [_stack([f[0][k] for f in flat]) for k in range(n)])
-    return np.stack([np.asarray(o) for o in outs])
+    from .numpy import ShimArray
+    return np.stack([np.asarray(o) for o in outs]).view(ShimArray)
 
 
 def _axis_size(arg, ax):

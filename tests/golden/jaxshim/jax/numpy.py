@@ -13,3 +13,54 @@ def array(x, dtype=None, **kw):
 
 def asarray(x, dtype=None, **kw):
     return _np.asarray(x, dtype=dtype)
+
+
+class _At:
+    def __init__(self, arr):
+        self.arr = arr
+
+    def __getitem__(self, idx):
+        arr = self.arr
+
+        class _Setter:
+            def set(self, value):
+                out = _np.array(arr, copy=True).view(ShimArray)
+                out[idx] = value
+                return out
+
+            def add(self, value):
+                out = _np.array(arr, copy=True).view(ShimArray)
+                out[idx] += value
+                return out
+        return _Setter()
+
+
+class ShimArray(_np.ndarray):
+    """ndarray with the two jax.Array members the reference touches: .at[...].set() and .block_until_ready()"""
+
+    @property
+    def at(self):
+        return _At(self)
+
+    def block_until_ready(self):
+        return self
+
+
+def array(x, dtype=None, **kw):  # noqa: F811
+    return _np.array(x, dtype=dtype).view(ShimArray)
+
+
+def asarray(x, dtype=None, **kw):  # noqa: F811
+    return _np.asarray(x, dtype=dtype).view(ShimArray)
+
+
+def zeros(shape, dtype=float):  # noqa: F811
+    return _np.zeros(shape, dtype=dtype).view(ShimArray)
+
+
+def ones(shape, dtype=float):  # noqa: F811
+    return _np.ones(shape, dtype=dtype).view(ShimArray)
+
+
+def append(arr, values, axis=None):  # noqa: F811
+    return _np.append(arr, values, axis=axis).view(ShimArray)

@@ -1,0 +1,112 @@
+"""Generate tests/golden/reference_runs_v1.npz: END-TO-END runs of the reference's own samplers.
+
+Same mechanism as make_reference_golden.py (the reference's unmodified source under the NumPy stand-in for jax,
+tests/golden/jaxshim), but whole algorithms instead of single functions: tempered EKI on the g-and-k simulator and the
+fixed-lag particle smoothers / FFBSi on a 1-d linear-Gaussian model -- the (f)-rows of SURVEY section 8 for which the
+reference ships no test.  The random streams are NumPy's, not jax's threefry, so these are STATISTICAL references: the
+tests compare summary statistics (temperature ladders, posterior moments, smoothing errors, path degeneracy) within
+Monte-Carlo tolerances, never samples.  vmap is a Python loop here, hence the small ensembles (about 5 minutes in total).
+
+Run from the repo root, in the build container:  python tests/golden/make_reference_runs.py
+"""
+import os
+import sys
+
+sys.dont_write_bytecode = True
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "jaxshim"))
+sys.path.insert(0, "/root/reference")
+
+import numpy as np  # noqa: E402
+from scipy.special import ndtri  # noqa: E402
+
+import mocat  # noqa: E402  (the reference)
+from mocat.src.abc.scenarios.gk import GKTransformedUniformPrior  # noqa: E402
+from mocat.src.ssm.linear_gaussian.linear_gaussian import TimeHomogenousLinearGaussian  # noqa: E402
+from jax import random  # noqa: E402  (the stand-in)
+
+
+def gk_problem():
+    truth = np.array([1.5, 1.0, 1.0, 0.5])
+    z = ndtri(np.random.default_rng(0).random(8))
+    e = np.exp(-truth[2] * z)
+    data = np.sort(truth[0] + truth[1] * (1 + 0.8 * (1 - e) / (1 + e)) * z * (1 + z * z) ** truth[3])
+
+    class GK(GKTransformedUniformPrior):
+        n_unsummarised_data = 8
+        prior_maxs = 2.0
+
+        def summarise_data(self, d):
+            return np.sort(d)
+    sc = GK()
+    sc.data = data
+    return sc, data
+
+
+def lg_problem(T=22):
+    F, Q, R, P0 = 0.9, 0.5, 0.8, 1.0
+    sc = TimeHomogenousLinearGaussian(initial_mean=np.zeros(1), initial_covariance=np.array([[P0]]),
+                                      transition_matrix=np.array([[F]]), transition_covariance=np.array([[Q]]),
+                                      likelihood_matrix=np.array([[1.0]]), likelihood_covariance=np.array([[R]]))
+    rng = np.random.default_rng(4)
+    x = np.zeros(T)
+    x[0] = rng.normal() * np.sqrt(P0)
+    for k in range(1, T):
+        x[k] = F * x[k - 1] + rng.normal() * np.sqrt(Q)
+    y = (x + rng.normal(size=T) * np.sqrt(R))[:, None]
+    mu, P, mus, Ps, mup, Pp = 0.0, P0, [], [], [], []
+    for k in range(T):
+        if k > 0:
+            mu, P = F * mu, F * P * F + Q
+        mup.append(mu); Pp.append(P)
+        K = P / (P + R)
+        mu, P = mu + K * (y[k, 0] - mu), (1 - K) * P
+        mus.append(mu); Ps.append(P)
+    sm, Pk = mus[:], Ps[:]
+    for k in range(T - 2, -1, -1):
+        G = Ps[k] * F / Pp[k + 1]
+        sm[k] = mus[k] + G * (sm[k + 1] - mup[k + 1])
+        Pk[k] = Ps[k] + G * (Pk[k + 1] - Pp[k + 1]) * G
+    return sc, y, np.arange(float(T)), np.array(sm), np.array(Pk)
+
+
+def build():
+    g = {}
+    # ---- tempered EKI (transport/teki.py) on the g-and-k simulator, prior U(0, 2)^4, 8 sorted draws
+    sc, data = gk_problem()
+    g["teki_data"] = data
+    for name, smp, n in (("adaptive", mocat.AdaptiveTemperedEKI(ess_threshold=0.9), 1000),
+                         ("schedule", mocat.TemperedEKI(temperature_schedule=np.linspace(0.0, 1.0, 11)), 1000)):
+        out = mocat.run(sc, smp, n, random.PRNGKey(1))
+        post = np.asarray(sc.constrain(out.value[-1]))
+        g[f"teki_{name}_temperature"] = np.asarray(out.temperature, np.float64)
+        g[f"teki_{name}_mean"], g[f"teki_{name}_std"] = post.mean(0), post.std(0)
+        g[f"teki_{name}_n"] = np.int64(n)
+    # ---- fixed-lag smoothers (ssm/online_smoothing.py) and FFBSi (ssm/backward.py) on the 1-d linear-Gaussian model
+    lg, y, t, sm, Pk = lg_problem()
+    g["lg_y"], g["lg_rts_mean"], g["lg_rts_var"] = y, sm, Pk
+    n, lag = 300, 6
+    pf = mocat.ssm.BootstrapFilter()
+    for name, bs in (("pf", False), ("bs", True)):
+        p = mocat.ssm.initiate_particles(lg, pf, n, random.PRNGKey(9), y[0], t[0])
+        for k in range(1, len(t)):
+            p = mocat.ssm.propagate_particle_smoother(lg, pf, p, y[k], t[k], random.PRNGKey(900 + k), lag, backward_sim=bs)
+        v = np.asarray(p.value)[:, :, 0]
+        g[f"smoother_{name}_mean"] = v.mean(1)
+        g[f"smoother_{name}_var"] = v.var(1)
+        g[f"smoother_{name}_unique_fraction"] = np.array([len(np.unique(r)) / n for r in v])
+    g["smoother_n"], g["smoother_lag"] = np.int64(n), np.int64(lag)
+    # forward_filtering_backward_simulation (backward.py:303-350) = the two calls below plus timing
+    filt = mocat.ssm.run_particle_filter_for_marginals(lg, pf, y, t, random.PRNGKey(5), n=n)
+    out = mocat.ssm.backward_simulation(lg, filt, random.PRNGKey(6), n)
+    v = np.asarray(out.value)[:, :, 0]
+    g["ffbsi_mean"], g["ffbsi_var"] = v.mean(1), v.var(1)
+    g["ffbsi_unique_fraction"] = np.array([len(np.unique(r)) / n for r in v])
+    return g
+
+
+if __name__ == "__main__":
+    g = build()
+    np.savez_compressed(os.path.join(HERE, "reference_runs_v1.npz"), **g)
+    for k, v in g.items():
+        print(k, np.round(np.asarray(v, np.float64), 3) if np.size(v) <= 22 else np.shape(v))

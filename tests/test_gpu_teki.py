@@ -81,9 +81,20 @@ def test_teki_run_api(mocat):
     npt.assert_allclose(post.std(0), post_ref.std(0), atol=0.05)
     assert abs(len(t) - len(ref['temperature_schedule'])) <= 1
     assert abs(post.mean(0)[0] - truth[0]) < abs(1.0 - truth[0])          # A moved from the prior mean towards the truth
+    # the REFERENCE'S OWN run of the same problem (its source under the NumPy stand-in for jax, n = 1000,
+    # tests/golden/make_reference_runs.py): temperature ladder and posterior moments, Monte-Carlo tolerances
+    import os
+    RR = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_runs_v1.npz"))
+    npt.assert_allclose(data, RR["teki_data"], rtol=1e-12)
+    assert abs(len(t) - len(RR["teki_adaptive_temperature"])) <= 3
+    assert abs(t[1] - RR["teki_adaptive_temperature"][1]) < 0.05
+    npt.assert_allclose(post.mean(0), RR["teki_adaptive_mean"], atol=0.08)
+    npt.assert_allclose(post.std(0), RR["teki_adaptive_std"], atol=0.06)
     fixed = mocat.run(sc, mocat.TemperedEKI(temperature_schedule=np.linspace(0, 1, 11)), 2000, random_key=2)
     npt.assert_allclose(fixed.temperature, np.linspace(0, 1, 11), atol=1e-12)
     npt.assert_allclose(sc.constrain(fixed.value[-1]).mean(0), post_ref.mean(0), atol=0.08)
+    npt.assert_allclose(sc.constrain(fixed.value[-1]).mean(0), RR["teki_schedule_mean"], atol=0.1)
+    npt.assert_allclose(sc.constrain(fixed.value[-1]).std(0), RR["teki_schedule_std"], atol=0.08)
     stop = mocat.run(sc, mocat.TemperedEKI(temperature_schedule=np.linspace(0, 1, 11), term_std=10.0), 500, random_key=3)
     assert len(stop.temperature) == 1 and stop.value.shape[0] == 1
     with pytest.raises(mocat.MocatB200Error):

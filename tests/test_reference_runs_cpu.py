@@ -1,0 +1,54 @@
+"""End-to-end runs of the REFERENCE's samplers (tests/golden/reference_runs_v1.npz, produced by
+tests/golden/make_reference_runs.py: the reference's own source under a NumPy stand-in for jax) against the oracle and
+against exact answers.  Statistical comparisons only -- the stand-in's random streams are neither jax's nor ours."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import models, teki as oteki
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def R():
+    return np.load(os.path.join(HERE, "golden", "reference_runs_v1.npz"))
+
+
+def test_teki_oracle_matches_the_reference_run(R):
+    """transport/teki.py end to end on the g-and-k simulator (prior U(0, 2)^4, 8 sorted draws): temperature ladder and
+    posterior moments of the constrained parameters, reference run (n = 1000) vs oracle run (n = 2000)"""
+    sc = models.GKTransformed(R["teki_data"], prior_max=2.0)
+    ad = oteki.TemperedEKI(sc, 2000, 1, adaptive=True, ess_threshold=0.9).run()
+    t_ref, t_or = R["teki_adaptive_temperature"], ad["temperature_schedule"]
+    assert t_ref[0] == 0.0 and t_ref[-1] == 1.0 and np.all(np.diff(t_ref) > 0)
+    assert abs(len(t_ref) - len(t_or)) <= 3
+    assert abs(t_ref[1] - t_or[1]) < 0.06                               # first adaptive temperature (ESS = 0.9 n)
+    post = sc.constrain(ad["x"])
+    np.testing.assert_allclose(post.mean(0), R["teki_adaptive_mean"], atol=0.08)
+    np.testing.assert_allclose(post.std(0), R["teki_adaptive_std"], atol=0.06)
+    fx = oteki.TemperedEKI(sc, 2000, 2, temperature_schedule=np.linspace(0.0, 1.0, 11)).run()
+    np.testing.assert_allclose(R["teki_schedule_temperature"], np.linspace(0.0, 1.0, 11), atol=1e-12)
+    np.testing.assert_allclose(fx["temperature_schedule"], R["teki_schedule_temperature"], atol=1e-12)
+    post = sc.constrain(fx["x"])
+    np.testing.assert_allclose(post.mean(0), R["teki_schedule_mean"], atol=0.08)
+    np.testing.assert_allclose(post.std(0), R["teki_schedule_std"], atol=0.06)
+
+
+def test_reference_smoothers_against_the_rts_smoother(R):
+    """ssm/online_smoothing.py and ssm/backward.py as the reference runs them (n = 300, lag 6): FFBSi is exact to
+    Monte-Carlo error; both fixed-lag branches re-sample the lag window at every step, so only a fraction of distinct
+    values survives at interior times -- the path degeneracy the device tests (tests/test_gpu_backward.py) account for"""
+    sm, var = R["lg_rts_mean"], R["lg_rts_var"]
+    n = int(R["smoother_n"])
+    se = np.sqrt(var.max() / n)
+    assert np.max(np.abs(R["ffbsi_mean"] - sm)) < 5 * se
+    assert np.median(R["ffbsi_unique_fraction"][:-1]) > 0.2
+    for name, frac_hi in (("pf", 0.2), ("bs", 0.45)):
+        err = np.abs(R[f"smoother_{name}_mean"] - sm)
+        uf = R[f"smoother_{name}_unique_fraction"]
+        assert err.max() < 0.8 and np.median(err) < 0.25, (name, err.max())
+        assert np.median(uf[2:-7]) < frac_hi, (name, uf)                # interior times: degenerate
+        assert uf[-1] > np.median(uf[2:-7])                             # the newest slice has been re-sampled once, not `lag` times
+        assert abs(R[f"smoother_{name}_var"][-1] - var[-1]) < 0.5 * var[-1]
