@@ -7,7 +7,8 @@ reference ships no test.  The random streams are NumPy's, not jax's threefry, so
 tests compare summary statistics (temperature ladders, posterior moments, smoothing errors, path degeneracy) within
 Monte-Carlo tolerances, never samples.  vmap is a Python loop here, hence the small ensembles (about 5 minutes in total).
 
-Run from the repo root, in the build container:  python tests/golden/make_reference_runs.py
+Run from the repo root, in the build container:  python tests/golden/make_reference_runs.py        (-> reference_runs_v1.npz)
+                                                  python tests/golden/make_reference_runs.py pf     (-> reference_runs_pf_v1.npz)
 """
 import os
 import sys
@@ -105,7 +106,38 @@ def build():
     return g
 
 
+def build_pf():
+    """the bootstrap particle filter of config C3 in small (ssm/filtering.py:255-324 on ssm/scenarios/lorenz96.py): d = 8,
+    R = 4 I (an ensemble of 1000 keeps an ESS of 10-250), trajectory started from the prior; the transition is the
+    reference's adaptive Dormand-Prince flow, resampling its multinomial `random.categorical` at ess < 0.5 n"""
+    from mocat.src.ssm.scenarios.lorenz96 import Lorenz96
+    d, T, n = 8, 10, 1000
+    sc = Lorenz96(dim=d, likelihood_covariance=4.0 * np.eye(d))
+    rng = np.random.default_rng(3)
+    xs = np.empty((T, d))
+    xs[0] = rng.standard_normal(d)
+    for k in range(1, T):
+        xs[k] = np.asarray(sc.transition_function(xs[k - 1], 0.0, 0.05)) + rng.standard_normal(d)
+    ys = xs + 2.0 * rng.standard_normal((T, d))
+    t = np.arange(T) * 0.05
+    out = mocat.ssm.run_particle_filter_for_marginals(sc, mocat.ssm.BootstrapFilter(), ys, t, random.PRNGKey(2), n=n,
+                                                      ess_threshold=0.5)
+    lw = np.asarray(out.log_weight)
+    w = np.exp(lw - lw.max(1, keepdims=True))
+    w /= w.sum(1, keepdims=True)
+    v = np.asarray(out.value)
+    mean = np.einsum('tn,tnd->td', w, v)
+    var = np.einsum('tn,tnd->td', w, (v - mean[:, None, :]) ** 2)
+    return {"pf_x": xs, "pf_y": ys, "pf_t": t, "pf_n": np.int64(n), "pf_ess": np.asarray(out.ess, np.float64),
+            "pf_mean": mean, "pf_var": var}
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "pf":
+        g = build_pf()
+        np.savez_compressed(os.path.join(HERE, "reference_runs_pf_v1.npz"), **g)
+        print(np.round(g["pf_ess"], 1), np.sqrt(np.mean((g["pf_mean"] - g["pf_x"]) ** 2, axis=1)))
+        sys.exit(0)
     g = build()
     np.savez_compressed(os.path.join(HERE, "reference_runs_v1.npz"), **g)
     for k, v in g.items():

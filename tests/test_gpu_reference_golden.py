@@ -75,3 +75,21 @@ def test_reference_rastrigin_potential(mocat):                            # scen
     sc = mocat.scenarios.Rastrigin(dim=5, a=1.3, prior_std=3.0)
     got = np.asarray(sc.likelihood_potential(R["ras_x"].astype(np.float32)))
     npt.assert_allclose(got, R["ras_likelihood_potential"], rtol=2e-5, atol=2e-4)
+
+
+def test_reference_run_lorenz96_particle_filter(mocat):
+    """the reference's OWN bootstrap-filter run on Lorenz-96 d = 8 (tests/golden/reference_runs_pf_v1.npz: its adaptive
+    flow, multinomial resampling, n = 1000) against the device filter (one RK4 step per interval, n = 20000) on the same
+    observations: filter means within the reference run's Monte-Carlo error, ESS fractions step by step"""
+    P = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_runs_pf_v1.npz"))
+    sc = mocat.ssm.Lorenz96(dim=8, likelihood_std=2.0)
+    n = 20000
+    out = mocat.ssm.run_particle_filter_for_marginals(sc, mocat.ssm.BootstrapFilter(), P["pf_y"].astype(np.float32), P["pf_t"],
+                                                      3, n=n, ess_threshold=0.5, resampling='multinomial')
+    d = out.mean - P["pf_mean"]
+    assert np.sqrt(np.mean(d ** 2)) < 0.35 and np.abs(d).max() < 1.0, (np.sqrt(np.mean(d ** 2)), np.abs(d).max())
+    ratio = (out.ess / n) / (P["pf_ess"] / float(P["pf_n"]))
+    assert np.all(ratio > 0.4) and np.all(ratio < 2.5), ratio
+    err_d = np.sqrt(np.mean((out.mean - P["pf_x"]) ** 2, axis=1))
+    err_r = np.sqrt(np.mean((P["pf_mean"] - P["pf_x"]) ** 2, axis=1))
+    assert np.max(np.abs(err_d - err_r)) < 0.2

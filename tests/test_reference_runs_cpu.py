@@ -52,3 +52,23 @@ def test_reference_smoothers_against_the_rts_smoother(R):
         assert np.median(uf[2:-7]) < frac_hi, (name, uf)                # interior times: degenerate
         assert uf[-1] > np.median(uf[2:-7])                             # the newest slice has been re-sampled once, not `lag` times
         assert abs(R[f"smoother_{name}_var"][-1] - var[-1]) < 0.5 * var[-1]
+
+
+def test_lorenz96_particle_filter_oracle_matches_the_reference_run():
+    """config C3 in small (tests/golden/reference_runs_pf_v1.npz): the reference's bootstrap filter on Lorenz-96 d = 8
+    (its adaptive Dormand-Prince flow, multinomial resampling, n = 1000) against the oracle (one RK4 step per interval, the
+    device convention, n = 20000) on the same observations: filter means within the reference run's Monte-Carlo error,
+    the ESS fractions step by step, and the same error against the simulated truth"""
+    from oracle import pf as opf
+    P = np.load(os.path.join(HERE, "golden", "reference_runs_pf_v1.npz"))
+    s = models.Lorenz96SSM(dim=8, r_std=2.0)
+    n = 20000
+    out = opf.BootstrapPF(s, n, 1, ess_threshold=0.5, resampling='multinomial').run(P["pf_y"])
+    means = np.array([opf.weighted_moments(o['x'], o['lw'])[0] for o in out])
+    d = means - P["pf_mean"]
+    assert np.sqrt(np.mean(d ** 2)) < 0.35 and np.abs(d).max() < 1.0
+    ratio = (np.array([o['ess'] for o in out]) / n) / (P["pf_ess"] / float(P["pf_n"]))
+    assert np.all(ratio > 0.4) and np.all(ratio < 2.5), ratio
+    err_o = np.sqrt(np.mean((means - P["pf_x"]) ** 2, axis=1))
+    err_r = np.sqrt(np.mean((P["pf_mean"] - P["pf_x"]) ** 2, axis=1))
+    assert np.max(np.abs(err_o - err_r)) < 0.2
