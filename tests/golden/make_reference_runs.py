@@ -128,8 +128,21 @@ def build_pf():
     v = np.asarray(out.value)
     mean = np.einsum('tn,tnd->td', w, v)
     var = np.einsum('tn,tnd->td', w, (v - mean[:, None, :]) ** 2)
-    return {"pf_x": xs, "pf_y": ys, "pf_t": t, "pf_n": np.int64(n), "pf_ess": np.asarray(out.ess, np.float64),
-            "pf_mean": mean, "pf_var": var}
+    g = {"pf_x": xs, "pf_y": ys, "pf_t": t, "pf_n": np.int64(n), "pf_ess": np.asarray(out.ess, np.float64),
+         "pf_mean": mean, "pf_var": var}
+    # the same observations through the optimal-proposal filter and the ensemble Kalman filter
+    # (ssm/nonlinear_gaussian.py:134-350) -- the reference ships no test for either
+    from mocat.src.ssm.nonlinear_gaussian import OptimalNonLinearGaussianParticleFilter, EnsembleKalmanFilter
+    for name, filt, m in (("opt", OptimalNonLinearGaussianParticleFilter(), 1000), ("enkf", EnsembleKalmanFilter(), 500)):
+        o = mocat.ssm.run_particle_filter_for_marginals(sc, filt, ys, t, random.PRNGKey(4), n=m, ess_threshold=0.5)
+        lw = np.asarray(o.log_weight)
+        w = np.exp(lw - lw.max(1, keepdims=True))
+        w /= w.sum(1, keepdims=True)
+        v = np.asarray(o.value)
+        mu = np.einsum('tn,tnd->td', w, v)
+        g[f"{name}_n"], g[f"{name}_ess"] = np.int64(m), np.asarray(o.ess, np.float64)
+        g[f"{name}_mean"], g[f"{name}_var"] = mu, np.einsum('tn,tnd->td', w, (v - mu[:, None, :]) ** 2)
+    return g
 
 
 if __name__ == "__main__":

@@ -93,3 +93,20 @@ def test_reference_run_lorenz96_particle_filter(mocat):
     err_d = np.sqrt(np.mean((out.mean - P["pf_x"]) ** 2, axis=1))
     err_r = np.sqrt(np.mean((P["pf_mean"] - P["pf_x"]) ** 2, axis=1))
     assert np.max(np.abs(err_d - err_r)) < 0.2
+
+
+@pytest.mark.parametrize("name,n", [("opt", 20000), ("enkf", 4000)])
+def test_reference_runs_optimal_proposal_and_enkf(mocat, name, n):
+    """the reference's OWN optimal-proposal and ensemble-Kalman filter runs (ssm/nonlinear_gaussian.py:134-350; no test
+    upstream) against the device filters on the same observations: filter means, spreads, ESS fractions"""
+    P = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_runs_pf_v1.npz"))
+    sc = mocat.ssm.Lorenz96(dim=8, likelihood_std=2.0)
+    filt = mocat.ssm.OptimalNonLinearGaussianParticleFilter() if name == "opt" else mocat.ssm.EnsembleKalmanFilter()
+    out = mocat.ssm.run_particle_filter_for_marginals(sc, filt, P["pf_y"].astype(np.float32), P["pf_t"], 5, n=n,
+                                                      ess_threshold=0.5, resampling='multinomial')
+    d = out.mean - P[name + "_mean"]
+    assert np.sqrt(np.mean(d ** 2)) < 0.25 and np.abs(d).max() < 0.7, (np.sqrt(np.mean(d ** 2)), np.abs(d).max())
+    vr = out.var.mean(1) / P[name + "_var"].mean(1)
+    assert np.all(vr > 0.8) and np.all(vr < 1.25), vr
+    ratio = (out.ess / n) / (P[name + "_ess"] / float(P[name + "_n"]))
+    assert np.all(ratio > 0.35) and np.all(ratio < 2.5), ratio

@@ -72,3 +72,23 @@ def test_lorenz96_particle_filter_oracle_matches_the_reference_run():
     err_o = np.sqrt(np.mean((means - P["pf_x"]) ** 2, axis=1))
     err_r = np.sqrt(np.mean((P["pf_mean"] - P["pf_x"]) ** 2, axis=1))
     assert np.max(np.abs(err_o - err_r)) < 0.2
+
+
+@pytest.mark.parametrize("name,n", [("opt", 20000), ("enkf", 4000)])
+def test_optimal_proposal_and_enkf_oracles_match_the_reference_runs(name, n):
+    """ssm/nonlinear_gaussian.py:134-350 (no test upstream): the reference's optimal-proposal filter (n = 1000) and
+    ensemble Kalman filter (n = 500) on the observations of the run above against oracle.pf.OptimalPF / EnKF: filter means,
+    spreads and -- for the weighted filter -- the ESS fractions step by step"""
+    from oracle import pf as opf
+    P = np.load(os.path.join(HERE, "golden", "reference_runs_pf_v1.npz"))
+    s = models.Lorenz96SSM(dim=8, r_std=2.0)
+    cls = opf.OptimalPF if name == "opt" else opf.EnKF
+    out = cls(s, n, 1, ess_threshold=0.5, resampling='multinomial').run(P["pf_y"])
+    mom = [opf.weighted_moments(o['x'], o['lw']) for o in out]
+    means, var = np.array([m[0] for m in mom]), np.array([m[1] for m in mom])
+    d = means - P[name + "_mean"]
+    assert np.sqrt(np.mean(d ** 2)) < 0.25 and np.abs(d).max() < 0.7
+    vr = var.mean(1) / P[name + "_var"].mean(1)
+    assert np.all(vr > 0.8) and np.all(vr < 1.25), vr
+    ratio = (np.array([o['ess'] for o in out]) / n) / (P[name + "_ess"] / float(P[name + "_n"]))
+    assert np.all(ratio > 0.35) and np.all(ratio < 2.5), ratio
