@@ -29,7 +29,10 @@ def _stack(outs):
         n = len(flat[0][0])
         return type(first).tree_unflatten(aux, [_stack([f[0][k] for f in flat]) for k in range(n)])
     from .numpy import ShimArray
-    return np.stack([np.asarray(o) for o in outs]).view(ShimArray)
+    out = np.stack([np.asarray(o) for o in outs])
+    if out.dtype.kind in 'iu' and out.dtype != np.uint32:           # jax's default integer type
+        out = out.astype(np.int32)
+    return out.view(ShimArray)
 
 
 def _axis_size(arg, ax):

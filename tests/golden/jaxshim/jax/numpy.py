@@ -42,6 +42,15 @@ class ShimArray(_np.ndarray):
     def at(self):
         return _At(self)
 
+    # jax arrays stay arrays under indexing and arithmetic (no NumPy scalars): the reference tests `isinstance(x,
+    # jnp.ndarray) and x.dtype == 'int32'` on values that went through vmap / scan
+    def __getitem__(self, idx):
+        out = super().__getitem__(idx)
+        return out if isinstance(out, _np.ndarray) else _np.asarray(out).view(ShimArray)
+
+    def __array_wrap__(self, obj, context=None, return_scalar=False):
+        return _np.asarray(obj).view(ShimArray)
+
     def block_until_ready(self):
         return self
 

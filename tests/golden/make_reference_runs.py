@@ -9,6 +9,7 @@ Monte-Carlo tolerances, never samples.  vmap is a Python loop here, hence the sm
 
 Run from the repo root, in the build container:  python tests/golden/make_reference_runs.py        (-> reference_runs_v1.npz)
                                                   python tests/golden/make_reference_runs.py pf     (-> reference_runs_pf_v1.npz)
+                                                  python tests/golden/make_reference_runs.py smc    (-> reference_runs_smc_v1.npz)
 """
 import os
 import sys
@@ -145,7 +146,37 @@ def build_pf():
     return g
 
 
+def build_smc():
+    """config C2 in small: MetropolisedSMCSampler with a random-walk move (transport/smc.py:228-373) on the Rastrigin
+    target (scenarios/toy_examples.py:135-149, a = 1, d = 2) under an N(0, 3^2 I) prior, adaptive tempering
+    (ESS retain 0.9, resample below 0.5 n), n = 1000"""
+    from mocat.src.scenarios import toy_examples
+    import jax.numpy as jnp
+
+    class Ras(toy_examples.Rastrigin):
+        def prior_potential(self, x, random_key=None):
+            return 0.5 * jnp.sum(jnp.square(x)) / 9.0
+
+        def prior_sample(self, random_key):
+            return 3.0 * random.normal(random_key, (self.dim,))
+    sc = Ras(dim=2, a=1.0)
+    out = mocat.run(sc, mocat.MetropolisedSMCSampler(mocat.RandomWalk(stepsize=0.5)), 1000, random.PRNGKey(0))
+    v = np.asarray(out.value[-1])
+    lw = np.asarray(out.log_weight[-1])
+    w = np.exp(lw - lw.max()); w /= w.sum()
+    return {"smc_n": np.int64(1000), "smc_temperature": np.asarray(out.temperature, np.float64),
+            "smc_log_norm_constant": np.asarray(out.log_norm_constant, np.float64), "smc_ess": np.asarray(out.ess, np.float64),
+            "smc_final_mean": w @ v, "smc_final_second_moment": w @ (v * v),
+            "smc_alpha_mean": np.asarray(out.alpha, np.float64).mean(axis=-1)}
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "smc":
+        g = build_smc()
+        np.savez_compressed(os.path.join(HERE, "reference_runs_smc_v1.npz"), **g)
+        for k, v in g.items():
+            print(k, np.round(v, 4))
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "pf":
         g = build_pf()
         np.savez_compressed(os.path.join(HERE, "reference_runs_pf_v1.npz"), **g)

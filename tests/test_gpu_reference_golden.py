@@ -110,3 +110,21 @@ def test_reference_runs_optimal_proposal_and_enkf(mocat, name, n):
     assert np.all(vr > 0.8) and np.all(vr < 1.25), vr
     ratio = (out.ess / n) / (P[name + "_ess"] / float(P[name + "_n"]))
     assert np.all(ratio > 0.35) and np.all(ratio < 2.5), ratio
+
+
+def test_reference_run_tempered_smc(mocat):
+    """config C2 in small: the reference's OWN run of MetropolisedSMCSampler + RandomWalk on Rastrigin d = 2 (n = 1000,
+    tests/golden/reference_runs_smc_v1.npz) against the device sampler (n = 20000): the adaptive temperature ladder entry
+    by entry, the ESS pattern with its resampling points, the log normalising constant"""
+    S = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_runs_smc_v1.npz"))
+    n = 20000
+    sc = mocat.scenarios.Rastrigin(dim=2, a=1.0, prior_std=3.0)
+    out = mocat.run(sc, mocat.MetropolisedSMCSampler(mocat.RandomWalk(stepsize=0.5), resampling='multinomial'), n, random_key=0)
+    beta = np.asarray(out.temperature, np.float64)
+    assert len(beta) == len(S["smc_temperature"])
+    npt.assert_allclose(beta[:8], S["smc_temperature"][:8], rtol=0.04)
+    npt.assert_allclose(beta[8:], S["smc_temperature"][8:], rtol=0.12)      # the reference run's Monte-Carlo state (n = 1000)
+    ess_d, ess_r = np.asarray(out.ess) / n, S["smc_ess"] / float(S["smc_n"])
+    npt.assert_allclose(ess_d[:-1], ess_r[:-1], atol=1e-3)
+    assert abs(ess_d[-1] - ess_r[-1]) < 0.08
+    npt.assert_allclose(out.log_norm_constant, S["smc_log_norm_constant"], atol=0.15)

@@ -92,3 +92,26 @@ def test_optimal_proposal_and_enkf_oracles_match_the_reference_runs(name, n):
     assert np.all(vr > 0.8) and np.all(vr < 1.25), vr
     ratio = (np.array([o['ess'] for o in out]) / n) / (P[name + "_ess"] / float(P[name + "_n"]))
     assert np.all(ratio > 0.35) and np.all(ratio < 2.5), ratio
+
+
+def test_tempered_smc_oracle_matches_the_reference_run():
+    """config C2 in small (tests/golden/reference_runs_smc_v1.npz): the reference's MetropolisedSMCSampler with a
+    random-walk move on Rastrigin d = 2 (n = 1000) against oracle.smc.TemperedSMC (n = 20000): the adaptive temperature
+    ladder entry by entry, the ESS pattern including the resampling points, the log normalising constant and the mean
+    acceptance probabilities"""
+    from oracle import smc as osmc
+    S = np.load(os.path.join(HERE, "golden", "reference_runs_smc_v1.npz"))
+    n = 20000
+    chain = osmc.TemperedSMC(models.IsoGaussianPrior(2, 0.0, 3.0), models.Rastrigin(2, 1.0), n=n, seed=0, move='rw',
+                             stepsize=0.5, resampling='multinomial').run()
+    beta = np.array([c['beta'] for c in chain])
+    assert len(beta) == len(S["smc_temperature"])
+    np.testing.assert_allclose(beta[:8], S["smc_temperature"][:8], rtol=0.04)
+    # later entries carry the Monte-Carlo state of the n = 1000 reference run (the oracle at n = 1000 spreads over
+    # 0.76-0.82 at entry 13 across seeds; the reference run has 0.823)
+    np.testing.assert_allclose(beta[8:], S["smc_temperature"][8:], rtol=0.12)
+    ess_o, ess_r = np.array([c['ess'] for c in chain]) / n, S["smc_ess"] / float(S["smc_n"])
+    np.testing.assert_allclose(ess_o[:-1], ess_r[:-1], atol=2e-4)       # pinned by the search: 0.9^k, reset when below 0.5
+    assert abs(ess_o[-1] - ess_r[-1]) < 0.08                            # the last step stops at temperature 1
+    np.testing.assert_allclose([c['log_norm_constant'] for c in chain], S["smc_log_norm_constant"], atol=0.15)
+    np.testing.assert_allclose([float(np.mean(c['alpha'])) for c in chain][1:-1], S["smc_alpha_mean"][1:-1], atol=0.06)
