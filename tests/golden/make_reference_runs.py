@@ -10,6 +10,7 @@ Monte-Carlo tolerances, never samples.  vmap is a Python loop here, hence the sm
 Run from the repo root, in the build container:  python tests/golden/make_reference_runs.py        (-> reference_runs_v1.npz)
                                                   python tests/golden/make_reference_runs.py pf     (-> reference_runs_pf_v1.npz)
                                                   python tests/golden/make_reference_runs.py smc    (-> reference_runs_smc_v1.npz)
+                                                  python tests/golden/make_reference_runs.py svgd   (-> reference_runs_svgd_v1.npz)
 """
 import os
 import sys
@@ -170,7 +171,32 @@ def build_smc():
             "smc_alpha_mean": np.asarray(out.alpha, np.float64).mean(axis=-1)}
 
 
+def build_svgd():
+    """transport/svgd.py:35-146 end to end: SVGD is deterministic once the ensemble is given, so this run is an EXACT
+    reference (up to the finite-difference gradients of the stand-in, 1e-8): 15 iterations, adagrad(0.1, momentum 0.9),
+    mean-distance bandwidth re-adapted every iteration (the default), full-covariance Gaussian likelihood
+    (scenarios/toy_examples.py:17-51) under an N(0, 2^2 I) prior, 100 particles"""
+    from mocat.src.scenarios import toy_examples
+    import jax.numpy as jnp
+
+    class G(toy_examples.Gaussian):
+        def prior_potential(self, x, random_key=None):
+            return 0.5 * jnp.sum(jnp.square(x)) / 4.0
+    mean, cov = np.array([1.0, -0.5]), np.array([[1.0, 0.6], [0.6, 2.0]])
+    sc = G(mean=mean, covariance=cov)
+    X0 = np.random.default_rng(0).standard_normal((100, 2)) * 2.0
+    out = mocat.run(sc, mocat.SVGD(stepsize=0.1, max_iter=15), 100, random.PRNGKey(0), initial_state=mocat.cdict(value=X0))
+    return {"svgd_X0": X0, "svgd_mean": mean, "svgd_cov": cov, "svgd_value": np.asarray(out.value, np.float64),
+            "svgd_potential": np.asarray(out.potential, np.float64),
+            "svgd_bandwidth": np.asarray(out.kernel_params.bandwidth, np.float64)}
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "svgd":
+        g = build_svgd()
+        np.savez_compressed(os.path.join(HERE, "reference_runs_svgd_v1.npz"), **g)
+        print(g["svgd_value"].shape, np.round(g["svgd_bandwidth"], 4), g["svgd_value"][-1].mean(0))
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "smc":
         g = build_smc()
         np.savez_compressed(os.path.join(HERE, "reference_runs_smc_v1.npz"), **g)

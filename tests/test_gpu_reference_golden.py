@@ -128,3 +128,18 @@ def test_reference_run_tempered_smc(mocat):
     npt.assert_allclose(ess_d[:-1], ess_r[:-1], atol=1e-3)
     assert abs(ess_d[-1] - ess_r[-1]) < 0.08
     npt.assert_allclose(out.log_norm_constant, S["smc_log_norm_constant"], atol=0.15)
+
+
+def test_reference_run_svgd(mocat):
+    """transport/svgd.py end to end: the reference's OWN 15 SVGD iterations from a given ensemble (deterministic:
+    adagrad, mean bandwidth re-adapted every iteration, full-covariance Gaussian target) against the device run from the
+    same ensemble -- fp32 round-off accumulated over the iterations"""
+    V = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_runs_svgd_v1.npz"))
+    sc = mocat.scenarios.Gaussian(mean=V["svgd_mean"], covariance=V["svgd_cov"], prior_std=2.0)
+    out = mocat.run(sc, mocat.SVGD(stepsize=0.1, max_iter=15, keep_history=True), 100, random_key=0,
+                    initial_state=mocat.cdict(value=V["svgd_X0"].astype(np.float32)))
+    assert out.value.shape == V["svgd_value"].shape
+    npt.assert_allclose(out.value[0], V["svgd_value"][0], atol=1e-6)
+    npt.assert_allclose(out.value, V["svgd_value"], atol=2e-4)
+    assert out.bandwidth == pytest.approx(float(V["svgd_bandwidth"][-1]), rel=1e-4)
+    npt.assert_allclose(out.potential[-1], V["svgd_potential"][-1], rtol=1e-4, atol=1e-4)

@@ -115,3 +115,26 @@ def test_tempered_smc_oracle_matches_the_reference_run():
     assert abs(ess_o[-1] - ess_r[-1]) < 0.08                            # the last step stops at temperature 1
     np.testing.assert_allclose([c['log_norm_constant'] for c in chain], S["smc_log_norm_constant"], atol=0.15)
     np.testing.assert_allclose([float(np.mean(c['alpha'])) for c in chain][1:-1], S["smc_alpha_mean"][1:-1], atol=0.06)
+
+
+def test_svgd_oracle_reproduces_the_reference_run():
+    """transport/svgd.py end to end (tests/golden/reference_runs_svgd_v1.npz): SVGD is deterministic once the ensemble is
+    given, so the oracle must reproduce the reference's own 15 iterations (adagrad, mean bandwidth re-adapted every
+    iteration, full-covariance Gaussian likelihood + Gaussian prior) to the accuracy of the stand-in's finite-difference
+    gradients"""
+    from oracle import svgd as osvgd
+    V = np.load(os.path.join(HERE, "golden", "reference_runs_svgd_v1.npz"))
+    prior, lik = models.IsoGaussianPrior(2, 0.0, 2.0), models.GaussianTarget(V["svgd_mean"], V["svgd_cov"])
+
+    def pg(x):
+        up, gp = prior.potential_and_grad(x)
+        ul, gl = lik.potential_and_grad(x)
+        return up + ul, gp + gl
+    s = osvgd.SVGD(pg, V["svgd_X0"], 0.1, bandwidth='mean', max_iter=15)
+    hs, xs = [s.h], [s.x.copy()]
+    while s.iter < 15:
+        xs.append(s.update().copy())
+        hs.append(s.h)
+    np.testing.assert_allclose(hs, V["svgd_bandwidth"], rtol=1e-6)
+    np.testing.assert_allclose(np.array(xs), V["svgd_value"], atol=2e-6)
+    np.testing.assert_allclose(s.U, V["svgd_potential"][-1], rtol=1e-5, atol=1e-6)
