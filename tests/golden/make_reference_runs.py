@@ -11,6 +11,7 @@ Run from the repo root, in the build container:  python tests/golden/make_refere
                                                   python tests/golden/make_reference_runs.py pf     (-> reference_runs_pf_v1.npz)
                                                   python tests/golden/make_reference_runs.py smc    (-> reference_runs_smc_v1.npz)
                                                   python tests/golden/make_reference_runs.py svgd   (-> reference_runs_svgd_v1.npz)
+                                                  python tests/golden/make_reference_runs.py abc    (-> reference_runs_abc_v1.npz)
 """
 import os
 import sys
@@ -191,7 +192,34 @@ def build_svgd():
             "svgd_bandwidth": np.asarray(out.kernel_params.bandwidth, np.float64)}
 
 
+def build_abc():
+    """config C5 in small: MetropolisedABCSMCSampler with the default random-walk ABC move (abc/smc.py:100-245) on the
+    g-and-k model (prior U(0, 10)^4 through the probit transform, 8 sorted draws, data simulated at (3, 1, 2, 0.5)),
+    12 iterations, n = 1000: adaptive thresholds (quantile of the distances at 0.9 ESS / n), ESS, acceptance"""
+    truth = np.array([3.0, 1.0, 2.0, 0.5])
+
+    class GK(GKTransformedUniformPrior):
+        n_unsummarised_data = 8
+
+        def summarise_data(self, d):
+            return np.sort(d)
+    sc = GK()
+    z = ndtri(1e-5 + np.random.default_rng(1).random(8) * (1 - 2e-5))
+    e = np.exp(-truth[2] * z)
+    sc.data = np.sort(truth[0] + truth[1] * (1 + 0.8 * (1 - e) / (1 + e)) * z * (1 + z * z) ** truth[3])
+    out = mocat.run(sc, mocat.abc.MetropolisedABCSMCSampler(max_iter=12), 1000, random.PRNGKey(0))
+    return {"abc_data": np.asarray(sc.data), "abc_n": np.int64(1000), "abc_threshold": np.asarray(out.threshold, np.float64),
+            "abc_ess": np.asarray(out.ess, np.float64), "abc_alpha_mean": np.asarray(out.alpha, np.float64).mean(axis=-1),
+            "abc_alive_fraction": (np.asarray(out.log_weight) > -np.inf).mean(axis=-1)}
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "abc":
+        g = build_abc()
+        np.savez_compressed(os.path.join(HERE, "reference_runs_abc_v1.npz"), **g)
+        for k, v in g.items():
+            print(k, np.round(v, 3))
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "svgd":
         g = build_svgd()
         np.savez_compressed(os.path.join(HERE, "reference_runs_svgd_v1.npz"), **g)

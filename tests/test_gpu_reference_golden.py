@@ -143,3 +143,17 @@ def test_reference_run_svgd(mocat):
     npt.assert_allclose(out.value, V["svgd_value"], atol=2e-4)
     assert out.bandwidth == pytest.approx(float(V["svgd_bandwidth"][-1]), rel=1e-4)
     npt.assert_allclose(out.potential[-1], V["svgd_potential"][-1], rtol=1e-4, atol=1e-4)
+
+
+def test_reference_run_smc_abc(mocat):
+    """config C5 in small: the reference's OWN SMC-ABC run on the g-and-k model (n = 1000, 12 iterations) against the
+    device sampler (n = 20000): ESS pattern with its resampling point, thresholds on the log scale, mean acceptance"""
+    A = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_runs_abc_v1.npz"))
+    n = 20000
+    sc = mocat.abc.GKTransformedUniformPrior(data=A["abc_data"])
+    out = mocat.run(sc, mocat.abc.MetropolisedABCSMCSampler(max_iter=12, keep_history=True), n, random_key=0)
+    assert len(out.threshold) == len(A["abc_threshold"])
+    npt.assert_allclose(np.asarray(out.ess) / n, A["abc_ess"] / float(A["abc_n"]), atol=2e-3)
+    dlog = np.log(out.threshold) - np.log(A["abc_threshold"])
+    assert np.all(np.abs(dlog[:7]) < 0.7) and np.all(np.abs(dlog[7:]) < 0.3), dlog
+    npt.assert_allclose(out.alpha.mean(axis=-1)[1:], A["abc_alpha_mean"][1:], atol=0.05)

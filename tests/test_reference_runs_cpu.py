@@ -138,3 +138,19 @@ def test_svgd_oracle_reproduces_the_reference_run():
     np.testing.assert_allclose(hs, V["svgd_bandwidth"], rtol=1e-6)
     np.testing.assert_allclose(np.array(xs), V["svgd_value"], atol=2e-6)
     np.testing.assert_allclose(s.U, V["svgd_potential"][-1], rtol=1e-5, atol=1e-6)
+
+
+def test_smc_abc_oracle_matches_the_reference_run():
+    """config C5 in small (tests/golden/reference_runs_abc_v1.npz): the reference's MetropolisedABCSMCSampler on the
+    g-and-k model (n = 1000, 12 iterations) against oracle.abc.SMCABC (n = 20000): the ESS / alive-fraction pattern with its
+    resampling point exactly, the adaptive thresholds (quantiles of a heavy-tailed distance distribution: log scale) and
+    the mean acceptance probability of the random-walk ABC move"""
+    from oracle import abc as oabc
+    A = np.load(os.path.join(HERE, "golden", "reference_runs_abc_v1.npz"))
+    n = 20000
+    chain = oabc.SMCABC(models.GKTransformed(A["abc_data"]), n, 0, max_iter=12).run()
+    assert len(chain) == len(A["abc_threshold"])
+    np.testing.assert_allclose(np.array([c['ess'] for c in chain]) / n, A["abc_ess"] / float(A["abc_n"]), atol=2e-3)
+    dlog = np.log([c['threshold'] for c in chain]) - np.log(A["abc_threshold"])
+    assert np.all(np.abs(dlog[:7]) < 0.7) and np.all(np.abs(dlog[7:]) < 0.3), dlog
+    np.testing.assert_allclose([float(np.mean(c['alpha'])) for c in chain][1:], A["abc_alpha_mean"][1:], atol=0.05)
