@@ -12,6 +12,7 @@ Run from the repo root, in the build container:  python tests/golden/make_refere
                                                   python tests/golden/make_reference_runs.py smc    (-> reference_runs_smc_v1.npz)
                                                   python tests/golden/make_reference_runs.py svgd   (-> reference_runs_svgd_v1.npz)
                                                   python tests/golden/make_reference_runs.py abc    (-> reference_runs_abc_v1.npz)
+                                                  python tests/golden/make_reference_runs.py rm     (-> reference_runs_rm_v1.npz)
 """
 import os
 import sys
@@ -213,7 +214,35 @@ def build_abc():
             "abc_alive_fraction": (np.asarray(out.log_weight) > -np.inf).mean(axis=-1)}
 
 
+def build_rm():
+    """RMMetropolisedSMCSampler (transport/smc.py:376-428) with the MALA move Underdamped(stepsize = 0.3) (friction = inf,
+    one leapfrog step: mcmc/standard_mcmc.py:72-153) on the Rastrigin / Gaussian-prior target of build_smc, n = 500:
+    Robbins-Monro adaptation of the stepsize towards the 0.651 acceptance target (gradients of the potentials by the
+    stand-in's central differences)"""
+    from mocat.src.scenarios import toy_examples
+    import jax.numpy as jnp
+
+    class Ras(toy_examples.Rastrigin):
+        def prior_potential(self, x, random_key=None):
+            return 0.5 * jnp.sum(jnp.square(x)) / 9.0
+
+        def prior_sample(self, random_key):
+            return 3.0 * random.normal(random_key, (self.dim,))
+    out = mocat.run(Ras(dim=2, a=1.0), mocat.RMMetropolisedSMCSampler(mocat.Underdamped(stepsize=0.3), rm_stepsize=1.0), 500,
+                    random.PRNGKey(0))
+    return {"rm_n": np.int64(500), "rm_temperature": np.asarray(out.temperature, np.float64),
+            "rm_stepsize": np.asarray(out.stepsize, np.float64), "rm_ess": np.asarray(out.ess, np.float64),
+            "rm_log_norm_constant": np.asarray(out.log_norm_constant, np.float64),
+            "rm_alpha_mean": np.asarray(out.alpha, np.float64).mean(axis=-1)}
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "rm":
+        g = build_rm()
+        np.savez_compressed(os.path.join(HERE, "reference_runs_rm_v1.npz"), **g)
+        for k, v in g.items():
+            print(k, np.round(v, 4))
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "abc":
         g = build_abc()
         np.savez_compressed(os.path.join(HERE, "reference_runs_abc_v1.npz"), **g)

@@ -157,3 +157,18 @@ def test_reference_run_smc_abc(mocat):
     dlog = np.log(out.threshold) - np.log(A["abc_threshold"])
     assert np.all(np.abs(dlog[:7]) < 0.7) and np.all(np.abs(dlog[7:]) < 0.3), dlog
     npt.assert_allclose(out.alpha.mean(axis=-1)[1:], A["abc_alpha_mean"][1:], atol=0.05)
+
+
+def test_reference_run_rm_metropolised_smc(mocat):
+    """the reference's OWN run of RMMetropolisedSMCSampler + MALA (n = 500, tests/golden/reference_runs_rm_v1.npz) against
+    the device sampler (n = 20000, stepsize adapted on the device): stepsize trajectory, ladder, evidence"""
+    S = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_runs_rm_v1.npz"))
+    sc = mocat.scenarios.Rastrigin(dim=2, a=1.0, prior_std=3.0)
+    smp = mocat.RMMetropolisedSMCSampler(mocat.Underdamped(stepsize=0.3), rm_stepsize=1.0, resampling='multinomial')
+    out = mocat.run(sc, smp, 20000, random_key=0)
+    assert len(out.temperature) == len(S["rm_temperature"])
+    npt.assert_allclose(out.stepsize[:9], S["rm_stepsize"][:9], rtol=0.03)
+    npt.assert_allclose(out.stepsize[9:], S["rm_stepsize"][9:], rtol=0.12)
+    npt.assert_allclose(out.temperature[:6], S["rm_temperature"][:6], rtol=0.04)
+    npt.assert_allclose(out.temperature[6:], S["rm_temperature"][6:], rtol=0.1)
+    assert abs(out.log_norm_constant[-1] - S["rm_log_norm_constant"][-1]) < 0.35

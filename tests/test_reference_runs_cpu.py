@@ -154,3 +154,21 @@ def test_smc_abc_oracle_matches_the_reference_run():
     dlog = np.log([c['threshold'] for c in chain]) - np.log(A["abc_threshold"])
     assert np.all(np.abs(dlog[:7]) < 0.7) and np.all(np.abs(dlog[7:]) < 0.3), dlog
     np.testing.assert_allclose([float(np.mean(c['alpha'])) for c in chain][1:], A["abc_alpha_mean"][1:], atol=0.05)
+
+
+def test_rm_metropolised_smc_oracle_matches_the_reference_run():
+    """RMMetropolisedSMCSampler with the MALA move (tests/golden/reference_runs_rm_v1.npz, n = 500) against the oracle
+    (n = 20000): the Robbins-Monro stepsize trajectory -- rising from 0.3 to about 1.25 while almost every proposal is
+    accepted, then falling back as the target sharpens -- the temperature ladder and the evidence"""
+    from oracle import smc as osmc
+    S = np.load(os.path.join(HERE, "golden", "reference_runs_rm_v1.npz"))
+    chain = osmc.TemperedSMC(models.IsoGaussianPrior(2, 0.0, 3.0), models.Rastrigin(2, 1.0), n=20000, seed=0, move='mala',
+                             stepsize=0.3, resampling='multinomial', rm_stepsize=1.0, rm_target=0.651).run()
+    assert len(chain) == len(S["rm_temperature"])
+    step = np.array([0.3] + [c['stepsize'] for c in chain[1:]])
+    np.testing.assert_allclose(step[:9], S["rm_stepsize"][:9], rtol=0.03)
+    np.testing.assert_allclose(step[9:], S["rm_stepsize"][9:], rtol=0.12)
+    beta = np.array([c['beta'] for c in chain])
+    np.testing.assert_allclose(beta[:6], S["rm_temperature"][:6], rtol=0.04)
+    np.testing.assert_allclose(beta[6:], S["rm_temperature"][6:], rtol=0.1)
+    assert abs(chain[-1]['log_norm_constant'] - S["rm_log_norm_constant"][-1]) < 0.35
