@@ -177,6 +177,22 @@ def build():
     xv = rng.standard_normal((501, 4)) * np.array([0.5, 1.0, 2.0, 0.1])
     _, ex2 = ref_abc_smc.adapt_stepsize_scaled_diag_cov(cdict(value=xv), cdict(parameters=cdict()))
     g["abc_value"], g["abc_stepsize"] = xv, np.asarray(ex2.parameters.stepsize)
+    # ---- core.cdict (core.py:20-84): integer / array / slice indexing and `+`, with a nested cdict, a static_cdict,
+    #      a scalar `time` and a python scalar -- recorded field by field (the container itself does not travel)
+    from mocat.src.core import static_cdict
+    mk = lambda o: cdict(value=np.arange(15.0).reshape(5, 3) + o, potential=np.arange(5.0) * 2 + o, time=1.5 + o, label=3,  # noqa: E731
+                         inner=cdict(alpha=np.arange(5.0) / 10 + o), frozen=static_cdict(beta=np.arange(5.0) + o))
+    c1, c2 = mk(0.0), mk(100.0)
+    picks = {"int": 2, "arr": np.array([0, 3, 3]), "slice": slice(1, 4)}
+    for name, idx in picks.items():
+        r = c1[idx]
+        g[f"cdict_get_{name}_value"], g[f"cdict_get_{name}_potential"] = np.asarray(r.value), np.asarray(r.potential)
+        g[f"cdict_get_{name}_inner_alpha"], g[f"cdict_get_{name}_frozen_beta"] = np.asarray(r.inner.alpha), np.asarray(r.frozen.beta)
+        g[f"cdict_get_{name}_time"], g[f"cdict_get_{name}_label"] = np.float64(r.time), np.int64(r.label)
+    a = c1 + c2
+    g["cdict_add_value"], g["cdict_add_potential"] = np.asarray(a.value), np.asarray(a.potential)
+    g["cdict_add_inner_alpha"], g["cdict_add_frozen_beta"] = np.asarray(a.inner.alpha), np.asarray(a.frozen.beta)
+    g["cdict_add_time"], g["cdict_add_label"] = np.float64(a.time), np.int64(a.label)
     return g
 
 

@@ -119,3 +119,27 @@ def test_gk_simulator_and_abc_adaptation(R):                              # gk.p
 def test_rastrigin_likelihood_potential(R):                               # scenarios/toy_examples.py:135-149
     u, _ = models.Rastrigin(5, 1.3).potential_and_grad(R["ras_x"])
     npt.assert_allclose(u, R["ras_likelihood_potential"], rtol=1e-10)
+
+
+def test_host_cdict_behaves_like_the_reference_container(R):             # core.py:20-84, the PRODUCT's host container
+    """mocat_b200.core.cdict (NumPy-backed, written from the interface) against what the reference's own cdict returned
+    for the same operations: indexing by int / index array / slice and `+`, with a nested cdict (indexed / appended),
+    a static_cdict (left alone), the scalar `time` (added) and a plain python scalar (kept)"""
+    from mocat_b200.core import cdict, static_cdict
+    mk = lambda o: cdict(value=np.arange(15.0).reshape(5, 3) + o, potential=np.arange(5.0) * 2 + o, time=1.5 + o, label=3,  # noqa: E731
+                         inner=cdict(alpha=np.arange(5.0) / 10 + o), frozen=static_cdict(beta=np.arange(5.0) + o))
+    c1, c2 = mk(0.0), mk(100.0)
+    for name, idx in {"int": 2, "arr": np.array([0, 3, 3]), "slice": slice(1, 4)}.items():
+        r = c1[idx]
+        npt.assert_array_equal(r.value, R[f"cdict_get_{name}_value"])
+        npt.assert_array_equal(r.potential, R[f"cdict_get_{name}_potential"])
+        npt.assert_array_equal(r.inner.alpha, R[f"cdict_get_{name}_inner_alpha"])
+        npt.assert_array_equal(r.frozen.beta, R[f"cdict_get_{name}_frozen_beta"])
+        assert r.time == float(R[f"cdict_get_{name}_time"]) and r.label == int(R[f"cdict_get_{name}_label"])
+    a = c1 + c2
+    npt.assert_array_equal(a.value, R["cdict_add_value"])
+    npt.assert_array_equal(a.potential, R["cdict_add_potential"])
+    npt.assert_array_equal(a.inner.alpha, R["cdict_add_inner_alpha"])
+    npt.assert_array_equal(a.frozen.beta, R["cdict_add_frozen_beta"])
+    assert a.time == float(R["cdict_add_time"]) and a.label == int(R["cdict_add_label"])
+    assert (c1 + None).potential is c1.potential                          # core.py:61-62
