@@ -293,6 +293,15 @@ def c5_record(steps, peaks, ncu=None):
            "hbm_frac_of_60B_contract": 60.0 * n / (ms * 1e-3) / 1e9 / hbm, "iter": int(c['iter']),
            "note": "the propagate kernel is simulator (ALU/MUFU) bound: 8 x (ndtri + exp + pow) per particle"}
     k = (ncu or {}).get("abc_move_kernel")
+    try:
+        _c5_issue_roofline(rec, k, n, ms)
+    except Exception as exc:                                           # a reporting extra must never cost the record
+        rec["issue_roofline"] = {"error": repr(exc)}
+    return rec
+
+
+def _c5_issue_roofline(rec, k, n, ms):
+    import torch
     if k and k.get("thread_instructions_per_particle"):
         # the simulator-bound kernel against the instruction-issue ceiling (148 SMs x 4 schedulers x 32 lanes
         # per clock) instead of HBM; instruction count and pipe shares from the ncu capture of the same build
@@ -306,7 +315,7 @@ def c5_record(steps, peaks, ncu=None):
                                  "frac_of_issue_peak_whole_step": k["thread_instructions_per_particle"] * n / (ms * 1e-3) / peak,
                                  "xu_pipe_pct_ncu": k.get("xu_pipe_pct"), "issue_active_pct_ncu": k.get("issue_active_pct"),
                                  "kernel_share_of_step_ncu": share, "source": k.get("source")}
-    return rec
+    return None
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
