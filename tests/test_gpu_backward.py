@@ -208,7 +208,8 @@ def test_fixed_lag_smoother_matches_rts(E, backward_sim):
     est = p.value[:, :, 0].mean(axis=1)
     # Both branches re-sample the lag window at every step, so a few hundred distinct values survive at an interior time
     # (measured here: 527 of 3000 with backward simulation, 215 without; a NumPy restatement of the reference algorithm
-    # gives 250 / 110 of 1500) and the error of the trajectory means is that of a few hundred draws, with rare larger
+    # gives 250 / 110 of 1500, and the reference's OWN runs at n = 300 -- tests/golden/reference_runs_v1.npz, checked by
+    # tests/test_reference_runs_cpu.py -- keep 25-35 % / 8-15 % distinct values at interior times) and the error of the trajectory means is that of a few hundred draws, with rare larger
     # excursions: over seeds 0.04-0.24 (backward simulation) and 0.18-0.68 (particle-filter branch) on the device,
     # 0.11-0.14 and 0.09-0.33 in NumPy.  The run is deterministic (Philox), so the bounds below are regression bounds.
     err = np.abs(est - np.array(sm))
