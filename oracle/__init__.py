@@ -12,9 +12,13 @@ Who may import it: `tests/`, `__graft_entry__.smoke()` and the `cpu_baseline` /
 CPU baseline), never as part of the shipped product path.  `mocat_b200/` must never
 import `oracle`; a test enforces that.
 
-Parity status.  The reference cannot be imported here: it needs `jax`/`jaxlib`
-(`/root/reference/setup.py:15-16`), which are not installed and not installable
-(no network, no wheel).  The oracle is therefore pinned on the reference's own
+Parity status.  The reference needs `jax`/`jaxlib` (`/root/reference/setup.py:15-16`),
+which are not installed and not installable (no network, no wheel).  The oracle is pinned
+(a) on OUTPUTS OF THE REFERENCE ITSELF: its own, unmodified source executed under a NumPy
+stand-in for jax (`tests/golden/jaxshim/`, `tests/golden/make_reference_golden.py` and
+`make_reference_runs.py`) -- deterministic functions to fp64 round-off
+(`tests/test_reference_golden_cpu.py`), whole sampler runs through their statistics, SVGD
+exactly (`tests/test_reference_runs_cpu.py`) -- and (b) on the reference's own
 known-answer tests (leapfrog `mocat/src/tests/test_utils.py:137-163`, Gaussian
 kernel `tests/test_kernels.py:16-29`, `gaussian_potential` vs scipy
 `tests/test_utils.py:37-118`, `bisect` `:178-194`, `while_loop_stacked` `:166-175`,

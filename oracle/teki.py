@@ -10,9 +10,11 @@ Follows /root/reference/mocat/src/transport/teki.py:
   :113-150  update
   :153-185  AdaptiveTemperedEKI.next_temperature: regula falsi (utils.bisect) on
             log_ess(-(x - temperature) * pseudo_likelihood_potential) - log(n * ess_threshold)
-The reference has no test for this sampler ("parity unpinned" beyond the shared pieces: bisect and log_ess are pinned
-by tests/test_oracle_kats.py); the update is checked against its defining property instead -- on a linear-Gaussian
-simulator the tempered ensemble reproduces the conjugate posterior (tests/test_oracle_teki_cpu.py).
+The reference ships no test for this sampler.  Pinned on the reference's own source run under the NumPy stand-in for
+jax: calculate_covariances and the adaptive temperature to fp64 round-off (tests/test_reference_golden_cpu.py), whole
+runs on the g-and-k simulator through ladder and posterior moments (tests/test_reference_runs_cpu.py); and on the
+defining property of the update -- on a linear-Gaussian simulator the tempered ensemble reproduces the conjugate
+posterior (tests/test_oracle_teki_cpu.py).
 Randomness (convention of csrc/teki.cu): perturbation normals = philox.normals(seed, gid, step = iter, P_MOVE, d_y);
 simulator uniforms = philox.uniforms24(seed, gid, step = iter, P_SIM, m) (step 0 at startup); prior sample =
 philox.normals(seed, gid, 0, P_INIT, d_x).
